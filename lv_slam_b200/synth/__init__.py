@@ -1,0 +1,76 @@
+"""Synthetic inputs: Velodyne-like scans ray-cast by ``synth.c`` and sphere pose graphs.
+
+Input manufacture only — the same arrays feed the CUDA path, the oracle and the CPU baseline.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libsynth.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "synth.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["/usr/bin/gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.synth_scan.restype = ctypes.c_int
+        _lib.synth_scan.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_double, ctypes.c_void_p, ctypes.c_int]
+        _lib.synth_traj_pose.restype = None
+        _lib.synth_traj_pose.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    return _lib
+
+
+def scan(seed, frame, pose6, n_beams=64, n_az=2000, noise_sigma=0.02, nthreads=None):
+    """Ray-cast one scan from ``pose6 = (x, y, z, yaw, pitch, roll)``; returns float32 [n, 3] in the sensor frame."""
+    lib = _load()
+    pose = np.ascontiguousarray(pose6, dtype=np.float64)
+    out = np.empty((n_beams * n_az, 3), dtype=np.float32)
+    nthreads = nthreads or min(16, os.cpu_count() or 1)
+    n = lib.synth_scan(int(seed), int(frame), pose.ctypes.data, n_beams, n_az, float(noise_sigma), out.ctypes.data, nthreads)
+    return np.ascontiguousarray(out[:n])
+
+
+def traj_pose(frame):
+    lib = _load()
+    pose = np.zeros(6, dtype=np.float64)
+    lib.synth_traj_pose(int(frame), pose.ctypes.data)
+    return pose
+
+
+def pose_matrix(pose6):
+    """4x4 world<-sensor matrix of a pose6, R = Rz(yaw) Ry(pitch) Rx(roll)."""
+    x, y, z, yaw, pitch, roll = [float(v) for v in pose6]
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    T = np.eye(4)
+    T[:3, :3] = [[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                 [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                 [-sp, cp * sr, cp * cr]]
+    T[:3, 3] = [x, y, z]
+    return T
+
+
+def config1_pair(n_beams=64, n_az=2000, seed=42):
+    """BASELINE config 1 stand-in (no KITTI data here): target at identity, source displaced by
+    (1.20, 0.05, 0.01) m, yaw 1.0 deg, pitch 0.2 deg; the reference's first-frame guess x = 1.5 m
+    (src/lidar_odometry/scan_matching_odom_nodelet.cpp:199-200).  Returns (target, source, guess4x4, truth4x4)."""
+    p0 = np.zeros(6)
+    p1 = np.array([1.20, 0.05, 0.01, np.deg2rad(1.0), np.deg2rad(0.2), 0.0])
+    tgt = scan(seed, 0, p0, n_beams, n_az)
+    src = scan(seed, 1, p1, n_beams, n_az)
+    guess = np.eye(4, dtype=np.float32)
+    guess[0, 3] = 1.5
+    truth = np.linalg.inv(pose_matrix(p0)) @ pose_matrix(p1)
+    return tgt, src, guess, truth

@@ -1,0 +1,225 @@
+"""ctypes binding of oracle/libndt_oracle.so — the CHECKER.  Test infrastructure only.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never by
+the product package (lv_slam_b200/).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ODIR = os.path.join(_ROOT, "oracle")
+_SO = os.path.join(_ODIR, "libndt_oracle.so")
+
+KDTREE, DIRECT26, DIRECT7, DIRECT1 = 0, 1, 2, 3
+VAR_OMP, VAR_PCA = 0, 1
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _ODIR, "all"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = ctypes.CDLL(_SO)
+        vp, i32, f32, f64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
+        L.ondt_create.restype = vp; L.ondt_create.argtypes = [i32]
+        L.ondt_destroy.restype = None; L.ondt_destroy.argtypes = [vp]
+        L.ondt_set_params.restype = None; L.ondt_set_params.argtypes = [vp, f32, f64, f64, f64, i32, i32, i32]
+        L.ondt_set_target.restype = None; L.ondt_set_target.argtypes = [vp, vp, sz, sz]
+        L.ondt_set_source.restype = None; L.ondt_set_source.argtypes = [vp, vp, sz, sz]
+        L.ondt_get_grid.restype = None; L.ondt_get_grid.argtypes = [vp, vp, vp, vp]
+        L.ondt_get_gauss.restype = None; L.ondt_get_gauss.argtypes = [vp, vp]
+        L.ondt_num_leaves.restype = i32; L.ondt_num_leaves.argtypes = [vp]
+        L.ondt_get_leaves.restype = None; L.ondt_get_leaves.argtypes = [vp] * 12
+        L.ondt_lookup_keys.restype = None; L.ondt_lookup_keys.argtypes = [vp, vp, sz, sz, vp]
+        L.ondt_transform.restype = None; L.ondt_transform.argtypes = [vp, sz, sz, vp, vp]
+        L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
+        L.ondt_eval_hessian.restype = None; L.ondt_eval_hessian.argtypes = [vp, vp, vp, vp]
+        L.ondt_calculate_score.restype = f64; L.ondt_calculate_score.argtypes = [vp, vp]
+        L.ondt_align.restype = i32; L.ondt_align.argtypes = [vp, vp, vp, vp, vp]
+        L.ondt_trace_len.restype = i32; L.ondt_trace_len.argtypes = [vp]
+        L.ondt_get_trace.restype = None; L.ondt_get_trace.argtypes = [vp, vp]
+        L.ose3_exp_matrix4f.restype = None; L.ose3_exp_matrix4f.argtypes = [vp, vp]
+        L.ose3_exp.restype = None; L.ose3_exp.argtypes = [vp, vp, vp]
+        L.ose3_log_from_matrix4f.restype = None; L.ose3_log_from_matrix4f.argtypes = [vp, vp]
+        L.ose3_compose_log.restype = None; L.ose3_compose_log.argtypes = [vp, vp, vp]
+        L.olin_svd6_solve.restype = None; L.olin_svd6_solve.argtypes = [vp, vp, vp, vp]
+        L.olin_sym3_eig.restype = None; L.olin_sym3_eig.argtypes = [vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _colmajor16(T):
+    """4x4 (numpy row-major view) -> Eigen::Matrix4f memory order."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T.reshape(16))
+
+
+def _from_colmajor16(v):
+    return np.asarray(v, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+class OracleNDT:
+    """Mirror of the reference registration object's API, on the CPU restatement."""
+
+    def __init__(self, variant=VAR_OMP, resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.1, max_iter=35,
+                 search=DIRECT7, num_threads=1):
+        self.L = lib()
+        self.h = self.L.ondt_create(variant)
+        self.variant = variant
+        self.params = dict(resolution=resolution, step_size=step_size, outlier_ratio=outlier_ratio, trans_eps=trans_eps,
+                           max_iter=max_iter, search=search, num_threads=num_threads)
+        self._push()
+
+    def _push(self):
+        p = self.params
+        self.L.ondt_set_params(self.h, p["resolution"], p["step_size"], p["outlier_ratio"], p["trans_eps"], p["max_iter"],
+                               p["search"], p["num_threads"])
+
+    def set(self, **kw):
+        self.params.update(kw)
+        self._push()
+
+    def __del__(self):
+        try:
+            self.L.ondt_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_target(self, xyz):
+        a = _f32(xyz)
+        self.L.ondt_set_target(self.h, a.ctypes.data, a.shape[0], a.shape[1])
+
+    def set_source(self, xyz):
+        a = _f32(xyz)
+        self.n_src = a.shape[0]
+        self.L.ondt_set_source(self.h, a.ctypes.data, a.shape[0], a.shape[1])
+
+    def grid(self):
+        mn, mx, dv = (np.zeros(3, np.int32) for _ in range(3))
+        self.L.ondt_get_grid(self.h, mn.ctypes.data, mx.ctypes.data, dv.ctypes.data)
+        return mn, mx, dv
+
+    def gauss(self):
+        d = np.zeros(3)
+        self.L.ondt_get_gauss(self.h, d.ctypes.data)
+        return d
+
+    def leaves(self):
+        n = self.L.ondt_num_leaves(self.h)
+        out = dict(keys=np.zeros(n, np.int32), nr_points=np.zeros(n, np.int32), raw_points=np.zeros(n, np.int32),
+                   mean=np.zeros((n, 3)), cov=np.zeros((n, 3, 3)), icov=np.zeros((n, 3, 3)), evals=np.zeros((n, 3)),
+                   centroid=np.zeros((n, 3), np.float32), weight=np.zeros(n, np.int32), label=np.zeros(n, np.int32),
+                   in_cloud=np.zeros(n, np.int32))
+        order = ["keys", "nr_points", "raw_points", "mean", "cov", "icov", "evals", "centroid", "weight", "label", "in_cloud"]
+        self.L.ondt_get_leaves(self.h, *[out[k].ctypes.data for k in order])
+        return out
+
+    def lookup_keys(self, xyz):
+        a = _f32(xyz)
+        keys = np.zeros(a.shape[0], np.int32)
+        self.L.ondt_lookup_keys(self.h, a.ctypes.data, a.shape[0], a.shape[1], keys.ctypes.data)
+        return keys
+
+    def eval_derivatives(self, p6, T=None, compute_hessian=True):
+        p = np.ascontiguousarray(p6, dtype=np.float64)
+        g, H = np.zeros(6), np.zeros((6, 6))
+        Tm = _colmajor16(T) if T is not None else None
+        s = self.L.ondt_eval_derivatives(self.h, p.ctypes.data, Tm.ctypes.data if Tm is not None else None,
+                                         int(compute_hessian), g.ctypes.data, H.ctypes.data)
+        return s, g, H
+
+    def eval_hessian(self, p6, T=None):
+        p = np.ascontiguousarray(p6, dtype=np.float64)
+        H = np.zeros((6, 6))
+        Tm = _colmajor16(T) if T is not None else None
+        self.L.ondt_eval_hessian(self.h, p.ctypes.data, Tm.ctypes.data if Tm is not None else None, H.ctypes.data)
+        return H
+
+    def calculate_score(self, T):
+        Tm = _colmajor16(T)
+        return self.L.ondt_calculate_score(self.h, Tm.ctypes.data)
+
+    def align(self, guess=None, want_cloud=False):
+        g = _colmajor16(np.eye(4) if guess is None else guess)
+        fin = np.zeros(16, np.float32)
+        stats = np.zeros(4)
+        cloud = np.zeros((self.n_src, 3), np.float32) if want_cloud else None
+        it = self.L.ondt_align(self.h, g.ctypes.data, fin.ctypes.data, stats.ctypes.data,
+                               cloud.ctypes.data if want_cloud else None)
+        res = dict(final=_from_colmajor16(fin), iterations=it, converged=bool(stats[0]), trans_probability=stats[1],
+                   n_eval=int(stats[2]), n_hess=int(stats[3]), trace=self.trace())
+        if want_cloud:
+            res["cloud"] = cloud
+        return res
+
+    def trace(self):
+        n = self.L.ondt_trace_len(self.h)
+        t = np.zeros((n, 22))
+        if n:
+            self.L.ondt_get_trace(self.h, t.ctypes.data)
+        return t
+
+
+def transform(xyz, T):
+    a = _f32(xyz)
+    out = np.zeros((a.shape[0], 3), np.float32)
+    Tm = _colmajor16(T)
+    lib().ondt_transform(a.ctypes.data, a.shape[0], a.shape[1], Tm.ctypes.data, out.ctypes.data)
+    return out
+
+
+def se3_exp_matrix4f(p6):
+    p = np.ascontiguousarray(p6, dtype=np.float64)
+    M = np.zeros(16, np.float32)
+    lib().ose3_exp_matrix4f(p.ctypes.data, M.ctypes.data)
+    return _from_colmajor16(M)
+
+
+def se3_exp(p6):
+    p = np.ascontiguousarray(p6, dtype=np.float64)
+    q, t = np.zeros(4), np.zeros(3)
+    lib().ose3_exp(p.ctypes.data, q.ctypes.data, t.ctypes.data)
+    return q, t
+
+
+def se3_log_from_matrix4f(T):
+    M = _colmajor16(T)
+    p = np.zeros(6)
+    lib().ose3_log_from_matrix4f(M.ctypes.data, p.ctypes.data)
+    return p
+
+
+def se3_compose_log(delta6, p6):
+    d = np.ascontiguousarray(delta6, dtype=np.float64)
+    p = np.ascontiguousarray(p6, dtype=np.float64)
+    o = np.zeros(6)
+    lib().ose3_compose_log(d.ctypes.data, p.ctypes.data, o.ctypes.data)
+    return o
+
+
+def svd6_solve(A, b):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x, sv = np.zeros(6), np.zeros(6)
+    lib().olin_svd6_solve(A.ctypes.data, b.ctypes.data, x.ctypes.data, sv.ctypes.data)
+    return x, sv
+
+
+def sym3_eig(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    ev, V = np.zeros(3), np.zeros((3, 3))
+    lib().olin_sym3_eig(A.ctypes.data, ev.ctypes.data, V.ctypes.data)
+    return ev, V
