@@ -1,0 +1,164 @@
+/* lvslam_b200 — C-ABI of the B200-native NDT scan-matching and pose-graph hot path.
+ *
+ * Drop-in boundary for BurryChen/lv_slam (reference paths relative to the reference tree):
+ *   - the NDT entry points replace the bodies behind pcl::Registration::align() for
+ *     pclomp::NormalDistributionsTransform  (include/ndt_omp/ndt_omp.h:69-551, computeTransformation at :256-267)
+ *     pclpca::NormalDistributionsTransform  (include/ndt_pca/ndt_pca.h, same layout)
+ *   - the pose-graph entry points replace lv_slam::GraphSLAM::optimize()
+ *     (include/global_graph/graph_slam.hpp:40-149, src/global_graph/graph_slam.cpp:298-331).
+ * INTEGRATION.md shows the C++ shim a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an lvs_status (0 = ok, < 0 = error);
+ * no exceptions cross the boundary; 4x4 matrices are COLUMN-major float[16] (Eigen::Matrix4f memory order);
+ * a handle is single-owner and not re-entrant, several handles may be used concurrently from different
+ * host threads (the two reference nodelets do exactly that).  There is no CPU fallback: every entry point
+ * fails with LVS_ERR_CUDA / LVS_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef LVSLAM_B200_H_
+#define LVSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef enum {
+  LVS_OK = 0,
+  LVS_ERR_INVALID_ARG = -1,
+  LVS_ERR_NO_DEVICE = -2,
+  LVS_ERR_CUDA = -3,
+  LVS_ERR_OOM = -4,
+  LVS_ERR_NO_TARGET = -5,     /* align()/eval before setInputTarget */
+  LVS_ERR_NO_SOURCE = -6,     /* align()/eval before setInputSource */
+  LVS_ERR_GRID_OVERFLOW = -7, /* dx*dy*dz > INT32_MAX: the reference warns and yields an empty grid
+                                 (include/ndt_omp/voxel_grid_covariance_omp_impl.hpp:76-85) */
+  LVS_ERR_BAD_SLOT = -8,
+  LVS_ERR_NOT_SPD = -9,       /* pose graph: Cholesky failure (g2o LinearSolver returns false) */
+  LVS_ERR_EMPTY_GRAPH = -10   /* GraphSLAM::optimize returns -1 when the graph has no edge */
+} lvs_status;
+
+/* pclomp::NeighborSearchMethod, include/ndt_omp/ndt_omp.h:61 (same values in pclpca) */
+typedef enum { LVS_KDTREE = 0, LVS_DIRECT26 = 1, LVS_DIRECT7 = 2, LVS_DIRECT1 = 3 } lvs_search_method;
+/* which of the two registration classes is mirrored */
+typedef enum { LVS_NDT_OMP = 0, LVS_NDT_PCA = 1 } lvs_ndt_variant;
+
+/* Parameters = the setters of the reference class; defaults = its constructor
+ * (include/ndt_omp/ndt_omp_impl2.hpp:54-83). */
+typedef struct {
+  float resolution;            /* setResolution            (1.0)  */
+  double step_size;            /* setStepSize              (0.1)  */
+  double outlier_ratio;        /* setOulierRatio [sic]     (0.55) */
+  double transformation_epsilon; /* setTransformationEpsilon (0.1) */
+  int32_t max_iterations;      /* setMaximumIterations     (35)   */
+  int32_t search_method;       /* setNeighborhoodSearchMethod (LVS_DIRECT7) */
+  int32_t variant;             /* LVS_NDT_OMP | LVS_NDT_PCA */
+  int32_t min_points_per_voxel;  /* VoxelGridCovariance default 6 (voxel_grid_covariance_omp.h:204) */
+  double min_covar_eigvalue_mult; /* 0.01 (voxel_grid_covariance_omp.h:205) */
+} lvs_ndt_params;
+
+/* What the reference object exposes after align(): getFinalTransformation, hasConverged,
+ * getFinalNumIteration, getTransformationProbability, plus evaluation counters. */
+typedef struct {
+  float final_transformation[16];
+  int32_t converged;
+  int32_t iterations;
+  double trans_probability;
+  int32_t n_eval;   /* computeDerivatives calls */
+  int32_t n_hess;   /* computeHessian calls */
+  double score;
+} lvs_ndt_result;
+
+/* One record per Newton iteration (parity tap): parameter vector before the step, unit direction,
+ * accepted step length, score after the step, parameter vector after composition, line-search trials,
+ * whether computeHessian ran. */
+typedef struct {
+  double p_before[6], dir[6], step, score, p_after[6];
+  int32_t trials, hessian_recomputed;
+} lvs_ndt_trace_rec;
+
+typedef struct lvs_ndt lvs_ndt_t;
+
+void lvs_ndt_default_params(lvs_ndt_params* p);
+const char* lvs_status_string(int status);
+const char* lvs_last_error(void);        /* thread-local detail string of the last failure */
+int lvs_device_count(void);
+
+/* One registration object (replaces pclomp::/pclpca:: NormalDistributionsTransform).  `stream` is a
+ * cudaStream_t (NULL = the handle creates its own); all device work of the handle is ordered on it. */
+int lvs_ndt_create(const lvs_ndt_params* params, int device, void* stream, lvs_ndt_t** out);
+int lvs_ndt_destroy(lvs_ndt_t* h);
+int lvs_ndt_set_params(lvs_ndt_t* h, const lvs_ndt_params* params);  /* re-voxelises if resolution changed (ndt_omp.h:126-136) */
+int lvs_ndt_get_params(const lvs_ndt_t* h, lvs_ndt_params* out);
+
+/* setInputTarget (ndt_omp.h:116-121 -> init() :283-289 -> VoxelGridCovariance::filter(true)).
+ * xyz points to the first x; consecutive points are stride_bytes apart (32 for pcl::PointXYZI, 12 packed).
+ * on_device != 0: xyz is a device pointer on the handle's device (inputs already resident in HBM). */
+int lvs_ndt_set_target(lvs_ndt_t* h, const float* xyz, size_t n, size_t stride_bytes, int on_device);
+/* setInputSource */
+int lvs_ndt_set_source(lvs_ndt_t* h, const float* xyz, size_t n, size_t stride_bytes, int on_device);
+
+/* align(output, guess): runs computeTransformation (ndt_omp_impl2.hpp:88-188) on the device. */
+int lvs_ndt_align(lvs_ndt_t* h, const float guess[16], lvs_ndt_result* out);
+/* The `output` cloud of align(): final_transformation * source, packed xyz float, n_source points. */
+int lvs_ndt_get_aligned_cloud(lvs_ndt_t* h, float* xyz_out, int on_device);
+/* Per-iteration trace of the last align (at most max_iterations + 2 records). */
+int lvs_ndt_get_trace(lvs_ndt_t* h, lvs_ndt_trace_rec* recs, int capacity, int* n_out);
+
+/* Parity taps.
+ * eval_derivatives = one computeDerivatives call (ndt_omp_impl2.hpp:197-305): transformed cloud =
+ * T16 * source (T16 NULL: float(SE3::exp(p))), point Jacobians from p.  H36 row-major, full 6x6. */
+int lvs_ndt_eval_derivatives(lvs_ndt_t* h, const double p[6], const float* T16, int compute_hessian,
+                             double* score, double g[6], double H36[36]);
+/* computeHessian (ndt_omp_impl2.hpp:623-679): all-double, radius-search neighbours, unweighted. */
+int lvs_ndt_eval_hessian(lvs_ndt_t* h, const double p[6], const float* T16, double H36[36]);
+/* calculateScore (ndt_omp_impl2.hpp:1007-1040) of T16 * source. */
+int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score);
+
+/* Voxel grid taps.  grid: min_b, max_b, div_b (voxel_grid_covariance_omp_impl.hpp:87-103). */
+int lvs_ndt_get_grid(lvs_ndt_t* h, int32_t min_b[3], int32_t max_b[3], int32_t div_b[3]);
+int lvs_ndt_num_cells(lvs_ndt_t* h, int* n_cells);   /* every occupied cell, i.e. leaves_.size() */
+/* All occupied cells in ascending key order; any pointer may be NULL.  nr_points is the raw count
+ * (-1 where the reference invalidates the leaf); mean/cov/icov/evals are zero for cells below
+ * min_points_per_voxel except mean, exactly like the reference's Leaf. */
+int lvs_ndt_get_cells(lvs_ndt_t* h, int32_t* keys, int32_t* nr_points, double* mean3, double* icov9,
+                      double* evals3, float* centroid3, int32_t* weight);
+/* Voxel key the lookup path computes for T16 * source point i, -1 outside the bounding box
+ * (voxel_grid_covariance_omp_impl.hpp:379-394). */
+int lvs_ndt_lookup_keys(lvs_ndt_t* h, const float T16[16], int32_t* keys_out);
+
+/* ---- batched registration: many (source, target, guess) pairs advanced together on one device ----
+ * Targets and sources live in slots; a pair names one of each.  This is the throughput path used for
+ * loop-closure candidates (include/global_graph/loop_detector.hpp:238-263) and stream replay. */
+typedef struct lvs_ndt_batch lvs_ndt_batch_t;
+int lvs_ndt_batch_create(const lvs_ndt_params* params, int device, void* stream, int n_target_slots,
+                         int n_source_slots, lvs_ndt_batch_t** out);
+int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b);
+int lvs_ndt_batch_set_target(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device);
+int lvs_ndt_batch_set_source(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device);
+int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot,
+                        const float* guesses16 /* n_pairs x 16 */, lvs_ndt_result* results /* n_pairs */);
+/* Device time in ms of the last batch_align and the number of kernel launches it issued. */
+int lvs_ndt_batch_last_stats(lvs_ndt_batch_t* b, double* device_ms, int* launches, double* deriv_kernel_ms, int* deriv_launches);
+/* Measurement controls.  profiling != 0 brackets every evaluation launch with a CUDA event pair so that
+ * last_stats can report the summed duration of the launches that did work (deriv_kernel_ms over deriv_launches). */
+int lvs_ndt_batch_set_profiling(lvs_ndt_batch_t* b, int on);
+/* blocks_per_pair (0 = automatic), evaluation launches queued before the first / each later completion check. */
+int lvs_ndt_batch_set_tuning(lvs_ndt_batch_t* b, int blocks_per_pair, int chunk_first, int chunk_next);
+/* Kernel launches issued by this object since creation (voxelisation, evaluation, packing). */
+int lvs_ndt_batch_total_launches(lvs_ndt_batch_t* b, long long* launches);
+int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int target_slot, int* n_cells, int* n_valid);
+/* The batch object that backs a single registration handle (1 target slot, 1 source slot). */
+int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVSLAM_B200_H_ */

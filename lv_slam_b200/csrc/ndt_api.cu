@@ -1,0 +1,725 @@
+// C-ABI of the NDT path (include/lvslam_b200.h).  Host-side plumbing only: every number the reference's
+// computeTransformation produces is computed by the kernels in ndt_voxel.cu / ndt_eval.cu and the device-resident
+// state machine in ndt_state.cuh.  No CPU fallback: without a usable sm_100 device every entry point fails.
+#include <cmath>
+#include <cstdarg>
+#include <new>
+#include "ndt_internal.cuh"
+#include "ndt_state.cuh"
+
+namespace lvs {
+
+static thread_local char g_err[512] = "";
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  (void)cudaGetLastError();
+  int st = (e == cudaErrorMemoryAllocation) ? LVS_ERR_OOM
+           : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? LVS_ERR_NO_DEVICE
+                                                                                                          : LVS_ERR_CUDA;
+  return fail(st, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+}
+
+static AlignConsts make_consts(const lvs_ndt_params& p) {
+  AlignConsts c;
+  // gauss constants, eq. 6.8 [Magnusson 2009] as in ndt_omp_impl2.hpp:93-100
+  double c1 = 10 * (1 - p.outlier_ratio);
+  double c2 = p.outlier_ratio / std::pow((double)p.resolution, 3);
+  c.gauss_d3 = -std::log(c2);
+  c.gauss_d1 = -std::log(c1 + c2) - c.gauss_d3;
+  c.gauss_d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - c.gauss_d3) / c.gauss_d1);
+  c.step_size = p.step_size;
+  c.trans_eps = p.transformation_epsilon;
+  c.max_iter = p.max_iterations;
+  c.search = p.search_method;
+  c.variant = p.variant;
+  c.resolution = p.resolution;
+  return c;
+}
+
+static int check_params(const lvs_ndt_params* p) {
+  if (!p) return fail(LVS_ERR_INVALID_ARG, "params is NULL");
+  if (!(p->resolution > 0.0f)) return fail(LVS_ERR_INVALID_ARG, "resolution must be > 0");
+  if (p->search_method < LVS_KDTREE || p->search_method > LVS_DIRECT1) return fail(LVS_ERR_INVALID_ARG, "unknown search_method %d", p->search_method);
+  if (p->variant != LVS_NDT_OMP && p->variant != LVS_NDT_PCA) return fail(LVS_ERR_INVALID_ARG, "unknown variant %d", p->variant);
+  if (p->max_iterations < 0 || p->max_iterations > kMaxTrace - 4) return fail(LVS_ERR_INVALID_ARG, "max_iterations must be in [0, %d]", kMaxTrace - 4);
+  if (p->min_points_per_voxel < 1) return fail(LVS_ERR_INVALID_ARG, "min_points_per_voxel must be >= 1");
+  return LVS_OK;
+}
+
+struct CloudSlot {
+  float4* d_pts = nullptr;
+  size_t cap = 0;
+  int n = 0;
+  bool set = false;
+};
+
+constexpr int kMaxEvents = 2048;
+
+}  // namespace lvs
+
+using namespace lvs;
+
+struct lvs_ndt_batch {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  bool own_stream = false;
+  lvs_ndt_params prm{};
+  BuildScratch ws;
+  std::vector<TargetGrid> targets;
+  std::vector<CloudSlot> target_pts, sources;
+  // upload staging
+  float* d_stage = nullptr;
+  size_t stage_cap = 0;
+  // pair state
+  int pair_cap = 0, bpp_cap = 0;
+  PairDesc *d_pairs = nullptr, *h_pairs = nullptr;
+  AlignState *d_states = nullptr, *h_states = nullptr;
+  TraceRec *d_trace = nullptr;
+  double* d_partials = nullptr;
+  unsigned int* d_tickets = nullptr;
+  int *d_done = nullptr, *h_done = nullptr;
+  float* d_T16 = nullptr;        // scratch 16 floats
+  double *d_scalar = nullptr, *h_scalar = nullptr;
+  int trace_on = 0;
+  int last_n_pairs = 0;
+  // stats
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  int profiling = 0;
+  double last_device_ms = 0, last_deriv_ms = 0;
+  int last_launches = 0, last_deriv_launches = 0;
+  long total_launches = 0;
+  int blocks_per_pair_override = 0;
+  int chunk_first = 6, chunk_next = 4;
+};
+
+namespace lvs {
+
+static int set_device(lvs_ndt_batch* b) {
+  CUDA_TRY(cudaSetDevice(b->device));
+  return LVS_OK;
+}
+
+static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  if (n > 0 && !xyz) return fail(LVS_ERR_INVALID_ARG, "xyz is NULL");
+  if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(LVS_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
+  if (n > (size_t)0x7fffff00) return fail(LVS_ERR_INVALID_ARG, "too many points");
+  if (n > slot.cap) {
+    if (slot.d_pts) cudaFree(slot.d_pts);
+    slot.d_pts = nullptr; slot.cap = 0;
+    size_t cap = n + n / 8 + 256;
+    CUDA_TRY(cudaMalloc(&slot.d_pts, cap * sizeof(float4)));
+    slot.cap = cap;
+  }
+  slot.n = (int)n;
+  slot.set = true;
+  if (n == 0) return LVS_OK;
+  const float* d_in = xyz;
+  if (!on_device) {
+    size_t bytes = (n - 1) * stride_bytes + 12;
+    if (bytes > b->stage_cap) {
+      if (b->d_stage) cudaFree(b->d_stage);
+      b->d_stage = nullptr; b->stage_cap = 0;
+      size_t cap = bytes + bytes / 8 + 4096;
+      CUDA_TRY(cudaMalloc(&b->d_stage, cap));
+      b->stage_cap = cap;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_stage, xyz, bytes, cudaMemcpyHostToDevice, b->st));
+    d_in = b->d_stage;
+  }
+  int rc = pack_points(b->st, d_in, stride_bytes / 4, (int)n, slot.d_pts);
+  b->total_launches++;
+  return rc;
+}
+
+static int reserve_pairs(lvs_ndt_batch* b, int n_pairs, int bpp) {
+  if (n_pairs > b->pair_cap) {
+    if (b->d_pairs) cudaFree(b->d_pairs);
+    if (b->d_states) cudaFree(b->d_states);
+    if (b->d_trace) cudaFree(b->d_trace);
+    if (b->d_tickets) cudaFree(b->d_tickets);
+    if (b->h_pairs) cudaFreeHost(b->h_pairs);
+    if (b->h_states) cudaFreeHost(b->h_states);
+    b->d_pairs = nullptr; b->d_states = nullptr; b->d_trace = nullptr; b->d_tickets = nullptr; b->h_pairs = nullptr; b->h_states = nullptr;
+    b->pair_cap = 0;
+    int cap = n_pairs + n_pairs / 4 + 4;
+    CUDA_TRY(cudaMalloc(&b->d_pairs, cap * sizeof(PairDesc)));
+    CUDA_TRY(cudaMalloc(&b->d_states, cap * sizeof(AlignState)));
+    if (b->trace_on) CUDA_TRY(cudaMalloc(&b->d_trace, (size_t)cap * kMaxTrace * sizeof(TraceRec)));
+    CUDA_TRY(cudaMalloc(&b->d_tickets, cap * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(b->d_tickets, 0, cap * sizeof(unsigned int), b->st));
+    CUDA_TRY(cudaMallocHost(&b->h_pairs, cap * sizeof(PairDesc)));
+    CUDA_TRY(cudaMallocHost(&b->h_states, cap * sizeof(AlignState)));
+    b->pair_cap = cap;
+    b->bpp_cap = 0;
+  }
+  if ((size_t)b->pair_cap * bpp > (size_t)b->bpp_cap) {
+    if (b->d_partials) cudaFree(b->d_partials);
+    b->d_partials = nullptr;
+    CUDA_TRY(cudaMalloc(&b->d_partials, (size_t)b->pair_cap * bpp * kAcc * sizeof(double)));
+    b->bpp_cap = b->pair_cap * bpp;
+  }
+  return LVS_OK;
+}
+
+static PairDesc make_pair(lvs_ndt_batch* b, int src_slot, int tgt_slot) {
+  PairDesc P;
+  const TargetGrid& tg = b->targets[tgt_slot];
+  P.src = b->sources[src_slot].d_pts;
+  P.n_src = b->sources[src_slot].n;
+  P.grid = tg.d_grid;
+  P.recs = tg.d_recs;
+  P.centroids = tg.d_centroids;
+  P.icov64 = tg.d_icov64;
+  P.gp = tg.d_gp;
+  return P;
+}
+
+static int choose_bpp(lvs_ndt_batch* b, int n_pairs, int max_src) {
+  if (b->blocks_per_pair_override > 0) return b->blocks_per_pair_override;
+  int by_points = std::max(1, (max_src + 255) / 256);                          // one point per thread
+  int resident = 148 * eval_max_resident_ctas_per_sm();                        // one full wave of CTAs
+  int by_machine = std::max(1, (resident + n_pairs - 1) / n_pairs);
+  return std::max(1, std::min(by_points, std::max(by_machine, 4)));
+}
+
+// Runs the evaluation launches of one batch until every pair's state machine reports done.
+static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, const int32_t* tgt_slot, const float* guesses16, lvs_ndt_result* results) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (n_pairs <= 0) return LVS_OK;
+  int max_src = 0;
+  for (int i = 0; i < n_pairs; i++) {
+    int s = src_slot[i], t = tgt_slot[i];
+    if (s < 0 || s >= (int)b->sources.size() || t < 0 || t >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "pair %d: slot out of range", i);
+    if (!b->target_pts[t].set) return fail(LVS_ERR_NO_TARGET, "pair %d: target slot %d has no cloud (setInputTarget not called)", i, t);
+    if (!b->sources[s].set) return fail(LVS_ERR_NO_SOURCE, "pair %d: source slot %d has no cloud (setInputSource not called)", i, s);
+    max_src = std::max(max_src, b->sources[s].n);
+  }
+  const int bpp = choose_bpp(b, n_pairs, max_src);
+  if ((rc = reserve_pairs(b, n_pairs, bpp))) return rc;
+  for (int i = 0; i < n_pairs; i++) {
+    b->h_pairs[i] = make_pair(b, src_slot[i], tgt_slot[i]);
+    align_state_init(b->h_states[i], guesses16 + 16 * i, b->trace_on);
+  }
+  CUDA_TRY(cudaEventRecord(b->ev_begin, b->st));
+  CUDA_TRY(cudaMemcpyAsync(b->d_pairs, b->h_pairs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, b->st));
+  CUDA_TRY(cudaMemcpyAsync(b->d_states, b->h_states, n_pairs * sizeof(AlignState), cudaMemcpyHostToDevice, b->st));
+  CUDA_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int), b->st));
+  EvalLaunch L;
+  L.d_pairs = b->d_pairs; L.d_states = b->d_states; L.d_trace = b->trace_on ? b->d_trace : nullptr;
+  L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
+  L.n_pairs = n_pairs; L.blocks_per_pair = bpp; L.advance = 1;
+  L.consts = make_consts(b->prm);
+  // worst case: initial pass + (max_iter + 2) outer iterations of (first + 10 trials + Hessian pass)
+  const int max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
+  int launches = 0;
+  *b->h_done = 0;
+  const bool prof = b->profiling != 0;
+  if (prof && (int)b->ev_pool.size() < 2 * kMaxEvents) {
+    size_t old = b->ev_pool.size();
+    b->ev_pool.resize(2 * kMaxEvents);
+    for (size_t k = old; k < b->ev_pool.size(); k++) CUDA_TRY(cudaEventCreate(&b->ev_pool[k]));
+  }
+  // The radius-search passes are only reachable in KDTREE mode or when the reference's More-Thuente loop can run, i.e.
+  // when `interval_converged = (step_max - step_min) > 0` (ndt_omp_impl2.hpp:888) is false.
+  const bool need_cold = b->prm.search_method == LVS_KDTREE || !((b->prm.step_size - b->prm.transformation_epsilon / 2) > 0);
+  int chunk = b->chunk_first;
+  while (launches < max_launches) {
+    for (int k = 0; k < chunk && launches < max_launches; k++) {
+      const bool ev = prof && launches < kMaxEvents;
+      if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * launches], b->st));
+      if ((rc = launch_eval(b->st, L))) return rc;
+      if (need_cold && (rc = launch_eval_cold(b->st, L))) return rc;
+      if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * launches + 1], b->st));
+      launches++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
+    CUDA_TRY(cudaStreamSynchronize(b->st));
+    if (*b->h_done >= n_pairs) break;
+    chunk = b->chunk_next;
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, n_pairs * sizeof(AlignState), cudaMemcpyDeviceToHost, b->st));
+  CUDA_TRY(cudaEventRecord(b->ev_end, b->st));
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  if (*b->h_done < n_pairs) return fail(LVS_ERR_CUDA, "align state machine did not finish within %d evaluation launches", max_launches);
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, b->ev_begin, b->ev_end));
+  b->last_device_ms = ms;
+  b->last_launches = launches;
+  b->total_launches += launches * (need_cold ? 2 : 1);
+  b->last_n_pairs = n_pairs;
+  int active = 0;
+  for (int i = 0; i < n_pairs; i++) {
+    const AlignState& s = b->h_states[i];
+    active = std::max(active, s.n_eval + s.n_hess);
+    if (results) {
+      lvs_ndt_result& r = results[i];
+      memcpy(r.final_transformation, s.final_T, sizeof r.final_transformation);
+      r.converged = s.converged;
+      r.iterations = s.nr_iterations;
+      r.trans_probability = s.trans_probability;
+      r.n_eval = s.n_eval;
+      r.n_hess = s.n_hess;
+      r.score = s.score;
+    }
+  }
+  b->last_deriv_launches = active;
+  b->last_deriv_ms = 0;
+  if (prof) {
+    double sum = 0;
+    for (int k = 0; k < std::min(active, kMaxEvents); k++) {
+      float t = 0;
+      CUDA_TRY(cudaEventElapsedTime(&t, b->ev_pool[2 * k], b->ev_pool[2 * k + 1]));
+      sum += t;
+    }
+    b->last_deriv_ms = sum;
+  }
+  return LVS_OK;
+}
+
+// Tap: one evaluation of pair 0 = (source 0, target 0) with an explicit state.
+static int run_tap(lvs_ndt_batch* b, int kind, const double p[6], const float* T16, double* score, double* g, double* H36) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
+  if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  const int bpp = choose_bpp(b, 1, b->sources[0].n);
+  if ((rc = reserve_pairs(b, 1, bpp))) return rc;
+  b->h_pairs[0] = make_pair(b, 0, 0);
+  AlignState& s = b->h_states[0];
+  const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  align_state_init(s, I4, 0);
+  state_set_eval_point(s, p);            // T = float(SE3::exp(p)), R from p
+  if (T16) memcpy(s.T, T16, sizeof s.T);  // explicit transformed cloud
+  s.eval_kind = kind;
+  CUDA_TRY(cudaMemcpyAsync(b->d_pairs, b->h_pairs, sizeof(PairDesc), cudaMemcpyHostToDevice, b->st));
+  CUDA_TRY(cudaMemcpyAsync(b->d_states, b->h_states, sizeof(AlignState), cudaMemcpyHostToDevice, b->st));
+  EvalLaunch L;
+  L.d_pairs = b->d_pairs; L.d_states = b->d_states; L.d_trace = nullptr;
+  L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
+  L.n_pairs = 1; L.blocks_per_pair = bpp; L.advance = 0;
+  L.consts = make_consts(b->prm);
+  if (kind == EVAL_HESS27 || b->prm.search_method == LVS_KDTREE) rc = launch_eval_cold(b->st, L);
+  else rc = launch_eval(b->st, L);
+  if (rc) return rc;
+  b->total_launches++;
+  CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, sizeof(AlignState), cudaMemcpyDeviceToHost, b->st));
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  if (score) *score = s.score;
+  if (g) memcpy(g, s.g, sizeof s.g);
+  if (H36) memcpy(H36, s.H, sizeof s.H);
+  return LVS_OK;
+}
+
+static int batch_create(const lvs_ndt_params* params, int device, void* stream, int n_t, int n_s, int trace_on, lvs_ndt_batch** out) {
+  if (!out) return fail(LVS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  lvs_ndt_params p;
+  if (params) p = *params; else lvs_ndt_default_params(&p);
+  int rc = check_params(&p);
+  if (rc) return rc;
+  if (n_t < 1 || n_s < 1) return fail(LVS_ERR_INVALID_ARG, "slot counts must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { (void)cudaGetLastError(); return fail(LVS_ERR_NO_DEVICE, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)); }
+  if (device < 0 || device >= ndev) return fail(LVS_ERR_NO_DEVICE, "device %d out of range (have %d)", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(LVS_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(device));
+  lvs_ndt_batch* b = new (std::nothrow) lvs_ndt_batch();
+  if (!b) return fail(LVS_ERR_OOM, "host allocation failed");
+  b->device = device;
+  b->prm = p;
+  b->trace_on = trace_on;
+  b->targets.resize(n_t); b->target_pts.resize(n_t); b->sources.resize(n_s);
+  auto bail = [&](int st) { lvs_ndt_batch_destroy(b); return st; };
+  if (stream) b->st = (cudaStream_t)stream;
+  else {
+    e = cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    b->own_stream = true;
+  }
+  if ((e = cudaMalloc(&b->d_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
+  if ((e = cudaMallocHost(&b->h_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
+  if ((e = cudaMalloc(&b->d_T16, 16 * sizeof(float))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
+  if ((e = cudaMalloc(&b->d_scalar, 8 * sizeof(double))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
+  if ((e = cudaMallocHost(&b->h_scalar, 8 * sizeof(double))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
+  if ((e = cudaEventCreate(&b->ev_begin)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+  if ((e = cudaEventCreate(&b->ev_end)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+  *out = b;
+  return LVS_OK;
+}
+
+static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
+  if ((rc = upload_cloud(b, b->target_pts[slot], xyz, n, stride_bytes, on_device))) return rc;
+  rc = b->targets[slot].build(b->st, b->target_pts[slot].d_pts, (int)n, b->prm, b->ws);
+  b->total_launches += b->targets[slot].launches_last_build;
+  return rc;
+}
+
+static int set_source(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (slot < 0 || slot >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slot);
+  return upload_cloud(b, b->sources[slot], xyz, n, stride_bytes, on_device);
+}
+
+}  // namespace lvs
+
+struct lvs_ndt {
+  lvs_ndt_batch* b = nullptr;
+};
+
+extern "C" {
+
+void lvs_ndt_default_params(lvs_ndt_params* p) {
+  if (!p) return;
+  p->resolution = 1.0f;            // ndt_omp_impl2.hpp:54-83
+  p->step_size = 0.1;
+  p->outlier_ratio = 0.55;
+  p->transformation_epsilon = 0.1;
+  p->max_iterations = 35;
+  p->search_method = LVS_DIRECT7;
+  p->variant = LVS_NDT_OMP;
+  p->min_points_per_voxel = 6;
+  p->min_covar_eigvalue_mult = 0.01;
+}
+
+const char* lvs_status_string(int status) {
+  switch (status) {
+    case LVS_OK: return "ok";
+    case LVS_ERR_INVALID_ARG: return "invalid argument";
+    case LVS_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case LVS_ERR_CUDA: return "CUDA error";
+    case LVS_ERR_OOM: return "out of memory";
+    case LVS_ERR_NO_TARGET: return "no target cloud";
+    case LVS_ERR_NO_SOURCE: return "no source cloud";
+    case LVS_ERR_GRID_OVERFLOW: return "voxel grid index overflow";
+    case LVS_ERR_BAD_SLOT: return "bad slot";
+    case LVS_ERR_NOT_SPD: return "matrix not positive definite";
+    case LVS_ERR_EMPTY_GRAPH: return "empty graph";
+    default: return "unknown status";
+  }
+}
+
+const char* lvs_last_error(void) { return g_err; }
+
+int lvs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---- batch object
+int lvs_ndt_batch_create(const lvs_ndt_params* params, int device, void* stream, int n_target_slots, int n_source_slots, lvs_ndt_batch_t** out) {
+  return batch_create(params, device, stream, n_target_slots, n_source_slots, 0, out);
+}
+
+int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
+  if (!b) return LVS_OK;
+  cudaSetDevice(b->device);
+  if (b->st) cudaStreamSynchronize(b->st);
+  for (auto& t : b->targets) t.release();
+  for (auto& c : b->target_pts) if (c.d_pts) cudaFree(c.d_pts);
+  for (auto& c : b->sources) if (c.d_pts) cudaFree(c.d_pts);
+  b->ws.release();
+  if (b->ws.h_gp) cudaFreeHost(b->ws.h_gp);
+  if (b->d_stage) cudaFree(b->d_stage);
+  if (b->d_pairs) cudaFree(b->d_pairs);
+  if (b->d_states) cudaFree(b->d_states);
+  if (b->d_trace) cudaFree(b->d_trace);
+  if (b->d_partials) cudaFree(b->d_partials);
+  if (b->d_tickets) cudaFree(b->d_tickets);
+  if (b->d_done) cudaFree(b->d_done);
+  if (b->d_T16) cudaFree(b->d_T16);
+  if (b->d_scalar) cudaFree(b->d_scalar);
+  if (b->h_pairs) cudaFreeHost(b->h_pairs);
+  if (b->h_states) cudaFreeHost(b->h_states);
+  if (b->h_done) cudaFreeHost(b->h_done);
+  if (b->h_scalar) cudaFreeHost(b->h_scalar);
+  if (b->ev_begin) cudaEventDestroy(b->ev_begin);
+  if (b->ev_end) cudaEventDestroy(b->ev_end);
+  for (auto e : b->ev_pool) cudaEventDestroy(e);
+  if (b->own_stream && b->st) cudaStreamDestroy(b->st);
+  (void)cudaGetLastError();
+  delete b;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_set_target(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  return set_target(b, slot, xyz, n, stride_bytes, on_device);
+}
+
+int lvs_ndt_batch_set_source(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  return set_source(b, slot, xyz, n, stride_bytes, on_device);
+}
+
+int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot, const float* guesses16,
+                        lvs_ndt_result* results) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (n_pairs < 0 || (n_pairs > 0 && (!source_slot || !target_slot || !guesses16 || !results))) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  return run_align(b, n_pairs, source_slot, target_slot, guesses16, results);
+}
+
+int lvs_ndt_batch_last_stats(lvs_ndt_batch_t* b, double* device_ms, int* launches, double* deriv_kernel_ms, int* deriv_launches) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (device_ms) *device_ms = b->last_device_ms;
+  if (launches) *launches = b->last_launches;
+  if (deriv_kernel_ms) *deriv_kernel_ms = b->last_deriv_ms;
+  if (deriv_launches) *deriv_launches = b->last_deriv_launches;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_set_profiling(lvs_ndt_batch_t* b, int on) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  b->profiling = on;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_set_tuning(lvs_ndt_batch_t* b, int blocks_per_pair, int chunk_first, int chunk_next) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  b->blocks_per_pair_override = blocks_per_pair > 0 ? blocks_per_pair : 0;
+  if (chunk_first > 0) b->chunk_first = chunk_first;
+  if (chunk_next > 0) b->chunk_next = chunk_next;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_total_launches(lvs_ndt_batch_t* b, long long* launches) {
+  if (!b || !launches) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  *launches = b->total_launches;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int slot, int* n_cells, int* n_valid) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
+  if (n_cells) *n_cells = b->targets[slot].n_cells;
+  if (n_valid) *n_valid = b->targets[slot].gp.n_valid;
+  return LVS_OK;
+}
+
+// ---- single registration object
+int lvs_ndt_create(const lvs_ndt_params* params, int device, void* stream, lvs_ndt_t** out) {
+  if (!out) return fail(LVS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  lvs_ndt_batch* b = nullptr;
+  int rc = batch_create(params, device, stream, 1, 1, 1, &b);
+  if (rc) return rc;
+  lvs_ndt* h = new (std::nothrow) lvs_ndt();
+  if (!h) { lvs_ndt_batch_destroy(b); return fail(LVS_ERR_OOM, "host allocation failed"); }
+  h->b = b;
+  *out = h;
+  return LVS_OK;
+}
+
+int lvs_ndt_destroy(lvs_ndt_t* h) {
+  if (!h) return LVS_OK;
+  lvs_ndt_batch_destroy(h->b);
+  delete h;
+  return LVS_OK;
+}
+
+int lvs_ndt_set_params(lvs_ndt_t* h, const lvs_ndt_params* params) {
+  if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  int rc = check_params(params);
+  if (rc) return rc;
+  lvs_ndt_batch* b = h->b;
+  const bool revox = b->target_pts[0].set && (params->resolution != b->prm.resolution || params->variant != b->prm.variant ||
+                                              params->min_points_per_voxel != b->prm.min_points_per_voxel ||
+                                              params->min_covar_eigvalue_mult != b->prm.min_covar_eigvalue_mult);
+  b->prm = *params;
+  if (revox) {   // setResolution re-runs init() when the value changed and a target is set (ndt_omp.h:126-136)
+    if ((rc = set_device(b))) return rc;
+    rc = b->targets[0].build(b->st, b->target_pts[0].d_pts, b->target_pts[0].n, b->prm, b->ws);
+    b->total_launches += b->targets[0].launches_last_build;
+    return rc;
+  }
+  return LVS_OK;
+}
+
+int lvs_ndt_get_params(const lvs_ndt_t* h, lvs_ndt_params* out) {
+  if (!h || !out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  *out = h->b->prm;
+  return LVS_OK;
+}
+
+int lvs_ndt_set_target(lvs_ndt_t* h, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  return set_target(h->b, 0, xyz, n, stride_bytes, on_device);
+}
+
+int lvs_ndt_set_source(lvs_ndt_t* h, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+  if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  return set_source(h->b, 0, xyz, n, stride_bytes, on_device);
+}
+
+int lvs_ndt_align(lvs_ndt_t* h, const float guess[16], lvs_ndt_result* out) {
+  if (!h || !guess || !out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  const int32_t zero = 0;
+  return run_align(h->b, 1, &zero, &zero, guess, out);
+}
+
+int lvs_ndt_get_aligned_cloud(lvs_ndt_t* h, float* xyz_out, int on_device) {
+  if (!h || !xyz_out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  lvs_ndt_batch* b = h->b;
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  if (b->last_n_pairs < 1) return fail(LVS_ERR_INVALID_ARG, "align() has not run");
+  const int n = b->sources[0].n;
+  if (n == 0) return LVS_OK;
+  CUDA_TRY(cudaMemcpyAsync(b->d_T16, b->h_states[0].final_T, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st));
+  float* d_out = xyz_out;
+  if (!on_device) {
+    size_t bytes = (size_t)n * 12;
+    if (bytes > b->stage_cap) {
+      if (b->d_stage) cudaFree(b->d_stage);
+      b->d_stage = nullptr; b->stage_cap = 0;
+      CUDA_TRY(cudaMalloc(&b->d_stage, bytes + 4096));
+      b->stage_cap = bytes + 4096;
+    }
+    d_out = b->d_stage;
+  }
+  if ((rc = launch_transform(b->st, b->sources[0].d_pts, n, b->d_T16, d_out))) return rc;
+  b->total_launches++;
+  if (!on_device) CUDA_TRY(cudaMemcpyAsync(xyz_out, d_out, (size_t)n * 12, cudaMemcpyDeviceToHost, b->st));
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  return LVS_OK;
+}
+
+int lvs_ndt_get_trace(lvs_ndt_t* h, lvs_ndt_trace_rec* recs, int capacity, int* n_out) {
+  if (!h || !n_out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  lvs_ndt_batch* b = h->b;
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (b->last_n_pairs < 1) { *n_out = 0; return LVS_OK; }
+  int n = std::min(b->h_states[0].n_trace, (int)kMaxTrace);
+  *n_out = n;
+  n = std::min(n, capacity);
+  if (n > 0 && recs) {
+    static_assert(sizeof(lvs_ndt_trace_rec) == sizeof(TraceRec), "trace record layout");
+    CUDA_TRY(cudaMemcpyAsync(recs, b->d_trace, (size_t)n * sizeof(TraceRec), cudaMemcpyDeviceToHost, b->st));
+    CUDA_TRY(cudaStreamSynchronize(b->st));
+  }
+  return LVS_OK;
+}
+
+int lvs_ndt_eval_derivatives(lvs_ndt_t* h, const double p[6], const float* T16, int compute_hessian, double* score, double g[6], double H36[36]) {
+  if (!h || !p) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  return run_tap(h->b, compute_hessian ? EVAL_DERIV_H : EVAL_DERIV_NOH, p, T16, score, g, H36);
+}
+
+int lvs_ndt_eval_hessian(lvs_ndt_t* h, const double p[6], const float* T16, double H36[36]) {
+  if (!h || !p) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  return run_tap(h->b, EVAL_HESS27, p, T16, nullptr, nullptr, H36);
+}
+
+int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score) {
+  if (!h || !T16 || !score) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  lvs_ndt_batch* b = h->b;
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
+  if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  if (b->sources[0].n == 0) { *score = NAN; return LVS_OK; }   // 0/0 in the reference
+  const int bpp = choose_bpp(b, 1, b->sources[0].n);
+  if ((rc = reserve_pairs(b, 1, bpp))) return rc;
+  PairDesc P = make_pair(b, 0, 0);
+  CUDA_TRY(cudaMemcpyAsync(b->d_T16, T16, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st));
+  if ((rc = launch_calc_score(b->st, P, b->d_T16, make_consts(b->prm), b->d_partials, bpp * kAcc, b->d_tickets, b->d_scalar))) return rc;
+  b->total_launches++;
+  CUDA_TRY(cudaMemcpyAsync(b->h_scalar, b->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, b->st));
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  *score = b->h_scalar[0];
+  return LVS_OK;
+}
+
+int lvs_ndt_get_grid(lvs_ndt_t* h, int32_t min_b[3], int32_t max_b[3], int32_t div_b[3]) {
+  if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  const GridParams& g = h->b->targets[0].gp;
+  for (int a = 0; a < 3; a++) {
+    if (min_b) min_b[a] = g.min_b[a];
+    if (max_b) max_b[a] = g.max_b[a];
+    if (div_b) div_b[a] = g.div_b[a];
+  }
+  return LVS_OK;
+}
+
+int lvs_ndt_num_cells(lvs_ndt_t* h, int* n_cells) {
+  if (!h || !n_cells) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  *n_cells = h->b->targets[0].n_cells;
+  return LVS_OK;
+}
+
+int lvs_ndt_get_cells(lvs_ndt_t* h, int32_t* keys, int32_t* nr_points, double* mean3, double* icov9, double* evals3, float* centroid3, int32_t* weight) {
+  if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  lvs_ndt_batch* b = h->b;
+  int rc = set_device(b);
+  if (rc) return rc;
+  const TargetGrid& t = b->targets[0];
+  const int n = t.n_cells;
+  if (n == 0) return LVS_OK;
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  if (keys) CUDA_TRY(cudaMemcpy(keys, t.d_cell_keys, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (nr_points) CUDA_TRY(cudaMemcpy(nr_points, t.d_cell_npts, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (icov9) CUDA_TRY(cudaMemcpy(icov9, t.d_icov64, (size_t)n * 72, cudaMemcpyDeviceToHost));
+  if (evals3) CUDA_TRY(cudaMemcpy(evals3, t.d_cell_evals, (size_t)n * 24, cudaMemcpyDeviceToHost));
+  if (mean3 || weight) {
+    std::vector<VoxelRec> recs(n);
+    CUDA_TRY(cudaMemcpy(recs.data(), t.d_recs, (size_t)n * sizeof(VoxelRec), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+      if (mean3) for (int a = 0; a < 3; a++) mean3[i * 3 + a] = recs[i].mean[a];
+      if (weight) weight[i] = recs[i].meta & kMetaWeightMask;
+    }
+  }
+  if (centroid3) {
+    std::vector<float4> c(n);
+    CUDA_TRY(cudaMemcpy(c.data(), t.d_centroids, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) { centroid3[i * 3] = c[i].x; centroid3[i * 3 + 1] = c[i].y; centroid3[i * 3 + 2] = c[i].z; }
+  }
+  return LVS_OK;
+}
+
+int lvs_ndt_lookup_keys(lvs_ndt_t* h, const float T16[16], int32_t* keys_out) {
+  if (!h || !T16 || !keys_out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  lvs_ndt_batch* b = h->b;
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
+  if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  const int n = b->sources[0].n;
+  if (n == 0) return LVS_OK;
+  PairDesc P = make_pair(b, 0, 0);
+  int* d_keys = nullptr;
+  CUDA_TRY(cudaMalloc(&d_keys, (size_t)n * 4));
+  cudaError_t e = cudaMemcpyAsync(b->d_T16, T16, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st);
+  if (e == cudaSuccess) { rc = launch_lookup_keys(b->st, P, b->d_T16, d_keys); b->total_launches++; }
+  if (e == cudaSuccess && rc == LVS_OK) e = cudaMemcpyAsync(keys_out, d_keys, (size_t)n * 4, cudaMemcpyDeviceToHost, b->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->st);
+  cudaFree(d_keys);
+  if (e != cudaSuccess) return cuda_fail(e, "lookup_keys", __FILE__, __LINE__);
+  return rc;
+}
+
+int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out) {
+  if (!h || !out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  *out = h->b;
+  return LVS_OK;
+}
+
+}  // extern "C"

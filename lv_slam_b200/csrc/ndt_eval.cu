@@ -1,0 +1,276 @@
+// NDT derivative pass with direct voxel lookup — the hot kernel.  Replaces computeDerivatives / updateDerivatives /
+// computePointDerivatives_AngleAxisd (include/ndt_omp/ndt_omp_impl2.hpp:197-305, 504-532, 567-619; pca weight
+// include/ndt_pca/ndt_pca_impl2.hpp:293-296), getNeighborhoodAtPoint{,7,1}
+// (include/ndt_omp/voxel_grid_covariance_omp_impl.hpp:373-442) and pcl::transformPointCloud (:107,903,949).
+//
+// One launch = one evaluation of every active (source, target) pair; grid = n_pairs x blocks_per_pair CTAs.
+//   * a lane owns a source point: coalesced 16 B load, float transform (the reference's operation order, this TU is
+//     compiled with -fmad=false), voxel index, K probes of the dense int32 index grid, 64 B record fetch (4 x LDG.128);
+//   * the float32 contribution of a (point, cell) pair — score, 6 gradient terms, all 36 Hessian terms (the reference's H is
+//     not symmetric) — is computed exactly as the CPU path rounds it and staged in a per-warp shared-memory tile [43][32];
+//   * the fp64 accumulation the reference does per thread is done by the warp as a whole: the 43 x 4 (output, 8-lane group)
+//     sums are spread over the 32 lanes, so a lane keeps 6 fp64 accumulators instead of 43 — that is what lets three CTAs
+//     of 256 threads live on an SM instead of one;
+//   * CTA partial -> ticket -> the last CTA of the pair adds the partials in fixed order and advances the pair's
+//     Newton / More-Thuente state machine (eval_finish, ndt_state.cuh).
+#include "ndt_eval_common.cuh"
+
+namespace lvs {
+
+__constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+// pcl::getAllNeighborCellIndices (PCL 1.8 voxel_grid.h): 13 half-offsets, then their negatives; no centre cell.
+__constant__ int c_off26[26][3] = {
+    {-1, -1, -1}, {-1, 0, -1}, {-1, 1, -1}, {0, -1, -1}, {0, 0, -1}, {0, 1, -1}, {1, -1, -1}, {1, 0, -1}, {1, 1, -1},
+    {-1, -1, 0},  {0, -1, 0},  {1, -1, 0},  {-1, 0, 0},
+    {1, 1, 1},    {1, 0, 1},   {1, -1, 1},  {0, 1, 1},   {0, 0, 1},  {0, -1, 1},  {-1, 1, 1},  {-1, 0, 1},  {-1, -1, 1},
+    {1, 1, 0},    {0, 1, 0},   {-1, 1, 0},  {1, 0, 0}};
+
+constexpr int kTileStride = 33;            // floats per output row of the staging tile (32 lanes + 1 pad: conflict-free both ways)
+constexpr int kWarps = kEvalThreads / 32;
+
+template <bool HESS>
+struct Shape {
+  static constexpr int NV = HESS ? kAcc : 7;         // outputs per contribution
+  static constexpr int NTASK = NV * 4;               // (output, 8-lane group) sums
+  static constexpr int TPL = (NTASK + 31) / 32;      // tasks per lane: 6 (172 tasks) or 1 (28 tasks)
+};
+
+// updateDerivatives + computePointDerivatives_AngleAxisd for one (point, cell) pair, written into column `lane` of the
+// staging tile.  xr = R*x (float), d = x' - mean, C = float inverse covariance (row-major).  The zero / identity entries of
+// the reference's 4x6 and 24x6 matrices are folded away by hand; every remaining product and sum keeps the reference's
+// (Eigen SSE) order, so each float term is bit-identical to the CPU path.  Returns false on the reference's early-out
+// (d2*e > 1, < 0 or NaN, :588-589): nothing is written then.
+template <bool HESS>
+__device__ __forceinline__ bool contribute_tile(float* __restrict__ col /* tile + lane */, float xr, float yr, float zr, float d0, float d1,
+                                                float d2, const float* C, float gd2, double gauss_d1) {
+  const float xC0 = (d0 * C[0] + d2 * C[6]) + d1 * C[3];
+  const float xC1 = (d0 * C[1] + d2 * C[7]) + d1 * C[4];
+  const float xC2 = (d0 * C[2] + d2 * C[8]) + d1 * C[5];
+  const float q = (d0 * xC0 + d2 * xC2) + d1 * xC1;
+  float e = (float)exp((double)((-gd2 * q) * 0.5f));
+  const float score_inc = (float)(-gauss_d1 * (double)e);
+  e = gd2 * e;
+  if (e > kOne || e < 0.0f || e != e) return false;
+  e = (float)((double)e * gauss_d1);
+
+  const float nx = -xr, ny = -yr, nz = -zr;
+  float CJ[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    CJ[i][0] = C[i * 3]; CJ[i][1] = C[i * 3 + 1]; CJ[i][2] = C[i * 3 + 2];
+    CJ[i][3] = C[i * 3 + 1] * nz + C[i * 3 + 2] * yr;
+    CJ[i][4] = C[i * 3 + 0] * zr + C[i * 3 + 2] * nx;
+    CJ[i][5] = C[i * 3 + 0] * ny + C[i * 3 + 1] * xr;
+  }
+  float a[6];
+  a[0] = xC0; a[1] = xC1; a[2] = xC2;
+#pragma unroll
+  for (int j = 3; j < 6; j++) a[j] = (d0 * CJ[0][j] + d2 * CJ[2][j]) + d1 * CJ[1][j];
+
+  col[0] = score_inc;
+#pragma unroll
+  for (int j = 0; j < 6; j++) col[(1 + j) * kTileStride] = e * a[j];
+
+  if (HESS) {
+    // hp[i][j] = (d^T C) . Hp_ij  (non-zero only in the rotation block)
+    float hp[3][3];
+    hp[0][0] = xC2 * nz + xC1 * ny; hp[0][1] = xC1 * xr;            hp[0][2] = xC2 * xr;
+    hp[1][0] = xC0 * yr;            hp[1][1] = xC0 * nx + xC2 * nz; hp[1][2] = xC2 * yr;
+    hp[2][0] = xC0 * zr;            hp[2][1] = xC1 * zr;            hp[2][2] = xC0 * nx + xC1 * ny;
+    const float ngd2 = -gd2;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const float ai = ngd2 * a[i];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        // Mx[j][i] = J.col(j) . CJ.col(i)
+        float m;
+        if (j < 3) m = CJ[j][i];
+        else if (j == 3) m = yr * CJ[2][i] + nz * CJ[1][i];
+        else if (j == 4) m = zr * CJ[0][i] + nx * CJ[2][i];
+        else m = ny * CJ[0][i] + xr * CJ[1][i];
+        float t = ai * a[j];
+        if (i >= 3 && j >= 3) t = t + hp[i - 3][j - 3];
+        col[(7 + i * 6 + j) * kTileStride] = e * (t + m);
+      }
+    }
+  }
+  return true;
+}
+
+template <bool HESS, int MODE /* LVS_DIRECT1 / 7 / 26 */, bool PCA>
+__device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2,
+                                           double gd1, float* s_tile, double* s_w, double* s_red, double* partial) {
+  using Sh = Shape<HESS>;
+  constexpr int K = MODE == LVS_DIRECT1 ? 1 : (MODE == LVS_DIRECT7 ? 7 : 26);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = s_tile + warp * (kAcc * kTileStride);
+  double* wts = s_w + warp * 32;
+  double acc[Sh::TPL];
+#pragma unroll
+  for (int t = 0; t < Sh::TPL; t++) acc[t] = 0.0;
+
+  if (!G.empty) {
+    for (int base = (blk * kWarps + warp) * 32; base < P.n_src; base += bpp * kEvalThreads) {
+      const int i = base + lane;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      float tx = 0.f, ty = 0.f, tz = 0.f;
+      bool ok = i < P.n_src;
+      if (ok) {
+        s = __ldg(P.src + i);
+        transform_point(T, s.x, s.y, s.z, tx, ty, tz);
+        ok = isfinite(tx) && isfinite(ty) && isfinite(tz);
+      }
+      const int cx = (int)floorf(tx / G.leaf), cy = (int)floorf(ty / G.leaf), cz = (int)floorf(tz / G.leaf);
+      int rec[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        int ox = 0, oy = 0, oz = 0;
+        if (MODE == LVS_DIRECT7) { ox = c_off7[k][0]; oy = c_off7[k][1]; oz = c_off7[k][2]; }
+        if (MODE == LVS_DIRECT26) { ox = c_off26[k][0]; oy = c_off26[k][1]; oz = c_off26[k][2]; }
+        const int ix = cx + ox, iy = cy + oy, iz = cz + oz;
+        int v = -1;
+        if (ok && ix >= G.min_b[0] && ix <= G.max_b[0] && iy >= G.min_b[1] && iy <= G.max_b[1] && iz >= G.min_b[2] && iz <= G.max_b[2])
+          v = __ldg(P.grid + ((ix - G.min_b[0]) * G.mul[0] + (iy - G.min_b[1]) * G.mul[1] + (iz - G.min_b[2]) * G.mul[2]));
+        rec[k] = v;
+      }
+      // x_t = float(SE3::exp(p).matrix()) * [x, 0]: rotation only (:507-508)
+      const float xr = (R[0] * s.x + R[1] * s.y) + R[2] * s.z;
+      const float yr = (R[3] * s.x + R[4] * s.y) + R[5] * s.z;
+      const float zr = (R[6] * s.x + R[7] * s.y) + R[8] * s.z;
+      // ndt_pca multiplies the RUNNING per-point sums by each cell's weight (:293-296): the contribution of cell k ends up
+      // scaled by the product of the weights of cells k..last.
+      double wsuf[PCA ? K : 1];
+      if (PCA) {
+        double run = 1.0;
+#pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          if (rec[k] >= 0) run *= (double)(__ldg(&P.recs[rec[k]].meta) & kMetaWeightMask);
+          wsuf[k] = run;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const bool hit = rec[k] >= 0;
+        if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
+        bool used = false;
+        if (hit) {
+          const VoxelRec* vr = P.recs + rec[k];
+          const double2 m01 = __ldg(reinterpret_cast<const double2*>(vr));
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(vr) + 1);   // mean[2] (8 B) + icov[0..1]
+          const float4 q2 = __ldg(reinterpret_cast<const float4*>(vr) + 2);   // icov[2..5]
+          const float4 q3 = __ldg(reinterpret_cast<const float4*>(vr) + 3);   // icov[6..8] + meta
+          const double m2 = __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x));
+          const float C[9] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z};
+          const float d0 = (float)((double)tx - m01.x), d1 = (float)((double)ty - m01.y), d2 = (float)((double)tz - m2);
+          used = contribute_tile<HESS>(tile + lane, xr, yr, zr, d0, d1, d2, C, gd2, gd1);
+        }
+        if (!used) {
+#pragma unroll
+          for (int o = 0; o < Sh::NV; o++) tile[o * kTileStride + lane] = 0.0f;
+        }
+        if (PCA) wts[lane] = used ? wsuf[k] : 0.0;
+        const unsigned umask = __ballot_sync(0xffffffffu, used);   // also orders the tile writes before the reads below
+        __syncwarp();
+        if (umask != 0u) {
+#pragma unroll
+          for (int t = 0; t < Sh::TPL; t++) {
+            const int task = lane + 32 * t;
+            if (task < Sh::NTASK) {
+              const int o = task >> 2, g = task & 3;
+              if ((umask >> (8 * g)) & 0xffu) {
+                const float* row = tile + o * kTileStride + 8 * g;
+                double a = acc[t];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                  if (PCA) a += (double)row[jj] * wts[8 * g + jj];
+                  else a += (double)row[jj];
+                }
+                acc[t] = a;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // CTA partial: s_red[warp][task] -> output o sums its 4 groups over the 8 warps in fixed order
+#pragma unroll
+  for (int t = 0; t < Sh::TPL; t++) {
+    const int task = lane + 32 * t;
+    if (task < Sh::NTASK) s_red[warp * Sh::NTASK + task] = acc[t];
+  }
+  __syncthreads();
+  if (threadIdx.x < Sh::NV) {
+    double x = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++)
+#pragma unroll
+      for (int g = 0; g < 4; g++) x += s_red[w * Sh::NTASK + threadIdx.x * 4 + g];
+    partial[threadIdx.x] = x;
+  }
+}
+
+constexpr int kTileFloats = kWarps * kAcc * kTileStride;                       // 11 352 floats = 45 408 B
+constexpr size_t kHotSmem = kTileFloats * sizeof(float) + kWarps * 32 * sizeof(double) + kWarps * kAcc * 4 * sizeof(double);
+
+__global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ float s_T[16], s_R[9];
+  __shared__ int s_last;
+  const int pair = blockIdx.x / L.blocks_per_pair, blk = blockIdx.x % L.blocks_per_pair;
+  AlignState& S = L.d_states[pair];
+  const int kind = S.eval_kind;
+  const AlignConsts& c = L.consts;
+  if (kind != EVAL_DERIV_H && kind != EVAL_DERIV_NOH) return;
+  if (c.search == LVS_KDTREE) return;                      // radius-search derivatives live in the cold kernel
+  double* s_red = reinterpret_cast<double*>(s_dyn);                                   // [8][172]
+  double* s_w = s_red + kWarps * kAcc * 4;                                            // [8][32]
+  float* s_tile = reinterpret_cast<float*>(s_w + kWarps * 32);                        // [8][43][33]
+  const PairDesc P = L.d_pairs[pair];
+  if (threadIdx.x < 16) s_T[threadIdx.x] = S.T[threadIdx.x];
+  if (threadIdx.x < 9) s_R[threadIdx.x] = S.Rj[threadIdx.x];
+  __syncthreads();
+  const GridView G = load_grid_view(P.gp);
+  const float gd2 = (float)c.gauss_d2;
+  const bool pca = c.variant == LVS_NDT_PCA;
+  double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
+  const int bpp = L.blocks_per_pair;
+
+#define LVS_RUN(HESS, MODE)                                                                                              \
+  do {                                                                                                                   \
+    if (pca) run_direct<HESS, MODE, true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_tile, s_w, s_red, partial);       \
+    else run_direct<HESS, MODE, false>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_tile, s_w, s_red, partial);          \
+  } while (0)
+  if (kind == EVAL_DERIV_H) {
+    if (c.search == LVS_DIRECT1) LVS_RUN(true, LVS_DIRECT1);
+    else if (c.search == LVS_DIRECT7) LVS_RUN(true, LVS_DIRECT7);
+    else LVS_RUN(true, LVS_DIRECT26);
+  } else {
+    if (c.search == LVS_DIRECT1) LVS_RUN(false, LVS_DIRECT1);
+    else if (c.search == LVS_DIRECT7) LVS_RUN(false, LVS_DIRECT7);
+    else LVS_RUN(false, LVS_DIRECT26);
+  }
+#undef LVS_RUN
+  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_src, s_red, &s_last);
+}
+
+int launch_eval(cudaStream_t st, const EvalLaunch& L) {
+  if (L.n_pairs <= 0) return LVS_OK;
+  static bool attr_set = false;   // per-process; the attribute is per-device but every B200 is configured identically on first use
+  static int attr_dev = -1;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!attr_set || attr_dev != dev) {
+    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHotSmem));
+    attr_set = true; attr_dev = dev;
+  }
+  ndt_eval_kernel<<<L.n_pairs * L.blocks_per_pair, kEvalThreads, kHotSmem, st>>>(L);
+  CUDA_TRY(cudaGetLastError());
+  return LVS_OK;
+}
+
+int eval_max_resident_ctas_per_sm() { return 3; }
+
+}  // namespace lvs

@@ -1,0 +1,89 @@
+// Shared pieces of the NDT evaluation kernels (ndt_eval.cu = direct-search derivative pass, the hot kernel;
+// ndt_eval_cold.cu = radius-search passes: KDTREE-mode derivatives, computeHessian, calculateScore, taps).
+#pragma once
+#include "ndt_internal.cuh"
+#include "ndt_state.cuh"
+
+namespace lvs {
+
+constexpr int kEvalThreads = 256;
+constexpr float kOne = 1.0f;
+
+struct GridView {
+  int min_b[3], max_b[3], mul[3];
+  float leaf;
+  bool empty;
+};
+
+__device__ __forceinline__ GridView load_grid_view(const GridParams* gp) {
+  GridView g;
+  for (int a = 0; a < 3; a++) { g.min_b[a] = gp->min_b[a]; g.max_b[a] = gp->max_b[a]; g.mul[a] = gp->mul[a]; }
+  g.leaf = gp->leaf;
+  g.empty = gp->status != 0 || gp->n_cells == 0;
+  return g;
+}
+
+// pcl::transformPointCloud, dense branch: ((m00*x + m01*y) + m02*z) + m03, float, no contraction.
+__device__ __forceinline__ void transform_point(const float* T, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = ((T[0] * x + T[4] * y) + T[8] * z) + T[12];
+  oy = ((T[1] * x + T[5] * y) + T[9] * z) + T[13];
+  oz = ((T[2] * x + T[6] * y) + T[10] * z) + T[14];
+}
+
+// Completion of one evaluation of one pair: every CTA has stored its partial[nv]; the LAST CTA to take a ticket sums the
+// bpp partials in a fixed order (run-to-run deterministic), deposits (score, g, H) in the pair's AlignState and advances the
+// Newton / More-Thuente state machine so that the next launch knows what to evaluate.  s_scratch: >= 256 doubles of shared memory.
+__device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int kind, int nv, int n_src, double* s_scratch, int* s_last) {
+  AlignState& S = L.d_states[pair];
+  const AlignConsts& c = L.consts;
+  const int bpp = L.blocks_per_pair;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(&L.d_tickets[pair], 1u);
+    *s_last = (t == (unsigned)bpp - 1u);
+  }
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  constexpr int R = kEvalThreads / 64;   // 4 row groups x 64 columns (43 used)
+  {
+    const int k = threadIdx.x & 63, r = threadIdx.x >> 6;
+    double x = 0;
+    if (k < nv) {
+      const double* base = L.d_partials + (size_t)pair * bpp * kAcc;
+#pragma unroll 8
+      for (int b = r; b < bpp; b += R) x += __ldcg(base + (size_t)b * kAcc + k);
+    }
+    s_scratch[r * 64 + k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    double x = 0;
+    for (int r = 0; r < R; r++) x += s_scratch[r * 64 + threadIdx.x];
+    const int k = threadIdx.x;
+    if (kind == EVAL_HESS27) { if (k >= 7) S.H[k - 7] = x; }
+    else {
+      if (k == 0) S.score = x;
+      else if (k < 7) S.g[k - 1] = x;
+      else if (kind == EVAL_DERIV_H) S.H[k - 7] = x;
+    }
+  }
+  // computeDerivatives zeroes the Hessian even when it does not fill it (ndt_omp_impl2.hpp:204)
+  if (kind == EVAL_DERIV_NOH && threadIdx.x < 36) S.H[threadIdx.x] = 0.0;
+  __threadfence_block();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    L.d_tickets[pair] = 0;
+    if (L.advance) {
+      bool fin = align_state_advance(S, c, n_src, L.d_trace ? L.d_trace + (size_t)pair * kMaxTrace : nullptr);
+      if (fin) atomicAdd(L.d_done_count, 1);
+    } else {
+      S.eval_kind = EVAL_NONE;
+      if (kind != EVAL_HESS27) S.n_eval++; else S.n_hess++;
+    }
+    __threadfence();
+  }
+}
+
+}  // namespace lvs

@@ -1,0 +1,82 @@
+// Internal declarations shared by the NDT translation units of liblvslam_b200.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/lvslam_b200.h"
+#include "lvs_math.cuh"
+#include "ndt_types.cuh"
+
+namespace lvs {
+
+int fail(int status, const char* fmt, ...);          // records the thread-local error string, returns status
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define CUDA_TRY(expr)                                                      \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) return ::lvs::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+struct BuildScratch {                    // reusable workspace of the voxelisation pipeline
+  int capacity = 0;
+  unsigned int* d_keys[2] = {nullptr, nullptr};
+  int* d_idx[2] = {nullptr, nullptr};
+  int *d_flags = nullptr, *d_pos = nullptr, *d_seg_start = nullptr, *d_hist = nullptr, *d_hist_scan = nullptr;
+  float* d_bbox_partial = nullptr;
+  unsigned int* d_ticket = nullptr;
+  int *d_nseg = nullptr, *d_nvalidpts = nullptr;
+  GridParams* h_gp = nullptr;            // pinned
+  cudaError_t reserve(int n);
+  void release();
+};
+
+struct TargetGrid {                      // one voxelised target resident in HBM
+  const float4* pts = nullptr;
+  int n_points = 0;
+  GridParams gp{};                       // host copy
+  GridParams* d_gp = nullptr;
+  int* d_grid = nullptr;                 // dense int32 index grid, -1 = empty
+  size_t grid_capacity = 0;
+  VoxelRec* d_recs = nullptr;
+  float4* d_centroids = nullptr;         // float centroid (kd-tree cloud of the reference), w = 1 if in that cloud
+  int* d_cell_keys = nullptr;
+  int* d_cell_npts = nullptr;
+  double* d_cell_evals = nullptr;
+  double* d_icov64 = nullptr;            // [n_cells][9] double inverse covariance
+  size_t cell_capacity = 0;
+  int n_cells = 0;
+  int launches_last_build = 0;
+  int build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws);
+  void free_cells();
+  void release();
+};
+
+int pack_points(cudaStream_t st, const float* d_in, size_t stride_floats, int n, float4* d_out);
+
+// Evaluation kernels (ndt_eval.cu).  One launch advances every active pair by one evaluation and, in the
+// last CTA of each pair, by one step of the Newton / More-Thuente state machine.
+struct EvalLaunch {
+  const PairDesc* d_pairs;
+  AlignState* d_states;
+  TraceRec* d_trace;          // [n_pairs][kMaxTrace] or null
+  double* d_partials;         // [n_pairs][blocks_per_pair][kAcc]
+  unsigned int* d_tickets;    // [n_pairs]
+  int* d_done_count;          // incremented once per finished pair
+  int n_pairs;
+  int blocks_per_pair;
+  int advance;                // 1: run the align state machine; 0: tap mode, only store score/g/H
+  AlignConsts consts;
+};
+int launch_eval(cudaStream_t st, const EvalLaunch& L);        // direct-search derivative passes (hot)
+int launch_eval_cold(cudaStream_t st, const EvalLaunch& L);   // KDTREE-mode derivatives and the all-double Hessian pass
+int eval_max_resident_ctas_per_sm();
+int launch_calc_score(cudaStream_t st, const PairDesc& pair, const float* d_T16, const AlignConsts& c, double* d_partials, int max_blocks,
+                      unsigned int* d_ticket, double* d_out);
+int launch_lookup_keys(cudaStream_t st, const PairDesc& pair, const float* d_T16, int* d_keys_out);
+int launch_transform(cudaStream_t st, const float4* d_src, int n, const float* d_T16, float* d_out_xyz);
+
+}  // namespace lvs

@@ -1,0 +1,487 @@
+// Target voxelisation on the device — replaces VoxelGridCovariance::applyFilter
+// (include/ndt_omp/voxel_grid_covariance_omp_impl.hpp:49-370; pca label/weight
+// include/ndt_pca/voxel_grid_covariance_pca_impl.hpp:364-397).
+//
+// Pipeline (all stream-ordered, one host read-back of the grid geometry to size the dense index grid):
+//   pack_points      strided host layout -> float4
+//   bbox_kernel      min/max reduce, last CTA derives min_b/max_b/div_b/mul  (:72-103)
+//   key_kernel       int32 voxel key per point, float math exactly as :218-223
+//   radix sort       stable LSD sort of (key, point index): 8-bit digits, hist / scan / scatter
+//   head + scan      unique keys -> one segment per occupied cell, ascending key (= std::map order)
+//   leaf_kernel      one warp per cell: lanes 0..8 own the nine f64 moment accumulators, lanes 9..11 the
+//                    f32 centroid sums, each summed SEQUENTIALLY IN INPUT ORDER (bit-identical to the
+//                    reference's serial accumulation); lane 0 then finalises the leaf (:281-367)
+// Compiled with -fmad=false: no mul/add contraction anywhere in this file.
+#include "ndt_internal.cuh"
+
+namespace lvs {
+
+// ------------------------------------------------------------------ pack
+__global__ void pack_points_kernel(const float* __restrict__ in, size_t stride_floats, int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = in + (size_t)i * stride_floats;
+  out[i] = make_float4(p[0], p[1], p[2], 0.0f);
+}
+
+// ------------------------------------------------------------------ bbox
+__global__ void bbox_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partial /*[grid][6]*/,
+                            unsigned int* __restrict__ ticket, GridParams* __restrict__ gp, float leaf) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      cnt++;
+    }
+  }
+  __shared__ float s_mn[3][32], s_mx[3][32];
+  __shared__ int s_cnt[32];
+  __shared__ bool s_last;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = 16; o; o >>= 1) {
+    for (int a = 0; a < 3; a++) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) { for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; } s_cnt[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; w++) {
+      for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], s_mn[a][w]); mx[a] = fmaxf(mx[a], s_mx[a][w]); }
+      cnt += s_cnt[w];
+    }
+    float* o = partial + blockIdx.x * 8;
+    o[0] = mn[0]; o[1] = mn[1]; o[2] = mn[2]; o[3] = mx[0]; o[4] = mx[1]; o[5] = mx[2]; o[6] = __int_as_float(cnt);
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  for (int a = 0; a < 3; a++) { mn[a] = INFINITY; mx[a] = -INFINITY; }
+  cnt = 0;
+  for (unsigned b = 0; b < gridDim.x; b++) {
+    const volatile float* o = partial + b * 8;
+    for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], o[a]); mx[a] = fmaxf(mx[a], o[3 + a]); }
+    cnt += __float_as_int(o[6]);
+  }
+  *ticket = 0;
+  GridParams g;
+  g.leaf = leaf;
+  g.inv_leaf = __fdiv_rn(1.0f, leaf);               // pcl::VoxelGrid::setLeafSize
+  g.n_points = cnt; g.n_cells = 0; g.n_valid = 0; g.status = 0; g.total_cells = 0;
+  for (int a = 0; a < 3; a++) { g.min_p[a] = mn[a]; g.max_p[a] = mx[a]; g.min_b[a] = g.max_b[a] = g.div_b[a] = g.mul[a] = 0; }
+  if (cnt == 0) { g.status = 1; *gp = g; return; }
+  // overflow guard (:76-85)
+  long long dx = (long long)__fmul_rn(__fsub_rn(mx[0], mn[0]), g.inv_leaf) + 1;
+  long long dy = (long long)__fmul_rn(__fsub_rn(mx[1], mn[1]), g.inv_leaf) + 1;
+  long long dz = (long long)__fmul_rn(__fsub_rn(mx[2], mn[2]), g.inv_leaf) + 1;
+  if (dx * dy * dz > 2147483647LL) { g.status = LVS_ERR_GRID_OVERFLOW; *gp = g; return; }
+  for (int a = 0; a < 3; a++) {
+    g.min_b[a] = (int)floorf(__fmul_rn(mn[a], g.inv_leaf));
+    g.max_b[a] = (int)floorf(__fmul_rn(mx[a], g.inv_leaf));
+    g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
+  }
+  g.mul[0] = 1; g.mul[1] = g.div_b[0]; g.mul[2] = g.div_b[0] * g.div_b[1];
+  g.total_cells = (long long)g.div_b[0] * g.div_b[1] * g.div_b[2];
+  *gp = g;
+}
+
+// ------------------------------------------------------------------ keys
+constexpr unsigned int kInvalidKey = 0xFFFFFFFFu;
+
+__global__ void key_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
+                           unsigned int* __restrict__ keys, int* __restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  unsigned int k = kInvalidKey;
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    float inv = gp->inv_leaf;
+    int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)gp->min_b[0]);
+    int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)gp->min_b[1]);
+    int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)gp->min_b[2]);
+    k = (unsigned int)(i0 * gp->mul[0] + i1 * gp->mul[1] + i2 * gp->mul[2]);
+  }
+  keys[i] = k;
+  idx[i] = i;
+}
+
+// ------------------------------------------------------------------ single-CTA exclusive scan
+// out[i] = sum_{j<i} in[j]; total written to *total (may be null).  n up to a few million.
+__global__ void scan_exclusive_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += T) {
+    int i = base + threadIdx.x;
+    int v = (i < n) ? in[i] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = (lane < nw) ? s_warp[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      s_warp[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    int carry = s_carry;
+    int warp_off = warp ? s_warp[warp - 1] : 0;
+    if (i < n) out[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (threadIdx.x == T - 1) s_carry = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (total && threadIdx.x == 0) *total = s_carry;
+}
+
+// ------------------------------------------------------------------ stable LSD radix sort, 8-bit digits
+constexpr int kRsThreads = 256, kRsIpt = 8, kRsTile = kRsThreads * kRsIpt;
+
+__global__ void rs_hist_kernel(const unsigned int* __restrict__ keys, int n, int shift, int nblk, int* __restrict__ hist /*[256][nblk]*/) {
+  __shared__ int s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  int base = blockIdx.x * kRsTile;
+  for (int r = 0; r < kRsIpt; r++) {
+    int i = base + r * kRsThreads + threadIdx.x;
+    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255], 1);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void rs_scatter_kernel(const unsigned int* __restrict__ keys_in, const int* __restrict__ idx_in, int n, int shift, int nblk,
+                                  const int* __restrict__ offs /*[256][nblk] exclusive*/, unsigned int* __restrict__ keys_out,
+                                  int* __restrict__ idx_out) {
+  __shared__ int s_cnt[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < 8 * 256; k += kRsThreads) (&s_cnt[0][0])[k] = 0;
+  __syncthreads();
+  const int wbase = blockIdx.x * kRsTile + warp * (32 * kRsIpt);
+  unsigned int key[kRsIpt];
+  int val[kRsIpt], rank[kRsIpt], dig[kRsIpt];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < kRsIpt; r++) {
+    int i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    key[r] = ok ? keys_in[i] : 0u;
+    val[r] = ok ? idx_in[i] : 0;
+    int d = ok ? (int)((key[r] >> shift) & 255) : (256 + lane);
+    dig[r] = ok ? d : -1;
+    unsigned m = __match_any_sync(0xffffffffu, d);
+    int before = ok ? s_cnt[warp][d & 255] : 0;
+    rank[r] = before + __popc(m & lt);
+    __syncwarp();
+    if (ok && (m & lt) == 0) s_cnt[warp][d] = before + __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix over the 8 warps for every digit
+  {
+    int d = threadIdx.x, run = 0;
+    for (int w = 0; w < 8; w++) { int c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRsIpt; r++) {
+    if (dig[r] >= 0) {
+      int pos = offs[dig[r] * nblk + blockIdx.x] + s_cnt[warp][dig[r]] + rank[r];
+      keys_out[pos] = key[r];
+      idx_out[pos] = val[r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ segments
+__global__ void head_flag_kernel(const unsigned int* __restrict__ keys, int n, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned k = keys[i];
+  flags[i] = (k != kInvalidKey && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+}
+
+__global__ void seg_start_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ flags, const int* __restrict__ pos, int n,
+                                 int* __restrict__ seg_start, const int* __restrict__ n_seg, int* __restrict__ n_valid_pts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[i]) seg_start[pos[i]] = i;
+  // end sentinel: first invalid key or n
+  if (keys[i] != kInvalidKey && (i == n - 1 || keys[i + 1] == kInvalidKey)) { seg_start[*n_seg] = i + 1; *n_valid_pts = i + 1; }
+}
+
+__global__ void clear_cells_kernel(int* __restrict__ grid, const int* __restrict__ old_keys, int n_old) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_old) grid[old_keys[i]] = -1;
+}
+
+// ------------------------------------------------------------------ per-cell moments + leaf finalisation
+__global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ keys, const int* __restrict__ sidx,
+                            const int* __restrict__ seg_start, const int* __restrict__ n_seg_p, VoxelRec* __restrict__ recs,
+                            float4* __restrict__ centroids, int* __restrict__ cell_keys, int* __restrict__ cell_npts,
+                            double* __restrict__ cell_evals, double* __restrict__ icov64, int* __restrict__ grid, GridParams* __restrict__ gp,
+                            int min_points, double eig_mult, int variant) {
+  __shared__ float s_pt[8][32][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_seg = *n_seg_p;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  // which coordinate(s) this lane accumulates
+  int ci = 0, cj = 0;
+  if (lane < 3) { ci = lane; }
+  else if (lane < 9) { const int I[6] = {0, 0, 0, 1, 1, 2}, J[6] = {0, 1, 2, 1, 2, 2}; ci = I[lane - 3]; cj = J[lane - 3]; }
+  else if (lane < 12) { ci = lane - 9; }
+  int valid_cells = 0;
+  for (int seg = blockIdx.x * (blockDim.x >> 5) + warp; seg < n_seg; seg += warps_total) {
+    const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
+    double acc = 0.0;
+    float facc = 0.0f;
+    for (int base = s0; base < s1; base += 32) {
+      int m = min(32, s1 - base);
+      __syncwarp();
+      if (lane < m) {
+        float4 p = pts[sidx[base + lane]];
+        s_pt[warp][lane][0] = p.x; s_pt[warp][lane][1] = p.y; s_pt[warp][lane][2] = p.z;
+      }
+      __syncwarp();
+      if (lane < 3) {
+        for (int k = 0; k < m; k++) acc = __dadd_rn(acc, (double)s_pt[warp][k][ci]);
+      } else if (lane < 9) {
+        for (int k = 0; k < m; k++) acc = __dadd_rn(acc, __dmul_rn((double)s_pt[warp][k][ci], (double)s_pt[warp][k][cj]));
+      } else if (lane < 12) {
+        for (int k = 0; k < m; k++) facc = __fadd_rn(facc, s_pt[warp][k][ci]);
+      }
+    }
+    // gather the nine sums + centroid on lane 0
+    double S1[3], S2[6];
+    float cs[3];
+    for (int a = 0; a < 3; a++) S1[a] = __shfl_sync(0xffffffffu, acc, a);
+    for (int a = 0; a < 6; a++) S2[a] = __shfl_sync(0xffffffffu, acc, 3 + a);
+    for (int a = 0; a < 3; a++) cs[a] = __shfl_sync(0xffffffffu, facc, 9 + a);
+    if (lane != 0) continue;
+
+    const int npts = s1 - s0;
+    const int key = (int)keys[s0];
+    const double np = (double)npts;
+    double mean[3] = {S1[0] / np, S1[1] / np, S1[2] / np};
+    VoxelRec rec;
+    double ic[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < 3; a++) rec.mean[a] = mean[a];
+    for (int a = 0; a < 9; a++) rec.icov[a] = 0.0f;
+    rec.meta = 1;
+    float fn = (float)npts;
+    centroids[seg] = make_float4(__fdiv_rn(cs[0], fn), __fdiv_rn(cs[1], fn), __fdiv_rn(cs[2], fn), npts >= min_points ? 1.0f : 0.0f);
+    int out_npts = npts;
+    double ev[3] = {0, 0, 0};
+    bool usable = false;
+    if (npts >= min_points) {
+      // single-pass covariance (:329-330): full 3x3, element (i,j) uses pt_sum[i]*mean[j]
+      double cov[9];
+      const int sidx2[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+          double v = (S2[sidx2[i * 3 + j]] - 2.0 * (S1[i] * mean[j])) / np + mean[i] * mean[j];
+          cov[i * 3 + j] = v;
+        }
+      const double sc = (np - 1.0) / np;
+      for (int a = 0; a < 9; a++) cov[a] *= sc;
+      // SelfAdjointEigenSolver reads the lower triangle only
+      double low[9] = {cov[0], cov[3], cov[6], cov[3], cov[4], cov[7], cov[6], cov[7], cov[8]};
+      double V[9];
+      sym3_eigen(low, ev, V);
+      if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
+        out_npts = -1;
+        ev[0] = ev[1] = ev[2] = 0.0;    // evals_ is assigned only after the check (:357)
+      } else {
+        double min_ev = eig_mult * ev[2];
+        if (ev[0] < min_ev) {
+          ev[0] = min_ev;
+          if (ev[1] < min_ev) ev[1] = min_ev;
+          double Vi[9], VL[9];
+          mat3_inverse(V, Vi);
+          for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) VL[i * 3 + j] = V[i * 3 + j] * ev[j];
+          mat3_mul(VL, Vi, cov);
+        }
+        int weight = 1;
+        if (variant == LVS_NDT_PCA) {
+          double s0_ = sqrt(ev[0]), s1_ = sqrt(ev[1]), s2_ = sqrt(ev[2]);
+          double f0 = (s2_ - s1_) / s2_, f1 = (s1_ - s0_) / s2_, f2 = s0_ / s2_;
+          int d = 0; double fm = f0;
+          if (f1 > fm) { d = 1; fm = f1; }
+          if (f2 > fm) { d = 2; }
+          double scale = d == 1 ? 1.25 : (d == 2 ? 1.0 : 0.75);
+          double nm = sqrt(mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]);
+          weight = (int)(scale * nm);           // int getDimension2d() truncation (voxel_grid_covariance_pca.h:222-226)
+        }
+        mat3_inverse(cov, ic);
+        double mxc = ic[0], mnc = ic[0];
+        for (int a = 1; a < 9; a++) { mxc = fmax(mxc, ic[a]); mnc = fmin(mnc, ic[a]); }
+        for (int a = 0; a < 9; a++) rec.icov[a] = (float)ic[a];
+        if (mxc == (double)INFINITY || mnc == -(double)INFINITY) out_npts = -1;
+        else usable = true;
+        rec.meta = (weight & kMetaWeightMask) | (usable ? kMetaValidBit : 0);
+      }
+    }
+    recs[seg] = rec;
+    for (int a = 0; a < 9; a++) icov64[(size_t)seg * 9 + a] = ic[a];
+    cell_keys[seg] = key;
+    cell_npts[seg] = out_npts;
+    cell_evals[seg * 3] = ev[0]; cell_evals[seg * 3 + 1] = ev[1]; cell_evals[seg * 3 + 2] = ev[2];
+    grid[key] = usable ? seg : (-2 - seg);
+    if (usable) valid_cells++;
+  }
+  if (lane == 0 && valid_cells) atomicAdd(&gp->n_valid, valid_cells);
+  if (blockIdx.x == 0 && threadIdx.x == 0) gp->n_cells = n_seg;
+}
+
+// ------------------------------------------------------------------ host side
+int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws) {
+  n_points = n;
+  pts = d_pts;
+  CUDA_TRY(ws.reserve(n));
+  if (!d_gp) CUDA_TRY(cudaMalloc(&d_gp, sizeof(GridParams)));
+  // wipe the cells of the previous build while the old keys still describe this buffer
+  if (d_grid && n_cells > 0) {
+    clear_cells_kernel<<<(n_cells + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, n_cells);
+  }
+  n_cells = 0;
+  if (n == 0) {
+    GridParams g; memset(&g, 0, sizeof g); g.status = 1; g.leaf = prm.resolution; g.inv_leaf = 1.0f / prm.resolution;
+    CUDA_TRY(cudaMemcpyAsync(d_gp, &g, sizeof g, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    gp = g;
+    return LVS_OK;
+  }
+  int nb = std::min(1024, (n + 255) / 256);
+  CUDA_TRY(cudaMemsetAsync(ws.d_ticket, 0, sizeof(unsigned int), st));
+  bbox_kernel<<<nb, 256, 0, st>>>(d_pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, prm.resolution);
+  CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  gp = *ws.h_gp;
+  if (gp.status == LVS_ERR_GRID_OVERFLOW) return fail(LVS_ERR_GRID_OVERFLOW, "leaf size too small for the target extent: dx*dy*dz > INT32_MAX");
+  if (gp.status == 1) return LVS_OK;   // no finite point
+  // dense index grid: grow-only, -1 filled
+  if ((size_t)gp.total_cells > grid_capacity) {
+    if (d_grid) cudaFree(d_grid);
+    d_grid = nullptr;
+    size_t cap = (size_t)gp.total_cells + (size_t)gp.total_cells / 4 + 1024;
+    cudaError_t e = cudaMalloc(&d_grid, cap * sizeof(int));
+    if (e != cudaSuccess) { grid_capacity = 0; (void)cudaGetLastError(); return fail(LVS_ERR_OOM, "dense voxel index grid allocation failed"); }
+    grid_capacity = cap;
+    CUDA_TRY(cudaMemsetAsync(d_grid, 0xFF, cap * sizeof(int), st));
+  }
+  // cell arrays sized for the worst case of one cell per point
+  if ((size_t)n > cell_capacity) {
+    free_cells();
+    size_t cap = (size_t)n + n / 8 + 64;
+    CUDA_TRY(cudaMalloc(&d_recs, cap * sizeof(VoxelRec)));
+    CUDA_TRY(cudaMalloc(&d_centroids, cap * sizeof(float4)));
+    CUDA_TRY(cudaMalloc(&d_cell_keys, cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_cell_npts, cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_cell_evals, cap * 3 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_icov64, cap * 9 * sizeof(double)));
+    cell_capacity = cap;
+  }
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  key_kernel<<<gb, tb, 0, st>>>(d_pts, n, d_gp, ws.d_keys[0], ws.d_idx[0]);
+  // number of 8-bit passes needed for keys < total_cells (invalid keys 0xFFFFFFFF sort last in every pass)
+  int bits = 1;
+  while (bits < 32 && (1LL << bits) <= gp.total_cells) bits++;   // max key <= 2^bits - 2, never all-ones
+  int passes = (bits + 7) / 8;
+  const int nblk = (n + kRsTile - 1) / kRsTile;
+  int cur = 0;
+  for (int p = 0; p < passes; p++) {
+    rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], n, p * 8, nblk, ws.d_hist);
+    scan_exclusive_kernel<<<1, 1024, 0, st>>>(ws.d_hist, ws.d_hist_scan, 256 * nblk, nullptr);
+    rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], ws.d_idx[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], ws.d_idx[cur ^ 1]);
+    cur ^= 1;
+  }
+  head_flag_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], n, ws.d_flags);
+  scan_exclusive_kernel<<<1, 1024, 0, st>>>(ws.d_flags, ws.d_pos, n, ws.d_nseg);
+  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, ws.d_seg_start, ws.d_nseg, ws.d_nvalidpts);
+  int lb = std::min(148 * 8, (n + 7) / 8);
+  leaf_kernel<<<lb, 256, 0, st>>>(d_pts, ws.d_keys[cur], ws.d_idx[cur], ws.d_seg_start, ws.d_nseg, d_recs, d_centroids, d_cell_keys,
+                                  d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp, prm.min_points_per_voxel, prm.min_covar_eigvalue_mult, prm.variant);
+  CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  gp = *ws.h_gp;
+  n_cells = gp.n_cells;
+  launches_last_build = 6 + passes * 3;
+  return LVS_OK;
+}
+
+void TargetGrid::free_cells() {
+  if (d_recs) cudaFree(d_recs);
+  if (d_centroids) cudaFree(d_centroids);
+  if (d_cell_keys) cudaFree(d_cell_keys);
+  if (d_cell_npts) cudaFree(d_cell_npts);
+  if (d_cell_evals) cudaFree(d_cell_evals);
+  if (d_icov64) cudaFree(d_icov64);
+  d_icov64 = nullptr;
+  d_recs = nullptr; d_centroids = nullptr; d_cell_keys = nullptr; d_cell_npts = nullptr; d_cell_evals = nullptr;
+  cell_capacity = 0;
+}
+
+void TargetGrid::release() {
+  free_cells();
+  if (d_grid) cudaFree(d_grid);
+  if (d_gp) cudaFree(d_gp);
+  d_grid = nullptr; d_gp = nullptr; grid_capacity = 0; n_cells = 0;
+}
+
+cudaError_t BuildScratch::reserve(int n) {
+  if (n <= capacity) return cudaSuccess;
+  release();
+  int cap = n + n / 8 + 1024;
+  int nblk = (cap + kRsTile - 1) / kRsTile;
+  cudaError_t e;
+  for (int k = 0; k < 2; k++) {
+    if ((e = cudaMalloc(&d_keys[k], (size_t)cap * sizeof(unsigned int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d_idx[k], (size_t)cap * sizeof(int))) != cudaSuccess) return e;
+  }
+  if ((e = cudaMalloc(&d_flags, (size_t)cap * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_pos, (size_t)cap * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_seg_start, ((size_t)cap + 2) * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_hist, (size_t)256 * nblk * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_hist_scan, (size_t)256 * nblk * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_bbox_partial, 1024 * 8 * sizeof(float))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_ticket, 4 * sizeof(unsigned int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_nseg, 4 * sizeof(int))) != cudaSuccess) return e;
+  d_nvalidpts = d_nseg + 1;
+  if (!h_gp && (e = cudaMallocHost(&h_gp, sizeof(GridParams))) != cudaSuccess) return e;
+  capacity = cap;
+  return cudaSuccess;
+}
+
+void BuildScratch::release() {
+  for (int k = 0; k < 2; k++) { if (d_keys[k]) cudaFree(d_keys[k]); if (d_idx[k]) cudaFree(d_idx[k]); d_keys[k] = nullptr; d_idx[k] = nullptr; }
+  if (d_flags) cudaFree(d_flags);
+  if (d_pos) cudaFree(d_pos);
+  if (d_seg_start) cudaFree(d_seg_start);
+  if (d_hist) cudaFree(d_hist);
+  if (d_hist_scan) cudaFree(d_hist_scan);
+  if (d_bbox_partial) cudaFree(d_bbox_partial);
+  if (d_ticket) cudaFree(d_ticket);
+  if (d_nseg) cudaFree(d_nseg);
+  d_flags = d_pos = d_seg_start = d_hist = d_hist_scan = nullptr; d_bbox_partial = nullptr; d_ticket = nullptr; d_nseg = nullptr;
+  capacity = 0;
+}
+
+int pack_points(cudaStream_t st, const float* d_in, size_t stride_floats, int n, float4* d_out) {
+  if (n == 0) return LVS_OK;
+  pack_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_in, stride_floats, n, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return LVS_OK;
+}
+
+}  // namespace lvs

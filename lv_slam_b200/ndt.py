@@ -1,0 +1,266 @@
+"""Host mirror of the reference registration classes over the C-ABI.
+
+``NormalDistributionsTransform`` carries the method names of ``pclomp::NormalDistributionsTransform``
+(/root/reference/include/ndt_omp/ndt_omp.h:69-551) and ``pclpca::NormalDistributionsTransform``
+(include/ndt_pca/ndt_pca.h); clouds are numpy float32 [n, >=3] arrays (row stride = point stride) or CUDA torch
+tensors.  All arithmetic happens in liblvslam_b200.so on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi as C
+
+
+def _colmajor16(T):
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T.reshape(16))
+
+
+def _from_colmajor16(v):
+    return np.asarray(v, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+def _cloud_args(xyz):
+    """-> (pointer, n, stride_bytes, on_device, keepalive)"""
+    if hasattr(xyz, "is_cuda"):
+        import torch
+        t = xyz
+        if t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] < 3 or (t.shape[0] > 0 and t.stride(1) != 1):
+            raise ValueError("cloud tensor must be float32 [n, >=3] with unit inner stride")
+        stride = t.stride(0) * 4 if t.shape[0] > 1 else t.shape[1] * 4
+        return t.data_ptr(), t.shape[0], stride, 1 if t.is_cuda else 0, t
+    a = np.asarray(xyz)
+    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.shape[0] > 0 and a.strides[1] != 4:
+        a = np.ascontiguousarray(a)
+    stride = a.strides[0] if a.shape[0] > 1 else a.shape[1] * 4
+    return a.ctypes.data, a.shape[0], stride, 0, a
+
+
+def _params(**kw):
+    p = C.NdtParams()
+    C.lib().lvs_ndt_default_params(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class NormalDistributionsTransform:
+    """One registration object.  ``variant`` selects pclomp (LVS_NDT_OMP) or pclpca (LVS_NDT_PCA)."""
+
+    def __init__(self, variant=C.LVS_NDT_OMP, device=0, stream=None):
+        self._L = C.lib()
+        self._p = _params(variant=variant)
+        h = ctypes.c_void_p()
+        C.check(self._L.lvs_ndt_create(ctypes.byref(self._p), device, stream, ctypes.byref(h)))
+        self._h = h
+        self._res = None
+        self._n_src = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lvs_ndt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setters of the reference class
+    def _push(self):
+        C.check(self._L.lvs_ndt_set_params(self._h, ctypes.byref(self._p)))
+
+    def setResolution(self, r):
+        self._p.resolution = float(r); self._push()
+
+    def setStepSize(self, s):
+        self._p.step_size = float(s); self._push()
+
+    def setOulierRatio(self, o):  # [sic] the reference's spelling (ndt_omp.h:177)
+        self._p.outlier_ratio = float(o); self._push()
+
+    def setTransformationEpsilon(self, e):
+        self._p.transformation_epsilon = float(e); self._push()
+
+    def setMaximumIterations(self, n):
+        self._p.max_iterations = int(n); self._push()
+
+    def setNeighborhoodSearchMethod(self, m):
+        self._p.search_method = int(m); self._push()
+
+    def setNumThreads(self, n):
+        pass  # OpenMP team size of the reference; meaningless on the device
+
+    def getResolution(self):
+        return self._p.resolution
+
+    def getStepSize(self):
+        return self._p.step_size
+
+    def getOulierRatio(self):
+        return self._p.outlier_ratio
+
+    # ---- clouds
+    def setInputTarget(self, xyz):
+        ptr, n, stride, dev, keep = _cloud_args(xyz)
+        C.check(self._L.lvs_ndt_set_target(self._h, ptr, n, stride, dev))
+
+    def setInputSource(self, xyz):
+        ptr, n, stride, dev, keep = _cloud_args(xyz)
+        self._n_src = n
+        C.check(self._L.lvs_ndt_set_source(self._h, ptr, n, stride, dev))
+
+    # ---- registration
+    def align(self, guess=None, want_cloud=False):
+        g = _colmajor16(np.eye(4) if guess is None else guess)
+        r = C.NdtResult()
+        C.check(self._L.lvs_ndt_align(self._h, g.ctypes.data, ctypes.byref(r)))
+        self._res = r
+        if want_cloud:
+            out = np.empty((self._n_src, 3), np.float32)
+            C.check(self._L.lvs_ndt_get_aligned_cloud(self._h, out.ctypes.data, 0))
+            return out
+        return None
+
+    def getFinalTransformation(self):
+        return _from_colmajor16(np.frombuffer(self._res.final_transformation, dtype=np.float32))
+
+    def hasConverged(self):
+        return bool(self._res.converged)
+
+    def getFinalNumIteration(self):
+        return int(self._res.iterations)
+
+    def getTransformationProbability(self):
+        return float(self._res.trans_probability)
+
+    def result(self):
+        r = self._res
+        return dict(final=self.getFinalTransformation(), iterations=int(r.iterations), converged=bool(r.converged),
+                    trans_probability=float(r.trans_probability), n_eval=int(r.n_eval), n_hess=int(r.n_hess), score=float(r.score),
+                    trace=self.trace())
+
+    def trace(self):
+        recs = (C.NdtTraceRec * 80)()
+        n = ctypes.c_int(0)
+        C.check(self._L.lvs_ndt_get_trace(self._h, recs, 80, ctypes.byref(n)))
+        out = np.zeros((min(n.value, 80), 22))
+        for k in range(out.shape[0]):
+            t = recs[k]
+            out[k, 0:6] = t.p_before; out[k, 6:12] = t.dir; out[k, 12] = t.step; out[k, 13] = t.score
+            out[k, 14:20] = t.p_after; out[k, 20] = t.trials; out[k, 21] = t.hessian_recomputed
+        return out
+
+    def calculateScore(self, T):
+        g = _colmajor16(T)
+        s = ctypes.c_double(0)
+        C.check(self._L.lvs_ndt_calculate_score(self._h, g.ctypes.data, ctypes.byref(s)))
+        return s.value
+
+    # ---- parity taps
+    def eval_derivatives(self, p6, T=None, compute_hessian=True):
+        p = np.ascontiguousarray(p6, dtype=np.float64)
+        Tm = _colmajor16(T) if T is not None else None
+        s = ctypes.c_double(0)
+        g, H = np.zeros(6), np.zeros((6, 6))
+        C.check(self._L.lvs_ndt_eval_derivatives(self._h, p.ctypes.data, Tm.ctypes.data if Tm is not None else None,
+                                                 int(compute_hessian), ctypes.byref(s), g.ctypes.data, H.ctypes.data))
+        return s.value, g, H
+
+    def eval_hessian(self, p6, T=None):
+        p = np.ascontiguousarray(p6, dtype=np.float64)
+        Tm = _colmajor16(T) if T is not None else None
+        H = np.zeros((6, 6))
+        C.check(self._L.lvs_ndt_eval_hessian(self._h, p.ctypes.data, Tm.ctypes.data if Tm is not None else None, H.ctypes.data))
+        return H
+
+    def grid(self):
+        mn, mx, dv = (np.zeros(3, np.int32) for _ in range(3))
+        C.check(self._L.lvs_ndt_get_grid(self._h, mn.ctypes.data, mx.ctypes.data, dv.ctypes.data))
+        return mn, mx, dv
+
+    def cells(self):
+        n = ctypes.c_int(0)
+        C.check(self._L.lvs_ndt_num_cells(self._h, ctypes.byref(n)))
+        n = n.value
+        out = dict(keys=np.zeros(n, np.int32), nr_points=np.zeros(n, np.int32), mean=np.zeros((n, 3)), icov=np.zeros((n, 3, 3)),
+                   evals=np.zeros((n, 3)), centroid=np.zeros((n, 3), np.float32), weight=np.zeros(n, np.int32))
+        C.check(self._L.lvs_ndt_get_cells(self._h, *[out[k].ctypes.data for k in ("keys", "nr_points", "mean", "icov", "evals", "centroid", "weight")]))
+        return out
+
+    def lookup_keys(self, T):
+        g = _colmajor16(T)
+        keys = np.zeros(self._n_src, np.int32)
+        C.check(self._L.lvs_ndt_lookup_keys(self._h, g.ctypes.data, keys.ctypes.data))
+        return keys
+
+    def batch_handle(self):
+        b = ctypes.c_void_p()
+        C.check(self._L.lvs_ndt_handle_batch(self._h, ctypes.byref(b)))
+        return b
+
+
+class NdtBatch:
+    """Many (source, target, guess) pairs advanced together on one device (loop-closure candidates, stream replay)."""
+
+    def __init__(self, n_target_slots, n_source_slots, device=0, stream=None, **params):
+        self._L = C.lib()
+        self._p = _params(**params)
+        h = ctypes.c_void_p()
+        C.check(self._L.lvs_ndt_batch_create(ctypes.byref(self._p), device, stream, n_target_slots, n_source_slots, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lvs_ndt_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_target(self, slot, xyz):
+        ptr, n, stride, dev, keep = _cloud_args(xyz)
+        C.check(self._L.lvs_ndt_batch_set_target(self._h, slot, ptr, n, stride, dev))
+
+    def set_source(self, slot, xyz):
+        ptr, n, stride, dev, keep = _cloud_args(xyz)
+        C.check(self._L.lvs_ndt_batch_set_source(self._h, slot, ptr, n, stride, dev))
+
+    def align(self, source_slots, target_slots, guesses):
+        s = np.ascontiguousarray(source_slots, dtype=np.int32)
+        t = np.ascontiguousarray(target_slots, dtype=np.int32)
+        n = s.shape[0]
+        g = np.ascontiguousarray(np.stack([_colmajor16(G) for G in guesses]) if n else np.zeros((0, 16), np.float32))
+        res = (C.NdtResult * max(n, 1))()
+        C.check(self._L.lvs_ndt_batch_align(self._h, n, s.ctypes.data, t.ctypes.data, g.ctypes.data, res))
+        return [dict(final=_from_colmajor16(np.frombuffer(res[i].final_transformation, dtype=np.float32)), iterations=int(res[i].iterations),
+                     converged=bool(res[i].converged), trans_probability=float(res[i].trans_probability), n_eval=int(res[i].n_eval),
+                     n_hess=int(res[i].n_hess), score=float(res[i].score)) for i in range(n)]
+
+    def set_profiling(self, on):
+        C.check(self._L.lvs_ndt_batch_set_profiling(self._h, int(on)))
+
+    def set_tuning(self, blocks_per_pair=0, chunk_first=0, chunk_next=0):
+        C.check(self._L.lvs_ndt_batch_set_tuning(self._h, blocks_per_pair, chunk_first, chunk_next))
+
+    def last_stats(self):
+        ms, dms = ctypes.c_double(0), ctypes.c_double(0)
+        nl, dl = ctypes.c_int(0), ctypes.c_int(0)
+        C.check(self._L.lvs_ndt_batch_last_stats(self._h, ctypes.byref(ms), ctypes.byref(nl), ctypes.byref(dms), ctypes.byref(dl)))
+        return dict(device_ms=ms.value, launches=nl.value, deriv_kernel_ms=dms.value, deriv_launches=dl.value)
+
+    def total_launches(self):
+        n = ctypes.c_longlong(0)
+        C.check(self._L.lvs_ndt_batch_total_launches(self._h, ctypes.byref(n)))
+        return n.value
+
+    def num_cells(self, slot):
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        C.check(self._L.lvs_ndt_batch_num_cells(self._h, slot, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value

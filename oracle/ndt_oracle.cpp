@@ -122,10 +122,14 @@ void apply_filter(NDT& n) {         // voxel_grid_covariance_omp_impl.hpp:49-370
   if (P.empty()) { for (int a = 0; a < 3; a++) n.min_b[a] = n.max_b[a] = n.div_b[a] = n.divb_mul[a] = 0; return; }
   float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
   float mx[3] = {-mn[0], -mn[1], -mn[2]};
-  for (const Pt& p : P) {           // pcl::getMinMax3D (dense cloud)
+  size_t n_finite = 0;
+  for (const Pt& p : P) {           // pcl::getMinMax3D: the is_dense=false branch skips non-finite points; on a dense cloud both branches agree
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+    n_finite++;
     mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
     mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
   }
+  if (n_finite == 0) { for (int a = 0; a < 3; a++) n.min_b[a] = n.max_b[a] = n.div_b[a] = n.divb_mul[a] = 0; return; }
   int64_t dx = (int64_t)((mx[0] - mn[0]) * n.inv_leaf) + 1;   // :76-85 overflow guard
   int64_t dy = (int64_t)((mx[1] - mn[1]) * n.inv_leaf) + 1;
   int64_t dz = (int64_t)((mx[2] - mn[2]) * n.inv_leaf) + 1;

@@ -68,7 +68,8 @@ inline M3 m3_inverse(const M3& m) {
 // Cyclic Jacobi for a symmetric 3x3.  Output eigenvalues ascending, eigenvectors in columns of V.
 inline void sym3_eig(const M3& A_in, double evals[3], M3& V) {
   double a[3][3];
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = 0.5 * (A_in.a[i][j] + A_in.a[j][i]);
+  // Eigen::SelfAdjointEigenSolver reads the lower triangle only
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = (i >= j) ? A_in.a[i][j] : A_in.a[j][i];
   double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   for (int sweep = 0; sweep < 32; sweep++) {
     double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
@@ -120,7 +121,7 @@ inline void svd6_solve(const double A[36] /*row-major*/, const double b[6], doub
         double alpha = 0, beta = 0, gamma = 0;
         for (int k = 0; k < 6; k++) { alpha += U[k][p] * U[k][p]; beta += U[k][q] * U[k][q]; gamma += U[k][p] * U[k][q]; }
         if (gamma == 0.0) continue;
-        if (std::fabs(gamma) <= 1e-17 * std::sqrt(alpha * beta)) continue;
+        if (std::fabs(gamma) <= 2.220446049250313e-16 * std::sqrt(alpha * beta)) continue;
         rotated = true;
         double zeta = (beta - alpha) / (2.0 * gamma);
         double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));

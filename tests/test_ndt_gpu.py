@@ -1,0 +1,290 @@
+"""Parity of the CUDA NDT path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8c): voxel keys and point counts bit-exact; per-cell mean / inverse
+covariance 1e-9 relative (fp64 on both sides); (score, gradient, Hessian) 1e-9 relative to the largest entry (the float32
+per-point terms are bit-identical, only the fp64 summation order differs); per-iteration pose <= 1e-4 m / 1e-5 rad.
+"""
+import numpy as np
+import pytest
+
+import oracle_ndt as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(variant, search, **kw):
+    import lv_slam_b200 as L
+    n = L.NormalDistributionsTransform(variant=variant)
+    n.setTransformationEpsilon(kw.get("trans_eps", 0.01))
+    n.setMaximumIterations(kw.get("max_iter", 64))
+    n.setNeighborhoodSearchMethod(search)
+    n.setResolution(kw.get("resolution", 1.0))
+    n.setStepSize(kw.get("step_size", 0.1))
+    o = O.OracleNDT(variant=variant, resolution=kw.get("resolution", 1.0), step_size=kw.get("step_size", 0.1), trans_eps=kw.get("trans_eps", 0.01),
+                    max_iter=kw.get("max_iter", 64), search=search, num_threads=8)
+    return n, o
+
+
+def _relmax(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _rot_angle(Ra, Rb):
+    """Angle of Ra^T Rb from its skew part (well conditioned near zero, unlike arccos of the trace)."""
+    d = Ra.astype(np.float64).T @ Rb.astype(np.float64)
+    v = 0.5 * np.array([d[2, 1] - d[1, 2], d[0, 2] - d[2, 0], d[1, 0] - d[0, 1]])
+    return float(np.arcsin(min(1.0, np.linalg.norm(v))))
+
+
+def _check_cells(n, o):
+    gc, oc = n.cells(), o.leaves()
+    assert [a.tolist() for a in n.grid()] == [a.tolist() for a in o.grid()]
+    assert np.array_equal(gc["keys"], oc["keys"])                       # every occupied cell, ascending key
+    assert np.array_equal(gc["nr_points"], oc["nr_points"])            # raw count, -1 where the reference invalidates
+    assert np.array_equal(gc["centroid"], oc["centroid"])              # float32 sums in input order: bit-exact
+    assert np.array_equal(gc["weight"], oc["weight"])
+    np.testing.assert_allclose(gc["mean"], oc["mean"], rtol=1e-12, atol=0)
+    valid = oc["nr_points"] >= 6
+    np.testing.assert_allclose(gc["evals"][valid], oc["evals"][valid], rtol=1e-9, atol=1e-300)
+    scale = np.abs(oc["icov"]).reshape(-1, 9).max(axis=1)[:, None, None] + 1e-300
+    assert np.max(np.abs(gc["icov"] - oc["icov"]) / scale) < 1e-9
+    return int(valid.sum())
+
+
+@pytest.mark.parametrize("variant", [O.VAR_OMP, O.VAR_PCA])
+def test_voxel_grid_full_scan(scan_pair, variant):
+    tgt, src, guess, truth = scan_pair
+    n, o = _mk(variant, O.DIRECT7)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    assert _check_cells(n, o) > 1000
+
+
+@pytest.mark.parametrize("resolution", [0.5, 2.0, 0.7])
+def test_voxel_grid_other_leaf_sizes(small_pair, resolution):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_PCA, O.DIRECT7, resolution=resolution)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    _check_cells(n, o)
+
+
+def test_voxel_grid_strided_and_nan_points(small_pair):
+    tgt = small_pair[0]
+    xyzi = np.zeros((tgt.shape[0], 8), np.float32)      # pcl::PointXYZI: 32-byte stride
+    xyzi[:, :3] = tgt
+    xyzi[::97, 1] = np.nan                               # non-finite points are skipped by applyFilter (:215-217)
+    n, o = _mk(O.VAR_OMP, O.DIRECT7)
+    n.setInputTarget(xyzi); o.set_target(xyzi)
+    _check_cells(n, o)
+
+
+def test_lookup_keys_bit_exact(scan_pair):
+    tgt, src, guess, truth = scan_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    n.setInputSource(src); o.set_source(src)
+    for T in (guess, truth.astype(np.float32), np.eye(4, dtype=np.float32)):
+        gk = n.lookup_keys(T)
+        ok = o.lookup_keys(O.transform(src, T))
+        assert np.array_equal(gk, ok)
+        assert (gk >= 0).sum() > 0.9 * len(gk)
+
+
+@pytest.mark.parametrize("variant,search", [(O.VAR_OMP, O.DIRECT7), (O.VAR_PCA, O.DIRECT1), (O.VAR_OMP, O.DIRECT1), (O.VAR_PCA, O.DIRECT7),
+                                            (O.VAR_OMP, O.DIRECT26), (O.VAR_PCA, O.DIRECT26), (O.VAR_OMP, O.KDTREE), (O.VAR_PCA, O.KDTREE)])
+def test_derivatives_match_oracle(small_pair, variant, search):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(variant, search)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    n.setInputSource(src); o.set_source(src)
+    rng = np.random.default_rng(3)
+    p0 = O.se3_log_from_matrix4f(guess)
+    for k in range(3):
+        p = p0 + rng.normal(0, [0.05, 0.05, 0.02, 0.004, 0.004, 0.01])
+        for hess in (True, False):
+            gs, gg, gH = n.eval_derivatives(p, None, hess)
+            os_, og, oH = o.eval_derivatives(p, None, hess)
+            assert abs(gs - os_) <= 1e-9 * abs(os_)
+            assert _relmax(gg, og) < 1e-9
+            if hess:
+                assert _relmax(gH, oH) < 1e-9
+                assert np.max(np.abs(oH - oH.T)) > 0          # the reference's Hessian is NOT symmetric; neither is ours
+            else:
+                assert not gH.any()
+    # explicit transformed cloud that differs from exp(p) (the initial evaluation of computeTransformation)
+    gs, gg, gH = n.eval_derivatives(p0, guess, True)
+    os_, og, oH = o.eval_derivatives(p0, guess, True)
+    assert abs(gs - os_) <= 1e-9 * abs(os_) and _relmax(gg, og) < 1e-9 and _relmax(gH, oH) < 1e-9
+
+
+def test_derivatives_full_scan(scan_pair):
+    tgt, src, guess, truth = scan_pair
+    for variant, search in ((O.VAR_OMP, O.DIRECT7), (O.VAR_PCA, O.DIRECT1)):
+        n, o = _mk(variant, search)
+        n.setInputTarget(tgt); o.set_target(tgt)
+        n.setInputSource(src); o.set_source(src)
+        p = O.se3_log_from_matrix4f(guess)
+        gs, gg, gH = n.eval_derivatives(p, guess, True)
+        os_, og, oH = o.eval_derivatives(p, guess, True)
+        assert abs(gs - os_) <= 1e-9 * abs(os_) and _relmax(gg, og) < 1e-9 and _relmax(gH, oH) < 1e-9
+
+
+def test_double_hessian_and_score_match_oracle(small_pair):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_PCA, O.DIRECT1)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    n.setInputSource(src); o.set_source(src)
+    p = O.se3_log_from_matrix4f(guess)
+    assert _relmax(n.eval_hessian(p), o.eval_hessian(p)) < 1e-10
+    for T in (guess, truth.astype(np.float32)):
+        a, b = n.calculateScore(T), o.calculate_score(T)
+        assert abs(a - b) <= 1e-10 * abs(b)
+
+
+def _check_align(n, o, src, guess):
+    n.setInputSource(src); o.set_source(src)
+    cloud = n.align(guess, want_cloud=True)
+    g = n.result()
+    r = o.align(guess, want_cloud=True)
+    assert g["iterations"] == r["iterations"] and g["converged"] == r["converged"]
+    assert g["n_eval"] == r["n_eval"] and g["n_hess"] == r["n_hess"]
+    gt, rt = g["trace"], r["trace"]
+    assert gt.shape == rt.shape
+    if gt.shape[0]:
+        # per-iteration pose: translation part <= 1e-4 m, rotation part <= 1e-5 rad
+        assert np.max(np.abs(gt[:, 14:17] - rt[:, 14:17])) <= 1e-4
+        assert np.max(np.abs(gt[:, 17:20] - rt[:, 17:20])) <= 1e-5
+        assert np.array_equal(gt[:, 20:22], rt[:, 20:22])         # line-search trials, Hessian recomputation
+    assert np.max(np.abs(g["final"][:3, 3] - r["final"][:3, 3])) <= 1e-4
+    assert _rot_angle(g["final"][:3, :3], r["final"][:3, :3]) <= 1e-5
+    assert abs(g["trans_probability"] - r["trans_probability"]) <= 1e-6 * abs(r["trans_probability"]) + 1e-300
+    if cloud.size:
+        assert np.max(np.abs(cloud - r["cloud"])) <= 2e-4 * max(1.0, float(np.max(np.abs(r["cloud"]))) / 100.0)
+    return g, r
+
+
+@pytest.mark.parametrize("variant,search", [(O.VAR_OMP, O.DIRECT7), (O.VAR_PCA, O.DIRECT1)])
+def test_align_full_scan_matches_oracle(scan_pair, variant, search):
+    tgt, src, guess, truth = scan_pair
+    n, o = _mk(variant, search)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    g, r = _check_align(n, o, src, guess)
+    if variant == O.VAR_OMP:
+        assert np.max(np.abs(g["final"][:3, 3] - truth[:3, 3])) < 0.05    # and it actually registers the pair
+
+
+@pytest.mark.parametrize("variant,search", [(O.VAR_OMP, O.DIRECT1), (O.VAR_OMP, O.DIRECT26), (O.VAR_OMP, O.KDTREE), (O.VAR_PCA, O.DIRECT7)])
+def test_align_small_matches_oracle(small_pair, variant, search):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(variant, search, max_iter=30)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    _check_align(n, o, src, guess)
+
+
+def test_align_line_search_and_double_hessian_path(small_pair):
+    """step_size <= transformation_epsilon / 2 makes the reference's `interval_converged = (step_max - step_min) > 0`
+    false, which is the only way its More-Thuente loop (and the serial all-double computeHessian) ever runs.  Starting
+    next to the optimum with a forced 0.25 m step overshoots, so the loop actually iterates."""
+    tgt, src, guess, truth = small_pair
+    for ss, eps, g0 in ((0.2, 0.5, truth.astype(np.float32)), (0.2, 0.5, guess), (0.1, 0.3, truth.astype(np.float32))):
+        n, o = _mk(O.VAR_OMP, O.DIRECT7, step_size=ss, trans_eps=eps, max_iter=6)
+        n.setInputTarget(tgt); o.set_target(tgt)
+        g, r = _check_align(n, o, src, g0)
+        assert r["n_hess"] > 0 and r["trace"][:, 20].max() > 0
+    n, o = _mk(O.VAR_PCA, O.DIRECT1, step_size=0.2, trans_eps=0.5, max_iter=6)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    g, r = _check_align(n, o, src, truth.astype(np.float32))
+    assert r["n_hess"] > 0
+
+
+def test_align_identity_guess_and_repeat(small_pair):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7, max_iter=20)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    _check_align(n, o, src, np.eye(4, dtype=np.float32))
+    first = n.getFinalTransformation()
+    # the reference nodelet aligns scan 1 a second time from the first result (scan_matching_odom_nodelet.cpp:223-227)
+    _check_align(n, o, src, first)
+
+
+def test_align_is_run_to_run_deterministic(small_pair):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7, max_iter=20)
+    n.setInputTarget(tgt); n.setInputSource(src)
+    n.align(guess); a = n.result()
+    n.align(guess); b = n.result()
+    assert np.array_equal(a["final"], b["final"]) and np.array_equal(a["trace"], b["trace"])
+
+
+def test_edge_cases(small_pair):
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7, max_iter=10)
+    with pytest.raises(L.LvsError) as e:
+        n.align(guess)
+    assert e.value.status == -5                                   # align before setInputTarget
+    n.setInputTarget(tgt); o.set_target(tgt)
+    with pytest.raises(L.LvsError) as e:
+        n.align(guess)
+    assert e.value.status == -6                                   # align before setInputSource
+    # source entirely outside the target box: no neighbours, zero gradient -> delta_p_norm == 0 -> converged, 0 iterations
+    far = (src + np.float32(5000.0)).astype(np.float32)
+    _check_align(n, o, far, np.eye(4, dtype=np.float32))
+    assert n.getFinalNumIteration() == 0 and n.hasConverged()
+    # empty source
+    n.setInputSource(np.zeros((0, 3), np.float32))
+    n.align(guess)
+    assert n.getFinalNumIteration() == 0
+    # a target with fewer than min_points_per_voxel points per cell has no usable cell
+    n.setInputTarget(tgt[:5]); o.set_target(tgt[:5])
+    _check_align(n, o, src, guess)
+    # empty target cloud
+    n.setInputTarget(np.zeros((0, 3), np.float32))
+    n.setInputSource(src)
+    n.align(guess)
+    assert n.getFinalNumIteration() == 0
+    # ragged sizes that are not multiples of the CTA tile
+    for cnt in (1, 31, 257, 1025):
+        n.setInputTarget(tgt); o.set_target(tgt)
+        _check_align(n, o, src[:cnt], guess)
+
+
+def test_set_resolution_revoxelises(small_pair):
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7)
+    n.setInputTarget(tgt); o.set_target(tgt)
+    n.setResolution(0.5); o.set(resolution=0.5)                   # ndt_omp.h:126-136
+    _check_cells(n, o)
+
+
+def test_batch_matches_single(small_pair, scan_pair):
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    tgt2, src2 = scan_pair[0][::3].copy(), scan_pair[1][::3].copy()
+    b = L.NdtBatch(2, 3, transformation_epsilon=0.01, max_iterations=30, search_method=L.LVS_DIRECT7)
+    b.set_target(0, tgt); b.set_target(1, tgt2)
+    b.set_source(0, src); b.set_source(1, src2); b.set_source(2, src[:4000])
+    g2 = guess.copy(); g2[0, 3] = 1.0
+    pairs = [(0, 0, guess), (1, 1, scan_pair[2]), (2, 0, g2), (0, 0, g2), (1, 1, np.eye(4, dtype=np.float32))]
+    res = b.align([p[0] for p in pairs], [p[1] for p in pairs], [p[2] for p in pairs])
+    srcs, tgts = [src, src2, src[:4000]], [tgt, tgt2]
+    for (s, t, g), r in zip(pairs, res):
+        o = O.OracleNDT(variant=O.VAR_OMP, trans_eps=0.01, max_iter=30, search=O.DIRECT7, num_threads=8)
+        o.set_target(tgts[t]); o.set_source(srcs[s])
+        ref = o.align(g)
+        assert r["iterations"] == ref["iterations"] and r["converged"] == ref["converged"]
+        assert np.max(np.abs(r["final"][:3, 3] - ref["final"][:3, 3])) <= 1e-4
+        assert _rot_angle(r["final"][:3, :3], ref["final"][:3, :3]) <= 1e-5
+
+
+def test_device_resident_inputs(small_pair):
+    import torch
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7, max_iter=20)
+    n.setInputTarget(torch.from_numpy(tgt).cuda()); o.set_target(tgt)
+    o.set_source(src)
+    n.setInputSource(torch.from_numpy(src).cuda())
+    n.align(guess)
+    r = o.align(guess)
+    assert n.getFinalNumIteration() == r["iterations"]
+    assert np.max(np.abs(n.getFinalTransformation() - r["final"])) <= 1e-4
