@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — NDT scan-pair aligns/sec on the synthetic 64-beam scan stream (BASELINE.json configs[1]).
+
+A step = one pass of the hot path over one batch of the stream: voxelise every keyframe target the batch needs
+(setInputTarget), stage every scan (setInputSource) and run all scan-to-keyframe aligns of the batch in one batched call
+(pclomp semantics: DIRECT7, 1.0 m voxels, epsilon 0.01, <= 64 iterations; constant-velocity guesses as in
+src/lidar_odometry/scan_matching_odom_nodelet.cpp:249-250).  `value` is timed with the raw clouds already in HBM,
+`e2e` goes through the C-ABI from pinned host buffers with the H2D copies and the result read-back inside the timed region.
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference [...]                     # the reference's CPU path (oracle restatement, OpenMP)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ndt_scan_pair_aligns_per_sec"
+UNIT = "aligns/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="scan pairs per step per GPU")
+    ap.add_argument("--variant", default="omp", choices=["omp", "pca"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs timed for cpu_baseline (0 = sized for ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(batch, rank):
+    """Frames [rank*span, rank*span + batch + 2) of the synthetic drive, seed 1000."""
+    from lv_slam_b200 import synth
+    start = rank * (batch + 2)
+    scans, poses = synth.stream(batch + 2, seed=1000, start=start)
+    plan = synth.keyframe_plan(poses)[:batch]
+    keys = sorted({k for _, k, _ in plan})
+    return scans, poses, plan, keys
+
+
+def variant_params(variant):
+    # lidar odometry: pclpca / DIRECT1 (scan_matching_odom_nodelet.cpp:109-119); loop closure + BASELINE config 0: pclomp / DIRECT7
+    if variant == "pca":
+        return dict(variant=1, search_method=3)
+    return dict(variant=0, search_method=2)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def oracle_for(variant):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ndt as O  # the checker; only the cpu_baseline / --impl reference legs reach this
+    vp = variant_params(variant)
+    threads = os.cpu_count() or 1
+    o = O.OracleNDT(variant=vp["variant"], resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=64,
+                    search={2: O.DIRECT7, 3: O.DIRECT1}[vp["search_method"]], num_threads=threads)
+    return o, threads
+
+
+def run_cpu_pairs(o, scans, plan, idx):
+    """Times the CPU path over plan[idx]: setInputTarget when the keyframe changes + setInputSource + align."""
+    cur_key = None
+    t0 = time.perf_counter()
+    finals = []
+    for i in idx:
+        f, k, g = plan[i]
+        if k != cur_key:
+            o.set_target(scans[k]); cur_key = k
+        o.set_source(scans[f])
+        finals.append(o.align(g)["final"])
+    return time.perf_counter() - t0, finals
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scans, poses, plan, keys = make_workload(args.batch, 0)
+    o, threads = oracle_for(args.variant)
+    sample = list(range(min(4, len(plan))))
+    for _ in range(args.warmup):
+        run_cpu_pairs(o, scans, plan, sample)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = run_cpu_pairs(o, scans, plan, sample)
+        t += dt
+    ms = 1e3 * t / args.steps
+    val = len(sample) / (ms / 1e3)
+    n_pts = int(np.mean([scans[f].shape[0] for f, _, _ in plan]))
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": workload_config(args, n_pts, len(keys)),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d scan pairs of the step's batch per step (1 keyframe voxelisation + %d aligns)" % (len(sample), len(sample))},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_pts, n_keys):
+    vp = variant_params(args.variant)
+    return {"workload": "synthetic 64-beam scan stream, scan-to-keyframe NDT (BASELINE configs[1])", "pairs_per_step_per_gpu": args.batch,
+            "keyframes_per_step_per_gpu": n_keys, "points_per_scan": n_pts, "resolution_m": 1.0,
+            "registration": "pclomp/DIRECT7" if vp["variant"] == 0 else "pclpca/DIRECT1", "transformation_epsilon": 0.01, "max_iterations": 64,
+            "l2_policy": "inputs larger than L2 (%.0f MB of clouds per step vs 126 MB L2)" % ((args.batch + n_keys) * n_pts * 16 / 1e6)}
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lv_slam_b200 as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scans, poses, plan, keys = make_workload(args.batch, rank)
+    B = len(plan)
+    key_slot = {k: i for i, k in enumerate(keys)}
+    n_pts = int(np.mean([scans[f].shape[0] for f, _, _ in plan]))
+    vp = variant_params(args.variant)
+    stream = torch.cuda.Stream()
+    nb = L.NdtBatch(len(keys), B, device=local_rank, stream=stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64, **vp)
+    src_slots = list(range(B))
+    tgt_slots = [key_slot[k] for _, k, _ in plan]
+    guesses = [g for _, _, g in plan]
+
+    # resident copies (value) and pinned host copies (e2e)
+    dev_src = [torch.from_numpy(scans[f]).cuda() for f, _, _ in plan]
+    dev_tgt = [torch.from_numpy(scans[k]).cuda() for k in keys]
+    pin_src = [torch.from_numpy(scans[f]).pin_memory() for f, _, _ in plan]
+    pin_tgt = [torch.from_numpy(scans[k]).pin_memory() for k in keys]
+
+    def step(src, tgt):
+        for i, t in enumerate(tgt):
+            nb.set_target(i, t)
+        for i, s in enumerate(src):
+            nb.set_source(i, s)
+        return nb.align(src_slots, tgt_slots, guesses)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, tgt, steps, profile):
+        nb.set_profiling(profile)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = nb.total_launches()
+        kern_ms, kern_launches, n_eval_total, res = 0.0, 0, 0, None
+        barrier()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                res = step(src, tgt)
+                st = nb.last_stats()
+                kern_ms += st["deriv_kernel_ms"]; kern_launches += st["deriv_launches"]
+                n_eval_total += sum(r["n_eval"] for r in res)
+            ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        nb.set_profiling(0)
+        return ms / steps, nb.total_launches() - launches0, kern_ms, kern_launches, n_eval_total, res
+
+    # warm-up (both paths), then the timed regions
+    timed(dev_src, dev_tgt, args.warmup, 0)
+    timed(pin_src, pin_tgt, max(1, args.warmup // 2), 0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches, kern_ms, kern_launches, n_eval_total, res = timed(dev_src, dev_tgt, args.steps, 1)
+    clocks = sampler.stop()
+    xfer0 = nb.transfer_bytes()
+    ms_e2e, _, _, _, _, res_e2e = timed(pin_src, pin_tgt, args.steps, 0)
+    xfer1 = nb.transfer_bytes()
+    h2d_bytes, d2h_bytes = (xfer1[0] - xfer0[0]) // args.steps, (xfer1[1] - xfer0[1]) // args.steps
+
+    # sanity: the aligns registered the stream (pose error against the generator's ground truth)
+    err_t = max(float(np.abs(r["final"][:3, 3] - (np.linalg.inv(poses[k]) @ poses[f])[:3, 3]).max()) for r, (f, k, _) in zip(res, plan))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the derivative kernel: SURVEY.md §8d algorithmic bytes = 16 B per source point + 48 B per usable voxel, per evaluation
+    bytes_total = 0.0
+    for r, (f, k, _) in zip(res, plan):
+        n_valid = nb.num_cells(key_slot[k])[1]
+        bytes_total += r["n_eval"] * (16.0 * scans[f].shape[0] + 48.0 * n_valid)
+    bytes_total *= args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_total / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ndt_eval_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "ndt_eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": bytes_total / max(kern_launches, 1), "avg_launch_ms": kern_ms / max(kern_launches, 1),
+                "launches_timed": kern_launches, "kernel_share_of_step": kern_ms / (ms_dev * args.steps),
+                "note": "the kernel is FP32/FP64-issue bound, not HBM bound (float32 per-point math in the reference's exact operation order, 43 fp64 sums per term); see DESIGN.md"}
+
+    line = {"metric": METRIC, "value": world * B / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": workload_config(args, n_pts, len(keys)), "clocks": clocks,
+            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "evaluations_per_align": n_eval_total / (args.steps * B), "max_translation_error_vs_truth_m": err_t}
+
+    if world == 1 and not args.no_cpu_baseline:
+        o, threads = oracle_for(args.variant)
+        dt1, _ = run_cpu_pairs(o, scans, plan, [0])
+        n = args.cpu_sample or int(max(2, min(B, 15.0 / max(dt1, 1e-3))))
+        dt, finals = run_cpu_pairs(o, scans, plan, list(range(n)))
+        dev = max(float(np.abs(finals[i] - res[i]["final"]).max()) for i in range(n))
+        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "first %d scan pairs of the step's batch (keyframe voxelisations + aligns), %.1f s" % (n, dt),
+                                "max_abs_final_transform_diff_vs_gpu": dev}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -151,6 +151,8 @@ int lvs_ndt_batch_set_profiling(lvs_ndt_batch_t* b, int on);
 int lvs_ndt_batch_set_tuning(lvs_ndt_batch_t* b, int blocks_per_pair, int chunk_first, int chunk_next);
 /* Kernel launches issued by this object since creation (voxelisation, evaluation, packing). */
 int lvs_ndt_batch_total_launches(lvs_ndt_batch_t* b, long long* launches);
+/* Bytes this object has copied host->device and device->host since creation (clouds, pair states, results). */
+int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* d2h);
 int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int target_slot, int* n_cells, int* n_valid);
 /* The batch object that backs a single registration handle (1 target slot, 1 source slot). */
 int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out);

@@ -69,7 +69,7 @@ def lib():
             "lvs_ndt_batch_set_target": [vp, i32, vp, sz, sz, i32], "lvs_ndt_batch_set_source": [vp, i32, vp, sz, sz, i32],
             "lvs_ndt_batch_align": [vp, i32, vp, vp, vp, vp], "lvs_ndt_batch_last_stats": [vp, vp, vp, vp, vp],
             "lvs_ndt_batch_set_profiling": [vp, i32], "lvs_ndt_batch_set_tuning": [vp, i32, i32, i32],
-            "lvs_ndt_batch_total_launches": [vp, vp], "lvs_ndt_batch_num_cells": [vp, i32, vp, vp],
+            "lvs_ndt_batch_total_launches": [vp, vp], "lvs_ndt_batch_transfer_bytes": [vp, vp, vp], "lvs_ndt_batch_num_cells": [vp, i32, vp, vp],
         }.items():
             f = getattr(L, name)
             f.restype = i32

@@ -97,6 +97,7 @@ struct lvs_ndt_batch {
   double last_device_ms = 0, last_deriv_ms = 0;
   int last_launches = 0, last_deriv_launches = 0;
   long total_launches = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0;   // bytes this object copied across PCIe since creation
   int blocks_per_pair_override = 0;
   int chunk_first = 6, chunk_next = 4;
 };
@@ -133,6 +134,7 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
       b->stage_cap = cap;
     }
     CUDA_TRY(cudaMemcpyAsync(b->d_stage, xyz, bytes, cudaMemcpyHostToDevice, b->st));
+    b->h2d_bytes += (long long)bytes;
     d_in = b->d_stage;
   }
   int rc = pack_points(b->st, d_in, stride_bytes / 4, (int)n, slot.d_pts);
@@ -185,7 +187,8 @@ static PairDesc make_pair(lvs_ndt_batch* b, int src_slot, int tgt_slot) {
 
 static int choose_bpp(lvs_ndt_batch* b, int n_pairs, int max_src) {
   if (b->blocks_per_pair_override > 0) return b->blocks_per_pair_override;
-  int by_points = std::max(1, (max_src + 255) / 256);                          // one point per thread
+  const int ppi = eval_points_per_cta_iteration();
+  int by_points = std::max(1, (max_src + ppi - 1) / ppi);                      // one warp iteration per warp
   int resident = 148 * eval_max_resident_ctas_per_sm();                        // one full wave of CTAs
   int by_machine = std::max(1, (resident + n_pairs - 1) / n_pairs);
   return std::max(1, std::min(by_points, std::max(by_machine, 4)));
@@ -213,6 +216,7 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
   CUDA_TRY(cudaEventRecord(b->ev_begin, b->st));
   CUDA_TRY(cudaMemcpyAsync(b->d_pairs, b->h_pairs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, b->st));
   CUDA_TRY(cudaMemcpyAsync(b->d_states, b->h_states, n_pairs * sizeof(AlignState), cudaMemcpyHostToDevice, b->st));
+  b->h2d_bytes += (long long)n_pairs * (sizeof(PairDesc) + sizeof(AlignState));
   CUDA_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int), b->st));
   EvalLaunch L;
   L.d_pairs = b->d_pairs; L.d_states = b->d_states; L.d_trace = b->trace_on ? b->d_trace : nullptr;
@@ -243,11 +247,13 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
       launches++;
     }
     CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
+    b->d2h_bytes += sizeof(int);
     CUDA_TRY(cudaStreamSynchronize(b->st));
     if (*b->h_done >= n_pairs) break;
     chunk = b->chunk_next;
   }
   CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, n_pairs * sizeof(AlignState), cudaMemcpyDeviceToHost, b->st));
+  b->d2h_bytes += (long long)n_pairs * sizeof(AlignState);
   CUDA_TRY(cudaEventRecord(b->ev_end, b->st));
   CUDA_TRY(cudaStreamSynchronize(b->st));
   if (*b->h_done < n_pairs) return fail(LVS_ERR_CUDA, "align state machine did not finish within %d evaluation launches", max_launches);
@@ -367,6 +373,7 @@ static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   if ((rc = upload_cloud(b, b->target_pts[slot], xyz, n, stride_bytes, on_device))) return rc;
   rc = b->targets[slot].build(b->st, b->target_pts[slot].d_pts, (int)n, b->prm, b->ws);
   b->total_launches += b->targets[slot].launches_last_build;
+  b->d2h_bytes += 2 * (long long)sizeof(GridParams);   // grid geometry read back to size the dense index grid
   return rc;
 }
 
@@ -502,6 +509,13 @@ int lvs_ndt_batch_set_tuning(lvs_ndt_batch_t* b, int blocks_per_pair, int chunk_
 int lvs_ndt_batch_total_launches(lvs_ndt_batch_t* b, long long* launches) {
   if (!b || !launches) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
   *launches = b->total_launches;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* d2h) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (h2d) *h2d = b->h2d_bytes;
+  if (d2h) *d2h = b->d2h_bytes;
   return LVS_OK;
 }
 

@@ -98,104 +98,158 @@ __device__ __forceinline__ bool contribute_tile(float* __restrict__ col /* tile 
   return true;
 }
 
-template <bool HESS, int MODE /* LVS_DIRECT1 / 7 / 26 */, bool PCA>
-__device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2,
-                                           double gd1, float* s_tile, double* s_w, double* s_red, double* partial) {
+// Per-warp staging in shared memory (dynamic, carved up in SmemLayout):
+//   tile [43][33] f32   float contributions of one round of 32 (point, cell) pairs
+//   pts  [6][64]  f32   x', y', z' (transformed point) and R*x of the 64 points of the current warp iteration
+//   q    [256]    i32   queue of hits: record index * 64 + point slot
+//   qw   [256]    f64   ndt_pca only: weight that multiplies the entry's contribution
+constexpr int kPtsPerLane = 2;
+constexpr int kPtsPerIter = 32 * kPtsPerLane;
+constexpr int kQueueCap = 256;
+constexpr int kTileFloats = kAcc * kTileStride;
+
+struct SmemLayout {
+  static constexpr size_t tile_off = 0;
+  static constexpr size_t pts_off = tile_off + sizeof(float) * kWarps * kTileFloats;
+  static constexpr size_t q_off = pts_off + sizeof(float) * kWarps * 6 * kPtsPerIter;
+  static constexpr size_t qw_off = q_off + sizeof(int) * kWarps * kQueueCap;          // 8-byte aligned (all terms are multiples of 8)
+  static constexpr size_t bytes_omp = qw_off;
+  static constexpr size_t bytes_pca = qw_off + sizeof(double) * kWarps * kQueueCap;
+};
+static_assert(SmemLayout::qw_off % 8 == 0, "qw must be 8-byte aligned");
+static_assert(sizeof(double) * kWarps * kAcc * 4 <= SmemLayout::pts_off, "the CTA reduction scratch aliases the tile region");
+
+// One round: lanes e < n_round take queue entries q[head + lane], stage their float contributions in the tile, then the
+// warp adds the round into its fp64 accumulators.
+template <bool HESS, bool PCA>
+__device__ __forceinline__ void process_round(double* acc, const PairDesc& P, const float* pts, const int* q, const double* qw, float* tile,
+                                              int head, int n_round, float gd2, double gd1) {
   using Sh = Shape<HESS>;
-  constexpr int K = MODE == LVS_DIRECT1 ? 1 : (MODE == LVS_DIRECT7 ? 7 : 26);
+  const int lane = threadIdx.x & 31;
+  bool used = false;
+  double w = 0.0;
+  if (lane < n_round) {
+    const int ent = q[head + lane];
+    const int rec = ent / kPtsPerIter, slot = ent % kPtsPerIter;
+    const VoxelRec* vr = P.recs + rec;
+    const double2 m01 = __ldg(reinterpret_cast<const double2*>(vr));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(vr) + 1);   // mean[2] (8 B) + icov[0..1]
+    const float4 q2 = __ldg(reinterpret_cast<const float4*>(vr) + 2);   // icov[2..5]
+    const float4 q3 = __ldg(reinterpret_cast<const float4*>(vr) + 3);   // icov[6..8] + meta
+    const double m2 = __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x));
+    const float C[9] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z};
+    const float tx = pts[0 * kPtsPerIter + slot], ty = pts[1 * kPtsPerIter + slot], tz = pts[2 * kPtsPerIter + slot];
+    const float d0 = (float)((double)tx - m01.x), d1 = (float)((double)ty - m01.y), d2 = (float)((double)tz - m2);
+    used = contribute_tile<HESS>(tile + lane, pts[3 * kPtsPerIter + slot], pts[4 * kPtsPerIter + slot], pts[5 * kPtsPerIter + slot], d0, d1, d2, C,
+                                 gd2, gd1);
+    if (PCA) w = qw[head + lane];
+  }
+  const unsigned umask = __ballot_sync(0xffffffffu, used);
+  if (!used && umask != 0u) {
+#pragma unroll
+    for (int o = 0; o < Sh::NV; o++) tile[o * kTileStride + lane] = 0.0f;
+  }
+  __syncwarp();
+  if (umask != 0u) {
+#pragma unroll
+    for (int t = 0; t < Sh::TPL; t++) {
+      const int task = lane + 32 * t;
+      const int o = task >> 2, g = task & 3;
+      const bool live = task < Sh::NTASK && ((umask >> (8 * g)) & 0xffu) != 0u;
+      const float* row = tile + (task < Sh::NTASK ? o : 0) * kTileStride + 8 * g;
+      double a = acc[t];
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) {
+        if (PCA) {
+          const double wj = __shfl_sync(0xffffffffu, w, 8 * g + jj);   // all 32 lanes take part in the shuffle
+          if (live) a += (double)row[jj] * wj;
+        } else {
+          if (live) a += (double)row[jj];
+        }
+      }
+      acc[t] = a;
+    }
+  }
+  __syncwarp();
+}
+
+template <bool HESS, bool PCA>
+__device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, int mode,
+                                           float gd2, double gd1, unsigned char* s_dyn, double* partial) {
+  using Sh = Shape<HESS>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = s_tile + warp * (kAcc * kTileStride);
-  double* wts = s_w + warp * 32;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float* tile = reinterpret_cast<float*>(s_dyn + SmemLayout::tile_off) + warp * kTileFloats;
+  float* pts = reinterpret_cast<float*>(s_dyn + SmemLayout::pts_off) + warp * (6 * kPtsPerIter);
+  int* q = reinterpret_cast<int*>(s_dyn + SmemLayout::q_off) + warp * kQueueCap;
+  double* qw = reinterpret_cast<double*>(s_dyn + SmemLayout::qw_off) + warp * kQueueCap;   // only mapped for ndt_pca launches
+  const int K = mode == LVS_DIRECT1 ? 1 : (mode == LVS_DIRECT7 ? 7 : 26);
   double acc[Sh::TPL];
 #pragma unroll
   for (int t = 0; t < Sh::TPL; t++) acc[t] = 0.0;
 
   if (!G.empty) {
-    for (int base = (blk * kWarps + warp) * 32; base < P.n_src; base += bpp * kEvalThreads) {
-      const int i = base + lane;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      float tx = 0.f, ty = 0.f, tz = 0.f;
-      bool ok = i < P.n_src;
-      if (ok) {
-        s = __ldg(P.src + i);
-        transform_point(T, s.x, s.y, s.z, tx, ty, tz);
-        ok = isfinite(tx) && isfinite(ty) && isfinite(tz);
-      }
-      const int cx = (int)floorf(tx / G.leaf), cy = (int)floorf(ty / G.leaf), cz = (int)floorf(tz / G.leaf);
-      int rec[K];
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        int ox = 0, oy = 0, oz = 0;
-        if (MODE == LVS_DIRECT7) { ox = c_off7[k][0]; oy = c_off7[k][1]; oz = c_off7[k][2]; }
-        if (MODE == LVS_DIRECT26) { ox = c_off26[k][0]; oy = c_off26[k][1]; oz = c_off26[k][2]; }
-        const int ix = cx + ox, iy = cy + oy, iz = cz + oz;
-        int v = -1;
-        if (ok && ix >= G.min_b[0] && ix <= G.max_b[0] && iy >= G.min_b[1] && iy <= G.max_b[1] && iz >= G.min_b[2] && iz <= G.max_b[2])
-          v = __ldg(P.grid + ((ix - G.min_b[0]) * G.mul[0] + (iy - G.min_b[1]) * G.mul[1] + (iz - G.min_b[2]) * G.mul[2]));
-        rec[k] = v;
-      }
-      // x_t = float(SE3::exp(p).matrix()) * [x, 0]: rotation only (:507-508)
-      const float xr = (R[0] * s.x + R[1] * s.y) + R[2] * s.z;
-      const float yr = (R[3] * s.x + R[4] * s.y) + R[5] * s.z;
-      const float zr = (R[6] * s.x + R[7] * s.y) + R[8] * s.z;
-      // ndt_pca multiplies the RUNNING per-point sums by each cell's weight (:293-296): the contribution of cell k ends up
-      // scaled by the product of the weights of cells k..last.
-      double wsuf[PCA ? K : 1];
-      if (PCA) {
+    for (int base = (blk * kWarps + warp) * kPtsPerIter; base < P.n_src; base += bpp * kWarps * kPtsPerIter) {
+      // ---- phase A: transform, probe the index grid, queue every (point, cell) hit of the warp's 64 points
+      int nq = 0;
+      for (int h = 0; h < kPtsPerLane; h++) {
+        const int slot = h * 32 + lane;
+        const int i = base + slot;
+        float tx = 0.f, ty = 0.f, tz = 0.f;
+        bool ok = i < P.n_src;
+        if (ok) {
+          const float4 s = __ldg(P.src + i);
+          transform_point(T, s.x, s.y, s.z, tx, ty, tz);
+          ok = isfinite(tx) && isfinite(ty) && isfinite(tz);
+          pts[0 * kPtsPerIter + slot] = tx; pts[1 * kPtsPerIter + slot] = ty; pts[2 * kPtsPerIter + slot] = tz;
+          // x_t = float(SE3::exp(p).matrix()) * [x, 0]: rotation only (ndt_omp_impl2.hpp:507-508)
+          pts[3 * kPtsPerIter + slot] = (R[0] * s.x + R[1] * s.y) + R[2] * s.z;
+          pts[4 * kPtsPerIter + slot] = (R[3] * s.x + R[4] * s.y) + R[5] * s.z;
+          pts[5 * kPtsPerIter + slot] = (R[6] * s.x + R[7] * s.y) + R[8] * s.z;
+        }
+        const int cx = (int)floorf(tx / G.leaf), cy = (int)floorf(ty / G.leaf), cz = (int)floorf(tz / G.leaf);
+        // ndt_pca multiplies the RUNNING per-point sums by each cell's weight (ndt_pca_impl2.hpp:293-296): the contribution of
+        // cell k ends up scaled by the product of the weights of cells k..last, hence the probes run last-to-first.
         double run = 1.0;
-#pragma unroll
         for (int k = K - 1; k >= 0; k--) {
-          if (rec[k] >= 0) run *= (double)(__ldg(&P.recs[rec[k]].meta) & kMetaWeightMask);
-          wsuf[k] = run;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        const bool hit = rec[k] >= 0;
-        if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
-        bool used = false;
-        if (hit) {
-          const VoxelRec* vr = P.recs + rec[k];
-          const double2 m01 = __ldg(reinterpret_cast<const double2*>(vr));
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(vr) + 1);   // mean[2] (8 B) + icov[0..1]
-          const float4 q2 = __ldg(reinterpret_cast<const float4*>(vr) + 2);   // icov[2..5]
-          const float4 q3 = __ldg(reinterpret_cast<const float4*>(vr) + 3);   // icov[6..8] + meta
-          const double m2 = __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x));
-          const float C[9] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z};
-          const float d0 = (float)((double)tx - m01.x), d1 = (float)((double)ty - m01.y), d2 = (float)((double)tz - m2);
-          used = contribute_tile<HESS>(tile + lane, xr, yr, zr, d0, d1, d2, C, gd2, gd1);
-        }
-        if (!used) {
-#pragma unroll
-          for (int o = 0; o < Sh::NV; o++) tile[o * kTileStride + lane] = 0.0f;
-        }
-        if (PCA) wts[lane] = used ? wsuf[k] : 0.0;
-        const unsigned umask = __ballot_sync(0xffffffffu, used);   // also orders the tile writes before the reads below
-        __syncwarp();
-        if (umask != 0u) {
-#pragma unroll
-          for (int t = 0; t < Sh::TPL; t++) {
-            const int task = lane + 32 * t;
-            if (task < Sh::NTASK) {
-              const int o = task >> 2, g = task & 3;
-              if ((umask >> (8 * g)) & 0xffu) {
-                const float* row = tile + o * kTileStride + 8 * g;
-                double a = acc[t];
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                  if (PCA) a += (double)row[jj] * wts[8 * g + jj];
-                  else a += (double)row[jj];
-                }
-                acc[t] = a;
-              }
-            }
+          int ox = 0, oy = 0, oz = 0;
+          if (mode == LVS_DIRECT7) { ox = c_off7[k][0]; oy = c_off7[k][1]; oz = c_off7[k][2]; }
+          else if (mode == LVS_DIRECT26) { ox = c_off26[k][0]; oy = c_off26[k][1]; oz = c_off26[k][2]; }
+          const int ix = cx + ox, iy = cy + oy, iz = cz + oz;
+          int v = -1;
+          if (ok && ix >= G.min_b[0] && ix <= G.max_b[0] && iy >= G.min_b[1] && iy <= G.max_b[1] && iz >= G.min_b[2] && iz <= G.max_b[2])
+            v = __ldg(P.grid + ((ix - G.min_b[0]) * G.mul[0] + (iy - G.min_b[1]) * G.mul[1] + (iz - G.min_b[2]) * G.mul[2]));
+          const bool hit = v >= 0;
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (m == 0u) continue;
+          if (nq > kQueueCap - 32) {
+            // queue nearly full (dense DIRECT26 neighbourhoods): drain whole rounds, keep the remainder at the front
+            __syncwarp();
+            int head = 0;
+            for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, P, pts, q, qw, tile, head, 32, gd2, gd1);
+            const int rem = nq - head;
+            int ent = 0; double we = 0.0;
+            if (lane < rem) { ent = q[head + lane]; if (PCA) we = qw[head + lane]; }
+            __syncwarp();
+            if (lane < rem) { q[lane] = ent; if (PCA) qw[lane] = we; }
+            nq = rem;
           }
+          if (hit) {
+            const int pos = nq + __popc(m & lt_mask);
+            q[pos] = v * kPtsPerIter + slot;
+            if (PCA) { run *= (double)(__ldg(&P.recs[v].meta) & kMetaWeightMask); qw[pos] = run; }
+          }
+          nq += __popc(m);
         }
-        __syncwarp();
       }
+      __syncwarp();
+      // ---- phase B: rounds of 32 queued (point, cell) contributions
+      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, P, pts, q, qw, tile, head, min(32, nq - head), gd2, gd1);
     }
   }
-  // CTA partial: s_red[warp][task] -> output o sums its 4 groups over the 8 warps in fixed order
+  // CTA partial: s_red[warp][task] (aliases the tile region) -> output o sums its 4 groups over the 8 warps in fixed order
+  __syncthreads();
+  double* s_red = reinterpret_cast<double*>(s_dyn);
 #pragma unroll
   for (int t = 0; t < Sh::TPL; t++) {
     const int task = lane + 32 * t;
@@ -212,9 +266,6 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
   }
 }
 
-constexpr int kTileFloats = kWarps * kAcc * kTileStride;                       // 11 352 floats = 45 408 B
-constexpr size_t kHotSmem = kTileFloats * sizeof(float) + kWarps * 32 * sizeof(double) + kWarps * kAcc * 4 * sizeof(double);
-
 __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ float s_T[16], s_R[9];
@@ -225,9 +276,6 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const AlignConsts& c = L.consts;
   if (kind != EVAL_DERIV_H && kind != EVAL_DERIV_NOH) return;
   if (c.search == LVS_KDTREE) return;                      // radius-search derivatives live in the cold kernel
-  double* s_red = reinterpret_cast<double*>(s_dyn);                                   // [8][172]
-  double* s_w = s_red + kWarps * kAcc * 4;                                            // [8][32]
-  float* s_tile = reinterpret_cast<float*>(s_w + kWarps * 32);                        // [8][43][33]
   const PairDesc P = L.d_pairs[pair];
   if (threadIdx.x < 16) s_T[threadIdx.x] = S.T[threadIdx.x];
   if (threadIdx.x < 9) s_R[threadIdx.x] = S.Rj[threadIdx.x];
@@ -237,40 +285,32 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const bool pca = c.variant == LVS_NDT_PCA;
   double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
   const int bpp = L.blocks_per_pair;
-
-#define LVS_RUN(HESS, MODE)                                                                                              \
-  do {                                                                                                                   \
-    if (pca) run_direct<HESS, MODE, true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_tile, s_w, s_red, partial);       \
-    else run_direct<HESS, MODE, false>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_tile, s_w, s_red, partial);          \
-  } while (0)
   if (kind == EVAL_DERIV_H) {
-    if (c.search == LVS_DIRECT1) LVS_RUN(true, LVS_DIRECT1);
-    else if (c.search == LVS_DIRECT7) LVS_RUN(true, LVS_DIRECT7);
-    else LVS_RUN(true, LVS_DIRECT26);
+    if (pca) run_direct<true, true>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
+    else run_direct<true, false>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
   } else {
-    if (c.search == LVS_DIRECT1) LVS_RUN(false, LVS_DIRECT1);
-    else if (c.search == LVS_DIRECT7) LVS_RUN(false, LVS_DIRECT7);
-    else LVS_RUN(false, LVS_DIRECT26);
+    if (pca) run_direct<false, true>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
+    else run_direct<false, false>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
   }
-#undef LVS_RUN
-  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_src, s_red, &s_last);
+  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_src, reinterpret_cast<double*>(s_dyn), &s_last);
 }
 
 int launch_eval(cudaStream_t st, const EvalLaunch& L) {
   if (L.n_pairs <= 0) return LVS_OK;
-  static bool attr_set = false;   // per-process; the attribute is per-device but every B200 is configured identically on first use
-  static int attr_dev = -1;
+  static int attr_dev = -1;     // the opt-in shared-memory size is a per-device function attribute
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
-  if (!attr_set || attr_dev != dev) {
-    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHotSmem));
-    attr_set = true; attr_dev = dev;
+  if (attr_dev != dev) {
+    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::bytes_pca));
+    attr_dev = dev;
   }
-  ndt_eval_kernel<<<L.n_pairs * L.blocks_per_pair, kEvalThreads, kHotSmem, st>>>(L);
+  const size_t smem = L.consts.variant == LVS_NDT_PCA ? SmemLayout::bytes_pca : SmemLayout::bytes_omp;
+  ndt_eval_kernel<<<L.n_pairs * L.blocks_per_pair, kEvalThreads, smem, st>>>(L);
   CUDA_TRY(cudaGetLastError());
   return LVS_OK;
 }
 
 int eval_max_resident_ctas_per_sm() { return 3; }
+int eval_points_per_cta_iteration() { return kWarps * kPtsPerIter; }
 
 }  // namespace lvs

@@ -74,6 +74,7 @@ struct EvalLaunch {
 int launch_eval(cudaStream_t st, const EvalLaunch& L);        // direct-search derivative passes (hot)
 int launch_eval_cold(cudaStream_t st, const EvalLaunch& L);   // KDTREE-mode derivatives and the all-double Hessian pass
 int eval_max_resident_ctas_per_sm();
+int eval_points_per_cta_iteration();
 int launch_calc_score(cudaStream_t st, const PairDesc& pair, const float* d_T16, const AlignConsts& c, double* d_partials, int max_blocks,
                       unsigned int* d_ticket, double* d_out);
 int launch_lookup_keys(cudaStream_t st, const PairDesc& pair, const float* d_T16, int* d_keys_out);

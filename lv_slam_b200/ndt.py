@@ -260,6 +260,11 @@ class NdtBatch:
         C.check(self._L.lvs_ndt_batch_total_launches(self._h, ctypes.byref(n)))
         return n.value
 
+    def transfer_bytes(self):
+        a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        C.check(self._L.lvs_ndt_batch_transfer_bytes(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def num_cells(self, slot):
         a, b = ctypes.c_int(0), ctypes.c_int(0)
         C.check(self._L.lvs_ndt_batch_num_cells(self._h, slot, ctypes.byref(a), ctypes.byref(b)))

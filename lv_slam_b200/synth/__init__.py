@@ -74,3 +74,34 @@ def config1_pair(n_beams=64, n_az=2000, seed=42):
     guess[0, 3] = 1.5
     truth = np.linalg.inv(pose_matrix(p0)) @ pose_matrix(p1)
     return tgt, src, guess, truth
+
+
+def stream(n_frames, seed=1000, n_beams=64, n_az=2000, start=0):
+    """Frames ``start .. start+n_frames-1`` of the synthetic drive (configs 2 / 5): returns (scans, poses4x4)."""
+    scans, poses = [], []
+    for f in range(start, start + n_frames):
+        p = traj_pose(f)
+        scans.append(scan(seed, f, p, n_beams, n_az))
+        poses.append(pose_matrix(p))
+    return scans, poses
+
+
+def keyframe_plan(poses, delta_trans=10.0, delta_angle=0.17, delta_frames=10):
+    """Scan-to-keyframe schedule of ``matching_s2k`` (src/lidar_odometry/scan_matching_odom_nodelet.cpp:236-250) replayed on
+    known poses: frame 0 is the first keyframe; a frame whose motion from the current keyframe exceeds 10 m / 0.17 rad /
+    1 s (10 frames at 10 Hz; launch/dlo_lfa_ggo_kitti.launch:51-53) becomes the next keyframe after being matched.
+    Returns a list of (frame, key_frame, guess4x4) for frames >= 2; the guess is the constant-velocity prediction
+    key^-1 * prev * (prevprev^-1 * prev)."""
+    plan = []
+    key = 0
+    for f in range(1, len(poses)):
+        if f >= 2:
+            vel = np.linalg.inv(poses[f - 2]) @ poses[f - 1]
+            guess = np.linalg.inv(poses[key]) @ poses[f - 1] @ vel
+            plan.append((f, key, guess.astype(np.float32)))
+        rel = np.linalg.inv(poses[key]) @ poses[f]
+        dx = np.linalg.norm(rel[:3, 3])
+        da = np.arccos(np.clip((np.trace(rel[:3, :3]) - 1) / 2, -1, 1))
+        if dx > delta_trans or da > delta_angle or (f - key) > delta_frames:
+            key = f
+    return plan

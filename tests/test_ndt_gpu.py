@@ -21,7 +21,7 @@ def _mk(variant, search, **kw):
     n.setResolution(kw.get("resolution", 1.0))
     n.setStepSize(kw.get("step_size", 0.1))
     o = O.OracleNDT(variant=variant, resolution=kw.get("resolution", 1.0), step_size=kw.get("step_size", 0.1), trans_eps=kw.get("trans_eps", 0.01),
-                    max_iter=kw.get("max_iter", 64), search=search, num_threads=8)
+                    max_iter=kw.get("max_iter", 64), search=search, num_threads=kw.get("threads", 8))
     return n, o
 
 
@@ -184,14 +184,16 @@ def test_align_small_matches_oracle(small_pair, variant, search):
 def test_align_line_search_and_double_hessian_path(small_pair):
     """step_size <= transformation_epsilon / 2 makes the reference's `interval_converged = (step_max - step_min) > 0`
     false, which is the only way its More-Thuente loop (and the serial all-double computeHessian) ever runs.  Starting
-    next to the optimum with a forced 0.25 m step overshoots, so the loop actually iterates."""
+    next to the optimum with a forced 0.25 m step overshoots, so the loop actually iterates.  Every trial lands on the same
+    clamped step, so the loop's exit hinges on `f_t > f_l` between two evaluations of the SAME point: the oracle runs with one
+    thread here because its OpenMP `schedule(guided)` partial sums (like the reference's) are not run-to-run bit-stable."""
     tgt, src, guess, truth = small_pair
     for ss, eps, g0 in ((0.2, 0.5, truth.astype(np.float32)), (0.2, 0.5, guess), (0.1, 0.3, truth.astype(np.float32))):
-        n, o = _mk(O.VAR_OMP, O.DIRECT7, step_size=ss, trans_eps=eps, max_iter=6)
+        n, o = _mk(O.VAR_OMP, O.DIRECT7, step_size=ss, trans_eps=eps, max_iter=6, threads=1)
         n.setInputTarget(tgt); o.set_target(tgt)
         g, r = _check_align(n, o, src, g0)
         assert r["n_hess"] > 0 and r["trace"][:, 20].max() > 0
-    n, o = _mk(O.VAR_PCA, O.DIRECT1, step_size=0.2, trans_eps=0.5, max_iter=6)
+    n, o = _mk(O.VAR_PCA, O.DIRECT1, step_size=0.2, trans_eps=0.5, max_iter=6, threads=1)
     n.setInputTarget(tgt); o.set_target(tgt)
     g, r = _check_align(n, o, src, truth.astype(np.float32))
     assert r["n_hess"] > 0
