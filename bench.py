@@ -42,9 +42,10 @@ def parse():
 
 def make_workload(batch, rank):
     """Frames [rank*span, rank*span + batch + 2) of the synthetic drive, seed 1000."""
+    from lv_slam_b200 import dist as D
     from lv_slam_b200 import synth
-    start = rank * (batch + 2)
-    scans, poses = synth.stream(batch + 2, seed=1000, start=start)
+    start, span = D.frame_range(rank, batch)
+    scans, poses = synth.stream(span, seed=1000, start=start)
     plan = synth.keyframe_plan(poses)[:batch]
     keys = sorted({k for _, k, _ in plan})
     return scans, poses, plan, keys
@@ -168,10 +169,9 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
     import lv_slam_b200 as L
+    from lv_slam_b200 import dist as D
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local_rank, world = D.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -223,11 +223,7 @@ def main_ours(args):
                 n_eval_total += sum(r["n_eval"] for r in res)
             ev1.record(stream)
         barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = D.max_over_ranks(ev0.elapsed_time(ev1), world, "cuda")
         nb.set_profiling(0)
         return ms / steps, nb.total_launches() - launches0, kern_ms, kern_launches, n_eval_total, res
 

@@ -157,6 +157,57 @@ int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int target_slot, int* n_cells, i
 /* The batch object that backs a single registration handle (1 target slot, 1 source slot). */
 int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out);
 
+/* ===================================================================================================================
+ * Pose graph — replaces lv_slam::GraphSLAM::optimize (src/global_graph/graph_slam.cpp:298-331) and the g2o machinery under
+ * it for graphs of VertexSE3 / EdgeSE3 with optional Huber kernels (what global_graph builds with GPS/IMU/floor disabled,
+ * launch/dlo_lfa_ggo_kitti.launch:8-11).
+ *
+ * Solver kinds = the `solver_type` strings GraphSLAM's constructor accepts (graph_slam.cpp:48-70, g2o solver registry):
+ *   LVS_PGO_LM_CHOL  "lm_var", "lm_var_cholmod", "lm_fix6_3*"   Levenberg-Marquardt, linear system solved to round-off
+ *   LVS_PGO_GN_CHOL  "gn_var", "gn_var_cholmod", ...            Gauss-Newton (needs a fixed vertex: no damping)
+ *   LVS_PGO_LM_PCG   "lm_pcg"                                    Levenberg-Marquardt + g2o's block-Jacobi PCG (tolerance 1e-6)
+ *   LVS_PGO_GN_PCG   "gn_pcg"
+ * Poses and measurements are 7-vectors  x y z qx qy qz qw  (g2o's VERTEX_SE3:QUAT / EDGE_SE3:QUAT order); information
+ * matrices are the 21 upper-triangular entries, row-major, as in g2o files.  Edge k connects vertices()[0] = ij[2k] ("from")
+ * and vertices()[1] = ij[2k+1] ("to") exactly as GraphSLAM::add_se3_edge(v1, v2, ...) does (graph_slam.cpp:136-146).
+ * huber_delta[k] <= 0 (or a NULL array) means no robust kernel on edge k (add_robust_kernel, graph_slam.cpp:278-296).
+ * fixed[v] != 0 mirrors VertexSE3::setFixed(true); NULL = nothing fixed (the nodelet's default, fix_first_node = false).
+ */
+typedef enum { LVS_PGO_LM_CHOL = 0, LVS_PGO_GN_CHOL = 1, LVS_PGO_LM_PCG = 2, LVS_PGO_GN_PCG = 3 } lvs_pgo_solver;
+
+typedef struct {
+  int32_t iterations;        /* the return value of GraphSLAM::optimize: iterations run, 0 on solver failure, -1 on an empty graph */
+  int32_t status;            /* lvs_status of the run */
+  double chi2_before;        /* graph->chi2() before (sum of e^T Omega e, not robustified; graph_slam.cpp:316) */
+  double chi2_after;         /* the same sum at the final estimate */
+  double robust_chi2_after;  /* activeRobustChi2 at the final estimate (what LM compares) */
+  double lambda_final;
+  double device_ms, linearize_ms, solve_ms;
+  int32_t lm_trials, pcg_iterations, launches, linearize_launches;
+} lvs_pgo_stats;
+
+typedef struct { double chi2, lambda; int32_t trials, pcg_iterations; } lvs_pgo_iter_rec;   /* one per outer iteration */
+
+typedef struct lvs_pgo lvs_pgo_t;
+
+int lvs_pgo_create(int solver, int device, void* stream, lvs_pgo_t** out);
+int lvs_pgo_destroy(lvs_pgo_t* h);
+int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const uint8_t* fixed, int n_edges, const int32_t* ij,
+                      const double* meas7, const double* info21, const double* huber_delta);
+int lvs_pgo_set_poses(lvs_pgo_t* h, const double* poses7);          /* VertexSE3::setEstimate for every vertex */
+int lvs_pgo_optimize(lvs_pgo_t* h, int max_iterations, lvs_pgo_stats* stats);
+int lvs_pgo_get_poses(lvs_pgo_t* h, double* poses7);                /* VertexSE3::estimate() of every vertex */
+int lvs_pgo_get_trace(lvs_pgo_t* h, lvs_pgo_iter_rec* recs, int capacity, int* n_out);
+/* pcg_tolerance > 0 / pcg_max_iterations > 0 override the per-solver defaults (LinearSolverPCG::setTolerance / setMaxIterations). */
+int lvs_pgo_set_solver_options(lvs_pgo_t* h, double pcg_tolerance, int pcg_max_iterations);
+/* Parity taps: EdgeSE3::computeError + chi2 per edge and activeRobustChi2; the assembled normal equations of
+ * BlockSolver::buildSystem (diagonal blocks [n_free][36], unique upper off-diagonal blocks with their (row, col) block
+ * indices, right-hand side [6 n_free]); one linear solve of (H + lambda I) x = b on the last linearisation. */
+int lvs_pgo_compute_errors(lvs_pgo_t* h, double* err6, double* chi2, double* robust_total);
+int lvs_pgo_system_size(lvs_pgo_t* h, int* n_free, int* n_offdiag);
+int lvs_pgo_linearize(lvs_pgo_t* h, double* Hd, int32_t* off_ij, double* Ho, double* b);
+int lvs_pgo_solve(lvs_pgo_t* h, double lambda, double tolerance, int max_iterations, double* x, int* iterations);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -38,8 +38,15 @@ class NdtTraceRec(ctypes.Structure):
 
 class PgoStats(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("status", ctypes.c_int32), ("chi2_before", ctypes.c_double), ("chi2_after", ctypes.c_double),
-                ("lambda_final", ctypes.c_double), ("device_ms", ctypes.c_double), ("linearize_ms", ctypes.c_double), ("solve_ms", ctypes.c_double),
-                ("lm_trials", ctypes.c_int32), ("pcg_iterations", ctypes.c_int32), ("launches", ctypes.c_int32), ("linearize_launches", ctypes.c_int32)]
+                ("robust_chi2_after", ctypes.c_double), ("lambda_final", ctypes.c_double), ("device_ms", ctypes.c_double),
+                ("linearize_ms", ctypes.c_double), ("solve_ms", ctypes.c_double), ("lm_trials", ctypes.c_int32), ("pcg_iterations", ctypes.c_int32),
+                ("launches", ctypes.c_int32), ("linearize_launches", ctypes.c_int32)]
+
+
+class PgoIterRec(ctypes.Structure):
+    _fields_ = [("chi2", ctypes.c_double), ("lam", ctypes.c_double), ("trials", ctypes.c_int32), ("pcg_iterations", ctypes.c_int32)]
+
+LVS_PGO_LM_CHOL, LVS_PGO_GN_CHOL, LVS_PGO_LM_PCG, LVS_PGO_GN_PCG = 0, 1, 2, 3
 
 
 _lib = None
@@ -69,6 +76,11 @@ def lib():
             "lvs_ndt_batch_set_target": [vp, i32, vp, sz, sz, i32], "lvs_ndt_batch_set_source": [vp, i32, vp, sz, sz, i32],
             "lvs_ndt_batch_align": [vp, i32, vp, vp, vp, vp], "lvs_ndt_batch_last_stats": [vp, vp, vp, vp, vp],
             "lvs_ndt_batch_set_profiling": [vp, i32], "lvs_ndt_batch_set_tuning": [vp, i32, i32, i32],
+            "lvs_pgo_create": [i32, i32, vp, vp], "lvs_pgo_destroy": [vp], "lvs_pgo_set_graph": [vp, i32, vp, vp, i32, vp, vp, vp, vp],
+            "lvs_pgo_set_poses": [vp, vp], "lvs_pgo_optimize": [vp, i32, vp], "lvs_pgo_get_poses": [vp, vp], "lvs_pgo_get_trace": [vp, vp, i32, vp],
+            "lvs_pgo_set_solver_options": [vp, ctypes.c_double, i32], "lvs_pgo_compute_errors": [vp, vp, vp, vp],
+            "lvs_pgo_system_size": [vp, vp, vp], "lvs_pgo_linearize": [vp, vp, vp, vp, vp],
+            "lvs_pgo_solve": [vp, ctypes.c_double, ctypes.c_double, i32, vp, vp],
             "lvs_ndt_batch_total_launches": [vp, vp], "lvs_ndt_batch_transfer_bytes": [vp, vp, vp], "lvs_ndt_batch_num_cells": [vp, i32, vp, vp],
         }.items():
             f = getattr(L, name)

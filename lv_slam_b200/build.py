@@ -18,8 +18,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the NDT kernels reproduce the reference's float32 operation order bit for bit (the reference is built
 # with SSE4.2 and no FMA, /root/reference/CMakeLists.txt:6); contraction would change voxel indices on cell faces.
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-          "-fmad=false", "--expt-relaxed-constexpr"]
-SOURCES = ["ndt_voxel.cu", "ndt_eval.cu", "ndt_eval_cold.cu", "ndt_api.cu", "pgo_kernels.cu", "pgo_api.cu"]
+          "--expt-relaxed-constexpr"]
+NO_FMA = ["-fmad=false"]
+# (source, extra flags): the pose-graph code is fp64 throughout and compared to tolerance, so it keeps FMA contraction
+SOURCES = [("ndt_voxel.cu", NO_FMA), ("ndt_eval.cu", NO_FMA), ("ndt_eval_cold.cu", NO_FMA), ("ndt_api.cu", NO_FMA), ("pgo.cu", [])]
 
 
 def _deps():
@@ -28,23 +30,24 @@ def _deps():
     return hs
 
 
-def _stamp(src):
+def _stamp(src, extra=()):
     h = hashlib.sha1()
     for p in [src] + _deps():
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(COMMON).encode())
+    h.update(" ".join(COMMON + list(extra)).encode())
     return h.hexdigest()
 
 
-def _compile(name, verbose):
+def _compile(item, verbose):
+    name, extra = item
     src = os.path.join(CSRC, name)
     obj = os.path.join(OBJ, name + ".o")
     stamp_file = obj + ".stamp"
-    stamp = _stamp(src)
+    stamp = _stamp(src, extra)
     if os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return obj, False
-    cmd = [NVCC] + COMMON + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    cmd = [NVCC] + COMMON + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -61,7 +64,7 @@ def build(verbose=False, force=False):
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s[0]))]
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         res = list(ex.map(lambda s: _compile(s, verbose), srcs))
     objs = [o for o, _ in res]

@@ -1,0 +1,256 @@
+// SE(3) edge arithmetic of the pose-graph path, fp64, host + device.  Follows g2o a48ff8c (vendored by the reference as
+// 3rdtools/g2o-a48ff8c.zip; paths inside the zip, g2o/g2o/...):
+//   EdgeSE3::computeError                  types/slam3d/edge_se3.cpp:78-83
+//   toVectorMQT / fromVectorMQT / normalize types/slam3d/isometry3d_mappings.cpp:38-44,77-99,117-122
+//   computeEdgeSE3Gradient, skew / skewT   types/slam3d/isometry3d_gradients.h:43-84,193-263
+//   compute_dq_dR + generated cases        types/slam3d/dquat2mat.cpp:35-83, dquat2mat_maxima_generated.cpp:27-237
+//   VertexSE3::oplusImpl                   types/slam3d/vertex_se3.h:105-114
+//   RobustKernelHuber::robustify           core/robust_kernel_impl.cpp:65-78
+#pragma once
+#include "lvs_math.cuh"
+
+namespace lvs {
+
+struct Rt {            // Eigen::Isometry3d as row-major rotation + translation (96 B)
+  double R[9];
+  double t[3];
+};
+
+LVS_HD Rt rt_mul(const Rt& a, const Rt& b) {
+  Rt r;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) r.R[i * 3 + j] = (a.R[i * 3] * b.R[j] + a.R[i * 3 + 1] * b.R[3 + j]) + a.R[i * 3 + 2] * b.R[6 + j];
+    r.t[i] = ((a.R[i * 3] * b.t[0] + a.R[i * 3 + 1] * b.t[1]) + a.R[i * 3 + 2] * b.t[2]) + a.t[i];
+  }
+  return r;
+}
+
+LVS_HD Rt rt_inv(const Rt& a) {
+  Rt r;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r.R[i * 3 + j] = a.R[j * 3 + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) r.t[i] = -((r.R[i * 3] * a.t[0] + r.R[i * 3 + 1] * a.t[1]) + r.R[i * 3 + 2] * a.t[2]);
+  return r;
+}
+
+LVS_HD Rt rt_from_qt7(const double* v) {   // x y z qx qy qz qw; the quaternion is normalised like EdgeSE3::read does
+  Rt r;
+  Q4 q = {v[6], v[3], v[4], v[5]};
+  quat_normalize(q);
+  quat_to_mat(q, r.R);
+  r.t[0] = v[0]; r.t[1] = v[1]; r.t[2] = v[2];
+  return r;
+}
+
+LVS_HD void rt_to_qt7(const Rt& a, double* v) {   // toVectorQT
+  Q4 q = quat_from_mat(a.R);
+  quat_normalize(q);
+  v[0] = a.t[0]; v[1] = a.t[1]; v[2] = a.t[2]; v[3] = q.x; v[4] = q.y; v[5] = q.z; v[6] = q.w;
+}
+
+LVS_HD void rt_to_vector_mqt(const Rt& d, double* e) {
+  Q4 q = quat_from_mat(d.R);
+  quat_normalize(q);
+  if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+  e[0] = d.t[0]; e[1] = d.t[1]; e[2] = d.t[2]; e[3] = q.x; e[4] = q.y; e[5] = q.z;
+}
+
+LVS_HD Rt rt_from_vector_mqt(const double* v) {
+  Rt r;
+  double w = 1 - ((v[3] * v[3] + v[4] * v[4]) + v[5] * v[5]);
+  if (w < 0) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  } else {
+    Q4 q = {sqrt(w), v[3], v[4], v[5]};
+    quat_to_mat(q, r.R);
+  }
+  r.t[0] = v[0]; r.t[1] = v[1]; r.t[2] = v[2];
+  return r;
+}
+
+// e = toVectorMQT(Z^-1 * Xi^-1 * Xj)
+LVS_HD void edge_error(const Rt& Zinv, const Rt& Xi, const Rt& Xj, double* e) { rt_to_vector_mqt(rt_mul(rt_mul(Zinv, rt_inv(Xi)), Xj), e); }
+
+LVS_HD double chi2_of(const double* info /*6x6*/, const double* e) {
+  double s = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    double t = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) t += info[r * 6 + c] * e[c];
+    s += e[r] * t;
+  }
+  return s;
+}
+
+// rho[0] = rho(e), rho[1] = rho'(e)
+LVS_HD void huber_rho(double e, double delta, double* rho0, double* rho1) {
+  const double dsqr = delta * delta;
+  if (e <= dsqr) { *rho0 = e; *rho1 = 1.0; }
+  else { const double sq = sqrt(e); *rho0 = 2 * sq * delta - dsqr; *rho1 = delta / sq; }
+}
+
+// dq/dR, 3x9 with respect to the COLUMN-major vec(R); R row-major here.
+LVS_HD void compute_dq_dR(double* D /*[3][9]*/, const double* R) {
+  const double r00 = R[0], r10 = R[3], r20 = R[6], r01 = R[1], r11 = R[4], r21 = R[7], r02 = R[2], r12 = R[5], r22 = R[8];
+#pragma unroll
+  for (int i = 0; i < 27; i++) D[i] = 0.0;
+  const double tr = r00 + r11 + r22;
+  double S, qw;
+  int which;
+  if (tr > 0) { S = sqrt(tr + 1.0) * 2; qw = 0.25 * S; which = 0; }
+  else if ((r00 > r11) & (r00 > r22)) { S = sqrt(1.0 + r00 - r11 - r22) * 2; qw = (r21 - r12) / S; which = 1; }
+  else if (r11 > r22) { S = sqrt(1.0 + r11 - r00 - r22) * 2; qw = (r02 - r20) / S; which = 2; }
+  else { S = sqrt(1.0 + r22 - r00 - r11) * 2; qw = (r10 - r01) / S; which = 3; }
+  S *= .25;
+  const double i1 = 1 / S, i3 = 1 / (S * S * S);
+#define DQ(r, c) D[(r) * 9 + (c)]
+  if (which == 0) {
+    const double a2 = -0.03125 * (r21 - r12) * i3, a4 = 0.25 * i1, a5 = -0.25 * i1, a6 = 0.03125 * (r20 - r02) * i3, a7 = -0.03125 * (r10 - r01) * i3;
+    DQ(0, 0) = a2; DQ(0, 4) = a2; DQ(0, 5) = a4; DQ(0, 7) = a5; DQ(0, 8) = a2;
+    DQ(1, 0) = a6; DQ(1, 2) = a5; DQ(1, 4) = a6; DQ(1, 6) = a4; DQ(1, 8) = a6;
+    DQ(2, 0) = a7; DQ(2, 1) = a4; DQ(2, 3) = a5; DQ(2, 4) = a7; DQ(2, 8) = a7;
+  } else if (which == 1) {
+    const double a2 = -0.125 * i1, a4 = r10 + r01, a5 = 0.25 * i1, a6 = 0.03125 * i3 * a4, a7 = r20 + r02, a8 = 0.03125 * i3 * a7;
+    DQ(0, 0) = 0.125 * i1; DQ(0, 4) = a2; DQ(0, 8) = a2;
+    DQ(1, 0) = -0.03125 * i3 * a4; DQ(1, 1) = a5; DQ(1, 3) = a5; DQ(1, 4) = a6; DQ(1, 8) = a6;
+    DQ(2, 0) = -0.03125 * i3 * a7; DQ(2, 2) = a5; DQ(2, 4) = a8; DQ(2, 6) = a5; DQ(2, 8) = a8;
+  } else if (which == 2) {
+    const double a2 = r10 + r01, a3 = 0.03125 * i3 * a2, a5 = 0.25 * i1, a6 = -0.125 * i1, a7 = r21 + r12, a8 = 0.03125 * i3 * a7;
+    DQ(0, 0) = a3; DQ(0, 1) = a5; DQ(0, 3) = a5; DQ(0, 4) = -0.03125 * i3 * a2; DQ(0, 8) = a3;
+    DQ(1, 0) = a6; DQ(1, 4) = 0.125 * i1; DQ(1, 8) = a6;
+    DQ(2, 0) = a8; DQ(2, 4) = -0.03125 * i3 * a7; DQ(2, 5) = a5; DQ(2, 7) = a5; DQ(2, 8) = a8;
+  } else {
+    const double a2 = r20 + r02, a3 = 0.03125 * i3 * a2, a5 = 0.25 * i1, a6 = r21 + r12, a7 = 0.03125 * i3 * a6, a8 = -0.125 * i1;
+    DQ(0, 0) = a3; DQ(0, 2) = a5; DQ(0, 4) = a3; DQ(0, 6) = a5; DQ(0, 8) = -0.03125 * i3 * a2;
+    DQ(1, 0) = a7; DQ(1, 4) = a7; DQ(1, 5) = a5; DQ(1, 7) = a5; DQ(1, 8) = -0.03125 * i3 * a6;
+    DQ(2, 0) = a8; DQ(2, 4) = a8; DQ(2, 8) = 0.125 * i1;
+  }
+#undef DQ
+  if (qw <= 0) {
+#pragma unroll
+    for (int i = 0; i < 27; i++) D[i] = -D[i];
+  }
+}
+
+// rot block of a Jacobian: J[3+r][3+c] = sum_k D[r][k] * vec_colmajor(Rl * S_c)[k]
+LVS_HD void rot_block(const double* D, const double* Rl, const double* Sx, const double* Sy, const double* Sz, double* J) {
+  double M[3][9];
+  mat3_mul(Rl, Sx, M[0]); mat3_mul(Rl, Sy, M[1]); mat3_mul(Rl, Sz, M[2]);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) s += D[r * 9 + k] * M[c][(k % 3) * 3 + (k / 3)];
+      J[(3 + r) * 6 + 3 + c] = s;
+    }
+}
+
+// computeEdgeSE3Gradient: Ji, Jj row-major 6x6.
+LVS_HD void edge_gradient(const Rt& Z, const Rt& Xi, const Rt& Xj, double* Ji, double* Jj) {
+  const Rt A = rt_inv(Z);
+  const Rt B = rt_mul(rt_inv(Xi), Xj);
+  const Rt E = rt_mul(A, B);
+  double D[27];
+  compute_dq_dR(D, E.R);
+#pragma unroll
+  for (int i = 0; i < 36; i++) { Ji[i] = 0.0; Jj[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) { Ji[i * 6 + j] = -A.R[i * 3 + j]; Jj[i * 6 + j] = E.R[i * 3 + j]; }
+  {
+    const double x = 2 * B.t[0], y = 2 * B.t[1], z = 2 * B.t[2];
+    const double S[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+    double M[9];
+    mat3_mul(A.R, S, M);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Ji[i * 6 + 3 + j] = M[i * 3 + j];
+  }
+  {
+    const double* R = B.R;
+    const double r11 = 2 * R[0], r12 = 2 * R[1], r13 = 2 * R[2], r21 = 2 * R[3], r22 = 2 * R[4], r23 = 2 * R[5], r31 = 2 * R[6], r32 = 2 * R[7], r33 = 2 * R[8];
+    const double Sx[9] = {0, 0, 0, r31, r32, r33, -r21, -r22, -r23};
+    const double Sy[9] = {-r31, -r32, -r33, 0, 0, 0, r11, r12, r13};
+    const double Sz[9] = {r21, r22, r23, -r11, -r12, -r13, 0, 0, 0};
+    rot_block(D, A.R, Sx, Sy, Sz, Ji);
+  }
+  {
+    const double Sx[9] = {0, 0, 0, 0, 0, -2, 0, 2, 0};
+    const double Sy[9] = {0, 0, 2, 0, 0, 0, -2, 0, 0};
+    const double Sz[9] = {0, -2, 0, 2, 0, 0, 0, 0, 0};
+    rot_block(D, E.R, Sx, Sy, Sz, Jj);
+  }
+}
+
+// C = A^T * W * B, 6x6 row-major
+LVS_HD void atwb(const double* A, const double* W, const double* B, double* C) {
+  double WB[36];
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += W[r * 6 + k] * B[k * 6 + c];
+      WB[r * 6 + c] = s;
+    }
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += A[k * 6 + r] * WB[k * 6 + c];
+      C[r * 6 + c] = s;
+    }
+}
+
+// 6x6 inverse by Gauss-Jordan with partial pivoting (block-Jacobi preconditioner).  Static indices only.
+LVS_HD bool inv6(const double* M, double* R) {
+  double a[6][12];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) { a[i][j] = M[i * 6 + j]; a[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      if (fabs(a[i][k]) > fabs(a[k][k])) {
+#pragma unroll
+        for (int j = 0; j < 12; j++) { double t = a[k][j]; a[k][j] = a[i][j]; a[i][j] = t; }
+      }
+    }
+    if (a[k][k] == 0.0) ok = false;
+    const double inv = 1.0 / a[k][k];
+#pragma unroll
+    for (int j = 0; j < 12; j++) a[k][j] *= inv;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      if (i != k) {
+        const double f = a[i][k];
+#pragma unroll
+        for (int j = 0; j < 12; j++) a[i][j] -= f * a[k][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) R[i * 6 + j] = a[i][6 + j];
+  return ok;
+}
+
+}  // namespace lvs

@@ -1,0 +1,35 @@
+"""Multi-GPU plumbing of the benchmark / replay driver: one process per GPU, work split by independent scan pairs or pose
+graphs (the stream shards by frame, no collective on the data path), device timings combined as the max over ranks."""
+import os
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def frame_range(rank, pairs_per_rank):
+    """Frames of the synthetic drive owned by `rank`: two lead-in frames (keyframe 0 and the first constant-velocity
+    predecessor) followed by `pairs_per_rank` matched frames.  Ranges of different ranks are disjoint."""
+    span = pairs_per_rank + 2
+    return rank * span, span
+
+
+def max_over_ranks(value, world, device=None):
+    """MAX all-reduce of a scalar (timings are reported as the slowest rank's)."""
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, world, device=None):
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -1,0 +1,274 @@
+"""Host mirror of ``lv_slam::GraphSLAM`` (/root/reference/include/global_graph/graph_slam.hpp:40-149,
+src/global_graph/graph_slam.cpp) for the part of it the hot path covers: SE(3) nodes, SE(3) edges with optional robust kernels,
+``optimize``, g2o-text ``save`` / ``load``.  Vertices and edges are light Python handles (the reference hands out raw
+``g2o::VertexSE3*`` / ``g2o::EdgeSE3*``); all arithmetic happens in liblvslam_b200.so on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi as C
+from .synth import posegraph as _pg
+
+_SOLVERS = {"lm_var": C.LVS_PGO_LM_CHOL, "lm_var_cholmod": C.LVS_PGO_LM_CHOL, "lm_var_csparse": C.LVS_PGO_LM_CHOL, "lm_fix6_3": C.LVS_PGO_LM_CHOL,
+            "lm_fix6_3_cholmod": C.LVS_PGO_LM_CHOL, "lm_fix6_3_csparse": C.LVS_PGO_LM_CHOL, "gn_var": C.LVS_PGO_GN_CHOL,
+            "gn_var_cholmod": C.LVS_PGO_GN_CHOL, "gn_var_csparse": C.LVS_PGO_GN_CHOL, "gn_fix6_3": C.LVS_PGO_GN_CHOL,
+            "lm_pcg": C.LVS_PGO_LM_PCG, "gn_pcg": C.LVS_PGO_GN_PCG}
+
+
+class VertexSE3:
+    def __init__(self, vid, pose4x4):
+        self._id = vid
+        self._T = np.array(pose4x4, dtype=np.float64).reshape(4, 4)
+        self._fixed = False
+
+    def id(self):
+        return self._id
+
+    def estimate(self):
+        return self._T.copy()
+
+    def setEstimate(self, T):
+        self._T = np.array(T, dtype=np.float64).reshape(4, 4)
+
+    def setFixed(self, f):
+        self._fixed = bool(f)
+
+    def fixed(self):
+        return self._fixed
+
+
+class EdgeSE3:
+    def __init__(self, v1, v2, rel4x4, info6x6):
+        self.vertices = [v1, v2]
+        self.measurement = np.array(rel4x4, dtype=np.float64).reshape(4, 4)
+        self.information = np.array(info6x6, dtype=np.float64).reshape(6, 6)
+        self.kernel = None          # (type, delta)
+
+
+class GraphSLAM:
+    def __init__(self, solver_type="lm_var", device=0):
+        if solver_type not in _SOLVERS:
+            raise ValueError("unknown solver type %r (the reference prints g2o's solver list here)" % solver_type)
+        self._L = C.lib()
+        self._solver_type = solver_type
+        self._device = device
+        self._h = None                      # the device object is created on first optimize()
+        self._vertices, self._edges = [], []
+        self.last_stats = None
+
+    def _handle(self):
+        if not self._h:
+            h = ctypes.c_void_p()
+            C.check(self._L.lvs_pgo_create(_SOLVERS[self._solver_type], self._device, None, ctypes.byref(h)))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lvs_pgo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_solver(self, solver_type):
+        if solver_type not in _SOLVERS:
+            raise ValueError("unknown solver type %r" % solver_type)
+        self.close()
+        self._solver_type = solver_type
+
+    def num_vertices(self):
+        return len(self._vertices)
+
+    def num_edges(self):
+        return len(self._edges)
+
+    def add_se3_node(self, pose4x4):
+        v = VertexSE3(len(self._vertices), pose4x4)       # id = current vertex count (graph_slam.cpp:108)
+        self._vertices.append(v)
+        return v
+
+    def add_se3_edge(self, v1, v2, relative_pose, information_matrix):
+        e = EdgeSE3(v1, v2, relative_pose, information_matrix)
+        self._edges.append(e)
+        return e
+
+    def add_robust_kernel(self, edge, kernel_type, kernel_size):
+        if kernel_type == "NONE":
+            return
+        if kernel_type != "Huber":
+            print("warning : invalid robust kernel type: %s" % kernel_type)      # the reference warns and leaves the edge unkernelled
+            return
+        edge.kernel = (kernel_type, float(kernel_size))
+
+    def _arrays(self):
+        nv, ne = len(self._vertices), len(self._edges)
+        poses = np.array([_pg.pose7(v._T) for v in self._vertices]).reshape(nv, 7)
+        fixed = np.array([1 if v._fixed else 0 for v in self._vertices], dtype=np.uint8)
+        ij = np.array([[e.vertices[0]._id, e.vertices[1]._id] for e in self._edges], dtype=np.int32).reshape(ne, 2)
+        meas = np.array([_pg.pose7(e.measurement) for e in self._edges]).reshape(ne, 7)
+        info = np.array([[e.information[r, c] for r in range(6) for c in range(r, 6)] for e in self._edges]).reshape(ne, 21)
+        hub = np.array([e.kernel[1] if e.kernel else 0.0 for e in self._edges])
+        return poses, fixed, ij, meas, info, hub
+
+    def optimize(self, num_iterations):
+        if len(self._edges) < 1:
+            return -1                                                             # graph_slam.cpp:302-305
+        poses, fixed, ij, meas, info, hub = self._arrays()
+        st = optimize_arrays(self._L, self._handle(), poses, fixed, ij, meas, info, hub, num_iterations)
+        out = np.zeros((len(self._vertices), 7))
+        C.check(self._L.lvs_pgo_get_poses(self._handle(), out.ctypes.data))
+        for v, p in zip(self._vertices, out):
+            v._T = _pg.matrix(p)
+        self.last_stats = st
+        print("chi2: (before)%g -> (after)%g" % (st["chi2_before"], st["chi2_after"]))
+        return st["iterations"]
+
+    # ---- g2o text format (types/slam3d/vertex_se3.cpp:49-64, edge_se3.cpp:44-76)
+    def save(self, filename):
+        with open(filename, "w") as f:
+            for v in self._vertices:
+                f.write("VERTEX_SE3:QUAT %d %s\n" % (v._id, " ".join(repr(float(x)) for x in _pg.pose7(v._T))))
+                if v._fixed:
+                    f.write("FIX %d\n" % v._id)
+            for e in self._edges:
+                up = [e.information[r, c] for r in range(6) for c in range(r, 6)]
+                f.write("EDGE_SE3:QUAT %d %d %s %s\n" % (e.vertices[0]._id, e.vertices[1]._id, " ".join(repr(float(x)) for x in _pg.pose7(e.measurement)),
+                                                      " ".join(repr(float(x)) for x in up)))
+        with open(filename + ".kernels", "w") as f:                               # robust_kernel_io.cpp sidecar
+            for e in self._edges:
+                if e.kernel:
+                    f.write("%d %d %s %r\n" % (e.vertices[0]._id, e.vertices[1]._id, e.kernel[0], e.kernel[1]))
+        return True
+
+    def load(self, filename):
+        self._vertices, self._edges = [], []
+        by_id = {}
+        with open(filename) as f:
+            for line in f:
+                t = line.split()
+                if not t:
+                    continue
+                if t[0] == "VERTEX_SE3:QUAT":
+                    v = VertexSE3(int(t[1]), _pg.matrix(np.array(t[2:9], dtype=np.float64)))
+                    by_id[v._id] = v
+                    self._vertices.append(v)
+                elif t[0] == "FIX":
+                    for s in t[1:]:
+                        by_id[int(s)].setFixed(True)
+                elif t[0] == "EDGE_SE3:QUAT":
+                    a, b = int(t[1]), int(t[2])
+                    m = np.array(t[3:10], dtype=np.float64)
+                    up = np.array(t[10:31], dtype=np.float64)
+                    info = np.zeros((6, 6))
+                    k = 0
+                    for r in range(6):
+                        for c in range(r, 6):
+                            info[r, c] = info[c, r] = up[k]
+                            k += 1
+                    self._edges.append(EdgeSE3(by_id[a], by_id[b], _pg.matrix(m), info))
+        self._vertices.sort(key=lambda v: v._id)
+        try:
+            with open(filename + ".kernels") as f:
+                kern = {}
+                for line in f:
+                    t = line.split()
+                    if len(t) == 4:
+                        kern[(int(t[0]), int(t[1]))] = (t[2], float(t[3]))
+                for e in self._edges:
+                    k = kern.get((e.vertices[0]._id, e.vertices[1]._id))
+                    if k:
+                        e.kernel = k
+        except OSError:
+            pass
+        return True
+
+
+def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iterations):
+    """set_graph + optimize on flat arrays; returns the stats dict (used by GraphSLAM.optimize, the tests and the bench)."""
+    poses7 = np.ascontiguousarray(poses7, dtype=np.float64)
+    ij = np.ascontiguousarray(ij, dtype=np.int32)
+    meas7 = np.ascontiguousarray(meas7, dtype=np.float64)
+    info21 = np.ascontiguousarray(info21, dtype=np.float64)
+    hub = np.ascontiguousarray(huber, dtype=np.float64) if huber is not None else None
+    fx = np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None
+    C.check(L.lvs_pgo_set_graph(h, poses7.shape[0], poses7.ctypes.data, fx.ctypes.data if fx is not None else None, ij.shape[0], ij.ctypes.data,
+                                meas7.ctypes.data, info21.ctypes.data, hub.ctypes.data if hub is not None else None))
+    st = C.PgoStats()
+    rc = L.lvs_pgo_optimize(h, int(num_iterations), ctypes.byref(st))
+    if rc != 0 and rc != -10:
+        C.check(rc)
+    return {k: getattr(st, k) for k, _ in C.PgoStats._fields_}
+
+
+class PoseGraph:
+    """Flat-array handle on the pose-graph C-ABI (tests / bench)."""
+
+    def __init__(self, solver=C.LVS_PGO_LM_CHOL, device=0):
+        self._L = C.lib()
+        self._h = ctypes.c_void_p()
+        C.check(self._L.lvs_pgo_create(solver, device, None, ctypes.byref(self._h)))
+        self.nv = self.ne = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lvs_pgo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_graph(self, poses7, ij, meas7, info21, huber=None, fixed=None):
+        self._keep = [np.ascontiguousarray(poses7, dtype=np.float64), np.ascontiguousarray(ij, dtype=np.int32), np.ascontiguousarray(meas7, dtype=np.float64),
+                      np.ascontiguousarray(info21, dtype=np.float64), np.ascontiguousarray(huber, dtype=np.float64) if huber is not None else None,
+                      np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None]
+        p, e, m, i, hb, fx = self._keep
+        self.nv, self.ne = p.shape[0], e.shape[0]
+        C.check(self._L.lvs_pgo_set_graph(self._h, self.nv, p.ctypes.data, fx.ctypes.data if fx is not None else None, self.ne, e.ctypes.data,
+                                          m.ctypes.data, i.ctypes.data, hb.ctypes.data if hb is not None else None))
+
+    def set_options(self, pcg_tolerance=0.0, pcg_max_iterations=0):
+        C.check(self._L.lvs_pgo_set_solver_options(self._h, float(pcg_tolerance), int(pcg_max_iterations)))
+
+    def optimize(self, max_iterations):
+        st = C.PgoStats()
+        rc = self._L.lvs_pgo_optimize(self._h, int(max_iterations), ctypes.byref(st))
+        if rc != 0 and rc != -10:
+            C.check(rc)
+        out = {k: getattr(st, k) for k, _ in C.PgoStats._fields_}
+        recs = (C.PgoIterRec * 2048)()
+        n = ctypes.c_int(0)
+        C.check(self._L.lvs_pgo_get_trace(self._h, recs, 2048, ctypes.byref(n)))
+        out["trace"] = np.array([[recs[k].chi2, recs[k].lam, recs[k].trials, recs[k].pcg_iterations] for k in range(min(n.value, 2048))]).reshape(-1, 4)
+        return out
+
+    def poses(self):
+        out = np.zeros((self.nv, 7))
+        C.check(self._L.lvs_pgo_get_poses(self._h, out.ctypes.data))
+        return out
+
+    def errors(self):
+        e, c, tot = np.zeros((self.ne, 6)), np.zeros(self.ne), ctypes.c_double(0)
+        C.check(self._L.lvs_pgo_compute_errors(self._h, e.ctypes.data, c.ctypes.data, ctypes.byref(tot)))
+        return e, c, tot.value
+
+    def linearize(self):
+        nf, no = ctypes.c_int(0), ctypes.c_int(0)
+        C.check(self._L.lvs_pgo_system_size(self._h, ctypes.byref(nf), ctypes.byref(no)))
+        Hd, Ho, b, off = np.zeros((nf.value, 6, 6)), np.zeros((no.value, 6, 6)), np.zeros(nf.value * 6), np.zeros((no.value, 2), np.int32)
+        C.check(self._L.lvs_pgo_linearize(self._h, Hd.ctypes.data, off.ctypes.data, Ho.ctypes.data, b.ctypes.data))
+        return dict(Hd=Hd, Ho=Ho, off=off, b=b)
+
+    def solve(self, lam, tolerance=1e-24, max_iterations=0):
+        nf = ctypes.c_int(0)
+        C.check(self._L.lvs_pgo_system_size(self._h, ctypes.byref(nf), None))
+        x, it = np.zeros(nf.value * 6), ctypes.c_int(0)
+        C.check(self._L.lvs_pgo_solve(self._h, float(lam), float(tolerance), int(max_iterations), x.ctypes.data, ctypes.byref(it)))
+        return x, it.value

@@ -1,0 +1,37 @@
+"""Writes tests/golden/*.json from the CPU oracle on the seeded small inputs.
+
+These are REGRESSION pins of the oracle, not reference outputs: the reference (and PCL / Eigen / Sophus / g2o) cannot be built
+in this image, and it ships no golden vectors of its own."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle_ndt as O  # noqa: E402
+import oracle_pgo as P  # noqa: E402
+from lv_slam_b200 import synth  # noqa: E402
+from lv_slam_b200.synth import posegraph as G  # noqa: E402
+
+tgt, src, guess, truth = synth.config1_pair(n_beams=16, n_az=600, seed=5)
+o = O.OracleNDT(trans_eps=0.01, max_iter=30, search=O.DIRECT7, num_threads=1)
+o.set_target(tgt); o.set_source(src)
+lv = o.leaves()
+s, g, H = o.eval_derivatives(O.se3_log_from_matrix4f(guess), guess)
+r = o.align(guess)
+json.dump(dict(n_cells=len(lv["keys"]), n_usable=int((lv["nr_points"] >= 6).sum()), key_sum=int(lv["keys"].astype(np.int64).sum()), score=s,
+               gradient=g.tolist(), hessian=H.tolist(), iterations=r["iterations"], final=r["final"].astype(float).tolist()),
+          open(os.path.join(HERE, "ndt_small_pair.json"), "w"), indent=1)
+
+gr = G.sphere(20, 10, seed=7)
+p = P.OraclePGO()
+p.set_graph(gr["poses7"], gr["ij"], gr["meas7"], gr["info21"], gr["huber"])
+e, c, tot = p.errors()
+st = p.optimize(100, P.ALG_LM, P.SOLVER_DENSE)
+json.dump(dict(n_vertices=len(gr["poses7"]), n_edges=len(gr["ij"]), robust_chi2_initial=tot, chi2_initial=float(c.sum()), chi2_final=st["chi2_after"],
+               first_lambdas=st["trace"][:5, 1].tolist(), first_chi2=st["trace"][:5, 0].tolist()),
+          open(os.path.join(HERE, "pgo_sphere_200.json"), "w"), indent=1)
+print("golden files written")

@@ -1,0 +1,195 @@
+"""CPU checks that pin the NDT oracle itself (no GPU): closed-form known answers, property checks and finite differences.
+
+The reference ships no golden vector for this path, so these are the pins: the gauss constants the
+reference's formulas give for its own parameters, se(3) round trips to 1e-10 (Sophus' own test tolerance), the small dense
+solvers against numpy, a hand-built voxel, and finite differences of the score against the gradient / of the gradient against the
+Hessian at poses where the reference's point Jacobian is the true derivative (rotation vector = 0).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_ndt as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_gauss_constants_known_answers():
+    # values of ndt_omp_impl2.hpp:93-100 for the reference's parameters
+    o = O.OracleNDT(resolution=1.0, outlier_ratio=0.55)
+    np.testing.assert_allclose(o.gauss(), [-2.217225244043, 0.433123004704, 0.597837000756], rtol=0, atol=5e-12)
+    o = O.OracleNDT(resolution=0.5, outlier_ratio=0.55)
+    np.testing.assert_allclose(o.gauss(), [-0.704446735814, 0.756362730327, -1.481604540924], rtol=0, atol=5e-12)
+
+
+def test_se3_exp_log_round_trip():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        p = np.concatenate([rng.normal(0, 5, 3), rng.normal(0, 1, 3) * rng.uniform(0, 1)])
+        q, t = O.se3_exp(p)
+        assert abs(np.linalg.norm(q) - 1) < 1e-14
+        back = O.se3_compose_log(np.zeros(6), p)          # log(exp(0) * exp(p))
+        np.testing.assert_allclose(back, p, rtol=0, atol=1e-10)
+    # tiny angles take the Taylor branches (so3.cpp:180-186, se3.cpp:176-180,208)
+    p = np.array([1.0, -2.0, 0.5, 1e-12, -2e-12, 1e-13])
+    np.testing.assert_allclose(O.se3_compose_log(np.zeros(6), p), p, rtol=0, atol=1e-10)
+    # composition agrees with matrix products
+    a, b = np.array([0.3, -0.1, 0.2, 0.02, 0.01, -0.4]), np.array([1.0, 2.0, -0.5, -0.3, 0.2, 0.1])
+    Ta, Tb = O.se3_exp_matrix4f(a).astype(np.float64), O.se3_exp_matrix4f(b).astype(np.float64)
+    Tab = O.se3_exp_matrix4f(O.se3_compose_log(a, b)).astype(np.float64)
+    np.testing.assert_allclose(Tab, Ta @ Tb, atol=2e-6)
+
+
+def test_log_of_float_guess_matches_matrix():
+    T = np.eye(4, dtype=np.float32)
+    T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
+    np.testing.assert_allclose(O.se3_log_from_matrix4f(T), [1.5, 0, 0, 0, 0, 0], atol=1e-15)
+
+
+def test_small_dense_solvers_against_numpy():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        A = rng.normal(size=(6, 6)) * rng.uniform(0.1, 1e4, size=(6, 1))
+        b = rng.normal(size=6)
+        x, sv = O.svd6_solve(A, b)
+        np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(sv, np.linalg.svd(A, compute_uv=False), rtol=1e-10)
+    # rank-deficient: pseudo-inverse semantics of JacobiSVD::solve
+    A = np.zeros((6, 6)); A[:3, :3] = np.diag([2.0, 3.0, 4.0]); b = np.arange(1.0, 7.0)
+    x, _ = O.svd6_solve(A, b)
+    np.testing.assert_allclose(x, np.linalg.pinv(A) @ b, atol=1e-14)
+    for _ in range(50):
+        M = rng.normal(size=(3, 3)); S = M @ M.T
+        ev, V = O.sym3_eig(S)
+        np.testing.assert_allclose(ev, np.linalg.eigvalsh(S), rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(V @ np.diag(ev) @ V.T, S, atol=1e-12)
+
+
+def test_single_voxel_hand_case():
+    """Eight points in one 1 m cell: mean, sample covariance with the (n-1)/n factor, eigenvalue inflation, inverse."""
+    pts = np.array([[0.2, 0.2, 0.5], [0.8, 0.2, 0.5], [0.2, 0.8, 0.5], [0.8, 0.8, 0.5], [0.5, 0.5, 0.5], [0.4, 0.6, 0.5], [0.6, 0.4, 0.5],
+                    [0.5, 0.5, 0.5]], dtype=np.float32)
+    o = O.OracleNDT()
+    o.set_target(pts)
+    lv = o.leaves()
+    assert lv["keys"].tolist() == [0] and lv["nr_points"].tolist() == [8]
+    p = pts.astype(np.float64)
+    mean = p.mean(axis=0)
+    np.testing.assert_allclose(lv["mean"][0], mean, atol=1e-15)
+    cov = (p - mean).T @ (p - mean) / 8 * (7 / 8)           # one-pass covariance divided by n, times (n-1)/n (:329-330)
+    ev = np.linalg.eigvalsh(cov)
+    assert ev[0] < 0.01 * ev[2]                             # planar patch: the smallest eigenvalue gets inflated
+    np.testing.assert_allclose(lv["evals"][0], [0.01 * ev[2], ev[1], ev[2]], rtol=1e-9)
+    np.testing.assert_allclose(lv["icov"][0] @ lv["cov"][0], np.eye(3), atol=1e-9)
+    # five points: below min_points_per_voxel, the cell exists but is not usable
+    o.set_target(pts[:5])
+    lv = o.leaves()
+    assert lv["nr_points"].tolist() == [5] and not lv["icov"].any()
+    o.set_source(pts)
+    s, g, H = o.eval_derivatives(np.zeros(6))
+    assert s == 0 and not g.any() and not H.any()
+
+
+def test_voxel_index_matches_reference_formula(small_pair):
+    tgt = small_pair[0]
+    o = O.OracleNDT()
+    o.set_target(tgt)
+    mn, mx, dv = o.grid()
+    inv = np.float32(1.0)
+    ijk = (np.floor(tgt * inv) - mn.astype(np.float32)).astype(np.int32)
+    keys = ijk[:, 0] + ijk[:, 1] * dv[0] + ijk[:, 2] * dv[0] * dv[1]
+    uk, cnt = np.unique(keys, return_counts=True)
+    lv = o.leaves()
+    assert np.array_equal(lv["keys"], uk) and np.array_equal(lv["raw_points"], cnt)
+    assert np.array_equal(o.lookup_keys(tgt), keys)         # leaf 1.0 is a power of two: mul and div index forms agree
+
+
+def _fd(f, p, i, h):
+    e = np.zeros(6); e[i] = h
+    return (f(p + e) - f(p - e)) / (2 * h)
+
+
+def _interior_points(src, T, margin):
+    """Source points whose transformed position stays `margin` away from every voxel face: the NDT score is only piecewise
+    smooth (a point changes neighbourhood when it crosses a face), so finite differences are taken where no point crosses."""
+    x = O.transform(src, T).astype(np.float64)
+    fr = x - np.floor(x)
+    return src[(np.minimum(fr, 1 - fr).min(axis=1) > margin)]
+
+
+@pytest.mark.parametrize("variant,search", [(O.VAR_OMP, O.DIRECT7), (O.VAR_OMP, O.DIRECT1), (O.VAR_PCA, O.DIRECT1), (O.VAR_PCA, O.DIRECT7)])
+def test_gradient_and_hessian_against_finite_differences(small_pair, variant, search):
+    tgt, src, guess, truth = small_pair
+    o = O.OracleNDT(variant=variant, search=search, num_threads=1)
+    o.set_target(tgt)
+    score = lambda p: o.eval_derivatives(p, None, False)[0]
+    grad = lambda p: o.eval_derivatives(p, None, False)[1]
+    ht, hr = 2e-3, 1e-4
+    # (a) p = 0: the reference's Jacobian [I | -[R x]x] is the exact derivative in all six directions
+    p0 = np.zeros(6)
+    o.set_source(_interior_points(src, np.eye(4, dtype=np.float32), 0.03))
+    s, g, H = o.eval_derivatives(p0)
+    assert abs(s) > 100
+    for i in range(6):
+        fd = _fd(score, p0, i, ht if i < 3 else hr)
+        assert abs(fd - g[i]) <= 5e-3 * np.abs(g[:3] if i < 3 else g[3:]).max(), (i, fd, g[i])
+    # (b) a pure translation: exact for the translation block anywhere; the Hessian block is the derivative of the gradient
+    pt = np.array([0.4, -0.2, 0.05, 0, 0, 0.0])
+    o.set_source(_interior_points(src, O.se3_exp_matrix4f(pt), 0.03))
+    s, g, H = o.eval_derivatives(pt)
+    for i in range(3):
+        assert abs(_fd(score, pt, i, ht) - g[i]) <= 5e-3 * np.abs(g[:3]).max()
+        col = np.array([_fd(lambda q: grad(q)[j], pt, i, ht) for j in range(3)])
+        np.testing.assert_allclose(col, H[:3, i], rtol=0, atol=1e-2 * np.abs(H[:3, :3]).max())
+    assert np.abs(H - H.T).max() > 0                        # quirk 9: the rot-rot block is not symmetric
+    np.testing.assert_allclose(H[:3, :3], H[:3, :3].T, rtol=0, atol=1e-5 * np.abs(H[:3, :3]).max())
+
+
+def test_double_hessian_close_to_float_hessian(small_pair):
+    tgt, src, guess, truth = small_pair
+    o = O.OracleNDT(search=O.KDTREE, num_threads=1)
+    o.set_target(tgt); o.set_source(src[::5])
+    p = O.se3_log_from_matrix4f(guess)
+    _, _, Hf = o.eval_derivatives(p)
+    Hd = o.eval_hessian(p)
+    np.testing.assert_allclose(Hf, Hd, rtol=0, atol=1e-4 * np.abs(Hd).max())     # same neighbours, float32 vs float64 terms
+
+
+def test_align_recovers_known_motion_and_quirks(scan_pair):
+    tgt, src, guess, truth = scan_pair
+    o = O.OracleNDT(trans_eps=0.01, max_iter=64, search=O.DIRECT7, num_threads=os.cpu_count() or 1)
+    o.set_target(tgt); o.set_source(src)
+    r = o.align(guess)
+    assert r["converged"] and r["iterations"] >= 2          # quirk 7: at least two iterations
+    assert r["n_eval"] == r["iterations"] + 1 and r["n_hess"] == 0   # `interval_converged = (step_max - step_min) > 0` disables the MT loop
+    assert np.abs(r["final"][:3, 3] - truth[:3, 3]).max() < 0.05
+    assert (np.abs(r["trace"][:, 12]) <= 0.1 + 1e-12).all() # steps are clamped to step_size
+    # final_transformation_ is exp(x_t) of the LAST line-search point, i.e. p_before + dir * step of the last iteration (quirk 2)
+    last = r["trace"][-1]
+    np.testing.assert_array_equal(r["final"], O.se3_exp_matrix4f(last[0:6] + last[6:12] * last[12]))
+    # max_iterations + 2 iterations are possible (quirk 7)
+    o2 = O.OracleNDT(trans_eps=1e-9, max_iter=3, search=O.DIRECT7, num_threads=1)
+    o2.set_target(tgt[::8]); o2.set_source(src[::8])
+    assert o2.align(guess)["iterations"] == 5
+
+
+def test_golden_regression_of_the_oracle(small_pair):
+    """tests/golden/ndt_small_pair.json was written by tests/golden/make_golden.py from THIS oracle (not from the reference,
+    which cannot be built here): it pins the oracle against accidental edits."""
+    path = os.path.join(HERE, "golden", "ndt_small_pair.json")
+    gold = json.load(open(path))
+    tgt, src, guess, truth = small_pair
+    o = O.OracleNDT(trans_eps=0.01, max_iter=30, search=O.DIRECT7, num_threads=1)
+    o.set_target(tgt); o.set_source(src)
+    lv = o.leaves()
+    assert len(lv["keys"]) == gold["n_cells"] and int((lv["nr_points"] >= 6).sum()) == gold["n_usable"]
+    assert int(lv["keys"].astype(np.int64).sum()) == gold["key_sum"]
+    s, g, H = o.eval_derivatives(O.se3_log_from_matrix4f(guess), guess)
+    np.testing.assert_allclose(s, gold["score"], rtol=1e-12)
+    np.testing.assert_allclose(g, gold["gradient"], rtol=1e-10, atol=1e-9 * np.abs(g).max())
+    np.testing.assert_allclose(H, np.array(gold["hessian"]), rtol=1e-10, atol=1e-9 * np.abs(H).max())
+    r = o.align(guess)
+    assert r["iterations"] == gold["iterations"]
+    np.testing.assert_allclose(r["final"], np.array(gold["final"], dtype=np.float32), atol=1e-6)
