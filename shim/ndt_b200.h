@@ -1,0 +1,101 @@
+// Reference-side binding for the NDT path: a pcl::Registration subclass with the class name, namespace and setters of
+// pclomp::NormalDistributionsTransform (/root/reference/include/ndt_omp/ndt_omp.h:69-551) — and, under LVS_SHIM_PCA, of
+// pclpca::NormalDistributionsTransform (include/ndt_pca/ndt_pca.h) — whose computeTransformation forwards to liblvslam_b200.
+// Header-only; needs PCL 1.8 + Eigen, which are NOT in the build image of this repository, so it is compiled only on the
+// lv_slam side.  It replaces src/ndt_omp/ndt_omp.cpp / src/ndt_pca/ndt_pca.cpp in lv_slam's CMake targets.
+#pragma once
+#include <pcl/point_types.h>
+#include <pcl/registration/registration.h>
+#include <stdexcept>
+#include "lvslam_b200.h"
+
+#ifdef LVS_SHIM_PCA
+namespace pclpca {
+#else
+namespace pclomp {
+#endif
+
+enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };   // ndt_omp.h:61
+
+template <typename PointSource, typename PointTarget>
+class NormalDistributionsTransform : public pcl::Registration<PointSource, PointTarget> {
+  typedef pcl::Registration<PointSource, PointTarget> Base;
+  typedef typename Base::PointCloudSource PointCloudSource;
+  typedef typename Base::PointCloudTarget PointCloudTarget;
+  typedef typename PointCloudTarget::ConstPtr PointCloudTargetConstPtr;
+  typedef typename PointCloudSource::ConstPtr PointCloudSourceConstPtr;
+
+ public:
+  typedef boost::shared_ptr<NormalDistributionsTransform<PointSource, PointTarget> > Ptr;
+
+  NormalDistributionsTransform() {
+    this->reg_name_ = "NormalDistributionsTransform";
+    lvs_ndt_default_params(&prm_);
+#ifdef LVS_SHIM_PCA
+    prm_.variant = LVS_NDT_PCA;
+#endif
+    this->transformation_epsilon_ = prm_.transformation_epsilon;
+    this->max_iterations_ = prm_.max_iterations;
+    check(lvs_ndt_create(&prm_, 0, nullptr, &h_));
+  }
+  virtual ~NormalDistributionsTransform() { lvs_ndt_destroy(h_); }
+
+  void setNumThreads(int) {}   // OpenMP team size of the CPU implementation
+  inline void setInputTarget(const PointCloudTargetConstPtr& cloud) {
+    Base::setInputTarget(cloud);
+    const PointTarget* p = cloud->points.data();
+    check(lvs_ndt_set_target(h_, &p->x, cloud->points.size(), sizeof(PointTarget), 0));
+  }
+  inline void setInputSource(const PointCloudSourceConstPtr& cloud) {
+    Base::setInputSource(cloud);
+    const PointSource* p = cloud->points.data();
+    check(lvs_ndt_set_source(h_, &p->x, cloud->points.size(), sizeof(PointSource), 0));
+  }
+  inline void setResolution(float r) { prm_.resolution = r; push(); }
+  inline float getResolution() const { return prm_.resolution; }
+  inline double getStepSize() const { return prm_.step_size; }
+  inline void setStepSize(double s) { prm_.step_size = s; push(); }
+  inline double getOulierRatio() const { return prm_.outlier_ratio; }
+  inline void setOulierRatio(double o) { prm_.outlier_ratio = o; push(); }
+  inline void setNeighborhoodSearchMethod(NeighborSearchMethod m) { prm_.search_method = (int)m; push(); }
+  inline double getTransformationProbability() const { return res_.trans_probability; }
+  inline int getFinalNumIteration() const { return res_.iterations; }
+  double calculateScore(const PointCloudSource& cloud) const {   // evaluates an already transformed cloud (ndt_omp_impl2.hpp:1007-1040)
+    lvs_ndt_t* tmp = nullptr;
+    check(lvs_ndt_create(&prm_, 0, nullptr, &tmp));
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double s = 0;
+    const PointTarget* t = this->target_->points.data();
+    int rc = lvs_ndt_set_target(tmp, &t->x, this->target_->points.size(), sizeof(PointTarget), 0);
+    if (!rc) rc = lvs_ndt_set_source(tmp, &cloud.points.data()->x, cloud.points.size(), sizeof(PointSource), 0);
+    if (!rc) rc = lvs_ndt_calculate_score(tmp, I, &s);
+    lvs_ndt_destroy(tmp);
+    check(rc);
+    return s;
+  }
+
+ protected:
+  // pcl::Registration::align() calls this after copying the source into `output`.
+  virtual void computeTransformation(PointCloudSource& output, const Eigen::Matrix4f& guess) {
+    prm_.transformation_epsilon = this->transformation_epsilon_;   // setTransformationEpsilon / setMaximumIterations live in the base class
+    prm_.max_iterations = this->max_iterations_;
+    push();
+    check(lvs_ndt_align(h_, guess.data(), &res_));                 // Eigen::Matrix4f is column-major, like the ABI
+    this->nr_iterations_ = res_.iterations;
+    this->converged_ = res_.converged != 0;
+    this->final_transformation_ = Eigen::Map<const Eigen::Matrix4f>(res_.final_transformation);
+    // the reference leaves the cloud of the last line-search point in `output`
+    std::vector<float> xyz(3 * output.points.size());
+    check(lvs_ndt_get_aligned_cloud(h_, xyz.data(), 0));
+    for (size_t i = 0; i < output.points.size(); i++) { output.points[i].x = xyz[3 * i]; output.points[i].y = xyz[3 * i + 1]; output.points[i].z = xyz[3 * i + 2]; }
+  }
+
+ private:
+  void push() { check(lvs_ndt_set_params(h_, &prm_)); }
+  static void check(int rc) { if (rc != LVS_OK) throw std::runtime_error(std::string("lvslam_b200: ") + lvs_status_string(rc) + ": " + lvs_last_error()); }
+  lvs_ndt_t* h_ = nullptr;
+  lvs_ndt_params prm_;
+  lvs_ndt_result res_{};
+};
+
+}  // namespace
