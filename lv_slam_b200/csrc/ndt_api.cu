@@ -86,6 +86,7 @@ struct lvs_ndt_batch {
   double* d_partials = nullptr;
   unsigned int* d_tickets = nullptr;
   int *d_done = nullptr, *h_done = nullptr;
+  GridParams* h_gp_all = nullptr;   // pinned, one per target slot: batched geometry read-back
   float* d_T16 = nullptr;        // scratch 16 floats
   double *d_scalar = nullptr, *h_scalar = nullptr;
   int trace_on = 0;
@@ -142,6 +143,35 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
   return rc;
 }
 
+// Completes every queued voxelisation among `slots` with ONE synchronisation (plus a rebuild for the rare slot whose
+// bounding box outgrew its index grid).
+static int finish_targets(lvs_ndt_batch* b, const int32_t* slots, int n) {
+  bool any = false;
+  for (int i = 0; i < n; i++) {
+    TargetGrid& t = b->targets[slots[i]];
+    if (t.pending && !t.fetch_queued) {
+      CUDA_TRY(cudaMemcpyAsync(&b->h_gp_all[slots[i]], t.d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, b->st));
+      b->d2h_bytes += sizeof(GridParams);
+      t.fetch_queued = true;
+      any = true;
+    }
+  }
+  if (!any) return LVS_OK;
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  CUDA_TRY(cudaGetLastError());
+  for (int i = 0; i < n; i++) {
+    TargetGrid& t = b->targets[slots[i]];
+    if (!t.fetch_queued) continue;
+    t.fetch_queued = false;
+    int rc = t.accept(b->h_gp_all[slots[i]], b->st, b->ws);
+    if (rc) return rc;
+    if (t.pending) { b->total_launches += t.launches_last_build; if ((rc = t.finish(b->st, b->ws))) return rc; }
+  }
+  return LVS_OK;
+}
+
+static int finish_target(lvs_ndt_batch* b, int slot) { const int32_t s = slot; return finish_targets(b, &s, 1); }
+
 static int reserve_pairs(lvs_ndt_batch* b, int n_pairs, int bpp) {
   if (n_pairs > b->pair_cap) {
     if (b->d_pairs) cudaFree(b->d_pairs);
@@ -185,13 +215,26 @@ static PairDesc make_pair(lvs_ndt_batch* b, int src_slot, int tgt_slot) {
   return P;
 }
 
+// CTAs per pair.  All CTAs of a launch are identical in cost to first order, so what matters is wave quantisation: the launch
+// runs ceil(total / resident) waves and the last one should be full.  A CTA should also iterate a few times (its prologue and
+// the 43-double reduction are fixed costs) unless that would leave SMs idle.
 static int choose_bpp(lvs_ndt_batch* b, int n_pairs, int max_src) {
   if (b->blocks_per_pair_override > 0) return b->blocks_per_pair_override;
   const int ppi = eval_points_per_cta_iteration();
-  int by_points = std::max(1, (max_src + ppi - 1) / ppi);                      // one warp iteration per warp
-  int resident = 148 * eval_max_resident_ctas_per_sm();                        // one full wave of CTAs
-  int by_machine = std::max(1, (resident + n_pairs - 1) / n_pairs);
-  return std::max(1, std::min(by_points, std::max(by_machine, 4)));
+  const int by_points = std::max(1, (max_src + ppi - 1) / ppi);          // one iteration per CTA: the finest useful split
+  const int resident = 148 * eval_max_resident_ctas_per_sm();
+  if ((long long)n_pairs * by_points <= resident) return by_points;      // cannot even fill one wave: use every SM we can
+  const int coarse = std::max(1, by_points / 4);                          // >= 4 iterations per CTA
+  int best = 1;
+  double best_eff = -1.0;
+  for (int bpp = 1; bpp <= std::max(coarse, (resident + n_pairs - 1) / n_pairs); bpp++) {
+    if (bpp > by_points) break;
+    const long long total = (long long)n_pairs * bpp;
+    const long long waves = (total + resident - 1) / resident;
+    const double eff = (double)total / (double)(waves * resident);
+    if (eff >= best_eff - 1e-9) { best_eff = std::max(eff, best_eff); best = bpp; }
+  }
+  return best;
 }
 
 // Runs the evaluation launches of one batch until every pair's state machine reports done.
@@ -207,6 +250,7 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
     if (!b->sources[s].set) return fail(LVS_ERR_NO_SOURCE, "pair %d: source slot %d has no cloud (setInputSource not called)", i, s);
     max_src = std::max(max_src, b->sources[s].n);
   }
+  if ((rc = finish_targets(b, tgt_slot, n_pairs))) return rc;
   const int bpp = choose_bpp(b, n_pairs, max_src);
   if ((rc = reserve_pairs(b, n_pairs, bpp))) return rc;
   for (int i = 0; i < n_pairs; i++) {
@@ -298,6 +342,7 @@ static int run_tap(lvs_ndt_batch* b, int kind, const double p[6], const float* T
   if (rc) return rc;
   if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  if ((rc = finish_target(b, 0))) return rc;
   const int bpp = choose_bpp(b, 1, b->sources[0].n);
   if ((rc = reserve_pairs(b, 1, bpp))) return rc;
   b->h_pairs[0] = make_pair(b, 0, 0);
@@ -357,6 +402,7 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
   }
   if ((e = cudaMalloc(&b->d_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
+  if ((e = cudaMallocHost(&b->h_gp_all, n_t * sizeof(GridParams))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_T16, 16 * sizeof(float))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_scalar, 8 * sizeof(double))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_scalar, 8 * sizeof(double))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
@@ -373,7 +419,6 @@ static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   if ((rc = upload_cloud(b, b->target_pts[slot], xyz, n, stride_bytes, on_device))) return rc;
   rc = b->targets[slot].build(b->st, b->target_pts[slot].d_pts, (int)n, b->prm, b->ws);
   b->total_launches += b->targets[slot].launches_last_build;
-  b->d2h_bytes += 2 * (long long)sizeof(GridParams);   // grid geometry read back to size the dense index grid
   return rc;
 }
 
@@ -456,6 +501,7 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   if (b->h_pairs) cudaFreeHost(b->h_pairs);
   if (b->h_states) cudaFreeHost(b->h_states);
   if (b->h_done) cudaFreeHost(b->h_done);
+  if (b->h_gp_all) cudaFreeHost(b->h_gp_all);
   if (b->h_scalar) cudaFreeHost(b->h_scalar);
   if (b->ev_begin) cudaEventDestroy(b->ev_begin);
   if (b->ev_end) cudaEventDestroy(b->ev_end);
@@ -522,6 +568,9 @@ int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* 
 int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int slot, int* n_cells, int* n_valid) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
+  int rc = set_device(b);
+  if (!rc) rc = finish_target(b, slot);
+  if (rc) return rc;
   if (n_cells) *n_cells = b->targets[slot].n_cells;
   if (n_valid) *n_valid = b->targets[slot].gp.n_valid;
   return LVS_OK;
@@ -651,6 +700,7 @@ int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score) {
   if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
   if (b->sources[0].n == 0) { *score = NAN; return LVS_OK; }   // 0/0 in the reference
+  if ((rc = finish_target(b, 0))) return rc;
   const int bpp = choose_bpp(b, 1, b->sources[0].n);
   if ((rc = reserve_pairs(b, 1, bpp))) return rc;
   PairDesc P = make_pair(b, 0, 0);
@@ -665,6 +715,7 @@ int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score) {
 
 int lvs_ndt_get_grid(lvs_ndt_t* h, int32_t min_b[3], int32_t max_b[3], int32_t div_b[3]) {
   if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  { int rc = set_device(h->b); if (!rc) rc = finish_target(h->b, 0); if (rc) return rc; }
   const GridParams& g = h->b->targets[0].gp;
   for (int a = 0; a < 3; a++) {
     if (min_b) min_b[a] = g.min_b[a];
@@ -676,6 +727,7 @@ int lvs_ndt_get_grid(lvs_ndt_t* h, int32_t min_b[3], int32_t max_b[3], int32_t d
 
 int lvs_ndt_num_cells(lvs_ndt_t* h, int* n_cells) {
   if (!h || !n_cells) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  { int rc = set_device(h->b); if (!rc) rc = finish_target(h->b, 0); if (rc) return rc; }
   *n_cells = h->b->targets[0].n_cells;
   return LVS_OK;
 }
@@ -684,6 +736,7 @@ int lvs_ndt_get_cells(lvs_ndt_t* h, int32_t* keys, int32_t* nr_points, double* m
   if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   lvs_ndt_batch* b = h->b;
   int rc = set_device(b);
+  if (!rc) rc = finish_target(b, 0);
   if (rc) return rc;
   const TargetGrid& t = b->targets[0];
   const int n = t.n_cells;
@@ -718,6 +771,7 @@ int lvs_ndt_lookup_keys(lvs_ndt_t* h, const float T16[16], int32_t* keys_out) {
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
   const int n = b->sources[0].n;
   if (n == 0) return LVS_OK;
+  if ((rc = finish_target(b, 0))) return rc;
   PairDesc P = make_pair(b, 0, 0);
   int* d_keys = nullptr;
   CUDA_TRY(cudaMalloc(&d_keys, (size_t)n * 4));

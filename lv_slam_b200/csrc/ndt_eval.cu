@@ -25,7 +25,8 @@ __constant__ int c_off26[26][3] = {
     {1, 1, 1},    {1, 0, 1},   {1, -1, 1},  {0, 1, 1},   {0, 0, 1},  {0, -1, 1},  {-1, 1, 1},  {-1, 0, 1},  {-1, -1, 1},
     {1, 1, 0},    {0, 1, 0},   {-1, 1, 0},  {1, 0, 0}};
 
-constexpr int kTileStride = 33;            // floats per output row of the staging tile (32 lanes + 1 pad: conflict-free both ways)
+constexpr int kTileStride = 36;            // floats per output row of the staging tile: 32 lanes + 4 pad keeps rows 16 B aligned for the
+                                           // LDS.128 reads of the summing lanes and both the column writes and those reads conflict-free
 constexpr int kWarps = kEvalThreads / 32;
 
 template <bool HESS>
@@ -156,15 +157,17 @@ __device__ __forceinline__ void process_round(double* acc, const PairDesc& P, co
       const int task = lane + 32 * t;
       const int o = task >> 2, g = task & 3;
       const bool live = task < Sh::NTASK && ((umask >> (8 * g)) & 0xffu) != 0u;
-      const float* row = tile + (task < Sh::NTASK ? o : 0) * kTileStride + 8 * g;
+      const float4* row = reinterpret_cast<const float4*>(tile + (task < Sh::NTASK ? o : 0) * kTileStride + 8 * g);
+      const float4 lo = row[0], hi = row[1];
+      const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
       double a = acc[t];
 #pragma unroll
       for (int jj = 0; jj < 8; jj++) {
         if (PCA) {
           const double wj = __shfl_sync(0xffffffffu, w, 8 * g + jj);   // all 32 lanes take part in the shuffle
-          if (live) a += (double)row[jj] * wj;
+          if (live) a += (double)v[jj] * wj;
         } else {
-          if (live) a += (double)row[jj];
+          if (live) a += (double)v[jj];
         }
       }
       acc[t] = a;

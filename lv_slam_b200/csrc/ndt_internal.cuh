@@ -27,6 +27,9 @@ struct BuildScratch {                    // reusable workspace of the voxelisati
   int* d_idx[2] = {nullptr, nullptr};
   int *d_flags = nullptr, *d_pos = nullptr, *d_seg_start = nullptr, *d_hist = nullptr, *d_hist_scan = nullptr;
   float* d_bbox_partial = nullptr;
+  int* d_tile_tot = nullptr;             // per-tile totals of the two-level scans
+  double* d_moments = nullptr;           // [cell][9] S1, upper S2
+  float* d_csum = nullptr;               // [cell][3] float centroid sums
   unsigned int* d_ticket = nullptr;
   int *d_nseg = nullptr, *d_nvalidpts = nullptr;
   GridParams* h_gp = nullptr;            // pinned
@@ -50,7 +53,15 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   size_t cell_capacity = 0;
   int n_cells = 0;
   int launches_last_build = 0;
-  int build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws);
+  int prev_points = 0;                   // points of the build whose cells are currently marked in d_grid
+  bool pending = false;                  // a build is queued and its geometry has not been read back yet
+  bool fetch_queued = false;             // a read-back of d_gp into the batch's pinned array is in flight
+  lvs_ndt_params built_with{};
+  int build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws);   // asynchronous
+  int finish(cudaStream_t st, BuildScratch& ws);                                                         // lazy completion
+  int accept(const GridParams& g, cudaStream_t st, BuildScratch& ws);
+  int enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch& ws);
+  int grow_grid(cudaStream_t st, long long cells);
   void free_cells();
   void release();
 };

@@ -2,15 +2,16 @@
 // (include/ndt_omp/voxel_grid_covariance_omp_impl.hpp:49-370; pca label/weight
 // include/ndt_pca/voxel_grid_covariance_pca_impl.hpp:364-397).
 //
-// Pipeline (all stream-ordered, one host read-back of the grid geometry to size the dense index grid):
-//   pack_points      strided host layout -> float4
-//   bbox_kernel      min/max reduce, last CTA derives min_b/max_b/div_b/mul  (:72-103)
-//   key_kernel       int32 voxel key per point, float math exactly as :218-223
-//   radix sort       stable LSD sort of (key, point index): 8-bit digits, hist / scan / scatter
-//   head + scan      unique keys -> one segment per occupied cell, ascending key (= std::map order)
-//   leaf_kernel      one warp per cell: lanes 0..8 own the nine f64 moment accumulators, lanes 9..11 the
-//                    f32 centroid sums, each summed SEQUENTIALLY IN INPUT ORDER (bit-identical to the
-//                    reference's serial accumulation); lane 0 then finalises the leaf (:281-367)
+// Pipeline (all stream-ordered and asynchronous: no host synchronisation once the dense index grid has its capacity —
+// the geometry is checked on the device and read back lazily, see TargetGrid::finish):
+//   pack_points          strided host layout -> float4
+//   bbox_kernel          min/max reduce, last CTA derives min_b/max_b/div_b/mul  (:72-103) and checks the grid capacity
+//   key_kernel           int32 voxel key per point, float math exactly as :218-223
+//   radix sort           stable LSD sort of (key, point index): 8-bit digits, hist / two-level scan / scatter
+//   head + scan          unique keys -> one segment per occupied cell, ascending key (= std::map order)
+//   leaf_moments_kernel  one warp per cell: lanes 0..8 own the nine f64 moment accumulators, lanes 9..11 the f32 centroid
+//                        sums, each summed SEQUENTIALLY IN INPUT ORDER (bit-identical to the reference's serial accumulation)
+//   leaf_finalize_kernel one thread per cell: mean, covariance, eigen-decomposition, inflation, inverse, PCA weight (:281-367)
 // Compiled with -fmad=false: no mul/add contraction anywhere in this file.
 #include "ndt_internal.cuh"
 
@@ -25,8 +26,11 @@ __global__ void pack_points_kernel(const float* __restrict__ in, size_t stride_f
 }
 
 // ------------------------------------------------------------------ bbox
-__global__ void bbox_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partial /*[grid][6]*/,
-                            unsigned int* __restrict__ ticket, GridParams* __restrict__ gp, float leaf) {
+constexpr int kBboxBlocks = 148;
+constexpr int kStatusEmpty = 1, kStatusNeedsGrow = 2;
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partial /*[grid][8]*/,
+                                                   unsigned int* __restrict__ ticket, GridParams* __restrict__ gp, float leaf, long long grid_capacity) {
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   int cnt = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -37,47 +41,53 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, float* __rest
       cnt++;
     }
   }
-  __shared__ float s_mn[3][32], s_mx[3][32];
-  __shared__ int s_cnt[32];
+  __shared__ float s_mn[3][8], s_mx[3][8];
+  __shared__ int s_cnt[8];
   __shared__ bool s_last;
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int o = 16; o; o >>= 1) {
-    for (int a = 0; a < 3; a++) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_reduce = [&]() {
+    for (int o = 16; o; o >>= 1) {
+      for (int a = 0; a < 3; a++) {
+        mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+        mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+      }
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  if (lane == 0) { for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; } s_cnt[warp] = cnt; }
-  __syncthreads();
+    if (lane == 0) { for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; } s_cnt[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int w = 1; w < 8; w++) {
+        for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], s_mn[a][w]); mx[a] = fmaxf(mx[a], s_mx[a][w]); }
+        cnt += s_cnt[w];
+      }
+  };
+  block_reduce();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < nw; w++) {
-      for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], s_mn[a][w]); mx[a] = fmaxf(mx[a], s_mx[a][w]); }
-      cnt += s_cnt[w];
-    }
     float* o = partial + blockIdx.x * 8;
     o[0] = mn[0]; o[1] = mn[1]; o[2] = mn[2]; o[3] = mx[0]; o[4] = mx[1]; o[5] = mx[2]; o[6] = __int_as_float(cnt);
     __threadfence();
-    unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last) return;
   __threadfence();
   for (int a = 0; a < 3; a++) { mn[a] = INFINITY; mx[a] = -INFINITY; }
   cnt = 0;
-  for (unsigned b = 0; b < gridDim.x; b++) {
-    const volatile float* o = partial + b * 8;
-    for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], o[a]); mx[a] = fmaxf(mx[a], o[3 + a]); }
-    cnt += __float_as_int(o[6]);
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    const float* o = partial + b * 8;
+    for (int a = 0; a < 3; a++) { mn[a] = fminf(mn[a], __ldcg(o + a)); mx[a] = fmaxf(mx[a], __ldcg(o + 3 + a)); }
+    cnt += __float_as_int(__ldcg(o + 6));
   }
+  __syncthreads();
+  block_reduce();
+  if (threadIdx.x != 0) return;
   *ticket = 0;
   GridParams g;
   g.leaf = leaf;
   g.inv_leaf = __fdiv_rn(1.0f, leaf);               // pcl::VoxelGrid::setLeafSize
   g.n_points = cnt; g.n_cells = 0; g.n_valid = 0; g.status = 0; g.total_cells = 0;
   for (int a = 0; a < 3; a++) { g.min_p[a] = mn[a]; g.max_p[a] = mx[a]; g.min_b[a] = g.max_b[a] = g.div_b[a] = g.mul[a] = 0; }
-  if (cnt == 0) { g.status = 1; *gp = g; return; }
+  if (cnt == 0) { g.status = kStatusEmpty; *gp = g; return; }
   // overflow guard (:76-85)
   long long dx = (long long)__fmul_rn(__fsub_rn(mx[0], mn[0]), g.inv_leaf) + 1;
   long long dy = (long long)__fmul_rn(__fsub_rn(mx[1], mn[1]), g.inv_leaf) + 1;
@@ -90,6 +100,7 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, float* __rest
   }
   g.mul[0] = 1; g.mul[1] = g.div_b[0]; g.mul[2] = g.div_b[0] * g.div_b[1];
   g.total_cells = (long long)g.div_b[0] * g.div_b[1] * g.div_b[2];
+  if (g.total_cells > grid_capacity) g.status = kStatusNeedsGrow;   // the host grows the index grid and rebuilds (TargetGrid::finish)
   *gp = g;
 }
 
@@ -102,7 +113,7 @@ __global__ void key_kernel(const float4* __restrict__ pts, int n, const GridPara
   if (i >= n) return;
   float4 p = pts[i];
   unsigned int k = kInvalidKey;
-  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+  if (gp->status == 0 && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
     float inv = gp->inv_leaf;
     int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)gp->min_b[0]);
     int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)gp->min_b[1]);
@@ -113,35 +124,55 @@ __global__ void key_kernel(const float4* __restrict__ pts, int n, const GridPara
   idx[i] = i;
 }
 
-// ------------------------------------------------------------------ single-CTA exclusive scan
-// out[i] = sum_{j<i} in[j]; total written to *total (may be null).  n up to a few million.
-__global__ void scan_exclusive_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
+// ------------------------------------------------------------------ two-level exclusive scan
+// scan_tiles_kernel: exclusive scan inside tiles of 2048 ints + the tile totals; scan_add_kernel: every CTA sums the totals
+// of the tiles before it (they are few) and adds that offset to its tile.  total (may be null) receives the grand total.
+constexpr int kScanThreads = 256, kScanIpt = 8, kScanTile = kScanThreads * kScanIpt;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ tile_tot) {
+  __shared__ int s_warp[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanIpt;
+  int v[kScanIpt], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanIpt; k++) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+  int x = sum;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_warp[warp] = x;
   __syncthreads();
-  for (int base = 0; base < n; base += T) {
-    int i = base + threadIdx.x;
-    int v = (i < n) ? in[i] : 0;
-    int x = v;
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int w = (lane < nw) ? s_warp[lane] : 0;
-      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-      s_warp[lane] = w;   // inclusive over warps
-    }
-    __syncthreads();
-    int carry = s_carry;
-    int warp_off = warp ? s_warp[warp - 1] : 0;
-    if (i < n) out[i] = carry + warp_off + x - v;
-    __syncthreads();
-    if (threadIdx.x == T - 1) s_carry = carry + warp_off + x;
-    __syncthreads();
+  if (warp == 0) {
+    int w = (lane < kScanThreads / 32) ? s_warp[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    if (lane < kScanThreads / 32) s_warp[lane] = w;   // inclusive over warps
   }
-  if (total && threadIdx.x == 0) *total = s_carry;
+  __syncthreads();
+  int run = (warp ? s_warp[warp - 1] : 0) + x - sum;
+#pragma unroll
+  for (int k = 0; k < kScanIpt; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+  if (threadIdx.x == kScanThreads - 1) tile_tot[blockIdx.x] = s_warp[kScanThreads / 32 - 1];
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ out, int n, const int* __restrict__ tile_tot, int* __restrict__ total) {
+  __shared__ int s_warp[kScanThreads / 32];
+  __shared__ int s_off;
+  int acc = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) acc += tile_tot[b];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < kScanThreads / 32; w++) t += s_warp[w]; s_off = t; }
+  __syncthreads();
+  const int off = s_off;
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanIpt;
+#pragma unroll
+  for (int k = 0; k < kScanIpt; k++) if (base + k < n) out[base + k] += off;
+  if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = off + tile_tot[blockIdx.x];
+}
+
+static void exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total, int* tile_tot) {
+  const int nb = (n + kScanTile - 1) / kScanTile;
+  scan_tiles_kernel<<<nb, kScanThreads, 0, st>>>(in, out, n, tile_tot);
+  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(out, n, tile_tot, total);
 }
 
 // ------------------------------------------------------------------ stable LSD radix sort, 8-bit digits
@@ -220,36 +251,35 @@ __global__ void seg_start_kernel(const unsigned int* __restrict__ keys, const in
   if (keys[i] != kInvalidKey && (i == n - 1 || keys[i + 1] == kInvalidKey)) { seg_start[*n_seg] = i + 1; *n_valid_pts = i + 1; }
 }
 
-__global__ void clear_cells_kernel(int* __restrict__ grid, const int* __restrict__ old_keys, int n_old) {
+__global__ void clear_cells_kernel(int* __restrict__ grid, const int* __restrict__ old_keys, const GridParams* __restrict__ gp_old) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_old) grid[old_keys[i]] = -1;
+  if (gp_old->status == 0 && i < gp_old->n_cells) grid[old_keys[i]] = -1;
 }
 
-// ------------------------------------------------------------------ per-cell moments + leaf finalisation
-__global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* __restrict__ keys, const int* __restrict__ sidx,
-                            const int* __restrict__ seg_start, const int* __restrict__ n_seg_p, VoxelRec* __restrict__ recs,
-                            float4* __restrict__ centroids, int* __restrict__ cell_keys, int* __restrict__ cell_npts,
-                            double* __restrict__ cell_evals, double* __restrict__ icov64, int* __restrict__ grid, GridParams* __restrict__ gp,
-                            int min_points, double eig_mult, int variant) {
+// ------------------------------------------------------------------ per-cell moments
+// One warp per occupied cell.  Lanes 0..8 own S1[3] and the upper triangle of S2, lanes 9..11 the float centroid sums; each
+// accumulator is summed sequentially in input order, which is what makes the result bit-identical to the reference's loop.
+__global__ void __launch_bounds__(256) leaf_moments_kernel(const float4* __restrict__ pts, const int* __restrict__ sidx, const int* __restrict__ seg_start,
+                                                           const int* __restrict__ n_seg_p, const GridParams* __restrict__ gp,
+                                                           double* __restrict__ moments /*[cell][9]*/, float* __restrict__ csum /*[cell][3]*/) {
+  if (gp->status != 0) return;
   __shared__ float s_pt[8][32][3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_seg = *n_seg_p;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
-  // which coordinate(s) this lane accumulates
   int ci = 0, cj = 0;
   if (lane < 3) { ci = lane; }
   else if (lane < 9) { const int I[6] = {0, 0, 0, 1, 1, 2}, J[6] = {0, 1, 2, 1, 2, 2}; ci = I[lane - 3]; cj = J[lane - 3]; }
   else if (lane < 12) { ci = lane - 9; }
-  int valid_cells = 0;
   for (int seg = blockIdx.x * (blockDim.x >> 5) + warp; seg < n_seg; seg += warps_total) {
     const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
     double acc = 0.0;
     float facc = 0.0f;
     for (int base = s0; base < s1; base += 32) {
-      int m = min(32, s1 - base);
+      const int m = min(32, s1 - base);
       __syncwarp();
       if (lane < m) {
-        float4 p = pts[sidx[base + lane]];
+        const float4 p = pts[sidx[base + lane]];
         s_pt[warp][lane][0] = p.x; s_pt[warp][lane][1] = p.y; s_pt[warp][lane][2] = p.z;
       }
       __syncwarp();
@@ -261,14 +291,26 @@ __global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* 
         for (int k = 0; k < m; k++) facc = __fadd_rn(facc, s_pt[warp][k][ci]);
       }
     }
-    // gather the nine sums + centroid on lane 0
-    double S1[3], S2[6];
-    float cs[3];
-    for (int a = 0; a < 3; a++) S1[a] = __shfl_sync(0xffffffffu, acc, a);
-    for (int a = 0; a < 6; a++) S2[a] = __shfl_sync(0xffffffffu, acc, 3 + a);
-    for (int a = 0; a < 3; a++) cs[a] = __shfl_sync(0xffffffffu, facc, 9 + a);
-    if (lane != 0) continue;
+    if (lane < 9) moments[(size_t)seg * 9 + lane] = acc;
+    else if (lane < 12) csum[(size_t)seg * 3 + (lane - 9)] = facc;
+  }
+}
 
+// ------------------------------------------------------------------ leaf finalisation, one thread per cell (:281-367)
+__global__ void __launch_bounds__(128) leaf_finalize_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ seg_start,
+                                                            const int* __restrict__ n_seg_p, const double* __restrict__ moments,
+                                                            const float* __restrict__ csum, VoxelRec* __restrict__ recs, float4* __restrict__ centroids,
+                                                            int* __restrict__ cell_keys, int* __restrict__ cell_npts, double* __restrict__ cell_evals,
+                                                            double* __restrict__ icov64, int* __restrict__ grid, GridParams* __restrict__ gp,
+                                                            int min_points, double eig_mult, int variant) {
+  if (gp->status != 0) return;
+  const int n_seg = *n_seg_p;
+  int valid_cells = 0;
+  for (int seg = blockIdx.x * blockDim.x + threadIdx.x; seg < n_seg; seg += gridDim.x * blockDim.x) {
+    const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
+    const double* mo = moments + (size_t)seg * 9;
+    const double S1[3] = {mo[0], mo[1], mo[2]};
+    const double S2[6] = {mo[3], mo[4], mo[5], mo[6], mo[7], mo[8]};
     const int npts = s1 - s0;
     const int key = (int)keys[s0];
     const double np = (double)npts;
@@ -278,8 +320,9 @@ __global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* 
     for (int a = 0; a < 3; a++) rec.mean[a] = mean[a];
     for (int a = 0; a < 9; a++) rec.icov[a] = 0.0f;
     rec.meta = 1;
-    float fn = (float)npts;
-    centroids[seg] = make_float4(__fdiv_rn(cs[0], fn), __fdiv_rn(cs[1], fn), __fdiv_rn(cs[2], fn), npts >= min_points ? 1.0f : 0.0f);
+    const float fn = (float)npts;
+    centroids[seg] = make_float4(__fdiv_rn(csum[(size_t)seg * 3], fn), __fdiv_rn(csum[(size_t)seg * 3 + 1], fn), __fdiv_rn(csum[(size_t)seg * 3 + 2], fn),
+                                 npts >= min_points ? 1.0f : 0.0f);
     int out_npts = npts;
     double ev[3] = {0, 0, 0};
     bool usable = false;
@@ -288,21 +331,16 @@ __global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* 
       double cov[9];
       const int sidx2[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
       for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-          double v = (S2[sidx2[i * 3 + j]] - 2.0 * (S1[i] * mean[j])) / np + mean[i] * mean[j];
-          cov[i * 3 + j] = v;
-        }
+        for (int j = 0; j < 3; j++) cov[i * 3 + j] = (S2[sidx2[i * 3 + j]] - 2.0 * (S1[i] * mean[j])) / np + mean[i] * mean[j];
       const double sc = (np - 1.0) / np;
       for (int a = 0; a < 9; a++) cov[a] *= sc;
-      // SelfAdjointEigenSolver reads the lower triangle only
-      double low[9] = {cov[0], cov[3], cov[6], cov[3], cov[4], cov[7], cov[6], cov[7], cov[8]};
       double V[9];
-      sym3_eigen(low, ev, V);
+      sym3_eigen(cov, ev, V);                 // reads the lower triangle, like SelfAdjointEigenSolver
       if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
         out_npts = -1;
-        ev[0] = ev[1] = ev[2] = 0.0;    // evals_ is assigned only after the check (:357)
+        ev[0] = ev[1] = ev[2] = 0.0;          // evals_ is assigned only after the check (:357)
       } else {
-        double min_ev = eig_mult * ev[2];
+        const double min_ev = eig_mult * ev[2];
         if (ev[0] < min_ev) {
           ev[0] = min_ev;
           if (ev[1] < min_ev) ev[1] = min_ev;
@@ -313,13 +351,13 @@ __global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* 
         }
         int weight = 1;
         if (variant == LVS_NDT_PCA) {
-          double s0_ = sqrt(ev[0]), s1_ = sqrt(ev[1]), s2_ = sqrt(ev[2]);
-          double f0 = (s2_ - s1_) / s2_, f1 = (s1_ - s0_) / s2_, f2 = s0_ / s2_;
+          const double s0_ = sqrt(ev[0]), s1_ = sqrt(ev[1]), s2_ = sqrt(ev[2]);
+          const double f0 = (s2_ - s1_) / s2_, f1 = (s1_ - s0_) / s2_, f2 = s0_ / s2_;
           int d = 0; double fm = f0;
           if (f1 > fm) { d = 1; fm = f1; }
           if (f2 > fm) { d = 2; }
-          double scale = d == 1 ? 1.25 : (d == 2 ? 1.0 : 0.75);
-          double nm = sqrt(mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]);
+          const double scale = d == 1 ? 1.25 : (d == 2 ? 1.0 : 0.75);
+          const double nm = sqrt(mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]);
           weight = (int)(scale * nm);           // int getDimension2d() truncation (voxel_grid_covariance_pca.h:222-226)
         }
         mat3_inverse(cov, ic);
@@ -339,49 +377,74 @@ __global__ void leaf_kernel(const float4* __restrict__ pts, const unsigned int* 
     grid[key] = usable ? seg : (-2 - seg);
     if (usable) valid_cells++;
   }
-  if (lane == 0 && valid_cells) atomicAdd(&gp->n_valid, valid_cells);
+  if (valid_cells) atomicAdd(&gp->n_valid, valid_cells);
   if (blockIdx.x == 0 && threadIdx.x == 0) gp->n_cells = n_seg;
 }
 
 // ------------------------------------------------------------------ host side
+static int radix_passes_for(long long cells) {   // keys < cells, invalid keys 0xFFFFFFFF sort last in every pass
+  int bits = 1;
+  while (bits < 32 && (1LL << bits) <= cells) bits++;
+  return (bits + 7) / 8;
+}
+
+// Queues the whole voxelisation on `st`.  Needs d_grid to exist; never synchronises.
+int TargetGrid::enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch& ws) {
+  const int n = n_points;
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  // wipe the cells of the previous build while the old keys and the old geometry still describe this buffer
+  if (prev_points > 0) clear_cells_kernel<<<(prev_points + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, d_gp);
+  bbox_kernel<<<std::min(kBboxBlocks, gb), 256, 0, st>>>(pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, prm.resolution, (long long)grid_capacity);
+  key_kernel<<<gb, tb, 0, st>>>(pts, n, d_gp, ws.d_keys[0], ws.d_idx[0]);
+  const int passes = radix_passes_for((long long)grid_capacity);
+  const int nblk = (n + kRsTile - 1) / kRsTile;
+  int cur = 0;
+  for (int p = 0; p < passes; p++) {
+    rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], n, p * 8, nblk, ws.d_hist);
+    exclusive_scan(st, ws.d_hist, ws.d_hist_scan, 256 * nblk, nullptr, ws.d_tile_tot);
+    rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], ws.d_idx[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], ws.d_idx[cur ^ 1]);
+    cur ^= 1;
+  }
+  head_flag_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], n, ws.d_flags);
+  CUDA_TRY(cudaMemsetAsync(ws.d_nseg, 0, 2 * sizeof(int), st));
+  exclusive_scan(st, ws.d_flags, ws.d_pos, n, ws.d_nseg, ws.d_tile_tot);
+  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, ws.d_seg_start, ws.d_nseg, ws.d_nvalidpts);
+  leaf_moments_kernel<<<std::min(148 * 8, (n + 7) / 8), 256, 0, st>>>(pts, ws.d_idx[cur], ws.d_seg_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
+  leaf_finalize_kernel<<<std::min(148 * 4, (n + 127) / 128), 128, 0, st>>>(ws.d_keys[cur], ws.d_seg_start, ws.d_nseg, ws.d_moments, ws.d_csum, d_recs,
+                                                                          d_centroids, d_cell_keys, d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp,
+                                                                          prm.min_points_per_voxel, prm.min_covar_eigvalue_mult, prm.variant);
+  CUDA_TRY(cudaGetLastError());
+  launches_last_build = (prev_points > 0 ? 1 : 0) + 2 + passes * 4 + 1 + 2 + 1 + 2;
+  prev_points = n;
+  pending = true;
+  return LVS_OK;
+}
+
 int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws) {
   n_points = n;
   pts = d_pts;
+  built_with = prm;
   CUDA_TRY(ws.reserve(n));
-  if (!d_gp) CUDA_TRY(cudaMalloc(&d_gp, sizeof(GridParams)));
-  // wipe the cells of the previous build while the old keys still describe this buffer
-  if (d_grid && n_cells > 0) {
-    clear_cells_kernel<<<(n_cells + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, n_cells);
-  }
-  n_cells = 0;
-  if (n == 0) {
-    GridParams g; memset(&g, 0, sizeof g); g.status = 1; g.leaf = prm.resolution; g.inv_leaf = 1.0f / prm.resolution;
+  if (!d_gp) {
+    CUDA_TRY(cudaMalloc(&d_gp, sizeof(GridParams)));
+    GridParams g; memset(&g, 0, sizeof g); g.status = kStatusEmpty;
     CUDA_TRY(cudaMemcpyAsync(d_gp, &g, sizeof g, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    gp = g;
-    return LVS_OK;
   }
-  int nb = std::min(1024, (n + 255) / 256);
-  CUDA_TRY(cudaMemsetAsync(ws.d_ticket, 0, sizeof(unsigned int), st));
-  bbox_kernel<<<nb, 256, 0, st>>>(d_pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, prm.resolution);
-  CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  gp = *ws.h_gp;
-  if (gp.status == LVS_ERR_GRID_OVERFLOW) return fail(LVS_ERR_GRID_OVERFLOW, "leaf size too small for the target extent: dx*dy*dz > INT32_MAX");
-  if (gp.status == 1) return LVS_OK;   // no finite point
-  // dense index grid: grow-only, -1 filled
-  if ((size_t)gp.total_cells > grid_capacity) {
-    if (d_grid) cudaFree(d_grid);
-    d_grid = nullptr;
-    size_t cap = (size_t)gp.total_cells + (size_t)gp.total_cells / 4 + 1024;
-    cudaError_t e = cudaMalloc(&d_grid, cap * sizeof(int));
-    if (e != cudaSuccess) { grid_capacity = 0; (void)cudaGetLastError(); return fail(LVS_ERR_OOM, "dense voxel index grid allocation failed"); }
-    grid_capacity = cap;
-    CUDA_TRY(cudaMemsetAsync(d_grid, 0xFF, cap * sizeof(int), st));
+  if (n == 0) {
+    if (prev_points > 0 && d_grid) clear_cells_kernel<<<(prev_points + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, d_gp);
+    prev_points = 0;
+    GridParams g; memset(&g, 0, sizeof g); g.status = kStatusEmpty; g.leaf = prm.resolution; g.inv_leaf = 1.0f / prm.resolution;
+    CUDA_TRY(cudaMemcpyAsync(d_gp, &g, sizeof g, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // g lives on this stack frame
+    gp = g; n_cells = 0; pending = false; launches_last_build = 0;
+    return LVS_OK;
   }
   // cell arrays sized for the worst case of one cell per point
   if ((size_t)n > cell_capacity) {
+    CUDA_TRY(cudaStreamSynchronize(st));
     free_cells();
+    prev_points = 0;                        // the old keys are gone; the grid is re-filled below
+    if (d_grid) CUDA_TRY(cudaMemsetAsync(d_grid, 0xFF, grid_capacity * sizeof(int), st));
     size_t cap = (size_t)n + n / 8 + 64;
     CUDA_TRY(cudaMalloc(&d_recs, cap * sizeof(VoxelRec)));
     CUDA_TRY(cudaMalloc(&d_centroids, cap * sizeof(float4)));
@@ -391,32 +454,56 @@ int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt
     CUDA_TRY(cudaMalloc(&d_icov64, cap * 9 * sizeof(double)));
     cell_capacity = cap;
   }
-  const int tb = 256, gb = (n + tb - 1) / tb;
-  key_kernel<<<gb, tb, 0, st>>>(d_pts, n, d_gp, ws.d_keys[0], ws.d_idx[0]);
-  // number of 8-bit passes needed for keys < total_cells (invalid keys 0xFFFFFFFF sort last in every pass)
-  int bits = 1;
-  while (bits < 32 && (1LL << bits) <= gp.total_cells) bits++;   // max key <= 2^bits - 2, never all-ones
-  int passes = (bits + 7) / 8;
-  const int nblk = (n + kRsTile - 1) / kRsTile;
-  int cur = 0;
-  for (int p = 0; p < passes; p++) {
-    rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], n, p * 8, nblk, ws.d_hist);
-    scan_exclusive_kernel<<<1, 1024, 0, st>>>(ws.d_hist, ws.d_hist_scan, 256 * nblk, nullptr);
-    rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], ws.d_idx[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], ws.d_idx[cur ^ 1]);
-    cur ^= 1;
+  if (!d_grid) {
+    // first build of this slot: the index grid has no capacity yet, so size it from the geometry (one synchronisation, once)
+    bbox_kernel<<<std::min(kBboxBlocks, (n + 255) / 256), 256, 0, st>>>(d_pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, prm.resolution, 0LL);
+    CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    gp = *ws.h_gp;
+    if (gp.status == LVS_ERR_GRID_OVERFLOW) { pending = false; n_cells = 0; return fail(LVS_ERR_GRID_OVERFLOW, "leaf size too small for the target extent: dx*dy*dz > INT32_MAX"); }
+    if (gp.status == kStatusEmpty) { pending = false; n_cells = 0; return LVS_OK; }   // no finite point
+    int rc = grow_grid(st, gp.total_cells);
+    if (rc) return rc;
   }
-  head_flag_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], n, ws.d_flags);
-  scan_exclusive_kernel<<<1, 1024, 0, st>>>(ws.d_flags, ws.d_pos, n, ws.d_nseg);
-  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, ws.d_seg_start, ws.d_nseg, ws.d_nvalidpts);
-  int lb = std::min(148 * 8, (n + 7) / 8);
-  leaf_kernel<<<lb, 256, 0, st>>>(d_pts, ws.d_keys[cur], ws.d_idx[cur], ws.d_seg_start, ws.d_nseg, d_recs, d_centroids, d_cell_keys,
-                                  d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp, prm.min_points_per_voxel, prm.min_covar_eigvalue_mult, prm.variant);
-  CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  CUDA_TRY(cudaGetLastError());
-  gp = *ws.h_gp;
-  n_cells = gp.n_cells;
-  launches_last_build = 6 + passes * 3;
+  return enqueue(st, prm, ws);
+}
+
+int TargetGrid::grow_grid(cudaStream_t st, long long cells) {
+  if (d_grid) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(d_grid); }
+  d_grid = nullptr; grid_capacity = 0;
+  size_t cap = (size_t)cells + (size_t)cells / 4 + 1024;
+  cudaError_t e = cudaMalloc(&d_grid, cap * sizeof(int));
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(LVS_ERR_OOM, "dense voxel index grid allocation failed (%lld cells)", cells); }
+  grid_capacity = cap;
+  CUDA_TRY(cudaMemsetAsync(d_grid, 0xFF, cap * sizeof(int), st));
+  prev_points = 0;
+  return LVS_OK;
+}
+
+// Completes a queued build: reads the geometry back (one small copy + synchronisation) and, if the bounding box outgrew the
+// index grid, grows it and rebuilds.  Called lazily by whoever needs the grid (align, taps).
+int TargetGrid::finish(cudaStream_t st, BuildScratch& ws) {
+  for (int attempt = 0; pending && attempt < 3; attempt++) {
+    CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    int rc = accept(*ws.h_gp, st, ws);
+    if (rc) return rc;
+  }
+  return LVS_OK;
+}
+
+// Takes a geometry record that has just been read back for the queued build.  Leaves `pending` set when it had to re-queue.
+int TargetGrid::accept(const GridParams& g, cudaStream_t st, BuildScratch& ws) {
+  gp = g;
+  pending = false;
+  if (gp.status == LVS_ERR_GRID_OVERFLOW) { n_cells = 0; return fail(LVS_ERR_GRID_OVERFLOW, "leaf size too small for the target extent: dx*dy*dz > INT32_MAX"); }
+  if (gp.status == kStatusNeedsGrow) {
+    int rc = grow_grid(st, gp.total_cells);
+    if (rc) return rc;
+    return enqueue(st, built_with, ws);     // pending again
+  }
+  n_cells = gp.status == 0 ? gp.n_cells : 0;
   return LVS_OK;
 }
 
@@ -455,7 +542,11 @@ cudaError_t BuildScratch::reserve(int n) {
   if ((e = cudaMalloc(&d_hist, (size_t)256 * nblk * sizeof(int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&d_hist_scan, (size_t)256 * nblk * sizeof(int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&d_bbox_partial, 1024 * 8 * sizeof(float))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_tile_tot, (size_t)(256 * nblk / kScanTile + cap / kScanTile + 16) * sizeof(int))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_moments, (size_t)cap * 9 * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_csum, (size_t)cap * 3 * sizeof(float))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&d_ticket, 4 * sizeof(unsigned int))) != cudaSuccess) return e;
+  if ((e = cudaMemset(d_ticket, 0, 4 * sizeof(unsigned int))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&d_nseg, 4 * sizeof(int))) != cudaSuccess) return e;
   d_nvalidpts = d_nseg + 1;
   if (!h_gp && (e = cudaMallocHost(&h_gp, sizeof(GridParams))) != cudaSuccess) return e;
@@ -471,6 +562,10 @@ void BuildScratch::release() {
   if (d_hist) cudaFree(d_hist);
   if (d_hist_scan) cudaFree(d_hist_scan);
   if (d_bbox_partial) cudaFree(d_bbox_partial);
+  if (d_tile_tot) cudaFree(d_tile_tot);
+  if (d_moments) cudaFree(d_moments);
+  if (d_csum) cudaFree(d_csum);
+  d_tile_tot = nullptr; d_moments = nullptr; d_csum = nullptr;
   if (d_ticket) cudaFree(d_ticket);
   if (d_nseg) cudaFree(d_nseg);
   d_flags = d_pos = d_seg_start = d_hist = d_hist_scan = nullptr; d_bbox_partial = nullptr; d_ticket = nullptr; d_nseg = nullptr;
