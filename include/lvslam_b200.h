@@ -140,6 +140,11 @@ int lvs_ndt_batch_create(const lvs_ndt_params* params, int device, void* stream,
 int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b);
 int lvs_ndt_batch_set_target(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device);
 int lvs_ndt_batch_set_source(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device);
+/* set_target / set_source with a HOST pointer queue the copy and the repack on the object's upload stream and return; the
+ * consumer (voxelisation, align) waits on the device for exactly the clouds it reads, so the copies of later clouds overlap
+ * the aligns of earlier ones.  A pageable host buffer may be reused as soon as the call returns; a PINNED host buffer is read
+ * by DMA and must stay untouched until lvs_ndt_batch_wait_uploads (or an align that consumes the slot) has returned. */
+int lvs_ndt_batch_wait_uploads(lvs_ndt_batch_t* b);
 int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot,
                         const float* guesses16 /* n_pairs x 16 */, lvs_ndt_result* results /* n_pairs */);
 /* Device time in ms of the last batch_align and the number of kernel launches it issued. */

@@ -82,6 +82,7 @@ def lib():
             "lvs_pgo_system_size": [vp, vp, vp], "lvs_pgo_linearize": [vp, vp, vp, vp, vp],
             "lvs_pgo_solve": [vp, ctypes.c_double, ctypes.c_double, i32, vp, vp],
             "lvs_ndt_batch_total_launches": [vp, vp], "lvs_ndt_batch_transfer_bytes": [vp, vp, vp], "lvs_ndt_batch_num_cells": [vp, i32, vp, vp],
+            "lvs_ndt_batch_wait_uploads": [vp],
         }.items():
             f = getattr(L, name)
             f.restype = i32

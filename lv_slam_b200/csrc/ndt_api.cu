@@ -59,6 +59,19 @@ struct CloudSlot {
   size_t cap = 0;
   int n = 0;
   bool set = false;
+  // Host clouds are copied and repacked on the batch's upload stream; `ready` marks the end of that work and is waited for by
+  // the compute stream the first time the slot is consumed.  `used` marks the last compute-stream reader that was queued
+  // without a host synchronisation (a voxelisation), so that a re-upload cannot overwrite points that are still being read.
+  cudaEvent_t ready = nullptr, used = nullptr;
+  bool ready_pending = false, used_pending = false;
+};
+
+constexpr int kStageRing = 4;        // upload staging buffers: H2D copy of cloud i+1 overlaps the repack of cloud i
+struct StageBuf {
+  float* d = nullptr;
+  size_t cap = 0;
+  cudaEvent_t free_ev = nullptr;     // recorded after the repack kernel that read this buffer
+  bool in_flight = false;
 };
 
 constexpr int kMaxEvents = 2048;
@@ -75,7 +88,12 @@ struct lvs_ndt_batch {
   BuildScratch ws;
   std::vector<TargetGrid> targets;
   std::vector<CloudSlot> target_pts, sources;
-  // upload staging
+  // upload path: its own stream, a ring of staging buffers, and one more staging buffer for results on the compute stream
+  cudaStream_t up = nullptr;
+  StageBuf ring[kStageRing];
+  int ring_next = 0;
+  cudaEvent_t ev_up_all = nullptr;
+  bool uploads_in_flight = false;
   float* d_stage = nullptr;
   size_t stage_cap = 0;
   // pair state
@@ -110,37 +128,76 @@ static int set_device(lvs_ndt_batch* b) {
   return LVS_OK;
 }
 
+// Makes the compute stream wait for the slot's upload (once; later compute work is ordered behind that wait).
+static int wait_ready(lvs_ndt_batch* b, CloudSlot& slot) {
+  if (slot.ready_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(b->st, slot.ready, 0));
+    slot.ready_pending = false;
+  }
+  return LVS_OK;
+}
+
+// Makes the compute stream wait for every upload queued so far (single-handle taps and getters).
+static int wait_all_uploads(lvs_ndt_batch* b) {
+  if (!b->uploads_in_flight) return LVS_OK;
+  CUDA_TRY(cudaEventRecord(b->ev_up_all, b->up));
+  CUDA_TRY(cudaStreamWaitEvent(b->st, b->ev_up_all, 0));
+  b->uploads_in_flight = false;
+  for (auto& c : b->target_pts) c.ready_pending = false;
+  for (auto& c : b->sources) c.ready_pending = false;
+  return LVS_OK;
+}
+
 static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
   if (n > 0 && !xyz) return fail(LVS_ERR_INVALID_ARG, "xyz is NULL");
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(LVS_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)0x7fffff00) return fail(LVS_ERR_INVALID_ARG, "too many points");
   if (n > slot.cap) {
-    if (slot.d_pts) cudaFree(slot.d_pts);
+    if (slot.d_pts) cudaFree(slot.d_pts);      // cudaFree synchronises the device: no reader or writer of the old buffer is left
     slot.d_pts = nullptr; slot.cap = 0;
     size_t cap = n + n / 8 + 256;
     CUDA_TRY(cudaMalloc(&slot.d_pts, cap * sizeof(float4)));
     slot.cap = cap;
   }
+  if (!slot.ready) {
+    CUDA_TRY(cudaEventCreateWithFlags(&slot.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&slot.used, cudaEventDisableTiming));
+  }
   slot.n = (int)n;
   slot.set = true;
   if (n == 0) return LVS_OK;
-  const float* d_in = xyz;
-  if (!on_device) {
-    size_t bytes = (n - 1) * stride_bytes + 12;
-    if (bytes > b->stage_cap) {
-      if (b->d_stage) cudaFree(b->d_stage);
-      b->d_stage = nullptr; b->stage_cap = 0;
-      size_t cap = bytes + bytes / 8 + 4096;
-      CUDA_TRY(cudaMalloc(&b->d_stage, cap));
-      b->stage_cap = cap;
-    }
-    CUDA_TRY(cudaMemcpyAsync(b->d_stage, xyz, bytes, cudaMemcpyHostToDevice, b->st));
-    b->h2d_bytes += (long long)bytes;
-    d_in = b->d_stage;
+  if (on_device) {
+    // resident input: repack on the compute stream, behind any upload of this slot that is still in flight
+    int rc = wait_ready(b, slot);
+    if (rc) return rc;
+    rc = pack_points(b->st, xyz, stride_bytes / 4, (int)n, slot.d_pts);
+    b->total_launches++;
+    return rc;
   }
-  int rc = pack_points(b->st, d_in, stride_bytes / 4, (int)n, slot.d_pts);
+  StageBuf& sb = b->ring[b->ring_next];
+  b->ring_next = (b->ring_next + 1) % kStageRing;
+  if (!sb.free_ev) CUDA_TRY(cudaEventCreateWithFlags(&sb.free_ev, cudaEventDisableTiming));
+  if (sb.in_flight) { CUDA_TRY(cudaEventSynchronize(sb.free_ev)); sb.in_flight = false; }
+  const size_t bytes = (n - 1) * stride_bytes + 12;
+  if (bytes > sb.cap) {
+    if (sb.d) cudaFree(sb.d);
+    sb.d = nullptr; sb.cap = 0;
+    size_t cap = bytes + bytes / 8 + 4096;
+    CUDA_TRY(cudaMalloc(&sb.d, cap));
+    sb.cap = cap;
+  }
+  if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(b->up, slot.used, 0)); slot.used_pending = false; }
+  CUDA_TRY(cudaMemcpyAsync(sb.d, xyz, bytes, cudaMemcpyHostToDevice, b->up));
+  b->h2d_bytes += (long long)bytes;
+  int rc = pack_points(b->up, sb.d, stride_bytes / 4, (int)n, slot.d_pts);
   b->total_launches++;
-  return rc;
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(sb.free_ev, b->up));
+  sb.in_flight = true;
+  CUDA_TRY(cudaEventRecord(slot.ready, b->up));
+  slot.ready_pending = true;
+  b->uploads_in_flight = true;
+  return LVS_OK;
 }
 
 // Completes every queued voxelisation among `slots` with ONE synchronisation (plus a rebuild for the rare slot whose
@@ -250,6 +307,8 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
     if (!b->sources[s].set) return fail(LVS_ERR_NO_SOURCE, "pair %d: source slot %d has no cloud (setInputSource not called)", i, s);
     max_src = std::max(max_src, b->sources[s].n);
   }
+  for (int i = 0; i < n_pairs; i++)
+    if ((rc = wait_ready(b, b->sources[src_slot[i]]))) return rc;
   if ((rc = finish_targets(b, tgt_slot, n_pairs))) return rc;
   const int bpp = choose_bpp(b, n_pairs, max_src);
   if ((rc = reserve_pairs(b, n_pairs, bpp))) return rc;
@@ -342,6 +401,7 @@ static int run_tap(lvs_ndt_batch* b, int kind, const double p[6], const float* T
   if (rc) return rc;
   if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  if ((rc = wait_all_uploads(b))) return rc;
   if ((rc = finish_target(b, 0))) return rc;
   const int bpp = choose_bpp(b, 1, b->sources[0].n);
   if ((rc = reserve_pairs(b, 1, bpp))) return rc;
@@ -400,6 +460,8 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
     b->own_stream = true;
   }
+  if ((e = cudaStreamCreateWithFlags(&b->up, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+  if ((e = cudaEventCreateWithFlags(&b->ev_up_all, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_gp_all, n_t * sizeof(GridParams))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
@@ -416,9 +478,15 @@ static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   int rc = set_device(b);
   if (rc) return rc;
   if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
-  if ((rc = upload_cloud(b, b->target_pts[slot], xyz, n, stride_bytes, on_device))) return rc;
-  rc = b->targets[slot].build(b->st, b->target_pts[slot].d_pts, (int)n, b->prm, b->ws);
+  CloudSlot& cs = b->target_pts[slot];
+  if ((rc = upload_cloud(b, cs, xyz, n, stride_bytes, on_device))) return rc;
+  if ((rc = wait_ready(b, cs))) return rc;
+  rc = b->targets[slot].build(b->st, cs.d_pts, (int)n, b->prm, b->ws);
   b->total_launches += b->targets[slot].launches_last_build;
+  if (rc == LVS_OK && cs.used) {
+    CUDA_TRY(cudaEventRecord(cs.used, b->st));
+    cs.used_pending = true;
+  }
   return rc;
 }
 
@@ -483,10 +551,21 @@ int lvs_ndt_batch_create(const lvs_ndt_params* params, int device, void* stream,
 int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   if (!b) return LVS_OK;
   cudaSetDevice(b->device);
+  if (b->up) cudaStreamSynchronize(b->up);
   if (b->st) cudaStreamSynchronize(b->st);
   for (auto& t : b->targets) t.release();
-  for (auto& c : b->target_pts) if (c.d_pts) cudaFree(c.d_pts);
-  for (auto& c : b->sources) if (c.d_pts) cudaFree(c.d_pts);
+  for (auto* v : {&b->target_pts, &b->sources})
+    for (auto& c : *v) {
+      if (c.d_pts) cudaFree(c.d_pts);
+      if (c.ready) cudaEventDestroy(c.ready);
+      if (c.used) cudaEventDestroy(c.used);
+    }
+  for (auto& sb : b->ring) {
+    if (sb.d) cudaFree(sb.d);
+    if (sb.free_ev) cudaEventDestroy(sb.free_ev);
+  }
+  if (b->ev_up_all) cudaEventDestroy(b->ev_up_all);
+  if (b->up) cudaStreamDestroy(b->up);
   b->ws.release();
   if (b->ws.h_gp) cudaFreeHost(b->ws.h_gp);
   if (b->d_stage) cudaFree(b->d_stage);
@@ -565,6 +644,14 @@ int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* 
   return LVS_OK;
 }
 
+int lvs_ndt_batch_wait_uploads(lvs_ndt_batch_t* b) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  int rc = set_device(b);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(b->up));
+  return LVS_OK;
+}
+
 int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int slot, int* n_cells, int* n_valid) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
@@ -608,6 +695,7 @@ int lvs_ndt_set_params(lvs_ndt_t* h, const lvs_ndt_params* params) {
   b->prm = *params;
   if (revox) {   // setResolution re-runs init() when the value changed and a target is set (ndt_omp.h:126-136)
     if ((rc = set_device(b))) return rc;
+    if ((rc = wait_all_uploads(b))) return rc;
     rc = b->targets[0].build(b->st, b->target_pts[0].d_pts, b->target_pts[0].n, b->prm, b->ws);
     b->total_launches += b->targets[0].launches_last_build;
     return rc;
@@ -646,6 +734,7 @@ int lvs_ndt_get_aligned_cloud(lvs_ndt_t* h, float* xyz_out, int on_device) {
   if (b->last_n_pairs < 1) return fail(LVS_ERR_INVALID_ARG, "align() has not run");
   const int n = b->sources[0].n;
   if (n == 0) return LVS_OK;
+  if ((rc = wait_all_uploads(b))) return rc;
   CUDA_TRY(cudaMemcpyAsync(b->d_T16, b->h_states[0].final_T, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st));
   float* d_out = xyz_out;
   if (!on_device) {
@@ -700,6 +789,7 @@ int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score) {
   if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
   if (b->sources[0].n == 0) { *score = NAN; return LVS_OK; }   // 0/0 in the reference
+  if ((rc = wait_all_uploads(b))) return rc;
   if ((rc = finish_target(b, 0))) return rc;
   const int bpp = choose_bpp(b, 1, b->sources[0].n);
   if ((rc = reserve_pairs(b, 1, bpp))) return rc;
@@ -771,6 +861,7 @@ int lvs_ndt_lookup_keys(lvs_ndt_t* h, const float T16[16], int32_t* keys_out) {
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
   const int n = b->sources[0].n;
   if (n == 0) return LVS_OK;
+  if ((rc = wait_all_uploads(b))) return rc;
   if ((rc = finish_target(b, 0))) return rc;
   PairDesc P = make_pair(b, 0, 0);
   int* d_keys = nullptr;

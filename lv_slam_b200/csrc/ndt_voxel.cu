@@ -10,7 +10,8 @@
 //   radix sort           stable LSD sort of (key, point index): 8-bit digits, hist / two-level scan / scatter
 //   head + scan          unique keys -> one segment per occupied cell, ascending key (= std::map order)
 //   leaf_moments_kernel  one warp per cell: lanes 0..8 own the nine f64 moment accumulators, lanes 9..11 the f32 centroid
-//                        sums, each summed SEQUENTIALLY IN INPUT ORDER (bit-identical to the reference's serial accumulation)
+//                        sums, each summed SEQUENTIALLY IN INPUT ORDER (bit-identical to the reference's serial accumulation);
+//                        addends staged two chunks ahead in shared memory so that only the dependent add is on the chain
 //   leaf_finalize_kernel one thread per cell: mean, covariance, eigen-decomposition, inflation, inverse, PCA weight (:281-367)
 // Compiled with -fmad=false: no mul/add contraction anywhere in this file.
 #include "ndt_internal.cuh"
@@ -257,39 +258,73 @@ __global__ void clear_cells_kernel(int* __restrict__ grid, const int* __restrict
 }
 
 // ------------------------------------------------------------------ per-cell moments
-// One warp per occupied cell.  Lanes 0..8 own S1[3] and the upper triangle of S2, lanes 9..11 the float centroid sums; each
-// accumulator is summed sequentially in input order, which is what makes the result bit-identical to the reference's loop.
-__global__ void __launch_bounds__(256) leaf_moments_kernel(const float4* __restrict__ pts, const int* __restrict__ sidx, const int* __restrict__ seg_start,
-                                                           const int* __restrict__ n_seg_p, const GridParams* __restrict__ gp,
-                                                           double* __restrict__ moments /*[cell][9]*/, float* __restrict__ csum /*[cell][3]*/) {
+// One warp per occupied cell.  The reference adds each point to the leaf's Sx (3 doubles), Sxx^T (double) and float centroid in
+// INPUT ORDER (voxel_grid_covariance_omp_impl.hpp:233-262); its one-pass covariance cancels heavily, so the sums are reproduced
+// with exactly that order and rounding: twelve serial chains per cell (lanes 0..8 the f64 moments, lanes 9..11 the f32 centroid
+// sums).  The only serial resource is the dependent add, so everything else is taken off the chain:
+//   * all 32 lanes gather one point each and stage its twelve addends (products already formed, exact in f64) in shared memory,
+//     double-buffered, two chunks ahead of the chain (the index and the point of later chunks are already in flight);
+//   * the chain runs 32 fully unrolled steps per chunk, every lane issuing one DADD and one FADD per step (the lanes that do not
+//     own a chain of that type add into a dead register), so there is no divergence and the tail is padded with +0.0, which is
+//     exact: an accumulator that starts at +0.0 can never become -0.0.
+constexpr int kMomWarps = 4;                 // warps per CTA
+constexpr int kMomCtasPerSm = 9;                // 22.5 KB of staging per CTA
+struct __align__(16) MomStage {
+  double d[32][9];                           // Sx addends (3), upper triangle of x x^T (6)
+  float f[32][4];                            // float centroid addends (+ pad)
+};
+
+__device__ __forceinline__ void mom_stage(MomStage& s, int lane, bool live, const float4& p) {
+  double x = 0.0, y = 0.0, z = 0.0;
+  float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+  if (live) { x = (double)p.x; y = (double)p.y; z = (double)p.z; fx = p.x; fy = p.y; fz = p.z; }
+  double* d = s.d[lane];
+  d[0] = x; d[1] = y; d[2] = z;
+  d[3] = __dmul_rn(x, x); d[4] = __dmul_rn(x, y); d[5] = __dmul_rn(x, z);
+  d[6] = __dmul_rn(y, y); d[7] = __dmul_rn(y, z); d[8] = __dmul_rn(z, z);
+  *reinterpret_cast<float4*>(s.f[lane]) = make_float4(fx, fy, fz, 0.0f);
+}
+
+__global__ void __launch_bounds__(kMomWarps * 32) leaf_moments_kernel(const float4* __restrict__ pts, const int* __restrict__ sidx,
+                                                                      const int* __restrict__ seg_start, const int* __restrict__ n_seg_p,
+                                                                      const GridParams* __restrict__ gp, double* __restrict__ moments /*[cell][9]*/,
+                                                                      float* __restrict__ csum /*[cell][3]*/) {
   if (gp->status != 0) return;
-  __shared__ float s_pt[8][32][3];
+  __shared__ MomStage s_stage[kMomWarps][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_seg = *n_seg_p;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  int ci = 0, cj = 0;
-  if (lane < 3) { ci = lane; }
-  else if (lane < 9) { const int I[6] = {0, 0, 0, 1, 1, 2}, J[6] = {0, 1, 2, 1, 2, 2}; ci = I[lane - 3]; cj = J[lane - 3]; }
-  else if (lane < 12) { ci = lane - 9; }
-  for (int seg = blockIdx.x * (blockDim.x >> 5) + warp; seg < n_seg; seg += warps_total) {
+  const int warps_total = gridDim.x * kMomWarps;
+  const int dcol = lane < 9 ? lane : 8;                  // chain owned by this lane (lanes >= 9 shadow chain 8 into a dead register)
+  const int fcol = (lane >= 9 && lane < 12) ? lane - 9 : 3;   // column 3 is the zero pad
+  MomStage* st = s_stage[warp];
+  for (int seg = blockIdx.x * kMomWarps + warp; seg < n_seg; seg += warps_total) {
     const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
+    const int n_chunks = (s1 - s0 + 31) >> 5;
     double acc = 0.0;
     float facc = 0.0f;
-    for (int base = s0; base < s1; base += 32) {
-      const int m = min(32, s1 - base);
-      __syncwarp();
-      if (lane < m) {
-        const float4 p = pts[sidx[base + lane]];
-        s_pt[warp][lane][0] = p.x; s_pt[warp][lane][1] = p.y; s_pt[warp][lane][2] = p.z;
+    // software pipeline: while chunk c is summed, the points of chunks c+1..c+3 and the index of chunk c+4 are already in
+    // registers or in flight (a gather is ~2 dependent L2 round trips, one chunk's chain only ~300 cycles)
+    auto load_idx = [&](int chunk) { const int i = s0 + chunk * 32 + lane; return i < s1 ? __ldg(sidx + i) : -1; };
+    auto load_pt = [&](int idx) { float4 p = make_float4(0.f, 0.f, 0.f, 0.f); if (idx >= 0) { p = __ldg(pts + idx); p.w = 1.0f; } return p; };
+    const int j0 = load_idx(0), j1 = load_idx(1), j2 = load_idx(2), j3 = load_idx(3);
+    int idn = load_idx(4);
+    const float4 p0 = load_pt(j0);
+    float4 pa = load_pt(j1), pb = load_pt(j2), pc = load_pt(j3);
+    __syncwarp();
+    mom_stage(st[0], lane, p0.w != 0.0f, p0);
+    __syncwarp();
+    for (int c = 0; c < n_chunks; c++) {
+      const MomStage& cur = st[c & 1];
+      if (c + 1 < n_chunks) mom_stage(st[(c + 1) & 1], lane, pa.w != 0.0f, pa);
+      pa = pb; pb = pc;
+      pc = load_pt(idn);
+      idn = load_idx(c + 5);
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        acc = __dadd_rn(acc, cur.d[k][dcol]);
+        facc = __fadd_rn(facc, cur.f[k][fcol]);
       }
       __syncwarp();
-      if (lane < 3) {
-        for (int k = 0; k < m; k++) acc = __dadd_rn(acc, (double)s_pt[warp][k][ci]);
-      } else if (lane < 9) {
-        for (int k = 0; k < m; k++) acc = __dadd_rn(acc, __dmul_rn((double)s_pt[warp][k][ci], (double)s_pt[warp][k][cj]));
-      } else if (lane < 12) {
-        for (int k = 0; k < m; k++) facc = __fadd_rn(facc, s_pt[warp][k][ci]);
-      }
     }
     if (lane < 9) moments[(size_t)seg * 9 + lane] = acc;
     else if (lane < 12) csum[(size_t)seg * 3 + (lane - 9)] = facc;
@@ -409,7 +444,7 @@ int TargetGrid::enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch
   CUDA_TRY(cudaMemsetAsync(ws.d_nseg, 0, 2 * sizeof(int), st));
   exclusive_scan(st, ws.d_flags, ws.d_pos, n, ws.d_nseg, ws.d_tile_tot);
   seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, ws.d_seg_start, ws.d_nseg, ws.d_nvalidpts);
-  leaf_moments_kernel<<<std::min(148 * 8, (n + 7) / 8), 256, 0, st>>>(pts, ws.d_idx[cur], ws.d_seg_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
+  leaf_moments_kernel<<<std::min(148 * kMomCtasPerSm, (n + kMomWarps - 1) / kMomWarps), kMomWarps * 32, 0, st>>>(pts, ws.d_idx[cur], ws.d_seg_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
   leaf_finalize_kernel<<<std::min(148 * 4, (n + 127) / 128), 128, 0, st>>>(ws.d_keys[cur], ws.d_seg_start, ws.d_nseg, ws.d_moments, ws.d_csum, d_recs,
                                                                           d_centroids, d_cell_keys, d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp,
                                                                           prm.min_points_per_voxel, prm.min_covar_eigvalue_mult, prm.variant);

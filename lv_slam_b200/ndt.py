@@ -232,6 +232,10 @@ class NdtBatch:
         ptr, n, stride, dev, keep = _cloud_args(xyz)
         C.check(self._L.lvs_ndt_batch_set_source(self._h, slot, ptr, n, stride, dev))
 
+    def wait_uploads(self):
+        """Blocks until every host cloud handed to set_target / set_source has reached the device (pinned buffers are free again)."""
+        C.check(self._L.lvs_ndt_batch_wait_uploads(self._h))
+
     def align(self, source_slots, target_slots, guesses):
         s = np.ascontiguousarray(source_slots, dtype=np.int32)
         t = np.ascontiguousarray(target_slots, dtype=np.int32)
