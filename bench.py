@@ -187,6 +187,7 @@ def main_ours(args):
     stream = torch.cuda.Stream()
     nb = L.NdtBatch(len(keys), B, device=local_rank, stream=stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64, **vp)
     src_slots = list(range(B))
+    tgt_all = list(range(len(keys)))
     tgt_slots = [key_slot[k] for _, k, _ in plan]
     guesses = [g for _, _, g in plan]
 
@@ -199,10 +200,8 @@ def main_ours(args):
     def step(src, tgt, group):
         """One pass over the batch.  Host clouds are queued on the library's upload stream in the order they are needed and
         the aligns run in groups of `group` pairs, so the copies of later scans overlap the aligns of earlier ones."""
-        for i, t in enumerate(tgt):
-            nb.set_target(i, t)
-        for i, s in enumerate(src):
-            nb.set_source(i, s)
+        nb.set_targets(tgt_all, tgt)
+        nb.set_sources(src_slots, src)
         out, stats = [], {"deriv_kernel_ms": 0.0, "deriv_launches": 0}
         for a in range(0, B, group):
             out += nb.align(src_slots[a:a + group], tgt_slots[a:a + group], guesses[a:a + group])

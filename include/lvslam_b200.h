@@ -140,6 +140,12 @@ int lvs_ndt_batch_create(const lvs_ndt_params* params, int device, void* stream,
 int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b);
 int lvs_ndt_batch_set_target(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device);
 int lvs_ndt_batch_set_source(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device);
+/* Plural forms: n clouds in one call (slots[i], xyz[i], counts[i]; one stride and residency for all).  Same semantics as n
+ * single calls; resident source clouds are repacked by one kernel launch instead of n. */
+int lvs_ndt_batch_set_targets(lvs_ndt_batch_t* b, int n, const int32_t* slots, const float* const* xyz, const size_t* counts,
+                              size_t stride_bytes, int on_device);
+int lvs_ndt_batch_set_sources(lvs_ndt_batch_t* b, int n, const int32_t* slots, const float* const* xyz, const size_t* counts,
+                              size_t stride_bytes, int on_device);
 /* set_target / set_source with a HOST pointer queue the copy and the repack on the object's upload stream and return; the
  * consumer (voxelisation, align) waits on the device for exactly the clouds it reads, so the copies of later clouds overlap
  * the aligns of earlier ones.  A pageable host buffer may be reused as soon as the call returns; a PINNED host buffer is read

@@ -64,13 +64,30 @@ struct CloudSlot {
   // without a host synchronisation (a voxelisation), so that a re-upload cannot overwrite points that are still being read.
   cudaEvent_t ready = nullptr, used = nullptr;
   bool ready_pending = false, used_pending = false;
+  int up_lane = 0;     // upload stream of this slot (fixed, so that re-records of `ready` stay ordered behind earlier uploads)
 };
 
-constexpr int kStageRing = 4;        // upload staging buffers: H2D copy of cloud i+1 overlaps the repack of cloud i
+constexpr int kBuildLanes = 4;
+struct BuildLane {
+  cudaStream_t st = nullptr;
+  BuildScratch ws;
+};
+struct TargetBuildState {
+  int lane = 0;
+  cudaEvent_t built = nullptr;       // end of the queued voxelisation on its lane
+  bool built_pending = false;
+};
+
+// Upload staging buffers.  The pool grows while the budget allows instead of making the host wait for a buffer, so a whole
+// batch of clouds can be queued at once and the host is free to issue the aligns that consume the first ones.
+constexpr size_t kStageBudgetBytes = (size_t)1 << 30;
+constexpr int kStageGrow = 16;
+constexpr int kUploadLanes = 2;
 struct StageBuf {
   float* d = nullptr;
   size_t cap = 0;
-  cudaEvent_t free_ev = nullptr;     // recorded after the repack kernel that read this buffer
+  cudaEvent_t free_ev = nullptr;     // = the `ready` event of the slot this buffer was last used for (owned by the slot): recorded
+                                     // after the repack kernel that read the buffer; a later re-record of that event only delays re-use
   bool in_flight = false;
 };
 
@@ -85,14 +102,20 @@ struct lvs_ndt_batch {
   cudaStream_t st = nullptr;
   bool own_stream = false;
   lvs_ndt_params prm{};
-  BuildScratch ws;
+  // voxelisations run on a few build lanes (stream + scratch each) so that the ~16 small kernels of one keyframe overlap
+  // those of the next and the repacking of the scans; the compute stream waits for a grid the first time it is consumed
+  BuildLane lanes[kBuildLanes];
+  int lane_next = 0;
+  cudaEvent_t ev_mark = nullptr;     // position of the compute stream, for resident inputs produced on it
   std::vector<TargetGrid> targets;
+  std::vector<TargetBuildState> tstate;
   std::vector<CloudSlot> target_pts, sources;
   // upload path: its own stream, a ring of staging buffers, and one more staging buffer for results on the compute stream
-  cudaStream_t up = nullptr;
-  StageBuf ring[kStageRing];
+  cudaStream_t up[kUploadLanes] = {};   // clouds alternate between the lanes: the repack of one overlaps the copy of the next
+  std::vector<StageBuf> ring;
+  size_t ring_bytes = 0;
   int ring_next = 0;
-  cudaEvent_t ev_up_all = nullptr;
+  cudaEvent_t ev_up_all[kUploadLanes] = {};
   bool uploads_in_flight = false;
   float* d_stage = nullptr;
   size_t stage_cap = 0;
@@ -140,15 +163,18 @@ static int wait_ready(lvs_ndt_batch* b, CloudSlot& slot) {
 // Makes the compute stream wait for every upload queued so far (single-handle taps and getters).
 static int wait_all_uploads(lvs_ndt_batch* b) {
   if (!b->uploads_in_flight) return LVS_OK;
-  CUDA_TRY(cudaEventRecord(b->ev_up_all, b->up));
-  CUDA_TRY(cudaStreamWaitEvent(b->st, b->ev_up_all, 0));
+  for (int l = 0; l < kUploadLanes; l++) {
+    CUDA_TRY(cudaEventRecord(b->ev_up_all[l], b->up[l]));
+    CUDA_TRY(cudaStreamWaitEvent(b->st, b->ev_up_all[l], 0));
+  }
   b->uploads_in_flight = false;
   for (auto& c : b->target_pts) c.ready_pending = false;
   for (auto& c : b->sources) c.ready_pending = false;
   return LVS_OK;
 }
 
-static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
+static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, size_t n, size_t stride_bytes, int on_device,
+                        cudaStream_t resident_stream) {
   if (n > 0 && !xyz) return fail(LVS_ERR_INVALID_ARG, "xyz is NULL");
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(LVS_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)0x7fffff00) return fail(LVS_ERR_INVALID_ARG, "too many points");
@@ -167,34 +193,64 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
   slot.set = true;
   if (n == 0) return LVS_OK;
   if (on_device) {
-    // resident input: repack on the compute stream, behind any upload of this slot that is still in flight
-    int rc = wait_ready(b, slot);
-    if (rc) return rc;
-    rc = pack_points(b->st, xyz, stride_bytes / 4, (int)n, slot.d_pts);
+    // resident input: repack on the consumer's stream, behind any upload of this slot that is still in flight and behind
+    // whatever the caller has queued on the handle's stream to produce the cloud
+    if (slot.ready_pending) { CUDA_TRY(cudaStreamWaitEvent(resident_stream, slot.ready, 0)); slot.ready_pending = false; }
+    if (resident_stream != b->st) {
+      CUDA_TRY(cudaEventRecord(b->ev_mark, b->st));
+      CUDA_TRY(cudaStreamWaitEvent(resident_stream, b->ev_mark, 0));
+      if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(resident_stream, slot.used, 0)); slot.used_pending = false; }
+    }
+    int rc = pack_points(resident_stream, xyz, stride_bytes / 4, (int)n, slot.d_pts);
     b->total_launches++;
     return rc;
   }
-  StageBuf& sb = b->ring[b->ring_next];
-  b->ring_next = (b->ring_next + 1) % kStageRing;
-  if (!sb.free_ev) CUDA_TRY(cudaEventCreateWithFlags(&sb.free_ev, cudaEventDisableTiming));
-  if (sb.in_flight) { CUDA_TRY(cudaEventSynchronize(sb.free_ev)); sb.in_flight = false; }
   const size_t bytes = (n - 1) * stride_bytes + 12;
+  // staging buffer: the oldest one if its repack has finished, else a new one while the budget allows, else wait for the oldest
+  int pick = -1;
+  if (!b->ring.empty()) {
+    StageBuf& old = b->ring[b->ring_next];
+    if (!old.in_flight || cudaEventQuery(old.free_ev) == cudaSuccess) { old.in_flight = false; pick = b->ring_next; }
+    else (void)cudaGetLastError();
+  }
+  if (pick < 0 && b->ring.size() < 4096) {
+    // grow by several buffers at once (allocated here, not lazily): cudaMalloc stalls the pipeline, so the pool should reach
+    // its steady size within the first batch instead of one buffer per batch
+    const size_t cap = bytes + bytes / 8 + 4096;
+    int added = 0;
+    for (int k = 0; k < kStageGrow && b->ring_bytes + cap <= kStageBudgetBytes; k++) {
+      StageBuf nb;
+      if (cudaMalloc(&nb.d, cap) != cudaSuccess) { (void)cudaGetLastError(); break; }
+      nb.cap = cap;
+      b->ring_bytes += cap;
+      b->ring.insert(b->ring.begin() + b->ring_next, nb);          // in front of the oldest: keeps the ring in age order
+      added++;
+    }
+    if (added) pick = b->ring_next;
+  }
+  if (pick < 0) pick = b->ring_next;
+  StageBuf& sb = b->ring[pick];
+  b->ring_next = (pick + 1) % (int)b->ring.size();
+  if (sb.in_flight) { CUDA_TRY(cudaEventSynchronize(sb.free_ev)); sb.in_flight = false; }
   if (bytes > sb.cap) {
     if (sb.d) cudaFree(sb.d);
+    b->ring_bytes -= sb.cap;
     sb.d = nullptr; sb.cap = 0;
     size_t cap = bytes + bytes / 8 + 4096;
     CUDA_TRY(cudaMalloc(&sb.d, cap));
     sb.cap = cap;
+    b->ring_bytes += cap;
   }
-  if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(b->up, slot.used, 0)); slot.used_pending = false; }
-  CUDA_TRY(cudaMemcpyAsync(sb.d, xyz, bytes, cudaMemcpyHostToDevice, b->up));
+  cudaStream_t up = b->up[slot.up_lane];
+  if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(up, slot.used, 0)); slot.used_pending = false; }
+  CUDA_TRY(cudaMemcpyAsync(sb.d, xyz, bytes, cudaMemcpyHostToDevice, up));
   b->h2d_bytes += (long long)bytes;
-  int rc = pack_points(b->up, sb.d, stride_bytes / 4, (int)n, slot.d_pts);
+  int rc = pack_points(up, sb.d, stride_bytes / 4, (int)n, slot.d_pts);
   b->total_launches++;
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(sb.free_ev, b->up));
+  CUDA_TRY(cudaEventRecord(slot.ready, up));
+  sb.free_ev = slot.ready;
   sb.in_flight = true;
-  CUDA_TRY(cudaEventRecord(slot.ready, b->up));
   slot.ready_pending = true;
   b->uploads_in_flight = true;
   return LVS_OK;
@@ -206,6 +262,8 @@ static int finish_targets(lvs_ndt_batch* b, const int32_t* slots, int n) {
   bool any = false;
   for (int i = 0; i < n; i++) {
     TargetGrid& t = b->targets[slots[i]];
+    TargetBuildState& ts = b->tstate[slots[i]];
+    if (ts.built_pending) { CUDA_TRY(cudaStreamWaitEvent(b->st, ts.built, 0)); ts.built_pending = false; }
     if (t.pending && !t.fetch_queued) {
       CUDA_TRY(cudaMemcpyAsync(&b->h_gp_all[slots[i]], t.d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, b->st));
       b->d2h_bytes += sizeof(GridParams);
@@ -220,9 +278,12 @@ static int finish_targets(lvs_ndt_batch* b, const int32_t* slots, int n) {
     TargetGrid& t = b->targets[slots[i]];
     if (!t.fetch_queued) continue;
     t.fetch_queued = false;
-    int rc = t.accept(b->h_gp_all[slots[i]], b->st, b->ws);
+    // the builds this loop waits for have completed, so the compute stream and the lane's scratch are free for a re-build
+    BuildLane& ln = b->lanes[b->tstate[slots[i]].lane];
+    if (b->h_gp_all[slots[i]].status == kStatusNeedsGrow) CUDA_TRY(cudaStreamSynchronize(ln.st));   // a later build may be using the scratch
+    int rc = t.accept(b->h_gp_all[slots[i]], b->st, ln.ws);
     if (rc) return rc;
-    if (t.pending) { b->total_launches += t.launches_last_build; if ((rc = t.finish(b->st, b->ws))) return rc; }
+    if (t.pending) { b->total_launches += t.launches_last_build; if ((rc = t.finish(b->st, ln.ws))) return rc; }
   }
   return LVS_OK;
 }
@@ -452,7 +513,7 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
   b->device = device;
   b->prm = p;
   b->trace_on = trace_on;
-  b->targets.resize(n_t); b->target_pts.resize(n_t); b->sources.resize(n_s);
+  b->targets.resize(n_t); b->target_pts.resize(n_t); b->sources.resize(n_s); b->tstate.resize(n_t);
   auto bail = [&](int st) { lvs_ndt_batch_destroy(b); return st; };
   if (stream) b->st = (cudaStream_t)stream;
   else {
@@ -460,8 +521,15 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
     b->own_stream = true;
   }
-  if ((e = cudaStreamCreateWithFlags(&b->up, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
-  if ((e = cudaEventCreateWithFlags(&b->ev_up_all, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+  for (int l = 0; l < kUploadLanes; l++) {
+    if ((e = cudaStreamCreateWithFlags(&b->up[l], cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    if ((e = cudaEventCreateWithFlags(&b->ev_up_all[l], cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+  }
+  for (int i = 0; i < n_t; i++) b->target_pts[i].up_lane = i % kUploadLanes;
+  for (int i = 0; i < n_s; i++) b->sources[i].up_lane = (i + n_t) % kUploadLanes;
+  if ((e = cudaEventCreateWithFlags(&b->ev_mark, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+  for (auto& ln : b->lanes)
+    if ((e = cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_gp_all, n_t * sizeof(GridParams))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
@@ -479,22 +547,84 @@ static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   if (rc) return rc;
   if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
   CloudSlot& cs = b->target_pts[slot];
-  if ((rc = upload_cloud(b, cs, xyz, n, stride_bytes, on_device))) return rc;
-  if ((rc = wait_ready(b, cs))) return rc;
-  rc = b->targets[slot].build(b->st, cs.d_pts, (int)n, b->prm, b->ws);
+  TargetBuildState& ts = b->tstate[slot];
+  // a grid that was re-queued on the compute stream (grown index grid) or consumed there is complete by now: every consumer
+  // synchronises the host.  A build still in flight on another lane has to finish before this one touches the same arrays.
+  const int lane = b->lane_next;
+  b->lane_next = (b->lane_next + 1) % kBuildLanes;
+  BuildLane& ln = b->lanes[lane];
+  if (ts.built_pending && ts.lane != lane) CUDA_TRY(cudaStreamWaitEvent(ln.st, ts.built, 0));
+  if ((rc = upload_cloud(b, cs, xyz, n, stride_bytes, on_device, ln.st))) return rc;
+  if (cs.ready_pending) { CUDA_TRY(cudaStreamWaitEvent(ln.st, cs.ready, 0)); cs.ready_pending = false; }
+  rc = b->targets[slot].build(ln.st, cs.d_pts, (int)n, b->prm, ln.ws);
   b->total_launches += b->targets[slot].launches_last_build;
-  if (rc == LVS_OK && cs.used) {
-    CUDA_TRY(cudaEventRecord(cs.used, b->st));
+  if (rc) return rc;
+  if (!ts.built) CUDA_TRY(cudaEventCreateWithFlags(&ts.built, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(ts.built, ln.st));
+  ts.built_pending = true;
+  ts.lane = lane;
+  if (cs.used) {
+    CUDA_TRY(cudaEventRecord(cs.used, ln.st));
     cs.used_pending = true;
   }
-  return rc;
+  return LVS_OK;
 }
 
 static int set_source(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
   int rc = set_device(b);
   if (rc) return rc;
   if (slot < 0 || slot >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slot);
-  return upload_cloud(b, b->sources[slot], xyz, n, stride_bytes, on_device);
+  return upload_cloud(b, b->sources[slot], xyz, n, stride_bytes, on_device, b->st);
+}
+
+// Batched setInputSource: host clouds go through the upload stream one by one (each keeps its own ready event); resident
+// clouds are repacked by one launch per kPackMany clouds instead of one launch each.
+static int set_sources(lvs_ndt_batch* b, int n, const int32_t* slots, const float* const* xyz, const size_t* counts, size_t stride_bytes,
+                       int on_device) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++)
+    if (slots[i] < 0 || slots[i] >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slots[i]);
+  if (!on_device) {
+    for (int i = 0; i < n; i++)
+      if ((rc = upload_cloud(b, b->sources[slots[i]], xyz[i], counts[i], stride_bytes, 0, b->st))) return rc;
+    return LVS_OK;
+  }
+  if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(LVS_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
+  PackMany pm;
+  pm.count = 0;
+  int max_n = 0;
+  for (int i = 0; i < n; i++) {
+    CloudSlot& slot = b->sources[slots[i]];
+    // allocation and bookkeeping exactly as upload_cloud, the repack itself is deferred to the fused launch
+    if ((rc = upload_cloud(b, slot, xyz[i], 0, stride_bytes, 1, b->st))) return rc;
+    const size_t cnt = counts[i];
+    if (cnt > 0 && !xyz[i]) return fail(LVS_ERR_INVALID_ARG, "xyz is NULL");
+    if (cnt > (size_t)0x7fffff00) return fail(LVS_ERR_INVALID_ARG, "too many points");
+    if (cnt > slot.cap) {
+      if (slot.d_pts) cudaFree(slot.d_pts);
+      slot.d_pts = nullptr; slot.cap = 0;
+      size_t cap = cnt + cnt / 8 + 256;
+      CUDA_TRY(cudaMalloc(&slot.d_pts, cap * sizeof(float4)));
+      slot.cap = cap;
+    }
+    slot.n = (int)cnt;
+    if (cnt == 0) continue;
+    if ((rc = wait_ready(b, slot))) return rc;
+    PackOne& c = pm.c[pm.count++];
+    c.in = xyz[i]; c.out = slot.d_pts; c.n = (int)cnt; c.stride_floats = (int)(stride_bytes / 4);
+    max_n = std::max(max_n, (int)cnt);
+    if (pm.count == kPackMany || i == n - 1) {
+      if ((rc = pack_many(b->st, pm, max_n))) return rc;
+      b->total_launches++;
+      pm.count = 0; max_n = 0;
+    }
+  }
+  if (pm.count > 0) {
+    if ((rc = pack_many(b->st, pm, max_n))) return rc;
+    b->total_launches++;
+  }
+  return LVS_OK;
 }
 
 }  // namespace lvs
@@ -551,7 +681,8 @@ int lvs_ndt_batch_create(const lvs_ndt_params* params, int device, void* stream,
 int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   if (!b) return LVS_OK;
   cudaSetDevice(b->device);
-  if (b->up) cudaStreamSynchronize(b->up);
+  for (auto u : b->up) if (u) cudaStreamSynchronize(u);
+  for (auto& ln : b->lanes) if (ln.st) cudaStreamSynchronize(ln.st);
   if (b->st) cudaStreamSynchronize(b->st);
   for (auto& t : b->targets) t.release();
   for (auto* v : {&b->target_pts, &b->sources})
@@ -560,14 +691,17 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
       if (c.ready) cudaEventDestroy(c.ready);
       if (c.used) cudaEventDestroy(c.used);
     }
-  for (auto& sb : b->ring) {
+  for (auto& sb : b->ring)
     if (sb.d) cudaFree(sb.d);
-    if (sb.free_ev) cudaEventDestroy(sb.free_ev);
+  for (auto ev : b->ev_up_all) if (ev) cudaEventDestroy(ev);
+  for (auto u : b->up) if (u) cudaStreamDestroy(u);
+  for (auto& ln : b->lanes) {
+    ln.ws.release();
+    if (ln.ws.h_gp) cudaFreeHost(ln.ws.h_gp);
+    if (ln.st) cudaStreamDestroy(ln.st);
   }
-  if (b->ev_up_all) cudaEventDestroy(b->ev_up_all);
-  if (b->up) cudaStreamDestroy(b->up);
-  b->ws.release();
-  if (b->ws.h_gp) cudaFreeHost(b->ws.h_gp);
+  for (auto& ts : b->tstate) if (ts.built) cudaEventDestroy(ts.built);
+  if (b->ev_mark) cudaEventDestroy(b->ev_mark);
   if (b->d_stage) cudaFree(b->d_stage);
   if (b->d_pairs) cudaFree(b->d_pairs);
   if (b->d_states) cudaFree(b->d_states);
@@ -599,6 +733,24 @@ int lvs_ndt_batch_set_target(lvs_ndt_batch_t* b, int slot, const float* xyz, siz
 int lvs_ndt_batch_set_source(lvs_ndt_batch_t* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   return set_source(b, slot, xyz, n, stride_bytes, on_device);
+}
+
+int lvs_ndt_batch_set_sources(lvs_ndt_batch_t* b, int n, const int32_t* slots, const float* const* xyz, const size_t* counts, size_t stride_bytes,
+                              int on_device) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (n < 0 || (n > 0 && (!slots || !xyz || !counts))) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  return set_sources(b, n, slots, xyz, counts, stride_bytes, on_device);
+}
+
+int lvs_ndt_batch_set_targets(lvs_ndt_batch_t* b, int n, const int32_t* slots, const float* const* xyz, const size_t* counts, size_t stride_bytes,
+                              int on_device) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (n < 0 || (n > 0 && (!slots || !xyz || !counts))) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  for (int i = 0; i < n; i++) {
+    int rc = set_target(b, slots[i], xyz[i], counts[i], stride_bytes, on_device);
+    if (rc) return rc;
+  }
+  return LVS_OK;
 }
 
 int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot, const float* guesses16,
@@ -648,7 +800,7 @@ int lvs_ndt_batch_wait_uploads(lvs_ndt_batch_t* b) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   int rc = set_device(b);
   if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(b->up));
+  for (auto u : b->up) CUDA_TRY(cudaStreamSynchronize(u));
   return LVS_OK;
 }
 
@@ -696,7 +848,10 @@ int lvs_ndt_set_params(lvs_ndt_t* h, const lvs_ndt_params* params) {
   if (revox) {   // setResolution re-runs init() when the value changed and a target is set (ndt_omp.h:126-136)
     if ((rc = set_device(b))) return rc;
     if ((rc = wait_all_uploads(b))) return rc;
-    rc = b->targets[0].build(b->st, b->target_pts[0].d_pts, b->target_pts[0].n, b->prm, b->ws);
+    if ((rc = finish_target(b, 0))) return rc;     // the queued build (if any) is complete and its lane idle after this
+    BuildLane& ln = b->lanes[b->tstate[0].lane];
+    CUDA_TRY(cudaStreamSynchronize(ln.st));
+    rc = b->targets[0].build(b->st, b->target_pts[0].d_pts, b->target_pts[0].n, b->prm, ln.ws);
     b->total_launches += b->targets[0].launches_last_build;
     return rc;
   }

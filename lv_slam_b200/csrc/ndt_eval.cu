@@ -17,7 +17,7 @@
 
 namespace lvs {
 
-__constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+// DIRECT7 probes, in the reference's order (voxel_grid_covariance_omp_impl.hpp:423-430): centre, +x, -x, +y, -y, +z, -z.
 // pcl::getAllNeighborCellIndices (PCL 1.8 voxel_grid.h): 13 half-offsets, then their negatives; no centre cell.
 __constant__ int c_off26[26][3] = {
     {-1, -1, -1}, {-1, 0, -1}, {-1, 1, -1}, {0, -1, -1}, {0, 0, -1}, {0, 1, -1}, {1, -1, -1}, {1, 0, -1}, {1, 1, -1},
@@ -121,18 +121,19 @@ static_assert(SmemLayout::qw_off % 8 == 0, "qw must be 8-byte aligned");
 static_assert(sizeof(double) * kWarps * kAcc * 4 <= SmemLayout::pts_off, "the CTA reduction scratch aliases the tile region");
 
 // One round: lanes e < n_round take queue entries q[head + lane], stage their float contributions in the tile, then the
-// warp adds the round into its fp64 accumulators.
+// warp adds the round into its fp64 accumulators.  Columns of lanes without a contribution (short round, or the reference's
+// early-out) are zero-filled and summed like the others: adding +0.0 is exact and an accumulator that starts at +0.0 never
+// becomes -0.0, so no per-group predicate is needed in the summation.
 template <bool HESS, bool PCA>
-__device__ __forceinline__ void process_round(double* acc, const PairDesc& P, const float* pts, const int* q, const double* qw, float* tile,
-                                              int head, int n_round, float gd2, double gd1) {
+__device__ __forceinline__ void process_round(double* acc, const VoxelRec* __restrict__ recs, const float* pts, const int* q, const double* qw,
+                                              float* tile, int lane, int head, int n_round, float gd2, double gd1) {
   using Sh = Shape<HESS>;
-  const int lane = threadIdx.x & 31;
   bool used = false;
   double w = 0.0;
   if (lane < n_round) {
     const int ent = q[head + lane];
     const int rec = ent / kPtsPerIter, slot = ent % kPtsPerIter;
-    const VoxelRec* vr = P.recs + rec;
+    const VoxelRec* vr = recs + rec;
     const double2 m01 = __ldg(reinterpret_cast<const double2*>(vr));
     const float4 q1 = __ldg(reinterpret_cast<const float4*>(vr) + 1);   // mean[2] (8 B) + icov[0..1]
     const float4 q2 = __ldg(reinterpret_cast<const float4*>(vr) + 2);   // icov[2..5]
@@ -145,57 +146,77 @@ __device__ __forceinline__ void process_round(double* acc, const PairDesc& P, co
                                  gd2, gd1);
     if (PCA) w = qw[head + lane];
   }
-  const unsigned umask = __ballot_sync(0xffffffffu, used);
-  if (!used && umask != 0u) {
+  if (!used) {
 #pragma unroll
     for (int o = 0; o < Sh::NV; o++) tile[o * kTileStride + lane] = 0.0f;
   }
   __syncwarp();
-  if (umask != 0u) {
 #pragma unroll
-    for (int t = 0; t < Sh::TPL; t++) {
-      const int task = lane + 32 * t;
-      const int o = task >> 2, g = task & 3;
-      const bool live = task < Sh::NTASK && ((umask >> (8 * g)) & 0xffu) != 0u;
-      const float4* row = reinterpret_cast<const float4*>(tile + (task < Sh::NTASK ? o : 0) * kTileStride + 8 * g);
-      const float4 lo = row[0], hi = row[1];
-      const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-      double a = acc[t];
+  for (int t = 0; t < Sh::TPL; t++) {
+    const int task = lane + 32 * t;
+    const int o = task >> 2, g = task & 3;
+    const bool live = (Sh::NTASK % 32 == 0) || t + 1 < Sh::TPL || task < Sh::NTASK;
+    const float4* row = reinterpret_cast<const float4*>(tile + (live ? o : 0) * kTileStride + 8 * g);
+    const float4 lo = row[0], hi = row[1];
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    double a = acc[t];
 #pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        if (PCA) {
-          const double wj = __shfl_sync(0xffffffffu, w, 8 * g + jj);   // all 32 lanes take part in the shuffle
-          if (live) a += (double)v[jj] * wj;
-        } else {
-          if (live) a += (double)v[jj];
-        }
-      }
-      acc[t] = a;
+    for (int jj = 0; jj < 8; jj++) {
+      if (PCA) a += (double)v[jj] * __shfl_sync(0xffffffffu, w, 8 * g + jj);   // zero columns carry w = 0 or a finite weight: exact either way
+      else a += (double)v[jj];
     }
+    acc[t] = a;    // lanes past NTASK in the last pass sum row 0 into an accumulator that is never read
   }
   __syncwarp();
 }
 
-template <bool HESS, bool PCA>
-__device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, int mode,
-                                           float gd2, double gd1, unsigned char* s_dyn, double* partial) {
+template <int MODE> struct Probes;
+template <> struct Probes<LVS_DIRECT1> { static constexpr int K = 1; };
+template <> struct Probes<LVS_DIRECT7> { static constexpr int K = 7; };
+template <> struct Probes<LVS_DIRECT26> { static constexpr int K = 26; };
+
+template <int MODE, bool HESS, bool PCA>
+__device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2,
+                                           double gd1, unsigned char* s_dyn, double* partial) {
   using Sh = Shape<HESS>;
+  constexpr int K = Probes<MODE>::K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   float* tile = reinterpret_cast<float*>(s_dyn + SmemLayout::tile_off) + warp * kTileFloats;
   float* pts = reinterpret_cast<float*>(s_dyn + SmemLayout::pts_off) + warp * (6 * kPtsPerIter);
   int* q = reinterpret_cast<int*>(s_dyn + SmemLayout::q_off) + warp * kQueueCap;
   double* qw = reinterpret_cast<double*>(s_dyn + SmemLayout::qw_off) + warp * kQueueCap;   // only mapped for ndt_pca launches
-  const int K = mode == LVS_DIRECT1 ? 1 : (mode == LVS_DIRECT7 ? 7 : 26);
+  const VoxelRec* __restrict__ recs = P.recs;
+  const int* __restrict__ grid = P.grid;
   double acc[Sh::TPL];
 #pragma unroll
   for (int t = 0; t < Sh::TPL; t++) acc[t] = 0.0;
+  // floor(x / leaf) in float (voxel_grid_covariance_omp_impl.hpp:379-381).  For a power-of-two leaf the quotient equals the
+  // product with the (exact) reciprocal bit for bit, so the division is only issued for other leaf sizes.
+  const float inv_leaf = 1.0f / G.leaf;
+  const bool pow2 = (__float_as_uint(G.leaf) & 0x007fffffu) == 0u && isfinite(inv_leaf) && inv_leaf >= 1.1754944e-38f;
+  const int div0 = G.max_b[0] - G.min_b[0] + 1, div1 = G.max_b[1] - G.min_b[1] + 1, div2 = G.max_b[2] - G.min_b[2] + 1;
 
   if (!G.empty) {
     for (int base = (blk * kWarps + warp) * kPtsPerIter; base < P.n_src; base += bpp * kWarps * kPtsPerIter) {
       // ---- phase A: transform, probe the index grid, queue every (point, cell) hit of the warp's 64 points
       int nq = 0;
+      // consumes whole rounds from the queue and moves the remainder (< 32 entries) to its front; returns the new length
+      auto drain = [&]() {
+        __syncwarp();
+        int head = 0;
+        for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, 32, gd2, gd1);
+        const int rem = nq - head;
+        int ent = 0; double we = 0.0;
+        if (lane < rem) { ent = q[head + lane]; if (PCA) we = qw[head + lane]; }
+        __syncwarp();
+        if (lane < rem) { q[lane] = ent; if (PCA) qw[lane] = we; }
+        return rem;
+      };
       for (int h = 0; h < kPtsPerLane; h++) {
+        // one half of the warp's points adds at most 32 K entries: with K = 7 that fits behind a remainder of < 32 entries,
+        // so the queue is only checked here; DIRECT26 checks before every probe
+        if (MODE == LVS_DIRECT7 && h > 0 && nq >= 32) nq = drain();
         const int slot = h * 32 + lane;
         const int i = base + slot;
         float tx = 0.f, ty = 0.f, tz = 0.f;
@@ -210,44 +231,45 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
           pts[4 * kPtsPerIter + slot] = (R[3] * s.x + R[4] * s.y) + R[5] * s.z;
           pts[5 * kPtsPerIter + slot] = (R[6] * s.x + R[7] * s.y) + R[8] * s.z;
         }
-        const int cx = (int)floorf(tx / G.leaf), cy = (int)floorf(ty / G.leaf), cz = (int)floorf(tz / G.leaf);
+        int cx, cy, cz;
+        if (pow2) { cx = (int)floorf(tx * inv_leaf); cy = (int)floorf(ty * inv_leaf); cz = (int)floorf(tz * inv_leaf); }
+        else { cx = (int)floorf(tx / G.leaf); cy = (int)floorf(ty / G.leaf); cz = (int)floorf(tz / G.leaf); }
+        // cell coordinates relative to the grid origin; one unsigned compare per axis and offset tests the bounds
+        const int rx = cx - G.min_b[0], ry = cy - G.min_b[1], rz = cz - G.min_b[2];
+        const int cell0 = rx * G.mul[0] + ry * G.mul[1] + rz * G.mul[2];
         // ndt_pca multiplies the RUNNING per-point sums by each cell's weight (ndt_pca_impl2.hpp:293-296): the contribution of
         // cell k ends up scaled by the product of the weights of cells k..last, hence the probes run last-to-first.
         double run = 1.0;
+#pragma unroll(MODE == LVS_DIRECT26 ? 1 : K)
         for (int k = K - 1; k >= 0; k--) {
           int ox = 0, oy = 0, oz = 0;
-          if (mode == LVS_DIRECT7) { ox = c_off7[k][0]; oy = c_off7[k][1]; oz = c_off7[k][2]; }
-          else if (mode == LVS_DIRECT26) { ox = c_off26[k][0]; oy = c_off26[k][1]; oz = c_off26[k][2]; }
-          const int ix = cx + ox, iy = cy + oy, iz = cz + oz;
+          if (MODE == LVS_DIRECT7) { ox = k == 1 ? 1 : k == 2 ? -1 : 0; oy = k == 3 ? 1 : k == 4 ? -1 : 0; oz = k == 5 ? 1 : k == 6 ? -1 : 0; }
+          else if (MODE == LVS_DIRECT26) { ox = c_off26[k][0]; oy = c_off26[k][1]; oz = c_off26[k][2]; }
           int v = -1;
-          if (ok && ix >= G.min_b[0] && ix <= G.max_b[0] && iy >= G.min_b[1] && iy <= G.max_b[1] && iz >= G.min_b[2] && iz <= G.max_b[2])
-            v = __ldg(P.grid + ((ix - G.min_b[0]) * G.mul[0] + (iy - G.min_b[1]) * G.mul[1] + (iz - G.min_b[2]) * G.mul[2]));
+          if (ok && (unsigned)(rx + ox) < (unsigned)div0 && (unsigned)(ry + oy) < (unsigned)div1 && (unsigned)(rz + oz) < (unsigned)div2)
+            v = __ldg(grid + (cell0 + ox * G.mul[0] + oy * G.mul[1] + oz * G.mul[2]));
           const bool hit = v >= 0;
           const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (m == 0u) continue;
-          if (nq > kQueueCap - 32) {
-            // queue nearly full (dense DIRECT26 neighbourhoods): drain whole rounds, keep the remainder at the front
-            __syncwarp();
-            int head = 0;
-            for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, P, pts, q, qw, tile, head, 32, gd2, gd1);
-            const int rem = nq - head;
-            int ent = 0; double we = 0.0;
-            if (lane < rem) { ent = q[head + lane]; if (PCA) we = qw[head + lane]; }
-            __syncwarp();
-            if (lane < rem) { q[lane] = ent; if (PCA) qw[lane] = we; }
-            nq = rem;
+          if (MODE == LVS_DIRECT26) {
+            if (m == 0u) continue;
+            if (nq > kQueueCap - 32) {
+              // queue nearly full (dense DIRECT26 neighbourhoods): drain whole rounds, keep the remainder at the front
+              nq = drain();
+            }
           }
           if (hit) {
             const int pos = nq + __popc(m & lt_mask);
             q[pos] = v * kPtsPerIter + slot;
-            if (PCA) { run *= (double)(__ldg(&P.recs[v].meta) & kMetaWeightMask); qw[pos] = run; }
+            if (PCA) { run *= (double)(__ldg(&recs[v].meta) & kMetaWeightMask); qw[pos] = run; }
           }
           nq += __popc(m);
         }
       }
+      static_assert(MODE == LVS_DIRECT26 || 31 + 32 * Probes<MODE>::K <= kQueueCap, "queue capacity per half iteration");
+      static_assert(MODE != LVS_DIRECT1 || kPtsPerLane * 32 <= kQueueCap, "queue capacity");
       __syncwarp();
       // ---- phase B: rounds of 32 queued (point, cell) contributions
-      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, P, pts, q, qw, tile, head, min(32, nq - head), gd2, gd1);
+      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, min(32, nq - head), gd2, gd1);
     }
   }
   // CTA partial: s_red[warp][task] (aliases the tile region) -> output o sums its 4 groups over the 8 warps in fixed order
@@ -269,6 +291,7 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
   }
 }
 
+template <int MODE, bool PCA>
 __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ float s_T[16], s_R[9];
@@ -278,39 +301,45 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const int kind = S.eval_kind;
   const AlignConsts& c = L.consts;
   if (kind != EVAL_DERIV_H && kind != EVAL_DERIV_NOH) return;
-  if (c.search == LVS_KDTREE) return;                      // radius-search derivatives live in the cold kernel
   const PairDesc P = L.d_pairs[pair];
   if (threadIdx.x < 16) s_T[threadIdx.x] = S.T[threadIdx.x];
   if (threadIdx.x < 9) s_R[threadIdx.x] = S.Rj[threadIdx.x];
   __syncthreads();
   const GridView G = load_grid_view(P.gp);
   const float gd2 = (float)c.gauss_d2;
-  const bool pca = c.variant == LVS_NDT_PCA;
   double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
   const int bpp = L.blocks_per_pair;
-  if (kind == EVAL_DERIV_H) {
-    if (pca) run_direct<true, true>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
-    else run_direct<true, false>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
-  } else {
-    if (pca) run_direct<false, true>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
-    else run_direct<false, false>(P, G, s_T, s_R, blk, bpp, c.search, gd2, c.gauss_d1, s_dyn, partial);
-  }
+  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial);
+  else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial);
   eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_src, reinterpret_cast<double*>(s_dyn), &s_last);
 }
 
-int launch_eval(cudaStream_t st, const EvalLaunch& L) {
-  if (L.n_pairs <= 0) return LVS_OK;
+template <int MODE, bool PCA>
+static int launch_eval_as(cudaStream_t st, const EvalLaunch& L) {
   static int attr_dev = -1;     // the opt-in shared-memory size is a per-device function attribute
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
+  constexpr size_t smem = PCA ? SmemLayout::bytes_pca : SmemLayout::bytes_omp;
   if (attr_dev != dev) {
-    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::bytes_pca));
+    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel<MODE, PCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = dev;
   }
-  const size_t smem = L.consts.variant == LVS_NDT_PCA ? SmemLayout::bytes_pca : SmemLayout::bytes_omp;
-  ndt_eval_kernel<<<L.n_pairs * L.blocks_per_pair, kEvalThreads, smem, st>>>(L);
+  ndt_eval_kernel<MODE, PCA><<<L.n_pairs * L.blocks_per_pair, kEvalThreads, smem, st>>>(L);
   CUDA_TRY(cudaGetLastError());
   return LVS_OK;
+}
+
+// The search mode and the registration variant are launch constants, so each combination is its own kernel (unrolled probe
+// loop, no weight staging for ndt_omp); whether the Hessian is wanted is per-pair state and is decided inside.
+int launch_eval(cudaStream_t st, const EvalLaunch& L) {
+  if (L.n_pairs <= 0) return LVS_OK;
+  const bool pca = L.consts.variant == LVS_NDT_PCA;
+  switch (L.consts.search) {
+    case LVS_DIRECT1: return pca ? launch_eval_as<LVS_DIRECT1, true>(st, L) : launch_eval_as<LVS_DIRECT1, false>(st, L);
+    case LVS_DIRECT7: return pca ? launch_eval_as<LVS_DIRECT7, true>(st, L) : launch_eval_as<LVS_DIRECT7, false>(st, L);
+    case LVS_DIRECT26: return pca ? launch_eval_as<LVS_DIRECT26, true>(st, L) : launch_eval_as<LVS_DIRECT26, false>(st, L);
+    default: return LVS_OK;                                  // KDTREE: radius-search derivatives live in the cold kernel
+  }
 }
 
 int eval_max_resident_ctas_per_sm() { return 3; }

@@ -21,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::lvs::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
 
+// GridParams::status values besides 0 (ok) and LVS_ERR_GRID_OVERFLOW
+constexpr int kStatusEmpty = 1, kStatusNeedsGrow = 2;
+
 struct BuildScratch {                    // reusable workspace of the voxelisation pipeline
   int capacity = 0;
   unsigned int* d_keys[2] = {nullptr, nullptr};
@@ -67,6 +70,11 @@ struct TargetGrid {                      // one voxelised target resident in HBM
 };
 
 int pack_points(cudaStream_t st, const float* d_in, size_t stride_floats, int n, float4* d_out);
+// Repack of up to kPackMany resident clouds in one launch (descriptors travel as kernel parameters).
+constexpr int kPackMany = 96;
+struct PackOne { const float* in; float4* out; int n; int stride_floats; };
+struct PackMany { PackOne c[kPackMany]; int count; };
+int pack_many(cudaStream_t st, const PackMany& pm, int max_n);
 
 // Evaluation kernels (ndt_eval.cu).  One launch advances every active pair by one evaluation and, in the
 // last CTA of each pair, by one step of the Newton / More-Thuente state machine.

@@ -26,9 +26,17 @@ __global__ void pack_points_kernel(const float* __restrict__ in, size_t stride_f
   out[i] = make_float4(p[0], p[1], p[2], 0.0f);
 }
 
+// Many clouds in one launch (batched setInputSource of resident scans): blockIdx.y = cloud.
+__global__ void pack_many_kernel(PackMany pm) {
+  const PackOne c = pm.c[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    const float* p = c.in + (size_t)i * c.stride_floats;
+    c.out[i] = make_float4(p[0], p[1], p[2], 0.0f);
+  }
+}
+
 // ------------------------------------------------------------------ bbox
 constexpr int kBboxBlocks = 148;
-constexpr int kStatusEmpty = 1, kStatusNeedsGrow = 2;
 
 __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partial /*[grid][8]*/,
                                                    unsigned int* __restrict__ ticket, GridParams* __restrict__ gp, float leaf, long long grid_capacity) {
@@ -605,6 +613,14 @@ void BuildScratch::release() {
   if (d_nseg) cudaFree(d_nseg);
   d_flags = d_pos = d_seg_start = d_hist = d_hist_scan = nullptr; d_bbox_partial = nullptr; d_ticket = nullptr; d_nseg = nullptr;
   capacity = 0;
+}
+
+int pack_many(cudaStream_t st, const PackMany& pm, int max_n) {
+  if (pm.count <= 0 || max_n <= 0) return LVS_OK;
+  dim3 grid((unsigned)std::min((max_n + 255) / 256, 148 * 4), (unsigned)pm.count);
+  pack_many_kernel<<<grid, 256, 0, st>>>(pm);
+  CUDA_TRY(cudaGetLastError());
+  return LVS_OK;
 }
 
 int pack_points(cudaStream_t st, const float* d_in, size_t stride_floats, int n, float4* d_out) {

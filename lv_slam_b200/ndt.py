@@ -232,6 +232,26 @@ class NdtBatch:
         ptr, n, stride, dev, keep = _cloud_args(xyz)
         C.check(self._L.lvs_ndt_batch_set_source(self._h, slot, ptr, n, stride, dev))
 
+    def _set_many(self, fn, slots, clouds):
+        """Plural setter: every cloud must share stride and residency (one C call, one repack launch for resident scans)."""
+        n = len(slots)
+        if n == 0:
+            return
+        args = [_cloud_args(c) for c in clouds]
+        stride, dev = args[0][2], args[0][3]
+        if any(a[2] != stride or a[3] != dev for a in args):
+            raise ValueError("set_sources / set_targets need clouds of one stride and one residency")
+        sl = (ctypes.c_int32 * n)(*slots)
+        ptrs = (ctypes.c_void_p * n)(*[a[0] for a in args])
+        cnt = (ctypes.c_size_t * n)(*[a[1] for a in args])
+        C.check(fn(self._h, n, sl, ptrs, cnt, stride, dev))
+
+    def set_targets(self, slots, clouds):
+        self._set_many(self._L.lvs_ndt_batch_set_targets, slots, clouds)
+
+    def set_sources(self, slots, clouds):
+        self._set_many(self._L.lvs_ndt_batch_set_sources, slots, clouds)
+
     def wait_uploads(self):
         """Blocks until every host cloud handed to set_target / set_source has reached the device (pinned buffers are free again)."""
         C.check(self._L.lvs_ndt_batch_wait_uploads(self._h))

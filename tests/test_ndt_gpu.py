@@ -290,3 +290,48 @@ def test_device_resident_inputs(small_pair):
     r = o.align(guess)
     assert n.getFinalNumIteration() == r["iterations"]
     assert np.max(np.abs(n.getFinalTransformation() - r["final"])) <= 1e-4
+
+
+def test_plural_setters_and_overlapped_uploads(small_pair, scan_pair):
+    """set_targets / set_sources (one call, fused repack) from pinned host, pageable host and resident clouds, with targets
+    re-set several times in a row (build lanes, staging ring, slot re-use): every path must give the single-call results bit for bit."""
+    import torch
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    tgt2, src2 = scan_pair[0][::3].copy(), scan_pair[1][::3].copy()
+    clouds_t = [tgt, tgt2, tgt[::2].copy(), tgt2[::2].copy(), tgt, tgt2]
+    clouds_s = [src, src2, src[:4000].copy(), src2[:9000].copy(), src[::2].copy(), src2[::2].copy(), src, src2]
+    pairs = [(i, i % len(clouds_t), guess if i % 2 == 0 else scan_pair[2]) for i in range(len(clouds_s))]
+    kw = dict(transformation_epsilon=0.01, max_iterations=12, search_method=L.LVS_DIRECT7)
+    ref = L.NdtBatch(len(clouds_t), len(clouds_s), **kw)
+    for i, c in enumerate(clouds_t):
+        ref.set_target(i, c)
+    for i, c in enumerate(clouds_s):
+        ref.set_source(i, c)
+    want = ref.align([p[0] for p in pairs], [p[1] for p in pairs], [p[2] for p in pairs])
+
+    def as_kind(c, kind):
+        t = torch.from_numpy(c)
+        return t.pin_memory() if kind == "pinned" else t.cuda() if kind == "resident" else c
+
+    for kind in ("pinned", "pageable", "resident"):
+        b = L.NdtBatch(len(clouds_t), len(clouds_s), **kw)
+        tt = [as_kind(c, kind) for c in clouds_t]
+        ss = [as_kind(c, kind) for c in clouds_s]
+        junk_t = [as_kind(np.ascontiguousarray(c[::-1]), kind) for c in clouds_t]
+        b.set_targets(list(range(len(tt))), junk_t)            # overwritten below without an align in between
+        b.set_sources(list(range(len(ss))), ss)
+        b.set_targets(list(range(len(tt))), tt)
+        got = []
+        for a in range(0, len(pairs), 3):                      # grouped aligns: later uploads overlap earlier aligns
+            g = pairs[a:a + 3]
+            got += b.align([p[0] for p in g], [p[1] for p in g], [p[2] for p in g])
+        b.wait_uploads()
+        for w, r in zip(want, got):
+            assert r["iterations"] == w["iterations"] and np.array_equal(r["final"], w["final"]), kind
+        # second round on the same object: slots re-used with different clouds
+        b.set_sources([0, 1], [ss[1], ss[0]])
+        r2 = b.align([0, 1], [1, 0], [pairs[1][2], pairs[0][2]])
+        assert np.array_equal(r2[0]["final"], want[1]["final"]) and np.array_equal(r2[1]["final"], want[0]["final"]), kind
+        b.close()
+    ref.close()

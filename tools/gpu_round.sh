@@ -18,6 +18,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
     python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
 # full capture of the hot kernel inside the batched bench step
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_eval_kernel -s 20 -c 3 -o $OUT/ndt_eval \
-    python bench.py --steps 1 --warmup 1 --batch 32 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 ls -la $OUT
 tail -3 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -3; cat $OUT/bench.json; tail -2 $OUT/bench.err
