@@ -39,7 +39,8 @@ typedef enum {
                                  (include/ndt_omp/voxel_grid_covariance_omp_impl.hpp:76-85) */
   LVS_ERR_BAD_SLOT = -8,
   LVS_ERR_NOT_SPD = -9,       /* pose graph: Cholesky failure (g2o LinearSolver returns false) */
-  LVS_ERR_EMPTY_GRAPH = -10   /* GraphSLAM::optimize returns -1 when the graph has no edge */
+  LVS_ERR_EMPTY_GRAPH = -10,  /* GraphSLAM::optimize returns -1 when the graph has no edge */
+  LVS_ERR_PEER = -11          /* point-sharded evaluation: a peer rank did not deliver its sums in time */
 } lvs_status;
 
 /* pclomp::NeighborSearchMethod, include/ndt_omp/ndt_omp.h:61 (same values in pclpca) */
@@ -165,6 +166,16 @@ int lvs_ndt_batch_total_launches(lvs_ndt_batch_t* b, long long* launches);
 /* Bytes this object has copied host->device and device->host since creation (clouds, pair states, results). */
 int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* d2h);
 int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int target_slot, int* n_cells, int* n_valid);
+/* ---- point-sharded evaluation across the GPUs of one node (one process per GPU) ----
+ * The sum over source points of computeDerivatives (ndt_omp_impl2.hpp:197-305) is split over `world` ranks: every rank is given
+ * the same targets, sources, pairs and guesses; it keeps the contiguous chunk [rank*n/world, (rank+1)*n/world) of every source and
+ * the 43 sums of each evaluation are exchanged through NVLink peer memory inside the evaluation kernel (no collective launch, no host
+ * round trip).  All ranks return bit-identical results.  Set-up: shard_init on every rank -> exchange the 64-byte handles by any
+ * means (torch.distributed all_gather, MPI, a file) -> shard_connect with all of them in rank order.  Every rank must then issue
+ * the same sequence of align / eval calls.  world == 1 is allowed (self-exchange; used by the single-GPU tests). */
+#define LVS_IPC_HANDLE_BYTES 64
+int lvs_ndt_batch_shard_init(lvs_ndt_batch_t* b, int rank, int world, int max_pairs, unsigned char handle_out[LVS_IPC_HANDLE_BYTES]);
+int lvs_ndt_batch_shard_connect(lvs_ndt_batch_t* b, const unsigned char* handles /* world x LVS_IPC_HANDLE_BYTES */);
 /* The batch object that backs a single registration handle (1 target slot, 1 source slot). */
 int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out);
 

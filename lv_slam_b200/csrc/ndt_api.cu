@@ -64,6 +64,7 @@ struct CloudSlot {
   // without a host synchronisation (a voxelisation), so that a re-upload cannot overwrite points that are still being read.
   cudaEvent_t ready = nullptr, used = nullptr;
   bool ready_pending = false, used_pending = false;
+  int n_total = 0;     // points of the whole cloud (> n when the batch keeps only its shard of every source)
   int up_lane = 0;     // upload stream of this slot (fixed, so that re-records of `ready` stay ordered behind earlier uploads)
 };
 
@@ -140,6 +141,14 @@ struct lvs_ndt_batch {
   int last_launches = 0, last_deriv_launches = 0;
   long total_launches = 0;
   long long h2d_bytes = 0, d2h_bytes = 0;   // bytes this object copied across PCIe since creation
+  // point sharding (lvs_ndt_batch_shard_*)
+  bool shard_on = false;
+  int shard_rank = 0, shard_world = 1, shard_cap = 0;
+  double* d_mail = nullptr;            // this rank's mailbox
+  double** d_peers = nullptr;          // device array of every rank's mailbox as mapped here
+  std::vector<double*> peer_ptrs;      // the same on the host; entries != d_mail were opened with cudaIpcOpenMemHandle
+  long long shard_serial = 0;
+  int *d_shard_error = nullptr, *h_shard_error = nullptr;
   int blocks_per_pair_override = 0;
   int chunk_first = 6, chunk_next = 4;
 };
@@ -190,6 +199,7 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
     CUDA_TRY(cudaEventCreateWithFlags(&slot.used, cudaEventDisableTiming));
   }
   slot.n = (int)n;
+  slot.n_total = (int)n;
   slot.set = true;
   if (n == 0) return LVS_OK;
   if (on_device) {
@@ -325,6 +335,7 @@ static PairDesc make_pair(lvs_ndt_batch* b, int src_slot, int tgt_slot) {
   const TargetGrid& tg = b->targets[tgt_slot];
   P.src = b->sources[src_slot].d_pts;
   P.n_src = b->sources[src_slot].n;
+  P.n_total = b->sources[src_slot].n_total;
   P.grid = tg.d_grid;
   P.recs = tg.d_recs;
   P.centroids = tg.d_centroids;
@@ -353,6 +364,20 @@ static int choose_bpp(lvs_ndt_batch* b, int n_pairs, int max_src) {
     if (eff >= best_eff - 1e-9) { best_eff = std::max(eff, best_eff); best = bpp; }
   }
   return best;
+}
+
+static void shard_view(lvs_ndt_batch* b, EvalLaunch& L) {
+  if (!b->shard_on) return;
+  L.shard.peers = b->d_peers; L.shard.mine = b->d_mail;
+  L.shard.rank = b->shard_rank; L.shard.world = b->shard_world; L.shard.cap = b->shard_cap;
+  L.shard.timeout_cycles = 4000000000LL;      // ~2 s at 1.9 GHz
+  L.shard.d_error = b->d_shard_error;
+}
+
+static int shard_check(lvs_ndt_batch* b) {
+  if (!b->shard_on) return LVS_OK;
+  if (*b->h_shard_error) return fail(LVS_ERR_PEER, "point-sharded evaluation: a peer rank did not deliver its sums within the time-out");
+  return LVS_OK;
 }
 
 // Runs the evaluation launches of one batch until every pair's state machine reports done.
@@ -387,6 +412,8 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
   L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
   L.n_pairs = n_pairs; L.blocks_per_pair = bpp; L.advance = 1;
   L.consts = make_consts(b->prm);
+  if (b->shard_on && n_pairs > b->shard_cap) return fail(LVS_ERR_INVALID_ARG, "%d pairs exceed the sharded batch's max_pairs %d", n_pairs, b->shard_cap);
+  shard_view(b, L);
   // worst case: initial pass + (max_iter + 2) outer iterations of (first + 10 trials + Hessian pass)
   const int max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
   int launches = 0;
@@ -405,14 +432,17 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
     for (int k = 0; k < chunk && launches < max_launches; k++) {
       const bool ev = prof && launches < kMaxEvents;
       if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * launches], b->st));
+      L.shard.serial = ++b->shard_serial;        // one serial per kernel launch: a pair may be evaluated by both kernels of a step
       if ((rc = launch_eval(b->st, L))) return rc;
-      if (need_cold && (rc = launch_eval_cold(b->st, L))) return rc;
+      if (need_cold) { L.shard.serial = ++b->shard_serial; if ((rc = launch_eval_cold(b->st, L))) return rc; }
       if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * launches + 1], b->st));
       launches++;
     }
     CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
     b->d2h_bytes += sizeof(int);
+    if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->st));
     CUDA_TRY(cudaStreamSynchronize(b->st));
+    if ((rc = shard_check(b))) return rc;
     if (*b->h_done >= n_pairs) break;
     chunk = b->chunk_next;
   }
@@ -480,12 +510,16 @@ static int run_tap(lvs_ndt_batch* b, int kind, const double p[6], const float* T
   L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
   L.n_pairs = 1; L.blocks_per_pair = bpp; L.advance = 0;
   L.consts = make_consts(b->prm);
+  shard_view(b, L);
+  L.shard.serial = ++b->shard_serial;
   if (kind == EVAL_HESS27 || b->prm.search_method == LVS_KDTREE) rc = launch_eval_cold(b->st, L);
   else rc = launch_eval(b->st, L);
   if (rc) return rc;
   b->total_launches++;
   CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, sizeof(AlignState), cudaMemcpyDeviceToHost, b->st));
+  if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->st));
   CUDA_TRY(cudaStreamSynchronize(b->st));
+  if ((rc = shard_check(b))) return rc;
   if (score) *score = s.score;
   if (g) memcpy(g, s.g, sizeof s.g);
   if (H36) memcpy(H36, s.H, sizeof s.H);
@@ -570,11 +604,22 @@ static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   return LVS_OK;
 }
 
+// The chunk of an n-point source this rank evaluates: [rank*n/world, (rank+1)*n/world).
+static void shard_range(const lvs_ndt_batch* b, size_t n, size_t* lo, size_t* cnt) {
+  if (!b->shard_on) { *lo = 0; *cnt = n; return; }
+  const size_t a = (size_t)b->shard_rank * n / (size_t)b->shard_world, e = (size_t)(b->shard_rank + 1) * n / (size_t)b->shard_world;
+  *lo = a; *cnt = e - a;
+}
+
 static int set_source(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
   int rc = set_device(b);
   if (rc) return rc;
   if (slot < 0 || slot >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slot);
-  return upload_cloud(b, b->sources[slot], xyz, n, stride_bytes, on_device, b->st);
+  size_t lo = 0, cnt = n;
+  shard_range(b, n, &lo, &cnt);
+  rc = upload_cloud(b, b->sources[slot], xyz ? (const float*)((const char*)xyz + lo * stride_bytes) : xyz, cnt, stride_bytes, on_device, b->st);
+  b->sources[slot].n_total = (int)n;
+  return rc;
 }
 
 // Batched setInputSource: host clouds go through the upload stream one by one (each keeps its own ready event); resident
@@ -587,7 +632,7 @@ static int set_sources(lvs_ndt_batch* b, int n, const int32_t* slots, const floa
     if (slots[i] < 0 || slots[i] >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slots[i]);
   if (!on_device) {
     for (int i = 0; i < n; i++)
-      if ((rc = upload_cloud(b, b->sources[slots[i]], xyz[i], counts[i], stride_bytes, 0, b->st))) return rc;
+      if ((rc = set_source(b, slots[i], xyz[i], counts[i], stride_bytes, 0))) return rc;
     return LVS_OK;
   }
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(LVS_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
@@ -598,7 +643,9 @@ static int set_sources(lvs_ndt_batch* b, int n, const int32_t* slots, const floa
     CloudSlot& slot = b->sources[slots[i]];
     // allocation and bookkeeping exactly as upload_cloud, the repack itself is deferred to the fused launch
     if ((rc = upload_cloud(b, slot, xyz[i], 0, stride_bytes, 1, b->st))) return rc;
-    const size_t cnt = counts[i];
+    size_t lo = 0, cnt = counts[i];
+    shard_range(b, counts[i], &lo, &cnt);
+    slot.n_total = (int)counts[i];
     if (cnt > 0 && !xyz[i]) return fail(LVS_ERR_INVALID_ARG, "xyz is NULL");
     if (cnt > (size_t)0x7fffff00) return fail(LVS_ERR_INVALID_ARG, "too many points");
     if (cnt > slot.cap) {
@@ -612,7 +659,7 @@ static int set_sources(lvs_ndt_batch* b, int n, const int32_t* slots, const floa
     if (cnt == 0) continue;
     if ((rc = wait_ready(b, slot))) return rc;
     PackOne& c = pm.c[pm.count++];
-    c.in = xyz[i]; c.out = slot.d_pts; c.n = (int)cnt; c.stride_floats = (int)(stride_bytes / 4);
+    c.in = (const float*)((const char*)xyz[i] + lo * stride_bytes); c.out = slot.d_pts; c.n = (int)cnt; c.stride_floats = (int)(stride_bytes / 4);
     max_n = std::max(max_n, (int)cnt);
     if (pm.count == kPackMany || i == n - 1) {
       if ((rc = pack_many(b->st, pm, max_n))) return rc;
@@ -693,6 +740,12 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
     }
   for (auto& sb : b->ring)
     if (sb.d) cudaFree(sb.d);
+  for (int r = 0; r < (int)b->peer_ptrs.size(); r++)
+    if (b->peer_ptrs[r] && b->peer_ptrs[r] != b->d_mail) cudaIpcCloseMemHandle(b->peer_ptrs[r]);
+  if (b->d_mail) cudaFree(b->d_mail);
+  if (b->d_peers) cudaFree(b->d_peers);
+  if (b->d_shard_error) cudaFree(b->d_shard_error);
+  if (b->h_shard_error) cudaFreeHost(b->h_shard_error);
   for (auto ev : b->ev_up_all) if (ev) cudaEventDestroy(ev);
   for (auto u : b->up) if (u) cudaStreamDestroy(u);
   for (auto& ln : b->lanes) {
@@ -793,6 +846,50 @@ int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* 
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   if (h2d) *h2d = b->h2d_bytes;
   if (d2h) *d2h = b->d2h_bytes;
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_shard_init(lvs_ndt_batch_t* b, int rank, int world, int max_pairs, unsigned char handle_out[LVS_IPC_HANDLE_BYTES]) {
+  if (!b || !handle_out) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || max_pairs < 1) return fail(LVS_ERR_INVALID_ARG, "bad rank / world / max_pairs");
+  if (b->d_mail) return fail(LVS_ERR_INVALID_ARG, "shard_init was already called on this object");
+  static_assert(sizeof(cudaIpcMemHandle_t) == LVS_IPC_HANDLE_BYTES, "IPC handle size");
+  int rc = set_device(b);
+  if (rc) return rc;
+  const size_t bytes = (size_t)2 * world * max_pairs * kMailStride * sizeof(double);
+  CUDA_TRY(cudaMalloc(&b->d_mail, bytes));
+  CUDA_TRY(cudaMemset(b->d_mail, 0, bytes));
+  CUDA_TRY(cudaMalloc(&b->d_peers, world * sizeof(double*)));
+  CUDA_TRY(cudaMalloc(&b->d_shard_error, sizeof(int)));
+  CUDA_TRY(cudaMemset(b->d_shard_error, 0, sizeof(int)));
+  CUDA_TRY(cudaMallocHost(&b->h_shard_error, sizeof(int)));
+  *b->h_shard_error = 0;
+  b->shard_rank = rank; b->shard_world = world; b->shard_cap = max_pairs;
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, b->d_mail));
+  memcpy(handle_out, &h, sizeof h);
+  return LVS_OK;
+}
+
+int lvs_ndt_batch_shard_connect(lvs_ndt_batch_t* b, const unsigned char* handles) {
+  if (!b || !handles) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  if (!b->d_mail) return fail(LVS_ERR_INVALID_ARG, "shard_init has not been called");
+  if (b->shard_on) return fail(LVS_ERR_INVALID_ARG, "already connected");
+  int rc = set_device(b);
+  if (rc) return rc;
+  b->peer_ptrs.assign(b->shard_world, nullptr);
+  for (int r = 0; r < b->shard_world; r++) {
+    if (r == b->shard_rank) { b->peer_ptrs[r] = b->d_mail; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * LVS_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    b->peer_ptrs[r] = (double*)p;
+  }
+  CUDA_TRY(cudaMemcpy(b->d_peers, b->peer_ptrs.data(), b->shard_world * sizeof(double*), cudaMemcpyHostToDevice));
+  b->shard_on = true;
+  // sources set before this point hold whole clouds: they have to be set again
+  for (auto& c : b->sources) c.set = false;
   return LVS_OK;
 }
 
@@ -943,6 +1040,7 @@ int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score) {
   if (rc) return rc;
   if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  if (b->shard_on) return fail(LVS_ERR_INVALID_ARG, "calculateScore is not available on a point-sharded object");
   if (b->sources[0].n == 0) { *score = NAN; return LVS_OK; }   // 0/0 in the reference
   if ((rc = wait_all_uploads(b))) return rc;
   if ((rc = finish_target(b, 0))) return rc;

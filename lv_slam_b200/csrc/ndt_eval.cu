@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const int bpp = L.blocks_per_pair;
   if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial);
   else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial);
-  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_src, reinterpret_cast<double*>(s_dyn), &s_last);
+  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last);
 }
 
 template <int MODE, bool PCA>

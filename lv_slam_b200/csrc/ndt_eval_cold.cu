@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kEvalThreads) ndt_eval_cold_kernel(EvalLaunch 
   if (kind == EVAL_HESS27) run_hess27(P, G, s_T, s_Rd, blk, bpp, c.gauss_d1, c.gauss_d2, c.resolution, s_red, partial);
   else if (kind == EVAL_DERIV_H) run_kdtree<true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);
   else run_kdtree<false>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);
-  eval_finish(L, pair, kind, kAcc, P.n_src, s_red, &s_last);
+  eval_finish(L, pair, kind, kAcc, P.n_total, s_red, &s_last);
 }
 
 int launch_eval_cold(cudaStream_t st, const EvalLaunch& L) {

@@ -58,9 +58,43 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
     s_scratch[r * 64 + k] = x;
   }
   __syncthreads();
-  if (threadIdx.x < nv) {
-    double x = 0;
+  double x = 0;
+  if (threadIdx.x < nv)
     for (int r = 0; r < R; r++) x += s_scratch[r * 64 + threadIdx.x];
+  if (L.shard.world > 1 || L.shard.mine) {
+    // ---- exchange of the rank sums through peer memory (see ShardView)
+    const ShardView& sh = L.shard;
+    const size_t rec = (((size_t)(sh.serial & 1) * sh.world + sh.rank) * sh.cap + pair) * kMailStride;
+    if (threadIdx.x < nv)
+      for (int p = 0; p < sh.world; p++) *reinterpret_cast<volatile double*>(sh.peers[p] + rec + threadIdx.x) = x;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < sh.world) {    // one flag store per peer, after every value store of this CTA is visible system-wide
+      __threadfence_system();
+      *reinterpret_cast<volatile long long*>(sh.peers[threadIdx.x] + rec + 43) = sh.serial;
+    }
+    __shared__ int s_peer_ok;
+    if (threadIdx.x == 0) s_peer_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < sh.world) {
+      const volatile long long* flag =
+          reinterpret_cast<const volatile long long*>(sh.mine + (((size_t)(sh.serial & 1) * sh.world + threadIdx.x) * sh.cap + pair) * kMailStride + 43);
+      const long long t0 = clock64();
+      while (*flag != sh.serial) {
+        if (clock64() - t0 > sh.timeout_cycles) { s_peer_ok = 0; break; }
+        __nanosleep(64);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (!s_peer_ok && threadIdx.x == 0) *sh.d_error = 1;
+    if (threadIdx.x < nv) {
+      x = 0;
+      for (int r = 0; r < sh.world; r++)
+        x += *reinterpret_cast<const volatile double*>(sh.mine + (((size_t)(sh.serial & 1) * sh.world + r) * sh.cap + pair) * kMailStride + threadIdx.x);
+    }
+  }
+  if (threadIdx.x < nv) {
     const int k = threadIdx.x;
     if (kind == EVAL_HESS27) { if (k >= 7) S.H[k - 7] = x; }
     else {

@@ -78,7 +78,23 @@ int pack_many(cudaStream_t st, const PackMany& pm, int max_n);
 
 // Evaluation kernels (ndt_eval.cu).  One launch advances every active pair by one evaluation and, in the
 // last CTA of each pair, by one step of the Newton / More-Thuente state machine.
+// Point-sharded evaluation (sum over independent source points): every rank evaluates its contiguous chunk of the
+// source against a replicated voxel grid, and the 43 sums are exchanged through peer memory INSIDE the evaluation kernel: the last
+// CTA of a pair stores its rank's sums into the mailbox of every peer (NVLink stores on IPC-mapped memory), publishes a flag,
+// waits for the flags of all ranks in its own mailbox and adds the contributions in rank order, so every rank obtains the same
+// bits and advances an identical copy of the Newton state machine - no host round trip and no separate collective launch.
+constexpr int kMailStride = 48;            // doubles per (rank, pair, parity) record: 43 sums, [43] = serial flag, padded to 384 B
+struct ShardView {
+  double* const* peers = nullptr;          // device array [world]: mailbox base of every rank as mapped in this process
+  double* mine = nullptr;                  // this rank's mailbox: [2 parity][world][cap][kMailStride]
+  int rank = 0, world = 1, cap = 0;
+  long long serial = 0;                    // evaluation launch counter, identical on every rank
+  long long timeout_cycles = 0;
+  int* d_error = nullptr;                  // set to 1 when a peer did not answer in time
+};
+
 struct EvalLaunch {
+  ShardView shard;
   const PairDesc* d_pairs;
   AlignState* d_states;
   TraceRec* d_trace;          // [n_pairs][kMaxTrace] or null

@@ -85,7 +85,8 @@ struct AlignConsts {
 // One (source, target) pair as the kernels see it.
 struct PairDesc {
   const float4* src;
-  int n_src;
+  int n_src;                // points this device evaluates (its shard of the source when the batch is point-sharded)
+  int n_total;              // points of the whole source cloud (trans_probability divisor, ndt_omp_impl2.hpp:187)
   const int* grid;
   const VoxelRec* recs;
   const float4* centroids;

@@ -33,3 +33,19 @@ def sum_over_ranks(value, world, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def shard_range(n, rank, world):
+    """Contiguous chunk [lo, hi) of an n-point source evaluated by `rank` when one align is point-sharded (the library computes the
+    same split: rank*n // world)."""
+    return rank * n // world, (rank + 1) * n // world
+
+
+def all_gather_bytes(blob, world):
+    """-> [blob of rank 0, ..., blob of rank world-1] over the default torch.distributed group (gloo or nccl)."""
+    if world <= 1:
+        return [bytes(blob)]
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, bytes(blob))
+    return out

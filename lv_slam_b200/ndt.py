@@ -197,10 +197,24 @@ class NormalDistributionsTransform:
         C.check(self._L.lvs_ndt_lookup_keys(self._h, g.ctypes.data, keys.ctypes.data))
         return keys
 
+    def enable_point_sharding(self, rank, world, exchange):
+        """Point-sharded align() of this registration object across `world` GPUs (see NdtBatch.enable_point_sharding)."""
+        _shard_setup(self._L, self.batch_handle(), rank, world, 1, exchange)
+
     def batch_handle(self):
         b = ctypes.c_void_p()
         C.check(self._L.lvs_ndt_handle_batch(self._h, ctypes.byref(b)))
         return b
+
+
+def _shard_setup(L, batch_handle, rank, world, max_pairs, exchange):
+    mine = (ctypes.c_ubyte * 64)()
+    C.check(L.lvs_ndt_batch_shard_init(batch_handle, rank, world, max_pairs, mine))
+    blobs = exchange(bytes(mine))
+    if len(blobs) != world or any(len(x) != 64 for x in blobs):
+        raise ValueError("exchange() must return one 64-byte handle per rank")
+    allh = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(blobs))
+    C.check(L.lvs_ndt_batch_shard_connect(batch_handle, allh))
 
 
 class NdtBatch:
@@ -251,6 +265,13 @@ class NdtBatch:
 
     def set_sources(self, slots, clouds):
         self._set_many(self._L.lvs_ndt_batch_set_sources, slots, clouds)
+
+    def enable_point_sharding(self, rank, world, max_pairs, exchange):
+        """Splits every source cloud over `world` ranks (one process per GPU); the 43 sums of each evaluation are exchanged through
+        NVLink peer memory inside the evaluation kernel.  `exchange(blob) -> [blob of rank 0, ..., blob of rank world-1]` moves the
+        64-byte IPC handles between the processes (lv_slam_b200.dist.all_gather_bytes under torch.distributed).  Call before
+        set_source; afterwards every rank must issue the same calls with the same (whole) clouds, pairs and guesses."""
+        _shard_setup(self._L, self._h, rank, world, max_pairs, exchange)
 
     def wait_uploads(self):
         """Blocks until every host cloud handed to set_target / set_source has reached the device (pinned buffers are free again)."""

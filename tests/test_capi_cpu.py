@@ -133,8 +133,12 @@ sm = D.sum_over_ranks(span - 2, world)
 import torch
 lo = [None] * world
 dist.all_gather_object(lo, (start, span))
+# point-sharding plumbing: the 64-byte IPC handles travel in rank order, the source chunks tile the cloud
+blobs = D.all_gather_bytes(bytes([rank]) * 64, world)
+chunks = [D.shard_range(125001, r, world) for r in range(world)]
 if rank == 0:
     print("RESULT", mx, sm, lo)
+    print("SHARD", [b[0] for b in blobs], [len(b) for b in blobs], chunks)
 dist.destroy_process_group()
 """
 
@@ -148,3 +152,5 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0]
     assert "11.0 12.0 [(0, 8), (8, 8)]" in line            # max over ranks, total pairs, disjoint frame ranges
+    shard = [l for l in out.stdout.splitlines() if l.startswith("SHARD")][0]
+    assert "[0, 1] [64, 64] [(0, 62500), (62500, 125001)]" in shard

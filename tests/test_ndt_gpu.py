@@ -335,3 +335,30 @@ def test_plural_setters_and_overlapped_uploads(small_pair, scan_pair):
         assert np.array_equal(r2[0]["final"], want[1]["final"]) and np.array_equal(r2[1]["final"], want[0]["final"]), kind
         b.close()
     ref.close()
+
+
+def test_point_sharding_self_exchange(small_pair):
+    """world = 1: the evaluation kernel sends its 43 sums through its own mailbox (same code path as the multi-GPU exchange, one
+    rank) - results must equal the unsharded object bit for bit, on the batch and on the single registration object."""
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    kw = dict(transformation_epsilon=0.01, max_iterations=20, search_method=L.LVS_DIRECT7)
+    a = L.NdtBatch(1, 2, **kw)
+    b = L.NdtBatch(1, 2, **kw)
+    b.enable_point_sharding(0, 1, 4, lambda blob: [blob])
+    for nb in (a, b):
+        nb.set_target(0, tgt); nb.set_source(0, src); nb.set_source(1, src[:5000])
+    g2 = guess.copy(); g2[1, 3] += 0.2
+    ra = a.align([0, 1, 0], [0, 0, 0], [guess, guess, g2])
+    rb = b.align([0, 1, 0], [0, 0, 0], [guess, guess, g2])
+    for x, y in zip(ra, rb):
+        assert x["iterations"] == y["iterations"] and x["n_eval"] == y["n_eval"]
+        assert np.array_equal(x["final"], y["final"]) and x["score"] == y["score"]
+    n, o = _mk(O.VAR_PCA, O.DIRECT1, max_iter=15)
+    n.enable_point_sharding(0, 1, lambda blob: [blob])
+    n.setInputTarget(tgt); o.set_target(tgt)
+    n.setInputSource(src); o.set_source(src)
+    n.align(guess)
+    r = o.align(guess)
+    assert n.getFinalNumIteration() == r["iterations"]
+    assert np.max(np.abs(n.getFinalTransformation() - r["final"])) <= 1e-6
