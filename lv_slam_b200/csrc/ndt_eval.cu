@@ -25,28 +25,71 @@ __constant__ int c_off26[26][3] = {
     {1, 1, 1},    {1, 0, 1},   {1, -1, 1},  {0, 1, 1},   {0, 0, 1},  {0, -1, 1},  {-1, 1, 1},  {-1, 0, 1},  {-1, -1, 1},
     {1, 1, 0},    {0, 1, 0},   {-1, 1, 0},  {1, 0, 0}};
 
-constexpr int kTileStride = 36;            // floats per output row of the staging tile: 32 lanes + 4 pad keeps rows 16 B aligned for the
-                                           // LDS.128 reads of the summing lanes and both the column writes and those reads conflict-free
+// ---- packed FP32 (sm_100 FMUL2 / FFMA2): one issue slot carries two IEEE float operations, each rounded exactly like the scalar
+// instruction, so every term stays bit-identical to the CPU path while the float math of a contribution needs about half the
+// issue slots.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false (seen with CUDA 12.9), which
+// would change the rounding; the packed add is therefore written as fma(x, ONE, y) with ONE = 1.0f taken from a kernel
+// parameter — x * 1.0f is exact, the instruction cannot absorb a preceding multiply, and it costs the same FFMA2.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 c; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
+__device__ __forceinline__ f32x2 mul2s(float a, f32x2 b) { return mul2(pk(a, a), b); }                 // scalar broadcast operand
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b, f32x2 one) { f32x2 c; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(c) : "l"(a), "l"(one), "l"(b)); return c; }
+
+// Staging tile of one warp: 22 rows of output PAIRS, each row holds the float2 of the 32 lanes (+ 4 floats of padding so that the
+// LDS.128 reads of the summing lanes fall on distinct bank groups).  Pair p of a contribution (see kSlotOut for the outputs):
+//   p = 0        (score, unused)
+//   p = 1..3     (g[2k], g[2k+1]),            k = p - 1
+//   p = 4..21    (H[2k][j], H[2k+1][j]),      j = (p - 4) / 3, k = (p - 4) % 3
+constexpr int kPairsH = 22, kPairsNoH = 4;
+constexpr int kTileStride = 68;            // floats per pair row: 32 lanes x 2 + 4 pad (stride / 4 odd)
 constexpr int kWarps = kEvalThreads / 32;
+
+// slot (pair * 2 + half) -> index in the canonical output vector (0 score, 1..6 gradient, 7 + 6 i + j Hessian), -1 = padding
+__device__ __forceinline__ int slot_to_out(int slot) {
+  const int p = slot >> 1, h = slot & 1;
+  if (p == 0) return h ? -1 : 0;
+  if (p < 4) return 1 + 2 * (p - 1) + h;
+  const int j = (p - 4) / 3, k = (p - 4) % 3;
+  return 7 + 6 * (2 * k + h) + j;
+}
 
 template <bool HESS>
 struct Shape {
-  static constexpr int NV = HESS ? kAcc : 7;         // outputs per contribution
-  static constexpr int NTASK = NV * 4;               // (output, 8-lane group) sums
-  static constexpr int TPL = (NTASK + 31) / 32;      // tasks per lane: 6 (172 tasks) or 1 (28 tasks)
+  static constexpr int NV = HESS ? kAcc : 7;                       // outputs per contribution
+  static constexpr int NP = HESS ? kPairsH : kPairsNoH;            // output pairs per contribution
+  static constexpr int TPL = (NP + 7) / 8;                         // summation passes: a pass covers 8 pairs x 4 lane groups
+  static constexpr int NSLOT = NP * 2;
 };
 
 // updateDerivatives + computePointDerivatives_AngleAxisd for one (point, cell) pair, written into column `lane` of the
-// staging tile.  xr = R*x (float), d = x' - mean, C = float inverse covariance (row-major).  The zero / identity entries of
-// the reference's 4x6 and 24x6 matrices are folded away by hand; every remaining product and sum keeps the reference's
-// (Eigen SSE) order, so each float term is bit-identical to the CPU path.  Returns false on the reference's early-out
-// (d2*e > 1, < 0 or NaN, :588-589): nothing is written then.
+// staging tile.  xr = R*x (float), d = x' - mean, Cp/C2 = float inverse covariance.  The zero / identity entries of the
+// reference's 4x6 and 24x6 matrices are folded away by hand; every remaining product and sum keeps the reference's (Eigen SSE)
+// order and rounding, so each float term is bit-identical to the CPU path.  Rows of the 6x6 Hessian are processed two at a
+// time in packed registers.  Returns false on the reference's early-out (d2*e > 1, < 0 or NaN, :588-589): nothing is written then.
+//   Cp[r] = (C[r][0], C[r][1]),  C2[r] = C[r][2]
 template <bool HESS>
-__device__ __forceinline__ bool contribute_tile(float* __restrict__ col /* tile + lane */, float xr, float yr, float zr, float d0, float d1,
-                                                float d2, const float* C, float gd2, double gauss_d1) {
-  const float xC0 = (d0 * C[0] + d2 * C[6]) + d1 * C[3];
-  const float xC1 = (d0 * C[1] + d2 * C[7]) + d1 * C[4];
-  const float xC2 = (d0 * C[2] + d2 * C[8]) + d1 * C[5];
+__device__ __forceinline__ bool contribute_tile(float2* __restrict__ col /* tile + lane */, float xr, float yr, float zr, float d0, float d1,
+                                                float d2, const f32x2* Cp, const float* C2, float gd2, double gauss_d1, f32x2 one) {
+  constexpr int RS = kTileStride / 2;      // row stride in float2
+  const float nx = -xr, ny = -yr, nz = -zr;
+  // P[r][k], k = 0..2: row r of [C | C * dR-columns] = (CJ[r][2k], CJ[r][2k+1])
+  f32x2 P[3][3];
+  const f32x2 ZN = pk(zr, ny), NX = pk(nx, xr);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const float c0 = lo_of(Cp[r]), c1 = hi_of(Cp[r]), c2 = C2[r];
+    P[r][0] = Cp[r];
+    P[r][1] = pk(c2, c1 * nz + c2 * yr);                                        // CJ[r][3]
+    P[r][2] = add2(mul2s(c0, ZN), mul2(pk(c2, c1), NX), one);                   // CJ[r][4] = c0*zr + c2*nx, CJ[r][5] = c0*ny + c1*xr
+  }
+  // a[j] = (d0*CJ[0][j] + d2*CJ[2][j]) + d1*CJ[1][j];  a[0..2] = d^T C
+  f32x2 A[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) A[k] = add2(add2(mul2s(d0, P[0][k]), mul2s(d2, P[2][k]), one), mul2s(d1, P[1][k]), one);
+  const float xC0 = lo_of(A[0]), xC1 = hi_of(A[0]), xC2 = lo_of(A[1]);
   const float q = (d0 * xC0 + d2 * xC2) + d1 * xC1;
   float e = (float)exp((double)((-gd2 * q) * 0.5f));
   const float score_inc = (float)(-gauss_d1 * (double)e);
@@ -54,45 +97,42 @@ __device__ __forceinline__ bool contribute_tile(float* __restrict__ col /* tile 
   if (e > kOne || e < 0.0f || e != e) return false;
   e = (float)((double)e * gauss_d1);
 
-  const float nx = -xr, ny = -yr, nz = -zr;
-  float CJ[3][6];
+  col[0] = make_float2(score_inc, 0.0f);
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    CJ[i][0] = C[i * 3]; CJ[i][1] = C[i * 3 + 1]; CJ[i][2] = C[i * 3 + 2];
-    CJ[i][3] = C[i * 3 + 1] * nz + C[i * 3 + 2] * yr;
-    CJ[i][4] = C[i * 3 + 0] * zr + C[i * 3 + 2] * nx;
-    CJ[i][5] = C[i * 3 + 0] * ny + C[i * 3 + 1] * xr;
+  for (int k = 0; k < 3; k++) {
+    const f32x2 g = mul2s(e, A[k]);
+    col[(1 + k) * RS] = make_float2(lo_of(g), hi_of(g));
   }
-  float a[6];
-  a[0] = xC0; a[1] = xC1; a[2] = xC2;
-#pragma unroll
-  for (int j = 3; j < 6; j++) a[j] = (d0 * CJ[0][j] + d2 * CJ[2][j]) + d1 * CJ[1][j];
-
-  col[0] = score_inc;
-#pragma unroll
-  for (int j = 0; j < 6; j++) col[(1 + j) * kTileStride] = e * a[j];
 
   if (HESS) {
-    // hp[i][j] = (d^T C) . Hp_ij  (non-zero only in the rotation block)
-    float hp[3][3];
-    hp[0][0] = xC2 * nz + xC1 * ny; hp[0][1] = xC1 * xr;            hp[0][2] = xC2 * xr;
-    hp[1][0] = xC0 * yr;            hp[1][1] = xC0 * nx + xC2 * nz; hp[1][2] = xC2 * yr;
-    hp[2][0] = xC0 * zr;            hp[2][1] = xC1 * zr;            hp[2][2] = xC0 * nx + xC1 * ny;
+    const float a[6] = {xC0, xC1, xC2, hi_of(A[1]), lo_of(A[2]), hi_of(A[2])};
+    // hp[i][j] = (d^T C) . Hp_ij  (non-zero only in the rotation block); rows 1 and 2 are kept packed
+    const float hp0[3] = {xC2 * nz + xC1 * ny, xC1 * xr, xC2 * xr};
+    f32x2 HP[3];
+    HP[0] = mul2s(xC0, pk(yr, zr));                                             // (hp[1][0], hp[2][0])
+    HP[1] = pk(xC0 * nx + xC2 * nz, xC1 * zr);                                  // (hp[1][1], hp[2][1])
+    HP[2] = pk(xC2 * yr, xC0 * nx + xC1 * ny);                                  // (hp[1][2], hp[2][2])
     const float ngd2 = -gd2;
+    f32x2 AI[3];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const float ai = ngd2 * a[i];
+    for (int k = 0; k < 3; k++) AI[k] = mul2s(ngd2, A[k]);
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
-        // Mx[j][i] = J.col(j) . CJ.col(i)
-        float m;
-        if (j < 3) m = CJ[j][i];
-        else if (j == 3) m = yr * CJ[2][i] + nz * CJ[1][i];
-        else if (j == 4) m = zr * CJ[0][i] + nx * CJ[2][i];
-        else m = ny * CJ[0][i] + xr * CJ[1][i];
-        float t = ai * a[j];
-        if (i >= 3 && j >= 3) t = t + hp[i - 3][j - 3];
-        col[(7 + i * 6 + j) * kTileStride] = e * (t + m);
+    for (int j = 0; j < 6; j++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        // rows i = 2k, 2k+1:  t = (-d2 a_i) a_j  [+ hp[i-3][j-3]],  m = J.col(j) . CJ.col(i),  H_ij = e (t + m)
+        f32x2 t = mul2s(a[j], AI[k]);
+        if (j >= 3) {
+          if (k == 1) t = pk(lo_of(t), hi_of(t) + hp0[j - 3]);
+          if (k == 2) t = add2(t, HP[j - 3], one);
+        }
+        f32x2 m;
+        if (j < 3) m = P[j][k];
+        else if (j == 3) m = add2(mul2s(yr, P[2][k]), mul2s(nz, P[1][k]), one);
+        else if (j == 4) m = add2(mul2s(zr, P[0][k]), mul2s(nx, P[2][k]), one);
+        else m = add2(mul2s(ny, P[0][k]), mul2s(xr, P[1][k]), one);
+        const f32x2 o = mul2s(e, add2(t, m, one));
+        col[(4 + j * 3 + k) * RS] = make_float2(lo_of(o), hi_of(o));
       }
     }
   }
@@ -100,14 +140,14 @@ __device__ __forceinline__ bool contribute_tile(float* __restrict__ col /* tile 
 }
 
 // Per-warp staging in shared memory (dynamic, carved up in SmemLayout):
-//   tile [43][33] f32   float contributions of one round of 32 (point, cell) pairs
+//   tile [22][68] f32   float contributions of one round of 32 (point, cell) pairs, as output pairs
 //   pts  [6][64]  f32   x', y', z' (transformed point) and R*x of the 64 points of the current warp iteration
 //   q    [256]    i32   queue of hits: record index * 64 + point slot
 //   qw   [256]    f64   ndt_pca only: weight that multiplies the entry's contribution
 constexpr int kPtsPerLane = 2;
 constexpr int kPtsPerIter = 32 * kPtsPerLane;
 constexpr int kQueueCap = 256;
-constexpr int kTileFloats = kAcc * kTileStride;
+constexpr int kTileFloats = kPairsH * kTileStride;
 
 struct SmemLayout {
   static constexpr size_t tile_off = 0;
@@ -118,54 +158,64 @@ struct SmemLayout {
   static constexpr size_t bytes_pca = qw_off + sizeof(double) * kWarps * kQueueCap;
 };
 static_assert(SmemLayout::qw_off % 8 == 0, "qw must be 8-byte aligned");
-static_assert(sizeof(double) * kWarps * kAcc * 4 <= SmemLayout::pts_off, "the CTA reduction scratch aliases the tile region");
+static_assert((sizeof(float) * kTileFloats) % 16 == 0, "per-warp tiles must stay 16-byte aligned");
+static_assert(sizeof(double) * kWarps * kPairsH * 2 * 4 <= SmemLayout::pts_off, "the CTA reduction scratch aliases the tile region");
 
 // One round: lanes e < n_round take queue entries q[head + lane], stage their float contributions in the tile, then the
-// warp adds the round into its fp64 accumulators.  Columns of lanes without a contribution (short round, or the reference's
-// early-out) are zero-filled and summed like the others: adding +0.0 is exact and an accumulator that starts at +0.0 never
-// becomes -0.0, so no per-group predicate is needed in the summation.
+// warp adds the round into its fp64 accumulators: in pass t lane l owns pair 8t + (l & 7) and the lane group l >> 3 (8 lanes),
+// i.e. two accumulators (the two outputs of the pair), fed by four LDS.128.  Columns of lanes without a contribution (short
+// round, or the reference's early-out) are zero-filled and summed like the others: adding +0.0 is exact and an accumulator that
+// starts at +0.0 never becomes -0.0, so no per-group predicate is needed in the summation.
 template <bool HESS, bool PCA>
-__device__ __forceinline__ void process_round(double* acc, const VoxelRec* __restrict__ recs, const float* pts, const int* q, const double* qw,
-                                              float* tile, int lane, int head, int n_round, float gd2, double gd1) {
+__device__ __forceinline__ void process_round(double (*acc)[2], const VoxelRec* __restrict__ recs, const float* pts, const int* q, const double* qw,
+                                              float* tile, int lane, int head, int n_round, float gd2, double gd1, f32x2 one) {
   using Sh = Shape<HESS>;
   bool used = false;
   double w = 0.0;
+  float2* col = reinterpret_cast<float2*>(tile) + lane;
   if (lane < n_round) {
     const int ent = q[head + lane];
     const int rec = ent / kPtsPerIter, slot = ent % kPtsPerIter;
     const VoxelRec* vr = recs + rec;
     const double2 m01 = __ldg(reinterpret_cast<const double2*>(vr));
-    const float4 q1 = __ldg(reinterpret_cast<const float4*>(vr) + 1);   // mean[2] (8 B) + icov[0..1]
-    const float4 q2 = __ldg(reinterpret_cast<const float4*>(vr) + 2);   // icov[2..5]
-    const float4 q3 = __ldg(reinterpret_cast<const float4*>(vr) + 3);   // icov[6..8] + meta
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(vr) + 1);   // mean[2] (8 B) + C00 C01
+    const float4 q2 = __ldg(reinterpret_cast<const float4*>(vr) + 2);   // C10 C11 C20 C21
+    const float4 q3 = __ldg(reinterpret_cast<const float4*>(vr) + 3);   // C02 C12 C22 + meta
     const double m2 = __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x));
-    const float C[9] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z};
+    const f32x2 Cp[3] = {pk(q1.z, q1.w), pk(q2.x, q2.y), pk(q2.z, q2.w)};
+    const float C2[3] = {q3.x, q3.y, q3.z};
     const float tx = pts[0 * kPtsPerIter + slot], ty = pts[1 * kPtsPerIter + slot], tz = pts[2 * kPtsPerIter + slot];
     const float d0 = (float)((double)tx - m01.x), d1 = (float)((double)ty - m01.y), d2 = (float)((double)tz - m2);
-    used = contribute_tile<HESS>(tile + lane, pts[3 * kPtsPerIter + slot], pts[4 * kPtsPerIter + slot], pts[5 * kPtsPerIter + slot], d0, d1, d2, C,
-                                 gd2, gd1);
+    used = contribute_tile<HESS>(col, pts[3 * kPtsPerIter + slot], pts[4 * kPtsPerIter + slot], pts[5 * kPtsPerIter + slot], d0, d1, d2, Cp, C2,
+                                 gd2, gd1, one);
     if (PCA) w = qw[head + lane];
   }
   if (!used) {
 #pragma unroll
-    for (int o = 0; o < Sh::NV; o++) tile[o * kTileStride + lane] = 0.0f;
+    for (int p = 0; p < Sh::NP; p++) col[p * (kTileStride / 2)] = make_float2(0.0f, 0.0f);
   }
   __syncwarp();
+  const int g = lane >> 3;
 #pragma unroll
   for (int t = 0; t < Sh::TPL; t++) {
-    const int task = lane + 32 * t;
-    const int o = task >> 2, g = task & 3;
-    const bool live = (Sh::NTASK % 32 == 0) || t + 1 < Sh::TPL || task < Sh::NTASK;
-    const float4* row = reinterpret_cast<const float4*>(tile + (live ? o : 0) * kTileStride + 8 * g);
-    const float4 lo = row[0], hi = row[1];
-    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    double a = acc[t];
+    const int p = 8 * t + (lane & 7);
+    const bool live = (Sh::NP % 8 == 0) || t + 1 < Sh::TPL || p < Sh::NP;
+    // dead lanes of the last pass read a row whose bank group no live lane of their quarter-warp uses (rows 8 apart share banks)
+    const float4* row = reinterpret_cast<const float4*>(tile + (live ? p : p - (HESS ? 16 : 4)) * kTileStride + 16 * g);
+    double a0 = acc[t][0], a1 = acc[t][1];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      if (PCA) a += (double)v[jj] * __shfl_sync(0xffffffffu, w, 8 * g + jj);   // zero columns carry w = 0 or a finite weight: exact either way
-      else a += (double)v[jj];
+    for (int jj = 0; jj < 4; jj++) {
+      const float4 v = row[jj];          // lanes 8g + 2jj and 8g + 2jj + 1
+      if (PCA) {
+        const double w0 = __shfl_sync(0xffffffffu, w, 8 * g + 2 * jj), w1 = __shfl_sync(0xffffffffu, w, 8 * g + 2 * jj + 1);
+        a0 += (double)v.x * w0; a1 += (double)v.y * w0;      // zero columns carry w = 0 or a finite weight: exact either way
+        a0 += (double)v.z * w1; a1 += (double)v.w * w1;
+      } else {
+        a0 += (double)v.x; a1 += (double)v.y;
+        a0 += (double)v.z; a1 += (double)v.w;
+      }
     }
-    acc[t] = a;    // lanes past NTASK in the last pass sum row 0 into an accumulator that is never read
+    acc[t][0] = a0; acc[t][1] = a1;      // lanes past NP in the last pass sum a live row into accumulators that are never read
   }
   __syncwarp();
 }
@@ -177,7 +227,7 @@ template <> struct Probes<LVS_DIRECT26> { static constexpr int K = 26; };
 
 template <int MODE, bool HESS, bool PCA>
 __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2,
-                                           double gd1, unsigned char* s_dyn, double* partial) {
+                                           double gd1, unsigned char* s_dyn, double* partial, float one_f) {
   using Sh = Shape<HESS>;
   constexpr int K = Probes<MODE>::K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -188,9 +238,10 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
   double* qw = reinterpret_cast<double*>(s_dyn + SmemLayout::qw_off) + warp * kQueueCap;   // only mapped for ndt_pca launches
   const VoxelRec* __restrict__ recs = P.recs;
   const int* __restrict__ grid = P.grid;
-  double acc[Sh::TPL];
+  const f32x2 one = pk(one_f, one_f);
+  double acc[Sh::TPL][2];
 #pragma unroll
-  for (int t = 0; t < Sh::TPL; t++) acc[t] = 0.0;
+  for (int t = 0; t < Sh::TPL; t++) acc[t][0] = acc[t][1] = 0.0;
   // floor(x / leaf) in float (voxel_grid_covariance_omp_impl.hpp:379-381).  For a power-of-two leaf the quotient equals the
   // product with the (exact) reciprocal bit for bit, so the division is only issued for other leaf sizes.
   const float inv_leaf = 1.0f / G.leaf;
@@ -205,7 +256,7 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
       auto drain = [&]() {
         __syncwarp();
         int head = 0;
-        for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, 32, gd2, gd1);
+        for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, 32, gd2, gd1, one);
         const int rem = nq - head;
         int ent = 0; double we = 0.0;
         if (lane < rem) { ent = q[head + lane]; if (PCA) we = qw[head + lane]; }
@@ -269,25 +320,35 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
       static_assert(MODE != LVS_DIRECT1 || kPtsPerLane * 32 <= kQueueCap, "queue capacity");
       __syncwarp();
       // ---- phase B: rounds of 32 queued (point, cell) contributions
-      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, min(32, nq - head), gd2, gd1);
+      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, min(32, nq - head), gd2, gd1, one);
     }
   }
-  // CTA partial: s_red[warp][task] (aliases the tile region) -> output o sums its 4 groups over the 8 warps in fixed order
+  // CTA partial: s_red[warp][slot][group] (aliases the tile region) -> every output slot sums its 4 lane groups over the 8 warps in
+  // fixed order and lands at its place in the canonical output vector
   __syncthreads();
   double* s_red = reinterpret_cast<double*>(s_dyn);
+  {
+    const int g = lane >> 3;
 #pragma unroll
-  for (int t = 0; t < Sh::TPL; t++) {
-    const int task = lane + 32 * t;
-    if (task < Sh::NTASK) s_red[warp * Sh::NTASK + task] = acc[t];
+    for (int t = 0; t < Sh::TPL; t++) {
+      const int p = 8 * t + (lane & 7);
+      if (p < Sh::NP) {
+        s_red[(warp * Sh::NSLOT + 2 * p) * 4 + g] = acc[t][0];
+        s_red[(warp * Sh::NSLOT + 2 * p + 1) * 4 + g] = acc[t][1];
+      }
+    }
   }
   __syncthreads();
-  if (threadIdx.x < Sh::NV) {
-    double x = 0;
+  if (threadIdx.x < Sh::NSLOT) {
+    const int out = slot_to_out(threadIdx.x);
+    if (out >= 0) {
+      double x = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++)
+      for (int w = 0; w < kWarps; w++)
 #pragma unroll
-      for (int g = 0; g < 4; g++) x += s_red[w * Sh::NTASK + threadIdx.x * 4 + g];
-    partial[threadIdx.x] = x;
+        for (int g = 0; g < 4; g++) x += s_red[(w * Sh::NSLOT + threadIdx.x) * 4 + g];
+      partial[out] = x;
+    }
   }
 }
 
@@ -309,8 +370,8 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const float gd2 = (float)c.gauss_d2;
   double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
   const int bpp = L.blocks_per_pair;
-  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial);
-  else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial);
+  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one);
+  else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one);
   eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last);
 }
 

@@ -195,7 +195,7 @@ __device__ __noinline__ void point_kdtree(Acc<HESS>& A, const PairDesc& P, const
   for (int k = 0; k < Hh.n; k++) {
     const VoxelRec* vr = P.recs + Hh.rec[k];
     float C[9];
-    for (int a = 0; a < 9; a++) C[a] = vr->icov[a];
+    for (int a = 0; a < 9; a++) C[a] = vr->icov[icov_slot(a)];
     const float d0 = (float)((double)tx - vr->mean[0]), d1 = (float)((double)ty - vr->mean[1]), d2 = (float)((double)tz - vr->mean[2]);
     contribute<HESS>(A, xr, yr, zr, d0, d1, d2, C, gd2, gd1, wsuf[k]);
   }

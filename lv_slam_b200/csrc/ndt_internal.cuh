@@ -104,6 +104,7 @@ struct EvalLaunch {
   int n_pairs;
   int blocks_per_pair;
   int advance;                // 1: run the align state machine; 0: tap mode, only store score/g/H
+  float one = 1.0f;           // run-time 1.0f for the packed adds of the hot kernel (ndt_eval.cu: keeps ptxas from contracting them)
   AlignConsts consts;
 };
 int launch_eval(cudaStream_t st, const EvalLaunch& L);        // direct-search derivative passes (hot)

@@ -8,8 +8,9 @@ namespace lvs {
 // One record per occupied target cell, 64 B, 16 B aligned: four LDG.128 per probe.
 //   mean  : f64 x3  (the reference subtracts the double mean from the float point in double,
 //                    include/ndt_omp/ndt_omp_impl2.hpp:272-275)
-//   icov  : f32 x9  row-major = Matrix3d::cast<float>() of the inverse covariance (:572-573);
-//                    stored full because V*L*V^-1 rebuilt covariances are not exactly symmetric
+//   icov  : f32 x9  = Matrix3d::cast<float>() of the inverse covariance (:572-573); stored full because V*L*V^-1 rebuilt
+//                    covariances are not exactly symmetric.  Storage order C00 C01 | C10 C11 | C20 C21 | C02 C12 C22 (kIcovSlot):
+//                    the (C[r][0], C[r][1]) pairs land 8-byte aligned for the packed FP32 math of the hot kernel
 //   meta  : low 24 bits = ndt_pca integer weight int(scale*|mean|) (1 for ndt_omp),
 //           bit 30 = leaf usable by the direct searches (nr_points >= min_points and not invalidated)
 struct __align__(16) VoxelRec {
@@ -18,6 +19,9 @@ struct __align__(16) VoxelRec {
   int32_t meta;
 };
 static_assert(sizeof(VoxelRec) == 64, "VoxelRec must be 64 bytes");
+
+// storage position of the row-major element a = 3 r + c inside VoxelRec::icov
+__host__ __device__ constexpr int icov_slot(int a) { return (a % 3 == 2) ? 6 + a / 3 : 2 * (a / 3) + a % 3; }
 
 constexpr int kMetaValidBit = 1 << 30;
 constexpr int kMetaWeightMask = 0xFFFFFF;

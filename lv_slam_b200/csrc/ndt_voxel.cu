@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(128) leaf_finalize_kernel(const unsigned int* 
         mat3_inverse(cov, ic);
         double mxc = ic[0], mnc = ic[0];
         for (int a = 1; a < 9; a++) { mxc = fmax(mxc, ic[a]); mnc = fmin(mnc, ic[a]); }
-        for (int a = 0; a < 9; a++) rec.icov[a] = (float)ic[a];
+        for (int a = 0; a < 9; a++) rec.icov[icov_slot(a)] = (float)ic[a];
         if (mxc == (double)INFINITY || mnc == -(double)INFINITY) out_npts = -1;
         else usable = true;
         rec.meta = (weight & kMetaWeightMask) | (usable ? kMetaValidBit : 0);
