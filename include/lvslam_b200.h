@@ -229,6 +229,14 @@ int lvs_pgo_compute_errors(lvs_pgo_t* h, double* err6, double* chi2, double* rob
 int lvs_pgo_system_size(lvs_pgo_t* h, int* n_free, int* n_offdiag);
 int lvs_pgo_linearize(lvs_pgo_t* h, double* Hd, int32_t* off_ij, double* Ho, double* b);
 int lvs_pgo_solve(lvs_pgo_t* h, double lambda, double tolerance, int max_iterations, double* x, int* iterations);
+/* Direct solver of the LVS_PGO_*_CHOL kinds: supernodal multifrontal Cholesky on the 6x6 block pattern (replaces
+ * LinearSolverCholmod / LinearSolverCSparse, g2o solvers/cholmod/linear_solver_cholmod.h:115-154, solvers/csparse/
+ * linear_solver_csparse.h:126-307; block ordering as solver_cholmod.cpp:45-86 "var_cholmod").  lvs_pgo_solve uses it when
+ * tolerance <= 0.  chol_analyze is the host-side symbolic step alone (minimum-degree ordering, elimination tree, supernodes) on
+ * a block pattern given as n_off (row < col) pairs; stats = {nnz(L) in 6x6 blocks, supernodes, tree levels, largest frontal
+ * dimension, arena bytes, factorisation multiply-adds}.  It needs no device. */
+int lvs_pgo_chol_analyze(int n_blocks, int n_off, const int32_t* off_ij, long long stats[6], int32_t* perm_out);
+int lvs_pgo_chol_info(lvs_pgo_t* h, long long stats[6]);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

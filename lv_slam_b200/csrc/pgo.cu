@@ -25,6 +25,7 @@
 #include <new>
 #include "ndt_internal.cuh"
 #include "pgo_math.cuh"
+#include "pgo_chol.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -368,6 +369,10 @@ struct lvs_pgo {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double pcg_tol_override = 0.0;   // 0: by solver kind
   int pcg_max_iter_override = 0;
+  lvs::CholDevice chol;            // direct solver of the *_CHOL kinds (pgo_chol.cu)
+  bool use_chol = false;
+  long long chol_nnz_l = 0; double chol_flops = 0; int chol_fronts = 0, chol_levels = 0, chol_max_front = 0;
+  int solve_launches = 0;          // kernel launches of the linear solves since the last optimize() started
   std::vector<lvs_pgo_iter_rec> trace;
 };
 
@@ -390,6 +395,8 @@ static int dev_upload(lvs_pgo* h, T** p, const std::vector<T>& v) {
 }
 
 static void free_graph(lvs_pgo* h) {
+  chol_free(h->chol);
+  h->use_chol = false;
   for (void* p : h->allocs) cudaFree(p);
   h->allocs.clear();
   h->has_graph = false;
@@ -418,6 +425,11 @@ static int run_linearize(lvs_pgo* h) {
 }
 
 static int run_pcg(lvs_pgo* h, double lambda, double tol, double prev_residual, int max_iter) {
+  if (h->use_chol && tol <= 1e-20) {
+    // direct solve: sparse block Cholesky (LinearSolverCholmod / LinearSolverCSparse in the reference)
+    h->solve_launches--;             // callers count one launch per solve
+    return chol_solve(h->chol, h->st, h->D.Hd, h->D.Ho, h->D.b, lambda, h->D.x, &h->D.sc->scale, &h->D.sc->pcg_ok, &h->solve_launches);
+  }
   void* args[] = {(void*)&h->D, (void*)&lambda, (void*)&tol, (void*)&prev_residual, (void*)&max_iter};
   CUDA_TRY(cudaLaunchCooperativeKernel((const void*)pgo_pcg_kernel, dim3(h->pcg_grid), dim3(kPgoThreads), args, 0, h->st));
   return LVS_OK;
@@ -593,6 +605,17 @@ int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const 
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));
+  if ((h->solver == LVS_PGO_LM_CHOL || h->solver == LVS_PGO_GN_CHOL) && nfree > 0) {
+    // cholmod_analyze_p / cs_schol once per structure (linear_solver_cholmod.h:271-338): ordering + symbolic factorisation
+    std::vector<int> off_ij((size_t)noff * 2);
+    for (int o = 0; o < noff; o++) { off_ij[2 * o] = blocks[o].second; off_ij[2 * o + 1] = blocks[o].first; }
+    CholSymbolic sym;
+    chol_analyze(nfree, noff, off_ij.data(), sym);
+    if ((rc = chol_upload(sym, noff, h->chol, h->st))) { free_graph(h); return rc; }
+    h->use_chol = true;
+    h->chol_nnz_l = sym.nnz_l_blocks; h->chol_flops = sym.flops; h->chol_fronts = (int)sym.fronts.size();
+    h->chol_levels = (int)sym.level_ptr.size() - 1; h->chol_max_front = sym.max_front;
+  }
   h->has_graph = true;
   return LVS_OK;
 }
@@ -648,6 +671,7 @@ int lvs_pgo_optimize(lvs_pgo_t* h, int max_iterations, lvs_pgo_stats* stats) {
   solver_tolerance(h, &tol, &carry, &pcg_max);
   double prev_residual = -1.0;
   int launches = 0, lin_launches = 0, pcg_total = 0, trials_total = 0;
+  h->solve_launches = 0;
   float lin_ms = 0, solve_ms = 0;
   CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
   // graph->computeActiveErrors(); chi2 = graph->chi2()   (graph_slam.cpp:313-316)
@@ -742,7 +766,7 @@ int lvs_pgo_optimize(lvs_pgo_t* h, int max_iterations, lvs_pgo_stats* stats) {
   stats->robust_chi2_after = h->h_sc->chi2_robust;
   stats->lambda_final = lambda;
   stats->device_ms = total_ms; stats->linearize_ms = lin_ms; stats->solve_ms = solve_ms;
-  stats->lm_trials = trials_total; stats->pcg_iterations = pcg_total; stats->launches = launches; stats->linearize_launches = lin_launches;
+  stats->lm_trials = trials_total; stats->pcg_iterations = pcg_total; stats->launches = launches + h->solve_launches; stats->linearize_launches = lin_launches;
   return LVS_OK;
 }
 
@@ -807,6 +831,28 @@ int lvs_pgo_solve(lvs_pgo_t* h, double lambda, double tolerance, int max_iterati
   if ((rc = run_pcg(h, lambda, tolerance, -1.0, max_iterations > 0 ? max_iterations : h->D.nfree * 6)) || (rc = fetch_scalars(h))) return rc;
   if (x) CUDA_TRY(cudaMemcpy(x, h->D.x, (size_t)h->D.nfree * 6 * sizeof(double), cudaMemcpyDeviceToHost));
   if (iterations) *iterations = h->h_sc->pcg_iters;
+  return LVS_OK;
+}
+
+// Symbolic analysis of the direct solver, host only (no device needed): stats = {nnz(L) in 6x6 blocks, fronts, levels,
+// largest front dimension, arena bytes, factorisation multiply-adds}; perm_out (may be NULL) receives the elimination order.
+int lvs_pgo_chol_analyze(int n_blocks, int n_off, const int32_t* off_ij, long long stats[6], int32_t* perm_out) {
+  if (n_blocks < 0 || n_off < 0 || (n_off > 0 && !off_ij) || !stats) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  for (int o = 0; o < n_off; o++)
+    if (off_ij[2 * o] < 0 || off_ij[2 * o + 1] >= n_blocks || off_ij[2 * o] >= off_ij[2 * o + 1]) return fail(LVS_ERR_INVALID_ARG, "off block %d is not (row < col)", o);
+  CholSymbolic sym;
+  chol_analyze(n_blocks, n_off, off_ij, sym);
+  stats[0] = sym.nnz_l_blocks; stats[1] = (long long)sym.fronts.size(); stats[2] = (long long)sym.level_ptr.size() - 1;
+  stats[3] = sym.max_front; stats[4] = sym.arena * 8; stats[5] = (long long)sym.flops;
+  if (perm_out) for (int c = 0; c < n_blocks; c++) perm_out[c] = sym.perm[c];
+  return LVS_OK;
+}
+
+// Structure of the direct solver attached to this graph (zeros when the solver kind is iterative).
+int lvs_pgo_chol_info(lvs_pgo_t* h, long long stats[6]) {
+  if (!h || !stats) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  stats[0] = h->use_chol ? h->chol_nnz_l : 0; stats[1] = h->use_chol ? h->chol_fronts : 0; stats[2] = h->use_chol ? h->chol_levels : 0;
+  stats[3] = h->use_chol ? h->chol_max_front : 0; stats[4] = h->use_chol ? h->chol.arena_doubles * 8 : 0; stats[5] = h->use_chol ? (long long)h->chol_flops : 0;
   return LVS_OK;
 }
 

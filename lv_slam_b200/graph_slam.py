@@ -205,6 +205,19 @@ def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iteration
     return {k: getattr(st, k) for k, _ in C.PgoStats._fields_}
 
 
+CHOL_STAT_NAMES = ("nnz_l_blocks", "fronts", "levels", "max_front", "arena_bytes", "factor_fma")
+
+
+def chol_analyze(n_blocks, off_ij):
+    """Host-side symbolic analysis of the direct solver (lvs_pgo_chol_analyze): no device needed.
+    off_ij: (m, 2) int32 pairs (row < col) of the non-zero upper blocks.  Returns (stats dict, elimination order)."""
+    off = np.ascontiguousarray(off_ij, dtype=np.int32).reshape(-1, 2)
+    stats = (ctypes.c_longlong * 6)()
+    perm = np.zeros(int(n_blocks), np.int32)
+    C.check(C.lib().lvs_pgo_chol_analyze(int(n_blocks), off.shape[0], off.ctypes.data, stats, perm.ctypes.data))
+    return dict(zip(CHOL_STAT_NAMES, [int(v) for v in stats])), perm
+
+
 class PoseGraph:
     """Flat-array handle on the pose-graph C-ABI (tests / bench)."""
 
@@ -265,6 +278,11 @@ class PoseGraph:
         Hd, Ho, b, off = np.zeros((nf.value, 6, 6)), np.zeros((no.value, 6, 6)), np.zeros(nf.value * 6), np.zeros((no.value, 2), np.int32)
         C.check(self._L.lvs_pgo_linearize(self._h, Hd.ctypes.data, off.ctypes.data, Ho.ctypes.data, b.ctypes.data))
         return dict(Hd=Hd, Ho=Ho, off=off, b=b)
+
+    def chol_info(self):
+        stats = (ctypes.c_longlong * 6)()
+        C.check(self._L.lvs_pgo_chol_info(self._h, stats))
+        return dict(zip(CHOL_STAT_NAMES, [int(v) for v in stats]))
 
     def solve(self, lam, tolerance=1e-24, max_iterations=0):
         nf = ctypes.c_int(0)

@@ -154,3 +154,43 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     assert "11.0 12.0 [(0, 8), (8, 8)]" in line            # max over ranks, total pairs, disjoint frame ranges
     shard = [l for l in out.stdout.splitlines() if l.startswith("SHARD")][0]
     assert "[0, 1] [64, 64] [(0, 62500), (62500, 125001)]" in shard
+
+
+def _elimination_game(n, off, order):
+    """Independent symbolic Cholesky: eliminate in `order`, connecting the remaining neighbours of every pivot."""
+    pos = np.empty(n, np.int64)
+    pos[order] = np.arange(n)
+    adj = [set() for _ in range(n)]
+    for a, b in off:
+        adj[a].add(b); adj[b].add(a)
+    nnz = n
+    for p in order:
+        later = [v for v in adj[p] if pos[v] > pos[p]]
+        nnz += len(later)
+        for v in later:
+            adj[v].discard(p)
+            adj[v].update(u for u in later if u != v)
+    return nnz
+
+
+def test_direct_solver_symbolic_analysis_on_the_host():
+    """lvs_pgo_chol_analyze (minimum-degree ordering, elimination tree, supernodes) needs no device: the fill it reports is the
+    fill of an independent elimination game under its ordering, and it beats the natural ordering on the sphere graph."""
+    from lv_slam_b200.graph_slam import chol_analyze
+    from lv_slam_b200.synth import posegraph as G
+    g = G.sphere(20, 10, seed=7)
+    n = len(g["poses7"])
+    off = np.array(sorted({(min(a, b), max(a, b)) for a, b in np.asarray(g["ij"]) if a != b}), np.int32)
+    st, perm = chol_analyze(n, off)
+    assert sorted(perm.tolist()) == list(range(n))
+    assert st["nnz_l_blocks"] == _elimination_game(n, off, perm)
+    assert st["nnz_l_blocks"] < _elimination_game(n, off, np.arange(n))
+    assert 1 <= st["levels"] <= st["fronts"] <= n and st["max_front"] % 6 == 1 and st["arena_bytes"] > 0
+    # a chain (pure odometry) has no fill at all, and an empty pattern is n independent 1x1 fronts
+    chain = np.array([(i, i + 1) for i in range(49)], np.int32)
+    st, perm = chol_analyze(50, chain)
+    assert st["nnz_l_blocks"] == 50 + 49
+    st, perm = chol_analyze(7, np.zeros((0, 2), np.int32))
+    assert st["nnz_l_blocks"] == 7 and st["fronts"] == 7 and st["levels"] == 1
+    with pytest.raises(Exception):
+        chol_analyze(5, np.array([(3, 1)], np.int32))     # not (row < col)

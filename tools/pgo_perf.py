@@ -14,6 +14,7 @@ for (npl, laps, cpu) in ((100, 50, True), (250, 200, "--big" in sys.argv)):
         pg = L.PoseGraph(solver)
         t = time.time(); pg.set_graph(g["poses7"], g["ij"], g["meas7"], g["info21"], g["huber"]); ts = time.time() - t
         t = time.time(); st = pg.optimize(1024); to = time.time() - t
+        if solver == 0: print("  direct solver structure:", pg.chol_info())
         print("  GPU %-22s set_graph %.1f ms, optimize wall %.1f ms (device %.1f ms: linearize %.2f ms, solve %.1f ms), iters %d trials %d pcg %d launches %d chi2 %.4g -> %.6g" % (
             name, ts * 1e3, to * 1e3, st["device_ms"], st["linearize_ms"], st["solve_ms"], st["iterations"], st["lm_trials"], st["pcg_iterations"], st["launches"], st["chi2_before"], st["chi2_after"]))
     if cpu:
