@@ -120,6 +120,13 @@ int lvs_ndt_eval_hessian(lvs_ndt_t* h, const double p[6], const float* T16, doub
 /* calculateScore (ndt_omp_impl2.hpp:1007-1040) of T16 * source. */
 int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score);
 
+/* getFitnessScore(max_range) as the loop detector calls it right after align() (include/global_graph/loop_detector.hpp:176,255;
+ * pcl::Registration::getFitnessScore, PCL 1.8 registration.hpp) and InformationMatrixCalculator::calc_fitness_score
+ * (src/global_graph/information_matrix_calculator.cpp:53-87): mean SQUARED distance from every point of T16 * source to its nearest
+ * target point over the correspondences whose squared distance is <= max_range; DBL_MAX when there is none.  T16 NULL = the final
+ * transformation of the last align().  n_correspondences may be NULL. */
+int lvs_ndt_fitness_score(lvs_ndt_t* h, const float* T16, double max_range, double* score, int* n_correspondences);
+
 /* Voxel grid taps.  grid: min_b, max_b, div_b (voxel_grid_covariance_omp_impl.hpp:87-103). */
 int lvs_ndt_get_grid(lvs_ndt_t* h, int32_t min_b[3], int32_t max_b[3], int32_t div_b[3]);
 int lvs_ndt_num_cells(lvs_ndt_t* h, int* n_cells);   /* every occupied cell, i.e. leaves_.size() */
@@ -166,6 +173,9 @@ int lvs_ndt_batch_total_launches(lvs_ndt_batch_t* b, long long* launches);
 /* Bytes this object has copied host->device and device->host since creation (clouds, pair states, results). */
 int lvs_ndt_batch_transfer_bytes(lvs_ndt_batch_t* b, long long* h2d, long long* d2h);
 int lvs_ndt_batch_num_cells(lvs_ndt_batch_t* b, int target_slot, int* n_cells, int* n_valid);
+/* lvs_ndt_fitness_score for a (source slot, target slot) pair of a batch object (loop-closure candidates). */
+int lvs_ndt_batch_fitness_score(lvs_ndt_batch_t* b, int source_slot, int target_slot, const float T16[16], double max_range, double* score,
+                                int* n_correspondences);
 /* ---- point-sharded evaluation across the GPUs of one node (one process per GPU) ----
  * The sum over source points of computeDerivatives (ndt_omp_impl2.hpp:197-305) is split over `world` ranks: every rank is given
  * the same targets, sources, pairs and guesses; it keeps the contiguous chunk [rank*n/world, (rank+1)*n/world) of every source and

@@ -4,3 +4,4 @@ is the shared library ``liblvslam_b200.so`` built from ``csrc/``."""
 from ._capi import (LVS_DIRECT1, LVS_DIRECT7, LVS_DIRECT26, LVS_KDTREE, LVS_NDT_OMP, LVS_NDT_PCA, LvsError, lib)  # noqa: F401
 from .ndt import NdtBatch, NormalDistributionsTransform  # noqa: F401
 from .graph_slam import GraphSLAM, PoseGraph  # noqa: F401,E402
+from .information_matrix import InformationMatrixCalculator  # noqa: F401,E402

@@ -131,6 +131,9 @@ struct lvs_ndt_batch {
   GridParams* h_gp_all = nullptr;   // pinned, one per target slot: batched geometry read-back
   float* d_T16 = nullptr;        // scratch 16 floats
   double *d_scalar = nullptr, *h_scalar = nullptr;
+  // fitness score scratch (ndt_fitness.cu): best squared distance per source point, undecided list, CTA partials
+  float* d_fit_best = nullptr; int* d_fit_list = nullptr; double* d_fit_partials = nullptr; unsigned int* d_fit_ticket = nullptr;
+  size_t fit_cap = 0;
   int trace_on = 0;
   int last_n_pairs = 0;
   // stats
@@ -764,6 +767,10 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   if (b->d_done) cudaFree(b->d_done);
   if (b->d_T16) cudaFree(b->d_T16);
   if (b->d_scalar) cudaFree(b->d_scalar);
+  if (b->d_fit_best) cudaFree(b->d_fit_best);
+  if (b->d_fit_list) cudaFree(b->d_fit_list);
+  if (b->d_fit_partials) cudaFree(b->d_fit_partials);
+  if (b->d_fit_ticket) cudaFree(b->d_fit_ticket);
   if (b->h_pairs) cudaFreeHost(b->h_pairs);
   if (b->h_states) cudaFreeHost(b->h_states);
   if (b->h_done) cudaFreeHost(b->h_done);
@@ -1054,6 +1061,66 @@ int lvs_ndt_calculate_score(lvs_ndt_t* h, const float T16[16], double* score) {
   CUDA_TRY(cudaStreamSynchronize(b->st));
   *score = b->h_scalar[0];
   return LVS_OK;
+}
+
+// getFitnessScore of the pair (source slot, target slot) of a batch object under T16.
+static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const float* T16, double max_range, double* score, int* n_corr) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  if (tgt_slot < 0 || tgt_slot >= (int)b->targets.size() || src_slot < 0 || src_slot >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "slot out of range");
+  if (!b->target_pts[tgt_slot].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
+  if (!b->sources[src_slot].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
+  if (b->shard_on) return fail(LVS_ERR_INVALID_ARG, "getFitnessScore is not available on a point-sharded object");
+  if ((rc = wait_all_uploads(b))) return rc;
+  if ((rc = finish_target(b, tgt_slot))) return rc;
+  const CloudSlot& src = b->sources[src_slot];
+  const TargetGrid& tg = b->targets[tgt_slot];
+  if ((size_t)src.n + 1 > b->fit_cap) {
+    if (b->d_fit_best) cudaFree(b->d_fit_best);
+    if (b->d_fit_list) cudaFree(b->d_fit_list);
+    b->d_fit_best = nullptr; b->d_fit_list = nullptr; b->fit_cap = 0;
+    const size_t cap = (size_t)src.n + src.n / 8 + 64;
+    CUDA_TRY(cudaMalloc(&b->d_fit_best, cap * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b->d_fit_list, (cap + 1) * sizeof(int)));
+    b->fit_cap = cap;
+  }
+  if (!b->d_fit_partials) {
+    CUDA_TRY(cudaMalloc(&b->d_fit_partials, 2 * 64 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&b->d_fit_ticket, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(b->d_fit_ticket, 0, sizeof(unsigned int), b->st));
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->d_T16, T16, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st));
+  FitnessArgs a;
+  a.src = src.d_pts; a.n_src = src.n;
+  a.tgt = b->target_pts[tgt_slot].d_pts; a.n_tgt = b->target_pts[tgt_slot].n;
+  a.grid = tg.d_grid; a.gp = tg.d_gp; a.cell_start = tg.d_cell_start; a.sorted_idx = tg.d_sorted_idx;
+  a.T16 = b->d_T16; a.max_range = max_range;
+  a.best = b->d_fit_best; a.list = b->d_fit_list; a.partials = b->d_fit_partials; a.ticket = b->d_fit_ticket; a.out = b->d_scalar;
+  int launches = 0;
+  if ((rc = launch_fitness(b->st, a, &launches))) return rc;
+  b->total_launches += launches;
+  CUDA_TRY(cudaMemcpyAsync(b->h_scalar, b->d_scalar, 2 * sizeof(double), cudaMemcpyDeviceToHost, b->st));
+  b->d2h_bytes += 2 * sizeof(double);
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  if (score) *score = b->h_scalar[0];
+  if (n_corr) *n_corr = (int)b->h_scalar[1];
+  return LVS_OK;
+}
+
+int lvs_ndt_fitness_score(lvs_ndt_t* h, const float* T16, double max_range, double* score, int* n_correspondences) {
+  if (!h || !score) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  lvs_ndt_batch* b = h->b;
+  if (!T16) {
+    if (b->last_n_pairs < 1) return fail(LVS_ERR_INVALID_ARG, "align() has not run and no transformation was given");
+    T16 = b->h_states[0].final_T;
+  }
+  return fitness_score(b, 0, 0, T16, max_range, score, n_correspondences);
+}
+
+int lvs_ndt_batch_fitness_score(lvs_ndt_batch_t* b, int source_slot, int target_slot, const float T16[16], double max_range, double* score,
+                                int* n_correspondences) {
+  if (!b || !T16 || !score) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  return fitness_score(b, source_slot, target_slot, T16, max_range, score, n_correspondences);
 }
 
 int lvs_ndt_get_grid(lvs_ndt_t* h, int32_t min_b[3], int32_t max_b[3], int32_t div_b[3]) {

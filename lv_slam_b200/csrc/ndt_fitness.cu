@@ -1,0 +1,137 @@
+// Nearest-neighbour fitness score on the device — replaces pcl::Registration::getFitnessScore(max_range) as the loop detector
+// calls it right after align() (include/global_graph/loop_detector.hpp:176, 255) and
+// lv_slam::InformationMatrixCalculator::calc_fitness_score (src/global_graph/information_matrix_calculator.cpp:53-87):
+//   transform the source by the final transformation (pcl::transformPointCloud, float), find for every point its nearest TARGET
+//   POINT (pcl::search::KdTree / FLANN L2_Simple: ((dx*dx + dy*dy) + dz*dz) in float), keep the squared distances that are
+//   <= max_range (the reference compares the SQUARED distance with max_range), return their mean in double, or DBL_MAX when
+//   there is no correspondence.
+// The kd-tree is replaced by the voxel structure the target already has: the dense index grid, and the target points grouped by
+// cell (TargetGrid::d_sorted_idx / d_cell_start).  A query scans the 27 cells around its own cell, then the shells of radius 2
+// and 3; the best distance found is exact as soon as it is below the distance to the outside of the scanned block.  The few
+// queries that stay undecided (far from every target point) are finished by a brute-force pass, one warp per query.  The float
+// distances are bit-identical to the CPU path; the double sum is a fixed-shape reduction (run-to-run deterministic).
+#include <cfloat>
+#include "ndt_eval_common.cuh"
+
+namespace lvs {
+
+constexpr int kFitThreads = 256;
+constexpr int kFitMaxRing = 3;
+
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, const float4& p) {
+  const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+  return (dx * dx + dy * dy) + dz * dz;
+}
+
+__global__ void __launch_bounds__(kFitThreads) fitness_search_kernel(FitnessArgs a) {
+  const int i = blockIdx.x * kFitThreads + threadIdx.x;
+  if (i >= a.n_src) return;
+  const GridParams* gp = a.gp;
+  const float4 s = a.src[i];
+  float qx, qy, qz;
+  transform_point(a.T16, s.x, s.y, s.z, qx, qy, qz);
+  if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) { a.best[i] = -2.0f; return; }   // no neighbour: dropped from the mean
+  float best = INFINITY;
+  bool decided = false;
+  if (gp->status == 0 && gp->n_cells > 0) {
+    const float inv = gp->inv_leaf, leaf = gp->leaf;
+    // the query's cell with the arithmetic the target points were binned with (key_kernel): one monotone map for both
+    const int cx = (int)floorf(qx * inv) - gp->min_b[0], cy = (int)floorf(qy * inv) - gp->min_b[1], cz = (int)floorf(qz * inv) - gp->min_b[2];
+    const int d0 = gp->div_b[0], d1 = gp->div_b[1], d2 = gp->div_b[2];
+    const int m1 = gp->mul[1], m2 = gp->mul[2];
+    for (int r = 1; r <= kFitMaxRing && !decided; r++) {
+      for (int oz = -r; oz <= r; oz++) {
+        const int z = cz + oz;
+        if ((unsigned)z >= (unsigned)d2) continue;
+        for (int oy = -r; oy <= r; oy++) {
+          const int y = cy + oy;
+          if ((unsigned)y >= (unsigned)d1) continue;
+          const bool face = (oz == -r || oz == r || oy == -r || oy == r);
+          // inside the shell only the two end cells of the x run are new; on a face the whole run is
+          const int step = (face || r == 1) ? 1 : 2 * r;
+          for (int ox = -r; ox <= r; ox += step) {
+            const int x = cx + ox;
+            if ((unsigned)x >= (unsigned)d0) continue;
+            const int v = __ldg(a.grid + (x + y * m1 + z * m2));
+            if (v == -1) continue;
+            const int rec = grid_decode_any(v);
+            const int k0 = __ldg(a.cell_start + rec), k1 = __ldg(a.cell_start + rec + 1);
+            for (int k = k0; k < k1; k++) best = fminf(best, dist2(qx, qy, qz, __ldg(a.tgt + __ldg(a.sorted_idx + k))));
+          }
+        }
+      }
+      // every target point outside the (2r+1)^3 block is at least r cells away (minus the rounding of the binning)
+      const float safe = (float)r * leaf * 0.999f;
+      decided = best <= safe * safe;
+    }
+  }
+  if (decided) a.best[i] = best;
+  else {
+    a.best[i] = -1.0f;
+    a.list[1 + atomicAdd(a.list, 1)] = i;
+  }
+}
+
+// Undecided queries: exact scan of every target point, one warp per query.
+__global__ void __launch_bounds__(kFitThreads) fitness_brute_kernel(FitnessArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kFitThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kFitThreads) >> 5;
+  const int n_list = a.list[0];
+  for (int w = warp; w < n_list; w += n_warps) {
+    const int i = a.list[1 + w];
+    const float4 s = a.src[i];
+    float qx, qy, qz;
+    transform_point(a.T16, s.x, s.y, s.z, qx, qy, qz);
+    float best = INFINITY;
+    for (int k = lane; k < a.n_tgt; k += 32) {
+      const float4 p = __ldg(a.tgt + k);
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) best = fminf(best, dist2(qx, qy, qz, p));
+    }
+    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) a.best[i] = isfinite(best) ? best : -2.0f;
+  }
+}
+
+// sum and count of the accepted squared distances, fixed shape: CTA partials, the last CTA adds them in order
+__global__ void __launch_bounds__(kFitThreads) fitness_reduce_kernel(FitnessArgs a) {
+  __shared__ double s_sum[kFitThreads / 32], s_cnt[kFitThreads / 32];
+  __shared__ bool s_last;
+  double sum = 0.0, cnt = 0.0;
+  for (int i = blockIdx.x * kFitThreads + threadIdx.x; i < a.n_src; i += gridDim.x * kFitThreads) {
+    const float d = a.best[i];
+    if (d >= 0.0f && (double)d <= a.max_range) { sum += (double)d; cnt += 1.0; }
+  }
+  for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sum = 0.0; cnt = 0.0;
+    for (int w = 0; w < kFitThreads / 32; w++) { sum += s_sum[w]; cnt += s_cnt[w]; }
+    a.partials[2 * blockIdx.x] = sum; a.partials[2 * blockIdx.x + 1] = cnt;
+    __threadfence();
+    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  sum = 0.0; cnt = 0.0;
+  for (unsigned b = 0; b < gridDim.x; b++) { sum += __ldcg(a.partials + 2 * b); cnt += __ldcg(a.partials + 2 * b + 1); }
+  a.out[0] = cnt > 0.0 ? sum / cnt : DBL_MAX;
+  a.out[1] = cnt;
+  *a.ticket = 0;
+}
+
+int launch_fitness(cudaStream_t st, const FitnessArgs& a, int* launches) {
+  CUDA_TRY(cudaMemsetAsync(a.list, 0, sizeof(int), st));
+  if (a.n_src > 0) {
+    fitness_search_kernel<<<(a.n_src + kFitThreads - 1) / kFitThreads, kFitThreads, 0, st>>>(a);
+    fitness_brute_kernel<<<148 * 4, kFitThreads, 0, st>>>(a);
+  }
+  const int nb = std::max(1, std::min(64, (a.n_src + kFitThreads * 8 - 1) / (kFitThreads * 8)));   // partials: 2 doubles per CTA
+  fitness_reduce_kernel<<<nb, kFitThreads, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  if (launches) *launches += a.n_src > 0 ? 3 : 1;
+  return LVS_OK;
+}
+
+}  // namespace lvs

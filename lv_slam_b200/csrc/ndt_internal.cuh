@@ -53,6 +53,8 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   int* d_cell_npts = nullptr;
   double* d_cell_evals = nullptr;
   double* d_icov64 = nullptr;            // [n_cells][9] double inverse covariance
+  int* d_sorted_idx = nullptr;           // target point indices grouped by cell (stable: input order inside a cell), cell_capacity
+  int* d_cell_start = nullptr;           // [n_cells + 1] first position of every cell in d_sorted_idx
   size_t cell_capacity = 0;
   int n_cells = 0;
   int launches_last_build = 0;
@@ -115,5 +117,18 @@ int launch_calc_score(cudaStream_t st, const PairDesc& pair, const float* d_T16,
                       unsigned int* d_ticket, double* d_out);
 int launch_lookup_keys(cudaStream_t st, const PairDesc& pair, const float* d_T16, int* d_keys_out);
 int launch_transform(cudaStream_t st, const float4* d_src, int n, const float* d_T16, float* d_out_xyz);
+
+// Nearest-neighbour fitness score (ndt_fitness.cu): pcl::Registration::getFitnessScore / InformationMatrixCalculator::
+// calc_fitness_score.  d_best [n_src] floats, d_list [n_src + 1] ints and d_out [2] doubles are caller-provided scratch.
+struct FitnessArgs {
+  const float4* src; int n_src;
+  const float4* tgt; int n_tgt;
+  const int* grid; const GridParams* gp;
+  const int* cell_start; const int* sorted_idx;
+  const float* T16;
+  double max_range;
+  float* best; int* list; double* partials; unsigned int* ticket; double* out;   // out[0] = score, out[1] = correspondences
+};
+int launch_fitness(cudaStream_t st, const FitnessArgs& a, int* launches);
 
 }  // namespace lvs

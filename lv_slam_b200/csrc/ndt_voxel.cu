@@ -442,18 +442,24 @@ int TargetGrid::enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch
   const int passes = radix_passes_for((long long)grid_capacity);
   const int nblk = (n + kRsTile - 1) / kRsTile;
   int cur = 0;
+  // the index buffer the LAST pass writes is the target's own d_sorted_idx (kept for the nearest-neighbour queries of the fitness
+  // score), so the sorted order needs no extra copy; the other buffer of the ping-pong is scratch
+  int* idx_buf[2] = {ws.d_idx[0], ws.d_idx[1]};
+  idx_buf[passes & 1] = d_sorted_idx;
+  if (passes == 0) idx_buf[0] = d_sorted_idx;
   for (int p = 0; p < passes; p++) {
     rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], n, p * 8, nblk, ws.d_hist);
     exclusive_scan(st, ws.d_hist, ws.d_hist_scan, 256 * nblk, nullptr, ws.d_tile_tot);
-    rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], ws.d_idx[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], ws.d_idx[cur ^ 1]);
+    rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], p == 0 ? ws.d_idx[0] : idx_buf[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], idx_buf[cur ^ 1]);
     cur ^= 1;
   }
+  int* const sorted = idx_buf[cur];
   head_flag_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], n, ws.d_flags);
   CUDA_TRY(cudaMemsetAsync(ws.d_nseg, 0, 2 * sizeof(int), st));
   exclusive_scan(st, ws.d_flags, ws.d_pos, n, ws.d_nseg, ws.d_tile_tot);
-  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, ws.d_seg_start, ws.d_nseg, ws.d_nvalidpts);
-  leaf_moments_kernel<<<std::min(148 * kMomCtasPerSm, (n + kMomWarps - 1) / kMomWarps), kMomWarps * 32, 0, st>>>(pts, ws.d_idx[cur], ws.d_seg_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
-  leaf_finalize_kernel<<<std::min(148 * 4, (n + 127) / 128), 128, 0, st>>>(ws.d_keys[cur], ws.d_seg_start, ws.d_nseg, ws.d_moments, ws.d_csum, d_recs,
+  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, d_cell_start, ws.d_nseg, ws.d_nvalidpts);
+  leaf_moments_kernel<<<std::min(148 * kMomCtasPerSm, (n + kMomWarps - 1) / kMomWarps), kMomWarps * 32, 0, st>>>(pts, sorted, d_cell_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
+  leaf_finalize_kernel<<<std::min(148 * 4, (n + 127) / 128), 128, 0, st>>>(ws.d_keys[cur], d_cell_start, ws.d_nseg, ws.d_moments, ws.d_csum, d_recs,
                                                                           d_centroids, d_cell_keys, d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp,
                                                                           prm.min_points_per_voxel, prm.min_covar_eigvalue_mult, prm.variant);
   CUDA_TRY(cudaGetLastError());
@@ -495,6 +501,8 @@ int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt
     CUDA_TRY(cudaMalloc(&d_cell_npts, cap * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_cell_evals, cap * 3 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&d_icov64, cap * 9 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_sorted_idx, cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_cell_start, (cap + 2) * sizeof(int)));
     cell_capacity = cap;
   }
   if (!d_grid) {
@@ -557,7 +565,9 @@ void TargetGrid::free_cells() {
   if (d_cell_npts) cudaFree(d_cell_npts);
   if (d_cell_evals) cudaFree(d_cell_evals);
   if (d_icov64) cudaFree(d_icov64);
-  d_icov64 = nullptr;
+  if (d_sorted_idx) cudaFree(d_sorted_idx);
+  if (d_cell_start) cudaFree(d_cell_start);
+  d_icov64 = nullptr; d_sorted_idx = nullptr; d_cell_start = nullptr;
   d_recs = nullptr; d_centroids = nullptr; d_cell_keys = nullptr; d_cell_npts = nullptr; d_cell_evals = nullptr;
   cell_capacity = 0;
 }

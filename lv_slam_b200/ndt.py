@@ -154,6 +154,14 @@ class NormalDistributionsTransform:
             out[k, 14:20] = t.p_after; out[k, 20] = t.trials; out[k, 21] = t.hessian_recomputed
         return out
 
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max, T=None, with_count=False):
+        """pcl::Registration::getFitnessScore(max_range): mean squared nearest-neighbour distance of the aligned source (T = None:
+        the final transformation of the last align) to the target points, over squared distances <= max_range."""
+        s, n = ctypes.c_double(0), ctypes.c_int(0)
+        Tm = _colmajor16(T) if T is not None else None
+        C.check(self._L.lvs_ndt_fitness_score(self._h, Tm.ctypes.data if Tm is not None else None, float(max_range), ctypes.byref(s), ctypes.byref(n)))
+        return (s.value, n.value) if with_count else s.value
+
     def calculateScore(self, T):
         g = _colmajor16(T)
         s = ctypes.c_double(0)
@@ -287,6 +295,13 @@ class NdtBatch:
         return [dict(final=_from_colmajor16(np.frombuffer(res[i].final_transformation, dtype=np.float32)), iterations=int(res[i].iterations),
                      converged=bool(res[i].converged), trans_probability=float(res[i].trans_probability), n_eval=int(res[i].n_eval),
                      n_hess=int(res[i].n_hess), score=float(res[i].score)) for i in range(n)]
+
+    def fitness_score(self, source_slot, target_slot, T, max_range=np.finfo(np.float64).max):
+        """getFitnessScore of one (source, target) pair under T -> (score, correspondences)"""
+        s, n = ctypes.c_double(0), ctypes.c_int(0)
+        Tm = _colmajor16(T)
+        C.check(self._L.lvs_ndt_batch_fitness_score(self._h, int(source_slot), int(target_slot), Tm.ctypes.data, float(max_range), ctypes.byref(s), ctypes.byref(n)))
+        return s.value, n.value
 
     def set_profiling(self, on):
         C.check(self._L.lvs_ndt_batch_set_profiling(self._h, int(on)))

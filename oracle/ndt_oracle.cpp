@@ -734,6 +734,35 @@ double ondt_calculate_score(void* h, const float* T16) {
   return calculate_score(n, trans);
 }
 
+// pcl::Registration::getFitnessScore(max_range) (PCL 1.8 registration/impl/registration.hpp, un-vendored; called at
+// include/global_graph/loop_detector.hpp:176,255) and lv_slam::InformationMatrixCalculator::calc_fitness_score
+// (src/global_graph/information_matrix_calculator.cpp:53-87): transform the source with T16 (pcl::transformPointCloud), nearest
+// target point of every transformed point (kd-tree nearestKSearch, k = 1, FLANN L2_Simple = ((dx*dx + dy*dy) + dz*dz) in float;
+// restated as an exhaustive scan, which returns the same minimum), squared distances <= max_range are summed in double in point
+// order; mean, or DBL_MAX without a correspondence.  Non-finite points are skipped on both sides.
+double ondt_fitness_score(void* h, const float* T16, double max_range, int* n_corr) {
+  NDT& n = *(NDT*)h;
+  std::vector<Pt> trans; transform_cloud(n.input, trans, T16, n.num_threads);
+  std::vector<float> best(trans.size(), -1.0f);
+#pragma omp parallel for num_threads(n.num_threads) schedule(static)
+  for (long i = 0; i < (long)trans.size(); i++) {
+    const Pt& q = trans[i];
+    if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
+    float b = INFINITY;
+    for (const Pt& t : n.target) {
+      if (!(std::isfinite(t.x) && std::isfinite(t.y) && std::isfinite(t.z))) continue;
+      const float dx = q.x - t.x, dy = q.y - t.y, dz = q.z - t.z;
+      const float d = (dx * dx + dy * dy) + dz * dz;
+      if (d < b) b = d;
+    }
+    if (std::isfinite(b)) best[i] = b;
+  }
+  double sum = 0; int nr = 0;
+  for (float b : best) if (b >= 0.0f && (double)b <= max_range) { sum += (double)b; nr++; }
+  if (n_corr) *n_corr = nr;
+  return nr > 0 ? sum / nr : std::numeric_limits<double>::max();
+}
+
 // align(): returns nr_iterations.  out_final16 column-major.  stats = {converged, trans_probability, n_eval, n_hess}
 int ondt_align(void* h, const float* guess16, float* out_final16, double* stats4, float* out_cloud_xyz /*nullable, packed*/) {
   NDT& n = *(NDT*)h;

@@ -45,6 +45,7 @@ def lib():
         L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
         L.ondt_eval_hessian.restype = None; L.ondt_eval_hessian.argtypes = [vp, vp, vp, vp]
         L.ondt_calculate_score.restype = f64; L.ondt_calculate_score.argtypes = [vp, vp]
+        L.ondt_fitness_score.restype = f64; L.ondt_fitness_score.argtypes = [vp, vp, f64, vp]
         L.ondt_align.restype = i32; L.ondt_align.argtypes = [vp, vp, vp, vp, vp]
         L.ondt_trace_len.restype = i32; L.ondt_trace_len.argtypes = [vp]
         L.ondt_get_trace.restype = None; L.ondt_get_trace.argtypes = [vp, vp]
@@ -151,6 +152,12 @@ class OracleNDT:
     def calculate_score(self, T):
         Tm = _colmajor16(T)
         return self.L.ondt_calculate_score(self.h, Tm.ctypes.data)
+
+    def fitness_score(self, T, max_range=np.finfo(np.float64).max):
+        """getFitnessScore(max_range) of T * source against the target points -> (score, correspondences)"""
+        Tm = _colmajor16(T)
+        n = ctypes.c_int(0)
+        return self.L.ondt_fitness_score(self.h, Tm.ctypes.data, float(max_range), ctypes.byref(n)), n.value
 
     def align(self, guess=None, want_cloud=False):
         g = _colmajor16(np.eye(4) if guess is None else guess)

@@ -362,3 +362,84 @@ def test_point_sharding_self_exchange(small_pair):
     r = o.align(guess)
     assert n.getFinalNumIteration() == r["iterations"]
     assert np.max(np.abs(n.getFinalTransformation() - r["final"])) <= 1e-6
+
+
+def _shift(T, dx, dy=0.0, dz=0.0):
+    S = np.array(T, dtype=np.float64).copy()
+    S[:3, 3] += (dx, dy, dz)
+    return S.astype(np.float32)
+
+
+def test_fitness_score_matches_oracle(small_pair):
+    """getFitnessScore (loop_detector.hpp:176,255) / calc_fitness_score (information_matrix_calculator.cpp:53-87): the float
+    nearest-neighbour distances are bit-identical to the exhaustive CPU scan, so the correspondence COUNT is exact for any
+    max_range and the mean agrees to the order of the fp64 summation (1e-12 relative)."""
+    tgt, src, guess, truth = small_pair
+    n, o = _mk(O.VAR_OMP, O.DIRECT7)
+    n.setInputTarget(tgt); n.setInputSource(src)
+    o.set_target(tgt); o.set_source(src)
+    big = np.finfo(np.float64).max
+    cases = [(truth, big), (guess, big), (guess, 0.25), (truth, 0.01), (_shift(truth, 0.0, 0.0, 7.5), big),      # 7.5 m above: ring search gives up
+             (_shift(truth, 400.0, -300.0, 0.0), big), (_shift(truth, 400.0), 1.0)]                               # far outside the grid: brute force
+    for T, mr in cases:
+        gs, gn = n.getFitnessScore(mr, T=T, with_count=True)
+        os_, on = o.fitness_score(T, mr)
+        assert gn == on, (gn, on, mr)
+        if on == 0:
+            assert gs == big and os_ == big
+        else:
+            assert abs(gs - os_) <= 1e-12 * os_, (gs, os_)
+    # T = None: the final transformation of the last align
+    n.align(guess)
+    o.align(guess)
+    fin = n.getFinalTransformation()
+    assert n.getFitnessScore(0.5) == n.getFitnessScore(0.5, T=fin)
+    assert abs(n.getFitnessScore(0.5) - o.fitness_score(fin, 0.5)[0]) <= 1e-12 * o.fitness_score(fin, 0.5)[0]
+    # non-finite source points have no neighbour and drop out of the mean; an empty source has no correspondence at all
+    s2 = src.copy(); s2[::7, 1] = np.nan
+    n.setInputSource(s2); o.set_source(s2)
+    gs, gn = n.getFitnessScore(big, T=truth, with_count=True)
+    os_, on = o.fitness_score(truth, big)
+    assert gn == on == int(np.isfinite(s2[:, :3]).all(axis=1).sum()) and abs(gs - os_) <= 1e-12 * os_
+    n.setInputSource(np.zeros((0, 3), np.float32))
+    assert n.getFitnessScore(big, T=truth, with_count=True) == (big, 0)
+
+
+def test_fitness_score_full_scan_properties(scan_pair):
+    """At BASELINE's full size the exhaustive oracle is too slow; size-independent properties instead."""
+    tgt, src, guess, truth = scan_pair
+    n, _ = _mk(O.VAR_OMP, O.DIRECT7)
+    n.setInputTarget(tgt); n.setInputSource(tgt)
+    big = np.finfo(np.float64).max
+    assert n.getFitnessScore(big, T=np.eye(4, dtype=np.float32), with_count=True) == (0.0, int(np.isfinite(tgt[:, :3]).all(axis=1).sum()))   # a cloud against itself
+    n.setInputSource(src)
+    s_truth, c_truth = n.getFitnessScore(big, T=truth, with_count=True)
+    s_guess, c_guess = n.getFitnessScore(big, T=guess, with_count=True)
+    assert c_truth == c_guess == len(src) and s_truth < s_guess
+    # the count is monotone in max_range and the capped mean never exceeds the cap
+    prev = 0
+    for mr in (1e-4, 1e-2, 0.25, 4.0, big):
+        s, c = n.getFitnessScore(mr, T=truth, with_count=True)
+        assert c >= prev and (c == 0 or s <= mr)
+        prev = c
+    # batch entry point: same numbers as the single-object one
+    import lv_slam_b200 as L
+    b = L.NdtBatch(1, 1)
+    b.set_target(0, tgt); b.set_source(0, src)
+    assert b.fitness_score(0, 0, truth, 0.25) == n.getFitnessScore(0.25, T=truth, with_count=True)
+
+
+def test_information_matrix_calculator_mirror(small_pair):
+    """InformationMatrixCalculator (information_matrix_calculator.cpp:27-51): constant matrix, and the fitness-weighted one."""
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    c = L.InformationMatrixCalculator(use_const_inf_matrix=True, const_stddev_x=0.5, const_stddev_q=0.1)
+    assert np.array_equal(c.calc_information_matrix(tgt, src, truth), np.diag([2.0, 2, 2, 10, 10, 10]))     # dlo_lfa_ggo_kitti.launch:134-136
+    c = L.InformationMatrixCalculator(fitness_score_thresh=2.5)
+    o = O.OracleNDT(num_threads=8); o.set_target(tgt); o.set_source(src)
+    fs = o.fitness_score(truth)[0]
+    wx = np.float32(0.1 ** 2 + (5.0 ** 2 - 0.1 ** 2) * (1 - np.exp(-20.0 * fs)) / (1 - np.exp(-20.0 * 2.5)))
+    wq = np.float32(0.05 ** 2 + (0.2 ** 2 - 0.05 ** 2) * (1 - np.exp(-20.0 * fs)) / (1 - np.exp(-20.0 * 2.5)))
+    inf = c.calc_information_matrix(tgt, src, truth)
+    np.testing.assert_allclose(np.diag(inf), [1 / wx] * 3 + [1 / wq] * 3, rtol=1e-6)
+    assert np.count_nonzero(inf - np.diag(np.diag(inf))) == 0

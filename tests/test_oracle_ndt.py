@@ -193,3 +193,27 @@ def test_golden_regression_of_the_oracle(small_pair):
     r = o.align(guess)
     assert r["iterations"] == gold["iterations"]
     np.testing.assert_allclose(r["final"], np.array(gold["final"], dtype=np.float32), atol=1e-6)
+
+
+def test_fitness_score_known_answers():
+    """getFitnessScore restatement on a hand case: squared nearest-neighbour distances, capped by max_range, mean in double."""
+    tgt = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0], [np.nan, 0, 0]], np.float32)
+    src = np.array([[0.1, 0, 0], [0.9, 0.1, 0], [5, 5, 5], [0, np.inf, 0]], np.float32)
+    o = O.OracleNDT()
+    o.set_target(tgt); o.set_source(src)
+    I = np.eye(4, dtype=np.float32)
+    d = [np.float32(0.1) ** 2, np.float32(np.float32(0.1) ** 2 + np.float32(0.1) ** 2)]
+    d0 = np.float32(np.float32(0.1) * np.float32(0.1))
+    d1 = np.float32(np.float32(np.float32(0.9) - np.float32(1.0)) ** 2 + np.float32(0.1) * np.float32(0.1))
+    d2 = np.float32(25 + 9 + 25)
+    s, n = o.fitness_score(I)
+    assert n == 3 and abs(s - (float(d0) + float(d1) + float(d2)) / 3) < 1e-15 * s      # the non-finite source point is skipped
+    s, n = o.fitness_score(I, 1.0)
+    assert n == 2 and s == (float(d0) + float(d1)) / 2
+    s, n = o.fitness_score(I, 1e-6)
+    assert n == 0 and s == np.finfo(np.float64).max
+    T = I.copy(); T[0, 3] = -0.1                                                      # moves the first point onto a target point
+    s, n = o.fitness_score(T, 0.5)
+    x1 = np.float32(np.float32(0.9) + np.float32(-0.1))
+    e1 = np.float32(np.float32(x1 - np.float32(1.0)) ** 2 + np.float32(0.1) * np.float32(0.1))
+    assert n == 2 and s == (0.0 + float(e1)) / 2
