@@ -190,6 +190,22 @@ int lvs_ndt_batch_shard_connect(lvs_ndt_batch_t* b, const unsigned char* handles
 int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out);
 
 /* ===================================================================================================================
+ * Scan prefilter — the stage right before the NDT path: PrefilteringNodelet::distance_filter + downsample()
+ * (src/lidar_odometry/prefiltering_nodelet.cpp:164-181, 138-148; pcl::VoxelGrid with downsample_resolution, launch/
+ * dlo_lfa_ggo_kitti.launch:30-36).  Points are n_fields (3 = x y z, 4 = x y z intensity) floats, stride_bytes apart (32 for
+ * pcl::PointXYZI); the result is packed n_fields floats per point, at most `capacity` points.
+ *   use_distance_filter != 0: keep a point when its float norm d satisfies d > distance_near && d < distance_far (order kept);
+ *   leaf_size > 0: pcl::VoxelGrid — one output point per occupied leaf in ascending leaf index, the float mean of its points;
+ *                  flags bit 0 is set when PCL's "leaf size is too small" overflow guard fires and the cloud is passed through.
+ */
+typedef struct lvs_prefilter lvs_prefilter_t;
+int lvs_prefilter_create(int device, void* stream, lvs_prefilter_t** out);
+int lvs_prefilter_destroy(lvs_prefilter_t* p);
+int lvs_prefilter_run(lvs_prefilter_t* p, const float* xyz, size_t n, size_t stride_bytes, int n_fields, int on_device, double distance_near,
+                      double distance_far, int use_distance_filter, float leaf_size, float* out, size_t capacity, int out_on_device, size_t* n_out,
+                      int* flags_out);
+
+/* ===================================================================================================================
  * Pose graph — replaces lv_slam::GraphSLAM::optimize (src/global_graph/graph_slam.cpp:298-331) and the g2o machinery under
  * it for graphs of VertexSE3 / EdgeSE3 with optional Huber kernels (what global_graph builds with GPS/IMU/floor disabled,
  * launch/dlo_lfa_ggo_kitti.launch:8-11).

@@ -71,6 +71,12 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   void release();
 };
 
+// voxel-index machinery shared by the NDT target build and the prefilter's VoxelGrid (ndt_voxel.cu)
+void vox_bbox(cudaStream_t st, const float4* pts, int n, BuildScratch& ws, GridParams* d_gp, float leaf, long long grid_capacity);
+int vox_radix_passes(long long cells);
+void exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total, int* tile_tot);   // two-level exclusive scan
+int vox_sort_segments(cudaStream_t st, const float4* pts, int n, const GridParams* d_gp, int passes, BuildScratch& ws, int* sorted_out, int* cell_start_out);
+
 int pack_points(cudaStream_t st, const float* d_in, size_t stride_floats, int n, float4* d_out);
 // Repack of up to kPackMany resident clouds in one launch (descriptors travel as kernel parameters).
 constexpr int kPackMany = 96;

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict_
   if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = off + tile_tot[blockIdx.x];
 }
 
-static void exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total, int* tile_tot) {
+void exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total, int* tile_tot) {
   const int nb = (n + kScanTile - 1) / kScanTile;
   scan_tiles_kernel<<<nb, kScanThreads, 0, st>>>(in, out, n, tile_tot);
   scan_add_kernel<<<nb, kScanThreads, 0, st>>>(out, n, tile_tot, total);
@@ -431,33 +431,51 @@ static int radix_passes_for(long long cells) {   // keys < cells, invalid keys 0
   return (bits + 7) / 8;
 }
 
-// Queues the whole voxelisation on `st`.  Needs d_grid to exist; never synchronises.
-int TargetGrid::enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch& ws) {
-  const int n = n_points;
+// Bounding box and grid geometry of a cloud (getMinMax3D + the min_b / max_b / div_b arithmetic) into *d_gp.
+void vox_bbox(cudaStream_t st, const float4* pts, int n, BuildScratch& ws, GridParams* d_gp, float leaf, long long grid_capacity) {
+  bbox_kernel<<<std::max(1, std::min(kBboxBlocks, (n + 255) / 256)), 256, 0, st>>>(pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, leaf, grid_capacity);
+}
+
+int vox_radix_passes(long long cells) { return radix_passes_for(cells); }
+
+// Voxel key of every point, stable sort of the point indices by key, one segment per occupied cell: sorted_out [n] receives the
+// point indices grouped by cell in ascending key order (input order inside a cell), cell_start_out [cells + 1] the segment
+// starts, ws.d_nseg the number of cells; the sorted keys are left in ws.d_keys[passes & 1].
+int vox_sort_segments(cudaStream_t st, const float4* pts, int n, const GridParams* d_gp, int passes, BuildScratch& ws, int* sorted_out,
+                      int* cell_start_out) {
   const int tb = 256, gb = (n + tb - 1) / tb;
-  // wipe the cells of the previous build while the old keys and the old geometry still describe this buffer
-  if (prev_points > 0) clear_cells_kernel<<<(prev_points + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, d_gp);
-  bbox_kernel<<<std::min(kBboxBlocks, gb), 256, 0, st>>>(pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, prm.resolution, (long long)grid_capacity);
   key_kernel<<<gb, tb, 0, st>>>(pts, n, d_gp, ws.d_keys[0], ws.d_idx[0]);
-  const int passes = radix_passes_for((long long)grid_capacity);
   const int nblk = (n + kRsTile - 1) / kRsTile;
   int cur = 0;
-  // the index buffer the LAST pass writes is the target's own d_sorted_idx (kept for the nearest-neighbour queries of the fitness
-  // score), so the sorted order needs no extra copy; the other buffer of the ping-pong is scratch
+  // the index buffer the LAST pass writes is the caller's sorted_out, so the sorted order needs no extra copy; the other buffer of
+  // the ping-pong is scratch
   int* idx_buf[2] = {ws.d_idx[0], ws.d_idx[1]};
-  idx_buf[passes & 1] = d_sorted_idx;
-  if (passes == 0) idx_buf[0] = d_sorted_idx;
+  idx_buf[passes & 1] = sorted_out;
   for (int p = 0; p < passes; p++) {
     rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], n, p * 8, nblk, ws.d_hist);
     exclusive_scan(st, ws.d_hist, ws.d_hist_scan, 256 * nblk, nullptr, ws.d_tile_tot);
     rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], p == 0 ? ws.d_idx[0] : idx_buf[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], idx_buf[cur ^ 1]);
     cur ^= 1;
   }
-  int* const sorted = idx_buf[cur];
   head_flag_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], n, ws.d_flags);
   CUDA_TRY(cudaMemsetAsync(ws.d_nseg, 0, 2 * sizeof(int), st));
   exclusive_scan(st, ws.d_flags, ws.d_pos, n, ws.d_nseg, ws.d_tile_tot);
-  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, d_cell_start, ws.d_nseg, ws.d_nvalidpts);
+  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, cell_start_out, ws.d_nseg, ws.d_nvalidpts);
+  CUDA_TRY(cudaGetLastError());
+  return LVS_OK;
+}
+
+// Queues the whole voxelisation on `st`.  Needs d_grid to exist; never synchronises.
+int TargetGrid::enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch& ws) {
+  const int n = n_points;
+  // wipe the cells of the previous build while the old keys and the old geometry still describe this buffer
+  if (prev_points > 0) clear_cells_kernel<<<(prev_points + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, d_gp);
+  vox_bbox(st, pts, n, ws, d_gp, prm.resolution, (long long)grid_capacity);
+  const int passes = radix_passes_for((long long)grid_capacity);
+  int rc = vox_sort_segments(st, pts, n, d_gp, passes, ws, d_sorted_idx, d_cell_start);
+  if (rc) return rc;
+  const int cur = passes & 1;
+  int* const sorted = d_sorted_idx;
   leaf_moments_kernel<<<std::min(148 * kMomCtasPerSm, (n + kMomWarps - 1) / kMomWarps), kMomWarps * 32, 0, st>>>(pts, sorted, d_cell_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
   leaf_finalize_kernel<<<std::min(148 * 4, (n + 127) / 128), 128, 0, st>>>(ws.d_keys[cur], d_cell_start, ws.d_nseg, ws.d_moments, ws.d_csum, d_recs,
                                                                           d_centroids, d_cell_keys, d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp,

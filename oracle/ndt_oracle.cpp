@@ -763,6 +763,71 @@ double ondt_fitness_score(void* h, const float* T16, double max_range, int* n_co
   return nr > 0 ? sum / nr : std::numeric_limits<double>::max();
 }
 
+// PrefilteringNodelet: distance_filter (src/lidar_odometry/prefiltering_nodelet.cpp:164-181) then downsample() = pcl::VoxelGrid
+// (:41-47, 138-148).  pcl::VoxelGrid::applyFilter is un-vendored (PCL 1.8 filters/impl/voxel_grid.hpp); restated: bounding box of
+// the finite points, min_b / max_b = floor(p * inverse_leaf), overflow guard dx*dy*dz > INT32_MAX (output = input), leaf index
+// ijk . divb_mul with ijk = int(floor(x * inverse_leaf) - float(min_b)), points grouped by index (PCL: unstable std::sort on the
+// index; here stable, i.e. input order inside a leaf), one point per leaf in ascending index = float sums / float(count)
+// (downsample_all_data_ = true: the CentroidPoint accumulators average intensity as well).
+// in: npts points of n_fields floats, stride_floats apart; out: packed n_fields floats.  Returns the number of output points;
+// *flags bit 0 = overflow guard fired.
+size_t oprefilter(const float* xyz, size_t npts, size_t stride_floats, int n_fields, double near_t, double far_t, int use_filter, float leaf,
+                  float* out, int* flags) {
+  struct P4 { float x, y, z, w; };
+  std::vector<P4> kept;
+  kept.reserve(npts);
+  if (flags) *flags = 0;
+  for (size_t i = 0; i < npts; i++) {
+    const float* p = xyz + i * stride_floats;
+    P4 q = {p[0], p[1], p[2], n_fields > 3 ? p[3] : 0.0f};
+    if (use_filter) {
+      const double d = (double)std::sqrt((q.x * q.x + q.y * q.y) + q.z * q.z);      // Eigen Vector3f::norm(), float
+      if (!(d > near_t && d < far_t)) continue;
+    }
+    kept.push_back(q);
+  }
+  auto emit = [&](const std::vector<P4>& v) {
+    for (size_t i = 0; i < v.size(); i++) { out[i * n_fields] = v[i].x; out[i * n_fields + 1] = v[i].y; out[i * n_fields + 2] = v[i].z; if (n_fields > 3) out[i * n_fields + 3] = v[i].w; }
+    return v.size();
+  };
+  if (!(leaf > 0.0f) || kept.empty()) return emit(kept);
+  const float inv = 1.0f / leaf;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool any = false;
+  for (const P4& q : kept) {
+    if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
+    any = true;
+    mn[0] = std::min(mn[0], q.x); mn[1] = std::min(mn[1], q.y); mn[2] = std::min(mn[2], q.z);
+    mx[0] = std::max(mx[0], q.x); mx[1] = std::max(mx[1], q.y); mx[2] = std::max(mx[2], q.z);
+  }
+  if (!any) return 0;
+  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > 2147483647LL) { if (flags) *flags |= 1; return emit(kept); }
+  int min_b[3], max_b[3], div_b[3];
+  for (int a = 0; a < 3; a++) { min_b[a] = (int)std::floor(mn[a] * inv); max_b[a] = (int)std::floor(mx[a] * inv); div_b[a] = max_b[a] - min_b[a] + 1; }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  std::vector<std::pair<int, int>> order;       // (leaf index, point)
+  for (size_t i = 0; i < kept.size(); i++) {
+    const P4& q = kept[i];
+    if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
+    const int i0 = (int)(std::floor(q.x * inv) - (float)min_b[0]), i1 = (int)(std::floor(q.y * inv) - (float)min_b[1]), i2 = (int)(std::floor(q.z * inv) - (float)min_b[2]);
+    order.push_back({i0 * mul[0] + i1 * mul[1] + i2 * mul[2], (int)i});
+  }
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+  size_t n_out = 0;
+  for (size_t k = 0; k < order.size();) {
+    size_t e = k;
+    float sx = 0, sy = 0, sz = 0, sw = 0;
+    while (e < order.size() && order[e].first == order[k].first) { const P4& q = kept[order[e].second]; sx += q.x; sy += q.y; sz += q.z; sw += q.w; e++; }
+    const float fn = (float)(e - k);
+    out[n_out * n_fields] = sx / fn; out[n_out * n_fields + 1] = sy / fn; out[n_out * n_fields + 2] = sz / fn;
+    if (n_fields > 3) out[n_out * n_fields + 3] = sw / fn;
+    n_out++;
+    k = e;
+  }
+  return n_out;
+}
+
 // align(): returns nr_iterations.  out_final16 column-major.  stats = {converged, trans_probability, n_eval, n_hess}
 int ondt_align(void* h, const float* guess16, float* out_final16, double* stats4, float* out_cloud_xyz /*nullable, packed*/) {
   NDT& n = *(NDT*)h;

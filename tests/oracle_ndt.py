@@ -45,6 +45,7 @@ def lib():
         L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
         L.ondt_eval_hessian.restype = None; L.ondt_eval_hessian.argtypes = [vp, vp, vp, vp]
         L.ondt_calculate_score.restype = f64; L.ondt_calculate_score.argtypes = [vp, vp]
+        L.oprefilter.restype = sz; L.oprefilter.argtypes = [vp, sz, sz, i32, f64, f64, i32, f32, vp, vp]
         L.ondt_fitness_score.restype = f64; L.ondt_fitness_score.argtypes = [vp, vp, f64, vp]
         L.ondt_align.restype = i32; L.ondt_align.argtypes = [vp, vp, vp, vp, vp]
         L.ondt_trace_len.restype = i32; L.ondt_trace_len.argtypes = [vp]
@@ -178,6 +179,16 @@ class OracleNDT:
         if n:
             self.L.ondt_get_trace(self.h, t.ctypes.data)
         return t
+
+
+def prefilter(cloud, near=0.5, far=100.0, use_filter=True, leaf=0.1):
+    """distance_filter + pcl::VoxelGrid restatement -> (points [m, n_fields], overflow flag)"""
+    a = _f32(cloud)
+    nf = 4 if a.shape[1] >= 4 else 3
+    out = np.zeros((a.shape[0], nf), np.float32)
+    fl = ctypes.c_int(0)
+    m = lib().oprefilter(a.ctypes.data, a.shape[0], a.shape[1], nf, float(near), float(far), int(bool(use_filter)), float(leaf), out.ctypes.data, ctypes.byref(fl))
+    return out[:m].copy(), fl.value
 
 
 def transform(xyz, T):

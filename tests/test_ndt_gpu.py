@@ -443,3 +443,46 @@ def test_information_matrix_calculator_mirror(small_pair):
     inf = c.calc_information_matrix(tgt, src, truth)
     np.testing.assert_allclose(np.diag(inf), [1 / wx] * 3 + [1 / wq] * 3, rtol=1e-6)
     assert np.count_nonzero(inf - np.diag(np.diag(inf))) == 0
+
+
+def test_prefilter_matches_oracle(scan_pair, small_pair):
+    """PrefilteringNodelet chain (distance filter 0.5-100 m, VoxelGrid 0.1 m; launch/dlo_lfa_ggo_kitti.launch:30-36) on a full 64-beam
+    scan with an intensity column: same points, same order, bit for bit (both sides sum a leaf in input order)."""
+    import lv_slam_b200 as L
+    tgt = scan_pair[0]
+    rng = np.random.default_rng(3)
+    cloud = np.concatenate([tgt[:, :3], rng.random((len(tgt), 1), dtype=np.float32)], axis=1).astype(np.float32)
+    cloud[::997, 2] = np.nan
+    cloud[5::1201, :3] *= 0.001                                  # inside the near threshold
+    pf = L.Prefilter(distance_near_thresh=0.5, distance_far_thresh=100.0, downsample_resolution=0.1)
+    got = pf.filter(cloud)
+    exp, fl = O.prefilter(cloud, 0.5, 100.0, True, 0.1)
+    assert fl == 0 and pf.last_flags == 0
+    assert got.shape == exp.shape and 0.3 * len(cloud) < len(got) < len(cloud)
+    assert np.array_equal(got, exp)
+    # xyz only, a 32-byte PointXYZI stride, other leaf sizes, and no downsampling at all
+    wide = np.zeros((len(cloud), 8), np.float32); wide[:, :3] = cloud[:, :3]
+    for leaf in (0.1, 0.25, 1.0):
+        pf.downsample_resolution = leaf
+        assert np.array_equal(pf.filter(wide[:, :3]), O.prefilter(cloud[:, :3], 0.5, 100.0, True, leaf)[0])
+    pf.downsample_method = "NONE"
+    assert np.array_equal(pf.filter(cloud), O.prefilter(cloud, 0.5, 100.0, True, 0.0)[0])
+    # overflow guard -> pass-through with the flag; empty input; everything filtered away
+    pf.downsample_method, pf.downsample_resolution = "VOXELGRID", 1e-4
+    got = pf.filter(cloud[:, :3])
+    exp, fl = O.prefilter(cloud[:, :3], 0.5, 100.0, True, 1e-4)
+    assert fl == 1 and pf.last_flags == 1 and np.array_equal(got, exp)
+    pf.downsample_resolution = 0.1
+    assert pf.filter(np.zeros((0, 3), np.float32)).shape == (0, 3)
+    pf.distance_far_thresh = 0.6
+    assert len(pf.filter(small_pair[0])) == len(O.prefilter(small_pair[0], 0.5, 0.6, True, 0.1)[0])
+    # device-resident input and output
+    import torch
+    pf.distance_far_thresh = 100.0
+    got = pf.filter(torch.from_numpy(cloud).cuda())
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), O.prefilter(cloud, 0.5, 100.0, True, 0.1)[0])
+    # the filtered scan feeds the registration like the nodelet chain does
+    n, o = _mk(O.VAR_PCA, O.DIRECT1)
+    f_t, f_s = pf.filter(small_pair[0]), pf.filter(small_pair[1])
+    n.setInputTarget(f_t); n.setInputSource(f_s); o.set_target(f_t); o.set_source(f_s)
+    _check_align(n, o, f_s, small_pair[2])

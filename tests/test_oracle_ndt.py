@@ -217,3 +217,29 @@ def test_fitness_score_known_answers():
     x1 = np.float32(np.float32(0.9) + np.float32(-0.1))
     e1 = np.float32(np.float32(x1 - np.float32(1.0)) ** 2 + np.float32(0.1) * np.float32(0.1))
     assert n == 2 and s == (0.0 + float(e1)) / 2
+
+
+def test_prefilter_known_answers():
+    """distance_filter + pcl::VoxelGrid restatement on a hand case (prefiltering_nodelet.cpp:164-181, 138-148)."""
+    pts = np.array([[0.2, 0.0, 0.0, 1.0],      # |p| = 0.2 < near: dropped
+                    [1.02, 0.0, 0.0, 2.0],     # leaf (10, 0, 0) at 0.1 m
+                    [1.04, 0.0, 0.0, 4.0],     # same leaf
+                    [3.0, 4.0, 0.0, 5.0],      # |p| = 5
+                    [60.0, 80.0, 0.0, 7.0],    # |p| = 100: not < far, dropped
+                    [np.nan, 1.0, 1.0, 9.0],   # norm is NaN: dropped
+                    [-1.0, -1.0, 0.5, 3.0]], np.float32)
+    out, fl = O.prefilter(pts, near=0.5, far=100.0, leaf=0.1)
+    assert fl == 0 and out.shape == (3, 4)
+    # ascending leaf index = x fastest, then y, then z (divb_mul = 1, dx, dx*dy): z = 0 leaves before the z = 0.5 one, and within
+    # z = 0 the y = 0 row before y = 4
+    a = np.float32(np.float32(1.02) + np.float32(1.04)) / np.float32(2)
+    assert np.array_equal(out[0], np.array([a, 0, 0, 3.0], np.float32))
+    assert np.array_equal(out[1], pts[3]) and np.array_equal(out[2], pts[6])
+    # no downsampling: the kept points in input order; no distance filter: NaN rows survive the filter and vanish in the grid
+    out, _ = O.prefilter(pts, near=0.5, far=100.0, leaf=0.0)
+    assert np.array_equal(out, pts[[1, 2, 3, 6]])
+    out, _ = O.prefilter(pts, use_filter=False, leaf=0.1)
+    assert out.shape[0] == 5
+    # PCL's overflow guard: 1e-4 m leaves over a 140 m extent do not fit int32 -> the cloud passes through, flag set
+    out, fl = O.prefilter(pts[:, :3], near=0.5, far=1000.0, leaf=1e-4)
+    assert fl == 1 and np.array_equal(out, pts[[1, 2, 3, 4, 6], :3])
