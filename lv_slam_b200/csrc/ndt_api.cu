@@ -107,6 +107,7 @@ struct lvs_ndt_batch {
   // those of the next and the repacking of the scans; the compute stream waits for a grid the first time it is consumed
   BuildLane lanes[kBuildLanes];
   int lane_next = 0;
+  BuildScratch batch_ws[kVoxBatch];   // scratch of the batched voxelisation (set_targets): one per cloud of a launch group, used on lanes[0].st
   cudaEvent_t ev_mark = nullptr;     // position of the compute stream, for resident inputs produced on it
   std::vector<TargetGrid> targets;
   std::vector<TargetBuildState> tstate;
@@ -607,6 +608,54 @@ static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   return LVS_OK;
 }
 
+// Plural setInputTarget: the clouds are uploaded / repacked one by one, then voxelised TOGETHER by one set of batched launches
+// (TargetGrid::enqueue_many) on the first build lane's stream - about 20 launches per group of kVoxBatch clouds instead of 20 per
+// cloud.  A slot that is built for the first time (no index grid yet) sizes its grid inside prepare(), exactly like set_target.
+static int set_targets_many(lvs_ndt_batch* b, int n, const int32_t* slots, const float* const* xyz, const size_t* counts, size_t stride_bytes,
+                            int on_device) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++)
+    if (slots[i] < 0 || slots[i] >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slots[i]);
+  BuildLane& ln = b->lanes[0];
+  for (int base = 0; base < n; base += kVoxBatch) {
+    const int cnt = std::min(kVoxBatch, n - base);
+    TargetGrid* grids[kVoxBatch];
+    BuildScratch* wss[kVoxBatch];
+    int slot_of[kVoxBatch];
+    int m = 0;
+    for (int k = 0; k < cnt; k++) {
+      const int slot = slots[base + k];
+      for (int q = 0; q < m; q++)
+        if (slot_of[q] == slot) return fail(LVS_ERR_INVALID_ARG, "target slot %d appears twice in one set_targets call", slot);
+      CloudSlot& cs = b->target_pts[slot];
+      TargetBuildState& ts = b->tstate[slot];
+      if (ts.built_pending && ts.lane != 0) CUDA_TRY(cudaStreamWaitEvent(ln.st, ts.built, 0));
+      if ((rc = upload_cloud(b, cs, xyz[base + k], counts[base + k], stride_bytes, on_device, ln.st))) return rc;
+      if (cs.ready_pending) { CUDA_TRY(cudaStreamWaitEvent(ln.st, cs.ready, 0)); cs.ready_pending = false; }
+      rc = b->targets[slot].prepare(ln.st, cs.d_pts, (int)counts[base + k], b->prm, b->batch_ws[m]);
+      if (rc < 0) return rc;
+      ts.lane = 0;
+      if (rc == 0) { ts.built_pending = false; continue; }      // empty cloud: nothing queued
+      grids[m] = &b->targets[slot]; wss[m] = &b->batch_ws[m]; slot_of[m] = slot;
+      m++;
+    }
+    if (m == 0) continue;
+    if ((rc = TargetGrid::enqueue_many(ln.st, m, grids, wss, b->prm))) return rc;
+    for (int q = 0; q < m; q++) {
+      const int slot = slot_of[q];
+      TargetBuildState& ts = b->tstate[slot];
+      CloudSlot& cs = b->target_pts[slot];
+      b->total_launches += b->targets[slot].launches_last_build;
+      if (!ts.built) CUDA_TRY(cudaEventCreateWithFlags(&ts.built, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventRecord(ts.built, ln.st));
+      ts.built_pending = true;
+      if (cs.used) { CUDA_TRY(cudaEventRecord(cs.used, ln.st)); cs.used_pending = true; }
+    }
+  }
+  return LVS_OK;
+}
+
 // The chunk of an n-point source this rank evaluates: [rank*n/world, (rank+1)*n/world).
 static void shard_range(const lvs_ndt_batch* b, size_t n, size_t* lo, size_t* cnt) {
   if (!b->shard_on) { *lo = 0; *cnt = n; return; }
@@ -734,6 +783,7 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   for (auto u : b->up) if (u) cudaStreamSynchronize(u);
   for (auto& ln : b->lanes) if (ln.st) cudaStreamSynchronize(ln.st);
   if (b->st) cudaStreamSynchronize(b->st);
+  for (auto& w : b->batch_ws) { w.release(); if (w.h_gp) cudaFreeHost(w.h_gp); }
   for (auto& t : b->targets) t.release();
   for (auto* v : {&b->target_pts, &b->sources})
     for (auto& c : *v) {
@@ -806,11 +856,8 @@ int lvs_ndt_batch_set_targets(lvs_ndt_batch_t* b, int n, const int32_t* slots, c
                               int on_device) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   if (n < 0 || (n > 0 && (!slots || !xyz || !counts))) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
-  for (int i = 0; i < n; i++) {
-    int rc = set_target(b, slots[i], xyz[i], counts[i], stride_bytes, on_device);
-    if (rc) return rc;
-  }
-  return LVS_OK;
+  if (n == 1) return set_target(b, slots[0], xyz[0], counts[0], stride_bytes, on_device);
+  return set_targets_many(b, n, slots, xyz, counts, stride_bytes, on_device);
 }
 
 int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot, const float* guesses16,

@@ -23,6 +23,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // GridParams::status values besides 0 (ok) and LVS_ERR_GRID_OVERFLOW
 constexpr int kStatusEmpty = 1, kStatusNeedsGrow = 2;
+constexpr int kVoxBatch = 8;             // clouds voxelised by one set of launches
 
 struct BuildScratch {                    // reusable workspace of the voxelisation pipeline
   int capacity = 0;
@@ -66,6 +67,8 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   int finish(cudaStream_t st, BuildScratch& ws);                                                         // lazy completion
   int accept(const GridParams& g, cudaStream_t st, BuildScratch& ws);
   int enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch& ws);
+  int prepare(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws);   // host-side part of build()
+  static int enqueue_many(cudaStream_t st, int count, TargetGrid* const* grids, BuildScratch* const* wss, const lvs_ndt_params& prm);
   int grow_grid(cudaStream_t st, long long cells);
   void free_cells();
   void release();

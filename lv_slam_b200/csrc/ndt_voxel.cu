@@ -35,11 +35,43 @@ __global__ void pack_many_kernel(PackMany pm) {
   }
 }
 
+// ------------------------------------------------------------------ batched pipeline
+// Every kernel below works on up to kVoxBatch clouds at once: blockIdx.y selects the job, blockIdx.x covers the largest job of the
+// launch and the CTAs a smaller job does not need leave at once.  A keyframe batch therefore costs ~20 launches in total instead of
+// ~20 per cloud (the setters were bound by the host's launch rate, not by the device).  The job descriptors travel by value.
+struct VoxJob {
+  const float4* pts; int n;
+  float leaf; long long grid_capacity;
+  GridParams* gp;
+  int* grid; const int* old_keys; int prev_points;          // cells of the previous build to wipe
+  float* bbox_partial; unsigned int* ticket;
+  unsigned int* keys[2]; int* idx[2];                        // radix ping-pong; idx[] already arranged so that the last pass lands in `sorted`
+  int *hist, *hist_scan, *tile_tot, *flags, *pos, *nseg, *nvalid;
+  int* sorted; int* cell_start;
+  double* moments; float* csum;
+  VoxelRec* recs; float4* centroids; int* cell_keys; int* cell_npts; double* cell_evals; double* icov64;
+  int nblk;                                                  // radix tiles of this job
+};
+struct VoxBatch {
+  VoxJob j[kVoxBatch];
+  int count;
+  int min_points; double eig_mult; int variant;
+};
+struct ScanJob { const int* in; int* out; int n; int* tile_tot; int* total; };
+struct ScanBatch { ScanJob j[kVoxBatch]; int count; };
+
 // ------------------------------------------------------------------ bbox
 constexpr int kBboxBlocks = 148;
 
-__global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partial /*[grid][8]*/,
-                                                   unsigned int* __restrict__ ticket, GridParams* __restrict__ gp, float leaf, long long grid_capacity) {
+__global__ void __launch_bounds__(256) bbox_kernel(VoxBatch B) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const float4* __restrict__ pts = J.pts;
+  const int n = J.n;
+  float* __restrict__ partial = J.bbox_partial;      // [grid][8]
+  unsigned int* __restrict__ ticket = J.ticket;
+  GridParams* __restrict__ gp = J.gp;
+  const float leaf = J.leaf;
+  const long long grid_capacity = J.grid_capacity;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   int cnt = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -116,8 +148,13 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pt
 // ------------------------------------------------------------------ keys
 constexpr unsigned int kInvalidKey = 0xFFFFFFFFu;
 
-__global__ void key_kernel(const float4* __restrict__ pts, int n, const GridParams* __restrict__ gp,
-                           unsigned int* __restrict__ keys, int* __restrict__ idx) {
+__global__ void key_kernel(VoxBatch B) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const float4* __restrict__ pts = J.pts;
+  const int n = J.n;
+  const GridParams* __restrict__ gp = J.gp;
+  unsigned int* __restrict__ keys = J.keys[0];
+  int* __restrict__ idx = J.idx[0];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = pts[i];
@@ -138,7 +175,13 @@ __global__ void key_kernel(const float4* __restrict__ pts, int n, const GridPara
 // of the tiles before it (they are few) and adds that offset to its tile.  total (may be null) receives the grand total.
 constexpr int kScanThreads = 256, kScanIpt = 8, kScanTile = kScanThreads * kScanIpt;
 
-__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ tile_tot) {
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanBatch S) {
+  const ScanJob& J = S.j[blockIdx.y];
+  const int n = J.n;
+  if ((long long)blockIdx.x * kScanTile >= n) return;
+  const int* __restrict__ in = J.in;
+  int* __restrict__ out = J.out;
+  int* __restrict__ tile_tot = J.tile_tot;
   __shared__ int s_warp[kScanThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanIpt;
@@ -161,7 +204,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int* __r
   if (threadIdx.x == kScanThreads - 1) tile_tot[blockIdx.x] = s_warp[kScanThreads / 32 - 1];
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ out, int n, const int* __restrict__ tile_tot, int* __restrict__ total) {
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(ScanBatch S) {
+  const ScanJob& J = S.j[blockIdx.y];
+  const int n = J.n;
+  if ((long long)blockIdx.x * kScanTile >= n) return;
+  int* __restrict__ out = J.out;
+  const int* __restrict__ tile_tot = J.tile_tot;
+  int* __restrict__ total = J.total;
+  const unsigned last_block = (unsigned)((n + kScanTile - 1) / kScanTile) - 1u;
   __shared__ int s_warp[kScanThreads / 32];
   __shared__ int s_off;
   int acc = 0;
@@ -175,19 +225,33 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict_
   const int base = blockIdx.x * kScanTile + threadIdx.x * kScanIpt;
 #pragma unroll
   for (int k = 0; k < kScanIpt; k++) if (base + k < n) out[base + k] += off;
-  if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = off + tile_tot[blockIdx.x];
+  if (total && blockIdx.x == last_block && threadIdx.x == 0) *total = off + tile_tot[blockIdx.x];
+}
+
+static void exclusive_scan_many(cudaStream_t st, const ScanBatch& S) {
+  int nb = 0;
+  for (int k = 0; k < S.count; k++) nb = std::max(nb, (S.j[k].n + kScanTile - 1) / kScanTile);
+  if (nb == 0) return;
+  scan_tiles_kernel<<<dim3(nb, S.count), kScanThreads, 0, st>>>(S);
+  scan_add_kernel<<<dim3(nb, S.count), kScanThreads, 0, st>>>(S);
 }
 
 void exclusive_scan(cudaStream_t st, const int* in, int* out, int n, int* total, int* tile_tot) {
-  const int nb = (n + kScanTile - 1) / kScanTile;
-  scan_tiles_kernel<<<nb, kScanThreads, 0, st>>>(in, out, n, tile_tot);
-  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(out, n, tile_tot, total);
+  ScanBatch S;
+  S.count = 1;
+  S.j[0] = ScanJob{in, out, n, tile_tot, total};
+  exclusive_scan_many(st, S);
 }
 
 // ------------------------------------------------------------------ stable LSD radix sort, 8-bit digits
 constexpr int kRsThreads = 256, kRsIpt = 8, kRsTile = kRsThreads * kRsIpt;
 
-__global__ void rs_hist_kernel(const unsigned int* __restrict__ keys, int n, int shift, int nblk, int* __restrict__ hist /*[256][nblk]*/) {
+__global__ void rs_hist_kernel(VoxBatch B, int cur, int shift) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const int nblk = J.nblk, n = J.n;
+  if ((int)blockIdx.x >= nblk) return;
+  const unsigned int* __restrict__ keys = J.keys[cur];
+  int* __restrict__ hist = J.hist;                   // [256][nblk]
   __shared__ int s_h[256];
   s_h[threadIdx.x] = 0;
   __syncthreads();
@@ -200,9 +264,15 @@ __global__ void rs_hist_kernel(const unsigned int* __restrict__ keys, int n, int
   hist[threadIdx.x * nblk + blockIdx.x] = s_h[threadIdx.x];
 }
 
-__global__ void rs_scatter_kernel(const unsigned int* __restrict__ keys_in, const int* __restrict__ idx_in, int n, int shift, int nblk,
-                                  const int* __restrict__ offs /*[256][nblk] exclusive*/, unsigned int* __restrict__ keys_out,
-                                  int* __restrict__ idx_out) {
+__global__ void rs_scatter_kernel(VoxBatch B, int cur, int shift) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const int nblk = J.nblk, n = J.n;
+  if ((int)blockIdx.x >= nblk) return;
+  const unsigned int* __restrict__ keys_in = J.keys[cur];
+  const int* __restrict__ idx_in = J.idx[cur];
+  const int* __restrict__ offs = J.hist_scan;        // [256][nblk] exclusive
+  unsigned int* __restrict__ keys_out = J.keys[cur ^ 1];
+  int* __restrict__ idx_out = J.idx[cur ^ 1];
   __shared__ int s_cnt[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < 8 * 256; k += kRsThreads) (&s_cnt[0][0])[k] = 0;
@@ -244,15 +314,27 @@ __global__ void rs_scatter_kernel(const unsigned int* __restrict__ keys_in, cons
 }
 
 // ------------------------------------------------------------------ segments
-__global__ void head_flag_kernel(const unsigned int* __restrict__ keys, int n, int* __restrict__ flags) {
+__global__ void head_flag_kernel(VoxBatch B, int cur) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const unsigned int* __restrict__ keys = J.keys[cur];
+  const int n = J.n;
+  int* __restrict__ flags = J.flags;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { J.nseg[0] = 0; J.nvalid[0] = 0; }      // the scan that follows deposits the segment count here
   if (i >= n) return;
   unsigned k = keys[i];
   flags[i] = (k != kInvalidKey && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
 }
 
-__global__ void seg_start_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ flags, const int* __restrict__ pos, int n,
-                                 int* __restrict__ seg_start, const int* __restrict__ n_seg, int* __restrict__ n_valid_pts) {
+__global__ void seg_start_kernel(VoxBatch B, int cur) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const unsigned int* __restrict__ keys = J.keys[cur];
+  const int* __restrict__ flags = J.flags;
+  const int* __restrict__ pos = J.pos;
+  const int n = J.n;
+  int* __restrict__ seg_start = J.cell_start;
+  const int* __restrict__ n_seg = J.nseg;
+  int* __restrict__ n_valid_pts = J.nvalid;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (flags[i]) seg_start[pos[i]] = i;
@@ -260,9 +342,10 @@ __global__ void seg_start_kernel(const unsigned int* __restrict__ keys, const in
   if (keys[i] != kInvalidKey && (i == n - 1 || keys[i + 1] == kInvalidKey)) { seg_start[*n_seg] = i + 1; *n_valid_pts = i + 1; }
 }
 
-__global__ void clear_cells_kernel(int* __restrict__ grid, const int* __restrict__ old_keys, const GridParams* __restrict__ gp_old) {
+__global__ void clear_cells_kernel(VoxBatch B) {
+  const VoxJob& J = B.j[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gp_old->status == 0 && i < gp_old->n_cells) grid[old_keys[i]] = -1;
+  if (J.prev_points > 0 && J.gp->status == 0 && i < J.gp->n_cells) J.grid[J.old_keys[i]] = -1;
 }
 
 // ------------------------------------------------------------------ per-cell moments
@@ -293,10 +376,15 @@ __device__ __forceinline__ void mom_stage(MomStage& s, int lane, bool live, cons
   *reinterpret_cast<float4*>(s.f[lane]) = make_float4(fx, fy, fz, 0.0f);
 }
 
-__global__ void __launch_bounds__(kMomWarps * 32) leaf_moments_kernel(const float4* __restrict__ pts, const int* __restrict__ sidx,
-                                                                      const int* __restrict__ seg_start, const int* __restrict__ n_seg_p,
-                                                                      const GridParams* __restrict__ gp, double* __restrict__ moments /*[cell][9]*/,
-                                                                      float* __restrict__ csum /*[cell][3]*/) {
+__global__ void __launch_bounds__(kMomWarps * 32) leaf_moments_kernel(VoxBatch B) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const float4* __restrict__ pts = J.pts;
+  const int* __restrict__ sidx = J.sorted;
+  const int* __restrict__ seg_start = J.cell_start;
+  const int* __restrict__ n_seg_p = J.nseg;
+  const GridParams* __restrict__ gp = J.gp;
+  double* __restrict__ moments = J.moments;          // [cell][9]
+  float* __restrict__ csum = J.csum;                 // [cell][3]
   if (gp->status != 0) return;
   __shared__ MomStage s_stage[kMomWarps][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -340,12 +428,23 @@ __global__ void __launch_bounds__(kMomWarps * 32) leaf_moments_kernel(const floa
 }
 
 // ------------------------------------------------------------------ leaf finalisation, one thread per cell (:281-367)
-__global__ void __launch_bounds__(128) leaf_finalize_kernel(const unsigned int* __restrict__ keys, const int* __restrict__ seg_start,
-                                                            const int* __restrict__ n_seg_p, const double* __restrict__ moments,
-                                                            const float* __restrict__ csum, VoxelRec* __restrict__ recs, float4* __restrict__ centroids,
-                                                            int* __restrict__ cell_keys, int* __restrict__ cell_npts, double* __restrict__ cell_evals,
-                                                            double* __restrict__ icov64, int* __restrict__ grid, GridParams* __restrict__ gp,
-                                                            int min_points, double eig_mult, int variant) {
+__global__ void __launch_bounds__(128) leaf_finalize_kernel(VoxBatch B, int cur) {
+  const VoxJob& J = B.j[blockIdx.y];
+  const unsigned int* __restrict__ keys = J.keys[cur];
+  const int* __restrict__ seg_start = J.cell_start;
+  const int* __restrict__ n_seg_p = J.nseg;
+  const double* __restrict__ moments = J.moments;
+  const float* __restrict__ csum = J.csum;
+  VoxelRec* __restrict__ recs = J.recs;
+  float4* __restrict__ centroids = J.centroids;
+  int* __restrict__ cell_keys = J.cell_keys;
+  int* __restrict__ cell_npts = J.cell_npts;
+  double* __restrict__ cell_evals = J.cell_evals;
+  double* __restrict__ icov64 = J.icov64;
+  int* __restrict__ grid = J.grid;
+  GridParams* __restrict__ gp = J.gp;
+  const int min_points = B.min_points, variant = B.variant;
+  const double eig_mult = B.eig_mult;
   if (gp->status != 0) return;
   const int n_seg = *n_seg_p;
   int valid_cells = 0;
@@ -431,63 +530,127 @@ static int radix_passes_for(long long cells) {   // keys < cells, invalid keys 0
   return (bits + 7) / 8;
 }
 
+// ---- launch helpers over a batch of jobs
+static void job_scratch(VoxJob& J, BuildScratch& ws, int passes, int* sorted_out, int* cell_start_out) {
+  J.bbox_partial = ws.d_bbox_partial; J.ticket = ws.d_ticket;
+  J.keys[0] = ws.d_keys[0]; J.keys[1] = ws.d_keys[1];
+  // the index buffer the LAST pass writes is the caller's sorted_out, so the sorted order needs no extra copy; pass 0 reads the
+  // identity permutation key_kernel leaves in idx[0]
+  J.idx[0] = ws.d_idx[0]; J.idx[1] = ws.d_idx[1];
+  J.idx[passes & 1] = sorted_out;
+  J.hist = ws.d_hist; J.hist_scan = ws.d_hist_scan; J.tile_tot = ws.d_tile_tot; J.flags = ws.d_flags; J.pos = ws.d_pos;
+  J.nseg = ws.d_nseg; J.nvalid = ws.d_nvalidpts;
+  J.sorted = sorted_out; J.cell_start = cell_start_out;
+  J.moments = ws.d_moments; J.csum = ws.d_csum;
+  J.nblk = (J.n + kRsTile - 1) / kRsTile;
+}
+
+static int max_n(const VoxBatch& B) { int m = 0; for (int k = 0; k < B.count; k++) m = std::max(m, B.j[k].n); return m; }
+
+static void launch_bbox(cudaStream_t st, const VoxBatch& B) {
+  const int gb = (max_n(B) + 255) / 256;
+  bbox_kernel<<<dim3(std::max(1, std::min(kBboxBlocks, gb)), B.count), 256, 0, st>>>(B);
+}
+
+// key -> stable radix sort -> segment heads -> scan -> segment starts.  Returns the index of the key buffer that holds the sorted keys.
+static int launch_sort_segments(cudaStream_t st, const VoxBatch& B, int passes) {
+  const int n = max_n(B), tb = 256, gb = (n + tb - 1) / tb;
+  const int nblk = (n + kRsTile - 1) / kRsTile;
+  key_kernel<<<dim3(gb, B.count), tb, 0, st>>>(B);
+  int cur = 0;
+  ScanBatch S;
+  S.count = B.count;
+  for (int p = 0; p < passes; p++) {
+    rs_hist_kernel<<<dim3(nblk, B.count), kRsThreads, 0, st>>>(B, cur, p * 8);
+    for (int k = 0; k < B.count; k++) S.j[k] = ScanJob{B.j[k].hist, B.j[k].hist_scan, 256 * B.j[k].nblk, B.j[k].tile_tot, nullptr};
+    exclusive_scan_many(st, S);
+    // pass 0 reads the identity permutation from the scratch buffer even when idx[0] was redirected to the caller's array
+    rs_scatter_kernel<<<dim3(nblk, B.count), kRsThreads, 0, st>>>(B, cur, p * 8);
+    cur ^= 1;
+  }
+  head_flag_kernel<<<dim3(gb, B.count), tb, 0, st>>>(B, cur);
+  for (int k = 0; k < B.count; k++) S.j[k] = ScanJob{B.j[k].flags, B.j[k].pos, B.j[k].n, B.j[k].tile_tot, B.j[k].nseg};
+  exclusive_scan_many(st, S);
+  seg_start_kernel<<<dim3(gb, B.count), tb, 0, st>>>(B, cur);
+  return cur;
+}
+
 // Bounding box and grid geometry of a cloud (getMinMax3D + the min_b / max_b / div_b arithmetic) into *d_gp.
 void vox_bbox(cudaStream_t st, const float4* pts, int n, BuildScratch& ws, GridParams* d_gp, float leaf, long long grid_capacity) {
-  bbox_kernel<<<std::max(1, std::min(kBboxBlocks, (n + 255) / 256)), 256, 0, st>>>(pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, leaf, grid_capacity);
+  VoxBatch B;
+  memset(&B, 0, sizeof B);
+  B.count = 1;
+  VoxJob& J = B.j[0];
+  J.pts = pts; J.n = n; J.leaf = leaf; J.grid_capacity = grid_capacity; J.gp = d_gp;
+  J.bbox_partial = ws.d_bbox_partial; J.ticket = ws.d_ticket;
+  launch_bbox(st, B);
 }
 
 int vox_radix_passes(long long cells) { return radix_passes_for(cells); }
 
 // Voxel key of every point, stable sort of the point indices by key, one segment per occupied cell: sorted_out [n] receives the
 // point indices grouped by cell in ascending key order (input order inside a cell), cell_start_out [cells + 1] the segment
-// starts, ws.d_nseg the number of cells; the sorted keys are left in ws.d_keys[passes & 1].
+// starts, ws.d_nseg the number of cells.
 int vox_sort_segments(cudaStream_t st, const float4* pts, int n, const GridParams* d_gp, int passes, BuildScratch& ws, int* sorted_out,
                       int* cell_start_out) {
-  const int tb = 256, gb = (n + tb - 1) / tb;
-  key_kernel<<<gb, tb, 0, st>>>(pts, n, d_gp, ws.d_keys[0], ws.d_idx[0]);
-  const int nblk = (n + kRsTile - 1) / kRsTile;
-  int cur = 0;
-  // the index buffer the LAST pass writes is the caller's sorted_out, so the sorted order needs no extra copy; the other buffer of
-  // the ping-pong is scratch
-  int* idx_buf[2] = {ws.d_idx[0], ws.d_idx[1]};
-  idx_buf[passes & 1] = sorted_out;
-  for (int p = 0; p < passes; p++) {
-    rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], n, p * 8, nblk, ws.d_hist);
-    exclusive_scan(st, ws.d_hist, ws.d_hist_scan, 256 * nblk, nullptr, ws.d_tile_tot);
-    rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(ws.d_keys[cur], p == 0 ? ws.d_idx[0] : idx_buf[cur], n, p * 8, nblk, ws.d_hist_scan, ws.d_keys[cur ^ 1], idx_buf[cur ^ 1]);
-    cur ^= 1;
+  VoxBatch B;
+  memset(&B, 0, sizeof B);
+  B.count = 1;
+  VoxJob& J = B.j[0];
+  J.pts = pts; J.n = n; J.gp = const_cast<GridParams*>(d_gp);
+  job_scratch(J, ws, passes, sorted_out, cell_start_out);
+  launch_sort_segments(st, B, passes);
+  CUDA_TRY(cudaGetLastError());
+  return LVS_OK;
+}
+
+// Queues the voxelisation of `count` targets on `st` in batched launches.  Every grid needs d_grid and its cell arrays, and its
+// own scratch; never synchronises.
+int TargetGrid::enqueue_many(cudaStream_t st, int count, TargetGrid* const* grids, BuildScratch* const* wss, const lvs_ndt_params& prm) {
+  for (int base = 0; base < count; base += kVoxBatch) {
+    VoxBatch B;
+    memset(&B, 0, sizeof B);
+    B.count = std::min(kVoxBatch, count - base);
+    B.min_points = prm.min_points_per_voxel; B.eig_mult = prm.min_covar_eigvalue_mult; B.variant = prm.variant;
+    int passes = 1, max_prev = 0;
+    for (int k = 0; k < B.count; k++) passes = std::max(passes, radix_passes_for((long long)grids[base + k]->grid_capacity));
+    for (int k = 0; k < B.count; k++) {
+      TargetGrid& g = *grids[base + k];
+      VoxJob& J = B.j[k];
+      J.pts = g.pts; J.n = g.n_points; J.leaf = prm.resolution; J.grid_capacity = (long long)g.grid_capacity; J.gp = g.d_gp;
+      J.grid = g.d_grid; J.old_keys = g.d_cell_keys; J.prev_points = g.prev_points;
+      J.recs = g.d_recs; J.centroids = g.d_centroids; J.cell_keys = g.d_cell_keys; J.cell_npts = g.d_cell_npts; J.cell_evals = g.d_cell_evals;
+      J.icov64 = g.d_icov64;
+      job_scratch(J, *wss[base + k], passes, g.d_sorted_idx, g.d_cell_start);
+      max_prev = std::max(max_prev, g.prev_points);
+    }
+    // wipe the cells of the previous builds while the old keys and the old geometry still describe the index grids
+    if (max_prev > 0) clear_cells_kernel<<<dim3((max_prev + 255) / 256, B.count), 256, 0, st>>>(B);
+    launch_bbox(st, B);
+    const int cur = launch_sort_segments(st, B, passes);
+    const int n = max_n(B);
+    leaf_moments_kernel<<<dim3(std::min(148 * kMomCtasPerSm, (n + kMomWarps - 1) / kMomWarps), B.count), kMomWarps * 32, 0, st>>>(B);
+    leaf_finalize_kernel<<<dim3(std::min(148 * 4, (n + 127) / 128), B.count), 128, 0, st>>>(B, cur);
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k < B.count; k++) {
+      TargetGrid& g = *grids[base + k];
+      g.launches_last_build = k == 0 ? (max_prev > 0 ? 1 : 0) + 2 + passes * 4 + 1 + 2 + 1 + 2 : 0;   // the batch's launches, booked once
+      g.prev_points = g.n_points;
+      g.pending = true;
+    }
   }
-  head_flag_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], n, ws.d_flags);
-  CUDA_TRY(cudaMemsetAsync(ws.d_nseg, 0, 2 * sizeof(int), st));
-  exclusive_scan(st, ws.d_flags, ws.d_pos, n, ws.d_nseg, ws.d_tile_tot);
-  seg_start_kernel<<<gb, tb, 0, st>>>(ws.d_keys[cur], ws.d_flags, ws.d_pos, n, cell_start_out, ws.d_nseg, ws.d_nvalidpts);
-  CUDA_TRY(cudaGetLastError());
   return LVS_OK;
 }
 
-// Queues the whole voxelisation on `st`.  Needs d_grid to exist; never synchronises.
 int TargetGrid::enqueue(cudaStream_t st, const lvs_ndt_params& prm, BuildScratch& ws) {
-  const int n = n_points;
-  // wipe the cells of the previous build while the old keys and the old geometry still describe this buffer
-  if (prev_points > 0) clear_cells_kernel<<<(prev_points + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, d_gp);
-  vox_bbox(st, pts, n, ws, d_gp, prm.resolution, (long long)grid_capacity);
-  const int passes = radix_passes_for((long long)grid_capacity);
-  int rc = vox_sort_segments(st, pts, n, d_gp, passes, ws, d_sorted_idx, d_cell_start);
-  if (rc) return rc;
-  const int cur = passes & 1;
-  int* const sorted = d_sorted_idx;
-  leaf_moments_kernel<<<std::min(148 * kMomCtasPerSm, (n + kMomWarps - 1) / kMomWarps), kMomWarps * 32, 0, st>>>(pts, sorted, d_cell_start, ws.d_nseg, d_gp, ws.d_moments, ws.d_csum);
-  leaf_finalize_kernel<<<std::min(148 * 4, (n + 127) / 128), 128, 0, st>>>(ws.d_keys[cur], d_cell_start, ws.d_nseg, ws.d_moments, ws.d_csum, d_recs,
-                                                                          d_centroids, d_cell_keys, d_cell_npts, d_cell_evals, d_icov64, d_grid, d_gp,
-                                                                          prm.min_points_per_voxel, prm.min_covar_eigvalue_mult, prm.variant);
-  CUDA_TRY(cudaGetLastError());
-  launches_last_build = (prev_points > 0 ? 1 : 0) + 2 + passes * 4 + 1 + 2 + 1 + 2;
-  prev_points = n;
-  pending = true;
-  return LVS_OK;
+  TargetGrid* g = this;
+  BuildScratch* w = &ws;
+  return enqueue_many(st, 1, &g, &w, prm);
 }
 
-int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws) {
+// Host-side preparation of a build (allocations, first-build sizing of the index grid).  Returns 1 when the target is ready for
+// enqueue / enqueue_many, 0 when the build is already complete (empty cloud), < 0 on error.
+int TargetGrid::prepare(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws) {
   n_points = n;
   pts = d_pts;
   built_with = prm;
@@ -498,13 +661,19 @@ int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt
     CUDA_TRY(cudaMemcpyAsync(d_gp, &g, sizeof g, cudaMemcpyHostToDevice, st));
   }
   if (n == 0) {
-    if (prev_points > 0 && d_grid) clear_cells_kernel<<<(prev_points + 255) / 256, 256, 0, st>>>(d_grid, d_cell_keys, d_gp);
+    if (prev_points > 0 && d_grid) {
+      VoxBatch B;
+      memset(&B, 0, sizeof B);
+      B.count = 1;
+      B.j[0].gp = d_gp; B.j[0].grid = d_grid; B.j[0].old_keys = d_cell_keys; B.j[0].prev_points = prev_points;
+      clear_cells_kernel<<<dim3((prev_points + 255) / 256, 1), 256, 0, st>>>(B);
+    }
     prev_points = 0;
     GridParams g; memset(&g, 0, sizeof g); g.status = kStatusEmpty; g.leaf = prm.resolution; g.inv_leaf = 1.0f / prm.resolution;
     CUDA_TRY(cudaMemcpyAsync(d_gp, &g, sizeof g, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // g lives on this stack frame
     gp = g; n_cells = 0; pending = false; launches_last_build = 0;
-    return LVS_OK;
+    return 0;
   }
   // cell arrays sized for the worst case of one cell per point
   if ((size_t)n > cell_capacity) {
@@ -525,15 +694,21 @@ int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt
   }
   if (!d_grid) {
     // first build of this slot: the index grid has no capacity yet, so size it from the geometry (one synchronisation, once)
-    bbox_kernel<<<std::min(kBboxBlocks, (n + 255) / 256), 256, 0, st>>>(d_pts, n, ws.d_bbox_partial, ws.d_ticket, d_gp, prm.resolution, 0LL);
+    vox_bbox(st, d_pts, n, ws, d_gp, prm.resolution, 0LL);
     CUDA_TRY(cudaMemcpyAsync(ws.h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     gp = *ws.h_gp;
     if (gp.status == LVS_ERR_GRID_OVERFLOW) { pending = false; n_cells = 0; return fail(LVS_ERR_GRID_OVERFLOW, "leaf size too small for the target extent: dx*dy*dz > INT32_MAX"); }
-    if (gp.status == kStatusEmpty) { pending = false; n_cells = 0; return LVS_OK; }   // no finite point
+    if (gp.status == kStatusEmpty) { pending = false; n_cells = 0; return 0; }   // no finite point
     int rc = grow_grid(st, gp.total_cells);
     if (rc) return rc;
   }
+  return 1;
+}
+
+int TargetGrid::build(cudaStream_t st, const float4* d_pts, int n, const lvs_ndt_params& prm, BuildScratch& ws) {
+  const int rc = prepare(st, d_pts, n, prm, ws);
+  if (rc <= 0) return rc;
   return enqueue(st, prm, ws);
 }
 
