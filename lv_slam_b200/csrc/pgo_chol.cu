@@ -298,7 +298,7 @@ __device__ __forceinline__ void team_sync(unsigned int* bar, unsigned int& targe
 }
 
 template <bool TEAM>
-__global__ void __launch_bounds__(kCholThreads) chol_front_kernel(CholView V, const int* __restrict__ list, int n_list, int team_size,
+__global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(CholView V, const int* __restrict__ list, int n_list, int team_size,
                                                                   unsigned int* __restrict__ bars) {
   const int team = blockIdx.x / team_size, rank = blockIdx.x % team_size, n_teams = gridDim.x / team_size;
   const int tid = rank * kCholThreads + threadIdx.x, nthr = team_size * kCholThreads;
@@ -366,18 +366,30 @@ __global__ void __launch_bounds__(kCholThreads) chol_front_kernel(CholView V, co
         s_D[i][j] = 0.0;
       }
       __syncthreads();
-      for (int j = 0; j < nb; j++) {
-        double d = s_S[j][j];
-        if (!(d > 0.0)) { if (tid == 0) *V.fail_flag = 1; d = 1.0; }
-        const double il = rsqrt(d);                  // one reciprocal square root instead of sqrt + divide on the serial path
-        for (int t = threadIdx.x; t < kNB * kNB; t += kCholThreads) {
-          const int i = t / kNB, k = t % kNB;
-          if (i < nb && k <= i) {
-            if (k == j) { s_D[i][j] = (i == j) ? d * il : s_S[i][j] * il; if (i == j) s_inv[j] = il; }
-            else if (k > j) s_S[i][k] -= (s_S[i][j] * il) * (s_S[k][j] * il);
-          }
+      {
+        // the (up to three) lower-triangle elements this thread owns, fixed for the whole panel
+        int ei[3], ek[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          const int t = threadIdx.x + u * kCholThreads;
+          ei[u] = t / kNB; ek[u] = t % kNB;
+          if (!(t < kNB * kNB && ei[u] < nb && ek[u] <= ei[u])) { ei[u] = -1; ek[u] = kNB; }     // inactive: i = -1 fails every test below
         }
-        __syncthreads();
+        for (int j = 0; j < nb; j++) {
+          if (ei[0] > j || ei[1] > j || ei[2] > j || ei[0] == j || ei[1] == j || ei[2] == j) {      // rows above j are finished
+            double d = s_S[j][j];
+            if (!(d > 0.0)) { *V.fail_flag = 1; d = 1.0; }     // every thread that sees it stores the same 1
+            const double il = rsqrt(d);                // one reciprocal square root instead of sqrt + divide on the serial path
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int i = ei[u], k = ek[u];
+              if (i < j) continue;
+              if (k == j) { s_D[i][j] = (i == j) ? d * il : s_S[i][j] * il; if (i == j) s_inv[j] = il; }
+              else if (k > j) s_S[i][k] -= (s_S[i][j] * il) * (s_S[k][j] * il);
+            }
+          }
+          __syncthreads();
+        }
       }
       // (B) rows below the diagonal block: x L_D^T = a, forward substitution along the row
       {
@@ -486,36 +498,38 @@ __global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V,
   for (int i = threadIdx.x; i < nr; i += kCholThreads) xs[p + i] = V.xp[(size_t)V.rows[f.rows_off + i / 6] * 6 + i % 6];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kW = kCholThreads / 32;
+  __syncthreads();
+  // xs[0:p] -= B^T x_R : one warp per pivot column (contiguous in memory), eight loads in flight, fixed shuffle tree
+  for (int j = warp; j < p; j += kW) {
+    const double* __restrict__ col = A + (size_t)j * F + p;
+    double acc = 0.0;
+    for (int i0 = lane; i0 < nr; i0 += 32 * 8) {
+      // unconditional loads from clamped addresses: with predicated loads the compiler sinks each one next to its use and
+      // only one is in flight at a time
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = col[min(i0 + 32 * u, nr - 1)];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u; acc += (i < nr) ? v[u] * xs[p + i] : 0.0; }
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) xs[j] -= acc;
+  }
   const int n_panels = (p + kNB - 1) / kNB;
   for (int pi = n_panels - 1; pi >= 0; pi--) {
     const int c = pi * kNB, nb = min(kNB, p - c);
-    __syncthreads();                                // xs of the previous panel is complete; s_D / s_dot are free
+    __syncthreads();                                // every update of this panel's right-hand side has landed
     for (int t = threadIdx.x; t < kNB * kNB; t += kCholThreads) {
       const int j = t / kNB, i = t % kNB;
       const double v = A[(size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1)];
       s_D[i][j] = (i < nb && j <= i) ? v : (i == j ? 1.0 : 0.0);
     }
-    for (int j = warp; j < nb; j += kW) {
-      const double* __restrict__ col = A + (size_t)(c + j) * F;
-      double acc = 0.0;
-      for (int i0 = c + nb + lane; i0 < F - 1; i0 += 32 * 8) {
-        // unconditional loads from clamped addresses: with predicated loads the compiler sinks each one next to its use and
-        // only one is in flight at a time
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = col[min(i0 + 32 * u, F - 2)];
-#pragma unroll
-        for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u; acc += (i < F - 1) ? v[u] * xs[i] : 0.0; }
-      }
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) s_dot[j] = acc;
-    }
     __syncthreads();
     if (threadIdx.x < 32) {
-      // L_D^T x = rhs: x_j = (rhs_j - sum_{i > j} L[i][j] x_i) / L[j][j]
+      // L_D^T x = rhs: x_j = (rhs_j - sum_{i > j} L[i][j] x_i) / L[j][j]; lane m accumulates its own row's sum as the x_i appear
       const int m = threadIdx.x;
       const bool on = m < nb;
-      const double rhs = on ? xs[c + m] - s_dot[m] : 0.0;
+      const double rhs = on ? xs[c + m] : 0.0;
       const double inv = on ? 1.0 / s_D[m][m] : 0.0;
       double acc = 0.0, mine = 0.0;
       for (int j = nb - 1; j >= 0; j--) {
@@ -523,7 +537,21 @@ __global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V,
         if (m == j) mine = xj;
         if (m < j) acc += s_D[j][m] * xj;
       }
+      if (m < kNB) s_dot[m] = on ? mine : 0.0;       // the panel's solution (zero padded)
       if (on) xs[c + m] = mine;
+    }
+    __syncthreads();
+    // right-looking update of every earlier pivot: xs[i] -= sum_j L[c + j][i] x_j.  Column i of the front is contiguous in j, so a
+    // thread streams its 24 entries with all loads in flight.
+    for (int i = threadIdx.x; i < c; i += kCholThreads) {
+      const double* __restrict__ col = A + (size_t)i * F + c;
+      double v[kNB];
+#pragma unroll
+      for (int j = 0; j < kNB; j++) v[j] = col[min(j, nb - 1)];
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < kNB; j++) acc += v[j] * s_dot[j];
+      xs[i] -= acc;
     }
   }
   __syncthreads();
