@@ -141,8 +141,8 @@ class GraphSLAM:
                                                       " ".join(repr(float(x)) for x in up)))
         with open(filename + ".kernels", "w") as f:                               # robust_kernel_io.cpp sidecar
             for e in self._edges:
-                if e.kernel:
-                    f.write("%d %d %s %r\n" % (e.vertices[0]._id, e.vertices[1]._id, e.kernel[0], e.kernel[1]))
+                if e.kernel:       # "<n vertices> <ids...> <type> <delta>" (g2o/robust_kernel_io.cpp:22-48)
+                    f.write("2 %d %d %s %r\n" % (e.vertices[0]._id, e.vertices[1]._id, e.kernel[0], e.kernel[1]))
         return True
 
     def load(self, filename):
@@ -177,7 +177,9 @@ class GraphSLAM:
                 kern = {}
                 for line in f:
                     t = line.split()
-                    if len(t) == 4:
+                    if len(t) == 5 and t[0] == "2":           # KernelData (robust_kernel_io.cpp:51-62)
+                        kern[(int(t[1]), int(t[2]))] = (t[3], float(t[4]))
+                    elif len(t) == 4:                         # sidecars written before the vertex count was added
                         kern[(int(t[0]), int(t[1]))] = (t[2], float(t[3]))
                 for e in self._edges:
                     k = kern.get((e.vertices[0]._id, e.vertices[1]._id))
@@ -186,6 +188,28 @@ class GraphSLAM:
         except OSError:
             pass
         return True
+
+
+def save_kitti_poses(filename, poses4x4):
+    """One pose per line, the first three rows of the 4x4 matrix row-major with %le, the odometry node's own output format
+    (src/lidar_odometry/scan_matching_odom_nodelet.cpp:157-160) and the KITTI ground-truth format it is compared with."""
+    with open(filename, "w") as f:
+        for T in poses4x4:
+            T = np.asarray(T, dtype=np.float64)
+            f.write(" ".join("%e" % T[r, c] for r in range(3) for c in range(4)) + "\n")
+
+
+def load_kitti_poses(filename):
+    out = []
+    with open(filename) as f:
+        for line in f:
+            v = line.split()
+            if len(v) != 12:
+                continue
+            T = np.eye(4)
+            T[:3, :4] = np.array(v, dtype=np.float64).reshape(3, 4)
+            out.append(T)
+    return out
 
 
 def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iterations):

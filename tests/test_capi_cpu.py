@@ -106,6 +106,23 @@ def test_graph_slam_text_round_trip(tmp_path):
     np.testing.assert_allclose(p2, p1, atol=1e-15); np.testing.assert_allclose(m2, m1, atol=1e-15)
     assert np.array_equal(ij1, ij2) and np.array_equal(f1, f2) and np.array_equal(h1, h2) and np.array_equal(i1, i2)
     assert M.GraphSLAM().optimize(5) == -1                  # no edges (graph_slam.cpp:302-305), decided before any device call
+    # the robust-kernel sidecar has the reference's own line format "<n vertices> <ids...> <type> <delta>" (robust_kernel_io.cpp:22-62)
+    kl = open(path + ".kernels").read().splitlines()
+    assert len(kl) == (len(g["ij"]) + 1) // 2 and all(len(l.split()) == 5 and l.split()[0] == "2" and l.split()[3] == "Huber" for l in kl)
+    # and a file written by the reference (g2o text + sidecar) loads
+    ref = str(tmp_path / "ref.g2o")
+    open(ref, "w").write("VERTEX_SE3:QUAT 0 0 0 0 0 0 0 1\nVERTEX_SE3:QUAT 1 1 0 0 0 0 0 1\nEDGE_SE3:QUAT 1 0 -1 0 0 0 0 0 1 " +
+                         " ".join("2" if k in (0, 6, 11) else "10" if k in (15, 18, 20) else "0" for k in range(21)) + "\n")
+    open(ref + ".kernels", "w").write("2 1 0 Huber 1\n")
+    gs3 = M.GraphSLAM()
+    assert gs3.load(ref) and gs3.num_edges() == 1 and gs3._arrays()[5][0] == 1.0 and np.array_equal(gs3._arrays()[2], [[1, 0]])
+    # KITTI pose lines (scan_matching_odom_nodelet.cpp:157-160)
+    from lv_slam_b200.graph_slam import load_kitti_poses, save_kitti_poses
+    Ts = [G.matrix(p) for p in g["poses7"][:5]]
+    save_kitti_poses(str(tmp_path / "odom.txt"), Ts)
+    back = load_kitti_poses(str(tmp_path / "odom.txt"))
+    assert len(back) == 5 and len(open(str(tmp_path / "odom.txt")).readline().split()) == 12
+    np.testing.assert_allclose(np.array(back), np.array(Ts), rtol=0, atol=1e-6 * 200)
 
 
 def test_keyframe_plan_follows_the_nodelet_policy():
