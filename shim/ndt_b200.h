@@ -6,6 +6,7 @@
 #pragma once
 #include <pcl/point_types.h>
 #include <pcl/registration/registration.h>
+#include <limits>
 #include <stdexcept>
 #include "lvslam_b200.h"
 
@@ -60,6 +61,14 @@ class NormalDistributionsTransform : public pcl::Registration<PointSource, Point
   inline void setNeighborhoodSearchMethod(NeighborSearchMethod m) { prm_.search_method = (int)m; push(); }
   inline double getTransformationProbability() const { return res_.trans_probability; }
   inline int getFinalNumIteration() const { return res_.iterations; }
+  // pcl::Registration::getFitnessScore is not virtual; a class-level overload with the same name and arguments hides it for callers
+  // that hold this type, and loop_detector.hpp:176,255 (which holds a pcl::Registration::Ptr) calls lvs_fitness_score() below.
+  // Evaluated for the final transformation of the last align(), like the base class.
+  inline double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
+    double s = 0;
+    check(lvs_ndt_fitness_score(h_, nullptr, max_range, &s, nullptr));
+    return s;
+  }
   double calculateScore(const PointCloudSource& cloud) const {   // evaluates an already transformed cloud (ndt_omp_impl2.hpp:1007-1040)
     lvs_ndt_t* tmp = nullptr;
     check(lvs_ndt_create(&prm_, 0, nullptr, &tmp));
@@ -97,5 +106,13 @@ class NormalDistributionsTransform : public pcl::Registration<PointSource, Point
   lvs_ndt_params prm_;
   lvs_ndt_result res_{};
 };
+
+// For callers that only hold the base pointer (include/global_graph/loop_detector.hpp:176,255):
+//   double score = lvs_fitness_score(registration, fitness_score_max_range);
+template <typename PointT>
+inline double lvs_fitness_score(const typename pcl::Registration<PointT, PointT>::Ptr& reg, double max_range) {
+  if (auto* n = dynamic_cast<NormalDistributionsTransform<PointT, PointT>*>(reg.get())) return n->getFitnessScore(max_range);
+  return reg->getFitnessScore(max_range);     // any other registration (GICP, ICP) keeps PCL's kd-tree path
+}
 
 }  // namespace

@@ -3,7 +3,7 @@
 import collections, csv, json, os, shutil, subprocess, sys
 tag, name = sys.argv[1], sys.argv[2]
 src = os.path.join("gpurun_out", tag); dst = os.path.join("profiles", name); os.makedirs(dst, exist_ok=True)
-for f in ("bench.json", "bench_pca.json", "bench_ref.json", "pytest_gpu.log", "smoke.log", "gpu_first.log", "pgo_perf.log", "gpu.txt", "nproc.txt", "breakdown.log",
+for f in ("bench.json", "bench_pca.json", "bench_ref.json", "pytest_gpu.log", "smoke.log", "gpu_first.log", "pgo_perf.log", "aux_perf.log", "chol_solve.log", "gpu.txt", "nproc.txt", "breakdown.log",
           "launches.csv", "shard.log", "bench_n2.json"):
     if os.path.exists(os.path.join(src, f)): shutil.copy(os.path.join(src, f), os.path.join(dst, f))
 # launch list -> per-kernel shares
