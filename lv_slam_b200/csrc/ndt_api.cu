@@ -1121,7 +1121,12 @@ static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const flo
   if ((rc = wait_all_uploads(b))) return rc;
   if ((rc = finish_target(b, tgt_slot))) return rc;
   const CloudSlot& src = b->sources[src_slot];
-  const TargetGrid& tg = b->targets[tgt_slot];
+  TargetGrid& tg = b->targets[tgt_slot];
+  if (!tg.sorted_pts_valid && tg.n_cells > 0) {      // first query against this build: put the target points into cell order
+    if ((rc = launch_fitness_gather(b->st, b->target_pts[tgt_slot].d_pts, b->target_pts[tgt_slot].n, tg.d_sorted_idx, tg.d_cell_start, tg.d_gp, tg.d_sorted_pts))) return rc;
+    b->total_launches++;
+    tg.sorted_pts_valid = true;
+  }
   if ((size_t)src.n + 1 > b->fit_cap) {
     if (b->d_fit_best) cudaFree(b->d_fit_best);
     if (b->d_fit_list) cudaFree(b->d_fit_list);
@@ -1140,7 +1145,7 @@ static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const flo
   FitnessArgs a;
   a.src = src.d_pts; a.n_src = src.n;
   a.tgt = b->target_pts[tgt_slot].d_pts; a.n_tgt = b->target_pts[tgt_slot].n;
-  a.grid = tg.d_grid; a.gp = tg.d_gp; a.cell_start = tg.d_cell_start; a.sorted_idx = tg.d_sorted_idx;
+  a.grid = tg.d_grid; a.gp = tg.d_gp; a.cell_start = tg.d_cell_start; a.sorted_idx = tg.d_sorted_idx; a.tgt_sorted = tg.d_sorted_pts;
   a.T16 = b->d_T16; a.max_range = max_range;
   a.best = b->d_fit_best; a.list = b->d_fit_list; a.partials = b->d_fit_partials; a.ticket = b->d_fit_ticket; a.out = b->d_scalar;
   int launches = 0;

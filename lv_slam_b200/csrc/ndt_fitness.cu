@@ -6,8 +6,10 @@
 //   <= max_range (the reference compares the SQUARED distance with max_range), return their mean in double, or DBL_MAX when
 //   there is no correspondence.
 // The kd-tree is replaced by the voxel structure the target already has: the dense index grid, and the target points grouped by
-// cell (TargetGrid::d_sorted_idx / d_cell_start).  A query scans the 27 cells around its own cell, then the shells of radius 2
-// and 3; the best distance found is exact as soon as it is below the distance to the outside of the scanned block.  The few
+// cell (TargetGrid::d_sorted_idx / d_cell_start; copied once per build into cell order, d_sorted_pts, so that a cell is one
+// contiguous run).  A query scans its own cell, then the 26 cells around it, then the shells of radius 2 and 3, skipping every
+// cell whose box is farther away than the best distance so far; the best distance found is exact as soon as it is below the
+// distance to the outside of the scanned block.  The few
 // queries that stay undecided (far from every target point) are finished by a brute-force pass, one warp per query.  The float
 // distances are bit-identical to the CPU path; the double sum is a fixed-shape reduction (run-to-run deterministic).
 #include <cfloat>
@@ -21,6 +23,15 @@ constexpr int kFitMaxRing = 3;
 __device__ __forceinline__ float dist2(float qx, float qy, float qz, const float4& p) {
   const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
   return (dx * dx + dy * dy) + dz * dz;
+}
+
+// target points copied into cell order (one contiguous run per cell): the search then streams a cell instead of gathering it
+__global__ void __launch_bounds__(kFitThreads) fitness_gather_kernel(const float4* __restrict__ tgt, const int* __restrict__ sorted_idx,
+                                                                     const int* __restrict__ cell_start, const GridParams* __restrict__ gp,
+                                                                     float4* __restrict__ out) {
+  const int k = blockIdx.x * kFitThreads + threadIdx.x;
+  if (gp->status != 0 || gp->n_cells <= 0) return;
+  if (k < cell_start[gp->n_cells]) out[k] = tgt[sorted_idx[k]];
 }
 
 __global__ void __launch_bounds__(kFitThreads) fitness_search_kernel(FitnessArgs a) {
@@ -39,30 +50,40 @@ __global__ void __launch_bounds__(kFitThreads) fitness_search_kernel(FitnessArgs
     const int cx = (int)floorf(qx * inv) - gp->min_b[0], cy = (int)floorf(qy * inv) - gp->min_b[1], cz = (int)floorf(qz * inv) - gp->min_b[2];
     const int d0 = gp->div_b[0], d1 = gp->div_b[1], d2 = gp->div_b[2];
     const int m1 = gp->mul[1], m2 = gp->mul[2];
-    for (int r = 1; r <= kFitMaxRing && !decided; r++) {
+    // position of the query inside its own cell, in metres from the cell's low corner: the distance to a neighbouring cell's box
+    // is a lower bound for every point in it, so most of the 26 neighbours are skipped once the own cell has produced a hit
+    const float fx = qx - (float)(cx + gp->min_b[0]) * leaf, fy = qy - (float)(cy + gp->min_b[1]) * leaf, fz = qz - (float)(cz + gp->min_b[2]) * leaf;
+    const float slack = 1e-3f * leaf;        // rounding of the binning at cell faces
+    for (int r = 0; r <= kFitMaxRing && !decided; r++) {
       for (int oz = -r; oz <= r; oz++) {
         const int z = cz + oz;
         if ((unsigned)z >= (unsigned)d2) continue;
+        const float gz = oz > 0 ? (float)oz * leaf - fz : (oz < 0 ? fz - (float)(oz + 1) * leaf : 0.0f);
         for (int oy = -r; oy <= r; oy++) {
           const int y = cy + oy;
           if ((unsigned)y >= (unsigned)d1) continue;
+          const float gy = oy > 0 ? (float)oy * leaf - fy : (oy < 0 ? fy - (float)(oy + 1) * leaf : 0.0f);
           const bool face = (oz == -r || oz == r || oy == -r || oy == r);
           // inside the shell only the two end cells of the x run are new; on a face the whole run is
-          const int step = (face || r == 1) ? 1 : 2 * r;
+          const int step = (face || r <= 1) ? 1 : 2 * r;
           for (int ox = -r; ox <= r; ox += step) {
             const int x = cx + ox;
             if ((unsigned)x >= (unsigned)d0) continue;
+            if (r == 1 && ox == 0 && oy == 0 && oz == 0) continue;      // the own cell was shell 0
+            const float gx = ox > 0 ? (float)ox * leaf - fx : (ox < 0 ? fx - (float)(ox + 1) * leaf : 0.0f);
+            const float hx = fmaxf(gx - slack, 0.0f), hy = fmaxf(gy - slack, 0.0f), hz = fmaxf(gz - slack, 0.0f);
+            if (hx * hx + hy * hy + hz * hz >= best) continue;          // nothing in that cell can beat the current best
             const int v = __ldg(a.grid + (x + y * m1 + z * m2));
             if (v == -1) continue;
             const int rec = grid_decode_any(v);
             const int k0 = __ldg(a.cell_start + rec), k1 = __ldg(a.cell_start + rec + 1);
-            for (int k = k0; k < k1; k++) best = fminf(best, dist2(qx, qy, qz, __ldg(a.tgt + __ldg(a.sorted_idx + k))));
+            for (int k = k0; k < k1; k++) best = fminf(best, dist2(qx, qy, qz, __ldg(a.tgt_sorted + k)));
           }
         }
       }
       // every target point outside the (2r+1)^3 block is at least r cells away (minus the rounding of the binning)
       const float safe = (float)r * leaf * 0.999f;
-      decided = best <= safe * safe;
+      decided = r >= 1 && best <= safe * safe;
     }
   }
   if (decided) a.best[i] = best;
@@ -119,6 +140,13 @@ __global__ void __launch_bounds__(kFitThreads) fitness_reduce_kernel(FitnessArgs
   a.out[0] = cnt > 0.0 ? sum / cnt : DBL_MAX;
   a.out[1] = cnt;
   *a.ticket = 0;
+}
+
+int launch_fitness_gather(cudaStream_t st, const float4* tgt, int n_tgt, const int* sorted_idx, const int* cell_start, const GridParams* gp, float4* out) {
+  if (n_tgt <= 0) return LVS_OK;
+  fitness_gather_kernel<<<(n_tgt + kFitThreads - 1) / kFitThreads, kFitThreads, 0, st>>>(tgt, sorted_idx, cell_start, gp, out);
+  CUDA_TRY(cudaGetLastError());
+  return LVS_OK;
 }
 
 int launch_fitness(cudaStream_t st, const FitnessArgs& a, int* launches) {

@@ -56,6 +56,8 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   double* d_icov64 = nullptr;            // [n_cells][9] double inverse covariance
   int* d_sorted_idx = nullptr;           // target point indices grouped by cell (stable: input order inside a cell), cell_capacity
   int* d_cell_start = nullptr;           // [n_cells + 1] first position of every cell in d_sorted_idx
+  float4* d_sorted_pts = nullptr;        // target points in cell order, filled lazily by the first fitness-score query of a build
+  bool sorted_pts_valid = false;
   size_t cell_capacity = 0;
   int n_cells = 0;
   int launches_last_build = 0;
@@ -134,10 +136,12 @@ struct FitnessArgs {
   const float4* tgt; int n_tgt;
   const int* grid; const GridParams* gp;
   const int* cell_start; const int* sorted_idx;
+  const float4* tgt_sorted;          // target points in cell order (TargetGrid::d_sorted_pts)
   const float* T16;
   double max_range;
   float* best; int* list; double* partials; unsigned int* ticket; double* out;   // out[0] = score, out[1] = correspondences
 };
 int launch_fitness(cudaStream_t st, const FitnessArgs& a, int* launches);
+int launch_fitness_gather(cudaStream_t st, const float4* tgt, int n_tgt, const int* sorted_idx, const int* cell_start, const GridParams* gp, float4* out);
 
 }  // namespace lvs

@@ -637,6 +637,7 @@ int TargetGrid::enqueue_many(cudaStream_t st, int count, TargetGrid* const* grid
       g.launches_last_build = k == 0 ? (max_prev > 0 ? 1 : 0) + 2 + passes * 4 + 1 + 2 + 1 + 2 : 0;   // the batch's launches, booked once
       g.prev_points = g.n_points;
       g.pending = true;
+      g.sorted_pts_valid = false;
     }
   }
   return LVS_OK;
@@ -690,6 +691,7 @@ int TargetGrid::prepare(cudaStream_t st, const float4* d_pts, int n, const lvs_n
     CUDA_TRY(cudaMalloc(&d_icov64, cap * 9 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&d_sorted_idx, cap * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_cell_start, (cap + 2) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_sorted_pts, cap * sizeof(float4)));
     cell_capacity = cap;
   }
   if (!d_grid) {
@@ -760,7 +762,8 @@ void TargetGrid::free_cells() {
   if (d_icov64) cudaFree(d_icov64);
   if (d_sorted_idx) cudaFree(d_sorted_idx);
   if (d_cell_start) cudaFree(d_cell_start);
-  d_icov64 = nullptr; d_sorted_idx = nullptr; d_cell_start = nullptr;
+  if (d_sorted_pts) cudaFree(d_sorted_pts);
+  d_icov64 = nullptr; d_sorted_idx = nullptr; d_cell_start = nullptr; d_sorted_pts = nullptr; sorted_pts_valid = false;
   d_recs = nullptr; d_centroids = nullptr; d_cell_keys = nullptr; d_cell_npts = nullptr; d_cell_evals = nullptr;
   cell_capacity = 0;
 }
