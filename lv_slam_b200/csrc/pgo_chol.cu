@@ -218,7 +218,6 @@ constexpr int kCholThreads = 256;
 constexpr int kCholMaxTeam = 1024;      // CTAs that may share one front (bounded by the cooperative grid)
 constexpr int kCholBigFront = 192;
 constexpr int kNB = 24;                 // pivot columns per panel
-static_assert(true, "");
 constexpr int kTile = 96;               // trailing-update tile (16 x 16 threads, 6 x 6 outputs each)      // fronts with F above this go to the team kernel
 
 struct CholView {
@@ -483,9 +482,10 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
 }
 
 // Backward substitution, one CTA per front of the level (levels top-down): x_piv = L_D^-T (y - B^T x_R), in panels of kNB pivot
-// columns from the last one up.  Left-looking: the panel's right-hand side takes the dot products of its columns with everything
-// already known below it (later pivots of this front and the ancestors' x_R) — columns are contiguous in memory, so a warp streams
-// a column with eight loads in flight — then warp 0 solves the 24 x 24 triangle (lane m keeps the running sum of its own row).
+// columns from the last one up.  First the ancestors' x_R is folded into the right-hand side (a warp streams a pivot column,
+// contiguous in memory, with eight loads in flight); then, per panel, warp 0 solves the 24 x 24 triangle (lane m keeps the
+// running sum of its own row) and every earlier pivot takes the panel's contribution (right-looking: a thread streams the 24
+// entries of its own column).
 __global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V, int level_begin) {
   extern __shared__ double s_dyn[];                 // xs[F - 1]: y, overwritten by x panel by panel, followed by x_R
   __shared__ double s_D[kNB][kNB + 1], s_dot[kNB];
