@@ -30,7 +30,7 @@ UNIT = "aligns/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="scan pairs per step per GPU")
@@ -70,16 +70,25 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi needs a moment to come up: wait for its first line so that the samples that follow fall INSIDE the timed region
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 2.0:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.01)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
-        time.sleep(0.12)
+        time.sleep(0.03)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -240,10 +249,10 @@ def main_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches, kern_ms, kern_launches, n_eval_total, res = timed(dev_src, dev_tgt, args.steps, 1, B)
-    clocks = sampler.stop()
     xfer0 = nb.transfer_bytes()
     ms_e2e, _, _, _, _, res_e2e = timed(pin_src, pin_tgt, args.steps, 0, g_e2e)
     xfer1 = nb.transfer_bytes()
+    clocks = sampler.stop()                      # sampled every 20 ms across both timed regions
     h2d_bytes, d2h_bytes = (xfer1[0] - xfer0[0]) // args.steps, (xfer1[1] - xfer0[1]) // args.steps
 
     # sanity: the aligns registered the stream (pose error against the generator's ground truth)

@@ -187,3 +187,40 @@ def test_graph_slam_mirror_and_edge_cases(tmp_path, sphere_small):
     assert dt <= 1e-6
     with pytest.raises(ValueError):
         L.GraphSLAM("no_such_solver")
+
+
+def test_direct_solver_at_baseline_size():
+    """BASELINE config 4 (5 000 vertices / 19 599 edges): too big for the CPU oracle inside a test, so size-independent properties of
+    the sparse Cholesky instead — the residual of (H + lambda I) x = b evaluated independently on the host from the assembled
+    blocks, agreement with the iterative kind run to round-off, and run-to-run bit-identical results."""
+    import scipy.sparse as sp
+    import lv_slam_b200 as L
+    g = G.sphere(100, 50, seed=7)
+    pg = L.PoseGraph(0)
+    pg.set_graph(g["poses7"], g["ij"], g["meas7"], g["info21"], g["huber"])
+    info = pg.chol_info()
+    assert info["fronts"] > 1000 and info["levels"] < 64 and info["nnz_l_blocks"] >= 5000 + 19599
+    lin = pg.linearize()
+    n = lin["Hd"].shape[0]
+    lam = 1e-5 * np.max(np.abs(np.einsum("nii->ni", lin["Hd"])))
+    # H as a scipy BSR matrix from the diagonal and the unique upper off-diagonal blocks
+    rows = np.concatenate([np.arange(n), lin["off"][:, 0], lin["off"][:, 1]])
+    cols = np.concatenate([np.arange(n), lin["off"][:, 1], lin["off"][:, 0]])
+    data = np.concatenate([lin["Hd"] + lam * np.eye(6), lin["Ho"], lin["Ho"].transpose(0, 2, 1)])
+    order = np.lexsort((cols, rows))
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))])
+    H = sp.bsr_matrix((data[order], cols[order], indptr), shape=(6 * n, 6 * n))
+    x, _ = pg.solve(lam, 0.0)
+    r = H @ x - lin["b"]
+    assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(lin["b"])
+    x2, _ = pg.solve(lam, 0.0)
+    assert np.array_equal(x, x2)                                   # deterministic: no atomics anywhere in the factorisation
+    pc = L.PoseGraph(2)                                            # the PCG kind pushed to round-off solves the same system
+    pc.set_graph(g["poses7"], g["ij"], g["meas7"], g["info21"], g["huber"])
+    pc.linearize()
+    xp, it = pc.solve(lam, 1e-26)
+    assert it > 100 and _rel(xp, x) < 1e-7
+    # and the whole LM run with the direct solver reaches the same optimum as with PCG
+    s0 = pg.optimize(100)
+    s2 = pc.optimize(200)
+    assert s0["iterations"] > 0 and abs(s0["chi2_after"] - s2["chi2_after"]) <= 1e-3 * s2["chi2_after"]

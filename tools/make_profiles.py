@@ -42,7 +42,7 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
             ur, uw = rows[1][h.index('dram__bytes_read.sum')], rows[1][h.index('dram__bytes_write.sum')]
             mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             json.dump({"kernel": rows[2][h.index('Kernel Name')], "dram_bytes_per_launch": rd * mul[ur] + wr * mul[uw],
-                       "duration_us_under_ncu": float(rows[2][h.index('gpu__time_duration.sum')]), "source": "%s/%s (ncu --set full, first captured launch)" % (name, rep)},
+                       "duration_us_under_ncu": float(rows[2][h.index('gpu__time_duration.sum')]), "grid_size": rows[2][h.index('launch__grid_size')], "source": "%s/%s (ncu --set full, first captured launch)" % (name, rep)},
                       open(os.path.join(dst, base + "_traffic.json"), "w"))
             if base == "ndt_eval": shutil.copy(os.path.join(dst, base + "_traffic.json"), os.path.join("profiles", "ndt_eval_traffic.json"))   # what bench.py reports
         except (ValueError, KeyError): pass
