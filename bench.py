@@ -195,25 +195,30 @@ def main_ours(args):
     vp = variant_params(args.variant)
     stream = torch.cuda.Stream()
     nb = L.NdtBatch(len(keys), B, device=local_rank, stream=stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64, **vp)
-    src_slots = list(range(B))
+    from lv_slam_b200.ndt import CloudBatch, pack_guesses
+    src_slots = np.arange(B, dtype=np.int32)
     tgt_all = list(range(len(keys)))
-    tgt_slots = [key_slot[k] for _, k, _ in plan]
-    guesses = [g for _, _, g in plan]
+    tgt_slots = np.array([key_slot[k] for _, k, _ in plan], dtype=np.int32)
+    guesses = pack_guesses([g for _, _, g in plan])          # [B, 16] column-major, the layout the C-ABI takes
+    src_slot_list = list(range(B))
 
     # resident copies (value) and pinned host copies (e2e)
     dev_src = [torch.from_numpy(scans[f]).cuda() for f, _, _ in plan]
     dev_tgt = [torch.from_numpy(scans[k]).cuda() for k in keys]
     pin_src = [torch.from_numpy(scans[f]).pin_memory() for f, _, _ in plan]
     pin_tgt = [torch.from_numpy(scans[k]).pin_memory() for k in keys]
+    # the buffers are the same every step: marshal their pointers once (what a C++ caller's std::vector<const float*> is)
+    dev_src, dev_tgt, pin_src, pin_tgt = CloudBatch(dev_src), CloudBatch(dev_tgt), CloudBatch(pin_src), CloudBatch(pin_tgt)
 
     def step(src, tgt, group):
         """One pass over the batch.  Host clouds are queued on the library's upload stream in the order they are needed and
         the aligns run in groups of `group` pairs, so the copies of later scans overlap the aligns of earlier ones."""
         nb.set_targets(tgt_all, tgt)
-        nb.set_sources(src_slots, src)
-        out, stats = [], {"deriv_kernel_ms": 0.0, "deriv_launches": 0}
+        nb.set_sources(src_slot_list, src)
+        out, stats = None, {"deriv_kernel_ms": 0.0, "deriv_launches": 0}
         for a in range(0, B, group):
-            out += nb.align(src_slots[a:a + group], tgt_slots[a:a + group], guesses[a:a + group])
+            r = nb.align(src_slots[a:a + group], tgt_slots[a:a + group], guesses[a:a + group])
+            out = r if out is None else out + r
             st = nb.last_stats()
             stats["deriv_kernel_ms"] += st["deriv_kernel_ms"]; stats["deriv_launches"] += st["deriv_launches"]
         return out, stats
@@ -235,7 +240,7 @@ def main_ours(args):
             for _ in range(steps):
                 res, st = step(src, tgt, group)
                 kern_ms += st["deriv_kernel_ms"]; kern_launches += st["deriv_launches"]
-                n_eval_total += sum(r["n_eval"] for r in res)
+                n_eval_total += int(res.n_eval.sum())
             ev1.record(stream)
         barrier()
         ms = D.max_over_ranks(ev0.elapsed_time(ev1), world, "cuda")

@@ -46,6 +46,78 @@ def _params(**kw):
     return p
 
 
+class CloudBatch:
+    """Clouds marshalled once for the plural setters (pointers, counts, stride, residency): a caller that hands the same buffers to
+    set_sources / set_targets step after step keeps the per-call host work to the C call itself."""
+
+    def __init__(self, clouds):
+        args = [_cloud_args(c) for c in clouds]
+        self.n = len(args)
+        self.stride, self.on_device = (args[0][2], args[0][3]) if args else (12, 0)
+        if any(a[2] != self.stride or a[3] != self.on_device for a in args):
+            raise ValueError("set_sources / set_targets need clouds of one stride and one residency")
+        self.ptrs = (ctypes.c_void_p * max(self.n, 1))(*[a[0] for a in args])
+        self.counts = (ctypes.c_size_t * max(self.n, 1))(*[a[1] for a in args])
+        self._keep = [a[4] for a in args]
+
+
+_RESULT_DTYPE = np.dtype({"names": ["final_transformation", "converged", "iterations", "trans_probability", "n_eval", "n_hess", "score"],
+                          "formats": [(np.float32, 16), np.int32, np.int32, np.float64, np.int32, np.int32, np.float64],
+                          "offsets": [C.NdtResult.final_transformation.offset, C.NdtResult.converged.offset, C.NdtResult.iterations.offset,
+                                      C.NdtResult.trans_probability.offset, C.NdtResult.n_eval.offset, C.NdtResult.n_hess.offset, C.NdtResult.score.offset],
+                          "itemsize": ctypes.sizeof(C.NdtResult)})
+
+
+class AlignResults:
+    """The lvs_ndt_result records of one batched align as numpy views (no per-pair Python objects on the hot path); indexing or
+    iterating yields the per-pair dicts the single-object API returns."""
+
+    def __init__(self, raw, n):
+        self._raw = raw
+        self._a = np.frombuffer(raw, dtype=_RESULT_DTYPE, count=n) if n else np.zeros(0, _RESULT_DTYPE)
+
+    def __len__(self):
+        return self._a.shape[0]
+
+    @property
+    def finals(self):
+        """[n, 4, 4] float32 final transformations (row-major views of the column-major records)"""
+        return self._a["final_transformation"].reshape(-1, 4, 4).transpose(0, 2, 1)
+
+    @property
+    def n_eval(self):
+        return self._a["n_eval"]
+
+    @property
+    def iterations(self):
+        return self._a["iterations"]
+
+    @property
+    def converged(self):
+        return self._a["converged"] != 0
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        r = self._a[i]
+        return dict(final=r["final_transformation"].reshape(4, 4).T.copy(), iterations=int(r["iterations"]), converged=bool(r["converged"]),
+                    trans_probability=float(r["trans_probability"]), n_eval=int(r["n_eval"]), n_hess=int(r["n_hess"]), score=float(r["score"]))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __add__(self, other):                      # results of consecutive align groups concatenate
+        out = AlignResults.__new__(AlignResults)
+        out._raw = (self._raw, getattr(other, "_raw", None))
+        out._a = np.concatenate([self._a, other._a]) if len(other) else self._a
+        return out
+
+
+def pack_guesses(guesses):
+    """[n, 16] float32 column-major guesses, the layout lvs_ndt_batch_align takes"""
+    return np.ascontiguousarray(np.stack([_colmajor16(G) for G in guesses])) if len(guesses) else np.zeros((0, 16), np.float32)
+
+
 class NormalDistributionsTransform:
     """One registration object.  ``variant`` selects pclomp (LVS_NDT_OMP) or pclpca (LVS_NDT_PCA)."""
 
@@ -255,18 +327,11 @@ class NdtBatch:
         C.check(self._L.lvs_ndt_batch_set_source(self._h, slot, ptr, n, stride, dev))
 
     def _set_many(self, fn, slots, clouds):
-        """Plural setter: every cloud must share stride and residency (one C call, one repack launch for resident scans)."""
-        n = len(slots)
-        if n == 0:
+        cb = clouds if isinstance(clouds, CloudBatch) else CloudBatch(clouds)
+        if cb.n == 0:
             return
-        args = [_cloud_args(c) for c in clouds]
-        stride, dev = args[0][2], args[0][3]
-        if any(a[2] != stride or a[3] != dev for a in args):
-            raise ValueError("set_sources / set_targets need clouds of one stride and one residency")
-        sl = (ctypes.c_int32 * n)(*slots)
-        ptrs = (ctypes.c_void_p * n)(*[a[0] for a in args])
-        cnt = (ctypes.c_size_t * n)(*[a[1] for a in args])
-        C.check(fn(self._h, n, sl, ptrs, cnt, stride, dev))
+        sl = slots if isinstance(slots, ctypes.Array) else (ctypes.c_int32 * cb.n)(*slots)
+        C.check(fn(self._h, cb.n, sl, cb.ptrs, cb.counts, cb.stride, cb.on_device))
 
     def set_targets(self, slots, clouds):
         self._set_many(self._L.lvs_ndt_batch_set_targets, slots, clouds)
@@ -286,15 +351,19 @@ class NdtBatch:
         C.check(self._L.lvs_ndt_batch_wait_uploads(self._h))
 
     def align(self, source_slots, target_slots, guesses):
+        """guesses: a list of 4x4 matrices, or an [n, 16] float32 array from pack_guesses.  Returns AlignResults."""
         s = np.ascontiguousarray(source_slots, dtype=np.int32)
         t = np.ascontiguousarray(target_slots, dtype=np.int32)
         n = s.shape[0]
-        g = np.ascontiguousarray(np.stack([_colmajor16(G) for G in guesses]) if n else np.zeros((0, 16), np.float32))
+        if isinstance(guesses, np.ndarray) and guesses.dtype == np.float32 and guesses.ndim == 2 and guesses.shape[1] == 16:
+            g = np.ascontiguousarray(guesses)
+        else:
+            g = pack_guesses(guesses)
+        if g.shape[0] != n or t.shape[0] != n:
+            raise ValueError("source slots, target slots and guesses must have one length")
         res = (C.NdtResult * max(n, 1))()
         C.check(self._L.lvs_ndt_batch_align(self._h, n, s.ctypes.data, t.ctypes.data, g.ctypes.data, res))
-        return [dict(final=_from_colmajor16(np.frombuffer(res[i].final_transformation, dtype=np.float32)), iterations=int(res[i].iterations),
-                     converged=bool(res[i].converged), trans_probability=float(res[i].trans_probability), n_eval=int(res[i].n_eval),
-                     n_hess=int(res[i].n_hess), score=float(res[i].score)) for i in range(n)]
+        return AlignResults(res, n)
 
     def fitness_score(self, source_slot, target_slot, T, max_range=np.finfo(np.float64).max):
         """getFitnessScore of one (source, target) pair under T -> (score, correspondences)"""

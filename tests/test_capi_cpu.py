@@ -211,3 +211,29 @@ def test_direct_solver_symbolic_analysis_on_the_host():
     assert st["nnz_l_blocks"] == 7 and st["fronts"] == 7 and st["levels"] == 1
     with pytest.raises(Exception):
         chol_analyze(5, np.array([(3, 1)], np.int32))     # not (row < col)
+
+
+def test_host_marshalling_helpers():
+    """CloudBatch / pack_guesses / AlignResults: the per-call host work of the batched API is a C call over prepared arrays, and the
+    result records are numpy views of the C structs (no device needed)."""
+    from lv_slam_b200 import _capi as C
+    from lv_slam_b200.ndt import AlignResults, CloudBatch, pack_guesses
+    clouds = [np.zeros((5, 3), np.float32), np.ones((7, 3), np.float32)]
+    cb = CloudBatch(clouds)
+    assert cb.n == 2 and cb.stride == 12 and cb.on_device == 0 and list(cb.counts) == [5, 7] and cb.ptrs[1] == clouds[1].ctypes.data
+    wide = np.zeros((4, 8), np.float32)
+    assert CloudBatch([wide[:, :3]]).stride == 32
+    with pytest.raises(ValueError):
+        CloudBatch([clouds[0], wide[:, :3]])
+    T = np.arange(16, dtype=np.float32).reshape(4, 4)
+    g = pack_guesses([T, np.eye(4)])
+    assert g.shape == (2, 16) and g.dtype == np.float32 and g[0, 1] == T[1, 0] and g[0, 12] == T[0, 3]      # column-major
+    raw = (C.NdtResult * 2)()
+    for i in range(2):
+        raw[i].iterations, raw[i].n_eval, raw[i].converged, raw[i].score = 5 + i, 1 + i, i, 1.5 * i
+        for k in range(16):
+            raw[i].final_transformation[k] = k + 100 * i
+    r = AlignResults(raw, 2)
+    assert len(r) == 2 and r[1]["iterations"] == 6 and r[1]["final"][0, 3] == 112.0 and r[0]["converged"] is False
+    assert r.n_eval.tolist() == [1, 2] and r.finals.shape == (2, 4, 4) and r.finals[1][3, 0] == 103.0
+    assert [x["score"] for x in r] == [0.0, 1.5] and len(r + r) == 4 and (r + r)[3]["n_eval"] == 2
