@@ -161,6 +161,13 @@ int lvs_ndt_batch_set_sources(lvs_ndt_batch_t* b, int n, const int32_t* slots, c
 int lvs_ndt_batch_wait_uploads(lvs_ndt_batch_t* b);
 int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot,
                         const float* guesses16 /* n_pairs x 16 */, lvs_ndt_result* results /* n_pairs */);
+/* The same align in two halves, for callers that stream: align_begin uploads the pair states and queues the evaluation launches of
+ * a typical align without waiting (the Newton / More-Thuente state machine runs on the device); until align_end collects the
+ * results the host is free to hand the NEXT batch to set_target(s) / set_source(s) - in other slots than the pairs in flight use -
+ * so that its copies and voxelisations overlap the aligns.  One align in flight per object; every other entry point that
+ * evaluates (align, fitness score, taps) returns LVS_ERR_INVALID_ARG in between.  lvs_ndt_batch_align = begin + end. */
+int lvs_ndt_batch_align_begin(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot, const float* guesses16);
+int lvs_ndt_batch_align_end(lvs_ndt_batch_t* b, lvs_ndt_result* results /* n_pairs of the begin call */);
 /* Device time in ms of the last batch_align and the number of kernel launches it issued. */
 int lvs_ndt_batch_last_stats(lvs_ndt_batch_t* b, double* device_ms, int* launches, double* deriv_kernel_ms, int* deriv_launches);
 /* Measurement controls.  profiling != 0 brackets every evaluation launch with a CUDA event pair so that

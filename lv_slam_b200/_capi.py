@@ -82,6 +82,7 @@ def lib():
             "lvs_pgo_system_size": [vp, vp, vp], "lvs_pgo_linearize": [vp, vp, vp, vp, vp],
             "lvs_pgo_solve": [vp, ctypes.c_double, ctypes.c_double, i32, vp, vp],
             "lvs_ndt_fitness_score": [vp, vp, ctypes.c_double, vp, vp], "lvs_ndt_batch_fitness_score": [vp, i32, i32, vp, ctypes.c_double, vp, vp],
+            "lvs_ndt_batch_align_begin": [vp, i32, vp, vp, vp], "lvs_ndt_batch_align_end": [vp, vp],
             "lvs_prefilter_create": [i32, vp, vp], "lvs_prefilter_destroy": [vp],
             "lvs_prefilter_run": [vp, vp, sz, sz, i32, i32, ctypes.c_double, ctypes.c_double, i32, ctypes.c_float, vp, sz, i32, vp, vp],
             "lvs_pgo_chol_analyze": [i32, i32, vp, vp, vp], "lvs_pgo_chol_info": [vp, vp],

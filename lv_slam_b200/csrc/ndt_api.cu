@@ -87,8 +87,10 @@ constexpr int kUploadLanes = 2;
 struct StageBuf {
   float* d = nullptr;
   size_t cap = 0;
-  cudaEvent_t free_ev = nullptr;     // = the `ready` event of the slot this buffer was last used for (owned by the slot): recorded
-                                     // after the repack kernel that read the buffer; a later re-record of that event only delays re-use
+  cudaEvent_t copied_ev = nullptr;   // end of the host-to-device copy into this buffer (copy stream)
+  cudaEvent_t free_ev = nullptr;     // the buffer's own event, recorded after the repack kernel that read it (a slot's `ready` event
+                                     // would not do: it is re-recorded by the slot's NEXT upload, which may already be queued when
+                                     // batches are pipelined, and the buffer would look busy until that one completes)
   bool in_flight = false;
 };
 
@@ -98,8 +100,16 @@ constexpr int kMaxEvents = 2048;
 
 using namespace lvs;
 
+struct PendingAlign {          // the align between align_begin and align_end
+  bool active = false;
+  int n_pairs = 0, launches = 0, max_launches = 0;
+  bool need_cold = false, prof = false;
+  EvalLaunch L;
+};
+
 struct lvs_ndt_batch {
   int device = 0;
+  PendingAlign pend;
   cudaStream_t st = nullptr;
   bool own_stream = false;
   lvs_ndt_params prm{};
@@ -113,7 +123,7 @@ struct lvs_ndt_batch {
   std::vector<TargetBuildState> tstate;
   std::vector<CloudSlot> target_pts, sources;
   // upload path: its own stream, a ring of staging buffers, and one more staging buffer for results on the compute stream
-  cudaStream_t up[kUploadLanes] = {};   // clouds alternate between the lanes: the repack of one overlaps the copy of the next
+  cudaStream_t up[kUploadLanes] = {};   // [0] host-to-device copies only, [1] the repack kernels (each waits for its own copy)
   std::vector<StageBuf> ring;
   size_t ring_bytes = 0;
   int ring_next = 0;
@@ -255,15 +265,24 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
     sb.cap = cap;
     b->ring_bytes += cap;
   }
-  cudaStream_t up = b->up[slot.up_lane];
-  if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(up, slot.used, 0)); slot.used_pending = false; }
-  CUDA_TRY(cudaMemcpyAsync(sb.d, xyz, bytes, cudaMemcpyHostToDevice, up));
+  // Copies and repacks live on different streams: the copy stream carries nothing but DMA transfers, so it never waits for an SM
+  // (while a batch is being aligned the evaluation kernels hold every SM for the length of a launch, and a repack kernel queued
+  // between two copies would stall all the copies behind it); the repack of a cloud waits for its own copy only.
+  cudaStream_t cp = b->up[0], pk = b->up[1];
+  if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(pk, slot.used, 0)); slot.used_pending = false; }
+  CUDA_TRY(cudaMemcpyAsync(sb.d, xyz, bytes, cudaMemcpyHostToDevice, cp));
   b->h2d_bytes += (long long)bytes;
-  int rc = pack_points(up, sb.d, stride_bytes / 4, (int)n, slot.d_pts);
+  if (!sb.free_ev) {
+    CUDA_TRY(cudaEventCreateWithFlags(&sb.free_ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&sb.copied_ev, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventRecord(sb.copied_ev, cp));
+  CUDA_TRY(cudaStreamWaitEvent(pk, sb.copied_ev, 0));
+  int rc = pack_points(pk, sb.d, stride_bytes / 4, (int)n, slot.d_pts);
   b->total_launches++;
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(slot.ready, up));
-  sb.free_ev = slot.ready;
+  CUDA_TRY(cudaEventRecord(slot.ready, pk));
+  CUDA_TRY(cudaEventRecord(sb.free_ev, pk));
   sb.in_flight = true;
   slot.ready_pending = true;
   b->uploads_in_flight = true;
@@ -385,10 +404,28 @@ static int shard_check(lvs_ndt_batch* b) {
 }
 
 // Runs the evaluation launches of one batch until every pair's state machine reports done.
-static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, const int32_t* tgt_slot, const float* guesses16, lvs_ndt_result* results) {
+// One evaluation launch (plus the cold kernel when reachable) of the align in flight, bracketed by profiling events on request.
+static int align_launch_one(lvs_ndt_batch* b) {
+  PendingAlign& P = b->pend;
+  int rc;
+  const bool ev = P.prof && P.launches < kMaxEvents;
+  if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * P.launches], b->st));
+  P.L.shard.serial = ++b->shard_serial;        // one serial per kernel launch: a pair may be evaluated by both kernels of a step
+  if ((rc = launch_eval(b->st, P.L))) return rc;
+  if (P.need_cold) { P.L.shard.serial = ++b->shard_serial; if ((rc = launch_eval_cold(b->st, P.L))) return rc; }
+  if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * P.launches + 1], b->st));
+  P.launches++;
+  return LVS_OK;
+}
+
+// First half of an align: uploads the pair states and queues the first chunk of evaluation launches (enough for a typical align;
+// finished pairs leave their CTAs at once), then returns without waiting.  The Newton / More-Thuente state machine lives on the
+// device, so nothing else is needed from the host until align_end collects the results.
+static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, const int32_t* tgt_slot, const float* guesses16) {
   int rc = set_device(b);
   if (rc) return rc;
-  if (n_pairs <= 0) return LVS_OK;
+  if (b->pend.active) return fail(LVS_ERR_INVALID_ARG, "an align is already in flight: call align_end first");
+  if (n_pairs <= 0) { b->pend = PendingAlign(); b->pend.active = true; return LVS_OK; }
   int max_src = 0;
   for (int i = 0; i < n_pairs; i++) {
     int s = src_slot[i], t = tgt_slot[i];
@@ -411,7 +448,9 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
   CUDA_TRY(cudaMemcpyAsync(b->d_states, b->h_states, n_pairs * sizeof(AlignState), cudaMemcpyHostToDevice, b->st));
   b->h2d_bytes += (long long)n_pairs * (sizeof(PairDesc) + sizeof(AlignState));
   CUDA_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int), b->st));
-  EvalLaunch L;
+  PendingAlign& P = b->pend;
+  P = PendingAlign();
+  EvalLaunch& L = P.L;
   L.d_pairs = b->d_pairs; L.d_states = b->d_states; L.d_trace = b->trace_on ? b->d_trace : nullptr;
   L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
   L.n_pairs = n_pairs; L.blocks_per_pair = bpp; L.advance = 1;
@@ -419,37 +458,49 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
   if (b->shard_on && n_pairs > b->shard_cap) return fail(LVS_ERR_INVALID_ARG, "%d pairs exceed the sharded batch's max_pairs %d", n_pairs, b->shard_cap);
   shard_view(b, L);
   // worst case: initial pass + (max_iter + 2) outer iterations of (first + 10 trials + Hessian pass)
-  const int max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
-  int launches = 0;
+  P.max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
+  P.n_pairs = n_pairs;
   *b->h_done = 0;
-  const bool prof = b->profiling != 0;
-  if (prof && (int)b->ev_pool.size() < 2 * kMaxEvents) {
+  P.prof = b->profiling != 0;
+  if (P.prof && (int)b->ev_pool.size() < 2 * kMaxEvents) {
     size_t old = b->ev_pool.size();
     b->ev_pool.resize(2 * kMaxEvents);
     for (size_t k = old; k < b->ev_pool.size(); k++) CUDA_TRY(cudaEventCreate(&b->ev_pool[k]));
   }
   // The radius-search passes are only reachable in KDTREE mode or when the reference's More-Thuente loop can run, i.e.
   // when `interval_converged = (step_max - step_min) > 0` (ndt_omp_impl2.hpp:888) is false.
-  const bool need_cold = b->prm.search_method == LVS_KDTREE || !((b->prm.step_size - b->prm.transformation_epsilon / 2) > 0);
-  int chunk = b->chunk_first;
-  while (launches < max_launches) {
-    for (int k = 0; k < chunk && launches < max_launches; k++) {
-      const bool ev = prof && launches < kMaxEvents;
-      if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * launches], b->st));
-      L.shard.serial = ++b->shard_serial;        // one serial per kernel launch: a pair may be evaluated by both kernels of a step
-      if ((rc = launch_eval(b->st, L))) return rc;
-      if (need_cold) { L.shard.serial = ++b->shard_serial; if ((rc = launch_eval_cold(b->st, L))) return rc; }
-      if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * launches + 1], b->st));
-      launches++;
-    }
+  P.need_cold = b->prm.search_method == LVS_KDTREE || !((b->prm.step_size - b->prm.transformation_epsilon / 2) > 0);
+  for (int k = 0; k < b->chunk_first && P.launches < P.max_launches; k++)
+    if ((rc = align_launch_one(b))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
+  b->d2h_bytes += sizeof(int);
+  if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->st));
+  P.active = true;
+  return LVS_OK;
+}
+
+// Second half: waits for the queued launches, keeps launching in chunks while pairs are still iterating, reads the results back.
+static int align_end(lvs_ndt_batch* b, lvs_ndt_result* results) {
+  int rc = set_device(b);
+  if (rc) return rc;
+  PendingAlign& P = b->pend;
+  if (!P.active) return fail(LVS_ERR_INVALID_ARG, "no align in flight: call align_begin first");
+  P.active = false;
+  const int n_pairs = P.n_pairs;
+  if (n_pairs <= 0) return LVS_OK;
+  const int max_launches = P.max_launches;
+  const bool need_cold = P.need_cold, prof = P.prof;
+  for (;;) {
+    CUDA_TRY(cudaStreamSynchronize(b->st));
+    if ((rc = shard_check(b))) return rc;
+    if (*b->h_done >= n_pairs || P.launches >= max_launches) break;
+    for (int k = 0; k < b->chunk_next && P.launches < max_launches; k++)
+      if ((rc = align_launch_one(b))) return rc;
     CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
     b->d2h_bytes += sizeof(int);
     if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->st));
-    CUDA_TRY(cudaStreamSynchronize(b->st));
-    if ((rc = shard_check(b))) return rc;
-    if (*b->h_done >= n_pairs) break;
-    chunk = b->chunk_next;
   }
+  const int launches = P.launches;
   CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, n_pairs * sizeof(AlignState), cudaMemcpyDeviceToHost, b->st));
   b->d2h_bytes += (long long)n_pairs * sizeof(AlignState);
   CUDA_TRY(cudaEventRecord(b->ev_end, b->st));
@@ -490,10 +541,17 @@ static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, con
   return LVS_OK;
 }
 
+static int run_align(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, const int32_t* tgt_slot, const float* guesses16, lvs_ndt_result* results) {
+  int rc = align_begin(b, n_pairs, src_slot, tgt_slot, guesses16);
+  if (rc) return rc;          // begin raises `active` only when everything is queued
+  return align_end(b, results);
+}
+
 // Tap: one evaluation of pair 0 = (source 0, target 0) with an explicit state.
 static int run_tap(lvs_ndt_batch* b, int kind, const double p[6], const float* T16, double* score, double* g, double* H36) {
   int rc = set_device(b);
   if (rc) return rc;
+  if (b->pend.active) return fail(LVS_ERR_INVALID_ARG, "an align is in flight: call align_end first");
   if (!b->target_pts[0].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[0].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
   if ((rc = wait_all_uploads(b))) return rc;
@@ -791,8 +849,11 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
       if (c.ready) cudaEventDestroy(c.ready);
       if (c.used) cudaEventDestroy(c.used);
     }
-  for (auto& sb : b->ring)
+  for (auto& sb : b->ring) {
     if (sb.d) cudaFree(sb.d);
+    if (sb.free_ev) cudaEventDestroy(sb.free_ev);
+    if (sb.copied_ev) cudaEventDestroy(sb.copied_ev);
+  }
   for (int r = 0; r < (int)b->peer_ptrs.size(); r++)
     if (b->peer_ptrs[r] && b->peer_ptrs[r] != b->d_mail) cudaIpcCloseMemHandle(b->peer_ptrs[r]);
   if (b->d_mail) cudaFree(b->d_mail);
@@ -865,6 +926,17 @@ int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_s
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   if (n_pairs < 0 || (n_pairs > 0 && (!source_slot || !target_slot || !guesses16 || !results))) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
   return run_align(b, n_pairs, source_slot, target_slot, guesses16, results);
+}
+
+int lvs_ndt_batch_align_begin(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot, const float* guesses16) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (n_pairs < 0 || (n_pairs > 0 && (!source_slot || !target_slot || !guesses16))) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  return align_begin(b, n_pairs, source_slot, target_slot, guesses16);
+}
+
+int lvs_ndt_batch_align_end(lvs_ndt_batch_t* b, lvs_ndt_result* results) {
+  if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  return align_end(b, results);
 }
 
 int lvs_ndt_batch_last_stats(lvs_ndt_batch_t* b, double* device_ms, int* launches, double* deriv_kernel_ms, int* deriv_launches) {
@@ -1118,6 +1190,7 @@ static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const flo
   if (!b->target_pts[tgt_slot].set) return fail(LVS_ERR_NO_TARGET, "setInputTarget not called");
   if (!b->sources[src_slot].set) return fail(LVS_ERR_NO_SOURCE, "setInputSource not called");
   if (b->shard_on) return fail(LVS_ERR_INVALID_ARG, "getFitnessScore is not available on a point-sharded object");
+  if (b->pend.active) return fail(LVS_ERR_INVALID_ARG, "an align is in flight: call align_end first");
   if ((rc = wait_all_uploads(b))) return rc;
   if ((rc = finish_target(b, tgt_slot))) return rc;
   const CloudSlot& src = b->sources[src_slot];

@@ -365,6 +365,25 @@ class NdtBatch:
         C.check(self._L.lvs_ndt_batch_align(self._h, n, s.ctypes.data, t.ctypes.data, g.ctypes.data, res))
         return AlignResults(res, n)
 
+    def align_begin(self, source_slots, target_slots, guesses):
+        """First half of align: queues the work and returns; set_targets / set_sources of OTHER slots may follow before align_end."""
+        s = np.ascontiguousarray(source_slots, dtype=np.int32)
+        t = np.ascontiguousarray(target_slots, dtype=np.int32)
+        n = s.shape[0]
+        g = np.ascontiguousarray(guesses) if (isinstance(guesses, np.ndarray) and guesses.dtype == np.float32 and guesses.ndim == 2 and guesses.shape[1] == 16) \
+            else pack_guesses(guesses)
+        if g.shape[0] != n or t.shape[0] != n:
+            raise ValueError("source slots, target slots and guesses must have one length")
+        C.check(self._L.lvs_ndt_batch_align_begin(self._h, n, s.ctypes.data, t.ctypes.data, g.ctypes.data))
+        self._pending = (n, s, t, g)
+
+    def align_end(self):
+        n = self._pending[0] if getattr(self, "_pending", None) else 0
+        self._pending = None
+        res = (C.NdtResult * max(n, 1))()
+        C.check(self._L.lvs_ndt_batch_align_end(self._h, res))
+        return AlignResults(res, n)
+
     def fitness_score(self, source_slot, target_slot, T, max_range=np.finfo(np.float64).max):
         """getFitnessScore of one (source, target) pair under T -> (score, correspondences)"""
         s, n = ctypes.c_double(0), ctypes.c_int(0)

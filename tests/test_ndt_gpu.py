@@ -486,3 +486,32 @@ def test_prefilter_matches_oracle(scan_pair, small_pair):
     f_t, f_s = pf.filter(small_pair[0]), pf.filter(small_pair[1])
     n.setInputTarget(f_t); n.setInputSource(f_s); o.set_target(f_t); o.set_source(f_s)
     _check_align(n, o, f_s, small_pair[2])
+
+
+def test_align_begin_end_overlaps_the_next_batch(small_pair, scan_pair):
+    """align_begin / align_end: the same results as the one-call align, and the next batch may be staged into other slots while the
+    aligns are in flight (lvs_ndt_batch_align_begin / _end)."""
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    tgt2, src2, guess2, _ = scan_pair
+    b = L.NdtBatch(2, 2, transformation_epsilon=0.01, max_iterations=64)
+    b.set_targets([0], [tgt]); b.set_sources([0], [src])
+    ref = b.align([0], [0], [guess])[0]
+    b.align_begin([0], [0], [guess])
+    b.set_targets([1], [tgt2]); b.set_sources([1], [src2])          # staged while pair (0, 0) is being aligned
+    with pytest.raises(L.LvsError):
+        b.align_begin([1], [1], [guess2])                           # one align in flight per object
+    with pytest.raises(L.LvsError):
+        b.fitness_score(0, 0, truth)
+    got = b.align_end()[0]
+    assert np.array_equal(got["final"], ref["final"]) and got["iterations"] == ref["iterations"] and got["n_eval"] == ref["n_eval"]
+    with pytest.raises(L.LvsError):
+        b.align_end()                                               # nothing in flight
+    one = L.NdtBatch(1, 1, transformation_epsilon=0.01, max_iterations=64)
+    one.set_target(0, tgt2); one.set_source(0, src2)
+    exp = one.align([0], [0], [guess2])[0]
+    b.align_begin([1], [1], [guess2])
+    b.set_targets([0], [tgt]); b.set_sources([0], [src])            # and back again
+    got2 = b.align_end()[0]
+    assert np.array_equal(got2["final"], exp["final"]) and got2["iterations"] == exp["iterations"]
+    assert np.array_equal(b.align([0], [0], [guess])[0]["final"], ref["final"])
