@@ -212,6 +212,15 @@ int lvs_prefilter_run(lvs_prefilter_t* p, const float* xyz, size_t n, size_t str
                       double distance_far, int use_distance_filter, float leaf_size, float* out, size_t capacity, int out_on_device, size_t* n_out,
                       int* flags_out);
 
+/* Window map of the global-graph nodelet (src/global_graph/global_graph_nodelet.cpp:199-243): between two keyframes every scan is
+ * moved into the window's frame with pcl::transformPointCloud and the DOUBLE matrix w_odom^-1 * odom, appended to w_cloud, and the
+ * window is downsampled by a 0.1 m VoxelGrid when the next keyframe is declared.  begin = w_cloud.clear(); add = w_cloud +=
+ * transform(cloud, T16) (T16 column-major double[16], NULL = the window's own first scan, no transform); flush = VoxelGrid(leaf). */
+int lvs_prefilter_accumulate_begin(lvs_prefilter_t* p);
+int lvs_prefilter_accumulate_add(lvs_prefilter_t* p, const float* xyz, size_t n, size_t stride_bytes, int n_fields, int on_device, const double* T16);
+int lvs_prefilter_accumulate_flush(lvs_prefilter_t* p, int n_fields, float leaf_size, float* out, size_t capacity, int out_on_device, size_t* n_out,
+                                   int* flags_out);
+
 /* ===================================================================================================================
  * Pose graph — replaces lv_slam::GraphSLAM::optimize (src/global_graph/graph_slam.cpp:298-331) and the g2o machinery under
  * it for graphs of VertexSE3 / EdgeSE3 with optional Huber kernels (what global_graph builds with GPS/IMU/floor disabled,

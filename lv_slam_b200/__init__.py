@@ -5,4 +5,4 @@ from ._capi import (LVS_DIRECT1, LVS_DIRECT7, LVS_DIRECT26, LVS_KDTREE, LVS_NDT_
 from .ndt import NdtBatch, NormalDistributionsTransform  # noqa: F401
 from .graph_slam import GraphSLAM, PoseGraph  # noqa: F401,E402
 from .information_matrix import InformationMatrixCalculator  # noqa: F401,E402
-from .prefilter import Prefilter  # noqa: F401,E402
+from .prefilter import Prefilter, WindowMap  # noqa: F401,E402

@@ -85,6 +85,8 @@ def lib():
             "lvs_ndt_batch_align_begin": [vp, i32, vp, vp, vp], "lvs_ndt_batch_align_end": [vp, vp],
             "lvs_prefilter_create": [i32, vp, vp], "lvs_prefilter_destroy": [vp],
             "lvs_prefilter_run": [vp, vp, sz, sz, i32, i32, ctypes.c_double, ctypes.c_double, i32, ctypes.c_float, vp, sz, i32, vp, vp],
+            "lvs_prefilter_accumulate_begin": [vp], "lvs_prefilter_accumulate_add": [vp, vp, sz, sz, i32, i32, vp],
+            "lvs_prefilter_accumulate_flush": [vp, i32, ctypes.c_float, vp, sz, i32, vp, vp],
             "lvs_pgo_chol_analyze": [i32, i32, vp, vp, vp], "lvs_pgo_chol_info": [vp, vp],
             "lvs_ndt_batch_total_launches": [vp, vp], "lvs_ndt_batch_transfer_bytes": [vp, vp, vp], "lvs_ndt_batch_num_cells": [vp, i32, vp, vp],
             "lvs_ndt_batch_wait_uploads": [vp], "lvs_ndt_batch_shard_init": [vp, i32, i32, i32, vp], "lvs_ndt_batch_shard_connect": [vp, vp],

@@ -53,3 +53,55 @@ class Prefilter:
                                           int(self.use_distance_filter), leaf, optr, n, on_device, ctypes.byref(m), ctypes.byref(fl)))
         self.last_flags = fl.value
         return out[:m.value]
+
+
+class WindowMap:
+    """The window cloud of GlobalGraphNodelet::cloud_callback (src/global_graph/global_graph_nodelet.cpp:199-243): scans between two
+    keyframes are transformed into the window's frame (double matrix, pcl::transformPointCloud) and appended; flush() applies the
+    0.1 m VoxelGrid that turns the window into the keyframe's cloud."""
+
+    def __init__(self, leaf=0.1, device=0, stream=None):
+        self.leaf = float(leaf)
+        self._L = C.lib()
+        self._h = ctypes.c_void_p()
+        C.check(self._L.lvs_prefilter_create(device, stream, ctypes.byref(self._h)))
+        self._nf, self._n = None, 0
+        self.last_flags = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lvs_prefilter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def start(self, cloud):
+        """w_cloud = *cloud (the window's first scan, its own frame)"""
+        C.check(self._L.lvs_prefilter_accumulate_begin(self._h))
+        self._nf, self._n = None, 0
+        self.add(cloud, None)
+
+    def add(self, cloud, T):
+        """w_cloud += transformPointCloud(cloud, T), T = w_odom^-1 * odom as a 4x4 double matrix (None: no transform)"""
+        ptr, n, stride, on_device, keep = _cloud_args(cloud)
+        nf = 4 if keep.shape[1] >= 4 else 3
+        if self._nf is None:
+            self._nf = nf
+        elif nf != self._nf:
+            raise ValueError("all clouds of a window need the same fields")
+        Tm = np.ascontiguousarray(np.asarray(T, dtype=np.float64).T.reshape(16)) if T is not None else None
+        C.check(self._L.lvs_prefilter_accumulate_add(self._h, ptr, n, stride, nf, on_device, Tm.ctypes.data if Tm is not None else None))
+        self._n += n
+
+    def flush(self):
+        """VoxelGrid(leaf) of the window -> float32 [m, 3 or 4]"""
+        nf = self._nf or 3
+        out = np.empty((max(self._n, 1), nf), np.float32)
+        m, fl = ctypes.c_size_t(0), ctypes.c_int(0)
+        C.check(self._L.lvs_prefilter_accumulate_flush(self._h, nf, self.leaf, out.ctypes.data, self._n, 0, ctypes.byref(m), ctypes.byref(fl)))
+        self.last_flags = fl.value
+        return out[:m.value].copy()

@@ -828,6 +828,21 @@ size_t oprefilter(const float* xyz, size_t npts, size_t stride_floats, int n_fie
   return n_out;
 }
 
+// pcl::transformPointCloud with a double matrix, as the window map of the global-graph nodelet uses it
+// (src/global_graph/global_graph_nodelet.cpp:239-241; PCL 1.8 common/impl/transforms.hpp, un-vendored): every coordinate is
+// float(m_r0 * x + m_r1 * y + m_r2 * z + m_r3), left to right in double; other fields are copied.  T16 column-major.
+void otransform_double(const float* xyz, size_t npts, size_t stride_floats, int n_fields, const double* T16, float* out) {
+  for (size_t i = 0; i < npts; i++) {
+    const float* p = xyz + i * stride_floats;
+    const double x = p[0], y = p[1], z = p[2];
+    float* o = out + i * n_fields;
+    o[0] = (float)(T16[0] * x + T16[4] * y + T16[8] * z + T16[12]);
+    o[1] = (float)(T16[1] * x + T16[5] * y + T16[9] * z + T16[13]);
+    o[2] = (float)(T16[2] * x + T16[6] * y + T16[10] * z + T16[14]);
+    if (n_fields > 3) o[3] = p[3];
+  }
+}
+
 // align(): returns nr_iterations.  out_final16 column-major.  stats = {converged, trans_probability, n_eval, n_hess}
 int ondt_align(void* h, const float* guess16, float* out_final16, double* stats4, float* out_cloud_xyz /*nullable, packed*/) {
   NDT& n = *(NDT*)h;

@@ -45,6 +45,7 @@ def lib():
         L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
         L.ondt_eval_hessian.restype = None; L.ondt_eval_hessian.argtypes = [vp, vp, vp, vp]
         L.ondt_calculate_score.restype = f64; L.ondt_calculate_score.argtypes = [vp, vp]
+        L.otransform_double.restype = None; L.otransform_double.argtypes = [vp, sz, sz, i32, vp, vp]
         L.oprefilter.restype = sz; L.oprefilter.argtypes = [vp, sz, sz, i32, f64, f64, i32, f32, vp, vp]
         L.ondt_fitness_score.restype = f64; L.ondt_fitness_score.argtypes = [vp, vp, f64, vp]
         L.ondt_align.restype = i32; L.ondt_align.argtypes = [vp, vp, vp, vp, vp]
@@ -189,6 +190,23 @@ def prefilter(cloud, near=0.5, far=100.0, use_filter=True, leaf=0.1):
     fl = ctypes.c_int(0)
     m = lib().oprefilter(a.ctypes.data, a.shape[0], a.shape[1], nf, float(near), float(far), int(bool(use_filter)), float(leaf), out.ctypes.data, ctypes.byref(fl))
     return out[:m].copy(), fl.value
+
+
+def window_map(clouds, transforms, leaf=0.1):
+    """w_cloud = clouds[0] + sum transformPointCloud(clouds[k], transforms[k]) (double matrices), then VoxelGrid(leaf)
+    (global_graph_nodelet.cpp:199-243)."""
+    parts = []
+    for c, T in zip(clouds, transforms):
+        a = _f32(c)
+        nf = 4 if a.shape[1] >= 4 else 3
+        if T is None:
+            parts.append(a[:, :nf].copy())
+            continue
+        out = np.zeros((a.shape[0], nf), np.float32)
+        Tm = np.ascontiguousarray(np.asarray(T, dtype=np.float64).T.reshape(16))
+        lib().otransform_double(a.ctypes.data, a.shape[0], a.shape[1], nf, Tm.ctypes.data, out.ctypes.data)
+        parts.append(out)
+    return prefilter(np.concatenate(parts), use_filter=False, leaf=leaf)[0]
 
 
 def transform(xyz, T):

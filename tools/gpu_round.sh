@@ -12,7 +12,7 @@ timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exi
 timeout 600 python bench.py --variant pca > $OUT/bench_pca.json 2> $OUT/bench_pca.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 timeout 300 python tools/gpu_first.py > $OUT/gpu_first.log 2>&1
-timeout 400 python tools/pgo_perf.py --big > $OUT/pgo_perf.log 2>&1
+timeout 400 python tools/pgo_perf.py > $OUT/pgo_perf.log 2>&1
 timeout 300 python tools/aux_perf.py > $OUT/aux_perf.log 2>&1
 timeout 300 python tools/chol_profile.py 100 50 5 > $OUT/chol_solve.log 2>&1
 # launch list of the bench command (cold-cache, serialised: shares only)
