@@ -164,7 +164,8 @@ int lvs_ndt_batch_align(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_s
 /* The same align in two halves, for callers that stream: align_begin uploads the pair states and queues the evaluation launches of
  * a typical align without waiting (the Newton / More-Thuente state machine runs on the device); until align_end collects the
  * results the host is free to hand the NEXT batch to set_target(s) / set_source(s) - in other slots than the pairs in flight use -
- * so that its copies and voxelisations overlap the aligns.  One align in flight per object; every other entry point that
+ * so that its copies and voxelisations overlap the aligns (a device-resident cloud handed over in between must be complete, or
+ * have been produced on the object's stream before align_begin).  One align in flight per object; every other entry point that
  * evaluates (align, fitness score, taps) returns LVS_ERR_INVALID_ARG in between.  lvs_ndt_batch_align = begin + end. */
 int lvs_ndt_batch_align_begin(lvs_ndt_batch_t* b, int n_pairs, const int32_t* source_slot, const int32_t* target_slot, const float* guesses16);
 int lvs_ndt_batch_align_end(lvs_ndt_batch_t* b, lvs_ndt_result* results /* n_pairs of the begin call */);

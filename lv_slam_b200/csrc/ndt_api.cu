@@ -221,7 +221,9 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
     // whatever the caller has queued on the handle's stream to produce the cloud
     if (slot.ready_pending) { CUDA_TRY(cudaStreamWaitEvent(resident_stream, slot.ready, 0)); slot.ready_pending = false; }
     if (resident_stream != b->st) {
-      CUDA_TRY(cudaEventRecord(b->ev_mark, b->st));
+      // while an align is in flight the handle's stream is full of its evaluation launches: order the repack behind the point
+      // where align_begin found the stream (whatever the caller had queued by then), not behind the aligns themselves
+      if (!b->pend.active) CUDA_TRY(cudaEventRecord(b->ev_mark, b->st));
       CUDA_TRY(cudaStreamWaitEvent(resident_stream, b->ev_mark, 0));
       if (slot.used_pending) { CUDA_TRY(cudaStreamWaitEvent(resident_stream, slot.used, 0)); slot.used_pending = false; }
     }
@@ -444,6 +446,7 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
     align_state_init(b->h_states[i], guesses16 + 16 * i, b->trace_on);
   }
   CUDA_TRY(cudaEventRecord(b->ev_begin, b->st));
+  CUDA_TRY(cudaEventRecord(b->ev_mark, b->st));      // position of the stream before this align (see upload_cloud)
   CUDA_TRY(cudaMemcpyAsync(b->d_pairs, b->h_pairs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, b->st));
   CUDA_TRY(cudaMemcpyAsync(b->d_states, b->h_states, n_pairs * sizeof(AlignState), cudaMemcpyHostToDevice, b->st));
   b->h2d_bytes += (long long)n_pairs * (sizeof(PairDesc) + sizeof(AlignState));
