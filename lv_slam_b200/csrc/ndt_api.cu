@@ -165,6 +165,8 @@ struct lvs_ndt_batch {
   int *d_shard_error = nullptr, *h_shard_error = nullptr;
   int blocks_per_pair_override = 0;
   int chunk_first = 6, chunk_next = 4;
+  int learned_first = 0;      // evaluations the previous align needed + 1: how many launches the next align queues up front (unless set_tuning fixed it)
+  bool chunk_fixed = false;
 };
 
 namespace lvs {
@@ -473,7 +475,10 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   // The radius-search passes are only reachable in KDTREE mode or when the reference's More-Thuente loop can run, i.e.
   // when `interval_converged = (step_max - step_min) > 0` (ndt_omp_impl2.hpp:888) is false.
   P.need_cold = b->prm.search_method == LVS_KDTREE || !((b->prm.step_size - b->prm.transformation_epsilon / 2) > 0);
-  for (int k = 0; k < b->chunk_first && P.launches < P.max_launches; k++)
+  // launches queued before the first completion check: every one beyond what the pairs need is a grid of CTAs that find nothing
+  // to do, so the count follows the previous align (streams are self-similar) unless the caller fixed it
+  const int first = (!b->chunk_fixed && b->learned_first > 0) ? b->learned_first : b->chunk_first;
+  for (int k = 0; k < first && P.launches < P.max_launches; k++)
     if ((rc = align_launch_one(b))) return rc;
   CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
   b->d2h_bytes += sizeof(int);
@@ -531,6 +536,7 @@ static int align_end(lvs_ndt_batch* b, lvs_ndt_result* results) {
     }
   }
   b->last_deriv_launches = active;
+  b->learned_first = std::max(2, std::min(active + 1, 16));
   b->last_deriv_ms = 0;
   if (prof) {
     double sum = 0;
@@ -960,7 +966,7 @@ int lvs_ndt_batch_set_profiling(lvs_ndt_batch_t* b, int on) {
 int lvs_ndt_batch_set_tuning(lvs_ndt_batch_t* b, int blocks_per_pair, int chunk_first, int chunk_next) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
   b->blocks_per_pair_override = blocks_per_pair > 0 ? blocks_per_pair : 0;
-  if (chunk_first > 0) b->chunk_first = chunk_first;
+  if (chunk_first > 0) { b->chunk_first = chunk_first; b->chunk_fixed = true; }
   if (chunk_next > 0) b->chunk_next = chunk_next;
   return LVS_OK;
 }

@@ -19,9 +19,10 @@ timeout 300 python tools/chol_profile.py 100 50 5 > $OUT/chol_solve.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
 # full capture of the hot kernel inside the batched bench step
-# (an align queues 6 evaluation launches, 3 of them do work: launches 0-5 warm-up resident, 6-11 warm-up host path, 12-17 the timed
-#  RESIDENT step - 12, 13, 14 are the 64-pair launches bench.py's roofline is about)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_eval_kernel -s 12 -c 3 -o $OUT/ndt_eval \
+# (the first align of an object queues 6 evaluation launches, later ones as many as the previous align needed + 1 = 4: launches 0-5
+#  warm-up resident, 6-9 warm-up host path, 10-13 the timed RESIDENT step - 10, 11, 12 are the working 64-pair launches bench.py's
+#  roofline is about)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_eval_kernel -s 10 -c 3 -o $OUT/ndt_eval \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 ls -la $OUT
 tail -3 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -3; cat $OUT/bench.json; tail -2 $OUT/bench.err
