@@ -149,17 +149,20 @@ constexpr int kPtsPerIter = 32 * kPtsPerLane;
 constexpr int kQueueCap = 256;
 constexpr int kTileFloats = kPairsH * kTileStride;
 
+// Everything a warp stages lives in ONE contiguous block of shared memory, so tile, points and queue are constant offsets from a
+// single per-warp base register (the compiler otherwise rebuilds three warp-indexed pointers in every round).
+template <bool PCA>
 struct SmemLayout {
   static constexpr size_t tile_off = 0;
-  static constexpr size_t pts_off = tile_off + sizeof(float) * kWarps * kTileFloats;
-  static constexpr size_t q_off = pts_off + sizeof(float) * kWarps * 6 * kPtsPerIter;
-  static constexpr size_t qw_off = q_off + sizeof(int) * kWarps * kQueueCap;          // 8-byte aligned (all terms are multiples of 8)
-  static constexpr size_t bytes_omp = qw_off;
-  static constexpr size_t bytes_pca = qw_off + sizeof(double) * kWarps * kQueueCap;
+  static constexpr size_t pts_off = tile_off + sizeof(float) * kTileFloats;
+  static constexpr size_t q_off = pts_off + sizeof(float) * 6 * kPtsPerIter;
+  static constexpr size_t qw_off = q_off + sizeof(int) * kQueueCap;
+  static constexpr size_t warp_bytes = qw_off + (PCA ? sizeof(double) * kQueueCap : 0);
+  static constexpr size_t bytes = warp_bytes * kWarps;
 };
-static_assert(SmemLayout::qw_off % 8 == 0, "qw must be 8-byte aligned");
-static_assert((sizeof(float) * kTileFloats) % 16 == 0, "per-warp tiles must stay 16-byte aligned");
-static_assert(sizeof(double) * kWarps * kPairsH * 2 * 4 <= SmemLayout::pts_off, "the CTA reduction scratch aliases the tile region");
+static_assert(SmemLayout<false>::qw_off % 8 == 0, "qw must be 8-byte aligned");
+static_assert(SmemLayout<false>::warp_bytes % 16 == 0 && SmemLayout<true>::warp_bytes % 16 == 0, "per-warp blocks must stay 16-byte aligned (LDS.128 on the tile)");
+static_assert(sizeof(double) * kWarps * kPairsH * 2 * 4 <= SmemLayout<false>::bytes, "the CTA reduction scratch aliases the staging blocks");
 
 // One round: lanes e < n_round take queue entries q[head + lane], stage their float contributions in the tile, then the
 // warp adds the round into its fp64 accumulators: in pass t lane l owns pair 8t + (l & 7) and the lane group l >> 3 (8 lanes),
@@ -232,10 +235,12 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
   constexpr int K = Probes<MODE>::K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  float* tile = reinterpret_cast<float*>(s_dyn + SmemLayout::tile_off) + warp * kTileFloats;
-  float* pts = reinterpret_cast<float*>(s_dyn + SmemLayout::pts_off) + warp * (6 * kPtsPerIter);
-  int* q = reinterpret_cast<int*>(s_dyn + SmemLayout::q_off) + warp * kQueueCap;
-  double* qw = reinterpret_cast<double*>(s_dyn + SmemLayout::qw_off) + warp * kQueueCap;   // only mapped for ndt_pca launches
+  using SL = SmemLayout<PCA>;
+  unsigned char* wbase = s_dyn + (size_t)warp * SL::warp_bytes;
+  float* tile = reinterpret_cast<float*>(wbase + SL::tile_off);
+  float* pts = reinterpret_cast<float*>(wbase + SL::pts_off);
+  int* q = reinterpret_cast<int*>(wbase + SL::q_off);
+  double* qw = reinterpret_cast<double*>(wbase + SL::qw_off);   // only mapped for ndt_pca launches
   const VoxelRec* __restrict__ recs = P.recs;
   const int* __restrict__ grid = P.grid;
   const f32x2 one = pk(one_f, one_f);
@@ -380,7 +385,7 @@ static int launch_eval_as(cudaStream_t st, const EvalLaunch& L) {
   static int attr_dev = -1;     // the opt-in shared-memory size is a per-device function attribute
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
-  constexpr size_t smem = PCA ? SmemLayout::bytes_pca : SmemLayout::bytes_omp;
+  constexpr size_t smem = SmemLayout<PCA>::bytes;
   if (attr_dev != dev) {
     CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel<MODE, PCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = dev;
