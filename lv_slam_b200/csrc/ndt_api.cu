@@ -102,6 +102,7 @@ using namespace lvs;
 
 struct PendingAlign {          // the align between align_begin and align_end
   bool active = false;
+  std::vector<int> src_slots, tgt_slots;     // slots the pairs in flight read: the setters refuse them until align_end
   int n_pairs = 0, launches = 0, max_launches = 0;
   bool need_cold = false, prof = false;
   EvalLaunch L;
@@ -455,6 +456,8 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   CUDA_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int), b->st));
   PendingAlign& P = b->pend;
   P = PendingAlign();
+  P.src_slots.assign(src_slot, src_slot + n_pairs);
+  P.tgt_slots.assign(tgt_slot, tgt_slot + n_pairs);
   EvalLaunch& L = P.L;
   L.d_pairs = b->d_pairs; L.d_states = b->d_states; L.d_trace = b->trace_on ? b->d_trace : nullptr;
   L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
@@ -647,10 +650,20 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
   return LVS_OK;
 }
 
+// A cloud that the align in flight reads must not be replaced before align_end.
+static int slot_in_flight(const lvs_ndt_batch* b, bool target, int slot) {
+  if (!b->pend.active) return LVS_OK;
+  const std::vector<int>& v = target ? b->pend.tgt_slots : b->pend.src_slots;
+  if (std::find(v.begin(), v.end(), slot) != v.end())
+    return fail(LVS_ERR_INVALID_ARG, "%s slot %d is read by the align in flight: call align_end first", target ? "target" : "source", slot);
+  return LVS_OK;
+}
+
 static int set_target(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, size_t stride_bytes, int on_device) {
   int rc = set_device(b);
   if (rc) return rc;
   if (slot < 0 || slot >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slot);
+  if ((rc = slot_in_flight(b, true, slot))) return rc;
   CloudSlot& cs = b->target_pts[slot];
   TargetBuildState& ts = b->tstate[slot];
   // a grid that was re-queued on the compute stream (grown index grid) or consumed there is complete by now: every consumer
@@ -682,8 +695,10 @@ static int set_targets_many(lvs_ndt_batch* b, int n, const int32_t* slots, const
                             int on_device) {
   int rc = set_device(b);
   if (rc) return rc;
-  for (int i = 0; i < n; i++)
+  for (int i = 0; i < n; i++) {
     if (slots[i] < 0 || slots[i] >= (int)b->targets.size()) return fail(LVS_ERR_BAD_SLOT, "target slot %d out of range", slots[i]);
+    if ((rc = slot_in_flight(b, true, slots[i]))) return rc;
+  }
   BuildLane& ln = b->lanes[0];
   for (int base = 0; base < n; base += kVoxBatch) {
     const int cnt = std::min(kVoxBatch, n - base);
@@ -734,6 +749,7 @@ static int set_source(lvs_ndt_batch* b, int slot, const float* xyz, size_t n, si
   int rc = set_device(b);
   if (rc) return rc;
   if (slot < 0 || slot >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slot);
+  if ((rc = slot_in_flight(b, false, slot))) return rc;
   size_t lo = 0, cnt = n;
   shard_range(b, n, &lo, &cnt);
   rc = upload_cloud(b, b->sources[slot], xyz ? (const float*)((const char*)xyz + lo * stride_bytes) : xyz, cnt, stride_bytes, on_device, b->st);
@@ -747,8 +763,10 @@ static int set_sources(lvs_ndt_batch* b, int n, const int32_t* slots, const floa
                        int on_device) {
   int rc = set_device(b);
   if (rc) return rc;
-  for (int i = 0; i < n; i++)
+  for (int i = 0; i < n; i++) {
     if (slots[i] < 0 || slots[i] >= (int)b->sources.size()) return fail(LVS_ERR_BAD_SLOT, "source slot %d out of range", slots[i]);
+    if ((rc = slot_in_flight(b, false, slots[i]))) return rc;
+  }
   if (!on_device) {
     for (int i = 0; i < n; i++)
       if ((rc = set_source(b, slots[i], xyz[i], counts[i], stride_bytes, 0))) return rc;

@@ -503,6 +503,10 @@ def test_align_begin_end_overlaps_the_next_batch(small_pair, scan_pair):
         b.align_begin([1], [1], [guess2])                           # one align in flight per object
     with pytest.raises(L.LvsError):
         b.fitness_score(0, 0, truth)
+    with pytest.raises(L.LvsError):
+        b.set_sources([0], [src2])                                  # a cloud the align in flight reads cannot be replaced
+    with pytest.raises(L.LvsError):
+        b.set_targets([1, 0], [tgt2, tgt2])
     got = b.align_end()[0]
     assert np.array_equal(got["final"], ref["final"]) and got["iterations"] == ref["iterations"] and got["n_eval"] == ref["n_eval"]
     with pytest.raises(L.LvsError):
@@ -537,3 +541,36 @@ def test_window_map_matches_oracle(small_pair):
     w.leaf = 0.5
     w.start(scans[2][:, :3]); w.add(scans[3][:, :3], Ts[1])
     assert np.array_equal(w.flush(), O.window_map([scans[2][:, :3], scans[3][:, :3]], [None, Ts[1]], 0.5))
+
+
+def test_edge_cases_of_the_neighbouring_stages(small_pair):
+    """Empty and degenerate inputs of getFitnessScore, the prefilter and the window map behave like the restatement."""
+    import torch
+    import lv_slam_b200 as L
+    tgt, src, guess, truth = small_pair
+    big = np.finfo(np.float64).max
+    n, o = _mk(O.VAR_OMP, O.DIRECT7)
+    # a target without a single finite point: no neighbour for anybody
+    bad = np.full((50, 3), np.nan, np.float32)
+    n.setInputTarget(bad); n.setInputSource(src); o.set_target(bad); o.set_source(src)
+    assert n.getFitnessScore(big, T=truth, with_count=True) == (big, 0) and o.fitness_score(truth, big) == (big, 0)
+    n.setInputTarget(np.zeros((0, 3), np.float32))
+    assert n.getFitnessScore(big, T=truth, with_count=True) == (big, 0)
+    # a one-point target: every source point has the same neighbour
+    one = np.array([[1.0, 2.0, 0.5]], np.float32)
+    n.setInputTarget(one); o.set_target(one)
+    gs, gn = n.getFitnessScore(big, T=truth, with_count=True)
+    os_, on = o.fitness_score(truth, big)
+    assert gn == on == len(src) and abs(gs - os_) <= 1e-12 * os_
+    # prefilter: nothing finite, a single point, everything inside one leaf
+    pf = L.Prefilter(distance_near_thresh=0.5, distance_far_thresh=100.0, downsample_resolution=0.1)
+    assert pf.filter(bad).shape[0] == 0
+    assert np.array_equal(pf.filter(one), one)
+    clump = (np.array([[5.0, 5.0, 1.0]], np.float32) + 0.01 * np.random.default_rng(1).random((40, 3), dtype=np.float32)).astype(np.float32)
+    got, exp = pf.filter(clump), O.prefilter(clump, 0.5, 100.0, True, 0.1)[0]
+    assert np.array_equal(got, exp) and 1 <= len(got) <= 8
+    # window map fed from device memory, identity transforms
+    w = L.WindowMap(0.1)
+    w.start(torch.from_numpy(tgt).cuda())
+    w.add(torch.from_numpy(src).cuda(), np.eye(4))
+    assert np.array_equal(w.flush(), O.window_map([tgt, src], [None, np.eye(4)], 0.1))
