@@ -673,6 +673,8 @@ int opgo_solve(void* h, double lambda, int solver, double pcg_tol, int pcg_max_i
   return ok ? 1 : 0;
 }
 int opgo_last_pcg_iters(void* h) { return ((PGO*)h)->last_pcg_iters; }
+// nnz(L) (scalar entries) of CSparse's symbolic factorisation under its own AMD ordering, after a SOLVER_CSPARSE solve; -1 if none
+double opgo_csparse_lnz(void* h) { PGO& g = *(PGO*)h; return g.symbolic ? g.symbolic->lnz : -1.0; }
 
 // stats5: chi2 before (plain), chi2 after (plain), final lambda, LM trials, robust chi2 after
 int opgo_optimize(void* h, int max_iters, int algorithm, int solver, double pcg_tol, int pcg_max_iter, double* stats5) {

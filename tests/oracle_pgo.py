@@ -49,6 +49,14 @@ def lib():
     return _lib
 
 
+def csparse_lnz(o):
+    """nnz(L) of CSparse's symbolic factorisation (its own AMD ordering) after a SOLVER_CSPARSE solve on OraclePGO `o`; -1 if none."""
+    L = lib()
+    L.opgo_csparse_lnz.restype = ctypes.c_double
+    L.opgo_csparse_lnz.argtypes = [ctypes.c_void_p]
+    return float(L.opgo_csparse_lnz(o.h))
+
+
 def have_csparse():
     return bool(lib().opgo_have_csparse())
 
