@@ -6,3 +6,4 @@ from .ndt import NdtBatch, NormalDistributionsTransform  # noqa: F401
 from .graph_slam import GraphSLAM, PoseGraph  # noqa: F401,E402
 from .information_matrix import InformationMatrixCalculator  # noqa: F401,E402
 from .prefilter import Prefilter, WindowMap  # noqa: F401,E402
+from . import keyframe_io  # noqa: F401,E402

@@ -260,3 +260,86 @@ def test_block_ordering_fill_is_comparable_to_the_references_amd():
         st, _ = chol_analyze(n, off)
         ours = (st["nnz_l_blocks"] - n) * 36 + n * 21          # scalar entries of the block factor
         assert ours <= 1.3 * P.csparse_lnz(o)
+
+
+def test_keyframe_dump_round_trip(tmp_path):
+    """dump_service artefacts (graph.g2o + .kernels, %06d/data + cloud.pcd, special_nodes.csv, ggo_*_odom.txt) written and read
+    back; `data` keeps the reference's token layout (keyframe.cpp:48-92) at Eigen's default 6 significant digits."""
+    from lv_slam_b200 import keyframe_io as K
+    from lv_slam_b200.graph_slam import GraphSLAM, load_kitti_poses
+    from lv_slam_b200.synth import posegraph as G
+    rng = np.random.default_rng(3)
+    g = GraphSLAM("lm_var_cholmod")
+    kfs, odoms = [], {}
+    T = np.eye(4)
+    for i in range(4):
+        T = T @ G.matrix(np.concatenate([[2.0 + i, 0.1, 0.0], G.pose7(np.eye(4))[3:]]))
+        node = g.add_se3_node(T)
+        cloud = rng.normal(size=(50 + i, 4)).astype(np.float32)
+        kfs.append(dict(stamp=(100 + i, 5000 * i), seq=3 * i, estimate=T.copy(), odom=T.copy(), accum_distance=2.5 * i, id=node.id(), cloud=cloud))
+        if i:
+            e = g.add_se3_edge(kfs[i - 1]["node"], node, np.linalg.inv(kfs[i - 1]["estimate"]) @ T, np.eye(6) * (i + 1))
+            g.add_robust_kernel(e, "Huber", 1.0)
+        kfs[-1]["node"] = node
+    for s in range(0, 12):
+        a, f = divmod(s, 3)
+        a = min(a, 3)
+        step = G.matrix(np.concatenate([[0.5 * (s - 3 * a), 0.0, 0.0], G.pose7(np.eye(4))[3:]]))
+        odoms[s] = kfs[a]["odom"] @ step
+    d = str(tmp_path / "dump")
+    K.dump(d, g, kfs, odoms)
+    txt = open(os.path.join(d, "000001", "data")).read().split("\n")
+    assert txt[0] == "stamp 101 5000" and txt[1] == "estimate" and txt[6] == "odom" and txt[11].startswith("accum_distance 2.5") and txt[12] == "id 1"
+    assert open(os.path.join(d, "special_nodes.csv")).read() == "anchor_node -1\nanchor_edge -1\nfloor_node -1\n"
+    hdr = open(os.path.join(d, "000002", "cloud.pcd"), "rb").read(200).decode("ascii", "replace")
+    assert "FIELDS x y z intensity" in hdr and "POINTS 52" in hdr and "DATA binary" in hdr
+    g2 = GraphSLAM("lm_var_cholmod")
+    back = K.load_dump(d, g2)
+    assert len(back) == 4 and g2.num_vertices() == 4 and g2.num_edges() == 3
+    for a, b in zip(kfs, back):
+        assert b["stamp"] == a["stamp"] and b["id"] == a["id"] and b["node"].id() == a["id"]
+        np.testing.assert_array_equal(b["cloud"], a["cloud"])                     # binary PCD: exact
+        np.testing.assert_allclose(b["estimate"], a["estimate"], rtol=1e-5, atol=1e-5)
+        assert abs(b["accum_distance"] - a["accum_distance"]) < 1e-5
+    assert all(e.kernel == ("Huber", 1.0) for e in g2._edges)
+    # the optimisation changed nothing here (estimate == odom), so the per-frame file is the odometry itself, from the first keyframe
+    kf_file = load_kitti_poses(os.path.join(d, "ggo_kf_odom.txt"))
+    wf_file = load_kitti_poses(os.path.join(d, "ggo_wf_odom.txt"))
+    assert len(kf_file) == 4 and len(wf_file) == 12
+    np.testing.assert_allclose(kf_file[2], kfs[2]["estimate"], atol=1e-6)
+    first = np.linalg.inv(kfs[0]["estimate"])
+    for s in range(12):
+        np.testing.assert_allclose(wf_file[s], first @ odoms[s], atol=1e-6)
+    # ascii PCD written by other tools reads the same
+    with open(os.path.join(d, "a.pcd"), "w") as f:
+        f.write("VERSION .7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA ascii\n1 2 3\n4 5 6.5\n")
+    np.testing.assert_array_equal(K.load_pcd(os.path.join(d, "a.pcd")), np.array([[1, 2, 3, 0], [4, 5, 6.5, 0]], np.float32))
+    # a camera calibration conjugates the written poses (save_pose :1081-1097)
+    with open(os.path.join(d, "calib.txt"), "w") as f:
+        f.write("P0: 0\nP1: 0\nP2: 0\nP3: 0\nTr: 0 -1 0 0.1 0 0 -1 0.2 1 0 0 0.3\n")
+    C4 = K.load_calib(os.path.join(d, "calib.txt"))
+    K.save_pose(d, kfs, odoms, C4)
+    np.testing.assert_allclose(load_kitti_poses(os.path.join(d, "ggo_kf_odom.txt"))[3], C4 @ kfs[3]["estimate"] @ np.linalg.inv(C4), atol=1e-6)
+
+
+def test_save_pose_distributes_the_correction_as_the_reference_writes_it(tmp_path):
+    """One segment of 4 frames whose optimised end moved by (0.4 m, 8 deg about z) against the odometry: the per-frame file applies
+    the translation share 1/4 and — as written at global_graph_nodelet.cpp:1118 — slerp(4, q), i.e. FOUR times the angle."""
+    from lv_slam_b200 import keyframe_io as K
+    from lv_slam_b200.graph_slam import load_kitti_poses
+
+    def rz(deg, t=(0, 0, 0)):
+        a = np.deg2rad(deg)
+        T = np.eye(4)
+        T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        T[:3, 3] = t
+        return T
+    odoms = {s: rz(0, (1.0 * s, 0, 0)) for s in range(5)}
+    corr = rz(8.0, (0.4, 0, 0))
+    kfs = [dict(seq=0, estimate=np.eye(4)), dict(seq=4, estimate=odoms[4] @ corr)]
+    n = K.save_pose(str(tmp_path), kfs, odoms)
+    assert n == 4 + 1                                       # frames 0..3 of the segment, then frame 4 (the last keyframe's own)
+    wf = load_kitti_poses(str(tmp_path / "ggo_wf_odom.txt"))
+    np.testing.assert_allclose(wf[0], np.eye(4), atol=1e-9)
+    np.testing.assert_allclose(wf[2], odoms[2] @ rz(32.0, (0.1, 0, 0)), atol=1e-6)
+    np.testing.assert_allclose(wf[4], odoms[4] @ corr, atol=1e-6)
