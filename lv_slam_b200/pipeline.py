@@ -129,9 +129,10 @@ class LoopDetector:
 
 
 def replay(scans, odom_registration, loop_registration, graph_slam, info_calc, prefilter=None, loop_params=None, optimize_iterations=512,
-           stamp_step=0.1):
+           stamp_step=0.1, dump_directory=None, tf_velo2cam=None):
     """Runs the chain over `scans` (list of float32 [n, >=3]).  Returns a dict with the odometry poses, the keyframe list, the loop
-    edges and the optimised keyframe poses."""
+    edges and the optimised keyframe poses.  With `dump_directory` the reference's dump_service artefacts are written at the end
+    (keyframe_io.dump: graph.g2o, keyframe directories, ggo_kf_odom.txt / ggo_wf_odom.txt)."""
     odo = ScanMatchingOdometry(odom_registration)
     det = LoopDetector(loop_registration, **(loop_params or {}))
     odom_poses, keyframes, loops = [], [], []
@@ -165,5 +166,10 @@ def replay(scans, odom_registration, loop_registration, graph_slam, info_calc, p
             loops.append((loop["key1"]["frame"], loop["key2"]["frame"], loop["score"]))
     iters = graph_slam.optimize(optimize_iterations) if len(keyframes) > 1 else -1
     est = [np.asarray(k["node"].estimate(), dtype=np.float64) for k in keyframes]
+    if dump_directory is not None:
+        from . import keyframe_io
+        recs = [dict(stamp=(int(k["frame"] * stamp_step), int(round((k["frame"] * stamp_step) % 1.0 * 1e9))), seq=k["frame"], estimate=e, odom=k["odom"],
+                     accum_distance=k["accum_distance"], id=k["node"].id(), cloud=k["cloud"]) for k, e in zip(keyframes, est)]
+        keyframe_io.dump(dump_directory, graph_slam, recs, dict(enumerate(odom_poses)), tf_velo2cam)
     return dict(odom=odom_poses, keyframe_frames=[k["frame"] for k in keyframes], loops=loops, optimized=est, iterations=iters,
                 odom_aligns=odo.aligns, loop_aligns=det.aligns)

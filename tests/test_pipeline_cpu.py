@@ -7,10 +7,10 @@ import pipeline_backends as B
 from lv_slam_b200 import pipeline as PL
 
 
-def test_replay_driver_on_the_cpu_chain():
+def test_replay_driver_on_the_cpu_chain(tmp_path):
     scans, truth = B.out_and_back()
     r = PL.replay(scans, B.OracleRegistration(O.VAR_PCA, O.DIRECT1), B.OracleRegistration(O.VAR_OMP, O.DIRECT7), B.OracleGraphSLAM("lm_var_cholmod"),
-                  B.OracleInformation(), prefilter=B.OraclePrefilter())
+                  B.OracleInformation(), prefilter=B.OraclePrefilter(), dump_directory=str(tmp_path / "dump"))
     kf = r["keyframe_frames"]
     assert kf[0] == 0 and all(b > a for a, b in zip(kf, kf[1:])) and len(kf) >= 10
     # 1.2 m per frame: a keyframe once 10 m are exceeded (launch/dlo_lfa_ggo_kitti.launch:51), i.e. every 9th frame on the straight legs
@@ -29,3 +29,17 @@ def test_replay_driver_on_the_cpu_chain():
     # the rotation gate of matching_s2k: 2 acos(w) of the float quaternion
     c, s = np.cos(0.2), np.sin(0.2)
     assert abs(PL._rot_angle_f32(np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])) - 0.2) < 1e-3
+    # the dump is the reference's artefact set and reads back as the same graph and keyframes
+    from lv_slam_b200 import keyframe_io as K
+    from lv_slam_b200.graph_slam import load_kitti_poses
+    g2 = B.OracleGraphSLAM("lm_var_cholmod")
+    back = K.load_dump(str(tmp_path / "dump"), g2)
+    assert len(back) == len(kf) and g2.num_edges() == len(kf) - 1 + len(r["loops"])
+    assert all(e.kernel == ("Huber", 1.0) for e in g2._edges)
+    for b, T in zip(back, r["optimized"]):
+        # KeyFrame::load overwrites the vertex with the 6-significant-digit estimate of `data` (keyframe.cpp:191-194)
+        np.testing.assert_allclose(b["node"].estimate(), T, rtol=1e-5, atol=1e-5)
+    wf = load_kitti_poses(str(tmp_path / "dump" / "ggo_wf_odom.txt"))
+    assert len(wf) == len(scans)
+    e_wf = max(np.linalg.norm((T0 @ truth[f])[:3, 3] - (np.linalg.inv(wf[0]) @ wf[f])[:3, 3]) for f in range(len(scans)))
+    assert e_wf < 1.5
