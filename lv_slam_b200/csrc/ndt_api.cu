@@ -1222,9 +1222,18 @@ static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const flo
   if ((rc = finish_target(b, tgt_slot))) return rc;
   const CloudSlot& src = b->sources[src_slot];
   TargetGrid& tg = b->targets[tgt_slot];
-  if (!tg.sorted_pts_valid && tg.n_cells > 0) {      // first query against this build: put the target points into cell order
-    if ((rc = launch_fitness_gather(b->st, b->target_pts[tgt_slot].d_pts, b->target_pts[tgt_slot].n, tg.d_sorted_idx, tg.d_cell_start, tg.d_gp, tg.d_sorted_pts))) return rc;
-    b->total_launches++;
+  if (!tg.sorted_pts_valid && tg.n_cells > 0) {      // first query against this build: put the target points into cell and slab order
+    if ((size_t)tg.n_cells > tg.slab_cells) {
+      if (tg.d_slab) cudaFree(tg.d_slab);
+      tg.d_slab = nullptr; tg.slab_cells = 0;
+      const size_t cells = (size_t)tg.n_cells + tg.n_cells / 4 + 64;
+      CUDA_TRY(cudaMalloc(&tg.d_slab, cells * kFitSlabsPerCell * sizeof(int)));
+      tg.slab_cells = cells;
+    }
+    int gl = 0;
+    if ((rc = launch_fitness_gather(b->st, b->target_pts[tgt_slot].d_pts, b->target_pts[tgt_slot].n, tg.n_cells, tg.d_sorted_idx, tg.d_cell_start, tg.d_gp,
+                                    tg.d_slab, tg.d_sorted_pts, &gl))) return rc;
+    b->total_launches += gl;
     tg.sorted_pts_valid = true;
   }
   if ((size_t)src.n + 1 > b->fit_cap) {
@@ -1233,7 +1242,7 @@ static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const flo
     b->d_fit_best = nullptr; b->d_fit_list = nullptr; b->fit_cap = 0;
     const size_t cap = (size_t)src.n + src.n / 8 + 64;
     CUDA_TRY(cudaMalloc(&b->d_fit_best, cap * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&b->d_fit_list, (cap + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&b->d_fit_list, 2 * (cap + 1) * sizeof(int)));      // list 1 (undecided after the 27-cell block), list 2 (brute force)
     b->fit_cap = cap;
   }
   if (!b->d_fit_partials) {
@@ -1245,9 +1254,9 @@ static int fitness_score(lvs_ndt_batch* b, int src_slot, int tgt_slot, const flo
   FitnessArgs a;
   a.src = src.d_pts; a.n_src = src.n;
   a.tgt = b->target_pts[tgt_slot].d_pts; a.n_tgt = b->target_pts[tgt_slot].n;
-  a.grid = tg.d_grid; a.gp = tg.d_gp; a.cell_start = tg.d_cell_start; a.sorted_idx = tg.d_sorted_idx; a.tgt_sorted = tg.d_sorted_pts;
+  a.grid = tg.d_grid; a.gp = tg.d_gp; a.cell_start = tg.d_cell_start; a.sorted_idx = tg.d_sorted_idx; a.tgt_sorted = tg.d_sorted_pts; a.slab_end = tg.d_slab;
   a.T16 = b->d_T16; a.max_range = max_range;
-  a.best = b->d_fit_best; a.list = b->d_fit_list; a.partials = b->d_fit_partials; a.ticket = b->d_fit_ticket; a.out = b->d_scalar;
+  a.best = b->d_fit_best; a.list = b->d_fit_list; a.list2 = b->d_fit_list + (b->fit_cap + 1); a.partials = b->d_fit_partials; a.ticket = b->d_fit_ticket; a.out = b->d_scalar;
   int launches = 0;
   if ((rc = launch_fitness(b->st, a, &launches))) return rc;
   b->total_launches += launches;

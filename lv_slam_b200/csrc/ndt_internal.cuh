@@ -57,6 +57,8 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   int* d_sorted_idx = nullptr;           // target point indices grouped by cell (stable: input order inside a cell), cell_capacity
   int* d_cell_start = nullptr;           // [n_cells + 1] first position of every cell in d_sorted_idx
   float4* d_sorted_pts = nullptr;        // target points in cell order, filled lazily by the first fitness-score query of a build
+  int* d_slab = nullptr;                 // [n_cells][kFitSlabsPerCell] end of every x slab inside its cell (same lazy fill)
+  size_t slab_cells = 0;                 // cells d_slab has room for
   bool sorted_pts_valid = false;
   size_t cell_capacity = 0;
   int n_cells = 0;
@@ -130,18 +132,21 @@ int launch_lookup_keys(cudaStream_t st, const PairDesc& pair, const float* d_T16
 int launch_transform(cudaStream_t st, const float4* d_src, int n, const float* d_T16, float* d_out_xyz);
 
 // Nearest-neighbour fitness score (ndt_fitness.cu): pcl::Registration::getFitnessScore / InformationMatrixCalculator::
-// calc_fitness_score.  d_best [n_src] floats, d_list [n_src + 1] ints and d_out [2] doubles are caller-provided scratch.
+// calc_fitness_score.  d_best [n_src] floats, d_list and d_list2 [n_src + 1] ints each and d_out [2] doubles are caller-provided scratch.
 struct FitnessArgs {
   const float4* src; int n_src;
   const float4* tgt; int n_tgt;
   const int* grid; const GridParams* gp;
   const int* cell_start; const int* sorted_idx;
-  const float4* tgt_sorted;          // target points in cell order (TargetGrid::d_sorted_pts)
+  const float4* tgt_sorted;          // target points in cell order, slab order inside a cell (TargetGrid::d_sorted_pts)
+  const int* slab_end;               // TargetGrid::d_slab
   const float* T16;
   double max_range;
-  float* best; int* list; double* partials; unsigned int* ticket; double* out;   // out[0] = score, out[1] = correspondences
+  float* best; int* list; int* list2; double* partials; unsigned int* ticket; double* out;   // out[0] = score, out[1] = correspondences
 };
 int launch_fitness(cudaStream_t st, const FitnessArgs& a, int* launches);
-int launch_fitness_gather(cudaStream_t st, const float4* tgt, int n_tgt, const int* sorted_idx, const int* cell_start, const GridParams* gp, float4* out);
+constexpr int kFitSlabsPerCell = 64;
+int launch_fitness_gather(cudaStream_t st, const float4* tgt, int n_tgt, int n_cells, const int* sorted_idx, const int* cell_start, const GridParams* gp,
+                          int* slab, float4* out, int* launches);
 
 }  // namespace lvs

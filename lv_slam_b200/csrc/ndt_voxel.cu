@@ -763,6 +763,8 @@ void TargetGrid::free_cells() {
   if (d_sorted_idx) cudaFree(d_sorted_idx);
   if (d_cell_start) cudaFree(d_cell_start);
   if (d_sorted_pts) cudaFree(d_sorted_pts);
+  if (d_slab) cudaFree(d_slab);
+  d_slab = nullptr; slab_cells = 0;
   d_icov64 = nullptr; d_sorted_idx = nullptr; d_cell_start = nullptr; d_sorted_pts = nullptr; sorted_pts_valid = false;
   d_recs = nullptr; d_centroids = nullptr; d_cell_keys = nullptr; d_cell_npts = nullptr; d_cell_evals = nullptr;
   cell_capacity = 0;
