@@ -11,7 +11,7 @@
 // far).  Pass 1, a thread per query: its own cell and the 26 around it, skipping every cell whose box is farther away than the
 // best distance so far, within a fixed work budget; the best distance is exact as soon as it is below the distance to the outside
 // of the scanned block.  Pass 2, a warp per query: the queries that are still undecided (compacted into a list) walk the shells up
-// to radius 3, each cell read cooperatively.  Pass 3: what is left (far from every target point) is finished by brute force over
+// to radius 6, each cell read cooperatively.  Pass 3: what is left (far from every target point) is finished by brute force over
 // shared-memory tiles.  The float distances are bit-identical to the CPU
 // path; the double sum is a fixed-shape reduction (run-to-run deterministic).
 #include <cfloat>
@@ -20,7 +20,7 @@
 namespace lvs {
 
 constexpr int kFitThreads = 256;
-constexpr int kFitMaxRing = 3;
+constexpr int kFitMaxRing = 6;                // shells the warp-per-query pass walks before brute force takes over
 constexpr int kFitSlabs = kFitSlabsPerCell;
 
 __device__ __forceinline__ float dist2(float qx, float qy, float qz, const float4& p) {
@@ -142,9 +142,9 @@ __device__ __forceinline__ float scan_cell_warp(const float4* __restrict__ pts, 
 }
 
 // Shells R0..R1 of the ring search around the query's cell; returns whether `best` is proven to be the nearest distance.
-//   WARP = false: one thread per query, `budget` steps of work at most (then undecided);  WARP = true: one warp per query.
-template <int R0, int R1, bool WARP>
-__device__ __forceinline__ bool search_rings(const FitnessArgs& a, const GridParams* gp, float qx, float qy, float qz, float& best, int budget, int lane) {
+// One thread per query, `budget` steps of work at most (then undecided).
+template <int R0, int R1>
+__device__ __forceinline__ bool search_rings(const FitnessArgs& a, const GridParams* gp, float qx, float qy, float qz, float& best, int budget) {
   const float inv = gp->inv_leaf, leaf = gp->leaf;
   // the query's cell with the arithmetic the target points were binned with (key_kernel): one monotone map for both
   const int cx = (int)floorf(qx * inv) - gp->min_b[0], cy = (int)floorf(qy * inv) - gp->min_b[1], cz = (int)floorf(qz * inv) - gp->min_b[2];
@@ -182,11 +182,8 @@ __device__ __forceinline__ bool search_rings(const FitnessArgs& a, const GridPar
           const int k0 = __ldg(a.cell_start + rec), k1 = __ldg(a.cell_start + rec + 1);
           const int* se = a.slab_end + (size_t)rec * kFitSlabs;
           const float xlow = (float)(x + gp->min_b[0]) * leaf;
-          if (WARP) best = scan_cell_warp(a.tgt_sorted, se, k0, xlow, sscale, wslack, qx, qy, qz, best, lane);
-          else {
-            best = scan_cell(a.tgt_sorted, se, k0, k1, xlow, sscale, wslack, qx, qy, qz, best, budget);
-            if (budget < 0) return false;
-          }
+          best = scan_cell(a.tgt_sorted, se, k0, k1, xlow, sscale, wslack, qx, qy, qz, best, budget);
+          if (budget < 0) return false;
         }
       }
     }
@@ -197,10 +194,61 @@ __device__ __forceinline__ bool search_rings(const FitnessArgs& a, const GridPar
   return decided;
 }
 
+// The same search by a whole warp for ONE query.  The cells of a shell are spread over the lanes (box test and index-grid lookup
+// of 32 cells at a time: the lookups are dependent loads and would otherwise be paid one after the other); the occupied ones are
+// then scanned cooperatively, one cell at a time, each against the best distance the previous ones left.
+template <int R0, int R1>
+__device__ __forceinline__ bool search_rings_warp(const FitnessArgs& a, const GridParams* gp, float qx, float qy, float qz, float& best, int lane) {
+  const float inv = gp->inv_leaf, leaf = gp->leaf;
+  const int cx = (int)floorf(qx * inv) - gp->min_b[0], cy = (int)floorf(qy * inv) - gp->min_b[1], cz = (int)floorf(qz * inv) - gp->min_b[2];
+  const int d0 = gp->div_b[0], d1 = gp->div_b[1], d2 = gp->div_b[2];
+  const int m1 = gp->mul[1], m2 = gp->mul[2];
+  const float fx = qx - (float)(cx + gp->min_b[0]) * leaf, fy = qy - (float)(cy + gp->min_b[1]) * leaf, fz = qz - (float)(cz + gp->min_b[2]) * leaf;
+  const float slack = 1e-3f * leaf;
+  const float sscale = (float)kFitSlabs * inv;
+  const float wslack = leaf * (1.01f / (float)kFitSlabs) + slack;
+  bool decided = false;
+  for (int r = R0; r <= R1 && !decided; r++) {
+    const int n = 2 * r + 1, n3 = n * n * n;
+    for (int c0 = 0; c0 < n3; c0 += 32) {
+      const int c = c0 + lane;
+      int v = -1, xcell = 0;
+      float h2 = 0.0f;
+      if (c < n3) {
+        const int ox = c % n - r, oy = (c / n) % n - r, oz = c / (n * n) - r;
+        const int x = cx + ox, y = cy + oy, z = cz + oz;
+        const bool shell = max(max(abs(ox), abs(oy)), abs(oz)) == r;        // the inner cube was the previous shells
+        if (shell && (unsigned)x < (unsigned)d0 && (unsigned)y < (unsigned)d1 && (unsigned)z < (unsigned)d2) {
+          const float gx = ox > 0 ? (float)ox * leaf - fx : (ox < 0 ? fx - (float)(ox + 1) * leaf : 0.0f);
+          const float gy = oy > 0 ? (float)oy * leaf - fy : (oy < 0 ? fy - (float)(oy + 1) * leaf : 0.0f);
+          const float gz = oz > 0 ? (float)oz * leaf - fz : (oz < 0 ? fz - (float)(oz + 1) * leaf : 0.0f);
+          const float hx = fmaxf(gx - slack, 0.0f), hy = fmaxf(gy - slack, 0.0f), hz = fmaxf(gz - slack, 0.0f);
+          h2 = hx * hx + hy * hy + hz * hz;
+          if (h2 < best) { v = __ldg(a.grid + (x + y * m1 + z * m2)); xcell = x; }
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, v != -1);
+      while (m) {
+        const int from = __ffs(m) - 1;
+        m &= m - 1;
+        const int vv = __shfl_sync(0xffffffffu, v, from), xx = __shfl_sync(0xffffffffu, xcell, from);
+        const float hh = __shfl_sync(0xffffffffu, h2, from);
+        if (hh >= best) continue;                                            // an earlier cell of the batch got closer than this box
+        const int rec = grid_decode_any(vv);
+        best = scan_cell_warp(a.tgt_sorted, a.slab_end + (size_t)rec * kFitSlabs, __ldg(a.cell_start + rec), (float)(xx + gp->min_b[0]) * leaf, sscale, wslack,
+                              qx, qy, qz, best, lane);
+      }
+    }
+    const float safe = (float)r * leaf * 0.999f;
+    decided = r >= 1 && best <= safe * safe;
+  }
+  return decided;
+}
+
 // Pass 1, every query, one thread each: its own cell and the 26 around it, within a budget of kFitBudget steps.  A query that is
 // still undecided (far from every target point, or next to dense cells it could not prune) goes on list 1 with the best distance
 // found so far (a real distance, or +inf).
-constexpr int kFitBudget = 48;               // x 4 points
+constexpr int kFitBudget = 24;               // x 4 points
 __global__ void __launch_bounds__(kFitThreads) fitness_search_kernel(FitnessArgs a) {
   const int i = blockIdx.x * kFitThreads + threadIdx.x;
   if (i >= a.n_src) return;
@@ -211,7 +259,7 @@ __global__ void __launch_bounds__(kFitThreads) fitness_search_kernel(FitnessArgs
   if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) { a.best[i] = -2.0f; return; }   // no neighbour: dropped from the mean
   float best = INFINITY;
   const bool grid_ok = gp->status == 0 && gp->n_cells > 0;
-  const bool decided = grid_ok && search_rings<0, 1, false>(a, gp, qx, qy, qz, best, kFitBudget, 0);
+  const bool decided = grid_ok && search_rings<0, 1>(a, gp, qx, qy, qz, best, kFitBudget);
   a.best[i] = best;
   if (!decided) {
     int* list = grid_ok ? a.list : a.list2;                   // without a grid there is nothing to walk
@@ -221,7 +269,7 @@ __global__ void __launch_bounds__(kFitThreads) fitness_search_kernel(FitnessArgs
 
 // Pass 2, the queries of list 1, one WARP each: all shells again, starting from the best distance of pass 1 (cells that were
 // already scanned prune to nothing).  The heavy and the far queries no longer hold up a warp of easy ones, and a long cell is
-// read with coalesced loads.  Still undecided after shell 3 -> list 2.
+// read with coalesced loads.  Still undecided after the last shell -> list 2.
 __global__ void __launch_bounds__(kFitThreads) fitness_far_kernel(FitnessArgs a) {
   const int n_list = a.list[0];
   const GridParams* gp = a.gp;
@@ -233,7 +281,7 @@ __global__ void __launch_bounds__(kFitThreads) fitness_far_kernel(FitnessArgs a)
     float qx, qy, qz;
     transform_point(a.T16, s.x, s.y, s.z, qx, qy, qz);
     float best = a.best[i];
-    const bool decided = search_rings<0, kFitMaxRing, true>(a, gp, qx, qy, qz, best, 0, lane);
+    const bool decided = search_rings_warp<0, kFitMaxRing>(a, gp, qx, qy, qz, best, lane);
     if (lane == 0) {
       a.best[i] = best;
       if (!decided) a.list2[1 + atomicAdd(a.list2, 1)] = i;
