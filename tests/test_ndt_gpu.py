@@ -405,6 +405,34 @@ def test_fitness_score_matches_oracle(small_pair):
     assert n.getFitnessScore(big, T=truth, with_count=True) == (big, 0)
 
 
+def test_fitness_score_dense_cells_far_queries_and_bad_target_points():
+    """The three passes of the search against the exhaustive scan: a cell with thousands of points next to the queries (the
+    thread pass runs out of budget -> warp pass), queries several cells away from every point (outer shells), queries far outside
+    the grid (brute-force tiles, more than one tile and more than one query group), NaN / inf target points, and a leaf size that
+    is not a power of two (the slab order must hold for the binning arithmetic, not for the ideal cell)."""
+    rng = np.random.default_rng(11)
+    dense = rng.normal([3.4, 2.6, 0.5], [0.25, 0.25, 0.02], size=(6000, 3))              # a slab-like blob inside one or two cells
+    wall = np.stack([np.full(3000, 9.3), rng.uniform(-6, 6, 3000), rng.uniform(0, 3, 3000)], axis=1)
+    sparse = rng.uniform([-20, -20, -1], [20, 20, 3], size=(1500, 3))
+    tgt = np.concatenate([dense, wall, sparse]).astype(np.float32)
+    tgt[::97, 0] = np.nan
+    tgt[5::211, 2] = np.inf
+    near = dense[:1500] + rng.normal(0, [0.6, 0.6, 0.3], size=(1500, 3))                 # around the blob, mostly outside it
+    mid = rng.uniform([-40, -40, -6], [40, 40, 9], size=(1500, 3))                        # up to many cells from anything
+    far = rng.uniform([150, -300, -5], [400, 300, 60], size=(300, 3))                     # outside the grid
+    src = np.concatenate([near, mid, far]).astype(np.float32)
+    big = np.finfo(np.float64).max
+    for res in (1.0, 0.7, 2.0):
+        n, o = _mk(O.VAR_OMP, O.DIRECT7, resolution=res)
+        n.setInputTarget(tgt); n.setInputSource(src)
+        o.set_target(tgt); o.set_source(src)
+        for T, mr in ((np.eye(4, dtype=np.float32), big), (_shift(np.eye(4), 0.3, -0.2, 0.1), 4.0), (_shift(np.eye(4), 0.0, 0.0, 30.0), big)):
+            gs, gn = n.getFitnessScore(mr, T=T, with_count=True)
+            os_, on = o.fitness_score(T, mr)
+            assert gn == on, (res, gn, on)
+            assert abs(gs - os_) <= 1e-12 * os_, (res, gs, os_)
+
+
 def test_fitness_score_full_scan_properties(scan_pair):
     """At BASELINE's full size the exhaustive oracle is too slow; size-independent properties instead."""
     tgt, src, guess, truth = scan_pair
