@@ -209,16 +209,29 @@ __device__ __forceinline__ bool search_rings_warp(const FitnessArgs& a, const Gr
   const float wslack = leaf * (1.01f / (float)kFitSlabs) + slack;
   bool decided = false;
   for (int r = R0; r <= R1 && !decided; r++) {
-    const int n = 2 * r + 1, n3 = n * n * n;
-    for (int c0 = 0; c0 < n3; c0 += 32) {
+    // the cells of shell r, enumerated without the inner cube: the two z faces (n x n each), then for every z in between the two
+    // y edges (n each) and the two x ends of the rows in between
+    const int n = 2 * r + 1, per_mid = 4 * n - 4;
+    const int n_shell = r == 0 ? 1 : 2 * n * n + (n - 2) * per_mid;
+    for (int c0 = 0; c0 < n_shell; c0 += 32) {
       const int c = c0 + lane;
       int v = -1, xcell = 0;
       float h2 = 0.0f;
-      if (c < n3) {
-        const int ox = c % n - r, oy = (c / n) % n - r, oz = c / (n * n) - r;
+      if (c < n_shell) {
+        int ox = 0, oy = 0, oz = 0;
+        if (r > 0) {
+          if (c < 2 * n * n) {
+            const int rem = c % (n * n);
+            oz = c < n * n ? -r : r; oy = rem / n - r; ox = rem % n - r;
+          } else {
+            const int u = c - 2 * n * n, w = u % per_mid;
+            oz = u / per_mid - r + 1;
+            if (w < 2 * n) { oy = w < n ? -r : r; ox = w % n - r; }
+            else { oy = (w - 2 * n) / 2 - r + 1; ox = ((w - 2 * n) & 1) ? r : -r; }
+          }
+        }
         const int x = cx + ox, y = cy + oy, z = cz + oz;
-        const bool shell = max(max(abs(ox), abs(oy)), abs(oz)) == r;        // the inner cube was the previous shells
-        if (shell && (unsigned)x < (unsigned)d0 && (unsigned)y < (unsigned)d1 && (unsigned)z < (unsigned)d2) {
+        if ((unsigned)x < (unsigned)d0 && (unsigned)y < (unsigned)d1 && (unsigned)z < (unsigned)d2) {
           const float gx = ox > 0 ? (float)ox * leaf - fx : (ox < 0 ? fx - (float)(ox + 1) * leaf : 0.0f);
           const float gy = oy > 0 ? (float)oy * leaf - fy : (oy < 0 ? fy - (float)(oy + 1) * leaf : 0.0f);
           const float gz = oz > 0 ? (float)oz * leaf - fz : (oz < 0 ? fz - (float)(oz + 1) * leaf : 0.0f);
