@@ -244,6 +244,7 @@ constexpr int kCholThreads = 256;
 constexpr int kCholMaxTeam = 1024;      // CTAs that may share one front (bounded by the cooperative grid)
 constexpr int kCholBigFront = 192;
 constexpr int kNB = 24;                 // pivot columns per panel
+constexpr int kCholSmemFront = 64;      // fronts up to this many rows are factored in shared memory (single-CTA kernel)
 constexpr int kTile = 96;               // trailing-update tile (16 x 16 threads, 6 x 6 outputs each)      // fronts with F above this go to the team kernel
 
 struct CholView {
@@ -331,10 +332,20 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
   unsigned int target = 0;
   __shared__ double s_D[kNB][kNB + 1], s_S[kNB][kNB + 1], s_inv[kNB];
   __shared__ double s_Li[kNB][kTile + 2], s_Lj[kNB][kTile + 2];
+  extern __shared__ double s_front[];             // single-CTA launches only: room for a front of kCholSmemFront rows
   for (int fi = team; fi < n_list; fi += n_teams) {
     const CholFront f = V.fronts[list[fi]];
-    double* __restrict__ A = V.arena + f.off;
+    double* const A_global = V.arena + f.off;
+    double* A = A_global;
     const int F = f.F, fb = f.w + f.r;            // fb = index of the right-hand-side row block (one row)
+    // A small front is worked on in shared memory: one read and one write of it instead of a global-memory round trip in every
+    // phase (the many small fronts of the lower levels are pure latency).
+    const bool in_smem = !TEAM && F <= kCholSmemFront;
+    if (in_smem) {
+      for (int t = threadIdx.x; t < F * F; t += kCholThreads) s_front[t] = A_global[t];
+      __syncthreads();
+      A = s_front;
+    }
     // ---- extend-add: U_c (child's trailing block, rows R_c + rhs row) into this front through the relative indices
     for (int ci = f.child_begin; ci < f.child_end; ci++) {
       const CholFront c = V.fronts[V.child_idx[ci]];
@@ -504,6 +515,10 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
       }
       team_sync<TEAM>(bar, target, team_size);
     }
+    if (in_smem) {
+      for (int t = threadIdx.x; t < F * F; t += kCholThreads) A_global[t] = s_front[t];
+      __syncthreads();                             // the next front of this CTA reuses the buffer
+    }
   }
 }
 
@@ -658,6 +673,7 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
   C.allocs.push_back((void*)C.fail_flag);
   const size_t smem = (size_t)S.max_front * sizeof(double);
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCholSmemFront * kCholSmemFront * sizeof(double))));
   CUDA_TRY(cudaStreamSynchronize(st));    // the host vectors of S may go away
   return LVS_OK;
 }
@@ -682,7 +698,7 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
     // small fronts: one CTA each; large fronts: teams of CTAs in one cooperative launch
     const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nb = C.big_ptr[l + 1] - C.big_ptr[l];
     if (ns > 0) {
-      chol_front_kernel<false><<<ns, kCholThreads, 0, st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
+      chol_front_kernel<false><<<ns, kCholThreads, kCholSmemFront * kCholSmemFront * sizeof(double), st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
       nl++;
     }
     if (nb > 0) {
