@@ -314,11 +314,14 @@ __device__ __forceinline__ void team_sync(unsigned int* bar, unsigned int& targe
   if (!TEAM) { __syncthreads(); return; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // arrive with release semantics (this CTA's writes, ordered before by the barrier above, become visible with the count) and
+    // without waiting for the atomic's return value; poll with acquire loads
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     target += (unsigned)team_size;
-    while (*reinterpret_cast<volatile unsigned int*>(bar) < target) __nanosleep(40);    // back off: tens of pollers on one L2 line
-    __threadfence();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while (seen < target);
   }
   __syncthreads();
 }
