@@ -292,7 +292,10 @@ def main_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak = peaks.get("hbm_gbs", 6650.0)
+    if isinstance(peak, dict):                         # tolerate {"hbm_gbs": {"value": ...}}
+        peak = next((v for k, v in peak.items() if isinstance(v, (int, float))), 6650.0)
+    peak = float(peak)
     achieved = bytes_total / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     traffic = None
     try:
@@ -300,7 +303,7 @@ def main_ours(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "ndt_eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_total / max(kern_launches, 1), "avg_launch_ms": kern_ms / max(kern_launches, 1),
                 "launches_timed": kern_launches, "kernel_share_of_step": kern_ms / (ms_dev * args.steps),
                 "note": "the kernel is FP32/FP64-issue bound, not HBM bound (float32 per-point math in the reference's exact operation order, 43 fp64 sums per term); see DESIGN.md"}
