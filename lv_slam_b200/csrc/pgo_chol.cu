@@ -242,10 +242,18 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
 // =====================================================================================================================
 constexpr int kCholThreads = 256;
 constexpr int kCholMaxTeam = 1024;      // CTAs that may share one front (bounded by the cooperative grid)
-constexpr int kCholBigFront = 192;
-constexpr int kNB = 24;                 // pivot columns per panel
+constexpr int kCholBigFront = 192;    // fronts with F above this go to the team kernel
+constexpr int kNB = 24;                 // pivot columns per panel of the backward substitution and of the single-CTA front kernel
+constexpr int kNBTeam = 24;             // pivot columns per panel of the team front kernel (48 was measured: 6.2 -> 7.1 ms per solve,
+                                        // the diagonal block and the row solve grow faster than the barriers shrink)
 constexpr int kCholSmemFront = 64;      // fronts up to this many rows are factored in shared memory (single-CTA kernel)
-constexpr int kTile = 96;               // trailing-update tile (16 x 16 threads, 6 x 6 outputs each)      // fronts with F above this go to the team kernel
+constexpr int kTile = 96;               // trailing-update tile (16 x 16 threads, 6 x 6 outputs each)
+template <bool TEAM>
+struct FrontSmem {                      // dynamic shared memory of chol_front_kernel<TEAM>, in doubles
+  static constexpr int NB = TEAM ? kNBTeam : kNB;
+  static constexpr size_t doubles = 2 * NB * (NB + 1) + 2 * NB * (kTile + 2) + NB + (TEAM ? 0 : kCholSmemFront * kCholSmemFront);
+  static constexpr size_t bytes = doubles * sizeof(double);
+};
 
 struct CholView {
   const CholFront* fronts;
@@ -333,9 +341,15 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
   const int tid = rank * kCholThreads + threadIdx.x, nthr = team_size * kCholThreads;
   unsigned int* bar = bars + team;
   unsigned int target = 0;
-  __shared__ double s_D[kNB][kNB + 1], s_S[kNB][kNB + 1], s_inv[kNB];
-  __shared__ double s_Li[kNB][kTile + 2], s_Lj[kNB][kTile + 2];
-  extern __shared__ double s_front[];             // single-CTA launches only: room for a front of kCholSmemFront rows
+  // Panel width per kernel variant; all staging lives in dynamic shared memory (FrontSmem<TEAM>).
+  constexpr int kNB = FrontSmem<TEAM>::NB;
+  extern __shared__ double s_dyn[];
+  double (*s_D)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(s_dyn);
+  double (*s_S)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(s_dyn + kNB * (kNB + 1));
+  double (*s_Li)[kTile + 2] = reinterpret_cast<double (*)[kTile + 2]>(s_dyn + 2 * kNB * (kNB + 1));
+  double (*s_Lj)[kTile + 2] = reinterpret_cast<double (*)[kTile + 2]>(s_dyn + 2 * kNB * (kNB + 1) + kNB * (kTile + 2));
+  double* s_inv = s_dyn + 2 * kNB * (kNB + 1) + 2 * kNB * (kTile + 2);
+  double* s_front = s_inv + kNB;                  // single-CTA launches only: room for a front of kCholSmemFront rows
   for (int fi = team; fi < n_list; fi += n_teams) {
     const CholFront f = V.fronts[list[fi]];
     double* const A_global = V.arena + f.off;
@@ -406,21 +420,25 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
       }
       __syncthreads();
       {
-        // the (up to three) lower-triangle elements this thread owns, fixed for the whole panel
-        int ei[3], ek[3];
+        // the lower-triangle elements this thread owns, fixed for the whole panel
+        constexpr int kOwn = (kNB * kNB + kCholThreads - 1) / kCholThreads;
+        int ei[kOwn], ek[kOwn];
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
+        for (int u = 0; u < kOwn; u++) {
           const int t = threadIdx.x + u * kCholThreads;
           ei[u] = t / kNB; ek[u] = t % kNB;
           if (!(t < kNB * kNB && ei[u] < nb && ek[u] <= ei[u])) { ei[u] = -1; ek[u] = kNB; }     // inactive: i = -1 fails every test below
         }
         for (int j = 0; j < nb; j++) {
-          if (ei[0] > j || ei[1] > j || ei[2] > j || ei[0] == j || ei[1] == j || ei[2] == j) {      // rows above j are finished
+          bool busy = false;
+#pragma unroll
+          for (int u = 0; u < kOwn; u++) busy |= ei[u] >= j;
+          if (busy) {                                                                                 // rows above j are finished
             double d = s_S[j][j];
             if (!(d > 0.0)) { *V.fail_flag = 1; d = 1.0; }     // every thread that sees it stores the same 1
             const double il = rsqrt(d);                // one reciprocal square root instead of sqrt + divide on the serial path
 #pragma unroll
-            for (int u = 0; u < 3; u++) {
+            for (int u = 0; u < kOwn; u++) {
               const int i = ei[u], k = ek[u];
               if (i < j) continue;
               if (k == j) { s_D[i][j] = (i == j) ? d * il : s_S[i][j] * il; if (i == j) s_inv[j] = il; }
@@ -430,17 +448,19 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
           __syncthreads();
         }
       }
-      // (B) rows below the diagonal block: x L_D^T = a, forward substitution along the row
+      // (B) rows below the diagonal block: x L_D^T = a, forward substitution along the row, right-looking: once x_m is final every
+      // later entry takes its term.  Each x_j still receives its terms in the order m = 0, 1, ... (the result does not change),
+      // but consecutive instructions are independent instead of one 276-long chain of dependent multiply-adds.
       {
         for (; i < F; i += nthr) {
 #pragma unroll
-          for (int j = 0; j < kNB; j++) {
-            if (j < nb) {
-              double v = x[j];
+          for (int m = 0; m < kNB; m++) {
+            if (m < nb) {
+              const double xm = x[m] * s_inv[m];
+              x[m] = xm;
+              A[(size_t)(c + m) * F + i] = xm;
 #pragma unroll
-              for (int m = 0; m < kNB; m++) if (m < j) v -= x[m] * s_D[j][m];
-              x[j] = v * s_inv[j];
-              A[(size_t)(c + j) * F + i] = x[j];
+              for (int j = m + 1; j < kNB; j++) x[j] -= xm * s_D[j][m];      // rows of s_D past nb are zero
             }
           }
           if (i + nthr < F) {
@@ -661,7 +681,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     int per_sm = 0, dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_front_kernel<true>, kCholThreads, 0));
+    CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontSmem<true>::bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_front_kernel<true>, kCholThreads, FrontSmem<true>::bytes));
     C.coop_grid = std::max(1, std::min(per_sm, 2) * sms);
     CUDA_TRY(cudaMalloc((void**)&C.bars, (size_t)C.coop_grid * sizeof(unsigned int)));
     C.allocs.push_back((void*)C.bars);
@@ -676,7 +697,7 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
   C.allocs.push_back((void*)C.fail_flag);
   const size_t smem = (size_t)S.max_front * sizeof(double);
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCholSmemFront * kCholSmemFront * sizeof(double))));
+  CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontSmem<false>::bytes));
   CUDA_TRY(cudaStreamSynchronize(st));    // the host vectors of S may go away
   return LVS_OK;
 }
@@ -701,7 +722,7 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
     // small fronts: one CTA each; large fronts: teams of CTAs in one cooperative launch
     const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nb = C.big_ptr[l + 1] - C.big_ptr[l];
     if (ns > 0) {
-      chol_front_kernel<false><<<ns, kCholThreads, kCholSmemFront * kCholSmemFront * sizeof(double), st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
+      chol_front_kernel<false><<<ns, kCholThreads, FrontSmem<false>::bytes, st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
       nl++;
     }
     if (nb > 0) {
@@ -712,11 +733,11 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
       int grid = n_teams * team_size;
       const int* list = C.big_list + C.big_ptr[l];
       int n_list = nb;
-      if (team_size == 1) chol_front_kernel<false><<<grid, kCholThreads, 0, st>>>(V, list, n_list, 1, C.bars);
+      if (team_size == 1) chol_front_kernel<false><<<grid, kCholThreads, FrontSmem<false>::bytes, st>>>(V, list, n_list, 1, C.bars);
       else {
         CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)n_teams * sizeof(unsigned int), st));
         void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars};
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_front_kernel<true>, dim3(grid), dim3(kCholThreads), args, 0, st));
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_front_kernel<true>, dim3(grid), dim3(kCholThreads), args, FrontSmem<true>::bytes, st));
       }
       nl++;
     }
