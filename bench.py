@@ -306,7 +306,7 @@ def main_ours(args):
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_total / max(kern_launches, 1), "avg_launch_ms": kern_ms / max(kern_launches, 1),
                 "launches_timed": kern_launches, "kernel_share_of_step": kern_ms / (ms_dev * args.steps),
-                "note": "the kernel is FP32/FP64-issue bound, not HBM bound (float32 per-point math in the reference's exact operation order, 43 fp64 sums per term); see DESIGN.md"}
+                "note": "the kernel is bound by the float->double conversion pipe (XU 62 % busy, issue 59 %: profiles/r01_final/ndt_eval_ncu_summary.txt), not by HBM: float32 per-point math in the reference's exact operation order, 43 fp64 sums per term; see DESIGN.md section 5"}
 
     line = {"metric": METRIC, "value": world * B / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
