@@ -1,4 +1,5 @@
-"""Pose-graph timing on BASELINE config 4 (5 000 vertices / 19 599 edges) and config 5's graph (50 000 / 198 999)."""
+"""Pose-graph timing on BASELINE config 4 (5 000 vertices / 19 599 edges) and, with --big, config 5's graph (50 000 / 198 999);
+--no-cpu skips the CPU oracle legs."""
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
@@ -7,7 +8,9 @@ import lv_slam_b200 as L
 import oracle_pgo as P
 from lv_slam_b200.synth import posegraph as G
 
-for (npl, laps, cpu) in ((100, 50, True), (250, 200, "--big" in sys.argv)):
+for (npl, laps, cpu) in ((100, 50, "--no-cpu" not in sys.argv), (250, 200, "--big" in sys.argv and "--no-cpu" not in sys.argv)):
+    if npl == 250 and "--big" not in sys.argv:
+        continue
     t = time.time(); g = G.sphere(npl, laps, seed=7); tg = time.time() - t
     print("graph %d vertices / %d edges (generated in %.1f s)" % (len(g["poses7"]), len(g["ij"]), tg))
     for solver, name in ((0, "lm_var (exact solve)"), (2, "lm_pcg")):
