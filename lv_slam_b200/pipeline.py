@@ -168,7 +168,7 @@ def replay(scans, odom_registration, loop_registration, graph_slam, info_calc, p
     est = [np.asarray(k["node"].estimate(), dtype=np.float64) for k in keyframes]
     if dump_directory is not None:
         from . import keyframe_io
-        recs = [dict(stamp=(int(k["frame"] * stamp_step), int(round((k["frame"] * stamp_step) % 1.0 * 1e9))), seq=k["frame"], estimate=e, odom=k["odom"],
+        recs = [dict(stamp=divmod(int(round(k["frame"] * stamp_step * 1e9)), 10 ** 9), seq=k["frame"], estimate=e, odom=k["odom"],
                      accum_distance=k["accum_distance"], id=k["node"].id(), cloud=k["cloud"]) for k, e in zip(keyframes, est)]
         keyframe_io.dump(dump_directory, graph_slam, recs, dict(enumerate(odom_poses)), tf_velo2cam)
     return dict(odom=odom_poses, keyframe_frames=[k["frame"] for k in keyframes], loops=loops, optimized=est, iterations=iters,
