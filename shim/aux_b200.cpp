@@ -9,6 +9,7 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <stdexcept>
+#include <vector>
 #include "lvslam_b200.h"
 
 namespace lv_slam {

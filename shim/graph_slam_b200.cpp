@@ -7,7 +7,12 @@
 #include <g2o/core/sparse_optimizer.h>
 #include <g2o/types/slam3d/edge_se3.h>
 #include <g2o/types/slam3d/vertex_se3.h>
+#include <algorithm>
+#include <cstdint>
 #include <iostream>
+#include <map>
+#include <string>
+#include <vector>
 #include "lvslam_b200.h"
 
 namespace lv_slam {

@@ -8,6 +8,8 @@
 #include <pcl/registration/registration.h>
 #include <limits>
 #include <stdexcept>
+#include <string>
+#include <vector>
 #include "lvslam_b200.h"
 
 #ifdef LVS_SHIM_PCA

@@ -343,3 +343,38 @@ def test_save_pose_distributes_the_correction_as_the_reference_writes_it(tmp_pat
     np.testing.assert_allclose(wf[0], np.eye(4), atol=1e-9)
     np.testing.assert_allclose(wf[2], odoms[2] @ rz(32.0, (0.1, 0, 0)), atol=1e-6)
     np.testing.assert_allclose(wf[4], odoms[4] @ corr, atol=1e-6)
+
+
+def test_shims_compile_and_link_against_the_abi(tmp_path):
+    """The reference-side bindings of shim/  need PCL, Eigen, g2o and boost, none of which is in this image.
+    They are compiled here against interface stubs (tests/shim_stubs: the names and signatures the shims touch, nothing more), with
+    the registration classes instantiated for the reference's three point types in both namespaces, and linked against
+    liblvslam_b200.so with --no-undefined: every ABI call in the shims type-checks against include/lvslam_b200.h and resolves."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    stubs = os.path.join(ROOT, "tests", "shim_stubs")
+    inc = ["-I" + stubs, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shim")]
+    units = [("graph_slam", [os.path.join(ROOT, "shim", "graph_slam_b200.cpp")]), ("aux", [os.path.join(ROOT, "shim", "aux_b200.cpp")]),
+             ("ndt_omp", [os.path.join(stubs, "instantiate.cpp")]), ("ndt_pca", ["-DLVS_SHIM_PCA", "-Dshim_probe=shim_probe_pca", os.path.join(stubs, "instantiate.cpp")])]
+    objs = []
+    for name, args in units:
+        o = str(tmp_path / (name + ".o"))
+        r = subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-fPIC", "-c"] + inc + args + ["-o", o], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        objs.append(o)
+    lib_dir = os.path.join(ROOT, "lv_slam_b200")
+    so = str(tmp_path / "libshim.so")
+    r = subprocess.run(["g++", "-shared"] + objs + ["-o", so, "-L" + lib_dir, "-llvslam_b200", "-Wl,--no-undefined", "-Wl,-rpath," + lib_dir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    und = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True).stdout
+    used = sorted({ln.split()[-1] for ln in und.splitlines() if ln.split() and ln.split()[-1].startswith("lvs_")})
+    header = open(os.path.join(ROOT, "include", "lvslam_b200.h")).read()
+    assert used and all(sym + "(" in header for sym in used), used
+    # both namespaces carry the three instantiations
+    defined = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True).stdout
+    for ns in ("pclomp", "pclpca"):
+        for pt in ("PointXYZ,", "PointXYZI,", "PointXYZRGBL,"):
+            assert any(ns + "::NormalDistributionsTransform<pcl::" + pt in ln and "computeTransformation" in ln for ln in defined.splitlines()), (ns, pt)
