@@ -354,6 +354,8 @@ def test_shims_compile_and_link_against_the_abi(tmp_path):
     import subprocess
     if shutil.which("g++") is None:
         pytest.skip("no g++")
+    from lv_slam_b200 import build
+    build.build()
     stubs = os.path.join(ROOT, "tests", "shim_stubs")
     inc = ["-I" + stubs, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shim")]
     units = [("graph_slam", [os.path.join(ROOT, "shim", "graph_slam_b200.cpp")]), ("aux", [os.path.join(ROOT, "shim", "aux_b200.cpp")]),
