@@ -380,3 +380,27 @@ def test_shims_compile_and_link_against_the_abi(tmp_path):
     for ns in ("pclomp", "pclpca"):
         for pt in ("PointXYZ,", "PointXYZI,", "PointXYZRGBL,"):
             assert any(ns + "::NormalDistributionsTransform<pcl::" + pt in ln and "computeTransformation" in ln for ln in defined.splitlines()), (ns, pt)
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as pedantic C99 and a C translation unit that takes the address of every
+    declared entry point links against the library (what a cgo / JNI / ctypes-free binding would do)."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from lv_slam_b200 import build
+    build.build()
+    hdr = os.path.join(ROOT, "include", "lvslam_b200.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    src = tmp_path / "caller.c"
+    names = _declared_functions()
+    src.write_text('#include "lvslam_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n  fn table[] = {\n'
+                   + "".join("    (fn)%s,\n" % n for n in names) + "  };\n  printf(\"%d\\n\", (int)(sizeof table / sizeof table[0]));\n  return 0;\n}\n")
+    exe = str(tmp_path / "caller")
+    lib_dir = os.path.join(ROOT, "lv_slam_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe, "-L" + lib_dir, "-llvslam_b200", "-Wl,-rpath," + lib_dir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and int(out.stdout) == len(names)
