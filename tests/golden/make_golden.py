@@ -26,6 +26,18 @@ json.dump(dict(n_cells=len(lv["keys"]), n_usable=int((lv["nr_points"] >= 6).sum(
                gradient=g.tolist(), hessian=H.tolist(), iterations=r["iterations"], final=r["final"].astype(float).tolist()),
           open(os.path.join(HERE, "ndt_small_pair.json"), "w"), indent=1)
 
+# the stages either side of the path on the same pair
+big = float(np.finfo(np.float64).max)
+fit = {}
+for name, T, mr in (("truth", truth, big), ("guess", guess, big), ("guess_capped", guess, 0.25)):
+    sc, cnt = o.fitness_score(T, mr)
+    fit[name] = dict(score=sc, correspondences=cnt)
+cloud = np.concatenate([tgt[:, :3], np.random.default_rng(3).random((len(tgt), 1), dtype=np.float32)], axis=1).astype(np.float32)
+pf, _ = O.prefilter(cloud, 0.5, 100.0, True, 0.1)
+json.dump(dict(fitness=fit, prefilter=dict(n_in=len(cloud), n_out=len(pf), column_sums=pf.astype(np.float64).sum(axis=0).tolist(),
+                                           first=pf[0].astype(float).tolist(), last=pf[-1].astype(float).tolist())),
+          open(os.path.join(HERE, "aux_small_pair.json"), "w"), indent=1)
+
 gr = G.sphere(20, 10, seed=7)
 p = P.OraclePGO()
 p.set_graph(gr["poses7"], gr["ij"], gr["meas7"], gr["info21"], gr["huber"])

@@ -243,3 +243,24 @@ def test_prefilter_known_answers():
     # PCL's overflow guard: 1e-4 m leaves over a 140 m extent do not fit int32 -> the cloud passes through, flag set
     out, fl = O.prefilter(pts[:, :3], near=0.5, far=1000.0, leaf=1e-4)
     assert fl == 1 and np.array_equal(out, pts[[1, 2, 3, 4, 6], :3])
+
+
+def test_golden_regression_of_fitness_and_prefilter(small_pair):
+    """tests/golden/aux_small_pair.json (written by make_golden.py from this oracle): the restatements of getFitnessScore and of the
+    prefilter chain pinned against accidental edits; the correspondence counts and the output size are exact."""
+    gold = json.load(open(os.path.join(HERE, "golden", "aux_small_pair.json")))
+    tgt, src, guess, truth = small_pair
+    o = O.OracleNDT(trans_eps=0.01, max_iter=30, search=O.DIRECT7, num_threads=1)
+    o.set_target(tgt); o.set_source(src)
+    big = float(np.finfo(np.float64).max)
+    for name, T, mr in (("truth", truth, big), ("guess", guess, big), ("guess_capped", guess, 0.25)):
+        sc, cnt = o.fitness_score(T, mr)
+        assert cnt == gold["fitness"][name]["correspondences"]
+        np.testing.assert_allclose(sc, gold["fitness"][name]["score"], rtol=1e-12)
+    cloud = np.concatenate([tgt[:, :3], np.random.default_rng(3).random((len(tgt), 1), dtype=np.float32)], axis=1).astype(np.float32)
+    pf, _ = O.prefilter(cloud, 0.5, 100.0, True, 0.1)
+    g = gold["prefilter"]
+    assert len(cloud) == g["n_in"] and len(pf) == g["n_out"]
+    np.testing.assert_allclose(pf.astype(np.float64).sum(axis=0), g["column_sums"], rtol=1e-12)
+    np.testing.assert_array_equal(pf[0], np.array(g["first"], np.float32))
+    np.testing.assert_array_equal(pf[-1], np.array(g["last"], np.float32))
