@@ -106,13 +106,16 @@ class GraphSLAM:
         edge.kernel = (kernel_type, float(kernel_size))
 
     def _arrays(self):
+        """The flat arrays lvs_pgo_set_graph takes (what shim/graph_slam_b200.cpp packs from the g2o containers), vectorised: the
+        per-object version cost 0.4 s for 5 000 vertices / 19 599 edges, more than the whole LM run on the device."""
         nv, ne = len(self._vertices), len(self._edges)
-        poses = np.array([_pg.pose7(v._T) for v in self._vertices]).reshape(nv, 7)
-        fixed = np.array([1 if v._fixed else 0 for v in self._vertices], dtype=np.uint8)
-        ij = np.array([[e.vertices[0]._id, e.vertices[1]._id] for e in self._edges], dtype=np.int32).reshape(ne, 2)
-        meas = np.array([_pg.pose7(e.measurement) for e in self._edges]).reshape(ne, 7)
-        info = np.array([[e.information[r, c] for r in range(6) for c in range(r, 6)] for e in self._edges]).reshape(ne, 21)
-        hub = np.array([e.kernel[1] if e.kernel else 0.0 for e in self._edges])
+        poses = _pg.pose7_batch(np.stack([v._T for v in self._vertices])) if nv else np.zeros((0, 7))
+        fixed = np.fromiter((1 if v._fixed else 0 for v in self._vertices), dtype=np.uint8, count=nv)
+        ij = np.fromiter((x for e in self._edges for x in (e.vertices[0]._id, e.vertices[1]._id)), dtype=np.int32, count=2 * ne).reshape(ne, 2)
+        meas = _pg.pose7_batch(np.stack([e.measurement for e in self._edges])) if ne else np.zeros((0, 7))
+        iu = np.triu_indices(6)
+        info = np.stack([e.information for e in self._edges])[:, iu[0], iu[1]] if ne else np.zeros((0, 21))
+        hub = np.fromiter((e.kernel[1] if e.kernel else 0.0 for e in self._edges), dtype=np.float64, count=ne)
         return poses, fixed, ij, meas, info, hub
 
     def optimize(self, num_iterations):
@@ -122,8 +125,8 @@ class GraphSLAM:
         st = optimize_arrays(self._L, self._handle(), poses, fixed, ij, meas, info, hub, num_iterations)
         out = np.zeros((len(self._vertices), 7))
         C.check(self._L.lvs_pgo_get_poses(self._handle(), out.ctypes.data))
-        for v, p in zip(self._vertices, out):
-            v._T = _pg.matrix(p)
+        for v, T in zip(self._vertices, _pg.matrix_batch(out)):
+            v._T = T
         self.last_stats = st
         print("chi2: (before)%g -> (after)%g" % (st["chi2_before"], st["chi2_after"]))
         return st["iterations"]

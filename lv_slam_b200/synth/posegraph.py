@@ -51,11 +51,62 @@ def pose7(T):
     return np.concatenate([T[:3, 3], q])
 
 
+def pose7_batch(T):
+    """pose7 of a stack of matrices [n, 4, 4] -> [n, 7]; the same branches and operations as _quat_from_R, taken per matrix."""
+    T = np.asarray(T, dtype=np.float64).reshape(-1, 4, 4)
+    R = T[:, :3, :3]
+    n = len(T)
+    q = np.zeros((n, 4))
+    tr = R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    pos = tr > 0
+    if pos.any():
+        Rp = R[pos]
+        t = np.sqrt(tr[pos] + 1.0)
+        w = 0.5 * t
+        t = 0.5 / t
+        q[pos] = np.stack([(Rp[:, 2, 1] - Rp[:, 1, 2]) * t, (Rp[:, 0, 2] - Rp[:, 2, 0]) * t, (Rp[:, 1, 0] - Rp[:, 0, 1]) * t, w], axis=1)
+    if not pos.all():
+        idx = np.zeros(n, dtype=np.int64)
+        idx[R[:, 1, 1] > R[:, 0, 0]] = 1
+        d = R[np.arange(n), idx, idx]
+        idx[R[:, 2, 2] > d] = 2
+        for i in range(3):
+            m = (~pos) & (idx == i)
+            if not m.any():
+                continue
+            j, k = (i + 1) % 3, (i + 2) % 3
+            Rm = R[m]
+            t = np.sqrt(Rm[:, i, i] - Rm[:, j, j] - Rm[:, k, k] + 1.0)
+            qm = np.zeros((len(Rm), 4))
+            qm[:, i] = 0.5 * t
+            t = 0.5 / t
+            qm[:, 3] = (Rm[:, k, j] - Rm[:, j, k]) * t
+            qm[:, j] = (Rm[:, j, i] + Rm[:, i, j]) * t
+            qm[:, k] = (Rm[:, k, i] + Rm[:, i, k]) * t
+            q[m] = qm
+    q /= np.sqrt((q * q).sum(axis=1))[:, None]
+    return np.concatenate([T[:, :3, 3], q], axis=1)
+
+
 def matrix(p7):
     T = np.eye(4)
     q = np.asarray(p7[3:7], dtype=np.float64)
     T[:3, :3] = _R_from_quat(q / np.linalg.norm(q))
     T[:3, 3] = p7[:3]
+    return T
+
+
+def matrix_batch(p7):
+    """matrix() of a stack of 7-vectors [n, 7] -> [n, 4, 4]."""
+    p7 = np.asarray(p7, dtype=np.float64).reshape(-1, 7)
+    q = p7[:, 3:7] / np.sqrt((p7[:, 3:7] * p7[:, 3:7]).sum(axis=1))[:, None]
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    T = np.zeros((len(p7), 4, 4))
+    T[:, 0, 0] = 1 - 2 * (y * y + z * z); T[:, 0, 1] = 2 * (x * y - z * w); T[:, 0, 2] = 2 * (x * z + y * w)
+    T[:, 1, 0] = 2 * (x * y + z * w); T[:, 1, 1] = 1 - 2 * (x * x + z * z); T[:, 1, 2] = 2 * (y * z - x * w)
+    T[:, 2, 0] = 2 * (x * z - y * w); T[:, 2, 1] = 2 * (y * z + x * w); T[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    T[:, :3, 3] = p7[:, :3]
+    T[:, 3, 3] = 1.0
     return T
 
 
