@@ -12,12 +12,17 @@ timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exi
 timeout 600 python bench.py --variant pca > $OUT/bench_pca.json 2> $OUT/bench_pca.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 timeout 300 python tools/gpu_first.py > $OUT/gpu_first.log 2>&1
-timeout 400 python tools/pgo_perf.py > $OUT/pgo_perf.log 2>&1
+timeout 400 python tools/pgo_perf.py --no-cpu --big > $OUT/pgo_perf.log 2>&1     # GPU legs of configs 4 and 5 (the CPU legs: tools/pgo_perf.py, ~25 s)
 timeout 300 python tools/aux_perf.py > $OUT/aux_perf.log 2>&1
 timeout 300 python tools/chol_profile.py 100 50 5 > $OUT/chol_solve.log 2>&1
 # launch list of the bench command (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
+# per-launch lists of the two secondary paths: one direct pose-graph solve, three getFitnessScore calls
+timeout 200 ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none --csv --log-file $OUT/chol_launches.csv \
+    python tools/chol_profile.py 100 50 1 > $OUT/chol_ncu.log 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/fitness_launches.csv \
+    python tools/fitness_profile.py > $OUT/fitness_ncu.log 2>&1
 # full capture of the hot kernel inside the batched bench step
 # (the first align of an object queues 6 evaluation launches, later ones as many as the previous align needed + 1 = 4: launches 0-5
 #  warm-up resident, 6-9 warm-up host path, 10-13 the timed RESIDENT step - 10, 11, 12 are the working 64-pair launches bench.py's
