@@ -5,7 +5,6 @@ import json
 import os
 
 import numpy as np
-import pytest
 
 import oracle_pgo as P
 from lv_slam_b200.synth import posegraph as G

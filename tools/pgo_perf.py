@@ -3,7 +3,6 @@
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
-import numpy as np
 import lv_slam_b200 as L
 import oracle_pgo as P
 from lv_slam_b200.synth import posegraph as G
