@@ -285,31 +285,6 @@ __global__ void __launch_bounds__(kCholThreads) chol_scatter_kernel(CholView V, 
   }
 }
 
-// In-place Cholesky of a 6x6 tile (lower triangle), executed by one thread.  Returns false when a pivot is not positive.
-__device__ __forceinline__ bool chol6_inplace(double* A, int ld, double* inv_diag) {
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    double d = A[(size_t)j * ld + j];
-#pragma unroll
-    for (int k = 0; k < 6; k++) if (k < j) d -= A[(size_t)k * ld + j] * A[(size_t)k * ld + j];
-    if (!(d > 0.0)) { ok = false; d = 1.0; }
-    const double l = sqrt(d), il = 1.0 / l;
-    A[(size_t)j * ld + j] = l;
-    inv_diag[j] = il;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      if (i > j) {
-        double s = A[(size_t)j * ld + i];
-#pragma unroll
-        for (int k = 0; k < 6; k++) if (k < j) s -= A[(size_t)k * ld + i] * A[(size_t)k * ld + j];
-        A[(size_t)j * ld + i] = s * il;
-      }
-    }
-  }
-  return ok;
-}
-
 // Fronts of one level.  A front is worked on by a TEAM of CTAs (team_size 1 for the many small fronts of the lower levels, tens
 // of CTAs for the few large fronts near the root); teams take the fronts of the list round-robin.  Inside a team the phases are
 // separated by a team barrier: __syncthreads for a single CTA, otherwise an arrive/spin counter in global memory (all CTAs are
@@ -354,7 +329,7 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
     const CholFront f = V.fronts[list[fi]];
     double* const A_global = V.arena + f.off;
     double* A = A_global;
-    const int F = f.F, fb = f.w + f.r;            // fb = index of the right-hand-side row block (one row)
+    const int F = f.F;                            // the right-hand side is row F - 1
     // A small front is worked on in shared memory: one read and one write of it instead of a global-memory round trip in every
     // phase (the many small fronts of the lower levels are pure latency).
     const bool in_smem = !TEAM && F <= kCholSmemFront;
