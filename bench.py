@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--e2e-group", type=int, default=64, help="pairs per align call on the host-buffer path")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs timed for cpu_baseline (0 = sized for ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--accumulation", default="exact", choices=["exact", "fast"], help="lvs_ndt_params::accumulation of the timed object")
     return ap.parse_args()
 
 
@@ -197,7 +198,8 @@ def main_ours(args):
     from lv_slam_b200.ndt import CloudBatch, pack_guesses
     # two slot sets: while the aligns of step k run on one, the clouds of step k + 1 are copied and voxelised into the other
     nk = len(keys)
-    nb = L.NdtBatch(2 * nk, 2 * B, device=local_rank, stream=stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64, **vp)
+    nb = L.NdtBatch(2 * nk, 2 * B, device=local_rank, stream=stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64,
+                    accumulation=1 if args.accumulation == "fast" else 0, **vp)
     tgt_all = [list(range(p * nk, (p + 1) * nk)) for p in (0, 1)]
     src_all = [list(range(p * B, (p + 1) * B)) for p in (0, 1)]
     src_slots = [np.arange(p * B, (p + 1) * B, dtype=np.int32) for p in (0, 1)]

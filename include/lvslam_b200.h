@@ -47,6 +47,15 @@ typedef enum {
 typedef enum { LVS_KDTREE = 0, LVS_DIRECT26 = 1, LVS_DIRECT7 = 2, LVS_DIRECT1 = 3 } lvs_search_method;
 /* which of the two registration classes is mirrored */
 typedef enum { LVS_NDT_OMP = 0, LVS_NDT_PCA = 1 } lvs_ndt_variant;
+/* How the per-(point, cell) terms of computeDerivatives (ndt_omp_impl2.hpp:567-619) are formed and summed.
+ *   LVS_ACC_EXACT (default): every float32 term is formed in the reference's operation order without contraction (bit-identical to
+ *                 the CPU path, expf included) and added in fp64, like `hessian(i,j) += float_expr` does.
+ *   LVS_ACC_FAST : tolerance mode.  Terms are formed in float32 with fused multiply-adds and a hardware exp2, the 31 distinct
+ *                 sums (score, gradient, symmetric translation blocks of H, full rotation block) are kept per thread in float32
+ *                 for at most 32 terms and then added in fp64.  Voxel indices stay bit-exact.  Agrees with LVS_ACC_EXACT to
+ *                 ~1e-6 relative on (score, g, H), i.e. <= 1e-4 m / 1e-5 rad per Newton iteration; about 3x faster.
+ * KDTREE search and the all-double computeHessian pass always run exact. */
+typedef enum { LVS_ACC_EXACT = 0, LVS_ACC_FAST = 1 } lvs_ndt_accumulation;
 
 /* Parameters = the setters of the reference class; defaults = its constructor
  * (include/ndt_omp/ndt_omp_impl2.hpp:54-83). */
@@ -60,6 +69,7 @@ typedef struct {
   int32_t variant;             /* LVS_NDT_OMP | LVS_NDT_PCA */
   int32_t min_points_per_voxel;  /* VoxelGridCovariance default 6 (voxel_grid_covariance_omp.h:204) */
   double min_covar_eigvalue_mult; /* 0.01 (voxel_grid_covariance_omp.h:205) */
+  int32_t accumulation;        /* lvs_ndt_accumulation; not a reference parameter (LVS_ACC_EXACT) */
 } lvs_ndt_params;
 
 /* What the reference object exposes after align(): getFinalTransformation, hasConverged,

@@ -8,10 +8,11 @@ LIB_PATH = os.path.join(_HERE, "liblvslam_b200.so")
 
 LVS_KDTREE, LVS_DIRECT26, LVS_DIRECT7, LVS_DIRECT1 = 0, 1, 2, 3
 LVS_NDT_OMP, LVS_NDT_PCA = 0, 1
+LVS_ACC_EXACT, LVS_ACC_FAST = 0, 1
 
 STATUS = {0: "LVS_OK", -1: "LVS_ERR_INVALID_ARG", -2: "LVS_ERR_NO_DEVICE", -3: "LVS_ERR_CUDA", -4: "LVS_ERR_OOM",
           -5: "LVS_ERR_NO_TARGET", -6: "LVS_ERR_NO_SOURCE", -7: "LVS_ERR_GRID_OVERFLOW", -8: "LVS_ERR_BAD_SLOT",
-          -9: "LVS_ERR_NOT_SPD", -10: "LVS_ERR_EMPTY_GRAPH"}
+          -9: "LVS_ERR_NOT_SPD", -10: "LVS_ERR_EMPTY_GRAPH", -11: "LVS_ERR_PEER"}
 
 
 class LvsError(RuntimeError):
@@ -23,7 +24,8 @@ class LvsError(RuntimeError):
 class NdtParams(ctypes.Structure):
     _fields_ = [("resolution", ctypes.c_float), ("step_size", ctypes.c_double), ("outlier_ratio", ctypes.c_double),
                 ("transformation_epsilon", ctypes.c_double), ("max_iterations", ctypes.c_int32), ("search_method", ctypes.c_int32),
-                ("variant", ctypes.c_int32), ("min_points_per_voxel", ctypes.c_int32), ("min_covar_eigvalue_mult", ctypes.c_double)]
+                ("variant", ctypes.c_int32), ("min_points_per_voxel", ctypes.c_int32), ("min_covar_eigvalue_mult", ctypes.c_double),
+                ("accumulation", ctypes.c_int32)]
 
 
 class NdtResult(ctypes.Structure):

@@ -21,7 +21,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-st
           "--expt-relaxed-constexpr"]
 NO_FMA = ["-fmad=false"]
 # (source, extra flags): the pose-graph code is fp64 throughout and compared to tolerance, so it keeps FMA contraction
-SOURCES = [("ndt_voxel.cu", NO_FMA), ("ndt_eval.cu", NO_FMA), ("ndt_eval_cold.cu", NO_FMA), ("ndt_api.cu", NO_FMA), ("ndt_fitness.cu", NO_FMA), ("prefilter.cu", NO_FMA), ("pgo.cu", []), ("pgo_chol.cu", [])]
+SOURCES = [("ndt_voxel.cu", NO_FMA), ("ndt_eval.cu", NO_FMA), ("ndt_eval_fast.cu", NO_FMA), ("ndt_eval_cold.cu", NO_FMA), ("ndt_api.cu", NO_FMA), ("ndt_fitness.cu", NO_FMA), ("prefilter.cu", NO_FMA), ("pgo.cu", []), ("pgo_chol.cu", [])]
 
 
 def _deps():

@@ -322,4 +322,40 @@ LVS_HD void matrix4f_to_se3_log(const float* M, double* p) {
   se3_log(P, p);
 }
 
+// ---- expf, as the reference binds it.  updateDerivatives calls unqualified `exp` on a float (include/ndt_omp/ndt_omp_impl2.hpp:581).
+// Under PCL's headers (<pcl/pcl_macros.h> includes <math.h>; libstdc++'s <math.h> wrapper does `using std::exp`) overload resolution
+// picks std::exp(float) = expf, i.e. glibc's single-precision routine (>= 2.27 on the reference's Ubuntu 18.04: sysdeps/ieee754/
+// flt-32/e_expf.c + e_exp2f_data.c, EXP2F_TABLE_BITS = 5, cubic polynomial, evaluated in double and rounded once to float).
+// This is that routine restated operation by operation, with the contractions of glibc's FMA build (the ifunc variant every
+// x86-64 CPU since Haswell selects): bit-identical to the host's expf over ALL 2.24e9 finite floats in [-104, 88.8]
+// (tools/expf_sweep.c; without the contraction of `z - kd` it differs in one input per sign).  T[i] = bits(2^(i/32)) - (i << 47).
+#ifdef __CUDACC__
+static __constant__ unsigned long long c_exp2f_tab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL, 0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL,
+    0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL, 0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL, 0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL,
+    0x3feea11473eb0187ULL, 0x3feea589994cce13ULL, 0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL, 0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL,
+    0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+
+// tab: the 32-entry table above, in shared memory (the index is lane-divergent) or in global memory.
+__device__ __forceinline__ float glibc_expf(float x, const unsigned long long* tab) {
+  if (!(x >= -0x1.9fe368p6f)) return x != x ? x + x : 0.0f;      // NaN; x < log(2^-150): underflow to +0 (and -inf)
+  if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);      // x > log(2^128): overflow
+  const double xd = (double)x;
+  const double z = __dmul_rn(0x1.71547652b82fep+5, xd);          // x * 32 / ln 2 (intrinsics: never contracted, whatever -fmad says)
+  double kd = __dadd_rn(z, 0x1.8p+52);                           // round to integer through the shift constant
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, 0x1.8p+52);
+  const double r = fma(0x1.71547652b82fep+5, xd, -kd);
+  const unsigned long long t = tab[ki & 31ULL] + (ki << 47);
+  const double s = __longlong_as_double((long long)t);
+  const double zz = fma(0x1.c6af84b912394p-20, r, 0x1.ebfce50fac4f3p-13);
+  const double r2 = __dmul_rn(r, r);
+  double y = fma(0x1.62e42ff0c52d6p-6, r, 1.0);
+  y = fma(zz, r2, y);
+  return (float)__dmul_rn(y, s);
+}
+#endif
+
 }  // namespace lvs

@@ -41,6 +41,7 @@ static AlignConsts make_consts(const lvs_ndt_params& p) {
   c.search = p.search_method;
   c.variant = p.variant;
   c.resolution = p.resolution;
+  c.fast = p.accumulation == LVS_ACC_FAST;
   return c;
 }
 
@@ -51,6 +52,7 @@ static int check_params(const lvs_ndt_params* p) {
   if (p->variant != LVS_NDT_OMP && p->variant != LVS_NDT_PCA) return fail(LVS_ERR_INVALID_ARG, "unknown variant %d", p->variant);
   if (p->max_iterations < 0 || p->max_iterations > kMaxTrace - 4) return fail(LVS_ERR_INVALID_ARG, "max_iterations must be in [0, %d]", kMaxTrace - 4);
   if (p->min_points_per_voxel < 1) return fail(LVS_ERR_INVALID_ARG, "min_points_per_voxel must be >= 1");
+  if (p->accumulation != LVS_ACC_EXACT && p->accumulation != LVS_ACC_FAST) return fail(LVS_ERR_INVALID_ARG, "unknown accumulation %d", p->accumulation);
   return LVS_OK;
 }
 
@@ -366,6 +368,7 @@ static PairDesc make_pair(lvs_ndt_batch* b, int src_slot, int tgt_slot) {
   P.n_total = b->sources[src_slot].n_total;
   P.grid = tg.d_grid;
   P.recs = tg.d_recs;
+  P.frecs = tg.d_frecs;
   P.centroids = tg.d_centroids;
   P.icov64 = tg.d_icov64;
   P.gp = tg.d_gp;
@@ -830,6 +833,7 @@ void lvs_ndt_default_params(lvs_ndt_params* p) {
   p->variant = LVS_NDT_OMP;
   p->min_points_per_voxel = 6;
   p->min_covar_eigvalue_mult = 0.01;
+  p->accumulation = LVS_ACC_EXACT;
 }
 
 const char* lvs_status_string(int status) {

@@ -17,14 +17,6 @@
 
 namespace lvs {
 
-// DIRECT7 probes, in the reference's order (voxel_grid_covariance_omp_impl.hpp:423-430): centre, +x, -x, +y, -y, +z, -z.
-// pcl::getAllNeighborCellIndices (PCL 1.8 voxel_grid.h): 13 half-offsets, then their negatives; no centre cell.
-__constant__ int c_off26[26][3] = {
-    {-1, -1, -1}, {-1, 0, -1}, {-1, 1, -1}, {0, -1, -1}, {0, 0, -1}, {0, 1, -1}, {1, -1, -1}, {1, 0, -1}, {1, 1, -1},
-    {-1, -1, 0},  {0, -1, 0},  {1, -1, 0},  {-1, 0, 0},
-    {1, 1, 1},    {1, 0, 1},   {1, -1, 1},  {0, 1, 1},   {0, 0, 1},  {0, -1, 1},  {-1, 1, 1},  {-1, 0, 1},  {-1, -1, 1},
-    {1, 1, 0},    {0, 1, 0},   {-1, 1, 0},  {1, 0, 0}};
-
 // ---- packed FP32 (sm_100 FMUL2 / FFMA2): one issue slot carries two IEEE float operations, each rounded exactly like the scalar
 // instruction, so every term stays bit-identical to the CPU path while the float math of a contribution needs about half the
 // issue slots.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false (seen with CUDA 12.9), which
@@ -72,7 +64,7 @@ struct Shape {
 //   Cp[r] = (C[r][0], C[r][1]),  C2[r] = C[r][2]
 template <bool HESS>
 __device__ __forceinline__ bool contribute_tile(float2* __restrict__ col /* tile + lane */, float xr, float yr, float zr, float d0, float d1,
-                                                float d2, const f32x2* Cp, const float* C2, float gd2, double gauss_d1, f32x2 one) {
+                                                float d2, const f32x2* Cp, const float* C2, float gd2, double gauss_d1, f32x2 one, const unsigned long long* etab) {
   constexpr int RS = kTileStride / 2;      // row stride in float2
   const float nx = -xr, ny = -yr, nz = -zr;
   // P[r][k], k = 0..2: row r of [C | C * dR-columns] = (CJ[r][2k], CJ[r][2k+1])
@@ -91,7 +83,7 @@ __device__ __forceinline__ bool contribute_tile(float2* __restrict__ col /* tile
   for (int k = 0; k < 3; k++) A[k] = add2(add2(mul2s(d0, P[0][k]), mul2s(d2, P[2][k]), one), mul2s(d1, P[1][k]), one);
   const float xC0 = lo_of(A[0]), xC1 = hi_of(A[0]), xC2 = lo_of(A[1]);
   const float q = (d0 * xC0 + d2 * xC2) + d1 * xC1;
-  float e = (float)exp((double)((-gd2 * q) * 0.5f));
+  float e = glibc_expf((-gd2 * q) * 0.5f, etab);      // the reference's exp(float) is expf (lvs_math.cuh)
   const float score_inc = (float)(-gauss_d1 * (double)e);
   e = gd2 * e;
   if (e > kOne || e < 0.0f || e != e) return false;
@@ -171,7 +163,7 @@ static_assert(sizeof(double) * kWarps * kPairsH * 2 * 4 <= SmemLayout<false>::by
 // starts at +0.0 never becomes -0.0, so no per-group predicate is needed in the summation.
 template <bool HESS, bool PCA>
 __device__ __forceinline__ void process_round(double (*acc)[2], const VoxelRec* __restrict__ recs, const float* pts, const int* q, const double* qw,
-                                              float* tile, int lane, int head, int n_round, float gd2, double gd1, f32x2 one) {
+                                              float* tile, int lane, int head, int n_round, float gd2, double gd1, f32x2 one, const unsigned long long* etab) {
   using Sh = Shape<HESS>;
   bool used = false;
   double w = 0.0;
@@ -190,7 +182,7 @@ __device__ __forceinline__ void process_round(double (*acc)[2], const VoxelRec* 
     const float tx = pts[0 * kPtsPerIter + slot], ty = pts[1 * kPtsPerIter + slot], tz = pts[2 * kPtsPerIter + slot];
     const float d0 = (float)((double)tx - m01.x), d1 = (float)((double)ty - m01.y), d2 = (float)((double)tz - m2);
     used = contribute_tile<HESS>(col, pts[3 * kPtsPerIter + slot], pts[4 * kPtsPerIter + slot], pts[5 * kPtsPerIter + slot], d0, d1, d2, Cp, C2,
-                                 gd2, gd1, one);
+                                 gd2, gd1, one, etab);
     if (PCA) w = qw[head + lane];
   }
   if (!used) {
@@ -223,14 +215,9 @@ __device__ __forceinline__ void process_round(double (*acc)[2], const VoxelRec* 
   __syncwarp();
 }
 
-template <int MODE> struct Probes;
-template <> struct Probes<LVS_DIRECT1> { static constexpr int K = 1; };
-template <> struct Probes<LVS_DIRECT7> { static constexpr int K = 7; };
-template <> struct Probes<LVS_DIRECT26> { static constexpr int K = 26; };
-
 template <int MODE, bool HESS, bool PCA>
 __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2,
-                                           double gd1, unsigned char* s_dyn, double* partial, float one_f) {
+                                           double gd1, unsigned char* s_dyn, double* partial, float one_f, const unsigned long long* etab) {
   using Sh = Shape<HESS>;
   constexpr int K = Probes<MODE>::K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -261,7 +248,7 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
       auto drain = [&]() {
         __syncwarp();
         int head = 0;
-        for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, 32, gd2, gd1, one);
+        for (; nq - head >= 32; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, 32, gd2, gd1, one, etab);
         const int rem = nq - head;
         int ent = 0; double we = 0.0;
         if (lane < rem) { ent = q[head + lane]; if (PCA) we = qw[head + lane]; }
@@ -325,7 +312,7 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
       static_assert(MODE != LVS_DIRECT1 || kPtsPerLane * 32 <= kQueueCap, "queue capacity");
       __syncwarp();
       // ---- phase B: rounds of 32 queued (point, cell) contributions
-      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, min(32, nq - head), gd2, gd1, one);
+      for (int head = 0; head < nq; head += 32) process_round<HESS, PCA>(acc, recs, pts, q, qw, tile, lane, head, min(32, nq - head), gd2, gd1, one, etab);
     }
   }
   // CTA partial: s_red[warp][slot][group] (aliases the tile region) -> every output slot sums its 4 lane groups over the 8 warps in
@@ -361,6 +348,7 @@ template <int MODE, bool PCA>
 __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ float s_T[16], s_R[9];
+  __shared__ unsigned long long s_etab[32];
   __shared__ int s_last;
   const int pair = blockIdx.x / L.blocks_per_pair, blk = blockIdx.x % L.blocks_per_pair;
   AlignState& S = L.d_states[pair];
@@ -370,13 +358,14 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const PairDesc P = L.d_pairs[pair];
   if (threadIdx.x < 16) s_T[threadIdx.x] = S.T[threadIdx.x];
   if (threadIdx.x < 9) s_R[threadIdx.x] = S.Rj[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 64) s_etab[threadIdx.x - 32] = c_exp2f_tab[threadIdx.x - 32];
   __syncthreads();
   const GridView G = load_grid_view(P.gp);
   const float gd2 = (float)c.gauss_d2;
   double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
   const int bpp = L.blocks_per_pair;
-  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one);
-  else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one);
+  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
+  else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
   eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last);
 }
 
@@ -399,6 +388,7 @@ static int launch_eval_as(cudaStream_t st, const EvalLaunch& L) {
 // loop, no weight staging for ndt_omp); whether the Hessian is wanted is per-pair state and is decided inside.
 int launch_eval(cudaStream_t st, const EvalLaunch& L) {
   if (L.n_pairs <= 0) return LVS_OK;
+  if (L.consts.fast) return launch_eval_fast(st, L);       // tolerance mode: ndt_eval_fast.cu
   const bool pca = L.consts.variant == LVS_NDT_PCA;
   switch (L.consts.search) {
     case LVS_DIRECT1: return pca ? launch_eval_as<LVS_DIRECT1, true>(st, L) : launch_eval_as<LVS_DIRECT1, false>(st, L);

@@ -33,7 +33,7 @@ __device__ __forceinline__ void contribute(Acc<HESS>& A, float xr, float yr, flo
   const float xC1 = (d0 * C[1] + d2 * C[7]) + d1 * C[4];
   const float xC2 = (d0 * C[2] + d2 * C[8]) + d1 * C[5];
   const float q = (d0 * xC0 + d2 * xC2) + d1 * xC1;
-  float e = (float)exp((double)((-gd2 * q) * 0.5f));
+  float e = glibc_expf((-gd2 * q) * 0.5f, c_exp2f_tab);      // the reference's exp(float) is expf (lvs_math.cuh)
   const float score_inc = (float)(-gauss_d1 * (double)e);
   e = gd2 * e;
   if (e > kOne || e < 0.0f || e != e) return;

@@ -9,6 +9,20 @@ namespace lvs {
 constexpr int kEvalThreads = 256;
 constexpr float kOne = 1.0f;
 
+// DIRECT7 probes, in the reference's order (voxel_grid_covariance_omp_impl.hpp:423-430): centre, +x, -x, +y, -y, +z, -z.
+// pcl::getAllNeighborCellIndices (PCL 1.8 voxel_grid.h): 13 half-offsets, then their negatives; no centre cell.
+static __constant__ int c_off26[26][3] = {
+    {-1, -1, -1}, {-1, 0, -1}, {-1, 1, -1}, {0, -1, -1}, {0, 0, -1}, {0, 1, -1}, {1, -1, -1}, {1, 0, -1}, {1, 1, -1},
+    {-1, -1, 0},  {0, -1, 0},  {1, -1, 0},  {-1, 0, 0},
+    {1, 1, 1},    {1, 0, 1},   {1, -1, 1},  {0, 1, 1},   {0, 0, 1},  {0, -1, 1},  {-1, 1, 1},  {-1, 0, 1},  {-1, -1, 1},
+    {1, 1, 0},    {0, 1, 0},   {-1, 1, 0},  {1, 0, 0}};
+
+template <int MODE> struct Probes;
+template <> struct Probes<LVS_DIRECT1> { static constexpr int K = 1; };
+template <> struct Probes<LVS_DIRECT7> { static constexpr int K = 7; };
+template <> struct Probes<LVS_DIRECT26> { static constexpr int K = 26; };
+
+
 struct GridView {
   int min_b[3], max_b[3], mul[3];
   float leaf;

@@ -49,6 +49,7 @@ struct TargetGrid {                      // one voxelised target resident in HBM
   int* d_grid = nullptr;                 // dense int32 index grid, -1 = empty
   size_t grid_capacity = 0;
   VoxelRec* d_recs = nullptr;
+  FastRec* d_frecs = nullptr;           // tolerance-mode twin of d_recs
   float4* d_centroids = nullptr;         // float centroid (kd-tree cloud of the reference), w = 1 if in that cloud
   int* d_cell_keys = nullptr;
   int* d_cell_npts = nullptr;
@@ -124,6 +125,8 @@ struct EvalLaunch {
 };
 int launch_eval(cudaStream_t st, const EvalLaunch& L);        // direct-search derivative passes (hot)
 int launch_eval_cold(cudaStream_t st, const EvalLaunch& L);   // KDTREE-mode derivatives and the all-double Hessian pass
+int launch_eval_fast(cudaStream_t st, const EvalLaunch& L);   // tolerance-mode direct-search derivative passes (ndt_eval_fast.cu)
+int eval_fast_max_resident_ctas_per_sm();
 int eval_max_resident_ctas_per_sm();
 int eval_points_per_cta_iteration();
 int launch_calc_score(cudaStream_t st, const PairDesc& pair, const float* d_T16, const AlignConsts& c, double* d_partials, int max_blocks,

@@ -20,6 +20,16 @@ struct __align__(16) VoxelRec {
 };
 static_assert(sizeof(VoxelRec) == 64, "VoxelRec must be 64 bytes");
 
+// Record of the same cell for the tolerance-mode evaluation (lvs_ndt_params::accumulation = LVS_ACC_FAST), 48 B, three LDG.128:
+//   mh + ml : the double mean split into two floats (mh = float(mean), ml = float(mean - mh)): (x' - mh) - ml reproduces the
+//             reference's double subtraction to ~1e-7 m without a conversion instruction
+//   c       : float inverse covariance, upper triangle c00 c01 c02 c11 c12 c22 (V*L*V^-1 rebuilt covariances are symmetric to ~1e-16)
+struct __align__(16) FastRec {
+  float mh[3], ml[3];
+  float c[6];
+};
+static_assert(sizeof(FastRec) == 48, "FastRec must be 48 bytes");
+
 // storage position of the row-major element a = 3 r + c inside VoxelRec::icov
 __host__ __device__ constexpr int icov_slot(int a) { return (a % 3 == 2) ? 6 + a / 3 : 2 * (a / 3) + a % 3; }
 
@@ -84,6 +94,7 @@ struct AlignConsts {
   int search;
   int variant;
   float resolution;
+  int fast;                 // lvs_ndt_params::accumulation == LVS_ACC_FAST
 };
 
 // One (source, target) pair as the kernels see it.
@@ -93,6 +104,7 @@ struct PairDesc {
   int n_total;              // points of the whole source cloud (trans_probability divisor, ndt_omp_impl2.hpp:187)
   const int* grid;
   const VoxelRec* recs;
+  const FastRec* frecs;     // tolerance-mode records (same indices as recs)
   const float4* centroids;
   const double* icov64;     // [n_cells][9] double inverse covariance (computeHessian / calculateScore are all-double)
   const GridParams* gp;

@@ -49,7 +49,7 @@ struct VoxJob {
   int *hist, *hist_scan, *tile_tot, *flags, *pos, *nseg, *nvalid;
   int* sorted; int* cell_start;
   double* moments; float* csum;
-  VoxelRec* recs; float4* centroids; int* cell_keys; int* cell_npts; double* cell_evals; double* icov64;
+  VoxelRec* recs; FastRec* frecs; float4* centroids; int* cell_keys; int* cell_npts; double* cell_evals; double* icov64;
   int nblk;                                                  // radix tiles of this job
 };
 struct VoxBatch {
@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(128) leaf_finalize_kernel(VoxBatch B, int cur)
   const double* __restrict__ moments = J.moments;
   const float* __restrict__ csum = J.csum;
   VoxelRec* __restrict__ recs = J.recs;
+  FastRec* __restrict__ frecs = J.frecs;
   float4* __restrict__ centroids = J.centroids;
   int* __restrict__ cell_keys = J.cell_keys;
   int* __restrict__ cell_npts = J.cell_npts;
@@ -512,6 +513,12 @@ __global__ void __launch_bounds__(128) leaf_finalize_kernel(VoxBatch B, int cur)
       }
     }
     recs[seg] = rec;
+    {
+      FastRec fr;
+      for (int a = 0; a < 3; a++) { fr.mh[a] = (float)mean[a]; fr.ml[a] = (float)(mean[a] - (double)fr.mh[a]); }
+      fr.c[0] = (float)ic[0]; fr.c[1] = (float)ic[1]; fr.c[2] = (float)ic[2]; fr.c[3] = (float)ic[4]; fr.c[4] = (float)ic[5]; fr.c[5] = (float)ic[8];
+      frecs[seg] = fr;
+    }
     for (int a = 0; a < 9; a++) icov64[(size_t)seg * 9 + a] = ic[a];
     cell_keys[seg] = key;
     cell_npts[seg] = out_npts;
@@ -619,7 +626,7 @@ int TargetGrid::enqueue_many(cudaStream_t st, int count, TargetGrid* const* grid
       VoxJob& J = B.j[k];
       J.pts = g.pts; J.n = g.n_points; J.leaf = prm.resolution; J.grid_capacity = (long long)g.grid_capacity; J.gp = g.d_gp;
       J.grid = g.d_grid; J.old_keys = g.d_cell_keys; J.prev_points = g.prev_points;
-      J.recs = g.d_recs; J.centroids = g.d_centroids; J.cell_keys = g.d_cell_keys; J.cell_npts = g.d_cell_npts; J.cell_evals = g.d_cell_evals;
+      J.recs = g.d_recs; J.frecs = g.d_frecs; J.centroids = g.d_centroids; J.cell_keys = g.d_cell_keys; J.cell_npts = g.d_cell_npts; J.cell_evals = g.d_cell_evals;
       J.icov64 = g.d_icov64;
       job_scratch(J, *wss[base + k], passes, g.d_sorted_idx, g.d_cell_start);
       max_prev = std::max(max_prev, g.prev_points);
@@ -684,6 +691,7 @@ int TargetGrid::prepare(cudaStream_t st, const float4* d_pts, int n, const lvs_n
     if (d_grid) CUDA_TRY(cudaMemsetAsync(d_grid, 0xFF, grid_capacity * sizeof(int), st));
     size_t cap = (size_t)n + n / 8 + 64;
     CUDA_TRY(cudaMalloc(&d_recs, cap * sizeof(VoxelRec)));
+    CUDA_TRY(cudaMalloc(&d_frecs, cap * sizeof(FastRec)));
     CUDA_TRY(cudaMalloc(&d_centroids, cap * sizeof(float4)));
     CUDA_TRY(cudaMalloc(&d_cell_keys, cap * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_cell_npts, cap * sizeof(int)));
@@ -755,6 +763,8 @@ int TargetGrid::accept(const GridParams& g, cudaStream_t st, BuildScratch& ws) {
 
 void TargetGrid::free_cells() {
   if (d_recs) cudaFree(d_recs);
+  if (d_frecs) cudaFree(d_frecs);
+  d_frecs = nullptr;
   if (d_centroids) cudaFree(d_centroids);
   if (d_cell_keys) cudaFree(d_cell_keys);
   if (d_cell_npts) cudaFree(d_cell_npts);

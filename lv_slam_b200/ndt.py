@@ -166,6 +166,10 @@ class NormalDistributionsTransform:
     def setNumThreads(self, n):
         pass  # OpenMP team size of the reference; meaningless on the device
 
+    def setAccumulation(self, mode):
+        """Not a reference setter: LVS_ACC_EXACT (default, the reference's arithmetic) or LVS_ACC_FAST (tolerance mode)."""
+        self._p.accumulation = int(mode); self._push()
+
     def getResolution(self):
         return self._p.resolution
 

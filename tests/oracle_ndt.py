@@ -55,6 +55,7 @@ def lib():
         L.ose3_exp.restype = None; L.ose3_exp.argtypes = [vp, vp, vp]
         L.ose3_log_from_matrix4f.restype = None; L.ose3_log_from_matrix4f.argtypes = [vp, vp]
         L.ose3_compose_log.restype = None; L.ose3_compose_log.argtypes = [vp, vp, vp]
+        L.oracle_expf_restated.restype = ctypes.c_longlong; L.oracle_expf_restated.argtypes = [vp, vp, ctypes.c_longlong]
         L.olin_svd6_solve.restype = None; L.olin_svd6_solve.argtypes = [vp, vp, vp, vp]
         L.olin_sym3_eig.restype = None; L.olin_sym3_eig.argtypes = [vp, vp, vp]
         _lib = L
@@ -259,3 +260,11 @@ def sym3_eig(A):
     ev, V = np.zeros(3), np.zeros((3, 3))
     lib().olin_sym3_eig(A.ctypes.data, ev.ctypes.data, V.ctypes.data)
     return ev, V
+
+
+def expf_restated(x):
+    """(restated glibc expf of x, number of inputs where it differs from the host libm's expf bit for bit)."""
+    x = _f32(x)
+    out = np.empty_like(x)
+    bad = lib().oracle_expf_restated(x.ctypes.data, out.ctypes.data, x.size)
+    return out, int(bad)

@@ -264,3 +264,25 @@ def test_golden_regression_of_fitness_and_prefilter(small_pair):
     np.testing.assert_allclose(pf.astype(np.float64).sum(axis=0), g["column_sums"], rtol=1e-12)
     np.testing.assert_array_equal(pf[0], np.array(g["first"], np.float32))
     np.testing.assert_array_equal(pf[-1], np.array(g["last"], np.float32))
+
+
+def test_expf_restatement_matches_the_host_libm():
+    """updateDerivatives calls exp on a float, which binds to glibc's expf (oracle/ndt_oracle.cpp header).  The oracle calls the
+    host's expf; the device path restates the routine (csrc/lvs_math.cuh: glibc_expf).  The restatement must be the host routine
+    bit for bit: 4M random arguments over the range the score can produce, a dense run of consecutive floats, the special cases.
+    (tools/expf_sweep.c runs all 2.24e9 finite floats of [-104, 88.8].)"""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([
+        -rng.random(2_000_000, dtype=np.float32) * 104.0,
+        -np.exp(rng.uniform(-40, 4.7, 1_000_000)).astype(np.float32),
+        rng.random(500_000, dtype=np.float32) * 88.8,
+        np.arange(0xC0000000, 0xC0000000 + 500_000, dtype=np.uint32).view(np.float32),
+        np.array([0.0, -0.0, -87.3, -87.4, -103.27, -103.9, -103.98, -104.5, -1e30, -np.inf, 88.7, 88.73, 1e30, np.inf, np.nan,
+                  -float.fromhex("0x1.f8cbb2p+5"), 1e-45, -1e-45], dtype=np.float32)])
+    out, bad = O.expf_restated(x)
+    assert bad == 0
+    assert out[-4] != out[-4]                       # NaN in, NaN out
+    fin = np.isfinite(x) & (np.abs(x) < 88)
+    ref = np.exp(x[fin].astype(np.float64))
+    ok = ref > 1e-37
+    assert np.abs(out[fin][ok] / ref[ok] - 1).max() < 1.2e-7       # <= 1 ulp of float
