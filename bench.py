@@ -1,11 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — NDT scan-pair aligns/sec on the synthetic 64-beam scan stream (BASELINE.json configs[1]).
+"""bench.py — NDT scan-pair aligns/sec on the synthetic 64-beam scan stream (BASELINE.json configs[1]), plus one sub-record per
+other BASELINE config so that every configuration is measured by the driver's own run.
 
 A step = one pass of the hot path over one batch of the stream: voxelise every keyframe target the batch needs
 (setInputTarget), stage every scan (setInputSource) and run all scan-to-keyframe aligns of the batch in one batched call
 (pclomp semantics: DIRECT7, 1.0 m voxels, epsilon 0.01, <= 64 iterations; constant-velocity guesses as in
 src/lidar_odometry/scan_matching_odom_nodelet.cpp:249-250).  `value` is timed with the raw clouds already in HBM,
 `e2e` goes through the C-ABI from pinned host buffers with the H2D copies and the result read-back inside the timed region.
+
+Top level = the library's default arithmetic (LVS_ACC_EXACT: the reference's float32 terms bit for bit, fp64 sums).  Sub-records:
+  modes.tolerance       the same workload with lvs_ndt_params::accumulation = LVS_ACC_FAST (north_star's 1e-4 m / 1e-5 rad bar)
+  configs.pca_direct1   pclpca / DIRECT1, what the odometry nodelet runs (scan_matching_odom_nodelet.cpp:109-119), both modes
+  configs.pair_latency  BASELINE configs[0]: one hard pair from the first-frame guess (66 iterations), single-object API
+  configs.beam128       BASELINE configs[2]: 128-beam scans (~240 k points), 0.5 m voxels; point-sharded across ranks when N > 1
+  configs.pgo           BASELINE configs[3]: 5 000-vertex / 19 599-edge sphere, LM and GN with the direct solver, LM with PCG
+Each carries its own cpu_baseline (the CPU restatement in oracle/, timed here) where one was run.
 
     python bench.py [--gpus N --steps K --warmup W]            # our arm (one process per GPU under torchrun for N > 1)
     python bench.py --impl reference [...]                     # the reference's CPU path (oracle restatement, OpenMP)
@@ -25,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ndt_scan_pair_aligns_per_sec"
 UNIT = "aligns/s"
+SMS, SMSP_PER_SM = 148, 4
 
 
 def parse():
@@ -34,20 +44,21 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="scan pairs per step per GPU")
-    ap.add_argument("--variant", default="omp", choices=["omp", "pca"])
+    ap.add_argument("--variant", default="omp", choices=["omp", "pca"], help="registration of the TOP-LEVEL record")
+    ap.add_argument("--accumulation", default="exact", choices=["exact", "fast"], help="lvs_ndt_params::accumulation of the TOP-LEVEL record")
     ap.add_argument("--e2e-group", type=int, default=64, help="pairs per align call on the host-buffer path")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs timed for cpu_baseline (0 = sized for ~15 s)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs timed for cpu_baseline (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--accumulation", default="exact", choices=["exact", "fast"], help="lvs_ndt_params::accumulation of the timed object")
+    ap.add_argument("--no-extras", action="store_true", help="top-level record only (no modes / configs sub-records)")
     return ap.parse_args()
 
 
-def make_workload(batch, rank):
+def make_workload(batch, rank, n_beams=64, n_az=2000):
     """Frames [rank*span, rank*span + batch + 2) of the synthetic drive, seed 1000."""
     from lv_slam_b200 import dist as D
     from lv_slam_b200 import synth
     start, span = D.frame_range(rank, batch)
-    scans, poses = synth.stream(span, seed=1000, start=start)
+    scans, poses = synth.stream(span, seed=1000, start=start, n_beams=n_beams, n_az=n_az)
     plan = synth.keyframe_plan(poses)[:batch]
     keys = sorted({k for _, k, _ in plan})
     return scans, poses, plan, keys
@@ -119,12 +130,13 @@ class ClockSampler:
         return out
 
 
-def oracle_for(variant):
+# ------------------------------------------------------------------------------------------------ CPU legs (the checker, timed)
+def oracle_for(variant, threads=None, resolution=1.0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_ndt as O  # the checker; only the cpu_baseline / --impl reference legs reach this
     vp = variant_params(variant)
-    threads = os.cpu_count() or 1
-    o = O.OracleNDT(variant=vp["variant"], resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=64,
+    threads = threads or (os.cpu_count() or 1)
+    o = O.OracleNDT(variant=vp["variant"], resolution=resolution, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=64,
                     search={2: O.DIRECT7, 3: O.DIRECT1}[vp["search_method"]], num_threads=threads)
     return o, threads
 
@@ -143,15 +155,29 @@ def run_cpu_pairs(o, scans, plan, idx):
     return time.perf_counter() - t0, finals
 
 
+def cpu_thread_sweep(variant, scans, plan, n_sample, resolution=1.0):
+    """aligns/s of the CPU path with the thread counts the reference itself configures: 4 (odometry, scan_matching_odom_nodelet.cpp:116)
+    and 8 (loop closure, launch/dlo_lfa_ggo_kitti.launch:112), on the first n_sample pairs of the batch."""
+    out = {}
+    n = min(n_sample, len(plan))
+    for th in (4, 8):
+        if th > (os.cpu_count() or 1):
+            continue
+        o, _ = oracle_for(variant, th, resolution)
+        dt, _ = run_cpu_pairs(o, scans, plan, list(range(n)))
+        out["threads_%d" % th] = {"value": n / dt, "unit": UNIT, "sample": "first %d pairs of the batch, %.1f s" % (n, dt)}
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     scans, poses, plan, keys = make_workload(args.batch, 0)
     o, threads = oracle_for(args.variant)
-    sample = list(range(min(4, len(plan))))
-    for _ in range(args.warmup):
-        run_cpu_pairs(o, scans, plan, sample)
+    sample = list(range(len(plan)))                 # the step of the repo arm: the whole batch, every keyframe voxelisation included
+    for _ in range(min(args.warmup, 1)):            # the CPU path has no warm-up effects beyond page faults: one short pass is enough
+        run_cpu_pairs(o, scans, plan, sample[:4])
     t = 0.0
     for _ in range(args.steps):
         dt, _ = run_cpu_pairs(o, scans, plan, sample)
@@ -159,21 +185,355 @@ def main_reference(args):
     ms = 1e3 * t / args.steps
     val = len(sample) / (ms / 1e3)
     n_pts = int(np.mean([scans[f].shape[0] for f, _, _ in plan]))
+    cb = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+          "sample": "the repo arm's step: %d scan pairs, %d keyframe voxelisations per step" % (len(sample), len(keys))}
+    cb.update(cpu_thread_sweep(args.variant, scans, plan, 16))
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": workload_config(args, n_pts, len(keys)),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d scan pairs of the step's batch per step (1 keyframe voxelisation + %d aligns)" % (len(sample), len(sample))},
+            "config": workload_config(args, n_pts, len(keys)), "cpu_baseline": cb,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(args, n_pts, n_keys):
-    vp = variant_params(args.variant)
-    return {"workload": "synthetic 64-beam scan stream, scan-to-keyframe NDT (BASELINE configs[1])", "pairs_per_step_per_gpu": args.batch,
-            "keyframes_per_step_per_gpu": n_keys, "points_per_scan": n_pts, "resolution_m": 1.0,
+def workload_config(args, n_pts, n_keys, variant=None, accumulation=None, resolution=1.0, name=None):
+    vp = variant_params(variant or args.variant)
+    return {"workload": name or "synthetic 64-beam scan stream, scan-to-keyframe NDT (BASELINE configs[1])", "pairs_per_step_per_gpu": args.batch,
+            "keyframes_per_step_per_gpu": n_keys, "points_per_scan": n_pts, "resolution_m": resolution,
             "registration": "pclomp/DIRECT7" if vp["variant"] == 0 else "pclpca/DIRECT1", "transformation_epsilon": 0.01, "max_iterations": 64,
+            "accumulation": accumulation or args.accumulation,
+            "guesses": "constant-velocity predictions of a smooth drive: every align stops at the minimum (2 iterations, 3 evaluations) - "
+                       "a best case per align; configs.pair_latency is the 66-iteration case",
             "l2_policy": "inputs larger than L2 (%.0f MB of clouds per step vs 126 MB L2)" % ((args.batch + n_keys) * n_pts * 16 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------ the NDT stream measurement
+def load_kernel_stats():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ndt_eval_traffic.json")))
+    except Exception:
+        return {}
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def hbm_peak():
+    peaks = load_peaks()
+    peak = peaks.get("hbm_gbs", 6650.0)
+    if isinstance(peak, dict):                         # tolerate {"hbm_gbs": {"value": ...}}
+        peak = next((v for k, v in peak.items() if isinstance(v, (int, float))), 6650.0)
+    return float(peak), ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+class StreamBench:
+    """The batched scan-to-keyframe workload on one NdtBatch object (one registration variant, one accumulation mode)."""
+
+    def __init__(self, args, L, torch, dist, D, rank, local_rank, world, scans, poses, plan, keys, variant, accumulation, resolution=1.0, buffers=None):
+        from lv_slam_b200.ndt import CloudBatch, pack_guesses
+        self.args, self.L, self.torch, self.dist, self.D, self.rank, self.world = args, L, torch, dist, D, rank, world
+        self.scans, self.poses, self.plan, self.keys = scans, poses, plan, keys
+        self.variant, self.accumulation, self.resolution = variant, accumulation, resolution
+        self.B = B = len(plan)
+        self.key_slot = {k: i for i, k in enumerate(keys)}
+        vp = variant_params(variant)
+        self.stream = torch.cuda.Stream()
+        nk = len(keys)
+        # two slot sets: while the aligns of step k run on one, the clouds of step k + 1 are copied and voxelised into the other
+        self.nb = L.NdtBatch(2 * nk, 2 * B, device=local_rank, stream=self.stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64,
+                             resolution=resolution, accumulation=1 if accumulation == "fast" else 0, **vp)
+        self.tgt_all = [list(range(p * nk, (p + 1) * nk)) for p in (0, 1)]
+        self.src_all = [list(range(p * B, (p + 1) * B)) for p in (0, 1)]
+        self.src_slots = [np.arange(p * B, (p + 1) * B, dtype=np.int32) for p in (0, 1)]
+        self.tgt_slots = [np.array([self.key_slot[k] + p * nk for _, k, _ in plan], dtype=np.int32) for p in (0, 1)]
+        self.guesses = pack_guesses([g for _, _, g in plan])          # [B, 16] column-major, the layout the C-ABI takes
+        if buffers is None:
+            # resident copies (value) and pinned host copies (e2e); the buffers are the same every step: marshal their pointers once
+            # (what a C++ caller's std::vector<const float*> is)
+            dev_src = [torch.from_numpy(scans[f]).cuda() for f, _, _ in plan]
+            dev_tgt = [torch.from_numpy(scans[k]).cuda() for k in keys]
+            pin_src = [torch.from_numpy(scans[f]).pin_memory() for f, _, _ in plan]
+            pin_tgt = [torch.from_numpy(scans[k]).pin_memory() for k in keys]
+            buffers = tuple(CloudBatch(x) for x in (dev_src, dev_tgt, pin_src, pin_tgt))
+        self.buffers = buffers
+
+    def stage(self, p, src, tgt):
+        """setInputTarget of the step's keyframes + setInputSource of its scans into slot set p (asynchronous: copies, repacks and the
+        batched voxelisation are queued on the library's upload / build streams)."""
+        self.nb.set_targets(self.tgt_all[p], tgt)
+        self.nb.set_sources(self.src_all[p], src)
+
+    def run_steps(self, src, tgt, steps, group):
+        """`steps` passes over the batch, software-pipelined: the aligns of a step are queued (align_begin), then the NEXT step's clouds
+        are staged into the other slot set, then the results are collected (align_end) - so host-to-device copies and
+        voxelisations overlap the aligns of the step before.  Every copy, every voxelisation and every result read-back of the
+        `steps` steps happens between the first stage() and the last align_end(), i.e. inside the timed region."""
+        nb, B = self.nb, self.B
+        stats = {"deriv_kernel_ms": 0.0, "deriv_launches": 0, "n_eval": 0}
+        out = None
+        self.stage(0, src, tgt)
+        for k in range(steps):
+            p = k & 1
+            out = None
+            for a in range(0, B, group):
+                nb.align_begin(self.src_slots[p][a:a + group], self.tgt_slots[p][a:a + group], self.guesses[a:a + group])
+                if a == 0 and k + 1 < steps:
+                    self.stage(1 - p, src, tgt)
+                r = nb.align_end()
+                out = r if out is None else out + r
+                st = nb.last_stats()
+                stats["deriv_kernel_ms"] += st["deriv_kernel_ms"]; stats["deriv_launches"] += st["deriv_launches"]
+            stats["n_eval"] += int(out.n_eval.sum())
+        return out, stats
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, src, tgt, steps, profile, group):
+        torch, nb = self.torch, self.nb
+        nb.set_profiling(profile)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = nb.total_launches()
+        self.barrier()
+        with torch.cuda.stream(self.stream):
+            ev0.record(self.stream)
+            res, st = self.run_steps(src, tgt, steps, group)
+            ev1.record(self.stream)
+        self.barrier()
+        ms = self.D.max_over_ranks(ev0.elapsed_time(ev1), self.world, "cuda")
+        nb.set_profiling(0)
+        return ms / steps, nb.total_launches() - launches0, st["deriv_kernel_ms"], st["deriv_launches"], st["n_eval"], res
+
+    def measure(self, steps, warmup, with_e2e=True, sampler=None):
+        """-> dict with value / e2e / roofline of this object's workload.  Rank 0 gets the roofline; every rank takes part."""
+        args, B, world = self.args, self.B, self.world
+        dev_src, dev_tgt, pin_src, pin_tgt = self.buffers
+        g_e2e = max(1, min(B, args.e2e_group))
+        self.timed(dev_src, dev_tgt, warmup, 0, B)
+        if with_e2e:
+            self.timed(pin_src, pin_tgt, warmup, 0, g_e2e)
+        if sampler is not None:
+            sampler.start()
+        ms_dev, launches, kern_ms, kern_launches, n_eval_total, res = self.timed(dev_src, dev_tgt, steps, 1, B)
+        rec = {"value": world * B / (ms_dev / 1e3), "unit": UNIT, "ms_per_step": ms_dev, "gpu_launches": int(launches),
+               "evaluations_per_align": n_eval_total / (steps * B)}
+        if with_e2e:
+            xfer0 = self.nb.transfer_bytes()
+            ms_e2e, _, _, _, _, res_e2e = self.timed(pin_src, pin_tgt, steps, 0, g_e2e)
+            xfer1 = self.nb.transfer_bytes()
+            rec["e2e"] = {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": (xfer1[0] - xfer0[0]) // steps,
+                          "d2h_bytes_per_step": (xfer1[1] - xfer0[1]) // steps, "ms_per_step": ms_e2e, "pairs_per_align_call": g_e2e,
+                          "pipeline": "two slot sets: step k+1's clouds are copied and voxelised while step k's aligns run; every copy and read-back of the timed steps is inside the timed region"}
+            rec["e2e_results_identical_to_resident"] = bool(all(np.array_equal(a["final"], b["final"]) for a, b in zip(res, res_e2e)))
+        if sampler is not None:
+            rec["clocks"] = sampler.stop()              # sampled every 20 ms across the timed regions
+        # sanity: the aligns registered the stream (pose error against the generator's ground truth)
+        rec["max_translation_error_vs_truth_m"] = max(float(np.abs(r["final"][:3, 3] - (np.linalg.inv(self.poses[k]) @ self.poses[f])[:3, 3]).max())
+                                                      for r, (f, k, _) in zip(res, self.plan))
+        self.results = res
+        if self.rank == 0:
+            rec["roofline"] = self.roofline(res, steps, ms_dev, kern_ms, kern_launches, rec.get("clocks"))
+        return rec
+
+    def roofline(self, res, steps, ms_dev, kern_ms, kern_launches, clocks):
+        """HBM roof (what the contract asks for) and, next to it, the roof that actually binds this kernel: the issue rate."""
+        # SURVEY.md §8d algorithmic bytes = 16 B per source point + 48 B per usable voxel, per evaluation
+        bytes_total = 0.0
+        for r, (f, k, _) in zip(res, self.plan):
+            n_valid = self.nb.num_cells(self.key_slot[k])[1]
+            bytes_total += r["n_eval"] * (16.0 * self.scans[f].shape[0] + 48.0 * n_valid)
+        bytes_total *= steps
+        peak, peak_src = hbm_peak()
+        achieved = bytes_total / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        tag = "%s_%s" % (self.accumulation, "direct7" if self.variant == "omp" else "pca_direct1")
+        ks = load_kernel_stats().get(tag, {})
+        alg_per_launch = bytes_total / max(kern_launches, 1)
+        avg_ms = kern_ms / max(kern_launches, 1)
+        out = {"bound": "hbm", "kernel": ks.get("kernel", "ndt_eval_fast_kernel" if self.accumulation == "fast" else "ndt_eval_kernel"),
+               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ks.get("dram_bytes_per_launch"),
+               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms, "launches_timed": kern_launches,
+               "kernel_share_of_step": kern_ms / (ms_dev * steps)}
+        if ks.get("warp_inst_per_launch") and avg_ms > 0:
+            # the kernel's issued warp instructions per launch come from the committed ncu capture of this very launch shape, scaled by
+            # the algorithmic bytes when the batch differs; the roof is one warp instruction per clock per SM sub-partition
+            inst = ks["warp_inst_per_launch"] * (alg_per_launch / ks["algorithmic_bytes_per_launch"] if ks.get("algorithmic_bytes_per_launch") else 1.0)
+            mhz = (clocks or {}).get("sm_mhz") or load_peaks().get("sm_max_mhz") or 1965.0
+            ipeak = SMS * SMSP_PER_SM * mhz * 1e6
+            out["binding"] = {"bound": "issue", "achieved": inst / (avg_ms * 1e-3) / 1e9, "peak": ipeak / 1e9, "unit": "G warp-inst/s",
+                              "frac": inst / (avg_ms * 1e-3) / ipeak, "warp_inst_per_launch": inst,
+                              "pipes_under_ncu_pct": {k: ks[k] for k in ("issue_active_pct", "xu_pct", "fma_pct", "fp64_pct", "lsu_pct") if k in ks},
+                              "source": ks.get("source")}
+        out["note"] = ("HBM time of a launch is far below its run time: the kernel executes the reference's per-point float arithmetic "
+                       "(~%d issued instructions per (point, cell) term), so the instruction issue rate is the binding roof (DESIGN.md section 5)"
+                       % (270 if self.accumulation == "fast" else 500))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ sub-records
+def bench_pair_latency(L, torch):
+    """BASELINE configs[0]: the config-1 pair from the reference's first-frame guess (x = 1.5 m), single registration object - the live
+    odometry call (scan_matching_odom_nodelet.cpp:192-261).  `align`: clouds resident; `frame`: setInputSource from a host buffer + align."""
+    from lv_slam_b200 import synth
+    tgt, src, guess, truth = synth.config1_pair()
+    out = {"workload": "BASELINE configs[0] stand-in: synthetic 64-beam pair, %d / %d points, guess x = 1.5 m, pclomp/DIRECT7, 1.0 m" % (len(tgt), len(src))}
+    finals = {}
+    for mode, acc in (("exact", 0), ("tolerance", 1)):
+        n = L.NormalDistributionsTransform(variant=0)
+        n.setTransformationEpsilon(0.01); n.setMaximumIterations(64); n.setNeighborhoodSearchMethod(L.LVS_DIRECT7)
+        n.setAccumulation(acc)
+        n.setInputTarget(tgt); n.setInputSource(src)
+        for _ in range(3):
+            n.align(guess)
+        torch.cuda.synchronize()
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            n.align(guess)
+        t_align = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            n.setInputSource(src); n.align(guess)
+        t_frame = (time.perf_counter() - t0) / reps
+        r = n.result()
+        finals[mode] = r["final"]
+        out[mode] = {"align_ms": t_align * 1e3, "frame_ms_with_host_source": t_frame * 1e3, "iterations": r["iterations"], "evaluations": r["n_eval"],
+                     "us_per_newton_iteration": t_align * 1e6 / max(r["n_eval"], 1), "aligns_per_sec": 1.0 / t_align,
+                     "translation_error_vs_truth_m": float(np.abs(r["final"][:3, 3] - truth[:3, 3]).max())}
+        n.close()
+    out["tolerance"]["final_vs_exact"] = {"translation_m": float(np.abs(finals["exact"][:3, 3] - finals["tolerance"][:3, 3]).max()),
+                                          "rotation_max_abs": float(np.abs(finals["exact"][:3, :3] - finals["tolerance"][:3, :3]).max())}
+    return out, (tgt, src, guess, finals["exact"])
+
+
+def cpu_pair_latency(tgt, src, guess, final_gpu):
+    out = {}
+    for th in sorted({4, 8, os.cpu_count() or 1}):
+        if th > (os.cpu_count() or 1):
+            continue
+        o, _ = oracle_for("omp", th)
+        o.set_target(tgt); o.set_source(src)
+        t0 = time.perf_counter()
+        r = o.align(guess)
+        dt = time.perf_counter() - t0
+        out["threads_%d" % th] = {"align_ms": dt * 1e3, "iterations": r["iterations"], "max_abs_final_transform_diff_vs_gpu": float(np.abs(r["final"] - final_gpu).max())}
+    return {"kind": "port", "unit": "ms/align", "cores": os.cpu_count() or 1, "sample": "the same pair, one align per thread count", **out}
+
+
+def bench_pgo(L, with_cpu):
+    """BASELINE configs[3]: g2o-sphere 5 000 vertices / 19 599 edges, information diag(2,2,2,10,10,10), Huber 1.0 on every edge."""
+    from lv_slam_b200 import _capi as C
+    from lv_slam_b200.synth import posegraph as G
+    g = G.sphere(100, 50, seed=7)
+    nv, ne = len(g["poses7"]), len(g["ij"])
+    out = {"workload": "BASELINE configs[3]: sphere, %d SE(3) vertices / %d edges (odometry + loop), Huber 1.0, no fixed vertex (LM) / vertex 0 fixed (GN)" % (nv, ne),
+           "metric": "pose_graph_optimize_runs_per_sec", "unit": "runs/s"}
+    info = None
+    for name, solver, fixed, iters in (("lm_direct", C.LVS_PGO_LM_CHOL, None, 1024), ("lm_pcg", C.LVS_PGO_LM_PCG, None, 1024), ("gn_direct", C.LVS_PGO_GN_CHOL, 0, 16)):
+        best = None
+        for rep in range(3):
+            pg = L.PoseGraph(solver)
+            fx = None
+            if fixed is not None:
+                fx = np.zeros(nv, np.uint8); fx[fixed] = 1
+            t0 = time.perf_counter()
+            pg.set_graph(g["poses7"], g["ij"], g["meas7"], g["info21"], g["huber"], fx)
+            ts = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            st = pg.optimize(iters)
+            to = time.perf_counter() - t0
+            if solver == C.LVS_PGO_LM_CHOL and info is None:
+                info = pg.chol_info()
+            if best is None or to < best[0]:
+                best = (to, ts, st)
+            pg.close()
+        to, ts, st = best
+        solves = max(st["lm_trials"], st["iterations"], 1)
+        out[name] = {"value": 1.0 / to, "unit": "runs/s", "optimize_ms": to * 1e3, "set_graph_ms": ts * 1e3, "device_ms": st["device_ms"], "linearize_ms": st["linearize_ms"],
+                     "solve_ms": st["solve_ms"], "iterations": st["iterations"], "linear_solves": solves, "ms_per_linear_solve": st["solve_ms"] / solves,
+                     "pcg_iterations": st["pcg_iterations"], "launches": st["launches"], "chi2_before": st["chi2_before"], "chi2_after": st["chi2_after"]}
+    if info:
+        # SURVEY.md §8d: linearisation 1 304 B/edge per trial; direct solve >= 2 * nnz(L) * 8 B (factor written once, read once)
+        hbm, _ = hbm_peak()
+        lm = out["lm_direct"]
+        solve_bytes = 2.0 * info["nnz_l_blocks"] * 36 * 8
+        ach = solve_bytes / (lm["ms_per_linear_solve"] * 1e-3) / 1e9
+        out["structure"] = info
+        out["roofline"] = {"bound": "hbm", "kernel": "chol_front_kernel (direct solve)", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                           "algorithmic_bytes_per_solve": solve_bytes, "linearize_algorithmic_bytes": 1304.0 * ne,
+                           "fp64_fma_per_solve": info["factor_fma"], "achieved_tflops_fp64": 2.0 * info["factor_fma"] / (lm["ms_per_linear_solve"] * 1e-3) / 1e12,
+                           "note": "latency-bound: an elimination tree of %d levels, largest front %d; neither HBM nor the fp64 pipes are near saturation" % (info["levels"], info["max_front"])}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_pgo as P
+        o = P.OraclePGO(); o.set_graph(g["poses7"], g["ij"], g["meas7"], g["info21"], g["huber"])
+        t0 = time.perf_counter()
+        r = o.optimize(1024, P.ALG_LM, P.SOLVER_CSPARSE if P.have_csparse() else P.SOLVER_PCG)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "runs/s", "optimize_ms": dt * 1e3, "cores": 1, "kind": "port",
+                               "sample": "the same graph, one LM run: g2o's LM restated + %s (g2o is single-threaded)" % (
+                                   "the reference's vendored CSparse (oracle/_ref), the `lm_var` solver; the launch-file default CHOLMOD is un-vendored and typically several times faster" if P.have_csparse() else "PCG"),
+                               "iterations": r["iterations"], "chi2_after": r["chi2_after"]}
+    return out
+
+
+def bench_beam128(args, L, torch, dist, D, rank, local_rank, world, with_cpu):
+    """BASELINE configs[2]: 128-beam scans (~240 k points), 0.5 m voxels, pclomp/DIRECT7.  One GPU: a batch of 8 stream pairs.
+    N > 1 GPUs: the same aligns POINT-SHARDED - every rank evaluates its 1/N of each source and the 43 sums are exchanged through
+    NVLink peer memory inside the evaluation kernel (lvs_ndt_batch_shard_*); results must be bit-identical on every rank."""
+    from lv_slam_b200 import synth
+    scans, poses = synth.stream(10, seed=1000, n_beams=128, n_az=1875)
+    plan = synth.keyframe_plan(poses)[:8]
+    keys = sorted({k for _, k, _ in plan})
+    key_slot = {k: i for i, k in enumerate(keys)}
+    kw = dict(resolution=0.5, transformation_epsilon=0.01, max_iterations=64, variant=0, search_method=2)
+    nb = L.NdtBatch(len(keys), len(plan), device=local_rank, **kw)
+    if world > 1:
+        nb.enable_point_sharding(rank, world, len(plan), lambda blob: D.all_gather_bytes(blob, world))
+    dev = {f: torch.from_numpy(scans[f]).cuda() for f in {f for f, _, _ in plan} | set(keys)}
+    for k in keys:
+        nb.set_target(key_slot[k], dev[k])
+    for i, (f, _, _) in enumerate(plan):
+        nb.set_source(i, dev[f])
+    ss, ts, gs = list(range(len(plan))), [key_slot[k] for _, k, _ in plan], [g for _, _, g in plan]
+    for _ in range(3):
+        res = nb.align(ss, ts, gs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 10
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(reps):
+        res = nb.align(ss, ts, gs)
+        dev_ms += nb.last_stats()["device_ms"]
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    wall = D.max_over_ranks(wall, world, "cuda")
+    fin = torch.from_numpy(np.stack([r["final"] for r in res])).cuda()
+    same = True
+    if world > 1:
+        allf = [torch.empty_like(fin) for _ in range(world)]
+        dist.all_gather(allf, fin)
+        same = all(bool(torch.equal(allf[0], f)) for f in allf)
+    err = max(float(np.abs(r["final"][:3, 3] - (np.linalg.inv(poses[k]) @ poses[f])[:3, 3]).max()) for r, (f, k, _) in zip(res, plan))
+    n_pts = int(np.mean([scans[f].shape[0] for f, _, _ in plan]))
+    out = {"workload": "BASELINE configs[2]: synthetic 128-beam stream, %d points per scan, 0.5 m voxels, pclomp/DIRECT7, %d pairs per call" % (n_pts, len(plan)),
+           "sharding": "points of every source split over %d ranks, sums exchanged through peer memory inside the kernel" % world if world > 1 else "none (one GPU)",
+           "n_gpus": world, "value": len(plan) / wall, "unit": UNIT, "ms_per_call": wall * 1e3, "device_ms_per_call": dev_ms / reps,
+           "iterations": [int(r["iterations"]) for r in res], "ranks_bit_identical": bool(same), "max_translation_error_vs_truth_m": err}
+    nb.close()
+    if with_cpu and rank == 0:
+        o, threads = oracle_for("omp", None, 0.5)
+        dt, finals = run_cpu_pairs(o, scans, plan, [0, 1])
+        out["cpu_baseline"] = {"value": 2 / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": "first 2 pairs of the call (1 keyframe voxelisation + 2 aligns), %.1f s" % dt,
+                               "max_abs_final_transform_diff_vs_gpu": max(float(np.abs(finals[i] - res[i]["final"]).max()) for i in range(2))}
+    return out
 
 
 def main_ours(args):
@@ -190,145 +550,76 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     scans, poses, plan, keys = make_workload(args.batch, rank)
-    B = len(plan)
-    key_slot = {k: i for i, k in enumerate(keys)}
     n_pts = int(np.mean([scans[f].shape[0] for f, _, _ in plan]))
-    vp = variant_params(args.variant)
-    stream = torch.cuda.Stream()
-    from lv_slam_b200.ndt import CloudBatch, pack_guesses
-    # two slot sets: while the aligns of step k run on one, the clouds of step k + 1 are copied and voxelised into the other
-    nk = len(keys)
-    nb = L.NdtBatch(2 * nk, 2 * B, device=local_rank, stream=stream.cuda_stream, transformation_epsilon=0.01, max_iterations=64,
-                    accumulation=1 if args.accumulation == "fast" else 0, **vp)
-    tgt_all = [list(range(p * nk, (p + 1) * nk)) for p in (0, 1)]
-    src_all = [list(range(p * B, (p + 1) * B)) for p in (0, 1)]
-    src_slots = [np.arange(p * B, (p + 1) * B, dtype=np.int32) for p in (0, 1)]
-    tgt_slots = [np.array([key_slot[k] + p * nk for _, k, _ in plan], dtype=np.int32) for p in (0, 1)]
-    guesses = pack_guesses([g for _, _, g in plan])          # [B, 16] column-major, the layout the C-ABI takes
+    common = (args, L, torch, dist, D, rank, local_rank, world, scans, poses, plan, keys)
 
-    # resident copies (value) and pinned host copies (e2e)
-    dev_src = [torch.from_numpy(scans[f]).cuda() for f, _, _ in plan]
-    dev_tgt = [torch.from_numpy(scans[k]).cuda() for k in keys]
-    pin_src = [torch.from_numpy(scans[f]).pin_memory() for f, _, _ in plan]
-    pin_tgt = [torch.from_numpy(scans[k]).pin_memory() for k in keys]
-    # the buffers are the same every step: marshal their pointers once (what a C++ caller's std::vector<const float*> is)
-    dev_src, dev_tgt, pin_src, pin_tgt = CloudBatch(dev_src), CloudBatch(dev_tgt), CloudBatch(pin_src), CloudBatch(pin_tgt)
+    top = StreamBench(*common, args.variant, args.accumulation)
+    rec = top.measure(args.steps, args.warmup, True, ClockSampler(local_rank))
+    line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": workload_config(args, n_pts, len(keys)), "clocks": rec.get("clocks"), "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"],
+            "roofline": rec.get("roofline"), "evaluations_per_align": rec["evaluations_per_align"],
+            "max_translation_error_vs_truth_m": rec["max_translation_error_vs_truth_m"],
+            "e2e_results_identical_to_resident": rec["e2e_results_identical_to_resident"]}
+    res_top = top.results
+    pca_results = None
 
-    def stage(p, src, tgt):
-        """setInputTarget of the step's keyframes + setInputSource of its scans into slot set p (asynchronous: copies, repacks and the
-        batched voxelisation are queued on the library's upload / build streams)."""
-        nb.set_targets(tgt_all[p], tgt)
-        nb.set_sources(src_all[p], src)
-
-    def run_steps(src, tgt, steps, group):
-        """`steps` passes over the batch, software-pipelined: the aligns of a step are queued (align_begin), then the NEXT step's clouds
-        are staged into the other slot set, then the results are collected (align_end) - so host-to-device copies and
-        voxelisations overlap the aligns of the step before.  Every copy, every voxelisation and every result read-back of the
-        `steps` steps happens between the first stage() and the last align_end(), i.e. inside the timed region."""
-        stats = {"deriv_kernel_ms": 0.0, "deriv_launches": 0, "n_eval": 0}
-        out = None
-        stage(0, src, tgt)
-        for k in range(steps):
-            p = k & 1
-            out = None
-            for a in range(0, B, group):
-                nb.align_begin(src_slots[p][a:a + group], tgt_slots[p][a:a + group], guesses[a:a + group])
-                if a == 0 and k + 1 < steps:
-                    stage(1 - p, src, tgt)
-                r = nb.align_end()
-                out = r if out is None else out + r
-                st = nb.last_stats()
-                stats["deriv_kernel_ms"] += st["deriv_kernel_ms"]; stats["deriv_launches"] += st["deriv_launches"]
-            stats["n_eval"] += int(out.n_eval.sum())
-        return out, stats
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(src, tgt, steps, profile, group):
-        nb.set_profiling(profile)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = nb.total_launches()
-        barrier()
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            res, st = run_steps(src, tgt, steps, group)
-            ev1.record(stream)
-        barrier()
-        ms = D.max_over_ranks(ev0.elapsed_time(ev1), world, "cuda")
-        nb.set_profiling(0)
-        return ms / steps, nb.total_launches() - launches0, st["deriv_kernel_ms"], st["deriv_launches"], st["n_eval"], res
-
-    # warm-up (both paths), then the timed regions
-    g_e2e = max(1, min(B, args.e2e_group))
-    timed(dev_src, dev_tgt, args.warmup, 0, B)
-    timed(pin_src, pin_tgt, args.warmup, 0, g_e2e)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms_dev, launches, kern_ms, kern_launches, n_eval_total, res = timed(dev_src, dev_tgt, args.steps, 1, B)
-    xfer0 = nb.transfer_bytes()
-    ms_e2e, _, _, _, _, res_e2e = timed(pin_src, pin_tgt, args.steps, 0, g_e2e)
-    xfer1 = nb.transfer_bytes()
-    clocks = sampler.stop()                      # sampled every 20 ms across both timed regions
-    h2d_bytes, d2h_bytes = (xfer1[0] - xfer0[0]) // args.steps, (xfer1[1] - xfer0[1]) // args.steps
-
-    # sanity: the aligns registered the stream (pose error against the generator's ground truth)
-    err_t = max(float(np.abs(r["final"][:3, 3] - (np.linalg.inv(poses[k]) @ poses[f])[:3, 3]).max()) for r, (f, k, _) in zip(res, plan))
+    if not args.no_extras:
+        # ---- the same workload in the other accumulation mode, and the other registration variant in both (every rank takes part:
+        # the timings are max-over-ranks like the top-level ones)
+        other = "fast" if args.accumulation == "exact" else "exact"
+        sb = StreamBench(*common, args.variant, other, buffers=top.buffers)
+        r2 = sb.measure(args.steps, args.warmup, True)
+        r2["config"] = workload_config(args, n_pts, len(keys), accumulation=other)
+        r2["vs_top_level_mode"] = {
+            "max_translation_diff_m": max(float(np.abs(a["final"][:3, 3] - b["final"][:3, 3]).max()) for a, b in zip(res_top, sb.results)),
+            "max_rotation_entry_diff": max(float(np.abs(a["final"][:3, :3] - b["final"][:3, :3]).max()) for a, b in zip(res_top, sb.results)),
+            "identical_iteration_counts": bool(all(a["iterations"] == b["iterations"] for a, b in zip(res_top, sb.results)))}
+        line["modes"] = {"tolerance" if other == "fast" else "exact": r2}
+        sb.nb.close()
+        other_variant = "pca" if args.variant == "omp" else "omp"
+        sub = {}
+        for acc in ("exact", "fast"):
+            sb = StreamBench(*common, other_variant, acc, buffers=top.buffers)
+            r3 = sb.measure(args.steps, args.warmup, True)
+            r3["config"] = workload_config(args, n_pts, len(keys), variant=other_variant, accumulation=acc)
+            sub["tolerance" if acc == "fast" else "exact"] = r3
+            if acc == "exact":
+                pca_results = sb.results
+            sb.nb.close()
+        line["configs"] = {"pca_direct1" if other_variant == "pca" else "omp_direct7": sub}
+        # BASELINE configs[2]: on one GPU a plain batch, on N > 1 the point-sharded evaluation (every rank takes part)
+        line["configs"]["beam128"] = bench_beam128(args, L, torch, dist, D, rank, local_rank, world, world == 1 and not args.no_cpu_baseline)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # roofline of the derivative kernel: SURVEY.md §8d algorithmic bytes = 16 B per source point + 48 B per usable voxel, per evaluation
-    bytes_total = 0.0
-    for r, (f, k, _) in zip(res, plan):
-        n_valid = nb.num_cells(key_slot[k])[1]
-        bytes_total += r["n_eval"] * (16.0 * scans[f].shape[0] + 48.0 * n_valid)
-    bytes_total *= args.steps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs", 6650.0)
-    if isinstance(peak, dict):                         # tolerate {"hbm_gbs": {"value": ...}}
-        peak = next((v for k, v in peak.items() if isinstance(v, (int, float))), 6650.0)
-    peak = float(peak)
-    achieved = bytes_total / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ndt_eval_traffic.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "ndt_eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_launch": bytes_total / max(kern_launches, 1), "avg_launch_ms": kern_ms / max(kern_launches, 1),
-                "launches_timed": kern_launches, "kernel_share_of_step": kern_ms / (ms_dev * args.steps),
-                "note": "the kernel is bound by the float->double conversion pipe (XU 62 % busy, issue 59 %: profiles/r01_final/ndt_eval_ncu_summary.txt), not by HBM: float32 per-point math in the reference's exact operation order, 43 fp64 sums per term; see DESIGN.md section 5"}
-
-    line = {"metric": METRIC, "value": world * B / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": workload_config(args, n_pts, len(keys)), "clocks": clocks,
-            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e, "pairs_per_align_call": g_e2e,
-                    "pipeline": "two slot sets: step k+1's clouds are copied and voxelised while step k's aligns run; every copy and read-back of the timed steps is inside the timed region"},
-            "gpu_launches": int(launches), "roofline": roofline,
-            "evaluations_per_align": n_eval_total / (args.steps * B), "max_translation_error_vs_truth_m": err_t,
-            "e2e_results_identical_to_resident": bool(all(np.array_equal(a["final"], b["final"]) for a, b in zip(res, res_e2e)))}
+    if world == 1 and not args.no_extras:
+        pl, pair = bench_pair_latency(L, torch)
+        if not args.no_cpu_baseline:
+            pl["cpu_baseline"] = cpu_pair_latency(*pair)
+        line["configs"]["pair_latency"] = pl
+        line["configs"]["pgo"] = bench_pgo(L, not args.no_cpu_baseline)
 
     if world == 1 and not args.no_cpu_baseline:
         o, threads = oracle_for(args.variant)
-        dt1, _ = run_cpu_pairs(o, scans, plan, [0])
-        n = args.cpu_sample or int(max(2, min(B, 15.0 / max(dt1, 1e-3))))
+        n = args.cpu_sample or len(plan)
         dt, finals = run_cpu_pairs(o, scans, plan, list(range(n)))
-        dev = max(float(np.abs(finals[i] - res[i]["final"]).max()) for i in range(n))
-        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "first %d scan pairs of the step's batch (keyframe voxelisations + aligns), %.1f s" % (n, dt),
-                                "max_abs_final_transform_diff_vs_gpu": dev}
+        cb = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+              "sample": "first %d scan pairs of the step's batch (keyframe voxelisations + aligns), %.1f s" % (n, dt),
+              "max_abs_final_transform_diff_vs_gpu": max(float(np.abs(finals[i] - res_top[i]["final"]).max()) for i in range(n))}
+        cb.update(cpu_thread_sweep(args.variant, scans, plan, 16))
+        line["cpu_baseline"] = cb
+        if pca_results is not None:
+            ov = "pca" if args.variant == "omp" else "omp"
+            o, threads = oracle_for(ov)
+            dt, finals = run_cpu_pairs(o, scans, plan, list(range(n)))
+            cb = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port", "sample": "first %d scan pairs of the step's batch, %.1f s" % (n, dt),
+                  "max_abs_final_transform_diff_vs_gpu": max(float(np.abs(finals[i] - pca_results[i]["final"]).max()) for i in range(n))}
+            cb.update(cpu_thread_sweep(ov, scans, plan, 16))
+            line["configs"]["pca_direct1" if ov == "pca" else "omp_direct7"]["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

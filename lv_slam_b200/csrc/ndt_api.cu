@@ -97,6 +97,9 @@ struct StageBuf {
 };
 
 constexpr int kMaxEvents = 2048;
+constexpr int kWinRing = 64;          // per-launch events kept for the window bookkeeping (>= launches ever in flight)
+constexpr int kWindow = 4;            // evaluation launches align_end keeps in flight while it polls the completion flag
+constexpr int kMaxFirst = 32;         // launches align_begin may queue up front
 
 }  // namespace lvs
 
@@ -106,6 +109,7 @@ struct PendingAlign {          // the align between align_begin and align_end
   bool active = false;
   std::vector<int> src_slots, tgt_slots;     // slots the pairs in flight read: the setters refuse them until align_end
   int n_pairs = 0, launches = 0, max_launches = 0;
+  int completed = 0;             // launches known to have finished (window bookkeeping of align_end)
   bool need_cold = false, prof = false;
   EvalLaunch L;
 };
@@ -142,6 +146,13 @@ struct lvs_ndt_batch {
   double* d_partials = nullptr;
   unsigned int* d_tickets = nullptr;
   int *d_done = nullptr, *h_done = nullptr;
+  // completion without a stream synchronisation: the device stores the align's serial into this host-mapped word when the last pair
+  // finishes (eval_finish); align_end polls it and keeps only a small window of launches in flight meanwhile
+  volatile int* h_flag = nullptr;
+  int* d_flag_alias = nullptr;
+  int align_serial = 0;
+  cudaStream_t rb = nullptr;         // read-back stream: results are copied out as soon as the flag is seen, ahead of idle launches still queued on st
+  std::vector<cudaEvent_t> ev_win;   // ring of per-launch events (window bookkeeping)
   GridParams* h_gp_all = nullptr;   // pinned, one per target slot: batched geometry read-back
   float* d_T16 = nullptr;        // scratch 16 floats
   double *d_scalar = nullptr, *h_scalar = nullptr;
@@ -152,6 +163,7 @@ struct lvs_ndt_batch {
   int last_n_pairs = 0;
   // stats
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  bool ev_end_pending = false;
   std::vector<cudaEvent_t> ev_pool;
   int profiling = 0;
   double last_device_ms = 0, last_deriv_ms = 0;
@@ -418,10 +430,10 @@ static int align_launch_one(lvs_ndt_batch* b) {
   int rc;
   const bool ev = P.prof && P.launches < kMaxEvents;
   if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * P.launches], b->st));
-  P.L.shard.serial = ++b->shard_serial;        // one serial per kernel launch: a pair may be evaluated by both kernels of a step
   if ((rc = launch_eval(b->st, P.L))) return rc;
-  if (P.need_cold) { P.L.shard.serial = ++b->shard_serial; if ((rc = launch_eval_cold(b->st, P.L))) return rc; }
+  if (P.need_cold) { if ((rc = launch_eval_cold(b->st, P.L))) return rc; }
   if (ev) CUDA_TRY(cudaEventRecord(b->ev_pool[2 * P.launches + 1], b->st));
+  CUDA_TRY(cudaEventRecord(b->ev_win[P.launches % kWinRing], b->st));
   P.launches++;
   return LVS_OK;
 }
@@ -468,8 +480,11 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   L.consts = make_consts(b->prm);
   if (b->shard_on && n_pairs > b->shard_cap) return fail(LVS_ERR_INVALID_ARG, "%d pairs exceed the sharded batch's max_pairs %d", n_pairs, b->shard_cap);
   shard_view(b, L);
+  L.h_done_flag = b->d_flag_alias; L.align_serial = ++b->align_serial;
   // worst case: initial pass + (max_iter + 2) outer iterations of (first + 10 trials + Hessian pass)
   P.max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
+  L.shard.serial = b->shard_serial;            // base of this align; every pair adds its own evaluation count (eval_finish)
+  b->shard_serial += 2 * P.max_launches + 2;
   P.n_pairs = n_pairs;
   *b->h_done = 0;
   P.prof = b->profiling != 0;
@@ -483,12 +498,9 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   P.need_cold = b->prm.search_method == LVS_KDTREE || !((b->prm.step_size - b->prm.transformation_epsilon / 2) > 0);
   // launches queued before the first completion check: every one beyond what the pairs need is a grid of CTAs that find nothing
   // to do, so the count follows the previous align (streams are self-similar) unless the caller fixed it
-  const int first = (!b->chunk_fixed && b->learned_first > 0) ? b->learned_first : b->chunk_first;
+  const int first = std::min(kMaxFirst, (!b->chunk_fixed && b->learned_first > 0) ? b->learned_first : b->chunk_first);
   for (int k = 0; k < first && P.launches < P.max_launches; k++)
     if ((rc = align_launch_one(b))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
-  b->d2h_bytes += sizeof(int);
-  if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->st));
   P.active = true;
   return LVS_OK;
 }
@@ -504,25 +516,44 @@ static int align_end(lvs_ndt_batch* b, lvs_ndt_result* results) {
   if (n_pairs <= 0) return LVS_OK;
   const int max_launches = P.max_launches;
   const bool need_cold = P.need_cold, prof = P.prof;
-  for (;;) {
-    CUDA_TRY(cudaStreamSynchronize(b->st));
-    if ((rc = shard_check(b))) return rc;
-    if (*b->h_done >= n_pairs || P.launches >= max_launches) break;
-    for (int k = 0; k < b->chunk_next && P.launches < max_launches; k++)
+  // Poll the host-mapped completion word instead of synchronising the stream; meanwhile keep a small window of evaluation launches
+  // in flight (a launch that finds every pair finished returns at once, so the few that outlive the align cost microseconds).
+  const int serial = P.L.align_serial;
+  bool done = false;
+  for (long spins = 0;; spins++) {
+    if (*b->h_flag == serial) { done = true; break; }
+    while (P.completed < P.launches) {
+      cudaError_t q = cudaEventQuery(b->ev_win[P.completed % kWinRing]);
+      if (q == cudaSuccess) P.completed++;
+      else if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
+      else return cuda_fail(q, "cudaEventQuery", __FILE__, __LINE__);
+    }
+    if (P.launches - P.completed < std::max(kWindow, b->chunk_next) && P.launches < max_launches) {
       if ((rc = align_launch_one(b))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(b->h_done, b->d_done, sizeof(int), cudaMemcpyDeviceToHost, b->st));
-    b->d2h_bytes += sizeof(int);
-    if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->st));
+      continue;
+    }
+    if (P.completed == P.launches && P.launches >= max_launches) { done = (*b->h_flag == serial); break; }
+    if (b->shard_on && (spins & 0xfff) == 0xfff) {      // a lost peer never completes: look at the error word from time to time
+      CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->rb));
+      CUDA_TRY(cudaStreamSynchronize(b->rb));
+      if ((rc = shard_check(b))) return rc;
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
   }
   const int launches = P.launches;
-  CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, n_pairs * sizeof(AlignState), cudaMemcpyDeviceToHost, b->st));
+  // every state is complete and fenced once the flag is visible: copy the results on the read-back stream, ahead of whatever idle
+  // launches are still queued on the compute stream
+  CUDA_TRY(cudaMemcpyAsync(b->h_states, b->d_states, n_pairs * sizeof(AlignState), cudaMemcpyDeviceToHost, b->rb));
   b->d2h_bytes += (long long)n_pairs * sizeof(AlignState);
+  if (b->shard_on) CUDA_TRY(cudaMemcpyAsync(b->h_shard_error, b->d_shard_error, sizeof(int), cudaMemcpyDeviceToHost, b->rb));
   CUDA_TRY(cudaEventRecord(b->ev_end, b->st));
-  CUDA_TRY(cudaStreamSynchronize(b->st));
-  if (*b->h_done < n_pairs) return fail(LVS_ERR_CUDA, "align state machine did not finish within %d evaluation launches", max_launches);
-  float ms = 0;
-  CUDA_TRY(cudaEventElapsedTime(&ms, b->ev_begin, b->ev_end));
-  b->last_device_ms = ms;
+  b->ev_end_pending = true;
+  CUDA_TRY(cudaStreamSynchronize(b->rb));
+  if ((rc = shard_check(b))) return rc;
+  if (!done) return fail(LVS_ERR_CUDA, "align state machine did not finish within %d evaluation launches", max_launches);
+  b->last_device_ms = -1.0;                      // computed on demand (lvs_ndt_batch_last_stats): needs ev_end, i.e. the idle launches too
   b->last_launches = launches;
   b->total_launches += launches * (need_cold ? 2 : 1);
   b->last_n_pairs = n_pairs;
@@ -542,9 +573,10 @@ static int align_end(lvs_ndt_batch* b, lvs_ndt_result* results) {
     }
   }
   b->last_deriv_launches = active;
-  b->learned_first = std::max(2, std::min(active + 1, 16));
+  b->learned_first = std::max(2, std::min(active + 1, kMaxFirst));
   b->last_deriv_ms = 0;
   if (prof) {
+    CUDA_TRY(cudaEventSynchronize(b->ev_end));
     double sum = 0;
     for (int k = 0; k < std::min(active, kMaxEvents); k++) {
       float t = 0;
@@ -588,7 +620,7 @@ static int run_tap(lvs_ndt_batch* b, int kind, const double p[6], const float* T
   L.n_pairs = 1; L.blocks_per_pair = bpp; L.advance = 0;
   L.consts = make_consts(b->prm);
   shard_view(b, L);
-  L.shard.serial = ++b->shard_serial;
+  L.shard.serial = b->shard_serial; b->shard_serial += 4;
   if (kind == EVAL_HESS27 || b->prm.search_method == LVS_KDTREE) rc = launch_eval_cold(b->st, L);
   else rc = launch_eval(b->st, L);
   if (rc) return rc;
@@ -643,6 +675,17 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
     if ((e = cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_done, 4 * sizeof(int))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
+  {
+    int* hf = nullptr;
+    if ((e = cudaHostAlloc(&hf, 64, cudaHostAllocMapped)) != cudaSuccess) return bail(cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__));
+    hf[0] = 0;
+    b->h_flag = hf;
+    if ((e = cudaHostGetDevicePointer((void**)&b->d_flag_alias, hf, 0)) != cudaSuccess) return bail(cuda_fail(e, "cudaHostGetDevicePointer", __FILE__, __LINE__));
+  }
+  if ((e = cudaStreamCreateWithFlags(&b->rb, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+  b->ev_win.assign(kWinRing, nullptr);
+  for (auto& ev : b->ev_win)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
   if ((e = cudaMallocHost(&b->h_gp_all, n_t * sizeof(GridParams))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_T16, 16 * sizeof(float))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
   if ((e = cudaMalloc(&b->d_scalar, 8 * sizeof(double))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
@@ -916,6 +959,9 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   if (b->h_pairs) cudaFreeHost(b->h_pairs);
   if (b->h_states) cudaFreeHost(b->h_states);
   if (b->h_done) cudaFreeHost(b->h_done);
+  if (b->h_flag) cudaFreeHost((void*)b->h_flag);
+  if (b->rb) { cudaStreamSynchronize(b->rb); cudaStreamDestroy(b->rb); }
+  for (auto ev : b->ev_win) if (ev) cudaEventDestroy(ev);
   if (b->h_gp_all) cudaFreeHost(b->h_gp_all);
   if (b->h_scalar) cudaFreeHost(b->h_scalar);
   if (b->ev_begin) cudaEventDestroy(b->ev_begin);
@@ -972,6 +1018,13 @@ int lvs_ndt_batch_align_end(lvs_ndt_batch_t* b, lvs_ndt_result* results) {
 
 int lvs_ndt_batch_last_stats(lvs_ndt_batch_t* b, double* device_ms, int* launches, double* deriv_kernel_ms, int* deriv_launches) {
   if (!b) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  if (b->ev_end_pending && b->last_device_ms < 0) {
+    float ms = 0;
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaEventSynchronize(b->ev_end));
+    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev_begin, b->ev_end));
+    b->last_device_ms = ms;
+  }
   if (device_ms) *device_ms = b->last_device_ms;
   if (launches) *launches = b->last_launches;
   if (deriv_kernel_ms) *deriv_kernel_ms = b->last_deriv_ms;

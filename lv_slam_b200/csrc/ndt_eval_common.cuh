@@ -46,7 +46,10 @@ __device__ __forceinline__ void transform_point(const float* T, float x, float y
 
 // Completion of one evaluation of one pair: every CTA has stored its partial[nv]; the LAST CTA to take a ticket sums the
 // bpp partials in a fixed order (run-to-run deterministic), deposits (score, g, H) in the pair's AlignState and advances the
-// Newton / More-Thuente state machine so that the next launch knows what to evaluate.  s_scratch: >= 256 doubles of shared memory.
+// Newton / More-Thuente state machine so that the next launch knows what to evaluate.  s_scratch: >= 320 doubles of shared memory.
+// The tail is what a single-pair align waits for between two evaluations, so it is kept short: the partials are fetched with every
+// load of a thread in flight at once (5 row groups x 43 columns of threads), and the ~0.9 KB state is copied to shared memory once,
+// advanced there by one thread (6x6 solve, SE(3) exp / log) and copied back once, instead of being walked field by field in L2.
 __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int kind, int nv, int n_src, double* s_scratch, int* s_last) {
   AlignState& S = L.d_states[pair];
   const AlignConsts& c = L.consts;
@@ -60,16 +63,30 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   __syncthreads();
   if (!*s_last) return;
   __threadfence();
-  constexpr int R = kEvalThreads / 64;   // 4 row groups x 64 columns (43 used)
+  __shared__ __align__(16) AlignState s_state;
+  static_assert(sizeof(AlignState) % 4 == 0, "AlignState is copied word by word");
   {
-    const int k = threadIdx.x & 63, r = threadIdx.x >> 6;
+    const int* src = reinterpret_cast<const int*>(&S);
+    int* dst = reinterpret_cast<int*>(&s_state);
+    for (int i = threadIdx.x; i < (int)(sizeof(AlignState) / 4); i += kEvalThreads) dst[i] = __ldcg(src + i);
+  }
+  constexpr int R = 5;                   // row groups x 43 columns = 215 of the 256 threads
+  static_assert(R * kAcc <= kEvalThreads, "reduction layout");
+  {
+    const int k = threadIdx.x % kAcc, r = threadIdx.x / kAcc;
     double x = 0;
-    if (k < nv) {
-      const double* base = L.d_partials + (size_t)pair * bpp * kAcc;
-#pragma unroll 8
-      for (int b = r; b < bpp; b += R) x += __ldcg(base + (size_t)b * kAcc + k);
+    if (r < R && k < nv) {
+      const double* base = L.d_partials + (size_t)pair * bpp * kAcc + k;
+      constexpr int kIn = 12;            // loads in flight per thread
+      for (int b0 = r; b0 < bpp; b0 += R * kIn) {
+        double v[kIn];
+#pragma unroll
+        for (int u = 0; u < kIn; u++) { const int b = b0 + R * u; v[u] = b < bpp ? __ldcg(base + (size_t)b * kAcc) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < kIn; u++) x += v[u];      // adding +0.0 past the end is exact
+      }
     }
-    s_scratch[r * 64 + k] = x;
+    if (r < R) s_scratch[r * 64 + k] = x;
   }
   __syncthreads();
   double x = 0;
@@ -78,23 +95,26 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   if (L.shard.world > 1 || L.shard.mine) {
     // ---- exchange of the rank sums through peer memory (see ShardView)
     const ShardView& sh = L.shard;
-    const size_t rec = (((size_t)(sh.serial & 1) * sh.world + sh.rank) * sh.cap + pair) * kMailStride;
+    // serial of THIS evaluation of THIS pair: the align's base plus the pair's own evaluation count - the same on every rank whatever
+    // number of launches (some of them idle for this pair) each host has issued
+    const long long serial = sh.serial + s_state.n_eval + s_state.n_hess + 1;
+    const size_t rec = (((size_t)(serial & 1) * sh.world + sh.rank) * sh.cap + pair) * kMailStride;
     if (threadIdx.x < nv)
       for (int p = 0; p < sh.world; p++) *reinterpret_cast<volatile double*>(sh.peers[p] + rec + threadIdx.x) = x;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < sh.world) {    // one flag store per peer, after every value store of this CTA is visible system-wide
       __threadfence_system();
-      *reinterpret_cast<volatile long long*>(sh.peers[threadIdx.x] + rec + 43) = sh.serial;
+      *reinterpret_cast<volatile long long*>(sh.peers[threadIdx.x] + rec + 43) = serial;
     }
     __shared__ int s_peer_ok;
     if (threadIdx.x == 0) s_peer_ok = 1;
     __syncthreads();
     if (threadIdx.x < sh.world) {
       const volatile long long* flag =
-          reinterpret_cast<const volatile long long*>(sh.mine + (((size_t)(sh.serial & 1) * sh.world + threadIdx.x) * sh.cap + pair) * kMailStride + 43);
+          reinterpret_cast<const volatile long long*>(sh.mine + (((size_t)(serial & 1) * sh.world + threadIdx.x) * sh.cap + pair) * kMailStride + 43);
       const long long t0 = clock64();
-      while (*flag != sh.serial) {
+      while (*flag != serial) {
         if (clock64() - t0 > sh.timeout_cycles) { s_peer_ok = 0; break; }
         __nanosleep(64);
       }
@@ -105,30 +125,44 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
     if (threadIdx.x < nv) {
       x = 0;
       for (int r = 0; r < sh.world; r++)
-        x += *reinterpret_cast<const volatile double*>(sh.mine + (((size_t)(sh.serial & 1) * sh.world + r) * sh.cap + pair) * kMailStride + threadIdx.x);
+        x += *reinterpret_cast<const volatile double*>(sh.mine + (((size_t)(serial & 1) * sh.world + r) * sh.cap + pair) * kMailStride + threadIdx.x);
     }
   }
   if (threadIdx.x < nv) {
     const int k = threadIdx.x;
-    if (kind == EVAL_HESS27) { if (k >= 7) S.H[k - 7] = x; }
+    if (kind == EVAL_HESS27) { if (k >= 7) s_state.H[k - 7] = x; }
     else {
-      if (k == 0) S.score = x;
-      else if (k < 7) S.g[k - 1] = x;
-      else if (kind == EVAL_DERIV_H) S.H[k - 7] = x;
+      if (k == 0) s_state.score = x;
+      else if (k < 7) s_state.g[k - 1] = x;
+      else if (kind == EVAL_DERIV_H) s_state.H[k - 7] = x;
     }
   }
   // computeDerivatives zeroes the Hessian even when it does not fill it (ndt_omp_impl2.hpp:204)
-  if (kind == EVAL_DERIV_NOH && threadIdx.x < 36) S.H[threadIdx.x] = 0.0;
-  __threadfence_block();
+  if (kind == EVAL_DERIV_NOH && threadIdx.x < 36) s_state.H[threadIdx.x] = 0.0;
+  __syncthreads();
+  bool fin = false;
+  if (threadIdx.x == 0) {
+    if (L.advance) fin = align_state_advance(s_state, c, n_src, L.d_trace ? L.d_trace + (size_t)pair * kMaxTrace : nullptr);
+    else {
+      s_state.eval_kind = EVAL_NONE;
+      if (kind != EVAL_HESS27) s_state.n_eval++; else s_state.n_hess++;
+    }
+  }
+  __syncthreads();
+  {
+    int* dst = reinterpret_cast<int*>(&S);
+    const int* src = reinterpret_cast<const int*>(&s_state);
+    for (int i = threadIdx.x; i < (int)(sizeof(AlignState) / 4); i += kEvalThreads) dst[i] = src[i];
+  }
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     L.d_tickets[pair] = 0;
-    if (L.advance) {
-      bool fin = align_state_advance(S, c, n_src, L.d_trace ? L.d_trace + (size_t)pair * kMaxTrace : nullptr);
-      if (fin) atomicAdd(L.d_done_count, 1);
-    } else {
-      S.eval_kind = EVAL_NONE;
-      if (kind != EVAL_HESS27) S.n_eval++; else S.n_hess++;
+    if (fin) {
+      // the pair that completes the batch publishes the align's serial in host-mapped memory: the host polls that word instead of
+      // synchronising the stream (every state of the batch is in device memory and fenced by then)
+      const int done = atomicAdd(L.d_done_count, 1) + 1;
+      if (done == L.n_pairs && L.h_done_flag) { __threadfence_system(); *L.h_done_flag = L.align_serial; }
     }
     __threadfence();
   }

@@ -104,7 +104,7 @@ struct ShardView {
   double* const* peers = nullptr;          // device array [world]: mailbox base of every rank as mapped in this process
   double* mine = nullptr;                  // this rank's mailbox: [2 parity][world][cap][kMailStride]
   int rank = 0, world = 1, cap = 0;
-  long long serial = 0;                    // evaluation launch counter, identical on every rank
+  long long serial = 0;                    // base serial of the align / tap in flight, identical on every rank (eval_finish adds the pair's evaluation count)
   long long timeout_cycles = 0;
   int* d_error = nullptr;                  // set to 1 when a peer did not answer in time
 };
@@ -117,6 +117,8 @@ struct EvalLaunch {
   double* d_partials;         // [n_pairs][blocks_per_pair][kAcc]
   unsigned int* d_tickets;    // [n_pairs]
   int* d_done_count;          // incremented once per finished pair
+  volatile int* h_done_flag = nullptr;   // host-mapped word: receives align_serial when the last pair of the batch finishes (null: not used)
+  int align_serial = 0;
   int n_pairs;
   int blocks_per_pair;
   int advance;                // 1: run the align state machine; 0: tap mode, only store score/g/H
