@@ -3,6 +3,7 @@
 // state machine in ndt_state.cuh.  No CPU fallback: without a usable sm_100 device every entry point fails.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <new>
 #include "ndt_internal.cuh"
 #include "ndt_state.cuh"
@@ -151,6 +152,7 @@ struct lvs_ndt_batch {
   volatile int* h_flag = nullptr;
   int* d_flag_alias = nullptr;
   int align_serial = 0;
+  long long* d_dbg = nullptr;        // LVS_DEBUG_TIMING=1: managed buffer of tail clock stamps (diagnostics, tools/tail_timing.py)
   cudaStream_t rb = nullptr;         // read-back stream: results are copied out as soon as the flag is seen, ahead of idle launches still queued on st
   std::vector<cudaEvent_t> ev_win;   // ring of per-launch events (window bookkeeping)
   GridParams* h_gp_all = nullptr;   // pinned, one per target slot: batched geometry read-back
@@ -366,7 +368,7 @@ static int reserve_pairs(lvs_ndt_batch* b, int n_pairs, int bpp) {
   if ((size_t)b->pair_cap * bpp > (size_t)b->bpp_cap) {
     if (b->d_partials) cudaFree(b->d_partials);
     b->d_partials = nullptr;
-    CUDA_TRY(cudaMalloc(&b->d_partials, (size_t)b->pair_cap * bpp * kAcc * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&b->d_partials, (size_t)b->pair_cap * bpp * kPartialStride * sizeof(double)));
     b->bpp_cap = b->pair_cap * bpp;
   }
   return LVS_OK;
@@ -393,9 +395,14 @@ static PairDesc make_pair(lvs_ndt_batch* b, int src_slot, int tgt_slot) {
 static int choose_bpp(lvs_ndt_batch* b, int n_pairs, int max_src) {
   if (b->blocks_per_pair_override > 0) return b->blocks_per_pair_override;
   const int ppi = eval_points_per_cta_iteration();
-  const int by_points = std::max(1, (max_src + ppi - 1) / ppi);          // one iteration per CTA: the finest useful split
+  const int by_points = std::max(1, (max_src + ppi - 1) / ppi);          // one full iteration per CTA
   const int resident = 148 * eval_max_resident_ctas_per_sm();
-  if ((long long)n_pairs * by_points <= resident) return by_points;      // cannot even fill one wave: use every SM we can
+  if ((long long)n_pairs * by_points <= resident) {
+    // cannot fill one wave with full iterations: spread the points over every resident CTA instead (the warps of a pair take equal
+    // contiguous ranges), down to 64 points per CTA - what a single-pair align waits for is the slowest warp
+    const int finest = std::max(1, (max_src + 63) / 64);
+    return std::max(1, std::min(resident / n_pairs, finest));
+  }
   const int coarse = std::max(1, by_points / 4);                          // >= 4 iterations per CTA
   int best = 1;
   double best_eff = -1.0;
@@ -481,6 +488,7 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   if (b->shard_on && n_pairs > b->shard_cap) return fail(LVS_ERR_INVALID_ARG, "%d pairs exceed the sharded batch's max_pairs %d", n_pairs, b->shard_cap);
   shard_view(b, L);
   L.h_done_flag = b->d_flag_alias; L.align_serial = ++b->align_serial;
+  L.d_dbg = b->d_dbg;
   // worst case: initial pass + (max_iter + 2) outer iterations of (first + 10 trials + Hessian pass)
   P.max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
   L.shard.serial = b->shard_serial;            // base of this align; every pair adds its own evaluation count (eval_finish)
@@ -683,6 +691,10 @@ static int batch_create(const lvs_ndt_params* params, int device, void* stream, 
     if ((e = cudaHostGetDevicePointer((void**)&b->d_flag_alias, hf, 0)) != cudaSuccess) return bail(cuda_fail(e, "cudaHostGetDevicePointer", __FILE__, __LINE__));
   }
   if ((e = cudaStreamCreateWithFlags(&b->rb, cudaStreamNonBlocking)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+  if (getenv("LVS_DEBUG_TIMING")) {
+    if ((e = cudaMallocManaged(&b->d_dbg, 8 * 64 * sizeof(long long))) != cudaSuccess) return bail(cuda_fail(e, "cudaMallocManaged", __FILE__, __LINE__));
+    memset(b->d_dbg, 0, 8 * 64 * sizeof(long long));
+  }
   b->ev_win.assign(kWinRing, nullptr);
   for (auto& ev : b->ev_win)
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
@@ -960,6 +972,7 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   if (b->h_states) cudaFreeHost(b->h_states);
   if (b->h_done) cudaFreeHost(b->h_done);
   if (b->h_flag) cudaFreeHost((void*)b->h_flag);
+  if (b->d_dbg) cudaFree(b->d_dbg);
   if (b->rb) { cudaStreamSynchronize(b->rb); cudaStreamDestroy(b->rb); }
   for (auto ev : b->ev_win) if (ev) cudaEventDestroy(ev);
   if (b->h_gp_all) cudaFreeHost(b->h_gp_all);
@@ -1411,6 +1424,15 @@ int lvs_ndt_lookup_keys(lvs_ndt_t* h, const float T16[16], int32_t* keys_out) {
   cudaFree(d_keys);
   if (e != cudaSuccess) return cuda_fail(e, "lookup_keys", __FILE__, __LINE__);
   return rc;
+}
+
+// Diagnostics, not part of the public header: the 8 tail stamps of pair 0's last evaluation (LVS_DEBUG_TIMING=1), in SM clocks.
+__attribute__((visibility("default"))) int lvs_ndt_batch_debug_stamps(lvs_ndt_batch_t* b, long long out8[8]) {
+  if (!b || !out8 || !b->d_dbg) return fail(LVS_ERR_INVALID_ARG, "debug timing is off");
+  cudaSetDevice(b->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 8; i++) out8[i] = b->d_dbg[i];
+  return LVS_OK;
 }
 
 int lvs_ndt_handle_batch(lvs_ndt_t* h, lvs_ndt_batch_t** out) {

@@ -241,7 +241,11 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
   const int div0 = G.max_b[0] - G.min_b[0] + 1, div1 = G.max_b[1] - G.min_b[1] + 1, div2 = G.max_b[2] - G.min_b[2] + 1;
 
   if (!G.empty) {
-    for (int base = (blk * kWarps + warp) * kPtsPerIter; base < P.n_src; base += bpp * kWarps * kPtsPerIter) {
+    // every warp of the pair's CTAs owns one contiguous range of the source, so that any number of CTAs splits the cloud evenly
+    // (a single pair is spread over every SM: 35 points per warp at 125 k points instead of 64 on half of the SMs)
+    const long long n_warps = (long long)bpp * kWarps, wid = (long long)blk * kWarps + warp;
+    const int lo = (int)(wid * P.n_src / n_warps), hi = (int)((wid + 1) * P.n_src / n_warps);
+    for (int base = lo; base < hi; base += kPtsPerIter) {
       // ---- phase A: transform, probe the index grid, queue every (point, cell) hit of the warp's 64 points
       int nq = 0;
       // consumes whole rounds from the queue and moves the remainder (< 32 entries) to its front; returns the new length
@@ -263,7 +267,7 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
         const int slot = h * 32 + lane;
         const int i = base + slot;
         float tx = 0.f, ty = 0.f, tz = 0.f;
-        bool ok = i < P.n_src;
+        bool ok = i < hi;
         if (ok) {
           const float4 s = __ldg(P.src + i);
           transform_point(T, s.x, s.y, s.z, tx, ty, tz);
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   __shared__ float s_T[16], s_R[9];
   __shared__ unsigned long long s_etab[32];
   __shared__ int s_last;
+  const long long t_entry = clock64();
   const int pair = blockIdx.x / L.blocks_per_pair, blk = blockIdx.x % L.blocks_per_pair;
   AlignState& S = L.d_states[pair];
   const int kind = S.eval_kind;
@@ -362,11 +367,11 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   __syncthreads();
   const GridView G = load_grid_view(P.gp);
   const float gd2 = (float)c.gauss_d2;
-  double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
+  double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kPartialStride;
   const int bpp = L.blocks_per_pair;
   if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
   else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
-  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last);
+  eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last, t_entry);
 }
 
 template <int MODE, bool PCA>

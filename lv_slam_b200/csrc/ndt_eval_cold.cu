@@ -269,7 +269,8 @@ __device__ __noinline__ void run_hess27(const PairDesc& P, const GridView& G, co
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEvalThreads) ndt_eval_cold_kernel(EvalLaunch L) {
-  __shared__ double s_red[(kEvalThreads / 32) * kAcc];
+  __shared__ double s_red[704];            // CTA reduction (8 warps x 43) and eval_finish's scratch (11 x 64)
+  static_assert((kEvalThreads / 32) * kAcc <= 704, "s_red");
   __shared__ float s_T[16], s_R[9];
   __shared__ double s_Rd[9];
   __shared__ int s_last;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kEvalThreads) ndt_eval_cold_kernel(EvalLaunch 
   const GridView G = load_grid_view(P.gp);
   const float gd2 = (float)c.gauss_d2;
   const bool pca = c.variant == LVS_NDT_PCA;
-  double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kAcc;
+  double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kPartialStride;
   const int bpp = L.blocks_per_pair;
   if (kind == EVAL_HESS27) run_hess27(P, G, s_T, s_Rd, blk, bpp, c.gauss_d1, c.gauss_d2, c.resolution, s_red, partial);
   else if (kind == EVAL_DERIV_H) run_kdtree<true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);

@@ -46,12 +46,15 @@ __device__ __forceinline__ void transform_point(const float* T, float x, float y
 
 // Completion of one evaluation of one pair: every CTA has stored its partial[nv]; the LAST CTA to take a ticket sums the
 // bpp partials in a fixed order (run-to-run deterministic), deposits (score, g, H) in the pair's AlignState and advances the
-// Newton / More-Thuente state machine so that the next launch knows what to evaluate.  s_scratch: >= 320 doubles of shared memory.
+// Newton / More-Thuente state machine so that the next launch knows what to evaluate.  s_scratch: >= 704 doubles of shared memory.
 // The tail is what a single-pair align waits for between two evaluations, so it is kept short: the partials are fetched with every
-// load of a thread in flight at once (5 row groups x 43 columns of threads), and the ~0.9 KB state is copied to shared memory once,
+// load of a thread in flight at once (11 row groups x 22 column pairs of threads, double2 loads), and the ~0.9 KB state is copied to shared memory once,
 // advanced there by one thread (6x6 solve, SE(3) exp / log) and copied back once, instead of being walked field by field in L2.
-__device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int kind, int nv, int n_src, double* s_scratch, int* s_last) {
+__device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int kind, int nv, int n_src, double* s_scratch, int* s_last, long long t_entry = 0) {
   AlignState& S = L.d_states[pair];
+  const bool dbg = L.d_dbg != nullptr && threadIdx.x == 0;
+  long long stamp[8];
+  if (dbg) { stamp[0] = t_entry; stamp[1] = clock64(); }
   const AlignConsts& c = L.consts;
   const int bpp = L.blocks_per_pair;
   __threadfence();
@@ -63,6 +66,7 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   __syncthreads();
   if (!*s_last) return;
   __threadfence();
+  if (dbg) stamp[2] = clock64();
   __shared__ __align__(16) AlignState s_state;
   static_assert(sizeof(AlignState) % 4 == 0, "AlignState is copied word by word");
   {
@@ -70,25 +74,26 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
     int* dst = reinterpret_cast<int*>(&s_state);
     for (int i = threadIdx.x; i < (int)(sizeof(AlignState) / 4); i += kEvalThreads) dst[i] = __ldcg(src + i);
   }
-  constexpr int R = 5;                   // row groups x 43 columns = 215 of the 256 threads
-  static_assert(R * kAcc <= kEvalThreads, "reduction layout");
+  constexpr int R = 11;                  // row groups x 22 column pairs = 242 of the 256 threads, one double2 per load
+  static_assert(R * (kPartialStride / 2) <= kEvalThreads && R * 64 <= 1024, "reduction layout");
   {
-    const int k = threadIdx.x % kAcc, r = threadIdx.x / kAcc;
-    double x = 0;
-    if (r < R && k < nv) {
-      const double* base = L.d_partials + (size_t)pair * bpp * kAcc + k;
-      constexpr int kIn = 12;            // loads in flight per thread
+    const int kp = threadIdx.x % (kPartialStride / 2), r = threadIdx.x / (kPartialStride / 2);
+    double x0 = 0, x1 = 0;
+    if (r < R && 2 * kp < nv) {
+      const double2* base = reinterpret_cast<const double2*>(L.d_partials + (size_t)pair * bpp * kPartialStride) + kp;
+      constexpr int kIn = 14;            // loads in flight per thread
       for (int b0 = r; b0 < bpp; b0 += R * kIn) {
-        double v[kIn];
+        double2 v[kIn];
 #pragma unroll
-        for (int u = 0; u < kIn; u++) { const int b = b0 + R * u; v[u] = b < bpp ? __ldcg(base + (size_t)b * kAcc) : 0.0; }
+        for (int u = 0; u < kIn; u++) { const int b = b0 + R * u; v[u] = b < bpp ? __ldcg(base + (size_t)b * (kPartialStride / 2)) : make_double2(0.0, 0.0); }
 #pragma unroll
-        for (int u = 0; u < kIn; u++) x += v[u];      // adding +0.0 past the end is exact
+        for (int u = 0; u < kIn; u++) { x0 += v[u].x; x1 += v[u].y; }      // adding +0.0 past the end is exact
       }
     }
-    if (r < R) s_scratch[r * 64 + k] = x;
+    if (r < R) { s_scratch[r * 64 + 2 * kp] = x0; s_scratch[r * 64 + 2 * kp + 1] = x1; }
   }
   __syncthreads();
+  if (dbg) stamp[3] = clock64();
   double x = 0;
   if (threadIdx.x < nv)
     for (int r = 0; r < R; r++) x += s_scratch[r * 64 + threadIdx.x];
@@ -140,14 +145,42 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   // computeDerivatives zeroes the Hessian even when it does not fill it (ndt_omp_impl2.hpp:204)
   if (kind == EVAL_DERIV_NOH && threadIdx.x < 36) s_state.H[threadIdx.x] = 0.0;
   __syncthreads();
+  if (dbg) stamp[4] = clock64();
+  // Newton direction H^-1 (-g) of this evaluation, by warp 1 (the state machine asks for it in almost every pass)
+  // and, by one thread of warp 2 at the same time, the pose composition log(exp(dir a_t) exp(p)) the state machine will ask for if this
+  // evaluation ends a line search (the normal case): two chains of fp64 transcendentals that do not depend on each other
+  __shared__ double s_lu[6][7], s_dp[6], s_pn[6], s_pn_at;
+  __shared__ int s_perm[6], s_lu_ok, s_pn_ok;
+  if (L.advance && threadIdx.x == 64) {
+    const bool useful = s_state.phase == PH_MT_FIRST || s_state.phase == PH_MT_TRIAL || s_state.phase == PH_HESS27;
+    if (useful) {
+      double delta[6], pn[6];
+      for (int i = 0; i < 6; i++) delta[i] = s_state.dir[i] * s_state.a_t;
+      se3_log(se3_mul(se3_exp(delta), se3_exp(s_state.p)), pn);
+      for (int i = 0; i < 6; i++) s_pn[i] = pn[i];
+      s_pn_at = s_state.a_t;
+    }
+    s_pn_ok = useful ? 1 : 0;
+  }
+  if (L.advance && threadIdx.x >= 32 && threadIdx.x < 64) {
+    const int lane = threadIdx.x - 32;
+    for (int e = lane; e < 42; e += 32) s_lu[e / 7][e % 7] = (e % 7 < 6) ? s_state.H[(e / 7) * 6 + e % 7] : -s_state.g[e / 7];
+    __syncwarp();
+    const bool ok = lu6_solve_warp(s_lu, s_perm, s_dp, lane);
+    if (lane == 0) s_lu_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (dbg) stamp[5] = clock64();
   bool fin = false;
   if (threadIdx.x == 0) {
-    if (L.advance) fin = align_state_advance(s_state, c, n_src, L.d_trace ? L.d_trace + (size_t)pair * kMaxTrace : nullptr);
+    if (L.advance) fin = align_state_advance(s_state, c, n_src, L.d_trace ? L.d_trace + (size_t)pair * kMaxTrace : nullptr, s_lu_ok ? s_dp : nullptr,
+                                             s_pn_ok ? s_pn : nullptr, s_pn_at);
     else {
       s_state.eval_kind = EVAL_NONE;
       if (kind != EVAL_HESS27) s_state.n_eval++; else s_state.n_hess++;
     }
   }
+  if (dbg) stamp[6] = clock64();
   __syncthreads();
   {
     int* dst = reinterpret_cast<int*>(&S);
@@ -156,6 +189,7 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   }
   __threadfence();
   __syncthreads();
+  if (dbg) { stamp[7] = clock64(); for (int i = 0; i < 8; i++) L.d_dbg[pair * 8 + i] = stamp[i]; }
   if (threadIdx.x == 0) {
     L.d_tickets[pair] = 0;
     if (fin) {

@@ -191,7 +191,10 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
   };
 
   if (!G.empty) {
-    for (int base = (blk * kFWarps + warp) * kFPtsPerIter; base < P.n_src; base += bpp * kFWarps * kFPtsPerIter) {
+    // every warp of the pair's CTAs owns one contiguous range of the source (see ndt_eval.cu)
+    const long long n_warps = (long long)bpp * kFWarps, wid = (long long)blk * kFWarps + warp;
+    const int lo = (int)(wid * P.n_src / n_warps), hi = (int)((wid + 1) * P.n_src / n_warps);
+    for (int base = lo; base < hi; base += kFPtsPerIter) {
       int nq = 0;
       // consumes whole rounds from the queue and moves the remainder (< 32 entries) to its front; returns the new length
       auto drain = [&]() {
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
         const int slot = h * 32 + lane;
         const int i = base + slot;
         float tx = 0.f, ty = 0.f, tz = 0.f;
-        bool ok = i < P.n_src;
+        bool ok = i < hi;
         if (ok) {
           const float4 s = __ldg(P.src + i);
           transform_point(T, s.x, s.y, s.z, tx, ty, tz);
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
   // CTA partial: every output slot sums the 8 warps in fixed order and lands at its place(s) in the canonical 43-vector
   s_red[warp][lane] = accd;
   __syncthreads();
-  double* partial = L.d_partials + ((size_t)pair * bpp + blk) * kAcc;
+  double* partial = L.d_partials + ((size_t)pair * bpp + blk) * kPartialStride;
   if (threadIdx.x < kFSlots) {
     double x = 0;
 #pragma unroll

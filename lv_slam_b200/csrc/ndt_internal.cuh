@@ -114,11 +114,12 @@ struct EvalLaunch {
   const PairDesc* d_pairs;
   AlignState* d_states;
   TraceRec* d_trace;          // [n_pairs][kMaxTrace] or null
-  double* d_partials;         // [n_pairs][blocks_per_pair][kAcc]
+  double* d_partials;         // [n_pairs][blocks_per_pair][kPartialStride], kAcc used
   unsigned int* d_tickets;    // [n_pairs]
   int* d_done_count;          // incremented once per finished pair
   volatile int* h_done_flag = nullptr;   // host-mapped word: receives align_serial when the last pair of the batch finishes (null: not used)
   int align_serial = 0;
+  long long* d_dbg = nullptr;   // diagnostics (LVS_DEBUG_TIMING=1): clock64 stamps of the last CTA's tail, 8 per pair; null in normal operation
   int n_pairs;
   int blocks_per_pair;
   int advance;                // 1: run the align state machine; 0: tap mode, only store score/g/H

@@ -97,6 +97,66 @@ LVS_HD void align_state_init(AlignState& s, const float* guess16, int trace_on) 
 
 struct StepOut { bool finished; };
 
+#ifdef __CUDACC__
+// The pseudo-inverse fallback is cold (H numerically singular): kept out of line so that its 36-element work arrays do not inflate the
+// stack frame and the register pressure of the state machine around it.
+static __device__ __noinline__ void svd6_solve_cold(const double* A, const double* b, double* x) { svd6_solve(A, b, x); }
+
+// lu6_solve (lvs_math.cuh) carried out by one warp on an augmented 6x7 matrix in shared memory: the same compare-and-swap pivoting
+// (through a row permutation instead of physical swaps), the same multiplier and the same element updates, each done by its own
+// lane - bit-identical results, ~1 us instead of a 36-double register array spilling on a single thread.  M[i][6] = right-hand side;
+// perm: 6 ints of shared memory; x: 6 doubles of shared memory.  Returns false (on every lane) where lu6_solve would.
+__device__ __forceinline__ bool lu6_solve_warp(double (*M)[7], int* perm, double* x, int lane) {
+  double amax = 0.0;
+  for (int e = lane; e < 36; e += 32) amax = fmax(amax, fabs(M[e / 6][e % 6]));
+  for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (!(amax > 0.0) || !(amax < 1.0e300)) return false;
+  const double tiny = amax * 1e-10;
+  if (lane < 6) perm[lane] = lane;
+  __syncwarp();
+  for (int k = 0; k < 6; k++) {
+    {
+      // pivot = the largest |entry| of column k among the remaining rows, the first one on a tie - the row lu6_solve's
+      // compare-and-swap chain brings to position k (the order it leaves the OTHER rows in differs, which no result depends on:
+      // every row's arithmetic is independent of its position and later pivots are chosen by value)
+      const int pi = (lane >= k && lane < 6) ? perm[lane] : 0;
+      double v = (lane >= k && lane < 6) ? fabs(M[pi][k]) : -1.0;
+      int at = lane;
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, o, 8);
+        const int oa = __shfl_down_sync(0xffffffffu, at, o, 8);
+        if (ov > v || (ov == v && oa < at)) { v = ov; at = oa; }      // the lower index wins ties
+      }
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (lane == 0 && at != k) { const int t = perm[k]; perm[k] = perm[at]; perm[at] = t; }
+    }
+    __syncwarp();
+    const int pk = perm[k];
+    const double piv = M[pk][k];
+    if (!(fabs(piv) > tiny)) return false;
+    const double inv = 1.0 / piv;
+    const int w = 6 - k;                                   // columns k+1 .. 6 of the rows below
+    if (lane < (5 - k) * w) {
+      const int pi = perm[k + 1 + lane / w], j = k + 1 + lane % w;
+      const double f = M[pi][k] * inv;
+      M[pi][j] -= f * M[pk][j];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    for (int k = 5; k >= 0; k--) {
+      const int pk = perm[k];
+      double t = M[pk][6];
+      for (int j = k + 1; j < 6; j++) t -= M[pk][j] * x[j];
+      x[k] = t / M[pk][k];
+    }
+  }
+  __syncwarp();
+  return true;
+}
+#endif
+
 LVS_HD bool mt_keep_searching(const AlignState& s) {   // loop condition at :920
   const double nu = 0.9;
   return !s.interval_converged && s.step_iterations < 10 && !(s.psi_t <= 0 && s.d_phi_t <= -nu * s.d_phi_0);
@@ -104,7 +164,11 @@ LVS_HD bool mt_keep_searching(const AlignState& s) {   // loop condition at :920
 
 // One pass through the state machine after an evaluation has deposited (score, g, H) in the state.
 // Returns true when the align is finished.  n_src = number of source points (trans_probability divisor).
-LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, TraceRec* trace) {
+// Device callers may hand in two results computed by other warps while this thread was busy elsewhere (eval_finish):
+//   newton_pre   H^-1 (-g) of this evaluation by elimination (null: the elimination failed -> pseudo-inverse fallback here)
+//   compose_pre  log(exp(dir * a_t) * exp(p)) for the dir, a_t and p the state held on entry, compose_a_t = that a_t (null: not computed)
+LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, TraceRec* trace, const double* newton_pre = nullptr,
+                                const double* compose_pre = nullptr, double compose_a_t = 0.0) {
   const double mu = 1.e-4;
   bool need_newton = false;   // start a new outer iteration (solve + line-search setup)
   bool step_done = false;     // computeStepLengthMT returned s.a_t
@@ -172,8 +236,13 @@ LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, 
     if (step_done) {
       // back in computeTransformation (:159-183)
       double delta[6], pn[6];
-      for (int i = 0; i < 6; i++) delta[i] = s.dir[i] * s.a_t;
-      se3_log(se3_mul(se3_exp(delta), se3_exp(s.p)), pn);
+      if (compose_pre && s.a_t == compose_a_t) {       // dir and p cannot have changed since entry when a_t has not
+        for (int i = 0; i < 6; i++) pn[i] = compose_pre[i];
+        compose_pre = nullptr;                           // valid for the first composition of this call only
+      } else {
+        for (int i = 0; i < 6; i++) delta[i] = s.dir[i] * s.a_t;
+        se3_log(se3_mul(se3_exp(delta), se3_exp(s.p)), pn);
+      }
       if (trace && s.trace_on && s.n_trace < kMaxTrace) {
         TraceRec& t = trace[s.n_trace];
         for (int i = 0; i < 6; i++) { t.p_before[i] = s.p[i]; t.dir[i] = s.dir[i]; t.p_after[i] = pn[i]; }
@@ -198,7 +267,13 @@ LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, 
       for (int i = 0; i < 6; i++) ng[i] = -s.g[i];
       // JacobiSVD::solve == H^-1 (-g) when H is numerically full rank (the normal case, cond ~1e4): elimination with partial
       // pivoting is ~50x cheaper on a single GPU thread; the one-sided Jacobi SVD keeps the pseudo-inverse semantics otherwise.
+      // newton_pre (device): the caller's warp has already run the elimination on this evaluation's (H, -g); null = it failed
+#ifdef __CUDA_ARCH__
+      if (newton_pre) { for (int i = 0; i < 6; i++) dp[i] = newton_pre[i]; }
+      else svd6_solve_cold(s.H, ng, dp);
+#else
       if (!lu6_solve(s.H, ng, dp)) svd6_solve(s.H, ng, dp);
+#endif
       double nrm = sqrt(dot6(dp, dp));
       if (nrm == 0 || nrm != nrm) {
         s.trans_probability = s.score / (double)n_src;

@@ -53,6 +53,7 @@ struct GridParams {
 __host__ __device__ inline int grid_decode_any(int v) { return v >= 0 ? v : -2 - v; }
 
 constexpr int kAcc = 43;   // score + gradient[6] + full Hessian[36] (the reference's H is not symmetric)
+constexpr int kPartialStride = 44;   // doubles between the partial vectors of two CTAs (even: the last CTA reads them as double2)
 
 enum EvalKind { EVAL_NONE = -1, EVAL_DERIV_H = 0, EVAL_DERIV_NOH = 1, EVAL_HESS27 = 2 };
 enum Phase { PH_INIT = 0, PH_MT_FIRST = 1, PH_MT_TRIAL = 2, PH_HESS27 = 3, PH_DONE = 9 };

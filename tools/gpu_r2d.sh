@@ -4,9 +4,9 @@ timeout 1500 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; ech
 tail -6 $OUT/pytest_gpu.log
 timeout 600 python bench.py --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?" >> $OUT/bench.err
 tail -3 $OUT/bench.err
-python - <<'PY'
+python - $OUT/bench.json <<'PY'
 import json,sys
-b=json.load(open(sys.argv[1] if len(sys.argv)>1 else 'gpurun_out/r2d/bench.json'))
+b=json.load(open(sys.argv[1]))
 print("top value %.0f e2e %.0f launch %.3f ms" % (b['value'], b['e2e']['value'], b['roofline']['avg_launch_ms']))
 t=b['modes']['tolerance']; print("tol value %.0f e2e %.0f launch %.3f ms" % (t['value'], t['e2e']['value'], t['roofline']['avg_launch_ms']))
 for k,v in b['configs']['pca_direct1'].items():
