@@ -115,7 +115,8 @@ int lvs_ndt_set_source(lvs_ndt_t* h, const float* xyz, size_t n, size_t stride_b
 
 /* align(output, guess): runs computeTransformation (ndt_omp_impl2.hpp:88-188) on the device. */
 int lvs_ndt_align(lvs_ndt_t* h, const float guess[16], lvs_ndt_result* out);
-/* The `output` cloud of align(): final_transformation * source, packed xyz float, n_source points. */
+/* The `output` cloud of align(): final_transformation * source, packed xyz float, n_source points (on a point-sharded object: the
+ * points of this rank's chunk only). */
 int lvs_ndt_get_aligned_cloud(lvs_ndt_t* h, float* xyz_out, int on_device);
 /* Per-iteration trace of the last align (at most max_iterations + 2 records). */
 int lvs_ndt_get_trace(lvs_ndt_t* h, lvs_ndt_trace_rec* recs, int capacity, int* n_out);

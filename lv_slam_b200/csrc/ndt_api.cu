@@ -163,6 +163,8 @@ struct lvs_ndt_batch {
   size_t fit_cap = 0;
   int trace_on = 0;
   int last_n_pairs = 0;
+  float last_final_T[16] = {};     // pair 0 of the last align (the parity taps reuse h_states[0], so the getters read these copies)
+  int last_n_trace = 0;
   // stats
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool ev_end_pending = false;
@@ -179,6 +181,8 @@ struct lvs_ndt_batch {
   double** d_peers = nullptr;          // device array of every rank's mailbox as mapped here
   std::vector<double*> peer_ptrs;      // the same on the host; entries != d_mail were opened with cudaIpcOpenMemHandle
   long long shard_serial = 0;
+  long long shard_timeout_cycles = 60000000000LL;   // ~30 s at 1.9 GHz (LVS_SHARD_TIMEOUT_S overrides): ranks are separate processes, a first-call
+                                                     // cudaMalloc, a sanitizer or a loaded host may delay a peer's launch by seconds
   int *d_shard_error = nullptr, *h_shard_error = nullptr;
   int blocks_per_pair_override = 0;
   int chunk_first = 6, chunk_next = 4;
@@ -420,7 +424,7 @@ static void shard_view(lvs_ndt_batch* b, EvalLaunch& L) {
   if (!b->shard_on) return;
   L.shard.peers = b->d_peers; L.shard.mine = b->d_mail;
   L.shard.rank = b->shard_rank; L.shard.world = b->shard_world; L.shard.cap = b->shard_cap;
-  L.shard.timeout_cycles = 4000000000LL;      // ~2 s at 1.9 GHz
+  L.shard.timeout_cycles = b->shard_timeout_cycles;
   L.shard.d_error = b->d_shard_error;
 }
 
@@ -485,6 +489,7 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   L.d_partials = b->d_partials; L.d_tickets = b->d_tickets; L.d_done_count = b->d_done;
   L.n_pairs = n_pairs; L.blocks_per_pair = bpp; L.advance = 1;
   L.consts = make_consts(b->prm);
+  if (b->shard_on) { CUDA_TRY(cudaMemsetAsync(b->d_shard_error, 0, sizeof(int), b->st)); *b->h_shard_error = 0; }
   if (b->shard_on && n_pairs > b->shard_cap) return fail(LVS_ERR_INVALID_ARG, "%d pairs exceed the sharded batch's max_pairs %d", n_pairs, b->shard_cap);
   shard_view(b, L);
   L.h_done_flag = b->d_flag_alias; L.align_serial = ++b->align_serial;
@@ -565,6 +570,8 @@ static int align_end(lvs_ndt_batch* b, lvs_ndt_result* results) {
   b->last_launches = launches;
   b->total_launches += launches * (need_cold ? 2 : 1);
   b->last_n_pairs = n_pairs;
+  memcpy(b->last_final_T, b->h_states[0].final_T, sizeof b->last_final_T);
+  b->last_n_trace = b->h_states[0].n_trace;
   int active = 0;
   for (int i = 0; i < n_pairs; i++) {
     const AlignState& s = b->h_states[i];
@@ -1088,6 +1095,7 @@ int lvs_ndt_batch_shard_init(lvs_ndt_batch_t* b, int rank, int world, int max_pa
   CUDA_TRY(cudaMallocHost(&b->h_shard_error, sizeof(int)));
   *b->h_shard_error = 0;
   b->shard_rank = rank; b->shard_world = world; b->shard_cap = max_pairs;
+  if (const char* ts = getenv("LVS_SHARD_TIMEOUT_S")) { const double sec = atof(ts); if (sec > 0) b->shard_timeout_cycles = (long long)(sec * 1.9e9); }
   cudaIpcMemHandle_t h;
   CUDA_TRY(cudaIpcGetMemHandle(&h, b->d_mail));
   memcpy(handle_out, &h, sizeof h);
@@ -1173,7 +1181,11 @@ int lvs_ndt_set_params(lvs_ndt_t* h, const lvs_ndt_params* params) {
     CUDA_TRY(cudaStreamSynchronize(ln.st));
     rc = b->targets[0].build(b->st, b->target_pts[0].d_pts, b->target_pts[0].n, b->prm, ln.ws);
     b->total_launches += b->targets[0].launches_last_build;
-    return rc;
+    if (rc) return rc;
+    // this rebuild runs on the compute stream with the lane's scratch and is tracked by no event: finish it here, so that a
+    // following setInputTarget (another lane, same grid arrays and point buffer) cannot run against it
+    CUDA_TRY(cudaStreamSynchronize(b->st));
+    return LVS_OK;
   }
   return LVS_OK;
 }
@@ -1210,7 +1222,7 @@ int lvs_ndt_get_aligned_cloud(lvs_ndt_t* h, float* xyz_out, int on_device) {
   const int n = b->sources[0].n;
   if (n == 0) return LVS_OK;
   if ((rc = wait_all_uploads(b))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(b->d_T16, b->h_states[0].final_T, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st));
+  CUDA_TRY(cudaMemcpyAsync(b->d_T16, b->last_final_T, 16 * sizeof(float), cudaMemcpyHostToDevice, b->st));
   float* d_out = xyz_out;
   if (!on_device) {
     size_t bytes = (size_t)n * 12;
@@ -1235,7 +1247,7 @@ int lvs_ndt_get_trace(lvs_ndt_t* h, lvs_ndt_trace_rec* recs, int capacity, int* 
   int rc = set_device(b);
   if (rc) return rc;
   if (b->last_n_pairs < 1) { *n_out = 0; return LVS_OK; }
-  int n = std::min(b->h_states[0].n_trace, (int)kMaxTrace);
+  int n = std::min(b->last_n_trace, (int)kMaxTrace);
   *n_out = n;
   n = std::min(n, capacity);
   if (n > 0 && recs) {
@@ -1343,7 +1355,7 @@ int lvs_ndt_fitness_score(lvs_ndt_t* h, const float* T16, double max_range, doub
   lvs_ndt_batch* b = h->b;
   if (!T16) {
     if (b->last_n_pairs < 1) return fail(LVS_ERR_INVALID_ARG, "align() has not run and no transformation was given");
-    T16 = b->h_states[0].final_T;
+    T16 = b->last_final_T;
   }
   return fitness_score(b, 0, 0, T16, max_range, score, n_correspondences);
 }

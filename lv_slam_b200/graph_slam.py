@@ -88,7 +88,10 @@ class GraphSLAM:
         return len(self._edges)
 
     def add_se3_node(self, pose4x4):
-        v = VertexSE3(len(self._vertices), pose4x4)       # id = current vertex count (graph_slam.cpp:108)
+        # id = current vertex count (graph_slam.cpp:108); after load() of a file with other ids, the next free one
+        vid = max(len(self._vertices), getattr(self, "_next_id", 0))
+        v = VertexSE3(vid, pose4x4)
+        self._next_id = vid + 1
         self._vertices.append(v)
         return v
 
@@ -111,7 +114,9 @@ class GraphSLAM:
         nv, ne = len(self._vertices), len(self._edges)
         poses = _pg.pose7_batch(np.stack([v._T for v in self._vertices])) if nv else np.zeros((0, 7))
         fixed = np.fromiter((1 if v._fixed else 0 for v in self._vertices), dtype=np.uint8, count=nv)
-        ij = np.fromiter((x for e in self._edges for x in (e.vertices[0]._id, e.vertices[1]._id)), dtype=np.int32, count=2 * ne).reshape(ne, 2)
+        # rows of the pose array are positions in the vertex list, NOT vertex ids: a loaded g2o file may skip ids (plane / GPS nodes)
+        row = {v._id: k for k, v in enumerate(self._vertices)}
+        ij = np.fromiter((row[x] for e in self._edges for x in (e.vertices[0]._id, e.vertices[1]._id)), dtype=np.int32, count=2 * ne).reshape(ne, 2)
         meas = _pg.pose7_batch(np.stack([e.measurement for e in self._edges])) if ne else np.zeros((0, 7))
         iu = np.triu_indices(6)
         info = np.stack([e.information for e in self._edges])[:, iu[0], iu[1]] if ne else np.zeros((0, 21))
@@ -175,19 +180,20 @@ class GraphSLAM:
                             k += 1
                     self._edges.append(EdgeSE3(by_id[a], by_id[b], _pg.matrix(m), info))
         self._vertices.sort(key=lambda v: v._id)
+        self._next_id = max((v._id for v in self._vertices), default=-1) + 1
         try:
             with open(filename + ".kernels") as f:
-                kern = {}
+                kern = {}                                     # (i, j) -> records in file order: one record is consumed per edge
                 for line in f:
                     t = line.split()
                     if len(t) == 5 and t[0] == "2":           # KernelData (robust_kernel_io.cpp:51-62)
-                        kern[(int(t[1]), int(t[2]))] = (t[3], float(t[4]))
+                        kern.setdefault((int(t[1]), int(t[2])), []).append((t[3], float(t[4])))
                     elif len(t) == 4:                         # sidecars written before the vertex count was added
-                        kern[(int(t[0]), int(t[1]))] = (t[2], float(t[3]))
+                        kern.setdefault((int(t[0]), int(t[1])), []).append((t[2], float(t[3])))
                 for e in self._edges:
-                    k = kern.get((e.vertices[0]._id, e.vertices[1]._id))
-                    if k:
-                        e.kernel = k
+                    q = kern.get((e.vertices[0]._id, e.vertices[1]._id))
+                    if q:
+                        e.kernel = q.pop(0)                   # parallel edges between the same vertices take one record each
         except OSError:
             pass
         return True

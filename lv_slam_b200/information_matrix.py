@@ -13,10 +13,13 @@ DBL_MAX = float(np.finfo(np.float64).max)
 
 
 class InformationMatrixCalculator:
-    """Parameter names and defaults of InformationMatrixCalculator::load (information_matrix_calculator.hpp:21-33)."""
+    """Parameter names of InformationMatrixCalculator; defaults of the constructor the nodelet uses,
+    InformationMatrixCalculator(ros::NodeHandle&) (src/global_graph/information_matrix_calculator.cpp:8-21) - fitness_score_thresh is
+    0.5 there (2.5 only in the unused load() template, information_matrix_calculator.hpp:32).  launch/dlo_lfa_ggo_kitti.launch:107
+    sets the node's fitness_score_thresh to 2.0, which this object reads as well: pass fitness_score_thresh=2.0 to mirror that launch file."""
 
     def __init__(self, use_const_inf_matrix=False, const_stddev_x=0.5, const_stddev_q=0.1, var_gain_a=20.0, min_stddev_x=0.1,
-                 max_stddev_x=5.0, min_stddev_q=0.05, max_stddev_q=0.2, fitness_score_thresh=2.5, device=0):
+                 max_stddev_x=5.0, min_stddev_q=0.05, max_stddev_q=0.2, fitness_score_thresh=0.5, device=0):
         self.use_const_inf_matrix = use_const_inf_matrix
         self.const_stddev_x, self.const_stddev_q = const_stddev_x, const_stddev_q
         self.var_gain_a = var_gain_a

@@ -116,6 +116,19 @@ def test_graph_slam_text_round_trip(tmp_path):
     open(ref + ".kernels", "w").write("2 1 0 Huber 1\n")
     gs3 = M.GraphSLAM()
     assert gs3.load(ref) and gs3.num_edges() == 1 and gs3._arrays()[5][0] == 1.0 and np.array_equal(gs3._arrays()[2], [[1, 0]])
+    # a foreign file whose SE3 ids are not 0..n-1 (a dump that also held a floor-plane node with id 2), with two parallel edges
+    # of which only the first has a kernel record: rows follow the vertex list, kernels are consumed one per edge, new ids do not collide
+    gap = str(tmp_path / "gap.g2o")
+    info = " ".join("2" if k in (0, 6, 11) else "10" if k in (15, 18, 20) else "0" for k in range(21))
+    open(gap, "w").write("VERTEX_SE3:QUAT 0 0 0 0 0 0 0 1\nVERTEX_SE3:QUAT 1 1 0 0 0 0 0 1\nVERTEX_SE3:QUAT 3 2 0 0 0 0 0 1\nVERTEX_SE3:QUAT 4 3 0 0 0 0 0 1\n"
+                         "EDGE_SE3:QUAT 3 1 -1 0 0 0 0 0 1 " + info + "\nEDGE_SE3:QUAT 4 3 -1 0 0 0 0 0 1 " + info + "\nEDGE_SE3:QUAT 4 3 -1 0 0 0 0 0 1 " + info + "\n")
+    open(gap + ".kernels", "w").write("2 4 3 Huber 0.5\n")
+    gs4 = M.GraphSLAM()
+    assert gs4.load(gap)
+    p4, f4, ij4, m4, i4, h4 = gs4._arrays()
+    assert np.array_equal(ij4, [[2, 1], [3, 2], [3, 2]]) and p4[2, 0] == 2.0 and p4[3, 0] == 3.0
+    assert h4.tolist() == [0.0, 0.5, 0.0]
+    assert gs4.add_se3_node(np.eye(4)).id() == 5
     # KITTI pose lines (scan_matching_odom_nodelet.cpp:157-160)
     from lv_slam_b200.graph_slam import load_kitti_poses, save_kitti_poses
     Ts = [G.matrix(p) for p in g["poses7"][:5]]

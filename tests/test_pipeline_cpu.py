@@ -10,7 +10,7 @@ from lv_slam_b200 import pipeline as PL
 def test_replay_driver_on_the_cpu_chain(tmp_path):
     scans, truth = B.out_and_back()
     r = PL.replay(scans, B.OracleRegistration(O.VAR_PCA, O.DIRECT1), B.OracleRegistration(O.VAR_OMP, O.DIRECT7), B.OracleGraphSLAM("lm_var_cholmod"),
-                  B.OracleInformation(), prefilter=B.OraclePrefilter(), dump_directory=str(tmp_path / "dump"))
+                  B.OracleInformation(fitness_score_thresh=2.0), prefilter=B.OraclePrefilter(), dump_directory=str(tmp_path / "dump"))
     kf = r["keyframe_frames"]
     assert kf[0] == 0 and all(b > a for a, b in zip(kf, kf[1:])) and len(kf) >= 10
     # 1.2 m per frame: a keyframe once 10 m are exceeded (launch/dlo_lfa_ggo_kitti.launch:51), i.e. every 9th frame on the straight legs

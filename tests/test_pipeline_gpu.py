@@ -26,10 +26,10 @@ def test_replay_matches_the_cpu_chain():
     odo.setNeighborhoodSearchMethod(L.LVS_DIRECT1); odo.setTransformationEpsilon(0.01); odo.setMaximumIterations(64)
     loop = L.NormalDistributionsTransform(variant=L.LVS_NDT_OMP)
     loop.setNeighborhoodSearchMethod(L.LVS_DIRECT7); loop.setTransformationEpsilon(0.01); loop.setMaximumIterations(64)
-    g = PL.replay(scans, odo, loop, L.GraphSLAM("lm_var_cholmod"), L.InformationMatrixCalculator(),
+    g = PL.replay(scans, odo, loop, L.GraphSLAM("lm_var_cholmod"), L.InformationMatrixCalculator(fitness_score_thresh=2.0),
                   prefilter=L.Prefilter(distance_near_thresh=0.5, distance_far_thresh=100.0, downsample_resolution=0.1))
     c = PL.replay(scans, B.OracleRegistration(O.VAR_PCA, O.DIRECT1), B.OracleRegistration(O.VAR_OMP, O.DIRECT7), B.OracleGraphSLAM("lm_var_cholmod"),
-                  B.OracleInformation(), prefilter=B.OraclePrefilter())
+                  B.OracleInformation(fitness_score_thresh=2.0), prefilter=B.OraclePrefilter())
     # every decision of the chain
     assert g["keyframe_frames"] == c["keyframe_frames"] and len(g["keyframe_frames"]) >= 10
     assert [(a, b) for a, b, _ in g["loops"]] == [(a, b) for a, b, _ in c["loops"]] and len(g["loops"]) >= 1
