@@ -49,3 +49,31 @@ def all_gather_bytes(blob, world):
     out = [None] * world
     dist.all_gather_object(out, bytes(blob))
     return out
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pins this process to the CPU cores that are local to GPU `local_rank` (sysfs local_cpulist of its PCI device), so that pinned
+    host buffers allocated afterwards are first-touched on that NUMA node and the copy engine does not cross the socket interconnect.
+    Returns a one-line description; does nothing (and says so) where the topology cannot be read."""
+    try:
+        import subprocess
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"], text=True).strip()
+        dev = bus.lower()
+        if dev.startswith("00000000:"):
+            dev = "0000:" + dev[9:]
+        path = "/sys/bus/pci/devices/%s/" % dev
+        cpus = open(path + "local_cpulist").read().strip()
+        node = open(path + "numa_node").read().strip()
+        ids = []
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-"); ids += list(range(int(a), int(b) + 1))
+            elif part:
+                ids.append(int(part))
+        allowed = sorted(set(ids) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "gpu %s numa %s cpus %s: none of them allowed for this process, not bound" % (dev, node, cpus)
+        os.sched_setaffinity(0, allowed)
+        return "gpu %s numa %s bound to %d cpus (%s)" % (dev, node, len(allowed), cpus)
+    except Exception as e:                       # containers often hide the topology
+        return "not bound (%s)" % e

@@ -20,6 +20,19 @@ namespace pclomp {
 
 enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };   // ndt_omp.h:61
 
+#ifdef LVS_SHIM_PCA
+// What pclpca::NormalDistributionsTransform::getTargetCells() (include/ndt_pca/ndt_pca.h:129-133) hands out.  The reference returns its
+// VoxelGridCovariance BY VALUE (a std::map of Leaf objects); no caller in lv_slam uses it.  The voxel grid of this implementation lives
+// in device memory, so the binding returns the same per-leaf data as flat arrays, one entry per occupied cell in ascending leaf index:
+// Leaf::nr_points / mean_ / icov_ / evals_ / centroid and the integer PCA weight getDimension2d() (voxel_grid_covariance_pca.h:128-265).
+struct TargetCells {
+  int min_b[3], max_b[3], div_b[3];                 // getMinBoxCoordinates / getMaxBoxCoordinates / getNrDivisions
+  std::vector<int32_t> keys, nr_points, weight;     // leaf index; raw point count (-1: invalidated leaf); int(scale * |mean|)
+  std::vector<double> mean, icov, evals;            // [n][3], [n][9] row-major, [n][3]
+  std::vector<float> centroid;                      // [n][3]
+};
+#endif
+
 template <typename PointSource, typename PointTarget>
 class NormalDistributionsTransform : public pcl::Registration<PointSource, PointTarget> {
   typedef pcl::Registration<PointSource, PointTarget> Base;
@@ -71,6 +84,18 @@ class NormalDistributionsTransform : public pcl::Registration<PointSource, Point
     check(lvs_ndt_fitness_score(h_, nullptr, max_range, &s, nullptr));
     return s;
   }
+#ifdef LVS_SHIM_PCA
+  TargetCells getTargetCells() const {
+    TargetCells c;
+    int n = 0;
+    check(lvs_ndt_get_grid(h_, c.min_b, c.max_b, c.div_b));
+    check(lvs_ndt_num_cells(h_, &n));
+    c.keys.resize(n); c.nr_points.resize(n); c.weight.resize(n); c.mean.resize(3 * (size_t)n); c.icov.resize(9 * (size_t)n); c.evals.resize(3 * (size_t)n);
+    c.centroid.resize(3 * (size_t)n);
+    if (n) check(lvs_ndt_get_cells(h_, c.keys.data(), c.nr_points.data(), c.mean.data(), c.icov.data(), c.evals.data(), c.centroid.data(), c.weight.data()));
+    return c;
+  }
+#endif
   double calculateScore(const PointCloudSource& cloud) const {   // evaluates an already transformed cloud (ndt_omp_impl2.hpp:1007-1040)
     lvs_ndt_t* tmp = nullptr;
     check(lvs_ndt_create(&prm_, 0, nullptr, &tmp));
