@@ -14,6 +14,8 @@ Top level = the library's default arithmetic (LVS_ACC_EXACT: the reference's flo
   configs.pair_latency  BASELINE configs[0]: one hard pair from the first-frame guess (66 iterations), single-object API
   configs.beam128       BASELINE configs[2]: 128-beam scans (~240 k points), 0.5 m voxels; point-sharded across ranks when N > 1
   configs.pgo           BASELINE configs[3]: 5 000-vertex / 19 599-edge sphere, LM and GN with the direct solver, LM with PCG
+  configs.replay        BASELINE configs[4] in small: every rank replays a chunk of the drive through prefilter + odometry (frames/s)
+  configs.pgo_50k       BASELINE configs[4] graph: 50 000 vertices / 198 999 edges, LM (one GPU)
 Each carries its own cpu_baseline (the CPU restatement in oracle/, timed here) where one was run.
 
     python bench.py [--gpus N --steps K --warmup W]            # our arm (one process per GPU under torchrun for N > 1)
@@ -536,6 +538,69 @@ def bench_beam128(args, L, torch, dist, D, rank, local_rank, world, with_cpu):
     return out
 
 
+def bench_replay(args, L, torch, dist, D, rank, local_rank, world, frames_per_rank=128):
+    """BASELINE configs[4] in small: every rank replays its own chunk of the synthetic drive through the dlo_lfa_ggo odometry chain
+    (prefilter 0.1 m -> pclpca/DIRECT1 scan-to-keyframe NDT with the nodelet's keyframe gate and constant-velocity guesses ->
+    information matrices of the keyframe edges), host clouds in, poses out; scan synthesis is outside the timed region.
+    tools/replay_scale.py is the full-size run (10 000 frames over 8 GPUs, stitched graph; profiles/r02_replay)."""
+    from lv_slam_b200 import pipeline as PL
+    from lv_slam_b200 import synth
+    lo = rank * frames_per_rank
+    scans, poses = synth.stream(frames_per_rank, seed=1000, start=lo)
+    pf = L.Prefilter(distance_near_thresh=0.5, distance_far_thresh=100.0, downsample_resolution=0.1, device=local_rank)
+    reg = L.NormalDistributionsTransform(variant=L.LVS_NDT_PCA, device=local_rank)
+    reg.setNeighborhoodSearchMethod(L.LVS_DIRECT1); reg.setTransformationEpsilon(0.01); reg.setMaximumIterations(64)
+    info = L.InformationMatrixCalculator(fitness_score_thresh=2.0, device=local_rank)
+
+    def run():
+        odo = PL.ScanMatchingOdometry(reg)
+        prev, n_key, iters = None, 0, 0
+        for f, raw in enumerate(scans):
+            cloud = np.ascontiguousarray(pf.filter(raw)[:, :3], dtype=np.float32)
+            T, is_key = odo.feed(f * 0.1, cloud)
+            if f:
+                iters += reg.getFinalNumIteration()
+            if is_key:
+                if prev is not None:
+                    info.calc_information_matrix(prev[1], cloud, np.linalg.inv(T) @ prev[0])
+                prev = (T.copy(), cloud)
+                n_key += 1
+        return T, n_key, iters, odo.aligns
+
+    run()                                            # warm-up: allocations, first-call costs
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    T, n_key, iters, aligns = run()
+    torch.cuda.synchronize()
+    wall = D.max_over_ranks(time.perf_counter() - t0, world, "cuda")
+    err = float(np.linalg.norm((np.linalg.inv(poses[0]) @ poses[-1])[:3, 3] - T[:3, 3]))
+    return {"workload": "BASELINE configs[4] in small: %d frames per rank of the synthetic 64-beam drive, prefilter + pclpca/DIRECT1 odometry + keyframe information matrices, host clouds" % frames_per_rank,
+            "metric": "replayed_frames_per_sec", "value": world * frames_per_rank / wall, "unit": "frames/s", "n_gpus": world, "wall_s": wall, "aligns_per_rank": aligns,
+            "newton_iterations_per_rank": iters, "keyframes_per_rank": n_key, "end_pose_error_vs_truth_m_rank0": err,
+            "sharding": "contiguous chunks of the drive, one per rank, no data-path collective (the chunks are stitched through their boundary frame: tools/replay_scale.py)",
+            "full_size_run": "profiles/r02_replay: 10 000 frames on 8 GPUs in 1.19 s (8 403 frames/s), 1 000 frames on one GPU in 1.06 s"}
+
+
+def bench_pgo_50k(L):
+    """The 50 000-vertex / 198 999-edge sphere of BASELINE configs[4] (LM, direct solver and PCG)."""
+    from lv_slam_b200.synth import posegraph as G
+    g = G.sphere(250, 200, seed=7)
+    out = {"workload": "BASELINE configs[4] graph: sphere, %d vertices / %d edges, Huber 1.0, LM" % (len(g["poses7"]), len(g["ij"]))}
+    for name, solver in (("lm_direct", 0), ("lm_pcg", 2)):
+        pg = L.PoseGraph(solver)
+        t0 = time.perf_counter(); pg.set_graph(g["poses7"], g["ij"], g["meas7"], g["info21"], g["huber"]); ts = time.perf_counter() - t0
+        t0 = time.perf_counter(); st = pg.optimize(1024); to = time.perf_counter() - t0
+        solves = max(st["lm_trials"], 1)
+        out[name] = {"optimize_ms": to * 1e3, "set_graph_ms": ts * 1e3, "iterations": st["iterations"], "linear_solves": solves, "ms_per_linear_solve": st["solve_ms"] / solves,
+                     "linearize_ms": st["linearize_ms"], "solve_ms": st["solve_ms"], "chi2_before": st["chi2_before"], "chi2_after": st["chi2_after"]}
+        if solver == 0:
+            out["structure"] = pg.chol_info()
+        pg.close()
+    return out
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -590,6 +655,7 @@ def main_ours(args):
         line["configs"] = {"pca_direct1" if other_variant == "pca" else "omp_direct7": sub}
         # BASELINE configs[2]: on one GPU a plain batch, on N > 1 the point-sharded evaluation (every rank takes part)
         line["configs"]["beam128"] = bench_beam128(args, L, torch, dist, D, rank, local_rank, world, world == 1 and not args.no_cpu_baseline)
+        line["configs"]["replay"] = bench_replay(args, L, torch, dist, D, rank, local_rank, world)
 
     if rank != 0:
         if world > 1:
@@ -602,6 +668,7 @@ def main_ours(args):
             pl["cpu_baseline"] = cpu_pair_latency(*pair)
         line["configs"]["pair_latency"] = pl
         line["configs"]["pgo"] = bench_pgo(L, not args.no_cpu_baseline)
+        line["configs"]["pgo_50k"] = bench_pgo_50k(L)
 
     if world == 1 and not args.no_cpu_baseline:
         o, threads = oracle_for(args.variant)
