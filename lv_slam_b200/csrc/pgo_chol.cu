@@ -1,5 +1,6 @@
 // Supernodal multifrontal block Cholesky for the pose-graph normal equations (see pgo_chol.cuh for what it replaces).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include "ndt_internal.cuh"
@@ -242,17 +243,42 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
 // =====================================================================================================================
 constexpr int kCholThreads = 256;
 constexpr int kCholMaxTeam = 1024;      // CTAs that may share one front (bounded by the cooperative grid)
-constexpr int kCholBigFront = 192;    // fronts with F above this go to the team kernel
-constexpr int kNB = 24;                 // pivot columns per panel of the backward substitution and of the single-CTA front kernel
-constexpr int kNBTeam = 24;             // pivot columns per panel of the team front kernel (48 was measured: 6.2 -> 7.1 ms per solve,
-                                        // the diagonal block and the row solve grow faster than the barriers shrink)
+constexpr int kCholBigFront = 192;      // fronts with F above this go to the team kernel
+constexpr int kNB = 24;                 // pivot columns per panel of the backward substitution
 constexpr int kCholSmemFront = 64;      // fronts up to this many rows are factored in shared memory (single-CTA kernel)
-constexpr int kTile = 96;               // trailing-update tile (16 x 16 threads, 6 x 6 outputs each)
+constexpr int kMB = 16;                 // micro block: factored and inverted by one warp in registers
+constexpr int kSlab = 64;               // rows of one row-solve work item
+
+// Partial dense Cholesky of a front, per kernel variant.  Panels are WIDE (96 pivot columns for the team kernel): a panel costs two
+// team barriers and one pass over the trailing matrix whatever its width, and with 24-column panels those were most of a front's time
+// (48 panels x (2 x 4 us barriers + 5 us update) on the 1 159-row root).  What made wide panels slower before - a column-by-column
+// diagonal block with a CTA barrier per column and a row solve that is one dependent chain of nb^2 / 2 multiply-adds per row - is gone:
+//   (A) the diagonal block is factored in 16 x 16 micro blocks, each by ONE WARP in registers (a lane owns a row, columns travel by
+//       shuffle), which also inverts the micro block; between micro blocks the CTA applies it to the rest of the diagonal block;
+//   (B) the rows below are solved in slabs of 64 rows against the micro blocks: a block product with the columns already done plus a
+//       product with the 16 x 16 inverse - independent multiply-adds instead of a chain;
+//   (C) the trailing update runs on the tensor cores: mma.sync.m8n8k4.f64 (DMMA), operands staged in shared memory with a row
+//       stride = 4 (mod 16) doubles so that every fragment load is bank-conflict free.
 template <bool TEAM>
-struct FrontSmem {                      // dynamic shared memory of chol_front_kernel<TEAM>, in doubles
-  static constexpr int NB = TEAM ? kNBTeam : kNB;
-  static constexpr size_t doubles = 2 * NB * (NB + 1) + 2 * NB * (kTile + 2) + NB + (TEAM ? 0 : kCholSmemFront * kCholSmemFront);
+struct FrontCfg {
+  static constexpr int NB = TEAM ? 96 : 48;       // pivot columns per panel
+  static constexpr int TILE = TEAM ? 96 : 64;     // trailing-update tile (outputs per CTA pass: TILE x TILE)
+  static constexpr int LDL = TILE + 4;            // row stride of the staged panels: = 4 (mod 16)
+  static constexpr int LDD = NB + 1;              // row stride of the diagonal block
+  static constexpr int NMB = NB / kMB;
+  static constexpr int WM = 4, WN = 2;            // warp grid over a tile
+  static constexpr int TM = TILE / 8 / WM, TN = TILE / 8 / WN;   // m8n8 tiles per warp
+  static constexpr int XC = ((NB - kMB) * kMB + kCholThreads - 1) / kCholThreads;   // in-block row-solve outputs per thread
+  // dynamic shared memory, in doubles: phases A + B and phase C alias
+  static constexpr size_t oD = 0;
+  static constexpr size_t oW = oD + (size_t)NB * LDD;
+  static constexpr size_t oX = oW + (size_t)NMB * kMB * (kMB + 1);
+  static constexpr size_t phaseAB = oX + (size_t)NB * kSlab;
+  static constexpr size_t phaseC = 2 * (size_t)NB * LDL;
+  static constexpr size_t oFront = phaseAB > phaseC ? phaseAB : phaseC;
+  static constexpr size_t doubles = oFront + (TEAM ? 0 : (size_t)kCholSmemFront * kCholSmemFront);
   static constexpr size_t bytes = doubles * sizeof(double);
+  static_assert(TILE % (8 * WM) == 0 && TILE % (8 * WN) == 0 && LDL % 16 == 4 && NB % kMB == 0 && NB % 4 == 0, "tile shape");
 };
 
 struct CholView {
@@ -265,6 +291,7 @@ struct CholView {
   double* xp;
   int* fail_flag;
   int n, n_off;
+  long long* dbg;          // diagnostics (LVS_DEBUG_TIMING): per-phase SM clocks of rank 0 of the LAST front of a team launch, null otherwise
 };
 
 __global__ void __launch_bounds__(kCholThreads) chol_scatter_kernel(CholView V, const double* __restrict__ Hd, const double* __restrict__ Ho,
@@ -309,22 +336,66 @@ __device__ __forceinline__ void team_sync(unsigned int* bar, unsigned int& targe
   __syncthreads();
 }
 
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// One warp: Cholesky of the 16 x 16 block at S (row stride ld, lower triangle; the strict upper part is ignored) and its inverse.
+// Lane l (and l + 16, redundantly: every shuffle source is a lane below 16) owns row l & 15.  Writes L over the lower triangle of S and
+// W = L^-1 (lower) to Wout[16][17].  A non-positive pivot raises *fail_flag and is replaced by 1.
+__device__ __forceinline__ void micro_factor_invert(double* S, int ld, double* Wout, int* fail_flag) {
+  const int lane = threadIdx.x & 31, row = lane & 15;
+  double s[kMB], il[kMB];
+#pragma unroll
+  for (int k = 0; k < kMB; k++) s[k] = (k <= row) ? S[row * ld + k] : 0.0;
+#pragma unroll
+  for (int j = 0; j < kMB; j++) {
+    double d = __shfl_sync(0xffffffffu, s[j], j);
+    if (!(d > 0.0)) { *fail_flag = 1; d = 1.0; }
+    il[j] = rsqrt(d);
+    const double lij = (row == j) ? d * il[j] : s[j] * il[j];          // rows above j hold 0 there
+    s[j] = lij;
+#pragma unroll
+    for (int k = j + 1; k < kMB; k++) {
+      const double lkj = __shfl_sync(0xffffffffu, lij, k);
+      s[k] -= lij * lkj;                                               // meaningful for row >= k; the rest is never read
+    }
+  }
+  // column `row` of W = L^-1 by forward substitution: W[i][c] = (delta_ic - sum_{k < i} L[i][k] W[k][c]) / L[i][i]
+  double w[kMB];
+#pragma unroll
+  for (int i = 0; i < kMB; i++) {
+    double acc = (i == row) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; k++) acc -= __shfl_sync(0xffffffffu, s[k], i) * w[k];
+    w[i] = acc * il[i];
+  }
+  if (lane < kMB) {
+#pragma unroll
+    for (int k = 0; k < kMB; k++) {
+      if (k <= row) S[row * ld + k] = s[k];
+      Wout[k * (kMB + 1) + row] = (k >= row) ? w[k] : 0.0;             // W[k][row]
+    }
+  }
+}
+
 template <bool TEAM>
 __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(CholView V, const int* __restrict__ list, int n_list, int team_size,
                                                                   unsigned int* __restrict__ bars) {
+  using Cfg = FrontCfg<TEAM>;
+  constexpr int NB = Cfg::NB, TILE = Cfg::TILE, LDL = Cfg::LDL, LDD = Cfg::LDD;
   const int team = blockIdx.x / team_size, rank = blockIdx.x % team_size, n_teams = gridDim.x / team_size;
   const int tid = rank * kCholThreads + threadIdx.x, nthr = team_size * kCholThreads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int* bar = bars + team;
   unsigned int target = 0;
-  // Panel width per kernel variant; all staging lives in dynamic shared memory (FrontSmem<TEAM>).
-  constexpr int kNB = FrontSmem<TEAM>::NB;
   extern __shared__ double s_dyn[];
-  double (*s_D)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(s_dyn);
-  double (*s_S)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(s_dyn + kNB * (kNB + 1));
-  double (*s_Li)[kTile + 2] = reinterpret_cast<double (*)[kTile + 2]>(s_dyn + 2 * kNB * (kNB + 1));
-  double (*s_Lj)[kTile + 2] = reinterpret_cast<double (*)[kTile + 2]>(s_dyn + 2 * kNB * (kNB + 1) + kNB * (kTile + 2));
-  double* s_inv = s_dyn + 2 * kNB * (kNB + 1) + 2 * kNB * (kTile + 2);
-  double* s_front = s_inv + kNB;                  // single-CTA launches only: room for a front of kCholSmemFront rows
+  double* s_D = s_dyn + Cfg::oD;                  // [NB][LDD] diagonal block of the panel: Schur complement, then its factor
+  double* s_W = s_dyn + Cfg::oW;                  // [NMB][16][17] inverses of the diagonal micro blocks
+  double* s_X = s_dyn + Cfg::oX;                  // [NB][kSlab] one slab of rows below the panel, column-major
+  double* s_Li = s_dyn;                           // phase C (aliases A / B): [NB][LDL] panel rows of the tile's row range
+  double* s_Lj = s_dyn + (size_t)NB * LDL;        //                          and of its column range
+  double* s_front = s_dyn + Cfg::oFront;          // single-CTA launches only: room for a front of kCholSmemFront rows
   for (int fi = team; fi < n_list; fi += n_teams) {
     const CholFront f = V.fronts[list[fi]];
     double* const A_global = V.arena + f.off;
@@ -371,148 +442,236 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
       }
       team_sync<TEAM>(bar, target, team_size);     // children are added one after the other: fixed summation order
     }
-    // ---- partial Cholesky of the p = 6 w pivot columns, right-looking in panels of kNB columns.  The right-hand side is simply
-    // the last row (F - 1) of the front.  Per panel: (A) the diagonal block is factored in shared memory by warp 0 of EVERY CTA of
-    // the team (same arithmetic, same result: no barrier needed before B), (B) the rows below are solved against it, one thread per
-    // row, (C) the trailing matrix gets the rank-nb update in 96 x 96 tiles staged through shared memory.
+    // ---- partial Cholesky of the p = 6 w pivot columns, right-looking in panels of NB columns.  The right-hand side is simply
+    // the last row (F - 1) of the front.
     const int p = 6 * f.w;
-    for (int c = 0; c < p; c += kNB) {
-      const int nb = min(kNB, p - c);
-      // rows of (B) are fetched first so that their latency hides behind (A)
-      int i = c + nb + tid;
-      double x[kNB];
-      if (i < F) {
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tl = clock64();
+    const bool dbg = TEAM && V.dbg != nullptr && rank == 0 && threadIdx.x == 0;
+#define LVS_PH(k) if (dbg) { const long long tn = clock64(); tph[k] += tn - tl; tl = tn; }
+    for (int c = 0; c < p; c += NB) {
+      const int nb = min(NB, p - c);
+      const int nmb = (nb + kMB - 1) / kMB;
+      LVS_PH(5)
+      // (A) diagonal block, by EVERY CTA of the team (same arithmetic, same result: no barrier needed before B).  Rows / columns past
+      // nb are padded with the identity.
+      // (every global load of the staging loops below is unconditional, from a clamped address, and a whole group of them is issued
+      // before the first use: with predicated loads the compiler sinks each one next to its store and only one is in flight at a time)
+      {
+        constexpr int kG = TEAM ? 12 : 9;
+        static_assert((NB * NB) % (kG * kCholThreads) == 0, "diagonal block staging");
+        for (int t0 = threadIdx.x; t0 < NB * NB; t0 += kG * kCholThreads) {
+          double v[kG];
 #pragma unroll
-        for (int j = 0; j < kNB; j++) x[j] = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + i);
-      }
-      // (A) diagonal block, all threads, one barrier per column: s_S holds the running Schur complement, column j of the factor is
-      // written to s_D while the columns right of j take its rank-1 update (reads column j of s_S, writes columns > j: no conflict)
-      for (int t = threadIdx.x; t < kNB * kNB; t += kCholThreads) {
-        const int j = t / kNB, i = t % kNB;
-        const double v = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1));
-        s_S[i][j] = (i < nb && j <= i) ? v : (i == j ? 1.0 : 0.0);
-        s_D[i][j] = 0.0;
+          for (int u = 0; u < kG; u++) {
+            const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
+            v[u] = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1));
+          }
+#pragma unroll
+          for (int u = 0; u < kG; u++) {
+            const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
+            s_D[i * LDD + j] = (i < nb && j <= i) ? v[u] : (i == j ? 1.0 : 0.0);
+          }
+        }
       }
       __syncthreads();
-      {
-        // the lower-triangle elements this thread owns, fixed for the whole panel
-        constexpr int kOwn = (kNB * kNB + kCholThreads - 1) / kCholThreads;
-        int ei[kOwn], ek[kOwn];
+      for (int mb = 0; mb < nmb; mb++) {
+        const int m0 = kMB * mb;
+        if (warp == 0) micro_factor_invert(s_D + m0 * LDD + m0, LDD, s_W + mb * kMB * (kMB + 1), V.fail_flag);
+        __syncthreads();
+        const int rows = nb - (m0 + kMB);          // rows of the diagonal block below this micro block
+        if (rows > 0) {
+          // X = S[rows][m0 .. m0+15] * W^T, staged in registers (other threads still read the old columns)
+          const double* W = s_W + mb * kMB * (kMB + 1);
+          double xv[Cfg::XC];
 #pragma unroll
-        for (int u = 0; u < kOwn; u++) {
-          const int t = threadIdx.x + u * kCholThreads;
-          ei[u] = t / kNB; ek[u] = t % kNB;
-          if (!(t < kNB * kNB && ei[u] < nb && ek[u] <= ei[u])) { ei[u] = -1; ek[u] = kNB; }     // inactive: i = -1 fails every test below
-        }
-        for (int j = 0; j < nb; j++) {
-          bool busy = false;
+          for (int u = 0; u < Cfg::XC; u++) {
+            const int t = threadIdx.x + u * kCholThreads;
+            xv[u] = 0.0;
+            if (t < rows * kMB) {
+              const int i = m0 + kMB + t % rows, q = t / rows;
+              double acc = 0.0;
 #pragma unroll
-          for (int u = 0; u < kOwn; u++) busy |= ei[u] >= j;
-          if (busy) {                                                                                 // rows above j are finished
-            double d = s_S[j][j];
-            if (!(d > 0.0)) { *V.fail_flag = 1; d = 1.0; }     // every thread that sees it stores the same 1
-            const double il = rsqrt(d);                // one reciprocal square root instead of sqrt + divide on the serial path
+              for (int k = 0; k < kMB; k++) acc += (k <= q) ? s_D[i * LDD + m0 + k] * W[q * (kMB + 1) + k] : 0.0;
+              xv[u] = acc;
+            }
+          }
+          __syncthreads();
 #pragma unroll
-            for (int u = 0; u < kOwn; u++) {
-              const int i = ei[u], k = ek[u];
-              if (i < j) continue;
-              if (k == j) { s_D[i][j] = (i == j) ? d * il : s_S[i][j] * il; if (i == j) s_inv[j] = il; }
-              else if (k > j) s_S[i][k] -= (s_S[i][j] * il) * (s_S[k][j] * il);
+          for (int u = 0; u < Cfg::XC; u++) {
+            const int t = threadIdx.x + u * kCholThreads;
+            if (t < rows * kMB) s_D[(m0 + kMB + t % rows) * LDD + m0 + t / rows] = xv[u];
+          }
+          __syncthreads();
+          // S[i][k] -= sum_q X[i][q] X[k][q] for the rest of the diagonal block, one 16-column strip after the other (lower part)
+          for (int k0 = m0 + kMB; k0 < nb; k0 += kMB) {
+            const int nr = nb - k0;
+            for (int t = threadIdx.x; t < nr * kMB; t += kCholThreads) {
+              const int i = k0 + t % nr, k = k0 + t / nr;
+              if (k < nb && k <= i) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < kMB; q++) acc += s_D[i * LDD + m0 + q] * s_D[k * LDD + m0 + q];
+                s_D[i * LDD + k] -= acc;
+              }
             }
           }
           __syncthreads();
         }
       }
-      // (B) rows below the diagonal block: x L_D^T = a, forward substitution along the row, right-looking: once x_m is final every
-      // later entry takes its term.  Each x_j still receives its terms in the order m = 0, 1, ... (the result does not change),
-      // but consecutive instructions are independent instead of one 276-long chain of dependent multiply-adds.
+      LVS_PH(0)
+      // (B) rows below the panel: X L_D^T = A, slab by slab.  In s_X the slab is column-major (a thread's row index runs along the
+      // lanes).  Micro column m: first the block product with the columns already solved, then the product with the inverse.
       {
-        for (; i < F; i += nthr) {
+        const int n_below = F - (c + nb);
+        const int n_slabs = (n_below + kSlab - 1) / kSlab;
+        for (int slab = rank; slab < n_slabs; slab += team_size) {
+          const int r0 = c + nb + slab * kSlab, nr = min(kSlab, F - r0);
+          {
+            constexpr int kG = 12;
+            static_assert((NB * kSlab) % (kG * kCholThreads) == 0, "slab staging");
+            for (int t0 = threadIdx.x; t0 < NB * kSlab; t0 += kG * kCholThreads) {
+              double v[kG];
 #pragma unroll
-          for (int m = 0; m < kNB; m++) {
-            if (m < nb) {
-              const double xm = x[m] * s_inv[m];
-              x[m] = xm;
-              A[(size_t)(c + m) * F + i] = xm;
+              for (int u = 0; u < kG; u++) {
+                const int t = t0 + u * kCholThreads, r = t % kSlab, q = t / kSlab;
+                v[u] = ldf<TEAM>(A + (size_t)(c + min(q, nb - 1)) * F + r0 + min(r, nr - 1));
+              }
 #pragma unroll
-              for (int j = m + 1; j < kNB; j++) x[j] -= xm * s_D[j][m];      // rows of s_D past nb are zero
+              for (int u = 0; u < kG; u++) {
+                const int t = t0 + u * kCholThreads, r = t % kSlab, q = t / kSlab;
+                s_X[q * kSlab + r] = (q < nb && r < nr) ? v[u] : 0.0;
+              }
             }
           }
-          if (i + nthr < F) {
+          __syncthreads();
+          const int r = threadIdx.x % kSlab, qg = threadIdx.x / kSlab;      // 4 threads per row, 4 columns of the micro block each
+          for (int mb = 0; mb < nmb; mb++) {
+            const int m0 = kMB * mb;
+            double acc[4];
 #pragma unroll
-            for (int j = 0; j < kNB; j++) x[j] = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + i + nthr);
+            for (int u = 0; u < 4; u++) acc[u] = s_X[(m0 + 4 * qg + u) * kSlab + r];
+            for (int q2 = 0; q2 < m0; q2++) {
+              const double xs = s_X[q2 * kSlab + r];
+#pragma unroll
+              for (int u = 0; u < 4; u++) acc[u] -= xs * s_D[(m0 + 4 * qg + u) * LDD + q2];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) s_X[(m0 + 4 * qg + u) * kSlab + r] = acc[u];      // own entries only
+            __syncthreads();
+            const double* W = s_W + mb * kMB * (kMB + 1);
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int q = 4 * qg + u;
+              double a2 = 0.0;
+#pragma unroll
+              for (int k = 0; k < kMB; k++) a2 += (k <= q) ? s_X[(m0 + k) * kSlab + r] * W[q * (kMB + 1) + k] : 0.0;
+              x[u] = a2;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 4; u++) s_X[(m0 + 4 * qg + u) * kSlab + r] = x[u];
+            __syncthreads();
           }
+          for (int t = threadIdx.x; t < nb * kSlab; t += kCholThreads) {
+            const int r2 = t % kSlab, q = t / kSlab;
+            if (r2 < nr) A[(size_t)(c + q) * F + r0 + r2] = s_X[q * kSlab + r2];
+          }
+          __syncthreads();
         }
       }
+      LVS_PH(1)
       team_sync<TEAM>(bar, target, team_size);
+      LVS_PH(2)
       // the factored diagonal block goes back to the front only now: before the barrier other CTAs may still be reading the
       // unfactored block for their own copy of (A); nothing in (C) touches it
       if (rank == 0)
         for (int t = threadIdx.x; t < nb * nb; t += kCholThreads) {
           const int j = t / nb, i = t % nb;
-          if (i >= j) A[(size_t)(c + j) * F + c + i] = s_D[i][j];
+          if (i >= j) A[(size_t)(c + j) * F + c + i] = s_D[i * LDD + j];
         }
-      // (C) A[i, j] -= sum_q L[i, c+q] L[j, c+q] for c + nb <= j <= i (lower triangle, plus the upper part of diagonal 6x6 blocks)
+      __syncthreads();                            // s_D / s_X are dead from here on: phase C reuses the memory
+      // (C) A[i, j] -= sum_q L[i, c+q] L[j, c+q] for c + nb <= j <= i (block-lower part), TILE x TILE outputs per pass on the tensor
+      // cores.  Warp (wm, wn) of the 4 x 2 grid owns TM x TN m8n8 tiles; per k-step of 4 it loads TM + TN fragments for TM * TN DMMAs.
       const int base = c + nb, rem = F - base;
-      const int nt = (rem + kTile - 1) / kTile;
+      const int nt = (rem + TILE - 1) / TILE;
       const int ntiles = nt * (nt + 1) / 2;
-      const int ty = threadIdx.x % 16, tx = threadIdx.x / 16;
+      const int nbk = (nb + 3) & ~3;
+      const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
       for (int tile = rank; tile < ntiles; tile += team_size) {
         int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
         while (ti * (ti + 1) / 2 > tile) ti--;
         while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
         const int tj = tile - ti * (ti + 1) / 2;
-        const int i0 = base + kTile * ti, j0 = base + kTile * tj;
+        const int i0 = base + TILE * ti, j0 = base + TILE * tj;
         {
-          constexpr int kLd = kNB * kTile / kCholThreads;      // 9 elements of each panel per thread
-          double vi[kLd], vj[kLd];
+          constexpr int kG = 6;
+          static_assert((NB * TILE) % (kG * kCholThreads) == 0, "panel staging");
+          for (int t0 = threadIdx.x; t0 < nbk * TILE; t0 += kG * kCholThreads) {
+            double vi[kG], vj[kG];
 #pragma unroll
-          for (int u = 0; u < kLd; u++) {                      // unconditional loads from clamped addresses, all in flight together
-            const int t = threadIdx.x + u * kCholThreads, q = min(t / kTile, nb - 1), r = t % kTile;
-            vi[u] = ldf<TEAM>(A + (size_t)(c + q) * F + min(i0 + r, F - 1));
-            vj[u] = ldf<TEAM>(A + (size_t)(c + q) * F + min(j0 + r, F - 1));
-          }
+            for (int u = 0; u < kG; u++) {
+              const int t = t0 + u * kCholThreads, r = t % TILE, q = min(t / TILE, nb - 1);
+              vi[u] = ldf<TEAM>(A + (size_t)(c + q) * F + min(i0 + r, F - 1));
+              vj[u] = ldf<TEAM>(A + (size_t)(c + q) * F + min(j0 + r, F - 1));
+            }
 #pragma unroll
-          for (int u = 0; u < kLd; u++) {
-            const int t = threadIdx.x + u * kCholThreads, q = t / kTile, r = t % kTile;
-            const int rp = r + (r >= 48 ? 2 : 0);
-            s_Li[q][rp] = (q < nb && i0 + r < F) ? vi[u] : 0.0;
-            s_Lj[q][rp] = (q < nb && j0 + r < F) ? vj[u] : 0.0;
+            for (int u = 0; u < kG; u++) {
+              const int t = t0 + u * kCholThreads, r = t % TILE, q = t / TILE;
+              if (q < nbk) {
+                s_Li[q * LDL + r] = (q < nb && i0 + r < F) ? vi[u] : 0.0;
+                s_Lj[q * LDL + r] = (q < nb && j0 + r < F) ? vj[u] : 0.0;
+              }
+            }
           }
         }
         __syncthreads();
-        double acc[6][6];
+        double acc[Cfg::TM][Cfg::TN][2];
 #pragma unroll
-        for (int a = 0; a < 6; a++)
+        for (int a = 0; a < Cfg::TM; a++)
 #pragma unroll
-          for (int b2 = 0; b2 < 6; b2++) acc[a][b2] = 0.0;
-        const int ro = 6 * ty + (ty >= 8 ? 2 : 0), co = 6 * tx + (tx >= 8 ? 2 : 0);
-        for (int q = 0; q < nb; q++) {
-          double li[6], lj[6];
+          for (int b2 = 0; b2 < Cfg::TN; b2++) acc[a][b2][0] = acc[a][b2][1] = 0.0;
+        const double* pa = s_Li + (lane & 3) * LDL + 8 * (wm * Cfg::TM) + (lane >> 2);
+        const double* pb = s_Lj + (lane & 3) * LDL + 8 * (wn * Cfg::TN) + (lane >> 2);
+        for (int k0 = 0; k0 < nbk; k0 += 4) {
+          double fa[Cfg::TM], fb[Cfg::TN];
 #pragma unroll
-          for (int a = 0; a < 6; a++) { li[a] = s_Li[q][ro + a]; lj[a] = s_Lj[q][co + a]; }
+          for (int a = 0; a < Cfg::TM; a++) fa[a] = pa[k0 * LDL + 8 * a];
 #pragma unroll
-          for (int a = 0; a < 6; a++)
+          for (int b2 = 0; b2 < Cfg::TN; b2++) fb[b2] = pb[k0 * LDL + 8 * b2];
 #pragma unroll
-            for (int b2 = 0; b2 < 6; b2++) acc[a][b2] += li[a] * lj[b2];
+          for (int a = 0; a < Cfg::TM; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < Cfg::TN; b2++) dmma884(acc[a][b2][0], acc[a][b2][1], fa[a], fb[b2]);
         }
-        const int ib = i0 + 6 * ty, jb = j0 + 6 * tx;
-        if (ib >= jb) {                       // 6x6 sub-tiles are aligned to the 6x6 blocks of the front: keep lower and diagonal ones
-          // all 36 loads first, then the stores (a load cannot be moved above an earlier store into the same array)
+        // a lane holds C[8 a + lane / 4][8 b + 2 (lane % 4) + e]; keep the block-lower part (6 x 6 blocks), all loads before the stores
 #pragma unroll
-          for (int b2 = 0; b2 < 6; b2++)
+        for (int a = 0; a < Cfg::TM; a++)
 #pragma unroll
-            for (int a = 0; a < 6; a++) acc[a][b2] = ldf<TEAM>(A + (size_t)min(jb + b2, F - 2) * F + min(ib + a, F - 1)) - acc[a][b2];
+          for (int b2 = 0; b2 < Cfg::TN; b2++)
 #pragma unroll
-          for (int b2 = 0; b2 < 6; b2++)
+            for (int e = 0; e < 2; e++) {
+              const int gi = i0 + 8 * (wm * Cfg::TM + a) + (lane >> 2), gj = j0 + 8 * (wn * Cfg::TN + b2) + 2 * (lane & 3) + e;
+              const bool live = gi < F && gj < F - 1 && gi / 6 >= gj / 6;
+              acc[a][b2][e] = live ? ldf<TEAM>(A + (size_t)gj * F + gi) - acc[a][b2][e] : 0.0;
+            }
 #pragma unroll
-            for (int a = 0; a < 6; a++)
-              if (jb + b2 < F - 1 && ib + a < F) A[(size_t)(jb + b2) * F + ib + a] = acc[a][b2];
-        }
+        for (int a = 0; a < Cfg::TM; a++)
+#pragma unroll
+          for (int b2 = 0; b2 < Cfg::TN; b2++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int gi = i0 + 8 * (wm * Cfg::TM + a) + (lane >> 2), gj = j0 + 8 * (wn * Cfg::TN + b2) + 2 * (lane & 3) + e;
+              if (gi < F && gj < F - 1 && gi / 6 >= gj / 6) A[(size_t)gj * F + gi] = acc[a][b2][e];
+            }
         __syncthreads();
       }
+      LVS_PH(3)
       team_sync<TEAM>(bar, target, team_size);
+      LVS_PH(4)
     }
+    if (dbg) { for (int k = 0; k < 6; k++) V.dbg[k] = tph[k]; V.dbg[6] = F; V.dbg[7] = team_size; }
+#undef LVS_PH
     if (in_smem) {
       for (int t = threadIdx.x; t < F * F; t += kCholThreads) A_global[t] = s_front[t];
       __syncthreads();                             // the next front of this CTA reuses the buffer
@@ -656,8 +815,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     int per_sm = 0, dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontSmem<true>::bytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_front_kernel<true>, kCholThreads, FrontSmem<true>::bytes));
+    CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontCfg<true>::bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_front_kernel<true>, kCholThreads, FrontCfg<true>::bytes));
     C.coop_grid = std::max(1, std::min(per_sm, 2) * sms);
     CUDA_TRY(cudaMalloc((void**)&C.bars, (size_t)C.coop_grid * sizeof(unsigned int)));
     C.allocs.push_back((void*)C.bars);
@@ -670,9 +829,13 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
   C.allocs.push_back((void*)C.xp);
   CUDA_TRY(cudaMalloc((void**)&C.fail_flag, sizeof(int)));
   C.allocs.push_back((void*)C.fail_flag);
+  if (getenv("LVS_DEBUG_TIMING")) {
+    CUDA_TRY(cudaMallocManaged((void**)&C.dbg, 8 * sizeof(long long)));
+    C.allocs.push_back((void*)C.dbg);
+  }
   const size_t smem = (size_t)S.max_front * sizeof(double);
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontSmem<false>::bytes));
+  CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontCfg<false>::bytes));
   CUDA_TRY(cudaStreamSynchronize(st));    // the host vectors of S may go away
   return LVS_OK;
 }
@@ -688,6 +851,7 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   V.fronts = C.fronts; V.rows = C.rows; V.rel = C.rel; V.child_idx = C.child_idx; V.level_fronts = C.level_fronts; V.perm = C.perm;
   V.diag_dst = C.diag_dst; V.off_dst = C.off_dst; V.rhs_dst = C.rhs_dst; V.diag_ld = C.diag_ld; V.off_ld = C.off_ld; V.off_tr = C.off_tr;
   V.arena = C.arena; V.xp = C.xp; V.fail_flag = C.fail_flag; V.n = C.n; V.n_off = C.n_off;
+  V.dbg = C.dbg;
   CUDA_TRY(cudaMemsetAsync(C.arena, 0, (size_t)C.arena_doubles * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(C.fail_flag, 0, sizeof(int), st));
   const long long total = (long long)C.n * 36 + (long long)C.n_off * 36 + (long long)C.n * 6;
@@ -697,22 +861,22 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
     // small fronts: one CTA each; large fronts: teams of CTAs in one cooperative launch
     const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nb = C.big_ptr[l + 1] - C.big_ptr[l];
     if (ns > 0) {
-      chol_front_kernel<false><<<ns, kCholThreads, FrontSmem<false>::bytes, st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
+      chol_front_kernel<false><<<ns, kCholThreads, FrontCfg<false>::bytes, st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
       nl++;
     }
     if (nb > 0) {
       const int n_teams = std::min(nb, C.coop_grid);
       // no more CTAs per front than the largest front of the level has 96 x 96 tiles in its trailing update (fewer barrier parties)
-      const int nt = (C.level_big[l] + 95) / 96, tiles = nt * (nt + 1) / 2;
+      const int nt = (C.level_big[l] + FrontCfg<true>::TILE - 1) / FrontCfg<true>::TILE, tiles = std::max(nt * (nt + 1) / 2, (C.level_big[l] + kSlab - 1) / kSlab);
       int team_size = std::max(1, std::min(std::min(C.coop_grid / n_teams, kCholMaxTeam), tiles));
       int grid = n_teams * team_size;
       const int* list = C.big_list + C.big_ptr[l];
       int n_list = nb;
-      if (team_size == 1) chol_front_kernel<false><<<grid, kCholThreads, FrontSmem<false>::bytes, st>>>(V, list, n_list, 1, C.bars);
+      if (team_size == 1) chol_front_kernel<false><<<grid, kCholThreads, FrontCfg<false>::bytes, st>>>(V, list, n_list, 1, C.bars);
       else {
         CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)n_teams * sizeof(unsigned int), st));
         void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars};
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_front_kernel<true>, dim3(grid), dim3(kCholThreads), args, FrontSmem<true>::bytes, st));
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_front_kernel<true>, dim3(grid), dim3(kCholThreads), args, FrontCfg<true>::bytes, st));
       }
       nl++;
     }
@@ -726,6 +890,11 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   }
   chol_finish_kernel<<<1, 1024, 0, st>>>(V, b, lambda, x, scale_out, ok_out);
   nl++;
+  if (C.dbg) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[chol dbg] last team front F=%lld team=%lld: A %.1f us, B %.1f us, barrier1 %.1f us, writeback+C %.1f us, barrier2 %.1f us, other %.1f us\n", C.dbg[6], C.dbg[7],
+            C.dbg[0] / 1965.0, C.dbg[1] / 1965.0, C.dbg[2] / 1965.0, C.dbg[3] / 1965.0, C.dbg[4] / 1965.0, C.dbg[5] / 1965.0);
+  }
   CUDA_TRY(cudaGetLastError());
   if (launches) *launches += nl;
   return LVS_OK;

@@ -56,6 +56,7 @@ struct CholDevice {
   double* arena = nullptr;
   double* xp = nullptr;                    // solution in permuted order [6 n]
   int* fail_flag = nullptr;                // set when a pivot is not positive (the matrix is not SPD)
+  long long* dbg = nullptr;                // LVS_DEBUG_TIMING: phase clocks of the last team front (diagnostics)
   long long arena_doubles = 0;
   std::vector<int> level_ptr;              // host copy
   std::vector<int> level_big;              // host: widest front of each level
