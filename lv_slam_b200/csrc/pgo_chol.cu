@@ -247,7 +247,8 @@ constexpr int kCholBigFront = 192;      // fronts with F above this go to the te
 constexpr int kNB = 24;                 // pivot columns per panel of the backward substitution
 constexpr int kCholSmemFront = 64;      // fronts up to this many rows are factored in shared memory (single-CTA kernel)
 constexpr int kMB = 16;                 // micro block: factored and inverted by one warp in registers
-constexpr int kSlab = 64;               // rows of one row-solve work item
+constexpr int kSlab = 32;               // rows of one row-solve work item (8 threads per row, 2 columns of a micro block each)
+constexpr int kSlabCols = kMB * kSlab / kCholThreads;
 
 // Partial dense Cholesky of a front, per kernel variant.  Panels are WIDE (96 pivot columns for the team kernel): a panel costs two
 // team barriers and one pass over the trailing matrix whatever its width, and with 24-column panels those were most of a front's time
@@ -272,7 +273,8 @@ struct FrontCfg {
   // dynamic shared memory, in doubles: phases A + B and phase C alias
   static constexpr size_t oD = 0;
   static constexpr size_t oW = oD + (size_t)NB * LDD;
-  static constexpr size_t oX = oW + (size_t)NMB * kMB * (kMB + 1);
+  static constexpr size_t oIl = oW + (size_t)NMB * kMB * (kMB + 1);
+  static constexpr size_t oX = oIl + NB;
   static constexpr size_t phaseAB = oX + (size_t)NB * kSlab;
   static constexpr size_t phaseC = 2 * (size_t)NB * LDL;
   static constexpr size_t oFront = phaseAB > phaseC ? phaseAB : phaseC;
@@ -336,33 +338,63 @@ __device__ __forceinline__ void team_sync(unsigned int* bar, unsigned int& targe
   __syncthreads();
 }
 
+// 8-byte asynchronous copy global -> shared; n_src = 0 writes zeros instead (out-of-range rows / columns of a tile)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src, int n_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(n_src) : "memory");
+}
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// One warp: Cholesky of the 16 x 16 block at S (row stride ld, lower triangle; the strict upper part is ignored) and its inverse.
-// Lane l (and l + 16, redundantly: every shuffle source is a lane below 16) owns row l & 15.  Writes L over the lower triangle of S and
-// W = L^-1 (lower) to Wout[16][17].  A non-positive pivot raises *fail_flag and is replaced by 1.
-__device__ __forceinline__ void micro_factor_invert(double* S, int ld, double* Wout, int* fail_flag) {
+// 1 / sqrt(d) for the pivot of a column: the hardware approximation (about 28 bits) and one Newton step - half the dependent latency of
+// the library routine, on the serial path of every pivot column.  The pivot itself is stored as d * il, the column as S * il.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d * y;                 // Newton: y <- y (1.5 - 0.5 d y^2), twice: 28 -> 56 -> full
+  y = fma(y, fma(-h, y, 0.5), y);
+  const double h2 = 0.5 * d * y;
+  return fma(y, fma(-h2, y, 0.5), y);
+}
+
+// One warp: Cholesky of the 16 x 16 block at S (row stride ld, lower triangle; the strict upper part is ignored).  Lane l (and l + 16,
+// redundantly: every shuffle source is a lane below 16) owns row l & 15.  Writes L over the lower triangle of S and the reciprocals of
+// its diagonal to il_out[16].  A non-positive pivot raises *fail_flag and is replaced by 1.
+__device__ __forceinline__ void micro_factor(double* S, int ld, double* il_out, int* fail_flag) {
   const int lane = threadIdx.x & 31, row = lane & 15;
-  double s[kMB], il[kMB];
+  double s[kMB];
 #pragma unroll
   for (int k = 0; k < kMB; k++) s[k] = (k <= row) ? S[row * ld + k] : 0.0;
 #pragma unroll
   for (int j = 0; j < kMB; j++) {
     double d = __shfl_sync(0xffffffffu, s[j], j);
     if (!(d > 0.0)) { *fail_flag = 1; d = 1.0; }
-    il[j] = rsqrt(d);
-    const double lij = (row == j) ? d * il[j] : s[j] * il[j];          // rows above j hold 0 there
+    const double il = fast_rsqrt(d);
+    const double lij = (row == j) ? d * il : s[j] * il;                // rows above j hold 0 there
     s[j] = lij;
+    if (lane == j) il_out[j] = il;
 #pragma unroll
     for (int k = j + 1; k < kMB; k++) {
       const double lkj = __shfl_sync(0xffffffffu, lij, k);
       s[k] -= lij * lkj;                                               // meaningful for row >= k; the rest is never read
     }
   }
-  // column `row` of W = L^-1 by forward substitution: W[i][c] = (delta_ic - sum_{k < i} L[i][k] W[k][c]) / L[i][i]
-  double w[kMB];
+  if (lane < kMB) {
+#pragma unroll
+    for (int k = 0; k < kMB; k++)
+      if (k <= row) S[row * ld + k] = s[k];
+  }
+}
+
+// One warp: W = L^-1 (lower) of the factored 16 x 16 block at S, to Wout[16][17].  Lane c (& 15) computes column c by forward
+// substitution, W[i][c] = (delta_ic - sum_{k < i} L[i][k] W[k][c]) / L[i][i]; row i of L travels by shuffle from lane i.
+__device__ __forceinline__ void micro_invert(const double* S, int ld, const double* il, double* Wout) {
+  const int lane = threadIdx.x & 31, row = lane & 15;
+  double s[kMB], w[kMB];
+#pragma unroll
+  for (int k = 0; k < kMB; k++) s[k] = (k <= row) ? S[row * ld + k] : 0.0;
 #pragma unroll
   for (int i = 0; i < kMB; i++) {
     double acc = (i == row) ? 1.0 : 0.0;
@@ -372,10 +404,7 @@ __device__ __forceinline__ void micro_factor_invert(double* S, int ld, double* W
   }
   if (lane < kMB) {
 #pragma unroll
-    for (int k = 0; k < kMB; k++) {
-      if (k <= row) S[row * ld + k] = s[k];
-      Wout[k * (kMB + 1) + row] = (k >= row) ? w[k] : 0.0;             // W[k][row]
-    }
+    for (int k = 0; k < kMB; k++) Wout[k * (kMB + 1) + row] = (k >= row) ? w[k] : 0.0;    // W[k][row]
   }
 }
 
@@ -392,6 +421,7 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
   extern __shared__ double s_dyn[];
   double* s_D = s_dyn + Cfg::oD;                  // [NB][LDD] diagonal block of the panel: Schur complement, then its factor
   double* s_W = s_dyn + Cfg::oW;                  // [NMB][16][17] inverses of the diagonal micro blocks
+  double* s_il = s_dyn + Cfg::oIl;                // [NB] reciprocals of the factor's diagonal
   double* s_X = s_dyn + Cfg::oX;                  // [NB][kSlab] one slab of rows below the panel, column-major
   double* s_Li = s_dyn;                           // phase C (aliases A / B): [NB][LDL] panel rows of the tile's row range
   double* s_Lj = s_dyn + (size_t)NB * LDL;        //                          and of its column range
@@ -476,30 +506,30 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
       __syncthreads();
       for (int mb = 0; mb < nmb; mb++) {
         const int m0 = kMB * mb;
-        if (warp == 0) micro_factor_invert(s_D + m0 * LDD + m0, LDD, s_W + mb * kMB * (kMB + 1), V.fail_flag);
+        if (warp == 0) micro_factor(s_D + m0 * LDD + m0, LDD, s_il + m0, V.fail_flag);
         __syncthreads();
         const int rows = nb - (m0 + kMB);          // rows of the diagonal block below this micro block
+        // the inverse (needed by phase B only) on warp 1, while warps 2.. solve the rows below by substitution against L itself:
+        // x_q = (s_q - sum_{k < q} x_k L[q][k]) / L[q][q], a thread per row, in place (a thread touches its own row only)
+        if (warp == 1) micro_invert(s_D + m0 * LDD + m0, LDD, s_il + m0, s_W + mb * kMB * (kMB + 1));
         if (rows > 0) {
-          // X = S[rows][m0 .. m0+15] * W^T, staged in registers (other threads still read the old columns)
-          const double* W = s_W + mb * kMB * (kMB + 1);
-          double xv[Cfg::XC];
+          const int tr = (int)threadIdx.x - 64;
+          if (tr >= 0 && tr < rows) {
+            double* xr = s_D + (m0 + kMB + tr) * LDD + m0;
+            const double* Lm = s_D + m0 * LDD + m0;
+            double x[kMB];
 #pragma unroll
-          for (int u = 0; u < Cfg::XC; u++) {
-            const int t = threadIdx.x + u * kCholThreads;
-            xv[u] = 0.0;
-            if (t < rows * kMB) {
-              const int i = m0 + kMB + t % rows, q = t / rows;
-              double acc = 0.0;
+            for (int q = 0; q < kMB; q++) x[q] = xr[q];
 #pragma unroll
-              for (int k = 0; k < kMB; k++) acc += (k <= q) ? s_D[i * LDD + m0 + k] * W[q * (kMB + 1) + k] : 0.0;
-              xv[u] = acc;
+            for (int q = 0; q < kMB; q++) {
+              double a0 = x[q], a1 = 0.0;
+#pragma unroll
+              for (int k = 0; k + 1 < q; k += 2) { a0 -= x[k] * Lm[q * LDD + k]; a1 -= x[k + 1] * Lm[q * LDD + k + 1]; }
+              if (q & 1) a0 -= x[q - 1] * Lm[q * LDD + q - 1];
+              x[q] = (a0 + a1) * s_il[m0 + q];
             }
-          }
-          __syncthreads();
 #pragma unroll
-          for (int u = 0; u < Cfg::XC; u++) {
-            const int t = threadIdx.x + u * kCholThreads;
-            if (t < rows * kMB) s_D[(m0 + kMB + t % rows) * LDD + m0 + t / rows] = xv[u];
+            for (int q = 0; q < kMB; q++) xr[q] = x[q];
           }
           __syncthreads();
           // S[i][k] -= sum_q X[i][q] X[k][q] for the rest of the diagonal block, one 16-column strip after the other (lower part)
@@ -527,7 +557,7 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
         for (int slab = rank; slab < n_slabs; slab += team_size) {
           const int r0 = c + nb + slab * kSlab, nr = min(kSlab, F - r0);
           {
-            constexpr int kG = 12;
+            constexpr int kG = (NB * kSlab / kCholThreads) % 12 == 0 ? 12 : 6;
             static_assert((NB * kSlab) % (kG * kCholThreads) == 0, "slab staging");
             for (int t0 = threadIdx.x; t0 < NB * kSlab; t0 += kG * kCholThreads) {
               double v[kG];
@@ -544,25 +574,32 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
             }
           }
           __syncthreads();
-          const int r = threadIdx.x % kSlab, qg = threadIdx.x / kSlab;      // 4 threads per row, 4 columns of the micro block each
+          const int r = threadIdx.x % kSlab, qg = threadIdx.x / kSlab;      // 8 threads per row, kSlabCols columns of the micro block each
           for (int mb = 0; mb < nmb; mb++) {
             const int m0 = kMB * mb;
-            double acc[4];
+            double acc[kSlabCols];
 #pragma unroll
-            for (int u = 0; u < 4; u++) acc[u] = s_X[(m0 + 4 * qg + u) * kSlab + r];
-            for (int q2 = 0; q2 < m0; q2++) {
-              const double xs = s_X[q2 * kSlab + r];
+            for (int u = 0; u < kSlabCols; u++) acc[u] = s_X[(m0 + kSlabCols * qg + u) * kSlab + r];
+            // two independent partial sums per output: the loop is a chain of dependent multiply-adds otherwise
+            double acc2[kSlabCols];
 #pragma unroll
-              for (int u = 0; u < 4; u++) acc[u] -= xs * s_D[(m0 + 4 * qg + u) * LDD + q2];
+            for (int u = 0; u < kSlabCols; u++) acc2[u] = 0.0;
+            for (int q2 = 0; q2 + 1 < m0; q2 += 2) {
+              const double xs0 = s_X[q2 * kSlab + r], xs1 = s_X[(q2 + 1) * kSlab + r];
+#pragma unroll
+              for (int u = 0; u < kSlabCols; u++) {
+                acc[u] -= xs0 * s_D[(m0 + kSlabCols * qg + u) * LDD + q2];
+                acc2[u] -= xs1 * s_D[(m0 + kSlabCols * qg + u) * LDD + q2 + 1];
+              }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) s_X[(m0 + 4 * qg + u) * kSlab + r] = acc[u];      // own entries only
+            for (int u = 0; u < kSlabCols; u++) s_X[(m0 + kSlabCols * qg + u) * kSlab + r] = acc[u] + acc2[u];      // own entries only
             __syncthreads();
             const double* W = s_W + mb * kMB * (kMB + 1);
-            double x[4];
+            double x[kSlabCols];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int q = 4 * qg + u;
+            for (int u = 0; u < kSlabCols; u++) {
+              const int q = kSlabCols * qg + u;
               double a2 = 0.0;
 #pragma unroll
               for (int k = 0; k < kMB; k++) a2 += (k <= q) ? s_X[(m0 + k) * kSlab + r] * W[q * (kMB + 1) + k] : 0.0;
@@ -570,7 +607,7 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
             }
             __syncthreads();
 #pragma unroll
-            for (int u = 0; u < 4; u++) s_X[(m0 + 4 * qg + u) * kSlab + r] = x[u];
+            for (int u = 0; u < kSlabCols; u++) s_X[(m0 + kSlabCols * qg + u) * kSlab + r] = x[u];
             __syncthreads();
           }
           for (int t = threadIdx.x; t < nb * kSlab; t += kCholThreads) {
@@ -604,26 +641,23 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
         while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
         const int tj = tile - ti * (ti + 1) / 2;
         const int i0 = base + TILE * ti, j0 = base + TILE * tj;
-        {
-          constexpr int kG = 6;
-          static_assert((NB * TILE) % (kG * kCholThreads) == 0, "panel staging");
-          for (int t0 = threadIdx.x; t0 < nbk * TILE; t0 += kG * kCholThreads) {
-            double vi[kG], vj[kG];
-#pragma unroll
-            for (int u = 0; u < kG; u++) {
-              const int t = t0 + u * kCholThreads, r = t % TILE, q = min(t / TILE, nb - 1);
-              vi[u] = ldf<TEAM>(A + (size_t)(c + q) * F + min(i0 + r, F - 1));
-              vj[u] = ldf<TEAM>(A + (size_t)(c + q) * F + min(j0 + r, F - 1));
-            }
-#pragma unroll
-            for (int u = 0; u < kG; u++) {
-              const int t = t0 + u * kCholThreads, r = t % TILE, q = t / TILE;
-              if (q < nbk) {
-                s_Li[q * LDL + r] = (q < nb && i0 + r < F) ? vi[u] : 0.0;
-                s_Lj[q * LDL + r] = (q < nb && j0 + r < F) ? vj[u] : 0.0;
-              }
-            }
+        // The two panels go to shared memory by cp.async (every copy of the tile in flight at once, no staging registers).  The lines
+        // land in L1 as well, which is safe in team mode although L1 is not coherent across SMs: panel columns are final when this
+        // phase starts (the barrier after (B)) and nothing else in the kernel reads the arena through L1.  A front held in shared memory
+        // (single-CTA kernel) is copied with plain loads.
+        if (in_smem) {
+          for (int t = threadIdx.x; t < nbk * TILE; t += kCholThreads) {
+            const int r = t % TILE, q = t / TILE;
+            s_Li[q * LDL + r] = (q < nb && i0 + r < F) ? A[(size_t)(c + q) * F + i0 + r] : 0.0;
+            s_Lj[q * LDL + r] = (q < nb && j0 + r < F) ? A[(size_t)(c + q) * F + j0 + r] : 0.0;
           }
+        } else {
+          for (int t = threadIdx.x; t < nbk * TILE; t += kCholThreads) {
+            const int r = t % TILE, q = t / TILE, qc = min(q, nb - 1);
+            cp_async8(s_Li + q * LDL + r, A + (size_t)(c + qc) * F + min(i0 + r, F - 1), (q < nb && i0 + r < F) ? 8 : 0);
+            cp_async8(s_Lj + q * LDL + r, A + (size_t)(c + qc) * F + min(j0 + r, F - 1), (q < nb && j0 + r < F) ? 8 : 0);
+          }
+          asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         double acc[Cfg::TM][Cfg::TN][2];
@@ -684,10 +718,10 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
 // contiguous in memory, with eight loads in flight); then, per panel, warp 0 solves the 24 x 24 triangle (lane m keeps the
 // running sum of its own row) and every earlier pivot takes the panel's contribution (right-looking: a thread streams the 24
 // entries of its own column).
-__global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V, int level_begin) {
+__global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V, const int* __restrict__ list) {
   extern __shared__ double s_dyn[];                 // xs[F - 1]: y, overwritten by x panel by panel, followed by x_R
   __shared__ double s_D[kNB][kNB + 1], s_dot[kNB];
-  const int s = V.level_fronts[level_begin + blockIdx.x];
+  const int s = list[blockIdx.x];
   const CholFront f = V.fronts[s];
   const double* __restrict__ A = V.arena + f.off;
   const int F = f.F, p = 6 * f.w, nr = 6 * f.r;
@@ -756,6 +790,117 @@ __global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V,
   for (int j = threadIdx.x; j < p; j += kCholThreads) V.xp[(size_t)f.c0 * 6 + j] = xs[j];
 }
 
+// Backward substitution of the LARGE fronts of a level by teams of CTAs (cooperative launch, like the forward kernel): one CTA needs
+// 4 ms for the 4 932 pivots of the 50 000-vertex graph's root - it streams the whole factor of the front through one SM.  Here every
+// CTA of the team holds the front's right-hand side / solution vector in shared memory; the panels are solved LEFT-looking from the
+// last one up: the product of the panel's block column with the part of the solution that is already known is split over the CTAs by
+// rows (coalesced: a column of the front is contiguous), the partial sums meet in global memory (one team barrier per panel, double
+// buffered), and every CTA adds them in the same fixed order and solves the 32 x 32 triangle itself - identical bits everywhere, no
+// broadcast needed.
+constexpr int kBNB = 32;
+__global__ void __launch_bounds__(kCholThreads, 1) chol_backward_team_kernel(CholView V, const int* __restrict__ list, int n_list, int team_size,
+                                                                             unsigned int* __restrict__ bars, double* __restrict__ scratch) {
+  extern __shared__ double s_dyn[];                 // xs[F - 1]
+  __shared__ double s_T[kBNB][kBNB + 1], s_rhs[kBNB];
+  const int team = blockIdx.x / team_size, rank = blockIdx.x % team_size, n_teams = gridDim.x / team_size;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kW = kCholThreads / 32;
+  unsigned int* bar = bars + team;
+  unsigned int target = 0;
+  double* xs = s_dyn;
+  double* part = scratch + (size_t)team * team_size * 2 * kBNB;      // [2 parity][team_size][kBNB]
+  for (int fi = team; fi < n_list; fi += n_teams) {
+    const CholFront f = V.fronts[list[fi]];
+    const double* __restrict__ A = V.arena + f.off;
+    const int F = f.F, p = 6 * f.w, nr = 6 * f.r;
+    for (int j = threadIdx.x; j < p; j += kCholThreads) xs[j] = __ldcg(A + (size_t)j * F + (F - 1));
+    for (int i = threadIdx.x; i < nr; i += kCholThreads) xs[p + i] = __ldcg(V.xp + (size_t)V.rows[f.rows_off + i / 6] * 6 + i % 6);
+    __syncthreads();
+    if (nr > 0) {
+      // y - B^T x_R: the team's warps share the pivot columns, the results travel through the front's own slice of xp
+      for (int j = rank * kW + warp; j < p; j += team_size * kW) {
+        const double* __restrict__ col = A + (size_t)j * F + p;
+        double acc = 0.0;
+        for (int i0 = lane; i0 < nr; i0 += 32 * 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = __ldcg(col + min(i0 + 32 * u, nr - 1));
+#pragma unroll
+          for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u; acc += (i < nr) ? v[u] * xs[p + i] : 0.0; }
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) V.xp[(size_t)f.c0 * 6 + j] = xs[j] - acc;
+      }
+      team_sync<true>(bar, target, team_size);
+      for (int j = threadIdx.x; j < p; j += kCholThreads) xs[j] = __ldcg(V.xp + (size_t)f.c0 * 6 + j);
+      __syncthreads();
+    }
+    const int n_panels = (p + kBNB - 1) / kBNB;
+    for (int pi = n_panels - 1; pi >= 0; pi--) {
+      const int c = pi * kBNB, nb = min(kBNB, p - c);
+      double* mine = part + ((size_t)(pi & 1) * team_size + rank) * kBNB;
+      // (a) partial[q] = sum over this CTA's rows i of L[i][c + q] xs[i], i in the part of (c + nb, p) it owns
+      const int later = p - (c + nb);
+      const int i_lo = c + nb + (int)((long long)later * rank / team_size), i_hi = c + nb + (int)((long long)later * (rank + 1) / team_size);
+      for (int q = warp; q < kBNB; q += kW) {
+        double acc = 0.0;
+        if (q < nb) {
+          const double* __restrict__ col = A + (size_t)(c + q) * F;
+          for (int i0 = i_lo + lane; i0 < i_hi; i0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(col + min(i0 + 32 * u, i_hi - 1));
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u; acc += (i < i_hi) ? v[u] * xs[i] : 0.0; }
+          }
+          for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0) mine[q] = acc;
+      }
+      // the panel's triangle, while the partial sums of the other CTAs arrive
+      for (int t = threadIdx.x; t < kBNB * kBNB; t += kCholThreads) {
+        const int j = t / kBNB, i = t % kBNB;
+        const double v = __ldcg(A + (size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1));
+        s_T[i][j] = (i < nb && j <= i) ? v : (i == j ? 1.0 : 0.0);
+      }
+      team_sync<true>(bar, target, team_size);
+      // (b) rhs = xs[panel] - sum of the partials, CTA by CTA in rank order
+      if (threadIdx.x < kBNB) {
+        const int q = threadIdx.x;
+        const double* src = part + (size_t)(pi & 1) * team_size * kBNB + q;
+        double ssum = 0.0;
+        for (int r0 = 0; r0 < team_size; r0 += 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (size_t)min(r0 + u, team_size - 1) * kBNB);
+#pragma unroll
+          for (int u = 0; u < 8; u++) ssum += (r0 + u < team_size) ? v[u] : 0.0;
+        }
+        s_rhs[q] = (q < nb) ? xs[c + q] - ssum : 0.0;
+      }
+      __syncthreads();
+      // (c) L_D^T x = rhs by warp 0: lane m accumulates its own row's sum as the x_i appear
+      if (warp == 0) {
+        const int m = lane;
+        const bool on = m < nb;
+        const double rhs = s_rhs[m];
+        const double inv = on ? 1.0 / s_T[m][m] : 0.0;
+        double acc = 0.0, mineX = 0.0;
+        for (int j = nb - 1; j >= 0; j--) {
+          const double xj = __shfl_sync(0xffffffffu, (rhs - acc) * inv, j);
+          if (m == j) mineX = xj;
+          if (m < j) acc += s_T[j][m] * xj;
+        }
+        if (on) xs[c + m] = mineX;
+      }
+      __syncthreads();
+    }
+    if (rank == 0)
+      for (int j = threadIdx.x; j < p; j += kCholThreads) V.xp[(size_t)f.c0 * 6 + j] = xs[j];
+    team_sync<true>(bar, target, team_size);       // xp of this front is complete before the team's next front (a descendant level never shares a launch)
+  }
+}
+
 // x (original numbering) from the permuted solution, and LM's gain-ratio denominator sum_j x_j (lambda x_j + b_j), one CTA.
 __global__ void __launch_bounds__(1024) chol_finish_kernel(CholView V, const double* __restrict__ b, double lambda, double* __restrict__ x,
                                                            double* __restrict__ scale_out, int* __restrict__ ok_out) {
@@ -820,6 +965,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     C.coop_grid = std::max(1, std::min(per_sm, 2) * sms);
     CUDA_TRY(cudaMalloc((void**)&C.bars, (size_t)C.coop_grid * sizeof(unsigned int)));
     C.allocs.push_back((void*)C.bars);
+    CUDA_TRY(cudaMalloc((void**)&C.back_scratch, (size_t)C.coop_grid * 2 * kBNB * sizeof(double)));
+    C.allocs.push_back((void*)C.back_scratch);
   }
   C.arena_doubles = S.arena;
   cudaError_t e = cudaMalloc((void**)&C.arena, std::max<long long>(1, S.arena) * sizeof(double));
@@ -834,7 +981,10 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     C.allocs.push_back((void*)C.dbg);
   }
   const size_t smem = (size_t)S.max_front * sizeof(double);
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) {
+    CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(chol_backward_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontCfg<false>::bytes));
   CUDA_TRY(cudaStreamSynchronize(st));    // the host vectors of S may go away
   return LVS_OK;
@@ -883,10 +1033,25 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   }
   const size_t smem = (size_t)C.max_front * sizeof(double);
   for (int l = C.n_levels - 1; l >= 0; l--) {
-    const int cnt = C.level_ptr[l + 1] - C.level_ptr[l];
-    if (cnt <= 0) continue;
-    chol_backward_kernel<<<cnt, kCholThreads, smem, st>>>(V, C.level_ptr[l]);
-    nl++;
+    const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nbig = C.big_ptr[l + 1] - C.big_ptr[l];
+    if (nbig > 0) {
+      const int n_teams = std::min(nbig, C.coop_grid);
+      int team_size = std::max(1, std::min(C.coop_grid / n_teams, (C.level_big[l] + 255) / 256));
+      const int* list = C.big_list + C.big_ptr[l];
+      int n_list = nbig;
+      if (team_size == 1) chol_backward_kernel<<<nbig, kCholThreads, smem, st>>>(V, list);
+      else {
+        int grid = n_teams * team_size;
+        CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)n_teams * sizeof(unsigned int), st));
+        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars, (void*)&C.back_scratch};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_backward_team_kernel, dim3(grid), dim3(kCholThreads), args, smem, st));
+      }
+      nl++;
+    }
+    if (ns > 0) {
+      chol_backward_kernel<<<ns, kCholThreads, smem, st>>>(V, C.small_list + C.small_ptr[l]);
+      nl++;
+    }
   }
   chol_finish_kernel<<<1, 1024, 0, st>>>(V, b, lambda, x, scale_out, ok_out);
   nl++;

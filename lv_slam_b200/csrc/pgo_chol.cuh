@@ -63,6 +63,7 @@ struct CholDevice {
   int *small_list = nullptr, *big_list = nullptr;      // fronts of every level split by size (device), with host offsets
   std::vector<int> small_ptr, big_ptr;
   unsigned int* bars = nullptr;            // team barrier counters
+  double* back_scratch = nullptr;          // partial sums of the team backward substitution: [coop_grid][2][32]
   int coop_grid = 0;                       // CTAs of a cooperative launch (all co-resident)
   std::vector<void*> allocs;
 };

@@ -224,3 +224,30 @@ def test_direct_solver_at_baseline_size():
     s0 = pg.optimize(100)
     s2 = pc.optimize(200)
     assert s0["iterations"] > 0 and abs(s0["chi2_after"] - s2["chi2_after"]) <= 1e-3 * s2["chi2_after"]
+
+
+@pytest.mark.skipif(not P.have_csparse(), reason="needs oracle/_ref/libcsparse_ref.so (the reference's vendored CSparse)")
+def test_config4_full_size_against_the_oracle_and_the_references_csparse():
+    """BASELINE config 4 at FULL size (5 000 vertices / 19 599 edges) against the CPU restatement of g2o's LM driving the reference's
+    own vendored CSparse (slow: the CPU run takes ~20 s).  One linear solve of the first linearisation at 1e-8 relative; then the
+    whole LM run: chi2 before / after and the optimised trajectory (vertex 0 anchored like the nodelet does) within 1e-6 m / 1e-7 rad.
+    Iteration counts are not compared (see the module docstring)."""
+    import lv_slam_b200 as L
+    g = G.sphere(100, 50, seed=7)
+    pg, o = _both(g)
+    gl, ol = pg.linearize(), o.linearize()
+    assert np.array_equal(gl["off"], ol["off"])
+    assert _rel(gl["Hd"], ol["Hd"]) < 1e-10 and _rel(gl["Ho"], ol["Ho"]) < 1e-10 and _rel(gl["b"], ol["b"]) < 1e-10
+    lam = 1e-5 * np.max(np.abs(np.einsum("nii->ni", ol["Hd"])))
+    gx, _ = pg.solve(lam, 0.0)
+    ok, ox, _ = o.solve(lam, P.SOLVER_CSPARSE)
+    assert ok and _rel(gx, ox) < 1e-8
+    sg = pg.optimize(1024)
+    so = o.optimize(1024, P.ALG_LM, P.SOLVER_CSPARSE)
+    assert sg["iterations"] > 0 and so["iterations"] > 0
+    assert abs(sg["chi2_before"] - so["chi2_before"]) <= 1e-9 * so["chi2_before"]
+    assert abs(sg["chi2_after"] - so["chi2_after"]) <= 1e-6 * so["chi2_after"]
+    dt, dr = _traj_diff(pg.poses(), o.poses())
+    print("config 4 full size: chi2 %.6f (gpu) %.6f (oracle + CSparse), trajectory difference %.2e m %.2e rad, iterations %d / %d" % (
+        sg["chi2_after"], so["chi2_after"], dt, dr, sg["iterations"], so["iterations"]))
+    assert dt <= 1e-6 and dr <= 1e-7
