@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   __shared__ unsigned long long s_etab[32];
   __shared__ int s_last;
   const long long t_entry = clock64();
+  pdl_wait();
   const int pair = blockIdx.x / L.blocks_per_pair, blk = blockIdx.x % L.blocks_per_pair;
   AlignState& S = L.d_states[pair];
   const int kind = S.eval_kind;
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const int bpp = L.blocks_per_pair;
   if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
   else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
+  pdl_trigger();
   eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last, t_entry);
 }
 
@@ -384,9 +386,7 @@ static int launch_eval_as(cudaStream_t st, const EvalLaunch& L) {
     CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel<MODE, PCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = dev;
   }
-  ndt_eval_kernel<MODE, PCA><<<L.n_pairs * L.blocks_per_pair, kEvalThreads, smem, st>>>(L);
-  CUDA_TRY(cudaGetLastError());
-  return LVS_OK;
+  return launch_pdl(ndt_eval_kernel<MODE, PCA>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, smem, st, L);
 }
 
 // The search mode and the registration variant are launch constants, so each combination is its own kernel (unrolled probe

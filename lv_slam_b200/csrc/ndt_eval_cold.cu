@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(kEvalThreads) ndt_eval_cold_kernel(EvalLaunch 
   __shared__ float s_T[16], s_R[9];
   __shared__ double s_Rd[9];
   __shared__ int s_last;
+  pdl_wait();
   const int pair = blockIdx.x / L.blocks_per_pair, blk = blockIdx.x % L.blocks_per_pair;
   AlignState& S = L.d_states[pair];
   const int kind = S.eval_kind;
@@ -292,14 +293,13 @@ __global__ void __launch_bounds__(kEvalThreads) ndt_eval_cold_kernel(EvalLaunch 
   if (kind == EVAL_HESS27) run_hess27(P, G, s_T, s_Rd, blk, bpp, c.gauss_d1, c.gauss_d2, c.resolution, s_red, partial);
   else if (kind == EVAL_DERIV_H) run_kdtree<true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);
   else run_kdtree<false>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);
+  pdl_trigger();
   eval_finish(L, pair, kind, kAcc, P.n_total, s_red, &s_last);
 }
 
 int launch_eval_cold(cudaStream_t st, const EvalLaunch& L) {
   if (L.n_pairs <= 0) return LVS_OK;
-  ndt_eval_cold_kernel<<<L.n_pairs * L.blocks_per_pair, kEvalThreads, 0, st>>>(L);
-  CUDA_TRY(cudaGetLastError());
-  return LVS_OK;
+  return launch_pdl(ndt_eval_cold_kernel, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, 0, st, L);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

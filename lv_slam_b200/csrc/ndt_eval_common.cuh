@@ -23,6 +23,25 @@ template <> struct Probes<LVS_DIRECT7> { static constexpr int K = 7; };
 template <> struct Probes<LVS_DIRECT26> { static constexpr int K = 26; };
 
 
+// Programmatic dependent launch: consecutive evaluation launches of an align are queued back to back, each reading the state the previous one's
+// last CTA left behind.  Launched with programmatic stream serialisation, a kernel's CTAs may be scheduled as soon as every CTA of the previous
+// launch has passed pdl_trigger() (after its share of the points, before the reduction tail) or exited; they then block in pdl_wait() until that
+// launch has completed and its writes are visible.  The launch latency and the prologue hide under the previous tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename Kernel>
+static int launch_pdl(Kernel kernel, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, const EvalLaunch& L) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, L));
+  return LVS_OK;
+}
+
 struct GridView {
   int min_b[3], max_b[3], mul[3];
   float leaf;

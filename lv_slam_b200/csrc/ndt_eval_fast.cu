@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
   __shared__ double s_red[kFWarps][kFSlots];
   __shared__ float s_T[16], s_R[9];
   __shared__ int s_last;
+  pdl_wait();
   const int pair = blockIdx.x / L.blocks_per_pair, blk = blockIdx.x % L.blocks_per_pair;
   AlignState& S = L.d_states[pair];
   const int kind = S.eval_kind;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
       __syncwarp();
     }
   }
+  pdl_trigger();
   fast_flush(A, accd, lane);
 
   // CTA partial: every output slot sums the 8 warps in fixed order and lands at its place(s) in the canonical 43-vector
@@ -282,9 +284,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
 
 template <int MODE, bool PCA>
 static int launch_fast_as(cudaStream_t st, const EvalLaunch& L) {
-  ndt_eval_fast_kernel<MODE, PCA><<<L.n_pairs * L.blocks_per_pair, kEvalThreads, 0, st>>>(L);
-  CUDA_TRY(cudaGetLastError());
-  return LVS_OK;
+  return launch_pdl(ndt_eval_fast_kernel<MODE, PCA>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, 0, st, L);
 }
 
 int launch_eval_fast(cudaStream_t st, const EvalLaunch& L) {
