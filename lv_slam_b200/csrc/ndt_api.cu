@@ -494,6 +494,12 @@ static int align_begin(lvs_ndt_batch* b, int n_pairs, const int32_t* src_slot, c
   shard_view(b, L);
   L.h_done_flag = b->d_flag_alias; L.align_serial = ++b->align_serial;
   L.d_dbg = b->d_dbg;
+  if (L.consts.fast && getenv("LVS_STAGE_RECORDS")) {      // experiment switch: voxel records of the pair staged in shared memory by a bulk copy
+    int max_cells = 0;
+    for (int i = 0; i < n_pairs; i++) max_cells = std::max(max_cells, b->targets[tgt_slot[i]].n_cells);
+    const long long bytes = (long long)max_cells * (long long)sizeof(FastRec);
+    L.stage_bytes = (bytes > 0 && bytes <= 160 * 1024) ? (int)((bytes + 15) & ~15LL) : 0;
+  }
   // worst case: initial pass + (max_iter + 2) outer iterations of (first + 10 trials + Hessian pass)
   P.max_launches = 1 + (b->prm.max_iterations + 2) * 12 + 8;
   L.shard.serial = b->shard_serial;            // base of this align; every pair adds its own evaluation count (eval_finish)

@@ -45,16 +45,43 @@ __device__ __forceinline__ void fast_slot_outputs(int s, int& a, int& b) {
   if (i != j) b = 7 + 6 * j + i;
 }
 
+// ---- staging of a pair's voxel records in shared memory by ONE bulk copy (TMA, cp.async.bulk) per CTA: north_star names "TMA / shared-memory
+// staging of voxel covariances".  The records of one target are ~1.6 k x 48 B = 77 KB: they fit, but cost the third resident CTA of an SM.
+// Measured: the L1-cached __ldg path is as fast, so staging is an option (LVS_STAGE_RECORDS=1), not the default.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_stage(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+  }
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+  } while (!ok);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // One (point, cell) contribution added into the lane's float sums.  pa = (x', y', z', xr), pb = (yr, zr): transformed point and
 // rotated point R*x; w: ndt_pca weight of this contribution (running product of the cell weights, ndt_pca_impl2.hpp:293-296).
-template <bool PCA>
+template <bool PCA, bool STAGE>
 __device__ __forceinline__ void fast_contribute(float (&A)[kFSlots], const FastRec* __restrict__ fr, const float4 pa, const float2 pb, float w,
                                                 float kexp, float gd1, float gd2) {
-  const float4 r0 = __ldg(reinterpret_cast<const float4*>(fr));        // mh0 mh1 mh2 ml0
-  const float4 r1 = __ldg(reinterpret_cast<const float4*>(fr) + 1);    // ml1 ml2 c00 c01
-  const float4 r2 = __ldg(reinterpret_cast<const float4*>(fr) + 2);    // c02 c11 c12 c22
+  float4 r0, r1, r2;
+  if (STAGE) {                                                         // records staged in shared memory
+    r0 = reinterpret_cast<const float4*>(fr)[0]; r1 = reinterpret_cast<const float4*>(fr)[1]; r2 = reinterpret_cast<const float4*>(fr)[2];
+  } else {
+    r0 = __ldg(reinterpret_cast<const float4*>(fr));                   // mh0 mh1 mh2 ml0
+    r1 = __ldg(reinterpret_cast<const float4*>(fr) + 1);               // ml1 ml2 c00 c01
+    r2 = __ldg(reinterpret_cast<const float4*>(fr) + 2);               // c02 c11 c12 c22
+  }
   const float d0 = (pa.x - r0.x) - r0.w, d1 = (pa.y - r0.y) - r1.x, d2 = (pa.z - r0.z) - r1.y;
   const float c00 = r1.z, c01 = r1.w, c02 = r2.x, c11 = r2.y, c12 = r2.z, c22 = r2.w;
   // c = C d (= d^T C), q = d^T C d
@@ -136,8 +163,10 @@ struct FastSmem {
   static constexpr size_t bytes = warp_bytes * kFWarps;
 };
 
-template <int MODE, bool PCA>
-__global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaunch L) {
+template <int MODE, bool PCA, bool STAGE>
+__global__ void __launch_bounds__(kEvalThreads, STAGE ? 2 : 3) ndt_eval_fast_kernel(EvalLaunch L) {
+  extern __shared__ __align__(16) unsigned char s_recs[];          // STAGE: the target's FastRec array
+  __shared__ unsigned long long s_bar;
   constexpr int K = Probes<MODE>::K;
   using SM = FastSmem<PCA>;
   __shared__ __align__(16) unsigned char s_stage[SM::bytes];
@@ -166,6 +195,10 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
   int* q = reinterpret_cast<int*>(wbase + SM::q_off);
   float* qw = reinterpret_cast<float*>(wbase + SM::qw_off);        // only mapped for ndt_pca launches
   const FastRec* __restrict__ frecs = P.frecs;
+  if (STAGE) {
+    const unsigned bytes = (unsigned)P.gp->n_cells * (unsigned)sizeof(FastRec);
+    if (bytes > 0 && bytes <= (unsigned)L.stage_bytes) { bulk_stage(s_recs, P.frecs, bytes, &s_bar); frecs = reinterpret_cast<const FastRec*>(s_recs); }
+  }
   const int* __restrict__ grid = P.grid;
   const float* T = s_T;
   const float* R = s_R;
@@ -186,7 +219,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
     if (lane < n_round) {
       const int ent = q[head + lane];
       const int rec = ent / kFPtsPerIter, slot = ent % kFPtsPerIter;
-      fast_contribute<PCA>(A, frecs + rec, pa[slot], pb[slot], PCA ? qw[head + lane] : 1.0f, kexp, gd1, gd2);
+      fast_contribute<PCA, STAGE>(A, frecs + rec, pa[slot], pb[slot], PCA ? qw[head + lane] : 1.0f, kexp, gd1, gd2);
     }
     if (++since_flush == kFlushRounds) { fast_flush(A, accd, lane); since_flush = 0; }
   };
@@ -284,7 +317,17 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_fast_kernel(EvalLaun
 
 template <int MODE, bool PCA>
 static int launch_fast_as(cudaStream_t st, const EvalLaunch& L) {
-  return launch_pdl(ndt_eval_fast_kernel<MODE, PCA>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, 0, st, L);
+  if (L.stage_bytes > 0) {
+    static int attr_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+      CUDA_TRY(cudaFuncSetAttribute(ndt_eval_fast_kernel<MODE, PCA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_dev = dev;
+    }
+    return launch_pdl(ndt_eval_fast_kernel<MODE, PCA, true>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, (size_t)L.stage_bytes, st, L);
+  }
+  return launch_pdl(ndt_eval_fast_kernel<MODE, PCA, false>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, 0, st, L);
 }
 
 int launch_eval_fast(cudaStream_t st, const EvalLaunch& L) {

@@ -119,6 +119,7 @@ struct EvalLaunch {
   int* d_done_count;          // incremented once per finished pair
   volatile int* h_done_flag = nullptr;   // host-mapped word: receives align_serial when the last pair of the batch finishes (null: not used)
   int align_serial = 0;
+  int stage_bytes = 0;          // tolerance mode: > 0 = stage the pair's voxel records in shared memory by one bulk copy (bytes of dynamic shared memory)
   long long* d_dbg = nullptr;   // diagnostics (LVS_DEBUG_TIMING=1): clock64 stamps of the last CTA's tail, 8 per pair; null in normal operation
   int n_pairs;
   int blocks_per_pair;
