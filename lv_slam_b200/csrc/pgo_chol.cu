@@ -153,9 +153,22 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
     if (!col[c].empty()) par[c] = col[c][0];
   }
   // fundamental supernodes: column c joins c-1 when pattern(c-1) = {c} u pattern(c)
+  // plus RELAXED amalgamation: the last child of a front (its columns directly precede the front's in the postorder) is merged into it
+  // when that pads the child's columns with few explicit zero rows - fewer, fatter fronts and fewer tree levels for a latency-bound
+  // factorisation, at the price of some arithmetic on zeros.  relax = largest number of index blocks a child column may be padded by
+  // (LVS_CHOL_RELAX overrides; 0 = fundamental supernodes only).
+  int relax = 12;
+  if (const char* e = getenv("LVS_CHOL_RELAX")) relax = atoi(e);
   S.col_front.assign(n, -1);
+  int pad_budget = 0;            // padding already accepted for the columns of the front being grown
   for (int c = 0; c < n; c++) {
-    const bool join = c > 0 && par[c - 1] == c && col[c - 1].size() == col[c].size() + 1;
+    bool join = c > 0 && par[c - 1] == c && col[c - 1].size() == col[c].size() + 1;
+    if (join) {}                            // fundamental: no padding added
+    else if (c > 0 && par[c - 1] == c && relax > 0) {
+      const int extra = (int)col[c].size() + 1 - (int)col[c - 1].size();     // rows the child's last column lacks (>= 1 here)
+      if (extra + pad_budget <= relax) { join = true; pad_budget += extra; }
+    }
+    if (!join) pad_budget = 0;
     if (join) { S.fronts.back().w++; }
     else { CholFront f; memset(&f, 0, sizeof f); f.c0 = c; f.w = 1; f.parent = -1; S.fronts.push_back(f); }
     S.col_front[c] = (int)S.fronts.size() - 1;
@@ -174,7 +187,7 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
     f.off = S.arena;
     S.arena += (long long)f.F * f.F;
     S.max_front = std::max(S.max_front, f.F);
-    S.nnz_l_blocks += (long long)f.w * (f.w + 1) / 2 + (long long)f.w * f.r;
+    for (int k = 0; k < f.w; k++) S.nnz_l_blocks += 1 + (long long)col[f.c0 + k].size();   // the true fill: padding of relaxed supernodes is stored (arena, flops) but not counted
     for (int k = 0; k < f.w; k++) { const double m = 6.0 * (f.w - k - 1 + f.r) + 1; S.flops += 3.0 * m * m; }   // 6 pivot columns x m^2 / 2
   }
   // relative indices: position of every row of R_S inside the parent's index set (its pivots, then its R)
