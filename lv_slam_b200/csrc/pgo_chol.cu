@@ -260,40 +260,47 @@ constexpr int kCholBigFront = 192;      // fronts with F above this go to the te
 constexpr int kNB = 24;                 // pivot columns per panel of the backward substitution
 constexpr int kCholSmemFront = 64;      // fronts up to this many rows are factored in shared memory (single-CTA kernel)
 constexpr int kMB = 16;                 // micro block: factored and inverted by one warp in registers
-constexpr int kSlab = 32;               // rows of one row-solve work item (8 threads per row, 2 columns of a micro block each)
-constexpr int kSlabCols = kMB * kSlab / kCholThreads;
+constexpr int kSlab = 32;               // rows of one row-solve work item: 4 x 2 m8n8 tiles of a 32 x 16 micro column, one per warp
 
 // Partial dense Cholesky of a front, per kernel variant.  Panels are WIDE (96 pivot columns for the team kernel): a panel costs two
-// team barriers and one pass over the trailing matrix whatever its width, and with 24-column panels those were most of a front's time
-// (48 panels x (2 x 4 us barriers + 5 us update) on the 1 159-row root).  What made wide panels slower before - a column-by-column
-// diagonal block with a CTA barrier per column and a row solve that is one dependent chain of nb^2 / 2 multiply-adds per row - is gone:
+// team barriers and one pass over the trailing matrix whatever its width.  All dense arithmetic but the 16 x 16 micro blocks themselves
+// runs on the FP64 tensor cores (mma.sync.m8n8k4.f64, DMMA); every operand array in shared memory has a row stride = 4 (mod 16) doubles,
+// which makes the fragment loads of all three phases bank-conflict free.
 //   (A) the diagonal block is factored in 16 x 16 micro blocks, each by ONE WARP in registers (a lane owns a row, columns travel by
-//       shuffle), which also inverts the micro block; between micro blocks the CTA applies it to the rest of the diagonal block;
-//   (B) the rows below are solved in slabs of 64 rows against the micro blocks: a block product with the columns already done plus a
-//       product with the 16 x 16 inverse - independent multiply-adds instead of a chain;
-//   (C) the trailing update runs on the tensor cores: mma.sync.m8n8k4.f64 (DMMA), operands staged in shared memory with a row
-//       stride = 4 (mod 16) doubles so that every fragment load is bank-conflict free.
+//       shuffle); the same warp builds the micro block's inverse W row by row as the rows of L complete.  The rows of the diagonal block
+//       below it are then X = S W^T and the rest of the block takes S -= X X^T, both as DMMA tiles spread over the warps.
+//       In a team, RANK 0 ALONE factors the block and does so one panel AHEAD: right after it has updated the next diagonal block (tile 0
+//       of the trailing update) it factors it while the other CTAs are still busy with the rest of the update (look-ahead); the factor
+//       and the inverses travel through the front / a per-team scratch and are picked up by everyone after the panel's closing barrier;
+//   (B) the rows below are solved in slabs of 32 rows: per micro column a DMMA block product with the columns already solved, then
+//       the DMMA product with the inverse;
+//   (C) the trailing update: TILE x TILE outputs per pass, K = NB, panels staged by cp.async.
 template <bool TEAM>
 struct FrontCfg {
   static constexpr int NB = TEAM ? 96 : 48;       // pivot columns per panel
   static constexpr int TILE = TEAM ? 96 : 64;     // trailing-update tile (outputs per CTA pass: TILE x TILE)
   static constexpr int LDL = TILE + 4;            // row stride of the staged panels: = 4 (mod 16)
-  static constexpr int LDD = NB + 1;              // row stride of the diagonal block
+  static constexpr int LDD = NB + 4;              // row stride of the diagonal block
+  static constexpr int LDW = kMB + 4;             // row stride of a micro block's inverse
+  static constexpr int LDX = kSlab + 4;           // column stride of a slab (column-major)
   static constexpr int NMB = NB / kMB;
   static constexpr int WM = 4, WN = 2;            // warp grid over a tile
   static constexpr int TM = TILE / 8 / WM, TN = TILE / 8 / WN;   // m8n8 tiles per warp
-  static constexpr int XC = ((NB - kMB) * kMB + kCholThreads - 1) / kCholThreads;   // in-block row-solve outputs per thread
+  static constexpr int WSCR = NMB * kMB * LDW + NB;               // per-team scratch: the inverses and the reciprocal diagonal (doubles)
   // dynamic shared memory, in doubles: phases A + B and phase C alias
   static constexpr size_t oD = 0;
   static constexpr size_t oW = oD + (size_t)NB * LDD;
-  static constexpr size_t oIl = oW + (size_t)NMB * kMB * (kMB + 1);
+  static constexpr size_t oIl = oW + (size_t)NMB * kMB * LDW;
   static constexpr size_t oX = oIl + NB;
-  static constexpr size_t phaseAB = oX + (size_t)NB * kSlab;
+  static constexpr size_t phaseAB = oX + (size_t)NB * LDX;
   static constexpr size_t phaseC = 2 * (size_t)NB * LDL;
-  static constexpr size_t oFront = phaseAB > phaseC ? phaseAB : phaseC;
+  static constexpr size_t phaseH = TEAM ? oX + (size_t)NB * LDL : 0;     // rank 0's look-ahead: the diagonal block next to the panel rows that update it
+  static constexpr size_t oFront = (phaseAB > phaseC ? phaseAB : phaseC) > phaseH ? (phaseAB > phaseC ? phaseAB : phaseC) : phaseH;
   static constexpr size_t doubles = oFront + (TEAM ? 0 : (size_t)kCholSmemFront * kCholSmemFront);
   static constexpr size_t bytes = doubles * sizeof(double);
-  static_assert(TILE % (8 * WM) == 0 && TILE % (8 * WN) == 0 && LDL % 16 == 4 && NB % kMB == 0 && NB % 4 == 0, "tile shape");
+  static_assert(TILE % (8 * WM) == 0 && TILE % (8 * WN) == 0 && LDL % 16 == 4 && LDD % 16 == 4 && LDW % 16 == 4 && LDX % 16 == 4 && NB % kMB == 0, "tile shape");
+  static_assert(!TEAM || TILE == NB, "look-ahead: tile 0 of the trailing update is the next diagonal block");
+  static_assert(kCholThreads == 256 && kSlab == 32 && kMB == 16, "phase B maps one m8n8 tile of a 32 x 16 micro column to each of the 8 warps");
 };
 
 struct CholView {
@@ -304,9 +311,10 @@ struct CholView {
   const unsigned char* off_tr;
   double* arena;
   double* xp;
+  double* wscratch;        // per team: inverses of the current panel's micro blocks + reciprocal diagonal (team kernel)
   int* fail_flag;
   int n, n_off;
-  long long* dbg;          // diagnostics (LVS_DEBUG_TIMING): per-phase SM clocks of rank 0 of the LAST front of a team launch, null otherwise
+  long long* dbg;          // diagnostics (LVS_DEBUG_TIMING): per-phase SM clocks of ranks 0 and 1 of the LAST front of a team launch, null otherwise
 };
 
 __global__ void __launch_bounds__(kCholThreads) chol_scatter_kernel(CholView V, const double* __restrict__ Hd, const double* __restrict__ Ho,
@@ -372,10 +380,26 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
   return fma(y, fma(-h2, y, 0.5), y);
 }
 
-// One warp: Cholesky of the 16 x 16 block at S (row stride ld, lower triangle; the strict upper part is ignored).  Lane l (and l + 16,
-// redundantly: every shuffle source is a lane below 16) owns row l & 15.  Writes L over the lower triangle of S and the reciprocals of
-// its diagonal to il_out[16].  A non-positive pivot raises *fail_flag and is replaced by 1.
-__device__ __forceinline__ void micro_factor(double* S, int ld, double* il_out, int* fail_flag) {
+// The 16 x 16 micro block at S (row stride ld, lower triangle; the strict upper part is ignored), by TWO WARPS: the producer factors it
+// in registers - lane l (and l + 16, redundantly: every shuffle source is a lane below 16) owns row l & 15, columns travel by shuffle - and
+// stores every finished column to S; the consumer trails one column behind (one mbarrier per column) and builds the inverse W = L^-1 row
+// by row: row j of L is complete once column j is stored, and W[j][c] = (delta_jc - sum_{k < j} L[j][k] W[k][c]) / L[j][j] needs nothing
+// else.  The producer's column is bound by the shuffle rate of one warp (a 64-bit shuffle issues every ~10 cycles: tools/ubench/chain_lat.cu),
+// so the inverse must not share its instruction stream (fused into one warp the block took 6 000 cycles instead of 3 000).
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// producer: writes L over the lower triangle of S and the reciprocals of its diagonal to il_out[16]; a non-positive pivot raises
+// *fail_flag and is replaced by 1
+__device__ __forceinline__ void micro_factor(double* S, int ld, double* il_out, int* fail_flag, unsigned long long* bars) {
   const int lane = threadIdx.x & 31, row = lane & 15;
   double s[kMB];
 #pragma unroll
@@ -386,59 +410,168 @@ __device__ __forceinline__ void micro_factor(double* S, int ld, double* il_out, 
     if (!(d > 0.0)) { *fail_flag = 1; d = 1.0; }
     const double il = fast_rsqrt(d);
     const double lij = (row == j) ? d * il : s[j] * il;                // rows above j hold 0 there
-    s[j] = lij;
+    if (lane < kMB && row >= j) S[row * ld + j] = lij;
     if (lane == j) il_out[j] = il;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + j);
 #pragma unroll
     for (int k = j + 1; k < kMB; k++) {
       const double lkj = __shfl_sync(0xffffffffu, lij, k);
       s[k] -= lij * lkj;                                               // meaningful for row >= k; the rest is never read
     }
   }
-  if (lane < kMB) {
+}
+
+// consumer: W to Wout[16][ldw] (upper part zero); lane c (and c + 16, redundantly) owns column c
+__device__ __forceinline__ void micro_invert(const double* S, int ld, const double* il, double* Wout, int ldw, unsigned long long* bars, unsigned parity) {
+  const int lane = threadIdx.x & 31, col = lane & 15;
+  double w[kMB];
 #pragma unroll
-    for (int k = 0; k < kMB; k++)
-      if (k <= row) S[row * ld + k] = s[k];
+  for (int j = 0; j < kMB; j++) {
+    mbar_wait(bars + j, parity);
+    double a0 = (col == j) ? 1.0 : 0.0, a1 = 0.0;                      // two partial sums: half the dependent chain
+#pragma unroll
+    for (int k = 0; k < j; k += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(S + j * ld + k);     // L[j][k], L[j][k + 1]: the same address for every lane
+      a0 -= v.x * w[k];
+      if (k + 1 < j) a1 -= v.y * w[k + 1];
+    }
+    w[j] = (a0 + a1) * il[j];                                          // zero for j < column
+    if (lane < kMB) Wout[j * ldw + col] = (j >= col) ? w[j] : 0.0;
   }
 }
 
-// One warp: W = L^-1 (lower) of the factored 16 x 16 block at S, to Wout[16][17].  Lane c (& 15) computes column c by forward
-// substitution, W[i][c] = (delta_ic - sum_{k < i} L[i][k] W[k][c]) / L[i][i]; row i of L travels by shuffle from lane i.
-__device__ __forceinline__ void micro_invert(const double* S, int ld, const double* il, double* Wout) {
-  const int lane = threadIdx.x & 31, row = lane & 15;
-  double s[kMB], w[kMB];
+// (A) The nb x nb diagonal block of the panel at column c of the front A (leading dimension F), in three steps that the callers combine:
+// stage_diag copies its lower triangle to s_D (rows / columns past nb padded with the identity), factor_core factors it there - leaving L
+// in s_D, the inverses of the micro blocks in s_W and the reciprocal diagonal in s_il - and writeback_diag stores the factor to the front.
+// Whole CTA; stage_diag does not end with a barrier, the other two do.
+template <bool TEAM>
+__device__ __forceinline__ void stage_diag(const double* A, int F, int c, int nb, double* s_D) {
+  using Cfg = FrontCfg<TEAM>;
+  constexpr int NB = Cfg::NB, LDD = Cfg::LDD;
+  // (every global load of the staging loops is unconditional, from a clamped address, and a whole group of them is issued before the
+  // first use: with predicated loads the compiler sinks each one next to its store and only one is in flight at a time)
+  constexpr int kG = TEAM ? 12 : 9;
+  static_assert((NB * NB) % (kG * kCholThreads) == 0, "diagonal block staging");
+  for (int t0 = threadIdx.x; t0 < NB * NB; t0 += kG * kCholThreads) {
+    double v[kG];
 #pragma unroll
-  for (int k = 0; k < kMB; k++) s[k] = (k <= row) ? S[row * ld + k] : 0.0;
+    for (int u = 0; u < kG; u++) {
+      const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
+      v[u] = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1));
+    }
 #pragma unroll
-  for (int i = 0; i < kMB; i++) {
-    double acc = (i == row) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; k++) acc -= __shfl_sync(0xffffffffu, s[k], i) * w[k];
-    w[i] = acc * il[i];
+    for (int u = 0; u < kG; u++) {
+      const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
+      s_D[i * LDD + j] = (i < nb && j <= i) ? v[u] : (i == j ? 1.0 : 0.0);
+    }
   }
-  if (lane < kMB) {
+}
+
+template <bool TEAM>
+__device__ __forceinline__ void factor_core(int nb, double* s_D, double* s_W, double* s_il, int* fail_flag, unsigned long long* mbars, unsigned& mb_uses,
+                                            long long* tm = nullptr) {
+  long long tl = clock64();
+#define LVS_TM(k) if (tm && threadIdx.x == 0) { const long long tn = clock64(); tm[k] += tn - tl; tl = tn; }
+  using Cfg = FrontCfg<TEAM>;
+  constexpr int LDD = Cfg::LDD, LDW = Cfg::LDW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nmb = (nb + kMB - 1) / kMB;
+  for (int mb = 0; mb < nmb; mb++) {
+    const int m0 = kMB * mb;
+    double* W = s_W + mb * kMB * LDW;
+    if (warp == 0) micro_factor(s_D + m0 * LDD + m0, LDD, s_il + m0, fail_flag, mbars);
+    else if (warp == 1) micro_invert(s_D + m0 * LDD + m0, LDD, s_il + m0, W, LDW, mbars, mb_uses & 1);
+    mb_uses++;
+    LVS_TM(0)
+    __syncthreads();
+    LVS_TM(1)
+    const int nrt = (kMB * nmb - (m0 + kMB)) / 8;          // 8-row tiles of the diagonal block below this micro block
+    if (nrt > 0) {
+      // X = S W^T for the rows below, in place: a warp owns whole rows, all fragments are in registers before the first store
+      for (int rt = warp; rt < nrt; rt += kCholThreads / 32) {
+        const int i0 = m0 + kMB + 8 * rt;
+        const double* pa = s_D + (i0 + (lane >> 2)) * LDD + m0 + (lane & 3);
+        const double* pw = W + (lane >> 2) * LDW + (lane & 3);
+        double fa[4], x[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, y[2][2] = {{0.0, 0.0}, {0.0, 0.0}};      // x / y: two halves of K, independent chains
 #pragma unroll
-    for (int k = 0; k < kMB; k++) Wout[k * (kMB + 1) + row] = (k >= row) ? w[k] : 0.0;    // W[k][row]
+        for (int ks = 0; ks < 4; ks++) fa[ks] = pa[4 * ks];
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+          for (int nh = 0; nh < 2; nh++) {
+            dmma884(x[nh][0], x[nh][1], fa[ks], pw[8 * nh * LDW + 4 * ks]);
+            dmma884(y[nh][0], y[nh][1], fa[ks + 2], pw[8 * nh * LDW + 4 * ks + 8]);
+          }
+        __syncwarp();
+        double* px = s_D + (i0 + (lane >> 2)) * LDD + m0 + 2 * (lane & 3);
+#pragma unroll
+        for (int nh = 0; nh < 2; nh++) { px[8 * nh] = x[nh][0] + y[nh][0]; px[8 * nh + 1] = x[nh][1] + y[nh][1]; }
+      }
+      __syncthreads();
+      LVS_TM(2)
+      // S[i][k] -= sum_q X[i][q] X[k][q] for the rest of the diagonal block: 8 x 8 tiles of the lower part (the strict upper part of a
+      // diagonal tile receives values nobody reads)
+      // (nrt is even: the triangle of tiles folds into an nrt / 2 x (nrt + 1) rectangle - row a holds tile row a and tile row nrt - 1 - a)
+      const int ntl = nrt * (nrt + 1) / 2, nw = nrt + 1;
+      for (int t = warp; t < ntl; t += kCholThreads / 32) {
+        const int a = t / nw, b = t - a * nw;
+        const int ti = (b <= a) ? a : nrt - 1 - a, tj = (b <= a) ? b : b - a - 1;
+        const int i0 = m0 + kMB + 8 * ti, k0 = m0 + kMB + 8 * tj;
+        const double* pa = s_D + (i0 + (lane >> 2)) * LDD + m0 + (lane & 3);
+        const double* pb = s_D + (k0 + (lane >> 2)) * LDD + m0 + (lane & 3);
+        double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
+        dmma884(u0, u1, pa[0], pb[0]);
+        dmma884(v0, v1, pa[8], pb[8]);
+        dmma884(u0, u1, pa[4], pb[4]);
+        dmma884(v0, v1, pa[12], pb[12]);
+        double* pc = s_D + (i0 + (lane >> 2)) * LDD + k0 + 2 * (lane & 3);
+        pc[0] -= u0 + v0; pc[1] -= u1 + v1;
+      }
+      __syncthreads();
+      LVS_TM(3)
+    }
   }
+#undef LVS_TM
+}
+
+// also publishes the inverses and the reciprocal diagonal to the team's scratch (team kernel; wscr = nullptr otherwise)
+template <bool TEAM>
+__device__ __forceinline__ void writeback_diag(double* A, int F, int c, int nb, const double* s_D, const double* s_W, double* wscr) {
+  using Cfg = FrontCfg<TEAM>;
+  for (int t = threadIdx.x; t < nb * nb; t += kCholThreads) {
+    const int j = t / nb, i = t % nb;
+    if (i >= j) A[(size_t)(c + j) * F + c + i] = s_D[i * Cfg::LDD + j];
+  }
+  if (TEAM && wscr)
+    for (int t = threadIdx.x; t < Cfg::WSCR; t += kCholThreads) wscr[t] = s_W[t];      // s_il follows s_W in shared memory
+  __syncthreads();
 }
 
 template <bool TEAM>
 __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(CholView V, const int* __restrict__ list, int n_list, int team_size,
                                                                   unsigned int* __restrict__ bars) {
   using Cfg = FrontCfg<TEAM>;
-  constexpr int NB = Cfg::NB, TILE = Cfg::TILE, LDL = Cfg::LDL, LDD = Cfg::LDD;
+  constexpr int NB = Cfg::NB, TILE = Cfg::TILE, LDL = Cfg::LDL, LDD = Cfg::LDD, LDW = Cfg::LDW, LDX = Cfg::LDX;
   const int team = blockIdx.x / team_size, rank = blockIdx.x % team_size, n_teams = gridDim.x / team_size;
   const int tid = rank * kCholThreads + threadIdx.x, nthr = team_size * kCholThreads;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int* bar = bars + team;
+  double* const wscr = TEAM ? V.wscratch + (size_t)team * Cfg::WSCR : nullptr;
   unsigned int target = 0;
-  extern __shared__ double s_dyn[];
+  extern __shared__ __align__(16) double s_dyn[];
   double* s_D = s_dyn + Cfg::oD;                  // [NB][LDD] diagonal block of the panel: Schur complement, then its factor
-  double* s_W = s_dyn + Cfg::oW;                  // [NMB][16][17] inverses of the diagonal micro blocks
+  double* s_W = s_dyn + Cfg::oW;                  // [NMB][16][LDW] inverses of the diagonal micro blocks
   double* s_il = s_dyn + Cfg::oIl;                // [NB] reciprocals of the factor's diagonal
-  double* s_X = s_dyn + Cfg::oX;                  // [NB][kSlab] one slab of rows below the panel, column-major
+  double* s_X = s_dyn + Cfg::oX;                  // [NB][LDX] one slab of rows below the panel, column-major
   double* s_Li = s_dyn;                           // phase C (aliases A / B): [NB][LDL] panel rows of the tile's row range
   double* s_Lj = s_dyn + (size_t)NB * LDL;        //                          and of its column range
   double* s_front = s_dyn + Cfg::oFront;          // single-CTA launches only: room for a front of kCholSmemFront rows
+  __shared__ unsigned long long s_mbar[kMB];      // one per column of a micro block: the factoring warp releases the inverting warp
+  unsigned mb_uses = 0;                           // micro blocks factored so far by this CTA: the mbarriers' phase
+  if (threadIdx.x < kMB) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(s_mbar + threadIdx.x)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
   for (int fi = team; fi < n_list; fi += n_teams) {
     const CholFront f = V.fronts[list[fi]];
     double* const A_global = V.arena + f.off;
@@ -489,84 +622,50 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
     // the last row (F - 1) of the front.
     const int p = 6 * f.w;
     long long tph[6] = {0, 0, 0, 0, 0, 0}, tl = clock64();
-    const bool dbg = TEAM && V.dbg != nullptr && rank == 0 && threadIdx.x == 0;
+    const bool dbg = TEAM && V.dbg != nullptr && rank <= 1 && threadIdx.x == 0;
 #define LVS_PH(k) if (dbg) { const long long tn = clock64(); tph[k] += tn - tl; tl = tn; }
+    if (TEAM) {
+      // the first diagonal block: rank 0, everyone else waits (later ones are factored ahead, inside phase C of the panel before)
+      if (rank == 0) {
+        const int nb0 = min(NB, p);
+        stage_diag<TEAM>(A, F, 0, nb0, s_D);
+        __syncthreads();
+        factor_core<TEAM>(nb0, s_D, s_W, s_il, V.fail_flag, s_mbar, mb_uses);
+        writeback_diag<TEAM>(A, F, 0, nb0, s_D, s_W, wscr);
+      }
+      team_sync<TEAM>(bar, target, team_size);
+    }
     for (int c = 0; c < p; c += NB) {
       const int nb = min(NB, p - c);
       const int nmb = (nb + kMB - 1) / kMB;
       LVS_PH(5)
-      // (A) diagonal block, by EVERY CTA of the team (same arithmetic, same result: no barrier needed before B).  Rows / columns past
-      // nb are padded with the identity.
-      // (every global load of the staging loops below is unconditional, from a clamped address, and a whole group of them is issued
-      // before the first use: with predicated loads the compiler sinks each one next to its store and only one is in flight at a time)
-      {
-        constexpr int kG = TEAM ? 12 : 9;
-        static_assert((NB * NB) % (kG * kCholThreads) == 0, "diagonal block staging");
-        for (int t0 = threadIdx.x; t0 < NB * NB; t0 += kG * kCholThreads) {
+      // (A) single CTA: factor the diagonal block now.  Team: rank 0 still holds the factor, its inverses and the reciprocal diagonal in
+      // shared memory; the others fetch them (the factor's lower triangle from the front, the rest from the team's scratch).
+      if (!TEAM) {
+        stage_diag<TEAM>(A, F, c, nb, s_D);
+        __syncthreads();
+        factor_core<TEAM>(nb, s_D, s_W, s_il, V.fail_flag, s_mbar, mb_uses);
+        writeback_diag<TEAM>(A, F, c, nb, s_D, s_W, nullptr);
+      } else if (rank != 0) {
+        stage_diag<TEAM>(A, F, c, nb, s_D);
+        constexpr int kG = 4;
+        for (int t0 = threadIdx.x; t0 < Cfg::WSCR; t0 += kG * kCholThreads) {
           double v[kG];
 #pragma unroll
-          for (int u = 0; u < kG; u++) {
-            const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
-            v[u] = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1));
-          }
+          for (int u = 0; u < kG; u++) v[u] = __ldcg(wscr + min(t0 + u * kCholThreads, Cfg::WSCR - 1));
 #pragma unroll
-          for (int u = 0; u < kG; u++) {
-            const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
-            s_D[i * LDD + j] = (i < nb && j <= i) ? v[u] : (i == j ? 1.0 : 0.0);
-          }
+          for (int u = 0; u < kG; u++) if (t0 + u * kCholThreads < Cfg::WSCR) s_W[t0 + u * kCholThreads] = v[u];
         }
-      }
-      __syncthreads();
-      for (int mb = 0; mb < nmb; mb++) {
-        const int m0 = kMB * mb;
-        if (warp == 0) micro_factor(s_D + m0 * LDD + m0, LDD, s_il + m0, V.fail_flag);
         __syncthreads();
-        const int rows = nb - (m0 + kMB);          // rows of the diagonal block below this micro block
-        // the inverse (needed by phase B only) on warp 1, while warps 2.. solve the rows below by substitution against L itself:
-        // x_q = (s_q - sum_{k < q} x_k L[q][k]) / L[q][q], a thread per row, in place (a thread touches its own row only)
-        if (warp == 1) micro_invert(s_D + m0 * LDD + m0, LDD, s_il + m0, s_W + mb * kMB * (kMB + 1));
-        if (rows > 0) {
-          const int tr = (int)threadIdx.x - 64;
-          if (tr >= 0 && tr < rows) {
-            double* xr = s_D + (m0 + kMB + tr) * LDD + m0;
-            const double* Lm = s_D + m0 * LDD + m0;
-            double x[kMB];
-#pragma unroll
-            for (int q = 0; q < kMB; q++) x[q] = xr[q];
-#pragma unroll
-            for (int q = 0; q < kMB; q++) {
-              double a0 = x[q], a1 = 0.0;
-#pragma unroll
-              for (int k = 0; k + 1 < q; k += 2) { a0 -= x[k] * Lm[q * LDD + k]; a1 -= x[k + 1] * Lm[q * LDD + k + 1]; }
-              if (q & 1) a0 -= x[q - 1] * Lm[q * LDD + q - 1];
-              x[q] = (a0 + a1) * s_il[m0 + q];
-            }
-#pragma unroll
-            for (int q = 0; q < kMB; q++) xr[q] = x[q];
-          }
-          __syncthreads();
-          // S[i][k] -= sum_q X[i][q] X[k][q] for the rest of the diagonal block, one 16-column strip after the other (lower part)
-          for (int k0 = m0 + kMB; k0 < nb; k0 += kMB) {
-            const int nr = nb - k0;
-            for (int t = threadIdx.x; t < nr * kMB; t += kCholThreads) {
-              const int i = k0 + t % nr, k = k0 + t / nr;
-              if (k < nb && k <= i) {
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < kMB; q++) acc += s_D[i * LDD + m0 + q] * s_D[k * LDD + m0 + q];
-                s_D[i * LDD + k] -= acc;
-              }
-            }
-          }
-          __syncthreads();
-        }
       }
       LVS_PH(0)
-      // (B) rows below the panel: X L_D^T = A, slab by slab.  In s_X the slab is column-major (a thread's row index runs along the
-      // lanes).  Micro column m: first the block product with the columns already solved, then the product with the inverse.
+      // (B) rows below the panel: X L_D^T = A, slab by slab.  In s_X the slab is column-major.  Warp (rt, nh) owns the 8 x 8 tile (rows
+      // 8 rt.., columns 8 nh..) of every 32 x 16 micro column: first the block product with the columns already solved (K = m0), then
+      // the product with the micro block's inverse (K = 16), both on DMMA.
       {
         const int n_below = F - (c + nb);
         const int n_slabs = (n_below + kSlab - 1) / kSlab;
+        const int rt = warp >> 1, nh = warp & 1;
         for (int slab = rank; slab < n_slabs; slab += team_size) {
           const int r0 = c + nb + slab * kSlab, nr = min(kSlab, F - r0);
           {
@@ -582,50 +681,39 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
 #pragma unroll
               for (int u = 0; u < kG; u++) {
                 const int t = t0 + u * kCholThreads, r = t % kSlab, q = t / kSlab;
-                s_X[q * kSlab + r] = (q < nb && r < nr) ? v[u] : 0.0;
+                s_X[q * LDX + r] = (q < nb && r < nr) ? v[u] : 0.0;
               }
             }
           }
           __syncthreads();
-          const int r = threadIdx.x % kSlab, qg = threadIdx.x / kSlab;      // 8 threads per row, kSlabCols columns of the micro block each
           for (int mb = 0; mb < nmb; mb++) {
             const int m0 = kMB * mb;
-            double acc[kSlabCols];
-#pragma unroll
-            for (int u = 0; u < kSlabCols; u++) acc[u] = s_X[(m0 + kSlabCols * qg + u) * kSlab + r];
-            // two independent partial sums per output: the loop is a chain of dependent multiply-adds otherwise
-            double acc2[kSlabCols];
-#pragma unroll
-            for (int u = 0; u < kSlabCols; u++) acc2[u] = 0.0;
-            for (int q2 = 0; q2 + 1 < m0; q2 += 2) {
-              const double xs0 = s_X[q2 * kSlab + r], xs1 = s_X[(q2 + 1) * kSlab + r];
-#pragma unroll
-              for (int u = 0; u < kSlabCols; u++) {
-                acc[u] -= xs0 * s_D[(m0 + kSlabCols * qg + u) * LDD + q2];
-                acc2[u] -= xs1 * s_D[(m0 + kSlabCols * qg + u) * LDD + q2 + 1];
+            double* pt = s_X + (m0 + 8 * nh + 2 * (lane & 3)) * LDX + 8 * rt + (lane >> 2);      // this lane's two outputs of the tile
+            if (m0 > 0) {
+              const double* pa = s_X + (lane & 3) * LDX + 8 * rt + (lane >> 2);
+              const double* pb = s_D + (m0 + 8 * nh + (lane >> 2)) * LDD + (lane & 3);
+              double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;           // two accumulator pairs: half the dependent DMMA chain
+              for (int q = 0; q < m0; q += 8) {
+                dmma884(a0, a1, pa[q * LDX], pb[q]);
+                dmma884(b0, b1, pa[(q + 4) * LDX], pb[q + 4]);
               }
-            }
-#pragma unroll
-            for (int u = 0; u < kSlabCols; u++) s_X[(m0 + kSlabCols * qg + u) * kSlab + r] = acc[u] + acc2[u];      // own entries only
-            __syncthreads();
-            const double* W = s_W + mb * kMB * (kMB + 1);
-            double x[kSlabCols];
-#pragma unroll
-            for (int u = 0; u < kSlabCols; u++) {
-              const int q = kSlabCols * qg + u;
-              double a2 = 0.0;
-#pragma unroll
-              for (int k = 0; k < kMB; k++) a2 += (k <= q) ? s_X[(m0 + k) * kSlab + r] * W[q * (kMB + 1) + k] : 0.0;
-              x[u] = a2;
+              pt[0] -= a0 + b0; pt[LDX] -= a1 + b1;                     // own entries only
             }
             __syncthreads();
+            double x0 = 0.0, x1 = 0.0;
+            {
+              const double* pa = s_X + (m0 + (lane & 3)) * LDX + 8 * rt + (lane >> 2);
+              const double* pw = s_W + mb * kMB * LDW + (8 * nh + (lane >> 2)) * LDW + (lane & 3);
 #pragma unroll
-            for (int u = 0; u < kSlabCols; u++) s_X[(m0 + kSlabCols * qg + u) * kSlab + r] = x[u];
+              for (int ks = 0; ks < 4; ks++) dmma884(x0, x1, pa[4 * ks * LDX], pw[4 * ks]);
+            }
+            __syncthreads();
+            pt[0] = x0; pt[LDX] = x1;
             __syncthreads();
           }
           for (int t = threadIdx.x; t < nb * kSlab; t += kCholThreads) {
             const int r2 = t % kSlab, q = t / kSlab;
-            if (r2 < nr) A[(size_t)(c + q) * F + r0 + r2] = s_X[q * kSlab + r2];
+            if (r2 < nr) A[(size_t)(c + q) * F + r0 + r2] = s_X[q * LDX + r2];
           }
           __syncthreads();
         }
@@ -633,22 +721,56 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
       LVS_PH(1)
       team_sync<TEAM>(bar, target, team_size);
       LVS_PH(2)
-      // the factored diagonal block goes back to the front only now: before the barrier other CTAs may still be reading the
-      // unfactored block for their own copy of (A); nothing in (C) touches it
-      if (rank == 0)
-        for (int t = threadIdx.x; t < nb * nb; t += kCholThreads) {
-          const int j = t / nb, i = t % nb;
-          if (i >= j) A[(size_t)(c + j) * F + c + i] = s_D[i * LDD + j];
-        }
-      __syncthreads();                            // s_D / s_X are dead from here on: phase C reuses the memory
       // (C) A[i, j] -= sum_q L[i, c+q] L[j, c+q] for c + nb <= j <= i (block-lower part), TILE x TILE outputs per pass on the tensor
       // cores.  Warp (wm, wn) of the 4 x 2 grid owns TM x TN m8n8 tiles; per k-step of 4 it loads TM + TN fragments for TM * TN DMMAs.
+      // Team, and another panel follows: rank 0 takes the next diagonal block (tile 0 when that panel is a full one) and factors it while
+      // the other CTAs share the rest of the update.
       const int base = c + nb, rem = F - base;
       const int nt = (rem + TILE - 1) / TILE;
       const int ntiles = nt * (nt + 1) / 2;
       const int nbk = (nb + 3) & ~3;
       const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
-      for (int tile = rank; tile < ntiles; tile += team_size) {
+      const bool has_next = TEAM && base < p;
+      const int nbn = has_next ? min(NB, p - base) : 0;
+      const bool fused_head = has_next && nbn == NB;          // rank 0 updates the next diagonal block in shared memory and factors it from there
+      // tiles of this CTA: everything round-robin, unless a panel follows - then rank 0 has the next diagonal block (nothing else when it
+      // updates that block in shared memory, tile 0 otherwise) and the others share tiles 1, 2, ...
+      int tile_first = rank, tile_step = team_size;
+      if (has_next) {
+        tile_first = (rank == 0) ? (fused_head ? ntiles : 0) : rank;
+        tile_step = (rank == 0) ? ntiles : team_size - 1;
+      }
+      if (has_next && fused_head && rank == 0) {
+        // the next diagonal block S and the NB panel rows X that update it: S -= X X^T on the lower 8 x 8 tiles, spread over the warps
+        double* s_H = s_dyn + Cfg::oX;                        // [nbk][LDL]: X[base + r][c + k] at k * LDL + r  (fits: oX + NB * LDL doubles of the phase C area)
+        stage_diag<TEAM>(A, F, base, NB, s_D);
+        for (int t = threadIdx.x; t < nbk * NB; t += kCholThreads) {
+          const int r = t % NB, q = t / NB, qc = min(q, nb - 1);
+          cp_async8(s_H + q * LDL + r, A + (size_t)(c + qc) * F + base + r, q < nb ? 8 : 0);
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        constexpr int NT8 = NB / 8, NTL = NT8 * (NT8 + 1) / 2;
+        for (int t = warp; t < NTL; t += kCholThreads / 32) {
+          int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+          while (ti * (ti + 1) / 2 > t) ti--;
+          while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+          const int tj = t - ti * (ti + 1) / 2;
+          const double* pa = s_H + (lane & 3) * LDL + 8 * ti + (lane >> 2);
+          const double* pb = s_H + (lane & 3) * LDL + 8 * tj + (lane >> 2);
+          double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
+          for (int k0 = 0; k0 < nbk; k0 += 8) {
+            dmma884(u0, u1, pa[k0 * LDL], pb[k0 * LDL]);
+            if (k0 + 4 < nbk) dmma884(v0, v1, pa[(k0 + 4) * LDL], pb[(k0 + 4) * LDL]);
+          }
+          double* pc = s_D + (8 * ti + (lane >> 2)) * LDD + 8 * tj + 2 * (lane & 3);
+          pc[0] -= u0 + v0; pc[1] -= u1 + v1;
+        }
+        __syncthreads();
+        factor_core<TEAM>(NB, s_D, s_W, s_il, V.fail_flag, s_mbar, mb_uses);
+        writeback_diag<TEAM>(A, F, base, NB, s_D, s_W, wscr);
+      }
+      for (int tile = tile_first; tile < ntiles; tile += tile_step) {
         int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
         while (ti * (ti + 1) / 2 > tile) ti--;
         while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
@@ -713,11 +835,18 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
             }
         __syncthreads();
       }
+      if (has_next && !fused_head && rank == 0) {
+        // the (partial) last panel's diagonal block: tile 0 above has brought it up to date
+        stage_diag<TEAM>(A, F, base, nbn, s_D);
+        __syncthreads();
+        factor_core<TEAM>(nbn, s_D, s_W, s_il, V.fail_flag, s_mbar, mb_uses);
+        writeback_diag<TEAM>(A, F, base, nbn, s_D, s_W, wscr);
+      }
       LVS_PH(3)
       team_sync<TEAM>(bar, target, team_size);
       LVS_PH(4)
     }
-    if (dbg) { for (int k = 0; k < 6; k++) V.dbg[k] = tph[k]; V.dbg[6] = F; V.dbg[7] = team_size; }
+    if (dbg) { for (int k = 0; k < 6; k++) V.dbg[8 * rank + k] = tph[k]; V.dbg[8 * rank + 6] = F; V.dbg[8 * rank + 7] = team_size; }
 #undef LVS_PH
     if (in_smem) {
       for (int t = threadIdx.x; t < F * F; t += kCholThreads) A_global[t] = s_front[t];
@@ -980,6 +1109,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     C.allocs.push_back((void*)C.bars);
     CUDA_TRY(cudaMalloc((void**)&C.back_scratch, (size_t)C.coop_grid * 2 * kBNB * sizeof(double)));
     C.allocs.push_back((void*)C.back_scratch);
+    CUDA_TRY(cudaMalloc((void**)&C.wscratch, (size_t)C.coop_grid * FrontCfg<true>::WSCR * sizeof(double)));
+    C.allocs.push_back((void*)C.wscratch);
   }
   C.arena_doubles = S.arena;
   cudaError_t e = cudaMalloc((void**)&C.arena, std::max<long long>(1, S.arena) * sizeof(double));
@@ -990,7 +1121,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
   CUDA_TRY(cudaMalloc((void**)&C.fail_flag, sizeof(int)));
   C.allocs.push_back((void*)C.fail_flag);
   if (getenv("LVS_DEBUG_TIMING")) {
-    CUDA_TRY(cudaMallocManaged((void**)&C.dbg, 8 * sizeof(long long)));
+    CUDA_TRY(cudaMallocManaged((void**)&C.dbg, 16 * sizeof(long long)));
+    memset(C.dbg, 0, 16 * sizeof(long long));
     C.allocs.push_back((void*)C.dbg);
   }
   const size_t smem = (size_t)S.max_front * sizeof(double);
@@ -1014,7 +1146,7 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   V.fronts = C.fronts; V.rows = C.rows; V.rel = C.rel; V.child_idx = C.child_idx; V.level_fronts = C.level_fronts; V.perm = C.perm;
   V.diag_dst = C.diag_dst; V.off_dst = C.off_dst; V.rhs_dst = C.rhs_dst; V.diag_ld = C.diag_ld; V.off_ld = C.off_ld; V.off_tr = C.off_tr;
   V.arena = C.arena; V.xp = C.xp; V.fail_flag = C.fail_flag; V.n = C.n; V.n_off = C.n_off;
-  V.dbg = C.dbg;
+  V.dbg = C.dbg; V.wscratch = C.wscratch;
   CUDA_TRY(cudaMemsetAsync(C.arena, 0, (size_t)C.arena_doubles * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(C.fail_flag, 0, sizeof(int), st));
   const long long total = (long long)C.n * 36 + (long long)C.n_off * 36 + (long long)C.n * 6;
@@ -1070,8 +1202,10 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   nl++;
   if (C.dbg) {
     cudaStreamSynchronize(st);
-    fprintf(stderr, "[chol dbg] last team front F=%lld team=%lld: A %.1f us, B %.1f us, barrier1 %.1f us, writeback+C %.1f us, barrier2 %.1f us, other %.1f us\n", C.dbg[6], C.dbg[7],
-            C.dbg[0] / 1965.0, C.dbg[1] / 1965.0, C.dbg[2] / 1965.0, C.dbg[3] / 1965.0, C.dbg[4] / 1965.0, C.dbg[5] / 1965.0);
+    for (int r = 0; r < 2; r++)
+      fprintf(stderr, "[chol dbg] last team front F=%lld team=%lld rank %d: diag %.1f us, B %.1f us, barrier1 %.1f us, C (rank 0: next diagonal block) %.1f us, barrier2 %.1f us, other %.1f us\n",
+              C.dbg[8 * r + 6], C.dbg[8 * r + 7], r, C.dbg[8 * r + 0] / 1965.0, C.dbg[8 * r + 1] / 1965.0, C.dbg[8 * r + 2] / 1965.0, C.dbg[8 * r + 3] / 1965.0, C.dbg[8 * r + 4] / 1965.0,
+              C.dbg[8 * r + 5] / 1965.0);
   }
   CUDA_TRY(cudaGetLastError());
   if (launches) *launches += nl;

@@ -64,6 +64,7 @@ struct CholDevice {
   std::vector<int> small_ptr, big_ptr;
   unsigned int* bars = nullptr;            // team barrier counters
   double* back_scratch = nullptr;          // partial sums of the team backward substitution: [coop_grid][2][32]
+  double* wscratch = nullptr;              // per team: inverses of the current panel's micro blocks (rank 0 publishes them)
   int coop_grid = 0;                       // CTAs of a cooperative launch (all co-resident)
   std::vector<void*> allocs;
 };
