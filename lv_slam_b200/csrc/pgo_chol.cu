@@ -939,18 +939,20 @@ __global__ void __launch_bounds__(kCholThreads) chol_backward_kernel(CholView V,
 // rows (coalesced: a column of the front is contiguous), the partial sums meet in global memory (one team barrier per panel, double
 // buffered), and every CTA adds them in the same fixed order and solves the 32 x 32 triangle itself - identical bits everywhere, no
 // broadcast needed.
-constexpr int kBNB = 32;
+constexpr int kBNB = 96;                // pivot columns per panel: one team barrier each (with 32 the barriers were most of a large front's time)
+constexpr int kBSlots = kBNB / 32;      // rows of the panel's triangle per lane of the solving warp
 __global__ void __launch_bounds__(kCholThreads, 1) chol_backward_team_kernel(CholView V, const int* __restrict__ list, int n_list, int team_size,
-                                                                             unsigned int* __restrict__ bars, double* __restrict__ scratch) {
-  extern __shared__ double s_dyn[];                 // xs[F - 1]
-  __shared__ double s_T[kBNB][kBNB + 1], s_rhs[kBNB];
+                                                                             unsigned int* __restrict__ bars, double* __restrict__ scratch, int max_chunks) {
+  extern __shared__ double s_dyn[];                 // s_T[kBNB][kBNB + 1] (the panel's triangle), then xs[F - 1]
+  __shared__ double s_rhs[kBNB];
+  double (*s_T)[kBNB + 1] = reinterpret_cast<double (*)[kBNB + 1]>(s_dyn);
   const int team = blockIdx.x / team_size, rank = blockIdx.x % team_size, n_teams = gridDim.x / team_size;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kW = kCholThreads / 32;
   unsigned int* bar = bars + team;
   unsigned int target = 0;
-  double* xs = s_dyn;
-  double* part = scratch + (size_t)team * team_size * 2 * kBNB;      // [2 parity][team_size][kBNB]
+  double* xs = s_dyn + kBNB * (kBNB + 1);
+  double* part = scratch + (size_t)team * 2 * kBNB * max_chunks;     // [2 parity][kBNB][max_chunks]
   for (int fi = team; fi < n_list; fi += n_teams) {
     const CholFront f = V.fronts[list[fi]];
     const double* __restrict__ A = V.arena + f.off;
@@ -980,24 +982,25 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_backward_team_kernel(Cho
     const int n_panels = (p + kBNB - 1) / kBNB;
     for (int pi = n_panels - 1; pi >= 0; pi--) {
       const int c = pi * kBNB, nb = min(kBNB, p - c);
-      double* mine = part + ((size_t)(pi & 1) * team_size + rank) * kBNB;
-      // (a) partial[q] = sum over this CTA's rows i of L[i][c + q] xs[i], i in the part of (c + nb, p) it owns
-      const int later = p - (c + nb);
-      const int i_lo = c + nb + (int)((long long)later * rank / team_size), i_hi = c + nb + (int)((long long)later * (rank + 1) / team_size);
-      for (int q = warp; q < kBNB; q += kW) {
+      // (a) partial[q][chunk] = sum over a chunk of 256 later rows i of L[i][c + q] xs[i]: the (column, chunk) items are dealt to the
+      // team's warps round-robin, one pass of eight coalesced loads per lane each (a warp that walked a whole column chunk after chunk
+      // had one pass of loads in flight at a time: the kernel was bound by that latency, not by the barrier)
+      double* mine = part + (size_t)(pi & 1) * kBNB * max_chunks;
+      const int later = p - (c + nb), n_chunks = (later + 255) / 256;
+      for (int item = rank * kW + warp; item < kBNB * n_chunks; item += team_size * kW) {
+        const int q = item % kBNB, ch = item / kBNB;
         double acc = 0.0;
         if (q < nb) {
           const double* __restrict__ col = A + (size_t)(c + q) * F;
-          for (int i0 = i_lo + lane; i0 < i_hi; i0 += 32 * 8) {
-            double v[8];
+          const int i0 = c + nb + 256 * ch + lane;
+          double v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = __ldcg(col + min(i0 + 32 * u, i_hi - 1));
+          for (int u = 0; u < 8; u++) v[u] = __ldcg(col + min(i0 + 32 * u, p - 1));
 #pragma unroll
-            for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u; acc += (i < i_hi) ? v[u] * xs[i] : 0.0; }
-          }
+          for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u; acc += (i < p) ? v[u] * xs[i] : 0.0; }
           for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         }
-        if (lane == 0) mine[q] = acc;
+        if (lane == 0) mine[q * max_chunks + ch] = acc;
       }
       // the panel's triangle, while the partial sums of the other CTAs arrive
       for (int t = threadIdx.x; t < kBNB * kBNB; t += kCholThreads) {
@@ -1006,34 +1009,46 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_backward_team_kernel(Cho
         s_T[i][j] = (i < nb && j <= i) ? v : (i == j ? 1.0 : 0.0);
       }
       team_sync<true>(bar, target, team_size);
-      // (b) rhs = xs[panel] - sum of the partials, CTA by CTA in rank order
+      // (b) rhs = xs[panel] - sum of the partials in chunk order
       if (threadIdx.x < kBNB) {
         const int q = threadIdx.x;
-        const double* src = part + (size_t)(pi & 1) * team_size * kBNB + q;
+        const double* src = mine + q * max_chunks;
         double ssum = 0.0;
-        for (int r0 = 0; r0 < team_size; r0 += 8) {
+        for (int r0 = 0; r0 < n_chunks; r0 += 8) {
           double v[8];
 #pragma unroll
-          for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (size_t)min(r0 + u, team_size - 1) * kBNB);
+          for (int u = 0; u < 8; u++) v[u] = __ldcg(src + min(r0 + u, n_chunks - 1));
 #pragma unroll
-          for (int u = 0; u < 8; u++) ssum += (r0 + u < team_size) ? v[u] : 0.0;
+          for (int u = 0; u < 8; u++) ssum += (r0 + u < n_chunks) ? v[u] : 0.0;
         }
         s_rhs[q] = (q < nb) ? xs[c + q] - ssum : 0.0;
       }
       __syncthreads();
-      // (c) L_D^T x = rhs by warp 0: lane m accumulates its own row's sum as the x_i appear
+      // (c) L_D^T x = rhs by warp 0: lane m keeps rows m, m + 32, m + 64 of the triangle and subtracts every x_j from their running
+      // right-hand sides as it appears; the dependent chain per column is multiply -> shuffle -> multiply-add
       if (warp == 0) {
-        const int m = lane;
-        const bool on = m < nb;
-        const double rhs = s_rhs[m];
-        const double inv = on ? 1.0 / s_T[m][m] : 0.0;
-        double acc = 0.0, mineX = 0.0;
-        for (int j = nb - 1; j >= 0; j--) {
-          const double xj = __shfl_sync(0xffffffffu, (rhs - acc) * inv, j);
-          if (m == j) mineX = xj;
-          if (m < j) acc += s_T[j][m] * xj;
+        double run[kBSlots], inv[kBSlots];
+#pragma unroll
+        for (int sl = 0; sl < kBSlots; sl++) {
+          const int r = lane + 32 * sl;
+          run[sl] = s_rhs[r];
+          inv[sl] = 1.0 / s_T[r][r];                               // 1 on the identity padding
         }
-        if (on) xs[c + m] = mineX;
+#pragma unroll
+        for (int sj = kBSlots - 1; sj >= 0; sj--) {
+#pragma unroll 8
+          for (int jl = 31; jl >= 0; jl--) {
+            const int j = 32 * sj + jl;                            // columns past nb: identity rows, zero right-hand side - harmless
+            double t[kBSlots];
+#pragma unroll
+            for (int sl = 0; sl <= sj; sl++) t[sl] = s_T[j][lane + 32 * sl];          // independent of x_j: issued ahead of the chain
+            const double xj = __shfl_sync(0xffffffffu, run[sj] * inv[sj], jl);
+            if (lane == jl && j < nb) xs[c + j] = xj;
+#pragma unroll
+            for (int sl = 0; sl <= sj; sl++)
+              if (lane + 32 * sl < j) run[sl] -= t[sl] * xj;
+          }
+        }
       }
       __syncthreads();
     }
@@ -1107,7 +1122,7 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     C.coop_grid = std::max(1, std::min(per_sm, 2) * sms);
     CUDA_TRY(cudaMalloc((void**)&C.bars, (size_t)C.coop_grid * sizeof(unsigned int)));
     C.allocs.push_back((void*)C.bars);
-    CUDA_TRY(cudaMalloc((void**)&C.back_scratch, (size_t)C.coop_grid * 2 * kBNB * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&C.back_scratch, (size_t)C.coop_grid * 2 * kBNB * ((S.max_front + 255) / 256) * sizeof(double)));      // [team][2 parity][kBNB][chunks of 256 rows]
     C.allocs.push_back((void*)C.back_scratch);
     CUDA_TRY(cudaMalloc((void**)&C.wscratch, (size_t)C.coop_grid * FrontCfg<true>::WSCR * sizeof(double)));
     C.allocs.push_back((void*)C.wscratch);
@@ -1126,10 +1141,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     C.allocs.push_back((void*)C.dbg);
   }
   const size_t smem = (size_t)S.max_front * sizeof(double);
-  if (smem > 48 * 1024) {
-    CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(chol_backward_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(chol_backward_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + kBNB * (kBNB + 1) * sizeof(double))));
   CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontCfg<false>::bytes));
   CUDA_TRY(cudaStreamSynchronize(st));    // the host vectors of S may go away
   return LVS_OK;
@@ -1181,15 +1194,16 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
     const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nbig = C.big_ptr[l + 1] - C.big_ptr[l];
     if (nbig > 0) {
       const int n_teams = std::min(nbig, C.coop_grid);
-      int team_size = std::max(1, std::min(C.coop_grid / n_teams, (C.level_big[l] + 255) / 256));
+      int team_size = std::max(1, std::min(C.coop_grid / n_teams, (C.level_big[l] + 63) / 64));
+      int max_chunks = (C.max_front + 255) / 256;
       const int* list = C.big_list + C.big_ptr[l];
       int n_list = nbig;
       if (team_size == 1) chol_backward_kernel<<<nbig, kCholThreads, smem, st>>>(V, list);
       else {
         int grid = n_teams * team_size;
         CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)n_teams * sizeof(unsigned int), st));
-        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars, (void*)&C.back_scratch};
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_backward_team_kernel, dim3(grid), dim3(kCholThreads), args, smem, st));
+        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars, (void*)&C.back_scratch, (void*)&max_chunks};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_backward_team_kernel, dim3(grid), dim3(kCholThreads), args, smem + kBNB * (kBNB + 1) * sizeof(double), st));
       }
       nl++;
     }
