@@ -1127,6 +1127,9 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     CUDA_TRY(cudaMalloc((void**)&C.wscratch, (size_t)C.coop_grid * FrontCfg<true>::WSCR * sizeof(double)));
     C.allocs.push_back((void*)C.wscratch);
   }
+  CUDA_TRY(cudaStreamCreateWithFlags(&C.side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&C.ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&C.ev_join, cudaEventDisableTiming));
   C.arena_doubles = S.arena;
   cudaError_t e = cudaMalloc((void**)&C.arena, std::max<long long>(1, S.arena) * sizeof(double));
   if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(LVS_ERR_OOM, "frontal arena allocation failed (%lld MB)", (long long)(S.arena * 8 >> 20)); }
@@ -1149,6 +1152,9 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
 }
 
 void chol_free(CholDevice& C) {
+  if (C.side) cudaStreamDestroy(C.side);
+  if (C.ev_fork) cudaEventDestroy(C.ev_fork);
+  if (C.ev_join) cudaEventDestroy(C.ev_join);
   for (void* p : C.allocs) cudaFree(p);
   C = CholDevice();
 }
@@ -1167,9 +1173,13 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   int nl = 1;
   for (int l = 0; l < C.n_levels; l++) {
     // small fronts: one CTA each; large fronts: teams of CTAs in one cooperative launch
+    // (a level that has both kinds runs them side by side: the fronts of a level are independent, a team launch rarely fills the GPU,
+    // and the few small fronts that sit high in the tree would otherwise add their whole latency to the critical path)
     const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nb = C.big_ptr[l + 1] - C.big_ptr[l];
+    const bool beside = ns > 0 && nb > 0;
+    if (beside) { CUDA_TRY(cudaEventRecord(C.ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(C.side, C.ev_fork, 0)); }
     if (ns > 0) {
-      chol_front_kernel<false><<<ns, kCholThreads, FrontCfg<false>::bytes, st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
+      chol_front_kernel<false><<<ns, kCholThreads, FrontCfg<false>::bytes, beside ? C.side : st>>>(V, C.small_list + C.small_ptr[l], ns, 1, C.bars);
       nl++;
     }
     if (nb > 0) {
@@ -1188,10 +1198,13 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
       }
       nl++;
     }
+    if (beside) { CUDA_TRY(cudaEventRecord(C.ev_join, C.side)); CUDA_TRY(cudaStreamWaitEvent(st, C.ev_join, 0)); }
   }
   const size_t smem = (size_t)C.max_front * sizeof(double);
   for (int l = C.n_levels - 1; l >= 0; l--) {
     const int ns = C.small_ptr[l + 1] - C.small_ptr[l], nbig = C.big_ptr[l + 1] - C.big_ptr[l];
+    const bool beside = ns > 0 && nbig > 0;
+    if (beside) { CUDA_TRY(cudaEventRecord(C.ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(C.side, C.ev_fork, 0)); }
     if (nbig > 0) {
       const int n_teams = std::min(nbig, C.coop_grid);
       int team_size = std::max(1, std::min(C.coop_grid / n_teams, (C.level_big[l] + 63) / 64));
@@ -1208,9 +1221,10 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
       nl++;
     }
     if (ns > 0) {
-      chol_backward_kernel<<<ns, kCholThreads, smem, st>>>(V, C.small_list + C.small_ptr[l]);
+      chol_backward_kernel<<<ns, kCholThreads, smem, beside ? C.side : st>>>(V, C.small_list + C.small_ptr[l]);
       nl++;
     }
+    if (beside) { CUDA_TRY(cudaEventRecord(C.ev_join, C.side)); CUDA_TRY(cudaStreamWaitEvent(st, C.ev_join, 0)); }
   }
   chol_finish_kernel<<<1, 1024, 0, st>>>(V, b, lambda, x, scale_out, ok_out);
   nl++;

@@ -66,6 +66,8 @@ struct CholDevice {
   double* back_scratch = nullptr;          // partial sums of the team backward substitution: [coop_grid][2][32]
   double* wscratch = nullptr;              // per team: inverses of the current panel's micro blocks (rank 0 publishes them)
   int coop_grid = 0;                       // CTAs of a cooperative launch (all co-resident)
+  cudaStream_t side = nullptr;             // the single-CTA fronts of a level run beside its team launch
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
 };
 
