@@ -270,6 +270,16 @@ int lvs_pgo_create(int solver, int device, void* stream, lvs_pgo_t** out);
 int lvs_pgo_destroy(lvs_pgo_t* h);
 int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const uint8_t* fixed, int n_edges, const int32_t* ij,
                       const double* meas7, const double* info21, const double* huber_delta);
+/* The same with the reference's unary priors on a VertexSE3 in the edge list (GPS / IMU constraints of the global-graph nodelet:
+ * GraphSLAM::add_se3_prior_{xy,xyz,quat,vec}_edge, src/global_graph/graph_slam.cpp:194-240; edge classes include/g2o/edge_se3_priorxy.hpp,
+ * edge_se3_priorxyz.hpp, edge_se3_priorquat.hpp, edge_se3_priorvec.hpp; numeric Jacobians as g2o's BaseUnaryEdge::linearizeOplus takes them).
+ * edge_type[k] (NULL: every edge is an EdgeSE3) is one of LVS_PGO_EDGE_*; for a prior, ij[2k] is the vertex (ij[2k+1] is ignored), the
+ * meas7 row carries  xy | xyz | qx qy qz qw | direction(3) measurement(3)  and the info21 row the D x D information matrix in the top-left
+ * corner of the 6 x 6 upper triangle (D = 2 for XY, 3 otherwise; the other entries must be zero).  Edges keep their order in the list, which is
+ * g2o's active-edge order (ascending edge id). */
+enum { LVS_PGO_EDGE_SE3 = 0, LVS_PGO_EDGE_PRIOR_XY = 1, LVS_PGO_EDGE_PRIOR_XYZ = 2, LVS_PGO_EDGE_PRIOR_QUAT = 3, LVS_PGO_EDGE_PRIOR_VEC = 4 };
+int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, const uint8_t* fixed, int n_edges, const int32_t* ij,
+                            const double* meas7, const double* info21, const double* huber_delta, const int32_t* edge_type);
 int lvs_pgo_set_poses(lvs_pgo_t* h, const double* poses7);          /* VertexSE3::setEstimate for every vertex */
 int lvs_pgo_optimize(lvs_pgo_t* h, int max_iterations, lvs_pgo_stats* stats);
 int lvs_pgo_get_poses(lvs_pgo_t* h, double* poses7);                /* VertexSE3::estimate() of every vertex */

@@ -51,6 +51,8 @@ struct PgoDev {
   const Rt* Z; const Rt* Zinv;
   const double* info; const double* huber;
   const unsigned char* edge_tr;
+  const int* edge_type;         // null: every edge is an EdgeSE3; else 0 EdgeSE3, 1-4 unary priors (vertex i == j)
+  const double* pm;             // [ne][6] measurements of the unary priors (edge_type != null)
   double* ws; double* err; double* chi;
   const int* vptr; const int* vinc;     // block row -> (edge * 2 + role) ascending
   const int* optr; const int* oinc;     // off block -> edges ascending
@@ -68,7 +70,9 @@ __global__ void __launch_bounds__(kPgoThreads) pgo_errors_kernel(PgoDev D) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D.ne; k += gridDim.x * blockDim.x) {
     const int2 ij = D.edge_ij[k];
     double e[6];
-    edge_error(D.Zinv[k], D.pose[ij.x], D.pose[ij.y], e);
+    const int ty = D.edge_type ? D.edge_type[k] : 0;
+    if (ty) prior_error(ty, D.pm + (size_t)k * 6, D.pose[ij.x], e);
+    else edge_error(D.Zinv[k], D.pose[ij.x], D.pose[ij.y], e);
     const double c = chi2_of(D.info + (size_t)k * 36, e);
 #pragma unroll
     for (int a = 0; a < 6; a++) D.err[(size_t)k * 6 + a] = e[a];
@@ -109,7 +113,9 @@ __global__ void __launch_bounds__(128) pgo_linearize_kernel(PgoDev D) {
   double* ws = D.ws + (size_t)k * kEdgeWs;
   if (h.x < 0 && h.y < 0) return;
   double A[36], B[36];
-  edge_gradient(D.Z[k], D.pose[ij.x], D.pose[ij.y], A, B);
+  const int ty = D.edge_type ? D.edge_type[k] : 0;
+  if (ty) prior_jacobian(ty, D.pm + (size_t)k * 6, D.pose[ij.x], A);      // unary: only the (i, i) block and b_i exist
+  else edge_gradient(D.Z[k], D.pose[ij.x], D.pose[ij.y], A, B);
   const double* info = D.info + (size_t)k * 36;
   double e[6];
 #pragma unroll
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(128) pgo_linearize_kernel(PgoDev D) {
       ws[108 + r] = s;
     }
   }
-  if (h.y >= 0) {
+  if (h.y >= 0 && !ty) {
     atwb(B, W, B, C);
 #pragma unroll
     for (int a = 0; a < 36; a++) ws[36 + a] = C[a];
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(128) pgo_linearize_kernel(PgoDev D) {
       ws[114 + r] = s;
     }
   }
-  if (h.x >= 0 && h.y >= 0 && h.x != h.y) {
+  if (h.x >= 0 && h.y >= 0 && h.x != h.y && !ty) {
     if (D.edge_tr[k]) atwb(B, W, A, C); else atwb(A, W, B, C);   // block (min, max): transposed when the edge runs high -> low
 #pragma unroll
     for (int a = 0; a < 36; a++) ws[72 + a] = C[a];
@@ -343,10 +349,13 @@ __global__ void pgo_unpack_poses_kernel(const Rt* __restrict__ in, int n, double
   if (v < n) rt_to_qt7(in[v], p7 + (size_t)v * 7);
 }
 __global__ void pgo_pack_edges_kernel(const double* __restrict__ m7, const double* __restrict__ info21, int n, Rt* __restrict__ Z, Rt* __restrict__ Zinv,
-                                      double* __restrict__ info) {
+                                      double* __restrict__ info, const int* __restrict__ edge_type, double* __restrict__ pm) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const Rt z = rt_from_qt7(m7 + (size_t)k * 7);
+  const int ty = edge_type ? edge_type[k] : 0;
+  const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+  if (ty) prior_set_measurement(ty, m7 + (size_t)k * 7, pm + (size_t)k * 6);
+  const Rt z = rt_from_qt7(ty ? ident : m7 + (size_t)k * 7);
   Z[k] = z; Zinv[k] = rt_inv(z);
   const double* u = info21 + (size_t)k * 21;
   int p = 0;
@@ -498,7 +507,23 @@ int lvs_pgo_destroy(lvs_pgo_t* h) {
 
 int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const uint8_t* fixed, int n_edges, const int32_t* ij, const double* meas7,
                       const double* info21, const double* huber_delta) {
+  return lvs_pgo_set_graph_typed(h, n_vertices, poses7, fixed, n_edges, ij, meas7, info21, huber_delta, nullptr);
+}
+
+int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, const uint8_t* fixed, int n_edges, const int32_t* ij_in, const double* meas7,
+                            const double* info21, const double* huber_delta, const int32_t* edge_type) {
   if (!h) return fail(LVS_ERR_INVALID_ARG, "handle is NULL");
+  const int32_t* ij = ij_in;
+  std::vector<int32_t> ij_fixed;
+  if (edge_type && n_edges > 0 && ij_in) {
+    // a unary prior is carried as a self-edge (i, i): no off-diagonal block, one incidence on vertex i
+    ij_fixed.assign(ij_in, ij_in + (size_t)n_edges * 2);
+    for (int k = 0; k < n_edges; k++) {
+      if (edge_type[k] < LVS_PGO_EDGE_SE3 || edge_type[k] > LVS_PGO_EDGE_PRIOR_VEC) return fail(LVS_ERR_INVALID_ARG, "edge %d has unknown kind %d", k, edge_type[k]);
+      if (edge_type[k] != LVS_PGO_EDGE_SE3) ij_fixed[2 * k + 1] = ij_fixed[2 * k];
+    }
+    ij = ij_fixed.data();
+  }
   if (n_vertices < 0 || n_edges < 0 || (n_vertices > 0 && !poses7) || (n_edges > 0 && (!ij || !meas7 || !info21)))
     return fail(LVS_ERR_INVALID_ARG, "NULL argument");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -578,7 +603,8 @@ int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const 
   D.hidx = d_hidx; D.free_vertex = d_free; D.vptr = d_vptr; D.vinc = d_vinc; D.optr = d_optr; D.oinc = d_oinc;
   D.rptr = d_rptr; D.rcol = d_rcol; D.rslot = d_rslot; D.edge_ij = d_eij; D.edge_h = d_eh; D.edge_tr = d_tr;
   Rt *d_Z, *d_Zinv;
-  double *d_info, *d_huber, *d_stage_p = nullptr, *d_stage_m = nullptr, *d_stage_i = nullptr;
+  double *d_info, *d_huber, *d_stage_p = nullptr, *d_stage_m = nullptr, *d_stage_i = nullptr, *d_pm = nullptr;
+  int* d_type = nullptr;
   std::vector<double> hub(ne, 0.0);
   if (huber_delta) for (int k = 0; k < ne; k++) hub[k] = huber_delta[k];
   if ((rc = dev_alloc(h, &D.pose, nv)) || (rc = dev_alloc(h, &D.pose_bak, nv)) || (rc = dev_alloc(h, &d_Z, ne)) || (rc = dev_alloc(h, &d_Zinv, ne)) ||
@@ -589,7 +615,11 @@ int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const 
       (rc = dev_alloc(h, &D.q, (size_t)nfree * 6)) || (rc = dev_alloc(h, &D.s, (size_t)nfree * 6)) || (rc = dev_alloc(h, &D.q2, (size_t)nfree * 6)) || (rc = dev_alloc(h, &D.partials, 2 * kMaxPartials)) ||
       (rc = dev_alloc(h, &D.ticket, 4)) || (rc = dev_alloc(h, &D.sc, 1)) || (rc = dev_alloc(h, &d_stage_p, (size_t)nv * 7)) ||
       (rc = dev_alloc(h, &d_stage_m, (size_t)ne * 7)) || (rc = dev_alloc(h, &d_stage_i, (size_t)ne * 21))) { free_graph(h); return rc; }
-  D.Z = d_Z; D.Zinv = d_Zinv; D.info = d_info; D.huber = d_huber;
+  if (edge_type) {
+    std::vector<int> ty(edge_type, edge_type + ne);
+    if ((rc = dev_upload(h, &d_type, ty)) || (rc = dev_alloc(h, &d_pm, (size_t)ne * 6))) { free_graph(h); return rc; }
+  }
+  D.Z = d_Z; D.Zinv = d_Zinv; D.info = d_info; D.huber = d_huber; D.edge_type = d_type; D.pm = d_pm;
   CUDA_TRY(cudaMemsetAsync(D.ticket, 0, 4 * sizeof(unsigned int), h->st));
   CUDA_TRY(cudaMemsetAsync(D.sc, 0, sizeof(PgoScalars), h->st));
   CUDA_TRY(cudaMemsetAsync(D.ws, 0, (size_t)std::max(ne, 1) * kEdgeWs * sizeof(double), h->st));
@@ -601,7 +631,7 @@ int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const 
   if (ne) {
     CUDA_TRY(cudaMemcpyAsync(d_stage_m, meas7, (size_t)ne * 7 * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CUDA_TRY(cudaMemcpyAsync(d_stage_i, info21, (size_t)ne * 21 * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    pgo_pack_edges_kernel<<<blocks_for(ne), kPgoThreads, 0, h->st>>>(d_stage_m, d_stage_i, ne, d_Z, d_Zinv, d_info);
+    pgo_pack_edges_kernel<<<blocks_for(ne), kPgoThreads, 0, h->st>>>(d_stage_m, d_stage_i, ne, d_Z, d_Zinv, d_info, d_type, d_pm);
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));

@@ -77,6 +77,63 @@ LVS_HD Rt rt_from_vector_mqt(const double* v) {
 // e = toVectorMQT(Z^-1 * Xi^-1 * Xj)
 LVS_HD void edge_error(const Rt& Zinv, const Rt& Xi, const Rt& Xj, double* e) { rt_to_vector_mqt(rt_mul(rt_mul(Zinv, rt_inv(Xi)), Xj), e); }
 
+// ---- unary priors on a VertexSE3 (the reference's own edge types, include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp; edge kinds
+// LVS_PGO_EDGE_PRIOR_* of include/lvslam_b200.h).  Errors are zero-padded to 6 so that the 6-vector / 6 x 6 code of the binary edge is reused.
+// setMeasurement: PriorQuat keeps w >= 0 (edge_se3_priorquat.hpp:52-57), PriorVec normalises direction and measurement
+// (edge_se3_priorvec.hpp:50-53).  m = xy | xyz | qx qy qz qw | direction(3) measurement(3).
+LVS_HD void prior_set_measurement(int type, const double* m, double* pm) {
+  for (int a = 0; a < 6; a++) pm[a] = 0.0;
+  if (type == 1) { pm[0] = m[0]; pm[1] = m[1]; }
+  else if (type == 2) { pm[0] = m[0]; pm[1] = m[1]; pm[2] = m[2]; }
+  else if (type == 3) { const double sg = m[3] < 0.0 ? -1.0 : 1.0; for (int a = 0; a < 4; a++) pm[a] = sg * m[a]; }
+  else if (type == 4) {
+    for (int h = 0; h < 2; h++) {
+      const double* v = m + 3 * h;
+      const double n = sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+      for (int a = 0; a < 3; a++) pm[3 * h + a] = v[a] / n;
+    }
+  }
+}
+
+// computeError (edge_se3_priorxy.hpp:41-46, priorxyz:41-46, priorquat:41-50, priorvec:41-50)
+LVS_HD void prior_error(int type, const double* pm, const Rt& X, double* e) {
+#pragma unroll
+  for (int a = 0; a < 6; a++) e[a] = 0.0;
+  if (type == 1) { e[0] = X.t[0] - pm[0]; e[1] = X.t[1] - pm[1]; }
+  else if (type == 2) { e[0] = X.t[0] - pm[0]; e[1] = X.t[1] - pm[1]; e[2] = X.t[2] - pm[2]; }
+  else if (type == 3) {
+    Q4 q = quat_from_mat(X.R);                                 // Eigen::Quaterniond(linear()), not normalised
+    const double dot = ((pm[0] * q.x + pm[1] * q.y) + pm[2] * q.z) + pm[3] * q.w;
+    const double sg = dot < 0.0 ? -1.0 : 1.0;
+    e[0] = sg * q.x - pm[0]; e[1] = sg * q.y - pm[1]; e[2] = sg * q.z - pm[2];
+  } else if (type == 4) {
+    // linear().inverse() * direction: Eigen's 3 x 3 inverse (cofactors over the determinant), not the transpose
+    const double* m = X.R;
+    double cof[9];
+    cof[0] = m[4] * m[8] - m[5] * m[7]; cof[1] = m[5] * m[6] - m[3] * m[8]; cof[2] = m[3] * m[7] - m[4] * m[6];
+    cof[3] = m[2] * m[7] - m[1] * m[8]; cof[4] = m[0] * m[8] - m[2] * m[6]; cof[5] = m[1] * m[6] - m[0] * m[7];
+    cof[6] = m[1] * m[5] - m[2] * m[4]; cof[7] = m[2] * m[3] - m[0] * m[5]; cof[8] = m[0] * m[4] - m[1] * m[3];
+    const double det = (m[0] * cof[0] + m[1] * cof[1]) + m[2] * cof[2];
+    const double id = 1.0 / det;
+#pragma unroll
+    for (int r = 0; r < 3; r++) e[r] = (((cof[r] * id) * pm[0] + (cof[3 + r] * id) * pm[1]) + (cof[6 + r] * id) * pm[2]) - pm[3 + r];
+  }
+}
+
+// BaseUnaryEdge::linearizeOplus (g2o core/base_unary_edge.hpp): central differences with delta = 1e-9 through VertexSE3::oplus.
+// J row-major 6 x 6, rows past the edge's dimension zero.
+LVS_HD void prior_jacobian(int type, const double* pm, const Rt& X, double* J) {
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (int d = 0; d < 6; d++) {
+    double add[6] = {0, 0, 0, 0, 0, 0}, e1[6], e2[6];
+    add[d] = delta;
+    prior_error(type, pm, rt_mul(X, rt_from_vector_mqt(add)), e1);
+    add[d] = -delta;
+    prior_error(type, pm, rt_mul(X, rt_from_vector_mqt(add)), e2);
+    for (int r = 0; r < 6; r++) J[r * 6 + d] = scalar * (e1[r] - e2[r]);
+  }
+}
+
 LVS_HD double chi2_of(const double* info /*6x6*/, const double* e) {
   double s = 0;
 #pragma unroll

@@ -46,6 +46,30 @@ class EdgeSE3:
         self.kernel = None          # (type, delta)
 
 
+# unary priors on a VertexSE3 (include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp): kind -> (LVS_PGO_EDGE_* code, g2o tag, measurement length)
+EDGE_SE3, PRIOR_XY, PRIOR_XYZ, PRIOR_QUAT, PRIOR_VEC = 0, 1, 2, 3, 4
+_PRIOR_TAGS = {PRIOR_XY: ("EDGE_SE3_PRIORXY", 2, 2), PRIOR_XYZ: ("EDGE_SE3_PRIORXYZ", 3, 3), PRIOR_QUAT: ("EDGE_SE3_PRIORQUAT", 4, 3),
+               PRIOR_VEC: ("EDGE_SE3_PRIORVEC", 6, 3)}
+
+
+class EdgeSE3Prior:
+    """One of EdgeSE3PriorXY / XYZ / Quat / Vec.  measurement: xy | xyz | (qx, qy, qz, qw) | direction(3) + measurement(3), stored as
+    the edge's setMeasurement leaves it (PriorQuat: w >= 0; PriorVec: both halves normalised)."""
+
+    def __init__(self, kind, v, measurement, information):
+        self.kind = kind
+        self.vertices = [v, v]
+        m = np.array(measurement, dtype=np.float64).ravel()
+        if kind == PRIOR_QUAT and m[3] < 0:
+            m = -m
+        if kind == PRIOR_VEC:
+            m = np.concatenate([m[:3] / np.linalg.norm(m[:3]), m[3:] / np.linalg.norm(m[3:])])
+        self.measurement = m
+        d = _PRIOR_TAGS[kind][2]
+        self.information = np.array(information, dtype=np.float64).reshape(d, d)
+        self.kernel = None
+
+
 class GraphSLAM:
     def __init__(self, solver_type="lm_var", device=0):
         if solver_type not in _SOLVERS:
@@ -100,6 +124,27 @@ class GraphSLAM:
         self._edges.append(e)
         return e
 
+    # GPS / IMU priors of the global-graph nodelet (graph_slam.cpp:194-240; global_graph_nodelet.cpp:420-427, 534-541)
+    def add_se3_prior_xy_edge(self, v_se3, xy, information_matrix):
+        e = EdgeSE3Prior(PRIOR_XY, v_se3, xy, information_matrix)
+        self._edges.append(e)
+        return e
+
+    def add_se3_prior_xyz_edge(self, v_se3, xyz, information_matrix):
+        e = EdgeSE3Prior(PRIOR_XYZ, v_se3, xyz, information_matrix)
+        self._edges.append(e)
+        return e
+
+    def add_se3_prior_quat_edge(self, v_se3, quat_xyzw, information_matrix):
+        e = EdgeSE3Prior(PRIOR_QUAT, v_se3, quat_xyzw, information_matrix)
+        self._edges.append(e)
+        return e
+
+    def add_se3_prior_vec_edge(self, v_se3, direction, measurement, information_matrix):
+        e = EdgeSE3Prior(PRIOR_VEC, v_se3, np.concatenate([np.asarray(direction, float), np.asarray(measurement, float)]), information_matrix)
+        self._edges.append(e)
+        return e
+
     def add_robust_kernel(self, edge, kernel_type, kernel_size):
         if kernel_type == "NONE":
             return
@@ -117,17 +162,33 @@ class GraphSLAM:
         # rows of the pose array are positions in the vertex list, NOT vertex ids: a loaded g2o file may skip ids (plane / GPS nodes)
         row = {v._id: k for k, v in enumerate(self._vertices)}
         ij = np.fromiter((row[x] for e in self._edges for x in (e.vertices[0]._id, e.vertices[1]._id)), dtype=np.int32, count=2 * ne).reshape(ne, 2)
-        meas = _pg.pose7_batch(np.stack([e.measurement for e in self._edges])) if ne else np.zeros((0, 7))
         iu = np.triu_indices(6)
-        info = np.stack([e.information for e in self._edges])[:, iu[0], iu[1]] if ne else np.zeros((0, 21))
+        types = np.fromiter((getattr(e, "kind", EDGE_SE3) for e in self._edges), dtype=np.int32, count=ne)
+        if not types.any():
+            meas = _pg.pose7_batch(np.stack([e.measurement for e in self._edges])) if ne else np.zeros((0, 7))
+            info = np.stack([e.information for e in self._edges])[:, iu[0], iu[1]] if ne else np.zeros((0, 21))
+            types = None
+        else:
+            meas, info6 = np.zeros((ne, 7)), np.zeros((ne, 6, 6))
+            binary = np.flatnonzero(types == EDGE_SE3)
+            if len(binary):
+                meas[binary] = _pg.pose7_batch(np.stack([self._edges[k].measurement for k in binary]))
+            for k, e in enumerate(self._edges):
+                if types[k] == EDGE_SE3:
+                    info6[k] = e.information
+                else:
+                    meas[k, :len(e.measurement)] = e.measurement
+                    d = e.information.shape[0]
+                    info6[k, :d, :d] = e.information
+            info = info6[:, iu[0], iu[1]]
         hub = np.fromiter((e.kernel[1] if e.kernel else 0.0 for e in self._edges), dtype=np.float64, count=ne)
-        return poses, fixed, ij, meas, info, hub
+        return poses, fixed, ij, meas, info, hub, types
 
     def optimize(self, num_iterations):
         if len(self._edges) < 1:
             return -1                                                             # graph_slam.cpp:302-305
-        poses, fixed, ij, meas, info, hub = self._arrays()
-        st = optimize_arrays(self._L, self._handle(), poses, fixed, ij, meas, info, hub, num_iterations)
+        poses, fixed, ij, meas, info, hub, types = self._arrays()
+        st = optimize_arrays(self._L, self._handle(), poses, fixed, ij, meas, info, hub, num_iterations, edge_type=types)
         out = np.zeros((len(self._vertices), 7))
         C.check(self._L.lvs_pgo_get_poses(self._handle(), out.ctypes.data))
         for v, T in zip(self._vertices, _pg.matrix_batch(out)):
@@ -144,12 +205,20 @@ class GraphSLAM:
                 if v._fixed:
                     f.write("FIX %d\n" % v._id)
             for e in self._edges:
+                if getattr(e, "kind", EDGE_SE3) != EDGE_SE3:      # write() of the prior edges: measurement, then the upper triangle
+                    tag, _, d = _PRIOR_TAGS[e.kind]
+                    m = e.measurement if e.kind != PRIOR_QUAT else e.measurement[[3, 0, 1, 2]]        # PriorQuat writes w x y z
+                    up = [e.information[r, c] for r in range(d) for c in range(r, d)]
+                    f.write("%s %d %s %s\n" % (tag, e.vertices[0]._id, " ".join(repr(float(x)) for x in m), " ".join(repr(float(x)) for x in up)))
+                    continue
                 up = [e.information[r, c] for r in range(6) for c in range(r, 6)]
                 f.write("EDGE_SE3:QUAT %d %d %s %s\n" % (e.vertices[0]._id, e.vertices[1]._id, " ".join(repr(float(x)) for x in _pg.pose7(e.measurement)),
                                                       " ".join(repr(float(x)) for x in up)))
         with open(filename + ".kernels", "w") as f:                               # robust_kernel_io.cpp sidecar
             for e in self._edges:
-                if e.kernel:       # "<n vertices> <ids...> <type> <delta>" (g2o/robust_kernel_io.cpp:22-48)
+                if e.kernel and getattr(e, "kind", EDGE_SE3) != EDGE_SE3:
+                    f.write("1 %d %s %r\n" % (e.vertices[0]._id, e.kernel[0], e.kernel[1]))
+                elif e.kernel:     # "<n vertices> <ids...> <type> <delta>" (g2o/robust_kernel_io.cpp:22-48)
                     f.write("2 %d %d %s %r\n" % (e.vertices[0]._id, e.vertices[1]._id, e.kernel[0], e.kernel[1]))
         return True
 
@@ -179,6 +248,20 @@ class GraphSLAM:
                             info[r, c] = info[c, r] = up[k]
                             k += 1
                     self._edges.append(EdgeSE3(by_id[a], by_id[b], _pg.matrix(m), info))
+                elif t[0] in _PRIOR_BY_TAG:
+                    kind = _PRIOR_BY_TAG[t[0]]
+                    _, nm, d = _PRIOR_TAGS[kind]
+                    m = np.array(t[2:2 + nm], dtype=np.float64)
+                    if kind == PRIOR_QUAT:
+                        m = m[[1, 2, 3, 0]]                   # the file holds w x y z
+                    up = np.array(t[2 + nm:2 + nm + d * (d + 1) // 2], dtype=np.float64)
+                    info = np.zeros((d, d))
+                    k = 0
+                    for r in range(d):
+                        for c in range(r, d):
+                            info[r, c] = info[c, r] = up[k]
+                            k += 1
+                    self._edges.append(EdgeSE3Prior(kind, by_id[int(t[1])], m, info))
         self._vertices.sort(key=lambda v: v._id)
         self._next_id = max((v._id for v in self._vertices), default=-1) + 1
         try:
@@ -188,10 +271,13 @@ class GraphSLAM:
                     t = line.split()
                     if len(t) == 5 and t[0] == "2":           # KernelData (robust_kernel_io.cpp:51-62)
                         kern.setdefault((int(t[1]), int(t[2])), []).append((t[3], float(t[4])))
+                    elif len(t) == 4 and t[0] == "1":         # a unary edge's record
+                        kern.setdefault((int(t[1]), int(t[1]), "unary"), []).append((t[2], float(t[3])))
                     elif len(t) == 4:                         # sidecars written before the vertex count was added
                         kern.setdefault((int(t[0]), int(t[1])), []).append((t[2], float(t[3])))
                 for e in self._edges:
-                    q = kern.get((e.vertices[0]._id, e.vertices[1]._id))
+                    unary = getattr(e, "kind", EDGE_SE3) != EDGE_SE3
+                    q = kern.get((e.vertices[0]._id, e.vertices[1]._id, "unary") if unary else (e.vertices[0]._id, e.vertices[1]._id))
                     if q:
                         e.kernel = q.pop(0)                   # parallel edges between the same vertices take one record each
         except OSError:
@@ -221,7 +307,10 @@ def load_kitti_poses(filename):
     return out
 
 
-def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iterations):
+_PRIOR_BY_TAG = {v[0]: k for k, v in _PRIOR_TAGS.items()}
+
+
+def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iterations, edge_type=None):
     """set_graph + optimize on flat arrays; returns the stats dict (used by GraphSLAM.optimize, the tests and the bench)."""
     poses7 = np.ascontiguousarray(poses7, dtype=np.float64)
     ij = np.ascontiguousarray(ij, dtype=np.int32)
@@ -229,8 +318,10 @@ def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iteration
     info21 = np.ascontiguousarray(info21, dtype=np.float64)
     hub = np.ascontiguousarray(huber, dtype=np.float64) if huber is not None else None
     fx = np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None
-    C.check(L.lvs_pgo_set_graph(h, poses7.shape[0], poses7.ctypes.data, fx.ctypes.data if fx is not None else None, ij.shape[0], ij.ctypes.data,
-                                meas7.ctypes.data, info21.ctypes.data, hub.ctypes.data if hub is not None else None))
+    ty = np.ascontiguousarray(edge_type, dtype=np.int32) if edge_type is not None else None
+    C.check(L.lvs_pgo_set_graph_typed(h, poses7.shape[0], poses7.ctypes.data, fx.ctypes.data if fx is not None else None, ij.shape[0], ij.ctypes.data,
+                                      meas7.ctypes.data, info21.ctypes.data, hub.ctypes.data if hub is not None else None,
+                                      ty.ctypes.data if ty is not None else None))
     st = C.PgoStats()
     rc = L.lvs_pgo_optimize(h, int(num_iterations), ctypes.byref(st))
     if rc != 0 and rc != -10:
@@ -271,14 +362,16 @@ class PoseGraph:
         except Exception:
             pass
 
-    def set_graph(self, poses7, ij, meas7, info21, huber=None, fixed=None):
+    def set_graph(self, poses7, ij, meas7, info21, huber=None, fixed=None, edge_type=None):
         self._keep = [np.ascontiguousarray(poses7, dtype=np.float64), np.ascontiguousarray(ij, dtype=np.int32), np.ascontiguousarray(meas7, dtype=np.float64),
                       np.ascontiguousarray(info21, dtype=np.float64), np.ascontiguousarray(huber, dtype=np.float64) if huber is not None else None,
-                      np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None]
-        p, e, m, i, hb, fx = self._keep
+                      np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None,
+                      np.ascontiguousarray(edge_type, dtype=np.int32) if edge_type is not None else None]
+        p, e, m, i, hb, fx, ty = self._keep
         self.nv, self.ne = p.shape[0], e.shape[0]
-        C.check(self._L.lvs_pgo_set_graph(self._h, self.nv, p.ctypes.data, fx.ctypes.data if fx is not None else None, self.ne, e.ctypes.data,
-                                          m.ctypes.data, i.ctypes.data, hb.ctypes.data if hb is not None else None))
+        C.check(self._L.lvs_pgo_set_graph_typed(self._h, self.nv, p.ctypes.data, fx.ctypes.data if fx is not None else None, self.ne, e.ctypes.data,
+                                                m.ctypes.data, i.ctypes.data, hb.ctypes.data if hb is not None else None,
+                                                ty.ctypes.data if ty is not None else None))
 
     def set_options(self, pcg_tolerance=0.0, pcg_max_iterations=0):
         C.check(self._L.lvs_pgo_set_solver_options(self._h, float(pcg_tolerance), int(pcg_max_iterations)))

@@ -204,7 +204,70 @@ void edge_gradient(const Iso& Z, const Iso& Xi, const Iso& Xj, double* Ji, doubl
   }
 }
 
-struct Edge { int i, j; Iso Z, Zinv; double info[36]; double huber; };   // huber <= 0: no kernel
+// type 0: EdgeSE3.  Types 1-4: the reference's unary priors on a VertexSE3 (include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp; i == j), whose
+// measurement is pm[] and whose D x D information sits in the top-left corner of info (D = 2 for xy, 3 otherwise; the rest is zero, so the
+// 6-vector / 6 x 6 code paths of the binary edge are reused with zero padding).
+enum { EDGE_SE3 = 0, PRIOR_XY = 1, PRIOR_XYZ = 2, PRIOR_QUAT = 3, PRIOR_VEC = 4 };
+struct Edge { int i, j; Iso Z, Zinv; double info[36]; double huber; int type = EDGE_SE3; double pm[6] = {0, 0, 0, 0, 0, 0}; };   // huber <= 0: no kernel
+
+// setMeasurement of the prior edges: PriorQuat keeps w >= 0 (edge_se3_priorquat.hpp:52-57), PriorVec normalises direction and measurement
+// (edge_se3_priorvec.hpp:50-53); meas6 = xy | xyz | qx qy qz qw | direction(3) measurement(3)
+void prior_set_measurement(int type, const double* m, double* pm) {
+  for (int a = 0; a < 6; a++) pm[a] = 0.0;
+  if (type == PRIOR_XY) { pm[0] = m[0]; pm[1] = m[1]; }
+  else if (type == PRIOR_XYZ) { pm[0] = m[0]; pm[1] = m[1]; pm[2] = m[2]; }
+  else if (type == PRIOR_QUAT) { const double sg = m[3] < 0.0 ? -1.0 : 1.0; for (int a = 0; a < 4; a++) pm[a] = sg * m[a]; }
+  else if (type == PRIOR_VEC) {
+    for (int h = 0; h < 2; h++) {
+      const double* v = m + 3 * h;
+      const double n = std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+      for (int a = 0; a < 3; a++) pm[3 * h + a] = v[a] / n;
+    }
+  }
+}
+
+// computeError of the prior edges, zero-padded to 6 (edge_se3_priorxy.hpp:41-46, priorxyz:41-46, priorquat:41-50, priorvec:41-50)
+void prior_error(int type, const double* pm, const Iso& X, double* e) {
+  for (int a = 0; a < 6; a++) e[a] = 0.0;
+  if (type == PRIOR_XY) { e[0] = X.t[0] - pm[0]; e[1] = X.t[1] - pm[1]; }
+  else if (type == PRIOR_XYZ) { for (int a = 0; a < 3; a++) e[a] = X.t[a] - pm[a]; }
+  else if (type == PRIOR_QUAT) {
+    Q q = quat_from_R(X.R);                                  // Eigen::Quaterniond(linear()), not normalised
+    const double dot = ((pm[0] * q.x + pm[1] * q.y) + pm[2] * q.z) + pm[3] * q.w;
+    if (dot < 0.0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+    e[0] = q.x - pm[0]; e[1] = q.y - pm[1]; e[2] = q.z - pm[2];
+  } else if (type == PRIOR_VEC) {
+    // linear().inverse() * direction: Eigen's 3 x 3 inverse (cofactors over the determinant), not the transpose
+    const double* m = X.R;
+    double cof[9];
+    cof[0] = m[4] * m[8] - m[5] * m[7]; cof[1] = m[5] * m[6] - m[3] * m[8]; cof[2] = m[3] * m[7] - m[4] * m[6];
+    cof[3] = m[2] * m[7] - m[1] * m[8]; cof[4] = m[0] * m[8] - m[2] * m[6]; cof[5] = m[1] * m[6] - m[0] * m[7];
+    cof[6] = m[1] * m[5] - m[2] * m[4]; cof[7] = m[2] * m[3] - m[0] * m[5]; cof[8] = m[0] * m[4] - m[1] * m[3];
+    const double det = (m[0] * cof[0] + m[1] * cof[1]) + m[2] * cof[2];
+    const double id = 1.0 / det;
+    // inverse[r][c] = cof[c][r] / det
+    for (int r = 0; r < 3; r++) {
+      const double v = ((cof[0 * 3 + r] * id) * pm[0] + (cof[1 * 3 + r] * id) * pm[1]) + (cof[2 * 3 + r] * id) * pm[2];
+      e[r] = v - pm[3 + r];
+    }
+  }
+}
+
+// BaseUnaryEdge::linearizeOplus (g2o!core/base_unary_edge.hpp: central differences, delta = 1e-9, through VertexSE3::oplus): J row-major
+// 6 x 6, rows past the edge's dimension zero.  (The 12 oplus calls count towards the vertex's 1000-call re-orthogonalisation in g2o; like
+// the update itself that cadence is not modelled here.)
+void prior_jacobian(int type, const double* pm, const Iso& X, double* J) {
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (int a = 0; a < 36; a++) J[a] = 0.0;
+  for (int d = 0; d < 6; d++) {
+    double add[6] = {0, 0, 0, 0, 0, 0}, e1[6], e2[6];
+    add[d] = delta;
+    prior_error(type, pm, iso_mul(X, from_vector_mqt(add)), e1);
+    add[d] = -delta;
+    prior_error(type, pm, iso_mul(X, from_vector_mqt(add)), e2);
+    for (int r = 0; r < 6; r++) J[r * 6 + d] = scalar * (e1[r] - e2[r]);
+  }
+}
 
 // ---------------------------------------------------------------- CSparse (vendored by the reference, loaded when built)
 struct cs { int nzmax, m, n; int* p; int* i; double* x; int nz; };
@@ -324,6 +387,7 @@ void huber(double e, double delta, double rho[3]) {   // robust_kernel_impl.cpp:
 void compute_errors(PGO& g) {   // SparseOptimizer::computeActiveErrors
   for (size_t k = 0; k < g.edges.size(); k++) {
     const Edge& e = g.edges[k];
+    if (e.type != EDGE_SE3) { prior_error(e.type, e.pm, g.X[e.i], &g.err[k * 6]); continue; }
     Iso d = iso_mul(iso_mul(e.Zinv, iso_inv(g.X[e.i])), g.X[e.j]);
     to_vector_mqt(d, &g.err[k * 6]);
   }
@@ -359,8 +423,10 @@ void build_system(PGO& g) {   // BlockSolver::buildSystem + constructQuadraticFo
     const Edge& e = g.edges[k];
     double* A = &g.Ji[k * 36];
     double* B = &g.Jj[k * 36];
-    edge_gradient(e.Z, g.X[e.i], g.X[e.j], A, B, nullptr);
-    const int a = g.hidx[e.i], c = g.hidx[e.j];
+    const bool unary = e.type != EDGE_SE3;
+    if (unary) { prior_jacobian(e.type, e.pm, g.X[e.i], A); for (int q = 0; q < 36; q++) B[q] = 0.0; }
+    else edge_gradient(e.Z, g.X[e.i], g.X[e.j], A, B, nullptr);
+    const int a = g.hidx[e.i], c = unary ? -1 : g.hidx[e.j];
     if (a < 0 && c < 0) continue;
     const double* er = &g.err[k * 6];
     double w = 1.0;
@@ -617,8 +683,10 @@ void* opgo_create() { return new PGO(); }
 void opgo_destroy(void* h) { delete (PGO*)h; }
 
 // poses7 / meas7: x y z qx qy qz qw.  info21: upper triangle, row-major, as in g2o files.  huber_delta <= 0: no kernel.
-void opgo_set_graph(void* h, int nv, const double* poses7, const uint8_t* fixed, int ne, const int32_t* ij, const double* meas7,
-                    const double* info21, const double* huber_delta) {
+// edge_type (may be NULL: all EdgeSE3): 0 EdgeSE3, 1-4 the unary priors, whose meas7 row carries xy | xyz | qx qy qz qw | direction +
+// measurement and whose info21 row carries the D x D information in the top-left corner of the 6 x 6 upper triangle.
+void opgo_set_graph_typed(void* h, int nv, const double* poses7, const uint8_t* fixed, int ne, const int32_t* ij, const double* meas7,
+                          const double* info21, const double* huber_delta, const int32_t* edge_type) {
   PGO& g = *(PGO*)h;
   g.X.resize(nv); g.fixed.assign(nv, 0);
   for (int v = 0; v < nv; v++) { g.X[v] = iso_from_qt7(poses7 + 7 * v); if (fixed) g.fixed[v] = fixed[v]; }
@@ -626,7 +694,13 @@ void opgo_set_graph(void* h, int nv, const double* poses7, const uint8_t* fixed,
   for (int k = 0; k < ne; k++) {
     Edge& e = g.edges[k];
     e.i = ij[2 * k]; e.j = ij[2 * k + 1];
-    e.Z = iso_from_qt7(meas7 + 7 * k);
+    e.type = edge_type ? edge_type[k] : EDGE_SE3;
+    if (e.type != EDGE_SE3) {
+      e.j = e.i;
+      prior_set_measurement(e.type, meas7 + 7 * k, e.pm);
+      const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+      e.Z = iso_from_qt7(ident);
+    } else e.Z = iso_from_qt7(meas7 + 7 * k);
     e.Zinv = iso_inv(e.Z);
     const double* u = info21 + 21 * k;
     int p = 0;
@@ -634,6 +708,21 @@ void opgo_set_graph(void* h, int nv, const double* poses7, const uint8_t* fixed,
     e.huber = huber_delta ? huber_delta[k] : 0.0;
   }
   build_structure(g);
+}
+
+void opgo_set_graph(void* h, int nv, const double* poses7, const uint8_t* fixed, int ne, const int32_t* ij, const double* meas7,
+                    const double* info21, const double* huber_delta) {
+  opgo_set_graph_typed(h, nv, poses7, fixed, ne, ij, meas7, info21, huber_delta, nullptr);
+}
+void opgo_prior_error(int type, const double* meas, const double* x7, double* e6) {
+  double pm[6];
+  prior_set_measurement(type, meas, pm);
+  prior_error(type, pm, iso_from_qt7(x7), e6);
+}
+void opgo_prior_jacobian(int type, const double* meas, const double* x7, double* J36) {
+  double pm[6];
+  prior_set_measurement(type, meas, pm);
+  prior_jacobian(type, pm, iso_from_qt7(x7), J36);
 }
 
 void opgo_get_poses(void* h, double* poses7) { PGO& g = *(PGO*)h; for (size_t v = 0; v < g.X.size(); v++) iso_to_qt7(g.X[v], poses7 + 7 * v); }

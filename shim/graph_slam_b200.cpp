@@ -7,6 +7,10 @@
 #include <g2o/core/sparse_optimizer.h>
 #include <g2o/types/slam3d/edge_se3.h>
 #include <g2o/types/slam3d/vertex_se3.h>
+#include <g2o/edge_se3_priorxy.hpp>       // the reference's own unary priors (include/g2o/ of lv_slam): GPS / IMU constraints
+#include <g2o/edge_se3_priorxyz.hpp>
+#include <g2o/edge_se3_priorquat.hpp>
+#include <g2o/edge_se3_priorvec.hpp>
 #include <algorithm>
 #include <cstdint>
 #include <iostream>
@@ -24,6 +28,18 @@ static void to_qt7(const Eigen::Isometry3d& T, double* v) {
   v[3] = q.x(); v[4] = q.y(); v[5] = q.z(); v[6] = q.w();
 }
 
+// the D x D information of a prior edge into the top-left corner of a 6 x 6 upper triangle (row-major, 21 numbers)
+template <typename E>
+static void pack_info(const E* e, int D, double* u21) {
+  std::fill(u21, u21 + 21, 0.0);
+  for (int r = 0; r < D; r++) for (int c = r; c < D; c++) u21[r * 6 - r * (r - 1) / 2 + (c - r)] = e->information()(r, c);
+}
+template <typename E>
+static double huber_of(const E* e) {
+  auto* hk = dynamic_cast<g2o::RobustKernelHuber*>(e->robustKernel());
+  return hk ? hk->delta() : 0.0;
+}
+
 static int solver_kind(const std::string& s) {   // the names GraphSLAM's constructor hands to g2o's factory
   const bool gn = s.compare(0, 2, "gn") == 0, pcg = s.find("pcg") != std::string::npos;
   return gn ? (pcg ? LVS_PGO_GN_PCG : LVS_PGO_GN_CHOL) : (pcg ? LVS_PGO_LM_PCG : LVS_PGO_LM_CHOL);
@@ -38,25 +54,66 @@ int GraphSLAM::optimize(int num_iterations) {
   for (auto& kv : graph->vertices()) if (auto* v = dynamic_cast<g2o::VertexSE3*>(kv.second)) vs.push_back(v);
   std::sort(vs.begin(), vs.end(), [](g2o::VertexSE3* a, g2o::VertexSE3* b) { return a->id() < b->id(); });
   for (size_t i = 0; i < vs.size(); i++) index[vs[i]->id()] = (int)i;
-  std::vector<g2o::EdgeSE3*> es;
-  for (auto* e : graph->edges()) if (auto* s = dynamic_cast<g2o::EdgeSE3*>(e)) es.push_back(s);
-  std::sort(es.begin(), es.end(), [](g2o::EdgeSE3* a, g2o::EdgeSE3* b) { return a->internalId() < b->internalId(); });
-  std::vector<double> poses(7 * vs.size()), meas(7 * es.size()), info(21 * es.size()), huber(es.size(), 0.0);
+  // EdgeSE3 and the unary priors on a VertexSE3 (add_se3_prior_{xy,xyz,quat,vec}_edge, graph_slam.cpp:194-240); plane vertices / edges
+  // (floor detection) are not on this path and are left out like any other type
+  struct Item { g2o::HyperGraph::Edge* e; long long id; int type; };
+  std::vector<Item> es;
+  for (auto* e : graph->edges()) {
+    if (auto* s = dynamic_cast<g2o::EdgeSE3*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_SE3});
+    else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorXY*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_XY});
+    else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorXYZ*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_XYZ});
+    else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorQuat*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_QUAT});
+    else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorVec*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_VEC});
+  }
+  std::sort(es.begin(), es.end(), [](const Item& a, const Item& b) { return a.id < b.id; });
+  std::vector<double> poses(7 * vs.size()), meas(7 * es.size(), 0.0), info(21 * es.size()), huber(es.size(), 0.0);
   std::vector<uint8_t> fixed(vs.size());
-  std::vector<int32_t> ij(2 * es.size());
+  std::vector<int32_t> ij(2 * es.size()), type(es.size());
   for (size_t i = 0; i < vs.size(); i++) { to_qt7(vs[i]->estimate(), &poses[7 * i]); fixed[i] = vs[i]->fixed(); }
   for (size_t k = 0; k < es.size(); k++) {
-    ij[2 * k] = index[es[k]->vertices()[0]->id()];
-    ij[2 * k + 1] = index[es[k]->vertices()[1]->id()];
-    to_qt7(es[k]->measurement(), &meas[7 * k]);
-    int p = 0;
-    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) info[21 * k + p++] = es[k]->information()(r, c);
-    if (auto* hk = dynamic_cast<g2o::RobustKernelHuber*>(es[k]->robustKernel())) huber[k] = hk->delta();
+    type[k] = es[k].type;
+    ij[2 * k] = index[es[k].e->vertices()[0]->id()];
+    ij[2 * k + 1] = es[k].type == LVS_PGO_EDGE_SE3 ? index[es[k].e->vertices()[1]->id()] : ij[2 * k];
+    double* m = &meas[7 * k];
+    switch (es[k].type) {
+      case LVS_PGO_EDGE_SE3: {
+        auto* e = static_cast<g2o::EdgeSE3*>(es[k].e);
+        to_qt7(e->measurement(), m);
+        int p = 0;
+        for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) info[21 * k + p++] = e->information()(r, c);
+        huber[k] = huber_of(e);
+        break;
+      }
+      case LVS_PGO_EDGE_PRIOR_XY: {
+        auto* e = static_cast<g2o::EdgeSE3PriorXY*>(es[k].e);
+        m[0] = e->measurement()(0, 0); m[1] = e->measurement()(1, 0);
+        pack_info(e, 2, &info[21 * k]); huber[k] = huber_of(e);
+        break;
+      }
+      case LVS_PGO_EDGE_PRIOR_XYZ: {
+        auto* e = static_cast<g2o::EdgeSE3PriorXYZ*>(es[k].e);
+        for (int a = 0; a < 3; a++) m[a] = e->measurement()(a, 0);
+        pack_info(e, 3, &info[21 * k]); huber[k] = huber_of(e);
+        break;
+      }
+      case LVS_PGO_EDGE_PRIOR_QUAT: {
+        auto* e = static_cast<g2o::EdgeSE3PriorQuat*>(es[k].e);
+        m[0] = e->measurement().x(); m[1] = e->measurement().y(); m[2] = e->measurement().z(); m[3] = e->measurement().w();
+        pack_info(e, 3, &info[21 * k]); huber[k] = huber_of(e);
+        break;
+      }
+      default: {
+        auto* e = static_cast<g2o::EdgeSE3PriorVec*>(es[k].e);
+        for (int a = 0; a < 6; a++) m[a] = e->measurement()(a, 0);
+        pack_info(e, 3, &info[21 * k]); huber[k] = huber_of(e);
+        break;
+      }
+    }
   }
   lvs_pgo_t* h = nullptr;
   if (lvs_pgo_create(solver_kind(solver_type_), 0, nullptr, &h) != LVS_OK) { std::cerr << "lvslam_b200: " << lvs_last_error() << std::endl; return 0; }
   lvs_pgo_stats st{};
-  int rc = lvs_pgo_set_graph(h, (int)vs.size(), poses.data(), fixed.data(), (int)es.size(), ij.data(), meas.data(), info.data(), huber.data());
+  int rc = lvs_pgo_set_graph_typed(h, (int)vs.size(), poses.data(), fixed.data(), (int)es.size(), ij.data(), meas.data(), info.data(), huber.data(), type.data());
   if (rc == LVS_OK) rc = lvs_pgo_optimize(h, num_iterations, &st);
   if (rc == LVS_OK) rc = lvs_pgo_get_poses(h, poses.data());
   lvs_pgo_destroy(h);

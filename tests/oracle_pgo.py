@@ -29,6 +29,9 @@ def lib():
         L.opgo_create.restype = vp
         L.opgo_destroy.argtypes = [vp]; L.opgo_destroy.restype = None
         L.opgo_set_graph.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp]; L.opgo_set_graph.restype = None
+        L.opgo_set_graph_typed.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]; L.opgo_set_graph_typed.restype = None
+        L.opgo_prior_error.argtypes = [i32, vp, vp, vp]; L.opgo_prior_error.restype = None
+        L.opgo_prior_jacobian.argtypes = [i32, vp, vp, vp]; L.opgo_prior_jacobian.restype = None
         L.opgo_get_poses.argtypes = [vp, vp]; L.opgo_get_poses.restype = None
         L.opgo_compute_errors.argtypes = [vp, vp, vp]; L.opgo_compute_errors.restype = f64
         L.opgo_linearize.argtypes = [vp, vp, vp]; L.opgo_linearize.restype = None
@@ -76,13 +79,14 @@ class OraclePGO:
         except Exception:
             pass
 
-    def set_graph(self, poses7, edges_ij, meas7, info21, huber=None, fixed=None):
+    def set_graph(self, poses7, edges_ij, meas7, info21, huber=None, fixed=None, edge_type=None):
         p, ij, m, inf = _c(poses7), _c(edges_ij, np.int32), _c(meas7), _c(info21)
         self.nv, self.ne = p.shape[0], ij.shape[0]
         hub = _c(huber) if huber is not None else None
         fx = _c(fixed, np.uint8) if fixed is not None else None
-        self.L.opgo_set_graph(self.h, self.nv, p.ctypes.data, fx.ctypes.data if fx is not None else None, self.ne, ij.ctypes.data, m.ctypes.data,
-                              inf.ctypes.data, hub.ctypes.data if hub is not None else None)
+        ty = _c(edge_type, np.int32) if edge_type is not None else None
+        self.L.opgo_set_graph_typed(self.h, self.nv, p.ctypes.data, fx.ctypes.data if fx is not None else None, self.ne, ij.ctypes.data, m.ctypes.data,
+                                    inf.ctypes.data, hub.ctypes.data if hub is not None else None, ty.ctypes.data if ty is not None else None)
 
     def poses(self):
         out = np.zeros((self.nv, 7))
@@ -139,6 +143,21 @@ def edge_jacobians(z7, xi7, xj7):
     Ji, Jj = np.zeros((6, 6)), np.zeros((6, 6))
     lib().opgo_edge_jacobians(_c(z7).ctypes.data, _c(xi7).ctypes.data, _c(xj7).ctypes.data, Ji.ctypes.data, Jj.ctypes.data)
     return Ji, Jj
+
+
+def prior_error(kind, meas, x7):
+    """computeError of EdgeSE3PriorXY / XYZ / Quat / Vec (kind 1-4), zero-padded to 6."""
+    e, m = np.zeros(6), np.zeros(7)
+    m[:len(meas)] = meas
+    lib().opgo_prior_error(int(kind), m.ctypes.data, _c(x7).ctypes.data, e.ctypes.data)
+    return e
+
+
+def prior_jacobian(kind, meas, x7):
+    J, m = np.zeros((6, 6)), np.zeros(7)
+    m[:len(meas)] = meas
+    lib().opgo_prior_jacobian(int(kind), m.ctypes.data, _c(x7).ctypes.data, J.ctypes.data)
+    return J
 
 
 def oplus(x7, d6):

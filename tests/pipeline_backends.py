@@ -35,7 +35,7 @@ class OracleGraphSLAM(GS.GraphSLAM):
     def optimize(self, num_iterations):
         if len(self._edges) < 1:
             return -1
-        poses, fixed, ij, meas, info, hub = self._arrays()
+        poses, fixed, ij, meas, info, hub, _types = self._arrays()
         o = P.OraclePGO()
         o.set_graph(poses, ij, meas, info, hub, fixed)
         r = o.optimize(num_iterations, P.ALG_LM, P.SOLVER_CSPARSE if P.have_csparse() else P.SOLVER_DENSE)

@@ -8,6 +8,10 @@
 #include <global_graph/information_matrix_calculator.hpp>
 #include <g2o/core/robust_kernel_impl.h>
 #include <g2o/types/slam3d/edge_se3.h>
+#include <g2o/edge_se3_priorxy.hpp>
+#include <g2o/edge_se3_priorxyz.hpp>
+#include <g2o/edge_se3_priorquat.hpp>
+#include <g2o/edge_se3_priorvec.hpp>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -102,7 +106,8 @@ int main(int argc, char** argv) {
   // ---------------- pose graph: a g2o graph filled the way GraphSLAM::add_se3_node / add_se3_edge / add_robust_kernel do, then optimize()
   {
     const std::vector<double> poses = slurp<double>(dir + "/poses7.f64"), meas = slurp<double>(dir + "/meas7.f64"), info21 = slurp<double>(dir + "/info21.f64");
-    const std::vector<int32_t> ij = slurp<int32_t>(dir + "/ij.i32");
+    const std::vector<int32_t> ij = slurp<int32_t>(dir + "/ij.i32"), etype = slurp<int32_t>(dir + "/etype.i32");
+    const std::vector<double> huber = slurp<double>(dir + "/huber.f64");
     lv_slam::GraphSLAM gs;
     gs.solver_type_ = "lm_var_cholmod";
     g2o::SparseOptimizer* graph = new g2o::SparseOptimizer();
@@ -115,19 +120,55 @@ int main(int argc, char** argv) {
       graph->addVertex(v);
       vs.push_back(v);
     }
-    for (size_t k = 0; k < ij.size() / 2; k++) {
-      auto* e = new g2o::EdgeSE3();
-      e->setMeasurement(iso_from7(&meas[7 * k]));
-      Eigen::Matrix<double, 6, 6> I;
-      int p = 0;
-      for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { I(r, c) = info21[21 * k + p]; I(c, r) = info21[21 * k + p]; p++; }
-      e->setInformation(I);
-      e->vertices().push_back(vs[ij[2 * k]]);
-      e->vertices().push_back(vs[ij[2 * k + 1]]);
+    // edges in file order; the unary priors the way GraphSLAM::add_se3_prior_{xy,xyz,quat,vec}_edge build them (graph_slam.cpp:194-240)
+    auto kernel = [&](size_t k) -> g2o::RobustKernel* {
+      if (!(huber[k] > 0)) return nullptr;
       auto* hk = new g2o::RobustKernelHuber();
-      hk->setDelta(1.0);
-      e->setRobustKernel(hk);
-      graph->addEdge(e);
+      hk->setDelta(huber[k]);
+      return hk;
+    };
+    auto info_dd = [&](size_t k, auto& I, int D) {
+      for (int r = 0; r < D; r++) for (int c = r; c < D; c++) { const double v = info21[21 * k + r * 6 - r * (r - 1) / 2 + (c - r)]; I(r, c) = v; I(c, r) = v; }
+    };
+    for (size_t k = 0; k < ij.size() / 2; k++) {
+      const double* m = &meas[7 * k];
+      if (etype[k] == 0) {
+        auto* e = new g2o::EdgeSE3();
+        e->setMeasurement(iso_from7(m));
+        Eigen::Matrix<double, 6, 6> I;
+        info_dd(k, I, 6);
+        e->setInformation(I);
+        e->vertices().push_back(vs[ij[2 * k]]);
+        e->vertices().push_back(vs[ij[2 * k + 1]]);
+        if (auto* hk = kernel(k)) e->setRobustKernel(hk);
+        graph->addEdge(e);
+      } else if (etype[k] == 1) {
+        auto* e = new g2o::EdgeSE3PriorXY();
+        Eigen::Matrix<double, 2, 1> z; z(0, 0) = m[0]; z(1, 0) = m[1];
+        Eigen::Matrix<double, 2, 2> I; info_dd(k, I, 2);
+        e->setMeasurement(z); e->setInformation(I); e->vertices().push_back(vs[ij[2 * k]]);
+        if (auto* hk = kernel(k)) e->setRobustKernel(hk);
+        graph->addEdge(e);
+      } else if (etype[k] == 2) {
+        auto* e = new g2o::EdgeSE3PriorXYZ();
+        Eigen::Matrix<double, 3, 3> I; info_dd(k, I, 3);
+        e->setMeasurement(Eigen::Vector3d(m[0], m[1], m[2])); e->setInformation(I); e->vertices().push_back(vs[ij[2 * k]]);
+        if (auto* hk = kernel(k)) e->setRobustKernel(hk);
+        graph->addEdge(e);
+      } else if (etype[k] == 3) {
+        auto* e = new g2o::EdgeSE3PriorQuat();
+        Eigen::Matrix<double, 3, 3> I; info_dd(k, I, 3);
+        e->setMeasurement(Eigen::Quaterniond(m[3], m[0], m[1], m[2])); e->setInformation(I); e->vertices().push_back(vs[ij[2 * k]]);
+        if (auto* hk = kernel(k)) e->setRobustKernel(hk);
+        graph->addEdge(e);
+      } else {
+        auto* e = new g2o::EdgeSE3PriorVec();
+        Eigen::Matrix<double, 6, 1> z; for (int a = 0; a < 6; a++) z(a, 0) = m[a];
+        Eigen::Matrix<double, 3, 3> I; info_dd(k, I, 3);
+        e->setMeasurement(z); e->setInformation(I); e->vertices().push_back(vs[ij[2 * k]]);
+        if (auto* hk = kernel(k)) e->setRobustKernel(hk);
+        graph->addEdge(e);
+      }
     }
     const int it = gs.optimize(100);
     std::printf("pgo_iterations %d\n", it);

@@ -37,6 +37,7 @@ struct Map {
 };
 struct Quaterniond {
   double c[4];                                         // x y z w
+  Quaterniond() : c{0, 0, 0, 1} {}
   Quaterniond(double w, double x, double y, double z) : c{x, y, z, w} {}
   explicit Quaterniond(const Matrix3d& m) : c{0, 0, 0, 1} {    // Eigen 3.3 Quaternion = rotation matrix (Geometry/Quaternion.h, quaternionbase_assign_impl)
     double t = m(0, 0) + m(1, 1) + m(2, 2);

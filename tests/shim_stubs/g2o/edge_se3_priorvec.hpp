@@ -1,0 +1,2 @@
+#pragma once
+#include "edge_se3_prior_stub.h"

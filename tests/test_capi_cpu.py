@@ -101,8 +101,8 @@ def test_graph_slam_text_round_trip(tmp_path):
     gs2 = M.GraphSLAM()
     assert gs2.load(path)
     assert gs2.num_vertices() == gs.num_vertices() and gs2.num_edges() == gs.num_edges()
-    p1, f1, ij1, m1, i1, h1 = gs._arrays()
-    p2, f2, ij2, m2, i2, h2 = gs2._arrays()
+    p1, f1, ij1, m1, i1, h1, _ = gs._arrays()
+    p2, f2, ij2, m2, i2, h2, _ = gs2._arrays()
     np.testing.assert_allclose(p2, p1, atol=1e-15); np.testing.assert_allclose(m2, m1, atol=1e-15)
     assert np.array_equal(ij1, ij2) and np.array_equal(f1, f2) and np.array_equal(h1, h2) and np.array_equal(i1, i2)
     assert M.GraphSLAM().optimize(5) == -1                  # no edges (graph_slam.cpp:302-305), decided before any device call
@@ -125,7 +125,7 @@ def test_graph_slam_text_round_trip(tmp_path):
     open(gap + ".kernels", "w").write("2 4 3 Huber 0.5\n")
     gs4 = M.GraphSLAM()
     assert gs4.load(gap)
-    p4, f4, ij4, m4, i4, h4 = gs4._arrays()
+    p4, f4, ij4, m4, i4, h4, _ = gs4._arrays()
     assert np.array_equal(ij4, [[2, 1], [3, 2], [3, 2]]) and p4[2, 0] == 2.0 and p4[3, 0] == 3.0
     assert h4.tolist() == [0.0, 0.5, 0.0]
     assert gs4.add_se3_node(np.eye(4)).id() == 5
@@ -184,6 +184,35 @@ def test_two_rank_plumbing_over_gloo(tmp_path):
     assert "11.0 12.0 [(0, 8), (8, 8)]" in line            # max over ranks, total pairs, disjoint frame ranges
     shard = [l for l in out.stdout.splitlines() if l.startswith("SHARD")][0]
     assert "[0, 1] [64, 64] [(0, 62500), (62500, 125001)]" in shard
+
+
+def test_graph_slam_prior_edges_round_trip(tmp_path):
+    """The reference's GPS / IMU prior edges (graph_slam.cpp:194-240) in the host mirror: setMeasurement semantics, the flat arrays
+    lvs_pgo_set_graph_typed takes, and the g2o text tags the reference registers (graph_slam.cpp:31-35).  No device needed."""
+    from lv_slam_b200.graph_slam import GraphSLAM, PRIOR_QUAT, PRIOR_VEC
+    gs = GraphSLAM("lm_var")
+    T = np.eye(4); T[:3, 3] = [1, 2, 3]
+    a, b = gs.add_se3_node(np.eye(4)), gs.add_se3_node(T)
+    gs.add_se3_edge(a, b, T, np.eye(6))
+    e1 = gs.add_se3_prior_xy_edge(b, [1.5, 2.5], np.diag([4.0, 5.0]))
+    gs.add_se3_prior_xyz_edge(a, [0.1, 0.2, 0.3], np.eye(3) * 2)
+    e3 = gs.add_se3_prior_quat_edge(b, [0.5, -0.5, -0.5, -0.5], np.eye(3) * 10)
+    e4 = gs.add_se3_prior_vec_edge(a, [0, 0, -2.0], [0.0, 3.0, -4.0], np.eye(3))
+    gs.add_robust_kernel(e1, "Huber", 1.5)
+    assert e3.kind == PRIOR_QUAT and np.allclose(e3.measurement, [-0.5, 0.5, 0.5, 0.5])                       # w >= 0
+    assert e4.kind == PRIOR_VEC and np.allclose(e4.measurement, [0, 0, -1, 0, 0.6, -0.8])                # both halves normalised
+    poses, fixed, ij, meas, info, hub, types = gs._arrays()
+    assert types.tolist() == [0, 1, 2, 3, 4] and ij.tolist() == [[0, 1], [1, 1], [0, 0], [1, 1], [0, 0]] and hub.tolist() == [0, 1.5, 0, 0, 0]
+    assert np.allclose(meas[1, :2], [1.5, 2.5]) and np.allclose(meas[3, :4], [-0.5, 0.5, 0.5, 0.5]) and info[1, 0] == 4.0 and info[1, 6] == 5.0 and info[1, 11] == 0.0
+    f = str(tmp_path / "g.g2o")
+    assert gs.save(f)
+    text = open(f).read()
+    assert "EDGE_SE3_PRIORXY 1 1.5 2.5 4.0 0.0 5.0" in text and "EDGE_SE3_PRIORQUAT 1 0.5 -0.5 0.5 0.5" in text and "EDGE_SE3_PRIORVEC 0" in text
+    gs2 = GraphSLAM("lm_var")
+    assert gs2.load(f) and gs2.num_edges() == 5
+    p2 = gs2._arrays()
+    for x, y in zip(gs._arrays(), p2):
+        assert np.allclose(x, y)
 
 
 def _elimination_game(n, off, order):

@@ -144,3 +144,106 @@ def test_empty_graph_returns_minus_one():
     o = P.OraclePGO()
     o.set_graph(np.array([[0, 0, 0, 0, 0, 0, 1.0]]), np.zeros((0, 2), np.int32), np.zeros((0, 7)), np.zeros((0, 21)))
     assert o.optimize(10)["iterations"] == -1               # graph_slam.cpp:302-305
+
+
+# ---- unary priors on a VertexSE3 (include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp; "later" row of SURVEY.md §8f)
+def _priors_on(g, rng, every=7):
+    """The sphere graph g with GPS / IMU style priors on every `every`-th vertex, interleaved after the binary edges of that vertex:
+    returns (ij, meas7, info21, huber, edge_type)."""
+    ij, meas, info, hub, ty = [], [], [], [], []
+    nv = len(g["poses7"])
+    by_first = {}
+    for k, (a, b) in enumerate(g["ij"]):
+        by_first.setdefault(int(a), []).append(k)
+    done = set()
+    for v in range(nv):
+        for k in by_first.get(v, []):
+            ij.append(g["ij"][k]); meas.append(g["meas7"][k]); info.append(g["info21"][k]); hub.append(g["huber"][k]); ty.append(0)
+            done.add(k)
+        if v % every:
+            continue
+        T = G.matrix(g["truth7"][v])
+        kind = 1 + (v // every) % 4
+        m, I6 = np.zeros(7), np.zeros((6, 6))
+        if kind == 1:
+            m[:2] = T[:2, 3] + rng.normal(0, 0.05, 2); I6[:2, :2] = np.array([[4.0, 0.3], [0.3, 5.0]])
+        elif kind == 2:
+            m[:3] = T[:3, 3] + rng.normal(0, 0.05, 3); I6[:3, :3] = np.diag([4.0, 4.0, 1.0]) + 0.2
+        elif kind == 3:
+            q = G.pose7(T)[3:] * (-1.0 if v % 2 else 1.0)           # either sign: setMeasurement keeps w >= 0
+            m[:4] = q + rng.normal(0, 0.01, 4); I6[:3, :3] = np.diag([50.0, 60.0, 70.0])
+        else:
+            d = np.array([0.0, 0.0, -1.0])
+            m[:3] = 3.0 * d; m[3:6] = T[:3, :3].T @ d + rng.normal(0, 0.02, 3); I6[:3, :3] = np.eye(3) * 30.0
+        iu = np.triu_indices(6)
+        ij.append([v, v]); meas.append(m); info.append(I6[iu]); hub.append(1.0 if v % (2 * every) == 0 else 0.0); ty.append(kind)
+    assert len(done) == len(g["ij"])
+    return np.array(ij, np.int32), np.array(meas), np.array(info), np.array(hub), np.array(ty, np.int32)
+
+
+def test_prior_edge_errors_and_numeric_jacobians():
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        x = _rand_pose(rng)
+        T = G.matrix(x)
+        # PriorXYZ / PriorXY: translation minus measurement; Jacobian of t + R dt is [R 0] (rows of the edge's dimension only)
+        m = rng.normal(0, 5, 3)
+        np.testing.assert_allclose(P.prior_error(2, m, x), np.r_[T[:3, 3] - m, 0, 0, 0], atol=1e-14)
+        np.testing.assert_allclose(P.prior_error(1, m[:2], x), np.r_[T[:2, 3] - m[:2], 0, 0, 0, 0], atol=1e-14)
+        J = P.prior_jacobian(2, m, x)
+        np.testing.assert_allclose(J[:3, :3], T[:3, :3], atol=3e-5)      # central differences with delta = 1e-9 on |t| ~ 10: round-off 1e-15 / 2e-9
+        np.testing.assert_allclose(J[:3, 3:], 0, atol=3e-5)
+        np.testing.assert_allclose(J[3:], 0, atol=0)
+        assert np.abs(P.prior_jacobian(1, m[:2], x)[2:]).max() == 0
+        # PriorQuat: zero at the pose's own quaternion whatever its sign; d vec(q (x) dq) / d dq at dq = 0 is  w I + [v]x
+        q = G.pose7(T)[3:]
+        np.testing.assert_allclose(P.prior_error(3, -q, x)[:3], 0, atol=1e-13)
+        qq = q if q[3] >= 0 else -q
+        vx = np.array([[0, -qq[2], qq[1]], [qq[2], 0, -qq[0]], [-qq[1], qq[0], 0]])
+        Jq = P.prior_jacobian(3, q, x)
+        np.testing.assert_allclose(Jq[:3, 3:], qq[3] * np.eye(3) + vx, atol=5e-6)
+        np.testing.assert_allclose(Jq[:3, :3], 0, atol=5e-6)
+        # PriorVec: R^T direction - measurement, both normalised by setMeasurement
+        d, z = rng.normal(size=3), rng.normal(size=3)
+        e = P.prior_error(4, np.r_[d, z], x)
+        np.testing.assert_allclose(e[:3], T[:3, :3].T @ (d / np.linalg.norm(d)) - z / np.linalg.norm(z), atol=1e-13)
+
+
+def test_single_vertex_with_position_and_orientation_priors_has_a_known_optimum():
+    """One vertex, a PriorXYZ and a PriorQuat: LM must land on (measurement, measured quaternion) - the only edges are unary."""
+    x0 = np.array([[1.0, -2.0, 0.5, 0.1, -0.2, 0.05, 0.97]]); x0[0, 3:] /= np.linalg.norm(x0[0, 3:])
+    target_q = np.array([0.2, 0.1, -0.15, 0.96]); target_q /= np.linalg.norm(target_q)
+    iu = np.triu_indices(6)
+    Ixyz, Iq = np.zeros((6, 6)), np.zeros((6, 6))
+    Ixyz[:3, :3] = np.diag([2.0, 3.0, 4.0]); Iq[:3, :3] = np.eye(3) * 100
+    meas = np.zeros((2, 7)); meas[0, :3] = [3.0, 1.0, -1.0]; meas[1, :4] = target_q
+    o = P.OraclePGO()
+    o.set_graph(x0, np.array([[0, 0], [0, 0]], np.int32), meas, np.array([Ixyz[iu], Iq[iu]]), None, None, np.array([2, 3], np.int32))
+    r = o.optimize(200, P.ALG_LM, P.SOLVER_DENSE)
+    assert r["iterations"] > 0 and r["chi2_after"] < 1e-12
+    p = o.poses()[0]
+    np.testing.assert_allclose(p[:3], [3.0, 1.0, -1.0], atol=1e-7)
+    np.testing.assert_allclose(p[3:] * np.sign(p[6]), target_q, atol=1e-7)
+
+
+def test_priors_pull_a_drifting_chain_back():
+    """Sphere graph with odometry edges only (no loop closures) + XYZ priors from the truth on every 5th vertex: the optimum is far
+    closer to the truth than the chained odometry, and typed and untyped set_graph agree when no prior is present."""
+    g = G.sphere(20, 5, seed=3)
+    odo = np.flatnonzero(np.abs(g["ij"][:, 0] - g["ij"][:, 1]) == 1)
+    ij, meas, info, hub = g["ij"][odo], g["meas7"][odo], g["info21"][odo], g["huber"][odo]
+    o0 = P.OraclePGO(); o0.set_graph(g["poses7"], ij, meas, info, hub)
+    o1 = P.OraclePGO(); o1.set_graph(g["poses7"], ij, meas, info, hub, None, np.zeros(len(ij), np.int32))
+    assert o0.errors()[2] == o1.errors()[2]
+    iu = np.triu_indices(6)
+    I6 = np.zeros((6, 6)); I6[:3, :3] = np.eye(3) * 25
+    vs = np.arange(0, len(g["poses7"]), 5)
+    pm = np.zeros((len(vs), 7)); pm[:, :3] = g["truth7"][vs, :3]
+    o = P.OraclePGO()
+    o.set_graph(g["poses7"], np.vstack([ij, np.stack([vs, vs], 1)]).astype(np.int32), np.vstack([meas, pm]), np.vstack([info, np.tile(I6[iu], (len(vs), 1))]),
+                np.r_[hub, np.zeros(len(vs))], None, np.r_[np.zeros(len(ij)), np.full(len(vs), 2)].astype(np.int32))
+    r = o.optimize(100, P.ALG_LM, P.SOLVER_DENSE)
+    assert r["iterations"] > 0
+    before = np.abs(g["poses7"][:, :3] - g["truth7"][:, :3]).max()
+    after = np.abs(o.poses()[:, :3] - g["truth7"][:, :3]).max()
+    assert after < 0.25 * before, (before, after)
