@@ -67,8 +67,11 @@ __device__ __forceinline__ void transform_point(const float* T, float x, float y
 // bpp partials in a fixed order (run-to-run deterministic), deposits (score, g, H) in the pair's AlignState and advances the
 // Newton / More-Thuente state machine so that the next launch knows what to evaluate.  s_scratch: >= 704 doubles of shared memory.
 // The tail is what a single-pair align waits for between two evaluations, so it is kept short: the partials are fetched with every
-// load of a thread in flight at once (11 row groups x 22 column pairs of threads, double2 loads), and the ~0.9 KB state is copied to shared memory once,
+// load of a thread in flight at once (10 row groups x 22 column pairs of threads, double2 loads), and the ~0.9 KB state is copied to shared memory once,
 // advanced there by one thread (6x6 solve, SE(3) exp / log) and copied back once, instead of being walked field by field in L2.
+// The pose composition log(exp(dir a_t) exp(p)) the state machine asks for at the end of a line search (~4.6 us of serial fp64 sin / cos /
+// atan2 on one thread) depends on nothing this evaluation computes: warp 7 takes no part in the reduction (warps 0-6 synchronise among
+// themselves on named barrier 1) and works it out meanwhile, joining the others just before the state machine runs.
 __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int kind, int nv, int n_src, double* s_scratch, int* s_last, long long t_entry = 0) {
   AlignState& S = L.d_states[pair];
   const bool dbg = L.d_dbg != nullptr && threadIdx.x == 0;
@@ -87,20 +90,39 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   __threadfence();
   if (dbg) stamp[2] = clock64();
   __shared__ __align__(16) AlignState s_state;
+  __shared__ double s_lu[6][7], s_dp[6], s_pn[6], s_pn_at;
+  __shared__ int s_perm[6], s_lu_ok, s_pn_ok;
   static_assert(sizeof(AlignState) % 4 == 0, "AlignState is copied word by word");
   {
     const int* src = reinterpret_cast<const int*>(&S);
     int* dst = reinterpret_cast<int*>(&s_state);
     for (int i = threadIdx.x; i < (int)(sizeof(AlignState) / 4); i += kEvalThreads) dst[i] = __ldcg(src + i);
   }
-  constexpr int R = 11;                  // row groups x 22 column pairs = 242 of the 256 threads, one double2 per load
-  static_assert(R * (kPartialStride / 2) <= kEvalThreads && R * 64 <= 1024, "reduction layout");
+  __syncthreads();
+  constexpr int kSumThreads = kEvalThreads - 32;          // warps 0-6 reduce, warp 7 composes the pose
+  const bool composer = threadIdx.x >= kSumThreads;
+#define LVS_SUB_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(kSumThreads) : "memory")
+  if (composer) {
+    if (L.advance && threadIdx.x == kSumThreads) {
+      const bool useful = s_state.phase == PH_MT_FIRST || s_state.phase == PH_MT_TRIAL || s_state.phase == PH_HESS27;
+      if (useful) {
+        double delta[6], pn[6];
+        for (int i = 0; i < 6; i++) delta[i] = s_state.dir[i] * s_state.a_t;
+        se3_log(se3_mul(se3_exp(delta), se3_exp(s_state.p)), pn);
+        for (int i = 0; i < 6; i++) s_pn[i] = pn[i];
+        s_pn_at = s_state.a_t;
+      }
+      s_pn_ok = useful ? 1 : 0;
+    }
+  } else {
+  constexpr int R = 10;                  // row groups x 22 column pairs = 220 of the 224 reducing threads, one double2 per load
+  static_assert(R * (kPartialStride / 2) <= kSumThreads && R * 64 <= 1024, "reduction layout");
   {
     const int kp = threadIdx.x % (kPartialStride / 2), r = threadIdx.x / (kPartialStride / 2);
     double x0 = 0, x1 = 0;
     if (r < R && 2 * kp < nv) {
       const double2* base = reinterpret_cast<const double2*>(L.d_partials + (size_t)pair * bpp * kPartialStride) + kp;
-      constexpr int kIn = 14;            // loads in flight per thread
+      constexpr int kIn = 15;            // loads in flight per thread (444 CTAs of a single pair: three passes)
       for (int b0 = r; b0 < bpp; b0 += R * kIn) {
         double2 v[kIn];
 #pragma unroll
@@ -111,7 +133,7 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
     }
     if (r < R) { s_scratch[r * 64 + 2 * kp] = x0; s_scratch[r * 64 + 2 * kp + 1] = x1; }
   }
-  __syncthreads();
+  LVS_SUB_SYNC();
   if (dbg) stamp[3] = clock64();
   double x = 0;
   if (threadIdx.x < nv)
@@ -126,14 +148,14 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
     if (threadIdx.x < nv)
       for (int p = 0; p < sh.world; p++) *reinterpret_cast<volatile double*>(sh.peers[p] + rec + threadIdx.x) = x;
     __threadfence_system();
-    __syncthreads();
+    LVS_SUB_SYNC();
     if (threadIdx.x < sh.world) {    // one flag store per peer, after every value store of this CTA is visible system-wide
       __threadfence_system();
       *reinterpret_cast<volatile long long*>(sh.peers[threadIdx.x] + rec + 43) = serial;
     }
     __shared__ int s_peer_ok;
     if (threadIdx.x == 0) s_peer_ok = 1;
-    __syncthreads();
+    LVS_SUB_SYNC();
     if (threadIdx.x < sh.world) {
       const volatile long long* flag =
           reinterpret_cast<const volatile long long*>(sh.mine + (((size_t)(serial & 1) * sh.world + threadIdx.x) * sh.cap + pair) * kMailStride + 43);
@@ -144,7 +166,7 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
       }
     }
     __threadfence_system();
-    __syncthreads();
+    LVS_SUB_SYNC();
     if (!s_peer_ok && threadIdx.x == 0) *sh.d_error = 1;
     if (threadIdx.x < nv) {
       x = 0;
@@ -163,24 +185,9 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   }
   // computeDerivatives zeroes the Hessian even when it does not fill it (ndt_omp_impl2.hpp:204)
   if (kind == EVAL_DERIV_NOH && threadIdx.x < 36) s_state.H[threadIdx.x] = 0.0;
-  __syncthreads();
+  LVS_SUB_SYNC();
   if (dbg) stamp[4] = clock64();
   // Newton direction H^-1 (-g) of this evaluation, by warp 1 (the state machine asks for it in almost every pass)
-  // and, by one thread of warp 2 at the same time, the pose composition log(exp(dir a_t) exp(p)) the state machine will ask for if this
-  // evaluation ends a line search (the normal case): two chains of fp64 transcendentals that do not depend on each other
-  __shared__ double s_lu[6][7], s_dp[6], s_pn[6], s_pn_at;
-  __shared__ int s_perm[6], s_lu_ok, s_pn_ok;
-  if (L.advance && threadIdx.x == 64) {
-    const bool useful = s_state.phase == PH_MT_FIRST || s_state.phase == PH_MT_TRIAL || s_state.phase == PH_HESS27;
-    if (useful) {
-      double delta[6], pn[6];
-      for (int i = 0; i < 6; i++) delta[i] = s_state.dir[i] * s_state.a_t;
-      se3_log(se3_mul(se3_exp(delta), se3_exp(s_state.p)), pn);
-      for (int i = 0; i < 6; i++) s_pn[i] = pn[i];
-      s_pn_at = s_state.a_t;
-    }
-    s_pn_ok = useful ? 1 : 0;
-  }
   if (L.advance && threadIdx.x >= 32 && threadIdx.x < 64) {
     const int lane = threadIdx.x - 32;
     for (int e = lane; e < 42; e += 32) s_lu[e / 7][e % 7] = (e % 7 < 6) ? s_state.H[(e / 7) * 6 + e % 7] : -s_state.g[e / 7];
@@ -188,6 +195,8 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
     const bool ok = lu6_solve_warp(s_lu, s_perm, s_dp, lane);
     if (lane == 0) s_lu_ok = ok ? 1 : 0;
   }
+  }      // warps 0-6
+#undef LVS_SUB_SYNC
   __syncthreads();
   if (dbg) stamp[5] = clock64();
   bool fin = false;
