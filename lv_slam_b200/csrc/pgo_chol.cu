@@ -224,6 +224,18 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
     std::vector<int> fill(S.level_ptr.begin(), S.level_ptr.end() - 1);
     for (int s = 0; s < nf; s++) S.level_fronts[fill[S.fronts[s].level]++] = s;
   }
+  if (getenv("LVS_CHOL_HIST")) {     // diagnostics: fronts per level by size class
+    for (int l = 0; l <= max_level; l++) {
+      int cnt[6] = {0, 0, 0, 0, 0, 0}, maxp = 0, maxF = 0, maxkids = 0;
+      for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; k++) {
+        const CholFront& f = S.fronts[S.level_fronts[k]];
+        cnt[f.F <= 32 ? 0 : f.F <= 48 ? 1 : f.F <= 64 ? 2 : f.F <= 96 ? 3 : f.F <= 192 ? 4 : 5]++;
+        maxp = std::max(maxp, 6 * f.w); maxF = std::max(maxF, f.F); maxkids = std::max(maxkids, f.child_end - f.child_begin);
+      }
+      fprintf(stderr, "[chol hist] level %2d: F<=32 %4d  <=48 %4d  <=64 %4d  <=96 %4d  <=192 %4d  >192 %4d   max F %4d  max pivots %4d  max children %d\n", l, cnt[0], cnt[1], cnt[2], cnt[3],
+              cnt[4], cnt[5], maxF, maxp, maxkids);
+    }
+  }
   // scatter maps
   S.diag_dst.resize(n); S.diag_ld.resize(n); S.rhs_dst.resize(n);
   for (int v = 0; v < n; v++) {
