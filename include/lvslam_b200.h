@@ -70,6 +70,11 @@ typedef struct {
   int32_t min_points_per_voxel;  /* VoxelGridCovariance default 6 (voxel_grid_covariance_omp.h:204) */
   double min_covar_eigvalue_mult; /* 0.01 (voxel_grid_covariance_omp.h:205) */
   int32_t accumulation;        /* lvs_ndt_accumulation; not a reference parameter (LVS_ACC_EXACT) */
+  int32_t lean_final_evaluation; /* not a reference parameter (0).  1: the derivative pass that ENDS an align computes the score and the
+                                * gradient only.  The reference computes that pass's Hessian too and never reads it: whether the step just
+                                * taken ends the iteration is known before the pass (its More-Thuente loop is dead code for step_size >
+                                * epsilon / 2, ndt_omp_impl2.hpp:888-891, so the step length is fixed beforehand; :175-179), and only the
+                                * pass's score survives (trans_probability_, :187).  Every result of align() is unchanged. */
 } lvs_ndt_params;
 
 /* What the reference object exposes after align(): getFinalTransformation, hasConverged,

@@ -25,7 +25,7 @@ class NdtParams(ctypes.Structure):
     _fields_ = [("resolution", ctypes.c_float), ("step_size", ctypes.c_double), ("outlier_ratio", ctypes.c_double),
                 ("transformation_epsilon", ctypes.c_double), ("max_iterations", ctypes.c_int32), ("search_method", ctypes.c_int32),
                 ("variant", ctypes.c_int32), ("min_points_per_voxel", ctypes.c_int32), ("min_covar_eigvalue_mult", ctypes.c_double),
-                ("accumulation", ctypes.c_int32)]
+                ("accumulation", ctypes.c_int32), ("lean_final_evaluation", ctypes.c_int32)]
 
 
 class NdtResult(ctypes.Structure):

@@ -43,6 +43,7 @@ static AlignConsts make_consts(const lvs_ndt_params& p) {
   c.variant = p.variant;
   c.resolution = p.resolution;
   c.fast = p.accumulation == LVS_ACC_FAST;
+  c.lean_final = p.lean_final_evaluation != 0;
   return c;
 }
 
@@ -902,6 +903,7 @@ void lvs_ndt_default_params(lvs_ndt_params* p) {
   p->min_points_per_voxel = 6;
   p->min_covar_eigvalue_mult = 0.01;
   p->accumulation = LVS_ACC_EXACT;
+  p->lean_final_evaluation = 0;
 }
 
 const char* lvs_status_string(int status) {

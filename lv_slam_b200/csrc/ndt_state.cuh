@@ -305,6 +305,9 @@ LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, 
       state_set_eval_point(s, x);
       for (int i = 0; i < 16; i++) s.final_T[i] = s.T[i];
       s.eval_kind = EVAL_DERIV_H;
+      // lean_final_evaluation: with the More-Thuente loop dead (interval_converged set above) the step length is final, so the test of
+      // :175-179 can be made now; when it will end the align, only the score of the coming pass is ever read (:187) - skip its Hessian
+      if (c.lean_final && s.interval_converged && (s.nr_iterations > c.max_iter || (s.nr_iterations && (fabs(s.a_t) < c.trans_eps)))) s.eval_kind = EVAL_DERIV_NOH;
       s.phase = PH_MT_FIRST;
       return false;
     }

@@ -96,6 +96,7 @@ struct AlignConsts {
   int variant;
   float resolution;
   int fast;                 // lvs_ndt_params::accumulation == LVS_ACC_FAST
+  int lean_final;           // lvs_ndt_params::lean_final_evaluation
 };
 
 // One (source, target) pair as the kernels see it.

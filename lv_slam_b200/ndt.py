@@ -170,6 +170,10 @@ class NormalDistributionsTransform:
         """Not a reference setter: LVS_ACC_EXACT (default, the reference's arithmetic) or LVS_ACC_FAST (tolerance mode)."""
         self._p.accumulation = int(mode); self._push()
 
+    def setLeanFinalEvaluation(self, on):
+        """Not a reference setter: skip the Hessian of the derivative pass that ends an align (nothing reads it); results unchanged."""
+        self._p.lean_final_evaluation = 1 if on else 0; self._push()
+
     def getResolution(self):
         return self._p.resolution
 

@@ -255,6 +255,30 @@ def test_direct_solver_symbolic_analysis_on_the_host():
         chol_analyze(5, np.array([(3, 1)], np.int32))     # not (row < col)
 
 
+def test_relaxed_supernodes_keep_the_fill_and_shorten_the_tree():
+    """Relaxed amalgamation (a chain child joins its parent when that pads its columns with few explicit zeros) must not change the
+    ordering or the fill that is reported - only the fronts: fewer of them, fewer levels, some more arithmetic (host only)."""
+    from lv_slam_b200.synth import posegraph as G
+    g = G.sphere(50, 20, seed=11)
+    n = len(g["poses7"])
+    off = np.array(sorted({(min(a, b), max(a, b)) for a, b in np.asarray(g["ij"]) if a != b}), np.int32)
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); from lv_slam_b200.graph_slam import chol_analyze; "
+            "off = np.load(sys.argv[1]); st, perm = chol_analyze(int(sys.argv[2]), off); print(json.dumps([st, perm.tolist()]))" % ROOT)
+    import json, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        np.save(os.path.join(d, "off.npy"), off)
+        res = {}
+        for relax in ("0", "12"):
+            out = subprocess.run([sys.executable, "-c", code, os.path.join(d, "off.npy"), str(n)], capture_output=True, text=True,
+                                 env=dict(os.environ, LVS_CHOL_RELAX=relax), timeout=300)
+            assert out.returncode == 0, out.stderr[-1500:]
+            res[relax] = json.loads(out.stdout.strip().splitlines()[-1])
+    (s0, p0), (s1, p1) = res["0"], res["12"]
+    assert p0 == p1 and s0["nnz_l_blocks"] == s1["nnz_l_blocks"] == _elimination_game(n, off, np.array(p0))
+    assert s1["fronts"] < s0["fronts"] and s1["levels"] <= s0["levels"] and s0["factor_fma"] <= s1["factor_fma"] <= 1.1 * s0["factor_fma"]
+    assert s1["max_front"] == s0["max_front"]
+
+
 def test_host_marshalling_helpers():
     """CloudBatch / pack_guesses / AlignResults: the per-call host work of the batched API is a C call over prepared arrays, and the
     result records are numpy views of the C structs (no device needed)."""

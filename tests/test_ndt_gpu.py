@@ -199,6 +199,30 @@ def test_align_line_search_and_double_hessian_path(small_pair):
     assert r["n_hess"] > 0
 
 
+@pytest.mark.parametrize("variant,search,acc", [(O.VAR_OMP, O.DIRECT7, 0), (O.VAR_PCA, O.DIRECT1, 0), (O.VAR_OMP, O.DIRECT7, 1), (O.VAR_OMP, O.KDTREE, 0)])
+def test_lean_final_evaluation_changes_no_result(small_pair, scan_pair, variant, search, acc):
+    """lvs_ndt_params::lean_final_evaluation skips the Hessian of the derivative pass that ends an align - a result the reference
+    computes and never reads.  Everything align() exposes must stay bit-identical: final transform, iterations, converged flag,
+    evaluation counts, trans_probability, the per-iteration trace, the aligned cloud; and the corner where the line search is alive
+    (step_size <= epsilon / 2: the step is not known beforehand) must not be touched by it."""
+    for pair, kw in ((small_pair, dict(max_iter=30)), (scan_pair, dict(max_iter=64)), (small_pair, dict(max_iter=3)), (small_pair, dict(step_size=0.2, trans_eps=0.5, max_iter=6))):
+        if pair is scan_pair and search == O.KDTREE:
+            continue
+        tgt, src, guess, truth = pair
+        out = []
+        for lean in (0, 1):
+            n, _ = _mk(variant, search, **kw)
+            n.setAccumulation(acc); n.setLeanFinalEvaluation(lean)
+            n.setInputTarget(tgt); n.setInputSource(src)
+            cloud = n.align(guess, want_cloud=True)
+            out.append((n.result(), cloud, n.getFitnessScore(1.0)))
+        (a, ca, fa), (b, cb, fb) = out
+        assert np.array_equal(a["final"], b["final"]) and a["iterations"] == b["iterations"] and a["converged"] == b["converged"]
+        assert a["n_eval"] == b["n_eval"] and a["n_hess"] == b["n_hess"] and a["trans_probability"] == b["trans_probability"]
+        assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(ca, cb) and fa == fb
+        assert a["iterations"] >= 2
+
+
 def test_align_identity_guess_and_repeat(small_pair):
     tgt, src, guess, truth = small_pair
     n, o = _mk(O.VAR_OMP, O.DIRECT7, max_iter=20)
