@@ -681,6 +681,12 @@ def main_ours(args):
                                               and a["trans_probability"] == b["trans_probability"] for a, b in zip(res_top, sb.results)))}
         line["modes"]["lean_final_evaluation"] = r4
         sb.nb.close()
+        sb = StreamBench(*common, args.variant, other, buffers=top.buffers, lean=1)
+        r5 = sb.measure(args.steps, args.warmup, True)
+        r5["config"] = workload_config(args, n_pts, len(keys), accumulation=other)
+        r5["config"]["lean_final_evaluation"] = 1
+        line["modes"]["%s_lean_final_evaluation" % ("tolerance" if other == "fast" else "exact")] = r5
+        sb.nb.close()
         other_variant = "pca" if args.variant == "omp" else "omp"
         sub = {}
         for acc in ("exact", "fast"):

@@ -71,7 +71,8 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 
 // One (point, cell) contribution added into the lane's float sums.  pa = (x', y', z', xr), pb = (yr, zr): transformed point and
 // rotated point R*x; w: ndt_pca weight of this contribution (running product of the cell weights, ndt_pca_impl2.hpp:293-296).
-template <bool PCA, bool STAGE>
+// HESS = false (line-search trials, and the last pass of an align under lean_final_evaluation): score and gradient only.
+template <bool PCA, bool STAGE, bool HESS>
 __device__ __forceinline__ void fast_contribute(float (&A)[kFSlots], const FastRec* __restrict__ fr, const float4 pa, const float2 pb, float w,
                                                 float kexp, float gd1, float gd2) {
   float4 r0, r1, r2;
@@ -102,6 +103,7 @@ __device__ __forceinline__ void fast_contribute(float (&A)[kFSlots], const FastR
   A[0] += sc;
   A[1] = fmaf(e2, c0, A[1]); A[2] = fmaf(e2, c1, A[2]); A[3] = fmaf(e2, c2, A[3]);
   A[4] = fmaf(e2, a3, A[4]); A[5] = fmaf(e2, a4, A[5]); A[6] = fmaf(e2, a5, A[6]);
+  if (!HESS) return;
   // H_ij += e2 (-d2 a_i a_j + c.Hp_ij + (J^T C J)_ij)  =  b_i a_j + e2 N_ij  with b = -d2 e2 a
   const float k = -gd2 * e2;
   const float b0 = k * c0, b1 = k * c1, b2 = k * c2, b3 = k * a3, b4 = k * a4, b5 = k * a5;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(kEvalThreads, STAGE ? 2 : 3) ndt_eval_fast_ker
     if (bytes > 0 && bytes <= (unsigned)L.stage_bytes) { bulk_stage(s_recs, P.frecs, bytes, &s_bar); frecs = reinterpret_cast<const FastRec*>(s_recs); }
   }
   const int* __restrict__ grid = P.grid;
+  const bool hess = kind == EVAL_DERIV_H;          // CTA-uniform
   const float* T = s_T;
   const float* R = s_R;
 
@@ -219,7 +222,8 @@ __global__ void __launch_bounds__(kEvalThreads, STAGE ? 2 : 3) ndt_eval_fast_ker
     if (lane < n_round) {
       const int ent = q[head + lane];
       const int rec = ent / kFPtsPerIter, slot = ent % kFPtsPerIter;
-      fast_contribute<PCA, STAGE>(A, frecs + rec, pa[slot], pb[slot], PCA ? qw[head + lane] : 1.0f, kexp, gd1, gd2);
+      if (hess) fast_contribute<PCA, STAGE, true>(A, frecs + rec, pa[slot], pb[slot], PCA ? qw[head + lane] : 1.0f, kexp, gd1, gd2);
+      else fast_contribute<PCA, STAGE, false>(A, frecs + rec, pa[slot], pb[slot], PCA ? qw[head + lane] : 1.0f, kexp, gd1, gd2);
     }
     if (++since_flush == kFlushRounds) { fast_flush(A, accd, lane); since_flush = 0; }
   };

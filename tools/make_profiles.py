@@ -28,22 +28,29 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
     open("/tmp/_raw.csv", "w").write(raw)
     out = subprocess.run([sys.executable, "tools/ncu_summary.py", "/tmp/_raw.csv"], capture_output=True, text=True).stdout
     open(os.path.join(dst, base + "_ncu_summary.txt"), "w").write(out)
-    sp = subprocess.run(["ncu", "-i", os.path.join(src, rep), "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", ":::1"],
+    # the capture holds two launches of an align; the working one is the longest (the other may find nothing left to do)
+    rows = list(csv.reader(raw.splitlines()))
+    longest = 1
+    if len(rows) > 2 and 'gpu__time_duration.sum' in rows[0]:
+        di = rows[0].index('gpu__time_duration.sum')
+        durs = [float(r[di].replace(',', '')) for r in rows[2:]]
+        longest = 1 + durs.index(max(durs))
+    sp = subprocess.run(["ncu", "-i", os.path.join(src, rep), "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", ":::%d" % longest],
                         capture_output=True, text=True).stdout
     open("/tmp/_src.csv", "w").write(sp)
     out = subprocess.run([sys.executable, "tools/ncu_lines.py", "/tmp/_src.csv", "40"], capture_output=True, text=True).stdout
     open(os.path.join(dst, base + "_ncu_source_lines.txt"), "w").write(out)
-    # dram traffic of the first (working) launch, for bench.py's roofline.traffic
-    rows = list(csv.reader(raw.splitlines()))
+    # dram traffic of the working launch (per-capture record; profiles/ndt_eval_traffic.json, which bench.py quotes, is written by
+    # tools/ncu_kernel_stats.py from the same captures)
     if len(rows) > 2:
         h = rows[0]
         try:
-            rd = float(rows[2][h.index('dram__bytes_read.sum')]); wr = float(rows[2][h.index('dram__bytes_write.sum')])
+            r = rows[1 + longest]
+            rd = float(r[h.index('dram__bytes_read.sum')]); wr = float(r[h.index('dram__bytes_write.sum')])
             ur, uw = rows[1][h.index('dram__bytes_read.sum')], rows[1][h.index('dram__bytes_write.sum')]
             mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            json.dump({"kernel": rows[2][h.index('Kernel Name')], "dram_bytes_per_launch": rd * mul[ur] + wr * mul[uw],
-                       "duration_us_under_ncu": float(rows[2][h.index('gpu__time_duration.sum')]), "grid_size": rows[2][h.index('launch__grid_size')], "source": "%s/%s (ncu --set full, first captured launch)" % (name, rep)},
+            json.dump({"kernel": r[h.index('Kernel Name')], "dram_bytes_per_launch": rd * mul[ur] + wr * mul[uw],
+                       "duration_us_under_ncu": float(r[h.index('gpu__time_duration.sum')]), "grid_size": r[h.index('launch__grid_size')], "source": "%s/%s (ncu --set full, longest captured launch)" % (name, rep)},
                       open(os.path.join(dst, base + "_traffic.json"), "w"))
-            if base == "ndt_eval": shutil.copy(os.path.join(dst, base + "_traffic.json"), os.path.join("profiles", "ndt_eval_traffic.json"))   # what bench.py reports
         except (ValueError, KeyError): pass
 print(sorted(os.listdir(dst)))
