@@ -1132,7 +1132,8 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
     CUDA_TRY(cudaFuncSetAttribute(chol_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrontCfg<true>::bytes));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_front_kernel<true>, kCholThreads, FrontCfg<true>::bytes));
     C.coop_grid = std::max(1, std::min(per_sm, 2) * sms);
-    CUDA_TRY(cudaMalloc((void**)&C.bars, (size_t)C.coop_grid * sizeof(unsigned int)));
+    // one set of team barrier counters per cooperative launch of a solve (2 per level at most), zeroed by ONE memset per solve
+    CUDA_TRY(cudaMalloc((void**)&C.bars, (size_t)C.coop_grid * (2 * std::max(C.n_levels, 1)) * sizeof(unsigned int)));
     C.allocs.push_back((void*)C.bars);
     CUDA_TRY(cudaMalloc((void**)&C.back_scratch, (size_t)C.coop_grid * 2 * kBNB * ((S.max_front + 255) / 256) * sizeof(double)));      // [team][2 parity][kBNB][chunks of 256 rows]
     C.allocs.push_back((void*)C.back_scratch);
@@ -1142,6 +1143,7 @@ int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st
   CUDA_TRY(cudaStreamCreateWithFlags(&C.side, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&C.ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&C.ev_join, cudaEventDisableTiming));
+
   C.arena_doubles = S.arena;
   cudaError_t e = cudaMalloc((void**)&C.arena, std::max<long long>(1, S.arena) * sizeof(double));
   if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(LVS_ERR_OOM, "frontal arena allocation failed (%lld MB)", (long long)(S.arena * 8 >> 20)); }
@@ -1167,6 +1169,7 @@ void chol_free(CholDevice& C) {
   if (C.side) cudaStreamDestroy(C.side);
   if (C.ev_fork) cudaEventDestroy(C.ev_fork);
   if (C.ev_join) cudaEventDestroy(C.ev_join);
+
   for (void* p : C.allocs) cudaFree(p);
   C = CholDevice();
 }
@@ -1178,8 +1181,12 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   V.diag_dst = C.diag_dst; V.off_dst = C.off_dst; V.rhs_dst = C.rhs_dst; V.diag_ld = C.diag_ld; V.off_ld = C.off_ld; V.off_tr = C.off_tr;
   V.arena = C.arena; V.xp = C.xp; V.fail_flag = C.fail_flag; V.n = C.n; V.n_off = C.n_off;
   V.dbg = C.dbg; V.wscratch = C.wscratch;
+  // (zeroing the arena on the side stream right after the previous solve's last kernel was measured: 2.53 -> 2.46 ms for an isolated solve, but
+  // 0.4 ms SLOWER per LM run - there the update / error kernels follow the solve at once and the memset only gets in their way)
   CUDA_TRY(cudaMemsetAsync(C.arena, 0, (size_t)C.arena_doubles * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(C.fail_flag, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)C.coop_grid * (2 * std::max(C.n_levels, 1)) * sizeof(unsigned int), st));
+  unsigned int* bars_next = C.bars;
   const long long total = (long long)C.n * 36 + (long long)C.n_off * 36 + (long long)C.n * 6;
   chol_scatter_kernel<<<(unsigned)((total + kCholThreads - 1) / kCholThreads), kCholThreads, 0, st>>>(V, Hd, Ho, b, lambda);
   int nl = 1;
@@ -1204,8 +1211,8 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
       int n_list = nb;
       if (team_size == 1) chol_front_kernel<false><<<grid, kCholThreads, FrontCfg<false>::bytes, st>>>(V, list, n_list, 1, C.bars);
       else {
-        CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)n_teams * sizeof(unsigned int), st));
-        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars};
+        unsigned int* bars = bars_next; bars_next += C.coop_grid;
+        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&bars};
         CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_front_kernel<true>, dim3(grid), dim3(kCholThreads), args, FrontCfg<true>::bytes, st));
       }
       nl++;
@@ -1226,8 +1233,8 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
       if (team_size == 1) chol_backward_kernel<<<nbig, kCholThreads, smem, st>>>(V, list);
       else {
         int grid = n_teams * team_size;
-        CUDA_TRY(cudaMemsetAsync(C.bars, 0, (size_t)n_teams * sizeof(unsigned int), st));
-        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&C.bars, (void*)&C.back_scratch, (void*)&max_chunks};
+        unsigned int* bars = bars_next; bars_next += C.coop_grid;
+        void* args[] = {(void*)&V, (void*)&list, (void*)&n_list, (void*)&team_size, (void*)&bars, (void*)&C.back_scratch, (void*)&max_chunks};
         CUDA_TRY(cudaLaunchCooperativeKernel((const void*)chol_backward_team_kernel, dim3(grid), dim3(kCholThreads), args, smem + kBNB * (kBNB + 1) * sizeof(double), st));
       }
       nl++;
@@ -1240,6 +1247,7 @@ int chol_solve(CholDevice& C, cudaStream_t st, const double* Hd, const double* H
   }
   chol_finish_kernel<<<1, 1024, 0, st>>>(V, b, lambda, x, scale_out, ok_out);
   nl++;
+
   if (C.dbg) {
     cudaStreamSynchronize(st);
     for (int r = 0; r < 2; r++)
