@@ -282,7 +282,12 @@ int lvs_pgo_set_graph(lvs_pgo_t* h, int n_vertices, const double* poses7, const 
  * meas7 row carries  xy | xyz | qx qy qz qw | direction(3) measurement(3)  and the info21 row the D x D information matrix in the top-left
  * corner of the 6 x 6 upper triangle (D = 2 for XY, 3 otherwise; the other entries must be zero).  Edges keep their order in the list, which is
  * g2o's active-edge order (ascending edge id). */
-enum { LVS_PGO_EDGE_SE3 = 0, LVS_PGO_EDGE_PRIOR_XY = 1, LVS_PGO_EDGE_PRIOR_XYZ = 2, LVS_PGO_EDGE_PRIOR_QUAT = 3, LVS_PGO_EDGE_PRIOR_VEC = 4 };
+enum { LVS_PGO_EDGE_SE3 = 0, LVS_PGO_EDGE_PRIOR_XY = 1, LVS_PGO_EDGE_PRIOR_XYZ = 2, LVS_PGO_EDGE_PRIOR_QUAT = 3, LVS_PGO_EDGE_PRIOR_VEC = 4, LVS_PGO_EDGE_SE3_PLANE = 5 };
+/* LVS_PGO_EDGE_SE3_PLANE: the floor constraint, EdgeSE3Plane (include/g2o/edge_se3_plane.hpp) between a pose and the ONE plane vertex the nodelet creates
+ * and fixes (add_plane_node + setFixed(true), global_graph_nodelet.cpp:601-611; GraphSLAM::add_se3_plane_edge, graph_slam.cpp:148-158): with that vertex fixed
+ * the edge constrains the pose alone.  Its meas7 row carries the measured plane's 4 coefficients, info21 the 3 x 3 information; the vertex's plane is
+ * set once per handle, before set_graph (default 0 0 1 0, the nodelet's). */
+int lvs_pgo_set_floor_plane(lvs_pgo_t* h, const double coeffs[4]);
 int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, const uint8_t* fixed, int n_edges, const int32_t* ij,
                             const double* meas7, const double* info21, const double* huber_delta, const int32_t* edge_type);
 int lvs_pgo_set_poses(lvs_pgo_t* h, const double* poses7);          /* VertexSE3::setEstimate for every vertex */

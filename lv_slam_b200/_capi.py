@@ -79,7 +79,7 @@ def lib():
             "lvs_ndt_batch_align": [vp, i32, vp, vp, vp, vp], "lvs_ndt_batch_last_stats": [vp, vp, vp, vp, vp],
             "lvs_ndt_batch_set_profiling": [vp, i32], "lvs_ndt_batch_set_tuning": [vp, i32, i32, i32],
             "lvs_pgo_create": [i32, i32, vp, vp], "lvs_pgo_destroy": [vp], "lvs_pgo_set_graph": [vp, i32, vp, vp, i32, vp, vp, vp, vp],
-            "lvs_pgo_set_graph_typed": [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp],
+            "lvs_pgo_set_graph_typed": [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp], "lvs_pgo_set_floor_plane": [vp, vp],
             "lvs_pgo_set_poses": [vp, vp], "lvs_pgo_optimize": [vp, i32, vp], "lvs_pgo_get_poses": [vp, vp], "lvs_pgo_get_trace": [vp, vp, i32, vp],
             "lvs_pgo_set_solver_options": [vp, ctypes.c_double, i32], "lvs_pgo_compute_errors": [vp, vp, vp, vp],
             "lvs_pgo_system_size": [vp, vp, vp], "lvs_pgo_linearize": [vp, vp, vp, vp, vp],

@@ -52,7 +52,7 @@ struct PgoDev {
   const double* info; const double* huber;
   const unsigned char* edge_tr;
   const int* edge_type;         // null: every edge is an EdgeSE3; else 0 EdgeSE3, 1-4 unary priors (vertex i == j)
-  const double* pm;             // [ne][6] measurements of the unary priors (edge_type != null)
+  const double* pm;             // [ne][8] measurements of the unary priors (edge_type != null)
   double* ws; double* err; double* chi;
   const int* vptr; const int* vinc;     // block row -> (edge * 2 + role) ascending
   const int* optr; const int* oinc;     // off block -> edges ascending
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kPgoThreads) pgo_errors_kernel(PgoDev D) {
     const int2 ij = D.edge_ij[k];
     double e[6];
     const int ty = D.edge_type ? D.edge_type[k] : 0;
-    if (ty) prior_error(ty, D.pm + (size_t)k * 6, D.pose[ij.x], e);
+    if (ty) prior_error(ty, D.pm + (size_t)k * 8, D.pose[ij.x], e);
     else edge_error(D.Zinv[k], D.pose[ij.x], D.pose[ij.y], e);
     const double c = chi2_of(D.info + (size_t)k * 36, e);
 #pragma unroll
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) pgo_linearize_kernel(PgoDev D) {
   if (h.x < 0 && h.y < 0) return;
   double A[36], B[36];
   const int ty = D.edge_type ? D.edge_type[k] : 0;
-  if (ty) prior_jacobian(ty, D.pm + (size_t)k * 6, D.pose[ij.x], A);      // unary: only the (i, i) block and b_i exist
+  if (ty) prior_jacobian(ty, D.pm + (size_t)k * 8, D.pose[ij.x], A);      // unary: only the (i, i) block and b_i exist
   else edge_gradient(D.Z[k], D.pose[ij.x], D.pose[ij.y], A, B);
   const double* info = D.info + (size_t)k * 36;
   double e[6];
@@ -349,12 +349,14 @@ __global__ void pgo_unpack_poses_kernel(const Rt* __restrict__ in, int n, double
   if (v < n) rt_to_qt7(in[v], p7 + (size_t)v * 7);
 }
 __global__ void pgo_pack_edges_kernel(const double* __restrict__ m7, const double* __restrict__ info21, int n, Rt* __restrict__ Z, Rt* __restrict__ Zinv,
-                                      double* __restrict__ info, const int* __restrict__ edge_type, double* __restrict__ pm) {
+                                      double* __restrict__ info, const int* __restrict__ edge_type, double* __restrict__ pm, double fp0, double fp1, double fp2,
+                                      double fp3) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int ty = edge_type ? edge_type[k] : 0;
   const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
-  if (ty) prior_set_measurement(ty, m7 + (size_t)k * 7, pm + (size_t)k * 6);
+  const double floor_plane[4] = {fp0, fp1, fp2, fp3};
+  if (ty) prior_set_measurement(ty, m7 + (size_t)k * 7, pm + (size_t)k * 8, floor_plane);
   const Rt z = rt_from_qt7(ty ? ident : m7 + (size_t)k * 7);
   Z[k] = z; Zinv[k] = rt_inv(z);
   const double* u = info21 + (size_t)k * 21;
@@ -383,6 +385,7 @@ struct lvs_pgo {
   long long chol_nnz_l = 0; double chol_flops = 0; int chol_fronts = 0, chol_levels = 0, chol_max_front = 0;
   int solve_launches = 0;          // kernel launches of the linear solves since the last optimize() started
   std::vector<lvs_pgo_iter_rec> trace;
+  double floor_plane[4] = {0.0, 0.0, 1.0, 0.0};   // the fixed VertexPlane of the LVS_PGO_EDGE_SE3_PLANE rows (lvs_pgo_set_floor_plane)
 };
 
 namespace lvs {
@@ -519,7 +522,7 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
     // a unary prior is carried as a self-edge (i, i): no off-diagonal block, one incidence on vertex i
     ij_fixed.assign(ij_in, ij_in + (size_t)n_edges * 2);
     for (int k = 0; k < n_edges; k++) {
-      if (edge_type[k] < LVS_PGO_EDGE_SE3 || edge_type[k] > LVS_PGO_EDGE_PRIOR_VEC) return fail(LVS_ERR_INVALID_ARG, "edge %d has unknown kind %d", k, edge_type[k]);
+      if (edge_type[k] < LVS_PGO_EDGE_SE3 || edge_type[k] > LVS_PGO_EDGE_SE3_PLANE) return fail(LVS_ERR_INVALID_ARG, "edge %d has unknown kind %d", k, edge_type[k]);
       if (edge_type[k] != LVS_PGO_EDGE_SE3) ij_fixed[2 * k + 1] = ij_fixed[2 * k];
     }
     ij = ij_fixed.data();
@@ -617,7 +620,7 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
       (rc = dev_alloc(h, &d_stage_m, (size_t)ne * 7)) || (rc = dev_alloc(h, &d_stage_i, (size_t)ne * 21))) { free_graph(h); return rc; }
   if (edge_type) {
     std::vector<int> ty(edge_type, edge_type + ne);
-    if ((rc = dev_upload(h, &d_type, ty)) || (rc = dev_alloc(h, &d_pm, (size_t)ne * 6))) { free_graph(h); return rc; }
+    if ((rc = dev_upload(h, &d_type, ty)) || (rc = dev_alloc(h, &d_pm, (size_t)ne * 8))) { free_graph(h); return rc; }
   }
   D.Z = d_Z; D.Zinv = d_Zinv; D.info = d_info; D.huber = d_huber; D.edge_type = d_type; D.pm = d_pm;
   CUDA_TRY(cudaMemsetAsync(D.ticket, 0, 4 * sizeof(unsigned int), h->st));
@@ -631,7 +634,8 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
   if (ne) {
     CUDA_TRY(cudaMemcpyAsync(d_stage_m, meas7, (size_t)ne * 7 * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CUDA_TRY(cudaMemcpyAsync(d_stage_i, info21, (size_t)ne * 21 * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    pgo_pack_edges_kernel<<<blocks_for(ne), kPgoThreads, 0, h->st>>>(d_stage_m, d_stage_i, ne, d_Z, d_Zinv, d_info, d_type, d_pm);
+    pgo_pack_edges_kernel<<<blocks_for(ne), kPgoThreads, 0, h->st>>>(d_stage_m, d_stage_i, ne, d_Z, d_Zinv, d_info, d_type, d_pm, h->floor_plane[0], h->floor_plane[1], h->floor_plane[2],
+                                                                     h->floor_plane[3]);
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -647,6 +651,13 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
     h->chol_levels = (int)sym.level_ptr.size() - 1; h->chol_max_front = sym.max_front;
   }
   h->has_graph = true;
+  return LVS_OK;
+}
+
+int lvs_pgo_set_floor_plane(lvs_pgo_t* h, const double coeffs[4]) {
+  if (!h || !coeffs) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  if (!((coeffs[0] * coeffs[0] + coeffs[1] * coeffs[1]) + coeffs[2] * coeffs[2] > 0.0)) return fail(LVS_ERR_INVALID_ARG, "the plane's normal is zero");
+  for (int a = 0; a < 4; a++) h->floor_plane[a] = coeffs[a];
   return LVS_OK;
 }
 

@@ -81,8 +81,29 @@ LVS_HD void edge_error(const Rt& Zinv, const Rt& Xi, const Rt& Xj, double* e) { 
 // LVS_PGO_EDGE_PRIOR_* of include/lvslam_b200.h).  Errors are zero-padded to 6 so that the 6-vector / 6 x 6 code of the binary edge is reused.
 // setMeasurement: PriorQuat keeps w >= 0 (edge_se3_priorquat.hpp:52-57), PriorVec normalises direction and measurement
 // (edge_se3_priorvec.hpp:50-53).  m = xy | xyz | qx qy qz qw | direction(3) measurement(3).
-LVS_HD void prior_set_measurement(int type, const double* m, double* pm) {
-  for (int a = 0; a < 6; a++) pm[a] = 0.0;
+// Kind 5: EdgeSE3Plane (include/g2o/edge_se3_plane.hpp) against a FIXED VertexPlane - the floor constraint as the nodelet builds it: one plane node,
+// fixed at creation (global_graph_nodelet.cpp:601-611) - i.e. a unary constraint on the pose.  pm = measured plane (4), the vertex's plane (4), both
+// as g2o's Plane3D keeps them (g2o types/slam3d_addons/plane3d.h: scaled to a unit normal).
+LVS_HD void plane_normalize(double* c) { const double n = sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]); const double k = 1. / n; for (int a = 0; a < 4; a++) c[a] = c[a] * k; }
+LVS_HD double plane_azimuth(const double* v) { return atan2(v[1], v[0]); }
+LVS_HD double plane_elevation(const double* v) { return atan2(v[2], sqrt(v[0] * v[0] + v[1] * v[1])); }
+LVS_HD void plane_rotation(const double* n, double* R) {      // Plane3D::rotation: AngleAxis(azimuth, Z) * AngleAxis(-elevation, Y), a quaternion product in Eigen
+  const double az = plane_azimuth(n), el = plane_elevation(n);
+  const Q4 q1 = {cos(0.5 * az), 0.0, 0.0, sin(0.5 * az)}, q2 = {cos(-0.5 * el), 0.0, sin(-0.5 * el), 0.0};
+  Q4 q;
+  q.w = q1.w * q2.w - q1.x * q2.x - q1.y * q2.y - q1.z * q2.z;
+  q.x = q1.w * q2.x + q1.x * q2.w + q1.y * q2.z - q1.z * q2.y;
+  q.y = q1.w * q2.y + q1.y * q2.w + q1.z * q2.x - q1.x * q2.z;
+  q.z = q1.w * q2.z + q1.z * q2.w + q1.x * q2.y - q1.y * q2.x;
+  quat_to_mat(q, R);
+}
+
+LVS_HD void prior_set_measurement(int type, const double* m, double* pm, const double* floor_plane) {
+  for (int a = 0; a < 8; a++) pm[a] = 0.0;
+  if (type == 5) {
+    for (int a = 0; a < 4; a++) { pm[a] = m[a]; pm[4 + a] = floor_plane[a]; }
+    plane_normalize(pm); plane_normalize(pm + 4);
+  }
   if (type == 1) { pm[0] = m[0]; pm[1] = m[1]; }
   else if (type == 2) { pm[0] = m[0]; pm[1] = m[1]; pm[2] = m[2]; }
   else if (type == 3) { const double sg = m[3] < 0.0 ? -1.0 : 1.0; for (int a = 0; a < 4; a++) pm[a] = sg * m[a]; }
@@ -117,6 +138,19 @@ LVS_HD void prior_error(int type, const double* pm, const Rt& X, double* e) {
     const double id = 1.0 / det;
 #pragma unroll
     for (int r = 0; r < 3; r++) e[r] = (((cof[r] * id) * pm[0] + (cof[3 + r] * id) * pm[1]) + (cof[6 + r] * id) * pm[2]) - pm[3 + r];
+  } else if (type == 5) {
+    // local_plane = X^-1 * plane (operator*(Isometry3d, Plane3D)); error = local_plane.ominus(measurement) (edge_se3_plane.hpp:40-47)
+    const Rt w2n = rt_inv(X);
+    double lp[4];
+#pragma unroll
+    for (int r = 0; r < 3; r++) lp[r] = (w2n.R[r * 3] * pm[4] + w2n.R[r * 3 + 1] * pm[5]) + w2n.R[r * 3 + 2] * pm[6];
+    lp[3] = pm[7] - ((w2n.t[0] * lp[0] + w2n.t[1] * lp[1]) + w2n.t[2] * lp[2]);
+    plane_normalize(lp);
+    double R[9], n[3];
+    plane_rotation(lp, R);
+#pragma unroll
+    for (int r = 0; r < 3; r++) n[r] = (R[r] * pm[0] + R[3 + r] * pm[1]) + R[6 + r] * pm[2];
+    e[0] = plane_azimuth(n); e[1] = plane_elevation(n); e[2] = (-lp[3]) - (-pm[3]);
   }
 }
 

@@ -47,9 +47,30 @@ class EdgeSE3:
 
 
 # unary priors on a VertexSE3 (include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp): kind -> (LVS_PGO_EDGE_* code, g2o tag, measurement length)
-EDGE_SE3, PRIOR_XY, PRIOR_XYZ, PRIOR_QUAT, PRIOR_VEC = 0, 1, 2, 3, 4
+EDGE_SE3, PRIOR_XY, PRIOR_XYZ, PRIOR_QUAT, PRIOR_VEC, SE3_PLANE = 0, 1, 2, 3, 4, 5
 _PRIOR_TAGS = {PRIOR_XY: ("EDGE_SE3_PRIORXY", 2, 2), PRIOR_XYZ: ("EDGE_SE3_PRIORXYZ", 3, 3), PRIOR_QUAT: ("EDGE_SE3_PRIORQUAT", 4, 3),
-               PRIOR_VEC: ("EDGE_SE3_PRIORVEC", 6, 3)}
+               PRIOR_VEC: ("EDGE_SE3_PRIORVEC", 6, 3), SE3_PLANE: ("EDGE_SE3_PLANE", 4, 3)}
+
+
+class VertexPlane:
+    """g2o::VertexPlane as the floor detection uses it: one node, fixed at creation (global_graph_nodelet.cpp:601-604).  The estimate is a
+    Plane3D: the four coefficients scaled to a unit normal."""
+
+    def __init__(self, vid, coeffs):
+        c = np.array(coeffs, dtype=np.float64).ravel()
+        self._id, self._c, self._fixed = vid, c / np.linalg.norm(c[:3]), False
+
+    def id(self):
+        return self._id
+
+    def estimate(self):
+        return self._c.copy()
+
+    def setFixed(self, f):
+        self._fixed = bool(f)
+
+    def fixed(self):
+        return self._fixed
 
 
 class EdgeSE3Prior:
@@ -64,10 +85,13 @@ class EdgeSE3Prior:
             m = -m
         if kind == PRIOR_VEC:
             m = np.concatenate([m[:3] / np.linalg.norm(m[:3]), m[3:] / np.linalg.norm(m[3:])])
+        if kind == SE3_PLANE:
+            m = m / np.linalg.norm(m[:3])
         self.measurement = m
         d = _PRIOR_TAGS[kind][2]
         self.information = np.array(information, dtype=np.float64).reshape(d, d)
         self.kernel = None
+        self.plane = None           # SE3_PLANE: the VertexPlane
 
 
 class GraphSLAM:
@@ -78,7 +102,7 @@ class GraphSLAM:
         self._solver_type = solver_type
         self._device = device
         self._h = None                      # the device object is created on first optimize()
-        self._vertices, self._edges = [], []
+        self._vertices, self._edges, self._planes = [], [], []
         self.last_stats = None
 
     def _handle(self):
@@ -113,7 +137,7 @@ class GraphSLAM:
 
     def add_se3_node(self, pose4x4):
         # id = current vertex count (graph_slam.cpp:108); after load() of a file with other ids, the next free one
-        vid = max(len(self._vertices), getattr(self, "_next_id", 0))
+        vid = max(len(self._vertices) + len(self._planes), getattr(self, "_next_id", 0))
         v = VertexSE3(vid, pose4x4)
         self._next_id = vid + 1
         self._vertices.append(v)
@@ -144,6 +168,29 @@ class GraphSLAM:
         e = EdgeSE3Prior(PRIOR_VEC, v_se3, np.concatenate([np.asarray(direction, float), np.asarray(measurement, float)]), information_matrix)
         self._edges.append(e)
         return e
+
+    # the floor constraint (graph_slam.cpp:116-126, 148-158; global_graph_nodelet.cpp:601-611): ONE plane node, fixed
+    def add_plane_node(self, plane_coeffs):
+        vid = max(len(self._vertices) + len(self._planes), getattr(self, "_next_id", 0))
+        v = VertexPlane(vid, plane_coeffs)
+        self._next_id = vid + 1
+        self._planes.append(v)
+        return v
+
+    def add_se3_plane_edge(self, v_se3, v_plane, plane_coeffs, information_matrix):
+        e = EdgeSE3Prior(SE3_PLANE, v_se3, plane_coeffs, information_matrix)
+        e.plane = v_plane
+        self._edges.append(e)
+        return e
+
+    def _floor_plane(self):
+        """The plane of the SE3_PLANE edges: they must share one FIXED plane node (a free plane vertex is another vertex type, not on this path)."""
+        planes = {id(e.plane): e.plane for e in self._edges if getattr(e, "kind", EDGE_SE3) == SE3_PLANE}
+        if not planes:
+            return None
+        if len(planes) != 1 or not next(iter(planes.values())).fixed():
+            raise NotImplementedError("EdgeSE3Plane is supported against ONE FIXED VertexPlane (the floor node of the global-graph nodelet)")
+        return next(iter(planes.values())).estimate()
 
     def add_robust_kernel(self, edge, kernel_type, kernel_size):
         if kernel_type == "NONE":
@@ -188,7 +235,7 @@ class GraphSLAM:
         if len(self._edges) < 1:
             return -1                                                             # graph_slam.cpp:302-305
         poses, fixed, ij, meas, info, hub, types = self._arrays()
-        st = optimize_arrays(self._L, self._handle(), poses, fixed, ij, meas, info, hub, num_iterations, edge_type=types)
+        st = optimize_arrays(self._L, self._handle(), poses, fixed, ij, meas, info, hub, num_iterations, edge_type=types, floor_plane=self._floor_plane())
         out = np.zeros((len(self._vertices), 7))
         C.check(self._L.lvs_pgo_get_poses(self._handle(), out.ctypes.data))
         for v, T in zip(self._vertices, _pg.matrix_batch(out)):
@@ -204,7 +251,15 @@ class GraphSLAM:
                 f.write("VERTEX_SE3:QUAT %d %s\n" % (v._id, " ".join(repr(float(x)) for x in _pg.pose7(v._T))))
                 if v._fixed:
                     f.write("FIX %d\n" % v._id)
+            for v in self._planes:                                # VertexPlane::write: coefficients and the colour
+                f.write("VERTEX_PLANE %d %s 0 0 0\n" % (v._id, " ".join(repr(float(x)) for x in v._c)))
+                if v._fixed:
+                    f.write("FIX %d\n" % v._id)
             for e in self._edges:
+                if getattr(e, "kind", EDGE_SE3) == SE3_PLANE:
+                    up = [e.information[r, c] for r in range(3) for c in range(r, 3)]
+                    f.write("EDGE_SE3_PLANE %d %d %s %s\n" % (e.vertices[0]._id, e.plane._id, " ".join(repr(float(x)) for x in e.measurement), " ".join(repr(float(x)) for x in up)))
+                    continue
                 if getattr(e, "kind", EDGE_SE3) != EDGE_SE3:      # write() of the prior edges: measurement, then the upper triangle
                     tag, _, d = _PRIOR_TAGS[e.kind]
                     m = e.measurement if e.kind != PRIOR_QUAT else e.measurement[[3, 0, 1, 2]]        # PriorQuat writes w x y z
@@ -223,7 +278,7 @@ class GraphSLAM:
         return True
 
     def load(self, filename):
-        self._vertices, self._edges = [], []
+        self._vertices, self._edges, self._planes = [], [], []
         by_id = {}
         with open(filename) as f:
             for line in f:
@@ -234,6 +289,18 @@ class GraphSLAM:
                     v = VertexSE3(int(t[1]), _pg.matrix(np.array(t[2:9], dtype=np.float64)))
                     by_id[v._id] = v
                     self._vertices.append(v)
+                elif t[0] == "VERTEX_PLANE":
+                    v = VertexPlane(int(t[1]), np.array(t[2:6], dtype=np.float64))
+                    by_id[v._id] = v
+                    self._planes.append(v)
+                elif t[0] == "EDGE_SE3_PLANE":
+                    up = np.array(t[7:13], dtype=np.float64)
+                    info = np.zeros((3, 3))
+                    info[np.triu_indices(3)] = up
+                    info = info + np.triu(info, 1).T
+                    e = EdgeSE3Prior(SE3_PLANE, by_id[int(t[1])], np.array(t[3:7], dtype=np.float64), info)
+                    e.plane = by_id[int(t[2])]
+                    self._edges.append(e)
                 elif t[0] == "FIX":
                     for s in t[1:]:
                         by_id[int(s)].setFixed(True)
@@ -263,7 +330,7 @@ class GraphSLAM:
                             k += 1
                     self._edges.append(EdgeSE3Prior(kind, by_id[int(t[1])], m, info))
         self._vertices.sort(key=lambda v: v._id)
-        self._next_id = max((v._id for v in self._vertices), default=-1) + 1
+        self._next_id = max((v._id for v in self._vertices + self._planes), default=-1) + 1
         try:
             with open(filename + ".kernels") as f:
                 kern = {}                                     # (i, j) -> records in file order: one record is consumed per edge
@@ -310,7 +377,7 @@ def load_kitti_poses(filename):
 _PRIOR_BY_TAG = {v[0]: k for k, v in _PRIOR_TAGS.items()}
 
 
-def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iterations, edge_type=None):
+def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iterations, edge_type=None, floor_plane=None):
     """set_graph + optimize on flat arrays; returns the stats dict (used by GraphSLAM.optimize, the tests and the bench)."""
     poses7 = np.ascontiguousarray(poses7, dtype=np.float64)
     ij = np.ascontiguousarray(ij, dtype=np.int32)
@@ -319,6 +386,9 @@ def optimize_arrays(L, h, poses7, fixed, ij, meas7, info21, huber, num_iteration
     hub = np.ascontiguousarray(huber, dtype=np.float64) if huber is not None else None
     fx = np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None
     ty = np.ascontiguousarray(edge_type, dtype=np.int32) if edge_type is not None else None
+    if floor_plane is not None:
+        fp = np.ascontiguousarray(floor_plane, dtype=np.float64)
+        C.check(L.lvs_pgo_set_floor_plane(h, fp.ctypes.data))
     C.check(L.lvs_pgo_set_graph_typed(h, poses7.shape[0], poses7.ctypes.data, fx.ctypes.data if fx is not None else None, ij.shape[0], ij.ctypes.data,
                                       meas7.ctypes.data, info21.ctypes.data, hub.ctypes.data if hub is not None else None,
                                       ty.ctypes.data if ty is not None else None))
@@ -362,7 +432,10 @@ class PoseGraph:
         except Exception:
             pass
 
-    def set_graph(self, poses7, ij, meas7, info21, huber=None, fixed=None, edge_type=None):
+    def set_graph(self, poses7, ij, meas7, info21, huber=None, fixed=None, edge_type=None, floor_plane=None):
+        if floor_plane is not None:
+            fp = np.ascontiguousarray(floor_plane, dtype=np.float64)
+            C.check(self._L.lvs_pgo_set_floor_plane(self._h, fp.ctypes.data))
         self._keep = [np.ascontiguousarray(poses7, dtype=np.float64), np.ascontiguousarray(ij, dtype=np.int32), np.ascontiguousarray(meas7, dtype=np.float64),
                       np.ascontiguousarray(info21, dtype=np.float64), np.ascontiguousarray(huber, dtype=np.float64) if huber is not None else None,
                       np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None,

@@ -207,13 +207,35 @@ void edge_gradient(const Iso& Z, const Iso& Xi, const Iso& Xj, double* Ji, doubl
 // type 0: EdgeSE3.  Types 1-4: the reference's unary priors on a VertexSE3 (include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp; i == j), whose
 // measurement is pm[] and whose D x D information sits in the top-left corner of info (D = 2 for xy, 3 otherwise; the rest is zero, so the
 // 6-vector / 6 x 6 code paths of the binary edge are reused with zero padding).
-enum { EDGE_SE3 = 0, PRIOR_XY = 1, PRIOR_XYZ = 2, PRIOR_QUAT = 3, PRIOR_VEC = 4 };
-struct Edge { int i, j; Iso Z, Zinv; double info[36]; double huber; int type = EDGE_SE3; double pm[6] = {0, 0, 0, 0, 0, 0}; };   // huber <= 0: no kernel
+// Type 5: EdgeSE3Plane (include/g2o/edge_se3_plane.hpp) against a FIXED VertexPlane - how the nodelet uses it: one floor plane node, fixed at
+// creation (global_graph_nodelet.cpp:601-611) - which makes it a unary constraint on the pose; pm = measured plane (4), the vertex's plane (4).
+enum { EDGE_SE3 = 0, PRIOR_XY = 1, PRIOR_XYZ = 2, PRIOR_QUAT = 3, PRIOR_VEC = 4, PRIOR_PLANE = 5 };
+struct Edge { int i, j; Iso Z, Zinv; double info[36]; double huber; int type = EDGE_SE3; double pm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };   // huber <= 0: no kernel
+
+// g2o Plane3D (g2o!types/slam3d_addons/plane3d.h): coefficients scaled to a unit normal; rotation(n) = AngleAxis(azimuth, Z) * AngleAxis(-elevation, Y)
+void plane_normalize(double* c) { const double n = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]); const double k = 1. / n; for (int a = 0; a < 4; a++) c[a] = c[a] * k; }
+double plane_azimuth(const double* v) { return std::atan2(v[1], v[0]); }
+double plane_elevation(const double* v) { return std::atan2(v[2], std::sqrt(v[0] * v[0] + v[1] * v[1])); }
+void plane_rotation(const double* n, double* R) {
+  const double az = plane_azimuth(n), el = plane_elevation(n);
+  // Eigen: AngleAxis * AngleAxis is a quaternion product, then toRotationMatrix
+  const Q q1 = {std::cos(0.5 * az), 0.0, 0.0, std::sin(0.5 * az)}, q2 = {std::cos(-0.5 * el), 0.0, std::sin(-0.5 * el), 0.0};
+  Q q;
+  q.w = q1.w * q2.w - q1.x * q2.x - q1.y * q2.y - q1.z * q2.z;
+  q.x = q1.w * q2.x + q1.x * q2.w + q1.y * q2.z - q1.z * q2.y;
+  q.y = q1.w * q2.y + q1.y * q2.w + q1.z * q2.x - q1.x * q2.z;
+  q.z = q1.w * q2.z + q1.z * q2.w + q1.x * q2.y - q1.y * q2.x;
+  quat_to_R(q, R);
+}
 
 // setMeasurement of the prior edges: PriorQuat keeps w >= 0 (edge_se3_priorquat.hpp:52-57), PriorVec normalises direction and measurement
 // (edge_se3_priorvec.hpp:50-53); meas6 = xy | xyz | qx qy qz qw | direction(3) measurement(3)
-void prior_set_measurement(int type, const double* m, double* pm) {
-  for (int a = 0; a < 6; a++) pm[a] = 0.0;
+void prior_set_measurement(int type, const double* m, double* pm, const double* floor_plane = nullptr) {
+  for (int a = 0; a < 8; a++) pm[a] = 0.0;
+  if (type == PRIOR_PLANE) {                                   // Plane3D(coeffs) of the measurement and of the vertex estimate
+    for (int a = 0; a < 4; a++) { pm[a] = m[a]; pm[4 + a] = floor_plane ? floor_plane[a] : (a == 2 ? 1.0 : 0.0); }
+    plane_normalize(pm); plane_normalize(pm + 4);
+  }
   if (type == PRIOR_XY) { pm[0] = m[0]; pm[1] = m[1]; }
   else if (type == PRIOR_XYZ) { pm[0] = m[0]; pm[1] = m[1]; pm[2] = m[2]; }
   else if (type == PRIOR_QUAT) { const double sg = m[3] < 0.0 ? -1.0 : 1.0; for (int a = 0; a < 4; a++) pm[a] = sg * m[a]; }
@@ -250,6 +272,17 @@ void prior_error(int type, const double* pm, const Iso& X, double* e) {
       const double v = ((cof[0 * 3 + r] * id) * pm[0] + (cof[1 * 3 + r] * id) * pm[1]) + (cof[2 * 3 + r] * id) * pm[2];
       e[r] = v - pm[3 + r];
     }
+  } else if (type == PRIOR_PLANE) {
+    // local_plane = X^-1 * plane (operator*(Isometry3d, Plane3D)); error = local_plane.ominus(measurement) (edge_se3_plane.hpp:40-47)
+    const Iso w2n = iso_inv(X);
+    double lp[4];
+    for (int r = 0; r < 3; r++) lp[r] = (w2n.R[r * 3] * pm[4] + w2n.R[r * 3 + 1] * pm[5]) + w2n.R[r * 3 + 2] * pm[6];
+    lp[3] = pm[7] - ((w2n.t[0] * lp[0] + w2n.t[1] * lp[1]) + w2n.t[2] * lp[2]);
+    plane_normalize(lp);
+    double R[9], n[3];
+    plane_rotation(lp, R);                                     // ominus: rotation(normal()).transpose() * measurement.normal()
+    for (int r = 0; r < 3; r++) n[r] = (R[r] * pm[0] + R[3 + r] * pm[1]) + R[6 + r] * pm[2];
+    e[0] = plane_azimuth(n); e[1] = plane_elevation(n); e[2] = (-lp[3]) - (-pm[3]);
   }
 }
 
@@ -312,6 +345,7 @@ enum Algorithm { ALG_LM = 0, ALG_GN = 1 };
 struct IterRec { double chi2, lambda; int trials, pcg_iters; };
 
 struct PGO {
+  double floor_plane[4] = {0, 0, 1, 0};   // the fixed VertexPlane the EdgeSE3Plane rows refer to
   std::vector<Iso> X;
   std::vector<uint8_t> fixed;
   std::vector<Edge> edges;
@@ -697,7 +731,7 @@ void opgo_set_graph_typed(void* h, int nv, const double* poses7, const uint8_t* 
     e.type = edge_type ? edge_type[k] : EDGE_SE3;
     if (e.type != EDGE_SE3) {
       e.j = e.i;
-      prior_set_measurement(e.type, meas7 + 7 * k, e.pm);
+      prior_set_measurement(e.type, meas7 + 7 * k, e.pm, g.floor_plane);
       const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
       e.Z = iso_from_qt7(ident);
     } else e.Z = iso_from_qt7(meas7 + 7 * k);
@@ -714,14 +748,16 @@ void opgo_set_graph(void* h, int nv, const double* poses7, const uint8_t* fixed,
                     const double* info21, const double* huber_delta) {
   opgo_set_graph_typed(h, nv, poses7, fixed, ne, ij, meas7, info21, huber_delta, nullptr);
 }
+void opgo_set_floor_plane(void* h, const double* coeffs4) { for (int a = 0; a < 4; a++) ((PGO*)h)->floor_plane[a] = coeffs4[a]; }
+// meas: the measurement, followed for PRIOR_PLANE (type 5) by the fixed plane's 4 coefficients at meas[4..7]
 void opgo_prior_error(int type, const double* meas, const double* x7, double* e6) {
-  double pm[6];
-  prior_set_measurement(type, meas, pm);
+  double pm[8];
+  prior_set_measurement(type, meas, pm, meas + 4);
   prior_error(type, pm, iso_from_qt7(x7), e6);
 }
 void opgo_prior_jacobian(int type, const double* meas, const double* x7, double* J36) {
-  double pm[6];
-  prior_set_measurement(type, meas, pm);
+  double pm[8];
+  prior_set_measurement(type, meas, pm, meas + 4);
   prior_jacobian(type, pm, iso_from_qt7(x7), J36);
 }
 

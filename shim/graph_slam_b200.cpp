@@ -11,6 +11,8 @@
 #include <g2o/edge_se3_priorxyz.hpp>
 #include <g2o/edge_se3_priorquat.hpp>
 #include <g2o/edge_se3_priorvec.hpp>
+#include <g2o/edge_se3_plane.hpp>        // floor constraint: EdgeSE3Plane against the nodelet's one fixed VertexPlane
+#include <g2o/types/slam3d_addons/vertex_plane.h>
 #include <algorithm>
 #include <cstdint>
 #include <iostream>
@@ -54,8 +56,9 @@ int GraphSLAM::optimize(int num_iterations) {
   for (auto& kv : graph->vertices()) if (auto* v = dynamic_cast<g2o::VertexSE3*>(kv.second)) vs.push_back(v);
   std::sort(vs.begin(), vs.end(), [](g2o::VertexSE3* a, g2o::VertexSE3* b) { return a->id() < b->id(); });
   for (size_t i = 0; i < vs.size(); i++) index[vs[i]->id()] = (int)i;
-  // EdgeSE3 and the unary priors on a VertexSE3 (add_se3_prior_{xy,xyz,quat,vec}_edge, graph_slam.cpp:194-240); plane vertices / edges
-  // (floor detection) are not on this path and are left out like any other type
+  // EdgeSE3, the unary priors on a VertexSE3 (add_se3_prior_{xy,xyz,quat,vec}_edge, graph_slam.cpp:194-240) and EdgeSE3Plane against a FIXED plane
+  // vertex (the floor node, global_graph_nodelet.cpp:601-611); edges to a free plane vertex and plane-plane edges are left out like any other type
+  g2o::VertexPlane* floor = nullptr;
   struct Item { g2o::HyperGraph::Edge* e; long long id; int type; };
   std::vector<Item> es;
   for (auto* e : graph->edges()) {
@@ -64,6 +67,10 @@ int GraphSLAM::optimize(int num_iterations) {
     else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorXYZ*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_XYZ});
     else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorQuat*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_QUAT});
     else if (auto* s = dynamic_cast<g2o::EdgeSE3PriorVec*>(e)) es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_PRIOR_VEC});
+    else if (auto* s = dynamic_cast<g2o::EdgeSE3Plane*>(e)) {
+      auto* pl = dynamic_cast<g2o::VertexPlane*>(s->vertices()[1]);
+      if (pl && pl->fixed() && (!floor || floor == pl)) { floor = pl; es.push_back({e, (long long)s->internalId(), LVS_PGO_EDGE_SE3_PLANE}); }
+    }
   }
   std::sort(es.begin(), es.end(), [](const Item& a, const Item& b) { return a.id < b.id; });
   std::vector<double> poses(7 * vs.size()), meas(7 * es.size(), 0.0), info(21 * es.size()), huber(es.size(), 0.0);
@@ -102,6 +109,13 @@ int GraphSLAM::optimize(int num_iterations) {
         pack_info(e, 3, &info[21 * k]); huber[k] = huber_of(e);
         break;
       }
+      case LVS_PGO_EDGE_SE3_PLANE: {
+        auto* e = static_cast<g2o::EdgeSE3Plane*>(es[k].e);
+        const Eigen::Vector4d pc = e->measurement().toVector();
+        for (int a = 0; a < 4; a++) m[a] = pc(a, 0);
+        pack_info(e, 3, &info[21 * k]); huber[k] = huber_of(e);
+        break;
+      }
       default: {
         auto* e = static_cast<g2o::EdgeSE3PriorVec*>(es[k].e);
         for (int a = 0; a < 6; a++) m[a] = e->measurement()(a, 0);
@@ -113,7 +127,13 @@ int GraphSLAM::optimize(int num_iterations) {
   lvs_pgo_t* h = nullptr;
   if (lvs_pgo_create(solver_kind(solver_type_), 0, nullptr, &h) != LVS_OK) { std::cerr << "lvslam_b200: " << lvs_last_error() << std::endl; return 0; }
   lvs_pgo_stats st{};
-  int rc = lvs_pgo_set_graph_typed(h, (int)vs.size(), poses.data(), fixed.data(), (int)es.size(), ij.data(), meas.data(), info.data(), huber.data(), type.data());
+  int rc = LVS_OK;
+  if (floor) {
+    const Eigen::Vector4d fc = floor->estimate().toVector();
+    const double c4[4] = {fc(0, 0), fc(1, 0), fc(2, 0), fc(3, 0)};
+    rc = lvs_pgo_set_floor_plane(h, c4);
+  }
+  if (rc == LVS_OK) rc = lvs_pgo_set_graph_typed(h, (int)vs.size(), poses.data(), fixed.data(), (int)es.size(), ij.data(), meas.data(), info.data(), huber.data(), type.data());
   if (rc == LVS_OK) rc = lvs_pgo_optimize(h, num_iterations, &st);
   if (rc == LVS_OK) rc = lvs_pgo_get_poses(h, poses.data());
   lvs_pgo_destroy(h);

@@ -31,6 +31,7 @@ def lib():
         L.opgo_set_graph.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp]; L.opgo_set_graph.restype = None
         L.opgo_set_graph_typed.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]; L.opgo_set_graph_typed.restype = None
         L.opgo_prior_error.argtypes = [i32, vp, vp, vp]; L.opgo_prior_error.restype = None
+        L.opgo_set_floor_plane.argtypes = [vp, vp]; L.opgo_set_floor_plane.restype = None
         L.opgo_prior_jacobian.argtypes = [i32, vp, vp, vp]; L.opgo_prior_jacobian.restype = None
         L.opgo_get_poses.argtypes = [vp, vp]; L.opgo_get_poses.restype = None
         L.opgo_compute_errors.argtypes = [vp, vp, vp]; L.opgo_compute_errors.restype = f64
@@ -79,7 +80,9 @@ class OraclePGO:
         except Exception:
             pass
 
-    def set_graph(self, poses7, edges_ij, meas7, info21, huber=None, fixed=None, edge_type=None):
+    def set_graph(self, poses7, edges_ij, meas7, info21, huber=None, fixed=None, edge_type=None, floor_plane=None):
+        if floor_plane is not None:
+            self.L.opgo_set_floor_plane(self.h, _c(floor_plane).ctypes.data)
         p, ij, m, inf = _c(poses7), _c(edges_ij, np.int32), _c(meas7), _c(info21)
         self.nv, self.ne = p.shape[0], ij.shape[0]
         hub = _c(huber) if huber is not None else None
@@ -147,14 +150,14 @@ def edge_jacobians(z7, xi7, xj7):
 
 def prior_error(kind, meas, x7):
     """computeError of EdgeSE3PriorXY / XYZ / Quat / Vec (kind 1-4), zero-padded to 6."""
-    e, m = np.zeros(6), np.zeros(7)
+    e, m = np.zeros(6), np.zeros(8)            # kind 5: the measured plane (4) followed by the fixed plane (4)
     m[:len(meas)] = meas
     lib().opgo_prior_error(int(kind), m.ctypes.data, _c(x7).ctypes.data, e.ctypes.data)
     return e
 
 
 def prior_jacobian(kind, meas, x7):
-    J, m = np.zeros((6, 6)), np.zeros(7)
+    J, m = np.zeros((6, 6)), np.zeros(8)
     m[:len(meas)] = meas
     lib().opgo_prior_jacobian(int(kind), m.ctypes.data, _c(x7).ctypes.data, J.ctypes.data)
     return J

@@ -12,6 +12,7 @@
 #include <g2o/edge_se3_priorxyz.hpp>
 #include <g2o/edge_se3_priorquat.hpp>
 #include <g2o/edge_se3_priorvec.hpp>
+#include <g2o/edge_se3_plane.hpp>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -121,6 +122,7 @@ int main(int argc, char** argv) {
       vs.push_back(v);
     }
     // edges in file order; the unary priors the way GraphSLAM::add_se3_prior_{xy,xyz,quat,vec}_edge build them (graph_slam.cpp:194-240)
+    g2o::VertexPlane* floor_node = nullptr;
     auto kernel = [&](size_t k) -> g2o::RobustKernel* {
       if (!(huber[k] > 0)) return nullptr;
       auto* hk = new g2o::RobustKernelHuber();
@@ -159,6 +161,24 @@ int main(int argc, char** argv) {
         auto* e = new g2o::EdgeSE3PriorQuat();
         Eigen::Matrix<double, 3, 3> I; info_dd(k, I, 3);
         e->setMeasurement(Eigen::Quaterniond(m[3], m[0], m[1], m[2])); e->setInformation(I); e->vertices().push_back(vs[ij[2 * k]]);
+        if (auto* hk = kernel(k)) e->setRobustKernel(hk);
+        graph->addEdge(e);
+      } else if (etype[k] == 5) {
+        // the floor constraint: one plane node, fixed at creation (global_graph_nodelet.cpp:601-611); the plane itself comes in floor.f64
+        if (!floor_node) {
+          const std::vector<double> fc = slurp<double>(dir + "/floor.f64");
+          Eigen::Vector4d c4; for (int a = 0; a < 4; a++) c4(a, 0) = fc[a];
+          floor_node = new g2o::VertexPlane();
+          floor_node->setId((int)graph->vertices().size());
+          floor_node->setEstimate(g2o::Plane3D(c4));
+          floor_node->setFixed(true);
+          graph->addVertex(floor_node);
+        }
+        auto* e = new g2o::EdgeSE3Plane();
+        Eigen::Vector4d z; for (int a = 0; a < 4; a++) z(a, 0) = m[a];
+        Eigen::Matrix<double, 3, 3> I; info_dd(k, I, 3);
+        e->setMeasurement(g2o::Plane3D(z)); e->setInformation(I);
+        e->vertices().push_back(vs[ij[2 * k]]); e->vertices().push_back(floor_node);
         if (auto* hk = kernel(k)) e->setRobustKernel(hk);
         graph->addEdge(e);
       } else {

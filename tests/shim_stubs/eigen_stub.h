@@ -28,6 +28,7 @@ typedef Matrix<float, 4, 4> Matrix4f;
 typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 4, 1> Vector4d;
 template <typename M>
 struct Map {
   typedef typename std::remove_const<M>::type Plain;

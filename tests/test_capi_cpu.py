@@ -199,17 +199,25 @@ def test_graph_slam_prior_edges_round_trip(tmp_path):
     e3 = gs.add_se3_prior_quat_edge(b, [0.5, -0.5, -0.5, -0.5], np.eye(3) * 10)
     e4 = gs.add_se3_prior_vec_edge(a, [0, 0, -2.0], [0.0, 3.0, -4.0], np.eye(3))
     gs.add_robust_kernel(e1, "Huber", 1.5)
+    floor = gs.add_plane_node([0.0, 0.0, 2.0, 0.0])                      # the floor node of the nodelet: id 2, normalised, fixed
+    e5 = gs.add_se3_plane_edge(b, floor, [0.0, 0.0, 1.0, -1.7], np.eye(3) * 5)
+    with pytest.raises(NotImplementedError):
+        gs._floor_plane()                                                # a FREE plane vertex is not on this path
+    floor.setFixed(True)
+    assert floor.id() == 2 and np.allclose(gs._floor_plane(), [0, 0, 1, 0]) and gs.add_se3_node(np.eye(4)).id() == 3
     assert e3.kind == PRIOR_QUAT and np.allclose(e3.measurement, [-0.5, 0.5, 0.5, 0.5])                       # w >= 0
     assert e4.kind == PRIOR_VEC and np.allclose(e4.measurement, [0, 0, -1, 0, 0.6, -0.8])                # both halves normalised
     poses, fixed, ij, meas, info, hub, types = gs._arrays()
-    assert types.tolist() == [0, 1, 2, 3, 4] and ij.tolist() == [[0, 1], [1, 1], [0, 0], [1, 1], [0, 0]] and hub.tolist() == [0, 1.5, 0, 0, 0]
+    assert types.tolist() == [0, 1, 2, 3, 4, 5] and ij.tolist() == [[0, 1], [1, 1], [0, 0], [1, 1], [0, 0], [1, 1]] and hub.tolist() == [0, 1.5, 0, 0, 0, 0]
+    assert np.allclose(meas[5, :4], [0, 0, 1, -1.7]) and info[5, 0] == 5.0
     assert np.allclose(meas[1, :2], [1.5, 2.5]) and np.allclose(meas[3, :4], [-0.5, 0.5, 0.5, 0.5]) and info[1, 0] == 4.0 and info[1, 6] == 5.0 and info[1, 11] == 0.0
     f = str(tmp_path / "g.g2o")
     assert gs.save(f)
     text = open(f).read()
     assert "EDGE_SE3_PRIORXY 1 1.5 2.5 4.0 0.0 5.0" in text and "EDGE_SE3_PRIORQUAT 1 0.5 -0.5 0.5 0.5" in text and "EDGE_SE3_PRIORVEC 0" in text
+    assert "VERTEX_PLANE 2 0.0 0.0 1.0 0.0 0 0 0" in text and "FIX 2" in text and "EDGE_SE3_PLANE 1 2 0.0 0.0 1.0 -1.7 5.0 0.0 0.0 5.0 0.0 5.0" in text
     gs2 = GraphSLAM("lm_var")
-    assert gs2.load(f) and gs2.num_edges() == 5
+    assert gs2.load(f) and gs2.num_edges() == 6 and np.allclose(gs2._floor_plane(), [0, 0, 1, 0])
     p2 = gs2._arrays()
     for x, y in zip(gs._arrays(), p2):
         assert np.allclose(x, y)

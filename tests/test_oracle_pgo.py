@@ -147,9 +147,20 @@ def test_empty_graph_returns_minus_one():
 
 
 # ---- unary priors on a VertexSE3 (include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp; "later" row of SURVEY.md §8f)
+FLOOR = np.array([0.3, -0.2, 0.9, 1.5])          # the fixed VertexPlane the EdgeSE3Plane rows (kind 5) refer to
+
+
+def _local_plane(T, plane):
+    """operator*(Isometry3d, Plane3D) with the inverse pose: the plane as seen from the vehicle (g2o plane3d.h)."""
+    p = plane / np.linalg.norm(plane[:3])
+    Ti = np.linalg.inv(T)
+    n = Ti[:3, :3] @ p[:3]
+    return np.r_[n, p[3] - Ti[:3, 3] @ n]
+
+
 def _priors_on(g, rng, every=7):
-    """The sphere graph g with GPS / IMU style priors on every `every`-th vertex, interleaved after the binary edges of that vertex:
-    returns (ij, meas7, info21, huber, edge_type)."""
+    """The sphere graph g with GPS / IMU / floor style unary constraints on every `every`-th vertex, interleaved after the binary edges of
+    that vertex: returns (ij, meas7, info21, huber, edge_type); the floor rows refer to the plane FLOOR."""
     ij, meas, info, hub, ty = [], [], [], [], []
     nv = len(g["poses7"])
     by_first = {}
@@ -163,7 +174,7 @@ def _priors_on(g, rng, every=7):
         if v % every:
             continue
         T = G.matrix(g["truth7"][v])
-        kind = 1 + (v // every) % 4
+        kind = 1 + (v // every) % 5
         m, I6 = np.zeros(7), np.zeros((6, 6))
         if kind == 1:
             m[:2] = T[:2, 3] + rng.normal(0, 0.05, 2); I6[:2, :2] = np.array([[4.0, 0.3], [0.3, 5.0]])
@@ -172,9 +183,12 @@ def _priors_on(g, rng, every=7):
         elif kind == 3:
             q = G.pose7(T)[3:] * (-1.0 if v % 2 else 1.0)           # either sign: setMeasurement keeps w >= 0
             m[:4] = q + rng.normal(0, 0.01, 4); I6[:3, :3] = np.diag([50.0, 60.0, 70.0])
-        else:
+        elif kind == 4:
             d = np.array([0.0, 0.0, -1.0])
             m[:3] = 3.0 * d; m[3:6] = T[:3, :3].T @ d + rng.normal(0, 0.02, 3); I6[:3, :3] = np.eye(3) * 30.0
+        else:
+            m[:4] = 2.5 * (_local_plane(T, FLOOR) + np.r_[rng.normal(0, 0.01, 3), rng.normal(0, 0.05)])      # any scale: Plane3D normalises
+            I6[:3, :3] = np.diag([40.0, 40.0, 8.0]) + 0.5
         iu = np.triu_indices(6)
         ij.append([v, v]); meas.append(m); info.append(I6[iu]); hub.append(1.0 if v % (2 * every) == 0 else 0.0); ty.append(kind)
     assert len(done) == len(g["ij"])
@@ -207,6 +221,13 @@ def test_prior_edge_errors_and_numeric_jacobians():
         d, z = rng.normal(size=3), rng.normal(size=3)
         e = P.prior_error(4, np.r_[d, z], x)
         np.testing.assert_allclose(e[:3], T[:3, :3].T @ (d / np.linalg.norm(d)) - z / np.linalg.norm(z), atol=1e-13)
+        # EdgeSE3Plane against a fixed plane: zero when the measurement IS the plane seen from the pose (whatever its scale); a shift of the
+        # measured distance is the third component; azimuth / elevation of the measured normal in the local plane's frame are the first two
+        lp = _local_plane(T, FLOOR)
+        np.testing.assert_allclose(P.prior_error(5, np.r_[3.0 * lp, FLOOR], x)[:3], 0, atol=1e-12)
+        np.testing.assert_allclose(P.prior_error(5, np.r_[lp + [0, 0, 0, 0.25], FLOOR], x)[:3], [0, 0, 0.25], atol=1e-12)      # distance() = -coeffs(3)
+        Jp = P.prior_jacobian(5, np.r_[lp, FLOOR], x)
+        assert np.abs(Jp[3:]).max() == 0 and np.abs(Jp[:3]).max() > 0.1 and np.linalg.matrix_rank(Jp[:3], tol=1e-3) == 3
 
 
 def test_single_vertex_with_position_and_orientation_priors_has_a_known_optimum():

@@ -60,12 +60,13 @@ def test_shims_run_on_the_gpu_and_match_the_oracle(tmp_path, small_pair, variant
     tgt.astype(np.float32).tofile(tmp_path / "tgt.f32"); src.astype(np.float32).tofile(tmp_path / "src.f32")
     np.ascontiguousarray(guess.T, dtype=np.float32).tofile(tmp_path / "guess.f32")                  # column-major, Eigen's order
     # a sphere graph with Huber kernels and the reference's GPS / IMU style unary priors (XY, XYZ, Quat, Vec) on every fifth vertex
-    from test_oracle_pgo import _priors_on
+    from test_oracle_pgo import _priors_on, FLOOR
     gr = G.sphere(20, 10, seed=7)
     p_ij, p_meas, p_info, p_hub, p_type = _priors_on(gr, np.random.default_rng(9), every=5)
     gr["poses7"].astype(np.float64).tofile(tmp_path / "poses7.f64"); p_meas.astype(np.float64).tofile(tmp_path / "meas7.f64")
     p_info.astype(np.float64).tofile(tmp_path / "info21.f64"); p_ij.astype(np.int32).tofile(tmp_path / "ij.i32")
     p_type.astype(np.int32).tofile(tmp_path / "etype.i32"); p_hub.astype(np.float64).tofile(tmp_path / "huber.f64")
+    FLOOR.astype(np.float64).tofile(tmp_path / "floor.f64")
     out = _run(_build(tmp_path, variant), tmp_path)
 
     # ---- registration vs the CPU restatement with the same settings
@@ -101,12 +102,12 @@ def test_shims_run_on_the_gpu_and_match_the_oracle(tmp_path, small_pair, variant
 
     # ---- pose graph: GraphSLAM::optimize on the g2o containers vs the CPU restatement of g2o's LM
     op = P.OraclePGO()
-    op.set_graph(gr["poses7"], p_ij, p_meas, p_info, p_hub, None, p_type)
+    op.set_graph(gr["poses7"], p_ij, p_meas, p_info, p_hub, None, p_type, FLOOR)
     ro = op.optimize(100, P.ALG_LM, P.SOLVER_CSPARSE if P.have_csparse() else P.SOLVER_DENSE)
     assert int(out["pgo_iterations"][0]) > 0 and int(out["pgo_empty"][0]) == -1
     got = np.array(out["poses"])
     want = op.poses()
     dmax = float(np.abs(got[:, :3] - want[:, :3]).max())          # the priors fix the gauge: the poses themselves agree
-    assert dmax <= 1e-6, dmax
+    assert dmax <= 1e-5, dmax                                      # (numeric Jacobians of the prior edges: see tests/test_pgo_gpu.py)
     assert np.abs(np.abs(np.sum(got[:, 3:] * want[:, 3:], axis=1)) - 1.0).max() <= 1e-10
     assert ro["iterations"] > 0
