@@ -799,10 +799,23 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
             s_Lj[q * LDL + r] = (q < nb && j0 + r < F) ? A[(size_t)(c + q) * F + j0 + r] : 0.0;
           }
         } else {
-          for (int t = threadIdx.x; t < nbk * TILE; t += kCholThreads) {
-            const int r = t % TILE, q = t / TILE, qc = min(q, nb - 1);
-            cp_async8(s_Li + q * LDL + r, A + (size_t)(c + qc) * F + min(i0 + r, F - 1), (q < nb && i0 + r < F) ? 8 : 0);
-            cp_async8(s_Lj + q * LDL + r, A + (size_t)(c + qc) * F + min(j0 + r, F - 1), (q < nb && j0 + r < F) ? 8 : 0);
+          // a warp copies whole panel columns (q = warp, warp + 8, ...), its lanes the rows lane, lane + 32, ...: one address per column
+          // and panel instead of a division, a clamp and a predicate per element (the element-wise loop issued more instructions than
+          // the tile's DMMA loop)
+          const int ri = F - 1 - i0, rj = F - 1 - j0;         // last valid row of each panel, relative to the tile
+          for (int q = warp; q < nbk; q += kCholThreads / 32) {
+            const int qc = min(q, nb - 1);
+            const double* srci = A + (size_t)(c + qc) * F + i0;
+            const double* srcj = A + (size_t)(c + qc) * F + j0;
+            double* di = s_Li + q * LDL;
+            double* dj = s_Lj + q * LDL;
+            const bool qok = q < nb;
+#pragma unroll
+            for (int u = 0; u < TILE / 32; u++) {
+              const int r = lane + 32 * u;
+              cp_async8(di + r, srci + min(r, ri), (qok && r <= ri) ? 8 : 0);
+              cp_async8(dj + r, srcj + min(r, rj), (qok && r <= rj) ? 8 : 0);
+            }
           }
           asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
         }
@@ -825,26 +838,33 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
 #pragma unroll
             for (int b2 = 0; b2 < Cfg::TN; b2++) dmma884(acc[a][b2][0], acc[a][b2][1], fa[a], fb[b2]);
         }
-        // a lane holds C[8 a + lane / 4][8 b + 2 (lane % 4) + e]; keep the block-lower part (6 x 6 blocks), all loads before the stores
+        // a lane holds C[8 a + lane / 4][8 b + 2 (lane % 4) + e]; keep the block-lower part (6 x 6 blocks), all loads before the stores.
+        // Row / column block indices and the column addresses are worked out once per lane (TM + 2 TN of them), not per element and pass.
+        int rblk[Cfg::TM], cblk[Cfg::TN][2];
+        const int gi_0 = i0 + 8 * (wm * Cfg::TM) + (lane >> 2), gj_0 = j0 + 8 * (wn * Cfg::TN) + 2 * (lane & 3);
+#pragma unroll
+        for (int a = 0; a < Cfg::TM; a++) rblk[a] = (gi_0 + 8 * a < F) ? (gi_0 + 8 * a) / 6 : -1;                       // -1: past the front
+#pragma unroll
+        for (int b2 = 0; b2 < Cfg::TN; b2++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) cblk[b2][e] = (gj_0 + 8 * b2 + e < F - 1) ? (gj_0 + 8 * b2 + e) / 6 : 0x7fffffff;     // never <= a row block
+        double* const C0 = A + (size_t)gj_0 * F + gi_0;
 #pragma unroll
         for (int a = 0; a < Cfg::TM; a++)
 #pragma unroll
           for (int b2 = 0; b2 < Cfg::TN; b2++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-              const int gi = i0 + 8 * (wm * Cfg::TM + a) + (lane >> 2), gj = j0 + 8 * (wn * Cfg::TN + b2) + 2 * (lane & 3) + e;
-              const bool live = gi < F && gj < F - 1 && gi / 6 >= gj / 6;
-              acc[a][b2][e] = live ? ldf<TEAM>(A + (size_t)gj * F + gi) - acc[a][b2][e] : 0.0;
+              const bool live = rblk[a] >= cblk[b2][e];
+              acc[a][b2][e] = live ? ldf<TEAM>(C0 + (size_t)(8 * b2 + e) * F + 8 * a) - acc[a][b2][e] : 0.0;
             }
 #pragma unroll
         for (int a = 0; a < Cfg::TM; a++)
 #pragma unroll
           for (int b2 = 0; b2 < Cfg::TN; b2++)
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const int gi = i0 + 8 * (wm * Cfg::TM + a) + (lane >> 2), gj = j0 + 8 * (wn * Cfg::TN + b2) + 2 * (lane & 3) + e;
-              if (gi < F && gj < F - 1 && gi / 6 >= gj / 6) A[(size_t)gj * F + gi] = acc[a][b2][e];
-            }
+            for (int e = 0; e < 2; e++)
+              if (rblk[a] >= cblk[b2][e]) C0[(size_t)(8 * b2 + e) * F + 8 * a] = acc[a][b2][e];
         __syncthreads();
       }
       if (has_next && !fused_head && rank == 0) {
