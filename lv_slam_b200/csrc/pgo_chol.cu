@@ -461,21 +461,28 @@ template <bool TEAM>
 __device__ __forceinline__ void stage_diag(const double* A, int F, int c, int nb, double* s_D) {
   using Cfg = FrontCfg<TEAM>;
   constexpr int NB = Cfg::NB, LDD = Cfg::LDD;
-  // (every global load of the staging loops is unconditional, from a clamped address, and a whole group of them is issued before the
-  // first use: with predicated loads the compiler sinks each one next to its store and only one is in flight at a time)
-  constexpr int kG = TEAM ? 12 : 9;
-  static_assert((NB * NB) % (kG * kCholThreads) == 0, "diagonal block staging");
-  for (int t0 = threadIdx.x; t0 < NB * NB; t0 += kG * kCholThreads) {
-    double v[kG];
+  // A warp copies whole columns (j = warp, warp + 8, ...), its lanes the rows lane, lane + 32, ...: one address per column instead of a
+  // division per element.  Every global load is unconditional, from a clamped address, and three columns' worth are issued before the
+  // first use (with predicated loads the compiler sinks each one next to its store and only one is in flight at a time).
+  constexpr int RPL = (NB + 31) / 32, CU = 3, kW = kCholThreads / 32;
+  static_assert((NB / kW) % CU == 0 && NB % kW == 0, "diagonal block staging");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = warp; j0 < NB; j0 += kW * CU) {
+    double v[CU][RPL];
 #pragma unroll
-    for (int u = 0; u < kG; u++) {
-      const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
-      v[u] = ldf<TEAM>(A + (size_t)(c + min(j, nb - 1)) * F + c + min(i, nb - 1));
+    for (int cu = 0; cu < CU; cu++) {
+      const double* col = A + (size_t)(c + min(j0 + kW * cu, nb - 1)) * F + c;
+#pragma unroll
+      for (int u = 0; u < RPL; u++) v[cu][u] = ldf<TEAM>(col + min(lane + 32 * u, nb - 1));
     }
 #pragma unroll
-    for (int u = 0; u < kG; u++) {
-      const int t = t0 + u * kCholThreads, j = t / NB, i = t % NB;
-      s_D[i * LDD + j] = (i < nb && j <= i) ? v[u] : (i == j ? 1.0 : 0.0);
+    for (int cu = 0; cu < CU; cu++) {
+      const int j = j0 + kW * cu;
+#pragma unroll
+      for (int u = 0; u < RPL; u++) {
+        const int i = lane + 32 * u;
+        if (i < NB) s_D[i * LDD + j] = (i < nb && j <= i) ? v[cu][u] : (i == j ? 1.0 : 0.0);
+      }
     }
   }
 }
@@ -551,9 +558,10 @@ __device__ __forceinline__ void factor_core(int nb, double* s_D, double* s_W, do
 template <bool TEAM>
 __device__ __forceinline__ void writeback_diag(double* A, int F, int c, int nb, const double* s_D, const double* s_W, double* wscr) {
   using Cfg = FrontCfg<TEAM>;
-  for (int t = threadIdx.x; t < nb * nb; t += kCholThreads) {
-    const int j = t / nb, i = t % nb;
-    if (i >= j) A[(size_t)(c + j) * F + c + i] = s_D[i * Cfg::LDD + j];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < nb; j += kCholThreads / 32) {          // a warp per column: no division by the (run-time) block size per element
+    double* col = A + (size_t)(c + j) * F + c;
+    for (int i = j + lane; i < nb; i += 32) col[i] = s_D[i * Cfg::LDD + j];
   }
   if (TEAM && wscr)
     for (int t = threadIdx.x; t < Cfg::WSCR; t += kCholThreads) wscr[t] = s_W[t];      // s_il follows s_W in shared memory
@@ -566,7 +574,6 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
   using Cfg = FrontCfg<TEAM>;
   constexpr int NB = Cfg::NB, TILE = Cfg::TILE, LDL = Cfg::LDL, LDD = Cfg::LDD, LDW = Cfg::LDW, LDX = Cfg::LDX;
   const int team = blockIdx.x / team_size, rank = blockIdx.x % team_size, n_teams = gridDim.x / team_size;
-  const int tid = rank * kCholThreads + threadIdx.x, nthr = team_size * kCholThreads;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int* bar = bars + team;
   double* const wscr = TEAM ? V.wscratch + (size_t)team * Cfg::WSCR : nullptr;
@@ -603,30 +610,34 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
       const double* __restrict__ U = V.arena + c.off;
       const int* __restrict__ rel = V.rel + c.rows_off;
       const int rc = c.r, Fc = c.F;
-      // tiles (bi >= bj), bi in [0, rc] (rc = rhs row), bj in [0, rc): enumerate the full rectangle and skip the upper part
-      const long long total = (long long)(rc + 1) * rc * 36;
-      // four elements per thread and step, all loads before the stores: the front is latency-bound otherwise (the compiler must
-      // keep a load behind the previous store into the same array)
-      constexpr int kEa = 4;
-      for (long long t0 = tid; t0 < total; t0 += (long long)nthr * kEa) {
-        double* dst[kEa];
-        double val[kEa];
+      // The team's warps take the scalar columns of the child's update block round-robin; a column's rows (from its own 6 x 6 diagonal
+      // block down, contiguous in the child) run along the lanes and land at 6 rel[i / 6] + i % 6 of the target column, the column's
+      // right-hand-side entry goes with lane 0.  (Enumerating the full (rc + 1) x rc x 36 rectangle element by element cost two 64-bit and
+      // two run-time 32-bit divisions per element and skipped half of them.)  Four elements per lane and step, all loads before the
+      // stores: the compiler must keep a load behind the previous store into the same array.
+      {
+        constexpr int kEa = 4, kW = kCholThreads / 32;
+        const int ncol = 6 * rc, gw = rank * kW + warp, nwarps = team_size * kW;
+        for (int jc = gw; jc < ncol; jc += nwarps) {
+          const int bj = jc / 6;
+          const double* __restrict__ Ucol = U + (size_t)(6 * c.w + jc) * Fc + 6 * c.w;       // row i of the update block at Ucol[i]
+          double* const Dcol = A + (size_t)(6 * rel[bj] + (jc - 6 * bj)) * F;
+          for (int i0 = 6 * bj + lane; i0 < ncol; i0 += 32 * kEa) {
+            double* dst[kEa];
+            double val[kEa];
 #pragma unroll
-        for (int u = 0; u < kEa; u++) {
-          const long long t = min(t0 + (long long)u * nthr, total - 1);
-          const int e = (int)(t % 36), tile = (int)(t / 36);
-          const int bi = tile % (rc + 1), bj = tile / (rc + 1);
-          const int a = e % 6, b = e / 6;            // a fastest: consecutive threads read consecutive child rows
-          const bool live = t0 + (long long)u * nthr < total && bi >= bj && !(bi == rc && a > 0);
-          const int src_row = (bi == rc) ? Fc - 1 : 6 * (c.w + bi) + a;
-          const int dst_row = (bi == rc) ? F - 1 : 6 * rel[bi] + a;
-          double* d = A + (size_t)(6 * rel[bj] + b) * F + dst_row;
-          // the loads are unconditional (every address is inside the two fronts) so that all of them are in flight together
-          val[u] = ldf<TEAM>(d) + __ldcg(U + (size_t)(6 * (c.w + bj) + b) * Fc + src_row);
-          dst[u] = live ? d : nullptr;
+            for (int u = 0; u < kEa; u++) {
+              const int i = i0 + 32 * u, ic = min(i, ncol - 1), bi = ic / 6;
+              double* d = Dcol + 6 * rel[bi] + (ic - 6 * bi);
+              // the loads are unconditional (every address is inside the two fronts) so that all of them are in flight together
+              val[u] = ldf<TEAM>(d) + __ldcg(Ucol + ic);
+              dst[u] = i < ncol ? d : nullptr;
+            }
+#pragma unroll
+            for (int u = 0; u < kEa; u++) if (dst[u]) *dst[u] = val[u];
+          }
+          if (lane == 0) { double* d = Dcol + (F - 1); *d = ldf<TEAM>(d) + __ldcg(Ucol - 6 * c.w + (Fc - 1)); }
         }
-#pragma unroll
-        for (int u = 0; u < kEa; u++) if (dst[u]) *dst[u] = val[u];
       }
       team_sync<TEAM>(bar, target, team_size);     // children are added one after the other: fixed summation order
     }
