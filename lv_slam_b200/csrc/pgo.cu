@@ -170,20 +170,21 @@ __global__ void __launch_bounds__(kPgoThreads) pgo_assemble_kernel(PgoDev D) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nd = (long long)D.nfree * 36, no = (long long)D.noff * 36, nb = (long long)D.nfree * 6;
   if (t < nd) {
-    const int v = (int)(t / 36), a = (int)(t % 36);
+    const unsigned tu = (unsigned)t;                // 42 nfree + 36 noff < 2^32 (checked in set_graph): 32-bit divisions by constants
+    const int v = (int)(tu / 36u), a = (int)(tu % 36u);
     double s = 0;
     for (int p = D.vptr[v]; p < D.vptr[v + 1]; p++) { const int inc = D.vinc[p]; s += D.ws[(size_t)(inc >> 1) * kEdgeWs + (inc & 1) * 36 + a]; }
     D.Hd[t] = s;
     if ((a % 7) == 0) atomicMax(&D.sc->max_diag_bits, (unsigned long long)__double_as_longlong(fabs(s)));   // exact: max is order independent
   } else if (t < nd + no) {
-    const long long u = t - nd;
-    const int o = (int)(u / 36), a = (int)(u % 36);
+    const unsigned u = (unsigned)(t - nd);
+    const int o = (int)(u / 36u), a = (int)(u % 36u);
     double s = 0;
     for (int p = D.optr[o]; p < D.optr[o + 1]; p++) s += D.ws[(size_t)D.oinc[p] * kEdgeWs + 72 + a];
     D.Ho[u] = s;
   } else if (t < nd + no + nb) {
-    const long long u = t - nd - no;
-    const int v = (int)(u / 6), a = (int)(u % 6);
+    const unsigned u = (unsigned)(t - nd - no);
+    const int v = (int)(u / 6u), a = (int)(u % 6u);
     double s = 0;
     for (int p = D.vptr[v]; p < D.vptr[v + 1]; p++) { const int inc = D.vinc[p]; s += D.ws[(size_t)(inc >> 1) * kEdgeWs + 108 + (inc & 1) * 6 + a]; }
     D.b[u] = s;
@@ -548,6 +549,7 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
   std::sort(blocks.begin(), blocks.end());
   blocks.erase(std::unique(blocks.begin(), blocks.end()), blocks.end());
   const int noff = (int)blocks.size();
+  if ((long long)nfree * 42 + (long long)noff * 36 >= (1ll << 32)) return fail(LVS_ERR_INVALID_ARG, "graph too large (the assembly kernels index its entries with 32 bits)");
   std::vector<int2> edge_ij(ne), edge_h(ne);
   std::vector<unsigned char> edge_tr(ne, 0);
   std::vector<int> edge_off(ne, -1);

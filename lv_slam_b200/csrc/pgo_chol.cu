@@ -334,15 +334,16 @@ __global__ void __launch_bounds__(kCholThreads) chol_scatter_kernel(CholView V, 
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nd = (long long)V.n * 36, no = (long long)V.n_off * 36;
   if (t < nd) {
-    const int v = (int)(t / 36), e = (int)(t % 36), a = e / 6, c = e % 6;
+    const unsigned tu = (unsigned)t;                          // n * 36 < 2^32 (checked at upload): 32-bit divisions by constants
+    const int v = (int)(tu / 36u), e = (int)(tu % 36u), a = e / 6, c = e % 6;
     V.arena[V.diag_dst[v] + (long long)c * V.diag_ld[v] + a] = Hd[t] + (a == c ? lambda : 0.0);
   } else if (t < nd + no) {
-    const long long u = t - nd;
-    const int o = (int)(u / 36), e = (int)(u % 36), a = e / 6, c = e % 6;     // target element (row part a, column part c)
+    const unsigned u = (unsigned)(t - nd);
+    const int o = (int)(u / 36u), e = (int)(u % 36u), a = e / 6, c = e % 6;     // target element (row part a, column part c)
     V.arena[V.off_dst[o] + (long long)c * V.off_ld[o] + a] = V.off_tr[o] ? Ho[(size_t)o * 36 + c * 6 + a] : Ho[(size_t)o * 36 + a * 6 + c];
   } else if (t < nd + no + (long long)V.n * 6) {
-    const long long u = t - nd - no;
-    const int v = (int)(u / 6), a = (int)(u % 6);
+    const unsigned u = (unsigned)(t - nd - no);
+    const int v = (int)(u / 6u), a = (int)(u % 6u);
     V.arena[V.rhs_dst[v] + (long long)a * V.diag_ld[v]] = b[u];
   }
 }
@@ -773,12 +774,12 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
         }
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        constexpr int NT8 = NB / 8, NTL = NT8 * (NT8 + 1) / 2;
+        // (NT8 is even: the triangle of tiles folds into an NT8 / 2 x (NT8 + 1) rectangle - row a holds tile row a and tile row NT8 - 1 - a)
+        constexpr int NT8 = NB / 8, NTL = NT8 * (NT8 + 1) / 2, NW8 = NT8 + 1;
+        static_assert(NT8 % 2 == 0, "folded tile triangle");
         for (int t = warp; t < NTL; t += kCholThreads / 32) {
-          int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-          while (ti * (ti + 1) / 2 > t) ti--;
-          while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-          const int tj = t - ti * (ti + 1) / 2;
+          const int fa = t / NW8, fb = t - fa * NW8;
+          const int ti = (fb <= fa) ? fa : NT8 - 1 - fa, tj = (fb <= fa) ? fb : fb - fa - 1;
           const double* pa = s_H + (lane & 3) * LDL + 8 * ti + (lane >> 2);
           const double* pb = s_H + (lane & 3) * LDL + 8 * tj + (lane >> 2);
           double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
         writeback_diag<TEAM>(A, F, base, NB, s_D, s_W, wscr);
       }
       for (int tile = tile_first; tile < ntiles; tile += tile_step) {
-        int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+        int ti = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);      // the two loops below make it exact
         while (ti * (ti + 1) / 2 > tile) ti--;
         while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
         const int tj = tile - ti * (ti + 1) / 2;
@@ -1135,6 +1136,7 @@ static int up(CholDevice& C, T** dst, const std::vector<T>& v, cudaStream_t st) 
 
 int chol_upload(const CholSymbolic& S, int n_off, CholDevice& C, cudaStream_t st) {
   chol_free(C);
+  if (((long long)S.n * 42 + (long long)n_off * 36) >= (1ll << 32)) return fail(LVS_ERR_INVALID_ARG, "graph too large for the scatter kernel's 32-bit element index");
   C.n = S.n; C.n_off = n_off; C.n_fronts = (int)S.fronts.size(); C.n_levels = (int)S.level_ptr.size() - 1; C.max_front = S.max_front;
   C.level_ptr = S.level_ptr;
   C.level_big.assign(std::max(C.n_levels, 0), 0);
