@@ -768,9 +768,11 @@ __global__ void __launch_bounds__(kCholThreads, TEAM ? 1 : 2) chol_front_kernel(
         // the next diagonal block S and the NB panel rows X that update it: S -= X X^T on the lower 8 x 8 tiles, spread over the warps
         double* s_H = s_dyn + Cfg::oX;                        // [nbk][LDL]: X[base + r][c + k] at k * LDL + r  (fits: oX + NB * LDL doubles of the phase C area)
         stage_diag<TEAM>(A, F, base, NB, s_D);
-        for (int t = threadIdx.x; t < nbk * NB; t += kCholThreads) {
-          const int r = t % NB, q = t / NB, qc = min(q, nb - 1);
-          cp_async8(s_H + q * LDL + r, A + (size_t)(c + qc) * F + base + r, q < nb ? 8 : 0);
+        for (int q = warp; q < nbk; q += kCholThreads / 32) {      // a warp per panel column, its lanes the 96 rows
+          const double* src = A + (size_t)(c + min(q, nb - 1)) * F + base;
+          double* dst = s_H + q * LDL;
+#pragma unroll
+          for (int u = 0; u < NB / 32; u++) cp_async8(dst + lane + 32 * u, src + lane + 32 * u, q < nb ? 8 : 0);
         }
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
