@@ -46,4 +46,16 @@ st = p.optimize(100, P.ALG_LM, P.SOLVER_DENSE)
 json.dump(dict(n_vertices=len(gr["poses7"]), n_edges=len(gr["ij"]), robust_chi2_initial=tot, chi2_initial=float(c.sum()), chi2_final=st["chi2_after"],
                first_lambdas=st["trace"][:5, 1].tolist(), first_chi2=st["trace"][:5, 0].tolist()),
           open(os.path.join(HERE, "pgo_sphere_200.json"), "w"), indent=1)
+# the same sphere with the global graph's unary constraints (GPS / IMU priors, the floor constraint) on every fifth vertex
+sys.path.insert(0, os.path.dirname(HERE))
+from test_oracle_pgo import _priors_on, FLOOR  # noqa: E402
+ij, meas, info, hub, ty = _priors_on(gr, np.random.default_rng(5), 5)
+p = P.OraclePGO()
+p.set_graph(gr["poses7"], ij, meas, info, hub, None, ty, FLOOR)
+e, c, tot = p.errors()
+st = p.optimize(100, P.ALG_LM, P.SOLVER_DENSE)
+json.dump(dict(n_vertices=len(gr["poses7"]), n_edges=len(ij), n_unary=int((ty != 0).sum()), kinds=sorted(set(int(t) for t in ty)), floor_plane=FLOOR.tolist(),
+               robust_chi2_initial=tot, chi2_initial=float(c.sum()), unary_error_abs_sum=float(np.abs(e[ty != 0]).sum()), chi2_final=st["chi2_after"],
+               pose_0=p.poses()[0].tolist(), pose_last=p.poses()[-1].tolist()),
+          open(os.path.join(HERE, "pgo_sphere_200_unary.json"), "w"), indent=1)
 print("golden files written")

@@ -268,3 +268,39 @@ def test_priors_pull_a_drifting_chain_back():
     before = np.abs(g["poses7"][:, :3] - g["truth7"][:, :3]).max()
     after = np.abs(o.poses()[:, :3] - g["truth7"][:, :3]).max()
     assert after < 0.25 * before, (before, after)
+
+
+def test_plane_edge_error_against_an_independent_numpy_restatement():
+    """EdgeSE3Plane::computeError (include/g2o/edge_se3_plane.hpp:40-47) with g2o's Plane3D arithmetic written out again in numpy with plain
+    rotation matrices (the oracle goes through Eigen's quaternion product): random poses, planes and measurements."""
+    rng = np.random.default_rng(12)
+
+    def rot(n):                                   # Plane3D::rotation: Rz(azimuth) * Ry(-elevation)
+        az, el = np.arctan2(n[1], n[0]), np.arctan2(n[2], np.hypot(n[0], n[1]))
+        Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+        Ry = np.array([[np.cos(-el), 0, np.sin(-el)], [0, 1, 0], [-np.sin(-el), 0, np.cos(-el)]])
+        return Rz @ Ry
+
+    for _ in range(200):
+        x = _rand_pose(rng)
+        plane, meas = rng.normal(size=4), rng.normal(size=4)
+        lp = _local_plane(G.matrix(x), plane)
+        lp = lp / np.linalg.norm(lp[:3])
+        m = meas / np.linalg.norm(meas[:3])
+        n = rot(lp[:3]).T @ m[:3]
+        want = [np.arctan2(n[1], n[0]), np.arctan2(n[2], np.hypot(n[0], n[1])), (-lp[3]) - (-m[3])]
+        np.testing.assert_allclose(P.prior_error(5, np.r_[meas, plane], x)[:3], want, atol=1e-11)
+
+
+def test_unary_constraint_graph_against_the_golden_pin():
+    gold = json.load(open(os.path.join(HERE, "golden", "pgo_sphere_200_unary.json")))
+    gr = G.sphere(20, 10, seed=7)
+    ij, meas, info, hub, ty = _priors_on(gr, np.random.default_rng(5), 5)
+    assert len(ij) == gold["n_edges"] and int((ty != 0).sum()) == gold["n_unary"] and sorted(set(int(t) for t in ty)) == gold["kinds"]
+    o = P.OraclePGO()
+    o.set_graph(gr["poses7"], ij, meas, info, hub, None, ty, np.array(gold["floor_plane"]))
+    e, c, tot = o.errors()
+    np.testing.assert_allclose([tot, c.sum(), np.abs(e[ty != 0]).sum()], [gold["robust_chi2_initial"], gold["chi2_initial"], gold["unary_error_abs_sum"]], rtol=1e-12)
+    st = o.optimize(100, P.ALG_LM, P.SOLVER_DENSE)
+    np.testing.assert_allclose(st["chi2_after"], gold["chi2_final"], rtol=1e-9)
+    np.testing.assert_allclose(o.poses()[0], gold["pose_0"], atol=1e-9)

@@ -86,3 +86,23 @@ def test_pose_graph_against_the_golden_sphere():
     k = min(5, len(st["trace"]), len(gold["first_chi2"]))
     assert np.allclose(st["trace"][:k, 0], gold["first_chi2"][:k], rtol=1e-6)
     assert np.allclose(st["trace"][:k, 1], gold["first_lambdas"][:k], rtol=1e-6)
+
+
+def test_unary_constraint_graph_against_the_golden_pin():
+    """The sphere with GPS / IMU priors and the floor constraint (lvs_pgo_set_graph_typed): the device against the committed pin, at the
+    tolerances of the live comparison (numeric Jacobians: tests/test_pgo_gpu.py)."""
+    import lv_slam_b200 as L
+    from test_oracle_pgo import _priors_on
+    gold = _gold("pgo_sphere_200_unary.json")
+    gr = G.sphere(20, 10, seed=7)
+    ij, meas, info, hub, ty = _priors_on(gr, np.random.default_rng(5), 5)
+    assert len(ij) == gold["n_edges"] and int((ty != 0).sum()) == gold["n_unary"]
+    pg = L.PoseGraph(0)
+    pg.set_graph(gr["poses7"], ij, meas, info, hub, None, ty, np.array(gold["floor_plane"]))
+    e, c, tot = pg.errors()
+    assert abs(tot - gold["robust_chi2_initial"]) <= 1e-9 * gold["robust_chi2_initial"]
+    assert abs(float(np.sum(c)) - gold["chi2_initial"]) <= 1e-9 * gold["chi2_initial"]
+    assert abs(float(np.abs(e[ty != 0]).sum()) - gold["unary_error_abs_sum"]) <= 1e-9 * gold["unary_error_abs_sum"]
+    st = pg.optimize(100)
+    assert abs(st["chi2_after"] - gold["chi2_final"]) <= 1e-5 * gold["chi2_final"]
+    assert np.abs(pg.poses()[0][:3] - np.array(gold["pose_0"])[:3]).max() <= 1e-5 and np.abs(pg.poses()[-1][:3] - np.array(gold["pose_last"])[:3]).max() <= 1e-5
