@@ -88,6 +88,7 @@ struct TargetBuildState {
 constexpr size_t kStageBudgetBytes = (size_t)1 << 30;
 constexpr int kStageGrow = 16;
 constexpr int kUploadLanes = 2;
+constexpr int kDeferGroup = 16;     // host clouds per repack launch of the plural setters
 struct StageBuf {
   float* d = nullptr;
   size_t cap = 0;
@@ -96,6 +97,7 @@ struct StageBuf {
                                      // would not do: it is re-recorded by the slot's NEXT upload, which may already be queued when
                                      // batches are pipelined, and the buffer would look busy until that one completes)
   bool in_flight = false;
+  bool pack_pending = false;         // copied, its repack waits for the group launch (plural setters)
 };
 
 constexpr int kMaxEvents = 2048;
@@ -128,6 +130,14 @@ struct lvs_ndt_batch {
   int lane_next = 0;
   BuildScratch batch_ws[kVoxBatch];   // scratch of the batched voxelisation (set_targets): one per cloud of a launch group, used on lanes[0].st
   cudaEvent_t ev_mark = nullptr;     // position of the compute stream, for resident inputs produced on it
+  // plural setters with host clouds: the repacks of a group of clouds go into ONE launch behind the group's last copy (72 repack launches of
+  // ~3 us each per bench step were the whole gap between the host-buffer and the resident step time)
+  bool defer_packs = false;
+  PackMany defer_pm;
+  int defer_max_n = 0;
+  CloudSlot* defer_slot[kPackMany];
+  int defer_stage[kPackMany];
+  cudaEvent_t ev_group = nullptr;
   std::vector<TargetGrid> targets;
   std::vector<TargetBuildState> tstate;
   std::vector<CloudSlot> target_pts, sources;
@@ -220,6 +230,30 @@ static int wait_all_uploads(lvs_ndt_batch* b) {
   return LVS_OK;
 }
 
+// Launches the deferred repacks of the plural setters' host clouds: one kernel behind the last copy of the group, then every slot's
+// `ready` and every staging buffer's `free` event.
+static int flush_packs(lvs_ndt_batch* b) {
+  PackMany& pm = b->defer_pm;
+  if (pm.count == 0) return LVS_OK;
+  cudaStream_t cp = b->up[0], pk = b->up[1];
+  if (!b->ev_group) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_group, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(b->ev_group, cp));
+  CUDA_TRY(cudaStreamWaitEvent(pk, b->ev_group, 0));
+  int rc = pack_many(pk, pm, b->defer_max_n);
+  if (rc) return rc;
+  b->total_launches++;
+  for (int k = 0; k < pm.count; k++) {
+    StageBuf& sb = b->ring[b->defer_stage[k]];
+    CUDA_TRY(cudaEventRecord(b->defer_slot[k]->ready, pk));
+    CUDA_TRY(cudaEventRecord(sb.free_ev, pk));
+    sb.in_flight = true; sb.pack_pending = false;
+    b->defer_slot[k]->ready_pending = true;
+  }
+  pm.count = 0; b->defer_max_n = 0;
+  b->uploads_in_flight = true;
+  return LVS_OK;
+}
+
 static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, size_t n, size_t stride_bytes, int on_device,
                         cudaStream_t resident_stream) {
   if (n > 0 && !xyz) return fail(LVS_ERR_INVALID_ARG, "xyz is NULL");
@@ -258,11 +292,13 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
   const size_t bytes = (n - 1) * stride_bytes + 12;
   // staging buffer: the oldest one if its repack has finished, else a new one while the budget allows, else wait for the oldest
   int pick = -1;
+  if (!b->ring.empty() && b->ring[b->ring_next].pack_pending) { int rcf = flush_packs(b); if (rcf) return rcf; }   // the ring came round inside a group
   if (!b->ring.empty()) {
     StageBuf& old = b->ring[b->ring_next];
     if (!old.in_flight || cudaEventQuery(old.free_ev) == cudaSuccess) { old.in_flight = false; pick = b->ring_next; }
     else (void)cudaGetLastError();
   }
+  if (pick < 0 && b->ring.size() < 4096 && b->defer_pm.count > 0) { int rcf = flush_packs(b); if (rcf) return rcf; }   // growing the ring renumbers its buffers
   if (pick < 0 && b->ring.size() < 4096) {
     // grow by several buffers at once (allocated here, not lazily): cudaMalloc stalls the pipeline, so the pool should reach
     // its steady size within the first batch instead of one buffer per batch
@@ -301,6 +337,17 @@ static int upload_cloud(lvs_ndt_batch* b, CloudSlot& slot, const float* xyz, siz
   if (!sb.free_ev) {
     CUDA_TRY(cudaEventCreateWithFlags(&sb.free_ev, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&sb.copied_ev, cudaEventDisableTiming));
+  }
+  if (b->defer_packs) {
+    PackMany& pm = b->defer_pm;
+    PackOne& c = pm.c[pm.count];
+    c.in = sb.d; c.out = slot.d_pts; c.n = (int)n; c.stride_floats = (int)(stride_bytes / 4);
+    b->defer_slot[pm.count] = &slot; b->defer_stage[pm.count] = pick;
+    pm.count++;
+    b->defer_max_n = std::max(b->defer_max_n, (int)n);
+    sb.pack_pending = true;
+    if (pm.count == kDeferGroup) return flush_packs(b);
+    return LVS_OK;
   }
   CUDA_TRY(cudaEventRecord(sb.copied_ev, cp));
   CUDA_TRY(cudaStreamWaitEvent(pk, sb.copied_ev, 0));
@@ -778,14 +825,24 @@ static int set_targets_many(lvs_ndt_batch* b, int n, const int32_t* slots, const
     BuildScratch* wss[kVoxBatch];
     int slot_of[kVoxBatch];
     int m = 0;
+    // host clouds: all copies of the group first, their repacks in one launch (flush_packs), then the voxelisation behind them
+    for (int k = 0; k < cnt; k++)
+      for (int q = 0; q < k; q++)
+        if (slots[base + q] == slots[base + k]) return fail(LVS_ERR_INVALID_ARG, "target slot %d appears twice in one set_targets call", slots[base + k]);
+    b->defer_packs = !on_device;
+    for (int k = 0; k < cnt && !rc; k++) {
+      const int slot = slots[base + k];
+      TargetBuildState& ts = b->tstate[slot];
+      if (ts.built_pending && ts.lane != 0) { cudaError_t e = cudaStreamWaitEvent(ln.st, ts.built, 0); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent", __FILE__, __LINE__); }
+      if (!rc) rc = upload_cloud(b, b->target_pts[slot], xyz[base + k], counts[base + k], stride_bytes, on_device, ln.st);
+    }
+    b->defer_packs = false;
+    { const int rcf = flush_packs(b); if (!rc) rc = rcf; }
+    if (rc) return rc;
     for (int k = 0; k < cnt; k++) {
       const int slot = slots[base + k];
-      for (int q = 0; q < m; q++)
-        if (slot_of[q] == slot) return fail(LVS_ERR_INVALID_ARG, "target slot %d appears twice in one set_targets call", slot);
       CloudSlot& cs = b->target_pts[slot];
       TargetBuildState& ts = b->tstate[slot];
-      if (ts.built_pending && ts.lane != 0) CUDA_TRY(cudaStreamWaitEvent(ln.st, ts.built, 0));
-      if ((rc = upload_cloud(b, cs, xyz[base + k], counts[base + k], stride_bytes, on_device, ln.st))) return rc;
       if (cs.ready_pending) { CUDA_TRY(cudaStreamWaitEvent(ln.st, cs.ready, 0)); cs.ready_pending = false; }
       rc = b->targets[slot].prepare(ln.st, cs.d_pts, (int)counts[base + k], b->prm, b->batch_ws[m]);
       if (rc < 0) return rc;
@@ -840,9 +897,11 @@ static int set_sources(lvs_ndt_batch* b, int n, const int32_t* slots, const floa
     if ((rc = slot_in_flight(b, false, slots[i]))) return rc;
   }
   if (!on_device) {
-    for (int i = 0; i < n; i++)
-      if ((rc = set_source(b, slots[i], xyz[i], counts[i], stride_bytes, 0))) return rc;
-    return LVS_OK;
+    b->defer_packs = true;
+    for (int i = 0; i < n && !rc; i++) rc = set_source(b, slots[i], xyz[i], counts[i], stride_bytes, 0);
+    b->defer_packs = false;
+    const int rcf = flush_packs(b);
+    return rc ? rc : rcf;
   }
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return fail(LVS_ERR_INVALID_ARG, "stride_bytes must be a multiple of 4 and >= 12");
   PackMany pm;
@@ -970,6 +1029,7 @@ int lvs_ndt_batch_destroy(lvs_ndt_batch_t* b) {
   }
   for (auto& ts : b->tstate) if (ts.built) cudaEventDestroy(ts.built);
   if (b->ev_mark) cudaEventDestroy(b->ev_mark);
+  if (b->ev_group) cudaEventDestroy(b->ev_group);
   if (b->d_stage) cudaFree(b->d_stage);
   if (b->d_pairs) cudaFree(b->d_pairs);
   if (b->d_states) cudaFree(b->d_states);
