@@ -185,19 +185,16 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
   }
   S.perm.resize(n); S.iperm.resize(n);
   for (int c = 0; c < n; c++) { S.perm[c] = order[post[c]]; S.iperm[S.perm[c]] = c; }
-  // column patterns in the final numbering, ascending: two transpositions instead of a sort per column (the row lists fill in column
-  // order, the column lists then fill in row order)
-  std::vector<std::vector<int>> col(n);
-  std::vector<int> par(n, -1);
-  {
-    std::vector<int> cnt(n, 0);
-    for (int c = 0; c < n; c++) for (int v : pat[S.perm[c]]) cnt[S.iperm[v]]++;
-    std::vector<std::vector<int>> row(n);
-    for (int r = 0; r < n; r++) row[r].reserve(cnt[r]);
-    for (int c = 0; c < n; c++) { col[c].reserve(pat[S.perm[c]].size()); for (int v : pat[S.perm[c]]) row[S.iperm[v]].push_back(c); }
-    for (int r = 0; r < n; r++) for (int c : row[r]) col[c].push_back(r);
+  // per column of the final numbering: pattern size and smallest row (its parent in the elimination tree) - all the supernode
+  // detection needs; the sorted patterns themselves are built further down for the LAST column of every front only
+  std::vector<int> csize(n), par(n, -1);
+  for (int c = 0; c < n; c++) {
+    const std::vector<int>& P = pat[S.perm[c]];
+    csize[c] = (int)P.size();
+    int best = n;
+    for (int v : P) best = std::min(best, S.iperm[v]);
+    if (!P.empty()) par[c] = best;
   }
-  for (int c = 0; c < n; c++) if (!col[c].empty()) par[c] = col[c][0];
   // fundamental supernodes: column c joins c-1 when pattern(c-1) = {c} u pattern(c)
   // plus RELAXED amalgamation: the last child of a front (its columns directly precede the front's in the postorder) is merged into it
   // when that pads the child's columns with few explicit zero rows - fewer, fatter fronts and fewer tree levels for a latency-bound
@@ -208,10 +205,10 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
   S.col_front.assign(n, -1);
   int pad_budget = 0;            // padding already accepted for the columns of the front being grown
   for (int c = 0; c < n; c++) {
-    bool join = c > 0 && par[c - 1] == c && col[c - 1].size() == col[c].size() + 1;
+    bool join = c > 0 && par[c - 1] == c && csize[c - 1] == csize[c] + 1;
     if (join) {}                            // fundamental: no padding added
     else if (c > 0 && par[c - 1] == c && relax > 0) {
-      const int extra = (int)col[c].size() + 1 - (int)col[c - 1].size();     // rows the child's last column lacks (>= 1 here)
+      const int extra = csize[c] + 1 - csize[c - 1];     // rows the child's last column lacks (>= 1 here)
       if (extra + pad_budget <= relax) { join = true; pad_budget += extra; }
     }
     if (!join) pad_budget = 0;
@@ -221,19 +218,30 @@ void chol_analyze(int n, int n_off, const int* off_ij, CholSymbolic& S) {
   }
   const int nf = (int)S.fronts.size();
   std::vector<std::vector<int>> fkids(nf);
+  // index sets R_S = pattern of the front's last column, ascending: two transpositions instead of a sort per column (the row lists fill
+  // in column order, the fronts' lists then fill in row order)
+  {
+    size_t total = 0;
+    for (int s = 0; s < nf; s++) { CholFront& f = S.fronts[s]; f.r = csize[f.c0 + f.w - 1]; f.rows_off = (int)total; total += f.r; }
+    S.rows.resize(total);
+    std::vector<int> rptr(n + 1, 0);
+    for (int s = 0; s < nf; s++) for (int v : pat[S.perm[S.fronts[s].c0 + S.fronts[s].w - 1]]) rptr[S.iperm[v] + 1]++;
+    for (int r = 0; r < n; r++) rptr[r + 1] += rptr[r];
+    std::vector<int> rfront(total), rfill(rptr.begin(), rptr.end() - 1);
+    for (int s = 0; s < nf; s++) for (int v : pat[S.perm[S.fronts[s].c0 + S.fronts[s].w - 1]]) rfront[rfill[S.iperm[v]]++] = s;
+    std::vector<int> ffill(nf);
+    for (int s = 0; s < nf; s++) ffill[s] = S.fronts[s].rows_off;
+    for (int r = 0; r < n; r++) for (int k = rptr[r]; k < rptr[r + 1]; k++) S.rows[ffill[rfront[k]]++] = r;
+  }
   for (int s = 0; s < nf; s++) {
     CholFront& f = S.fronts[s];
-    const std::vector<int>& R = col[f.c0 + f.w - 1];
-    f.r = (int)R.size();
     f.F = 6 * (f.w + f.r) + 1;
-    f.rows_off = (int)S.rows.size();
-    S.rows.insert(S.rows.end(), R.begin(), R.end());
-    f.parent = f.r ? S.col_front[R[0]] : -1;
+    f.parent = f.r ? S.col_front[par[f.c0 + f.w - 1]] : -1;
     if (f.parent >= 0) fkids[f.parent].push_back(s);
     f.off = S.arena;
     S.arena += (long long)f.F * f.F;
     S.max_front = std::max(S.max_front, f.F);
-    for (int k = 0; k < f.w; k++) S.nnz_l_blocks += 1 + (long long)col[f.c0 + k].size();   // the true fill: padding of relaxed supernodes is stored (arena, flops) but not counted
+    for (int k = 0; k < f.w; k++) S.nnz_l_blocks += 1 + (long long)csize[f.c0 + k];   // the true fill: padding of relaxed supernodes is stored (arena, flops) but not counted
     for (int k = 0; k < f.w; k++) { const double m = 6.0 * (f.w - k - 1 + f.r) + 1; S.flops += 3.0 * m * m; }   // 6 pivot columns x m^2 / 2
   }
   // relative indices: position of every row of R_S inside the parent's index set (its pivots, then its R)
