@@ -45,8 +45,13 @@ typedef enum {
 
 /* pclomp::NeighborSearchMethod, include/ndt_omp/ndt_omp.h:61 (same values in pclpca) */
 typedef enum { LVS_KDTREE = 0, LVS_DIRECT26 = 1, LVS_DIRECT7 = 2, LVS_DIRECT1 = 3 } lvs_search_method;
-/* which of the two registration classes is mirrored */
-typedef enum { LVS_NDT_OMP = 0, LVS_NDT_PCA = 1 } lvs_ndt_variant;
+/* which registration class is mirrored: pclomp:: (include/ndt_omp/ndt_omp.h), pclpca:: (include/ndt_pca/ndt_pca.h) or
+ * pclomp_ground::NormalDistributionsTransformGround (include/ndt_omp/ndt_ground.h, ndt_ground_impl.hpp) - the horizontal-voxel NDT
+ * that solves z / roll / pitch only: a source point counts when the LAST cell of its neighbourhood has a normal within 10 degrees of
+ * the z axis (computeDerivatives_seg with flag_class = 1, ndt_ground_impl.hpp:363-572), its gradient and Hessian terms count twice
+ * (updateDerivatives is called twice per cell, :519,522), rows and columns x, y, yaw are zeroed before the SVD solve (:554-561) and
+ * the step-length test also ends the first iteration (:173).  LVS_NDT_GROUND runs with LVS_ACC_EXACT only. */
+typedef enum { LVS_NDT_OMP = 0, LVS_NDT_PCA = 1, LVS_NDT_GROUND = 2 } lvs_ndt_variant;
 /* How the per-(point, cell) terms of computeDerivatives (ndt_omp_impl2.hpp:567-619) are formed and summed.
  *   LVS_ACC_EXACT (default): every float32 term is formed in the reference's operation order without contraction (bit-identical to
  *                 the CPU path, expf included) and added in fp64, like `hessian(i,j) += float_expr` does.
@@ -66,7 +71,7 @@ typedef struct {
   double transformation_epsilon; /* setTransformationEpsilon (0.1) */
   int32_t max_iterations;      /* setMaximumIterations     (35)   */
   int32_t search_method;       /* setNeighborhoodSearchMethod (LVS_DIRECT7) */
-  int32_t variant;             /* LVS_NDT_OMP | LVS_NDT_PCA */
+  int32_t variant;             /* lvs_ndt_variant (LVS_NDT_OMP) */
   int32_t min_points_per_voxel;  /* VoxelGridCovariance default 6 (voxel_grid_covariance_omp.h:204) */
   double min_covar_eigvalue_mult; /* 0.01 (voxel_grid_covariance_omp.h:205) */
   int32_t accumulation;        /* lvs_ndt_accumulation; not a reference parameter (LVS_ACC_EXACT) */
@@ -151,6 +156,10 @@ int lvs_ndt_num_cells(lvs_ndt_t* h, int* n_cells);   /* every occupied cell, i.e
  * min_points_per_voxel except mean, exactly like the reference's Leaf. */
 int lvs_ndt_get_cells(lvs_ndt_t* h, int32_t* keys, int32_t* nr_points, double* mean3, double* icov9,
                       double* evals3, float* centroid3, int32_t* weight);
+/* LVS_NDT_GROUND: per occupied cell (ascending key order, like lvs_ndt_get_cells) 1 when the cell's normal - the eigenvector of the
+ * smallest covariance eigenvalue, Leaf::getEvecs().col(0) - is less than 10 degrees from the z axis (ndt_ground_impl.hpp:507-511,533),
+ * else 0; all 0 for the other variants. */
+int lvs_ndt_get_cell_horizontal(lvs_ndt_t* h, int32_t* horizontal);
 /* Voxel key the lookup path computes for T16 * source point i, -1 outside the bounding box
  * (voxel_grid_covariance_omp_impl.hpp:379-394). */
 int lvs_ndt_lookup_keys(lvs_ndt_t* h, const float T16[16], int32_t* keys_out);

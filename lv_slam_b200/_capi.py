@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblvslam_b200.so")
 
 LVS_KDTREE, LVS_DIRECT26, LVS_DIRECT7, LVS_DIRECT1 = 0, 1, 2, 3
-LVS_NDT_OMP, LVS_NDT_PCA = 0, 1
+LVS_NDT_OMP, LVS_NDT_PCA, LVS_NDT_GROUND = 0, 1, 2
 LVS_ACC_EXACT, LVS_ACC_FAST = 0, 1
 
 STATUS = {0: "LVS_OK", -1: "LVS_ERR_INVALID_ARG", -2: "LVS_ERR_NO_DEVICE", -3: "LVS_ERR_CUDA", -4: "LVS_ERR_OOM",
@@ -73,7 +73,7 @@ def lib():
             "lvs_ndt_get_aligned_cloud": [vp, vp, i32], "lvs_ndt_get_trace": [vp, vp, i32, vp],
             "lvs_ndt_eval_derivatives": [vp, vp, vp, i32, vp, vp, vp], "lvs_ndt_eval_hessian": [vp, vp, vp, vp],
             "lvs_ndt_calculate_score": [vp, vp, vp], "lvs_ndt_get_grid": [vp, vp, vp, vp], "lvs_ndt_num_cells": [vp, vp],
-            "lvs_ndt_get_cells": [vp] * 8, "lvs_ndt_lookup_keys": [vp, vp, vp], "lvs_ndt_handle_batch": [vp, vp],
+            "lvs_ndt_get_cells": [vp] * 8, "lvs_ndt_get_cell_horizontal": [vp, vp], "lvs_ndt_lookup_keys": [vp, vp, vp], "lvs_ndt_handle_batch": [vp, vp],
             "lvs_ndt_batch_create": [vp, i32, vp, i32, i32, vp], "lvs_ndt_batch_destroy": [vp],
             "lvs_ndt_batch_set_target": [vp, i32, vp, sz, sz, i32], "lvs_ndt_batch_set_source": [vp, i32, vp, sz, sz, i32],
             "lvs_ndt_batch_align": [vp, i32, vp, vp, vp, vp], "lvs_ndt_batch_last_stats": [vp, vp, vp, vp, vp],

@@ -51,10 +51,11 @@ static int check_params(const lvs_ndt_params* p) {
   if (!p) return fail(LVS_ERR_INVALID_ARG, "params is NULL");
   if (!(p->resolution > 0.0f)) return fail(LVS_ERR_INVALID_ARG, "resolution must be > 0");
   if (p->search_method < LVS_KDTREE || p->search_method > LVS_DIRECT1) return fail(LVS_ERR_INVALID_ARG, "unknown search_method %d", p->search_method);
-  if (p->variant != LVS_NDT_OMP && p->variant != LVS_NDT_PCA) return fail(LVS_ERR_INVALID_ARG, "unknown variant %d", p->variant);
+  if (p->variant != LVS_NDT_OMP && p->variant != LVS_NDT_PCA && p->variant != LVS_NDT_GROUND) return fail(LVS_ERR_INVALID_ARG, "unknown variant %d", p->variant);
   if (p->max_iterations < 0 || p->max_iterations > kMaxTrace - 4) return fail(LVS_ERR_INVALID_ARG, "max_iterations must be in [0, %d]", kMaxTrace - 4);
   if (p->min_points_per_voxel < 1) return fail(LVS_ERR_INVALID_ARG, "min_points_per_voxel must be >= 1");
   if (p->accumulation != LVS_ACC_EXACT && p->accumulation != LVS_ACC_FAST) return fail(LVS_ERR_INVALID_ARG, "unknown accumulation %d", p->accumulation);
+  if (p->variant == LVS_NDT_GROUND && p->accumulation != LVS_ACC_EXACT) return fail(LVS_ERR_INVALID_ARG, "LVS_NDT_GROUND runs with LVS_ACC_EXACT only");
   return LVS_OK;
 }
 
@@ -1480,6 +1481,22 @@ int lvs_ndt_get_cells(lvs_ndt_t* h, int32_t* keys, int32_t* nr_points, double* m
     CUDA_TRY(cudaMemcpy(c.data(), t.d_centroids, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) { centroid3[i * 3] = c[i].x; centroid3[i * 3 + 1] = c[i].y; centroid3[i * 3 + 2] = c[i].z; }
   }
+  return LVS_OK;
+}
+
+int lvs_ndt_get_cell_horizontal(lvs_ndt_t* h, int32_t* horizontal) {
+  if (!h || !horizontal) return fail(LVS_ERR_INVALID_ARG, "NULL argument");
+  lvs_ndt_batch* b = h->b;
+  int rc = set_device(b);
+  if (!rc) rc = finish_target(b, 0);
+  if (rc) return rc;
+  const TargetGrid& t = b->targets[0];
+  const int n = t.n_cells;
+  if (n == 0) return LVS_OK;
+  CUDA_TRY(cudaStreamSynchronize(b->st));
+  std::vector<VoxelRec> recs(n);
+  CUDA_TRY(cudaMemcpy(recs.data(), t.d_recs, (size_t)n * sizeof(VoxelRec), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) horizontal[i] = (recs[i].meta & kMetaHorizBit) ? 1 : 0;
   return LVS_OK;
 }
 

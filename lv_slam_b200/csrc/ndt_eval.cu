@@ -215,7 +215,7 @@ __device__ __forceinline__ void process_round(double (*acc)[2], const VoxelRec* 
   __syncwarp();
 }
 
-template <int MODE, bool HESS, bool PCA>
+template <int MODE, bool HESS, bool PCA, bool GROUND>
 __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2,
                                            double gd1, unsigned char* s_dyn, double* partial, float one_f, const unsigned long long* etab) {
   using Sh = Shape<HESS>;
@@ -287,6 +287,9 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
         // ndt_pca multiplies the RUNNING per-point sums by each cell's weight (ndt_pca_impl2.hpp:293-296): the contribution of
         // cell k ends up scaled by the product of the weights of cells k..last, hence the probes run last-to-first.
         double run = 1.0;
+        // pclomp_ground counts a point only when the LAST cell of its neighbourhood is near-horizontal (ndt_ground_impl.hpp:484,511,533):
+        // the probes run last-to-first, so the first hit decides for all of the point's cells
+        bool gate_known = false, gate = true;
 #pragma unroll(MODE == LVS_DIRECT26 ? 1 : K)
         for (int k = K - 1; k >= 0; k--) {
           int ox = 0, oy = 0, oz = 0;
@@ -295,7 +298,11 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
           int v = -1;
           if (ok && (unsigned)(rx + ox) < (unsigned)div0 && (unsigned)(ry + oy) < (unsigned)div1 && (unsigned)(rz + oz) < (unsigned)div2)
             v = __ldg(grid + (cell0 + ox * G.mul[0] + oy * G.mul[1] + oz * G.mul[2]));
-          const bool hit = v >= 0;
+          bool hit = v >= 0;
+          if (GROUND && hit) {
+            if (!gate_known) { gate = (__ldg(&recs[v].meta) & kMetaHorizBit) != 0; gate_known = true; }
+            hit = gate;
+          }
           const unsigned m = __ballot_sync(0xffffffffu, hit);
           if (MODE == LVS_DIRECT26) {
             if (m == 0u) continue;
@@ -348,7 +355,7 @@ __device__ __forceinline__ void run_direct(const PairDesc& P, const GridView& G,
   }
 }
 
-template <int MODE, bool PCA>
+template <int MODE, bool PCA, bool GROUND>
 __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ float s_T[16], s_R[9];
@@ -370,23 +377,23 @@ __global__ void __launch_bounds__(kEvalThreads, 3) ndt_eval_kernel(EvalLaunch L)
   const float gd2 = (float)c.gauss_d2;
   double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kPartialStride;
   const int bpp = L.blocks_per_pair;
-  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
-  else run_direct<MODE, false, PCA>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
+  if (kind == EVAL_DERIV_H) run_direct<MODE, true, PCA, GROUND>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
+  else run_direct<MODE, false, PCA, GROUND>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, s_dyn, partial, L.one, s_etab);
   pdl_trigger();
   eval_finish(L, pair, kind, kind == EVAL_DERIV_H ? kAcc : 7, P.n_total, reinterpret_cast<double*>(s_dyn), &s_last, t_entry);
 }
 
-template <int MODE, bool PCA>
+template <int MODE, bool PCA, bool GROUND = false>
 static int launch_eval_as(cudaStream_t st, const EvalLaunch& L) {
   static int attr_dev = -1;     // the opt-in shared-memory size is a per-device function attribute
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   constexpr size_t smem = SmemLayout<PCA>::bytes;
   if (attr_dev != dev) {
-    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel<MODE, PCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(ndt_eval_kernel<MODE, PCA, GROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = dev;
   }
-  return launch_pdl(ndt_eval_kernel<MODE, PCA>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, smem, st, L);
+  return launch_pdl(ndt_eval_kernel<MODE, PCA, GROUND>, (unsigned)(L.n_pairs * L.blocks_per_pair), kEvalThreads, smem, st, L);
 }
 
 // The search mode and the registration variant are launch constants, so each combination is its own kernel (unrolled probe
@@ -395,6 +402,14 @@ int launch_eval(cudaStream_t st, const EvalLaunch& L) {
   if (L.n_pairs <= 0) return LVS_OK;
   if (L.consts.fast) return launch_eval_fast(st, L);       // tolerance mode: ndt_eval_fast.cu
   const bool pca = L.consts.variant == LVS_NDT_PCA;
+  if (L.consts.variant == LVS_NDT_GROUND) {                 // pclomp_ground: the ndt_omp pass with the last-neighbour gate
+    switch (L.consts.search) {
+      case LVS_DIRECT1: return launch_eval_as<LVS_DIRECT1, false, true>(st, L);
+      case LVS_DIRECT7: return launch_eval_as<LVS_DIRECT7, false, true>(st, L);
+      case LVS_DIRECT26: return launch_eval_as<LVS_DIRECT26, false, true>(st, L);
+      default: return LVS_OK;
+    }
+  }
   switch (L.consts.search) {
     case LVS_DIRECT1: return pca ? launch_eval_as<LVS_DIRECT1, true>(st, L) : launch_eval_as<LVS_DIRECT1, false>(st, L);
     case LVS_DIRECT7: return pca ? launch_eval_as<LVS_DIRECT7, true>(st, L) : launch_eval_as<LVS_DIRECT7, false>(st, L);

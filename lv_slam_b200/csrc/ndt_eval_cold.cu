@@ -176,13 +176,15 @@ __device__ __forceinline__ void radius_neighbours(RadiusHits& Hh, const PairDesc
 // KDTREE search mode of computeDerivatives: float contributions over radius neighbours.
 template <bool HESS>
 __device__ __noinline__ void point_kdtree(Acc<HESS>& A, const PairDesc& P, const GridView& G, const float* T, const float* R, float4 s, float gd2,
-                                          double gd1, bool pca, float radius) {
+                                          double gd1, bool pca, bool ground, float radius) {
   float tx, ty, tz;
   transform_point(T, s.x, s.y, s.z, tx, ty, tz);
   if (!(isfinite(tx) && isfinite(ty) && isfinite(tz))) return;
   RadiusHits Hh;
   radius_neighbours(Hh, P, G, tx, ty, tz, radius, true);
   if (Hh.n == 0) return;
+  // pclomp_ground: the point counts only when the LAST neighbour's normal is near the z axis (ndt_ground_impl.hpp:484,511,533)
+  if (ground && !(P.recs[Hh.rec[Hh.n - 1]].meta & kMetaHorizBit)) return;
   const float xr = (R[0] * s.x + R[1] * s.y) + R[2] * s.z;
   const float yr = (R[3] * s.x + R[4] * s.y) + R[5] * s.z;
   const float zr = (R[6] * s.x + R[7] * s.y) + R[8] * s.z;
@@ -244,12 +246,12 @@ __device__ __forceinline__ void block_reduce_store(const double* v, double* s_re
 
 template <bool HESS>
 __device__ __noinline__ void run_kdtree(const PairDesc& P, const GridView& G, const float* T, const float* R, int blk, int bpp, float gd2, double gd1,
-                                        bool pca, float radius, double* s_red, double* partial) {
+                                        bool pca, bool ground, float radius, double* s_red, double* partial) {
   Acc<HESS> A;
   A.zero();
   if (!G.empty)
     for (int i = blk * kEvalThreads + threadIdx.x; i < P.n_src; i += bpp * kEvalThreads)
-      point_kdtree<HESS>(A, P, G, T, R, __ldg(P.src + i), gd2, gd1, pca, radius);
+      point_kdtree<HESS>(A, P, G, T, R, __ldg(P.src + i), gd2, gd1, pca, ground, radius);
   double v[kAcc];
   v[0] = A.score;
   for (int i = 0; i < 6; i++) v[1 + i] = A.g[i];
@@ -287,12 +289,12 @@ __global__ void __launch_bounds__(kEvalThreads) ndt_eval_cold_kernel(EvalLaunch 
   __syncthreads();
   const GridView G = load_grid_view(P.gp);
   const float gd2 = (float)c.gauss_d2;
-  const bool pca = c.variant == LVS_NDT_PCA;
+  const bool pca = c.variant == LVS_NDT_PCA, ground = c.variant == LVS_NDT_GROUND;
   double* partial = L.d_partials + ((size_t)pair * L.blocks_per_pair + blk) * kPartialStride;
   const int bpp = L.blocks_per_pair;
   if (kind == EVAL_HESS27) run_hess27(P, G, s_T, s_Rd, blk, bpp, c.gauss_d1, c.gauss_d2, c.resolution, s_red, partial);
-  else if (kind == EVAL_DERIV_H) run_kdtree<true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);
-  else run_kdtree<false>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, c.resolution, s_red, partial);
+  else if (kind == EVAL_DERIV_H) run_kdtree<true>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, ground, c.resolution, s_red, partial);
+  else run_kdtree<false>(P, G, s_T, s_R, blk, bpp, gd2, c.gauss_d1, pca, ground, c.resolution, s_red, partial);
   pdl_trigger();
   eval_finish(L, pair, kind, kAcc, P.n_total, s_red, &s_last);
 }

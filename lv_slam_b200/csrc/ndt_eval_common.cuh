@@ -176,6 +176,13 @@ __device__ __forceinline__ void eval_finish(const EvalLaunch& L, int pair, int k
   }
   if (threadIdx.x < nv) {
     const int k = threadIdx.x;
+    if (c.variant == LVS_NDT_GROUND && kind != EVAL_HESS27 && k >= 1) {
+      // computeDerivatives_seg: updateDerivatives runs twice per cell and both calls add into the gradient and the Hessian, only the
+      // second one's score is kept (ndt_ground_impl.hpp:519,522); rows and columns x, y, yaw are zeroed afterwards (:554-561)
+      const int i = k < 7 ? k - 1 : (k - 7) / 6, j = k < 7 ? k - 1 : (k - 7) % 6;
+      const bool off = i == 0 || i == 1 || i == 5 || j == 0 || j == 1 || j == 5;
+      x = off ? 0.0 : 2.0 * x;
+    }
     if (kind == EVAL_HESS27) { if (k >= 7) s_state.H[k - 7] = x; }
     else {
       if (k == 0) s_state.score = x;

@@ -250,7 +250,8 @@ LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, 
       }
       if (s.trace_on) s.n_trace++;
       for (int i = 0; i < 6; i++) s.p[i] = pn[i];
-      if (s.nr_iterations > c.max_iter || (s.nr_iterations && (fabs(s.a_t) < c.trans_eps))) s.converged = 1;
+      // pclomp_ground tests the step length in the first iteration too (ndt_ground_impl.hpp:173)
+      if (s.nr_iterations > c.max_iter || ((s.nr_iterations || c.variant == LVS_NDT_GROUND) && (fabs(s.a_t) < c.trans_eps))) s.converged = 1;
       s.nr_iterations++;
       if (s.converged) {
         s.trans_probability = s.score / (double)n_src;
@@ -307,7 +308,9 @@ LVS_HD bool align_state_advance(AlignState& s, const AlignConsts& c, int n_src, 
       s.eval_kind = EVAL_DERIV_H;
       // lean_final_evaluation: with the More-Thuente loop dead (interval_converged set above) the step length is final, so the test of
       // :175-179 can be made now; when it will end the align, only the score of the coming pass is ever read (:187) - skip its Hessian
-      if (c.lean_final && s.interval_converged && (s.nr_iterations > c.max_iter || (s.nr_iterations && (fabs(s.a_t) < c.trans_eps)))) s.eval_kind = EVAL_DERIV_NOH;
+      if (c.lean_final && s.interval_converged &&
+          (s.nr_iterations > c.max_iter || ((s.nr_iterations || c.variant == LVS_NDT_GROUND) && (fabs(s.a_t) < c.trans_eps))))
+        s.eval_kind = EVAL_DERIV_NOH;
       s.phase = PH_MT_FIRST;
       return false;
     }

@@ -12,7 +12,8 @@ namespace lvs {
 //                    covariances are not exactly symmetric.  Storage order C00 C01 | C10 C11 | C20 C21 | C02 C12 C22 (kIcovSlot):
 //                    the (C[r][0], C[r][1]) pairs land 8-byte aligned for the packed FP32 math of the hot kernel
 //   meta  : low 24 bits = ndt_pca integer weight int(scale*|mean|) (1 for ndt_omp),
-//           bit 30 = leaf usable by the direct searches (nr_points >= min_points and not invalidated)
+//           bit 30 = leaf usable by the direct searches (nr_points >= min_points and not invalidated),
+//           bit 29 = pclomp_ground only: the leaf's normal is within 10 degrees of the z axis (ndt_ground_impl.hpp:507-511,533)
 struct __align__(16) VoxelRec {
   double mean[3];
   float icov[9];
@@ -34,6 +35,7 @@ static_assert(sizeof(FastRec) == 48, "FastRec must be 48 bytes");
 __host__ __device__ constexpr int icov_slot(int a) { return (a % 3 == 2) ? 6 + a / 3 : 2 * (a / 3) + a % 3; }
 
 constexpr int kMetaValidBit = 1 << 30;
+constexpr int kMetaHorizBit = 1 << 29;
 constexpr int kMetaWeightMask = 0xFFFFFF;
 
 // Geometry of one target's voxel grid (voxel_grid_covariance_omp_impl.hpp:87-103), produced on the device.

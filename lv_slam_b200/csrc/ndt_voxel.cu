@@ -479,6 +479,13 @@ __global__ void __launch_bounds__(128) leaf_finalize_kernel(VoxBatch B, int cur)
       for (int a = 0; a < 9; a++) cov[a] *= sc;
       double V[9];
       sym3_eigen(cov, ev, V);                 // reads the lower triangle, like SelfAdjointEigenSolver
+      // pclomp_ground: is the leaf's normal (first column of evecs_, assigned before the eigenvalue check below, :335) within 10 degrees of
+      // the z axis?  acos(|n_z| / |n|) * 180 / 3.1415926 < 10 as ndt_ground_impl.hpp:507-511,533 writes it
+      bool horiz = false;
+      if (variant == LVS_NDT_GROUND) {
+        const double nrm = sqrt((V[0] * V[0] + V[3] * V[3]) + V[6] * V[6]);
+        horiz = acos(fabs(V[6] / nrm)) * 180 / 3.1415926 < 10;
+      }
       if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
         out_npts = -1;
         ev[0] = ev[1] = ev[2] = 0.0;          // evals_ is assigned only after the check (:357)
@@ -511,6 +518,7 @@ __global__ void __launch_bounds__(128) leaf_finalize_kernel(VoxBatch B, int cur)
         else usable = true;
         rec.meta = (weight & kMetaWeightMask) | (usable ? kMetaValidBit : 0);
       }
+      if (horiz) rec.meta |= kMetaHorizBit;
     }
     recs[seg] = rec;
     {

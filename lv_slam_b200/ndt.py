@@ -119,7 +119,8 @@ def pack_guesses(guesses):
 
 
 class NormalDistributionsTransform:
-    """One registration object.  ``variant`` selects pclomp (LVS_NDT_OMP) or pclpca (LVS_NDT_PCA)."""
+    """One registration object.  ``variant`` selects pclomp (LVS_NDT_OMP), pclpca (LVS_NDT_PCA) or
+    pclomp_ground::NormalDistributionsTransformGround (LVS_NDT_GROUND, include/ndt_omp/ndt_ground.h)."""
 
     def __init__(self, variant=C.LVS_NDT_OMP, device=0, stream=None):
         self._L = C.lib()
@@ -279,6 +280,15 @@ class NormalDistributionsTransform:
         C.check(self._L.lvs_ndt_get_cells(self._h, *[out[k].ctypes.data for k in ("keys", "nr_points", "mean", "icov", "evals", "centroid", "weight")]))
         return out
 
+    def cell_horizontal(self):
+        """pclomp_ground: 1 per occupied cell (the order of cells()) whose normal is within 10 degrees of the z axis
+        (ndt_ground_impl.hpp:507-511,533); all 0 for the other variants."""
+        n = ctypes.c_int(0)
+        C.check(self._L.lvs_ndt_num_cells(self._h, ctypes.byref(n)))
+        out = np.zeros(n.value, np.int32)
+        C.check(self._L.lvs_ndt_get_cell_horizontal(self._h, out.ctypes.data))
+        return out
+
     def lookup_keys(self, T):
         g = _colmajor16(T)
         keys = np.zeros(self._n_src, np.int32)
@@ -303,6 +313,14 @@ def _shard_setup(L, batch_handle, rank, world, max_pairs, exchange):
         raise ValueError("exchange() must return one 64-byte handle per rank")
     allh = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(blobs))
     C.check(L.lvs_ndt_batch_shard_connect(batch_handle, allh))
+
+
+class NormalDistributionsTransformGround(NormalDistributionsTransform):
+    """pclomp_ground::NormalDistributionsTransformGround (include/ndt_omp/ndt_ground.h:69, ndt_ground_impl.hpp): the registration
+    object scan_matching_odom_nodelet.cpp:121-126 configures as ``ground_s2k`` (resolution 10, DIRECT1, epsilon 0.01, 64 iterations)."""
+
+    def __init__(self, device=0, stream=None):
+        super().__init__(variant=C.LVS_NDT_GROUND, device=device, stream=stream)
 
 
 class NdtBatch:

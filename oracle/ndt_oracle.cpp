@@ -21,6 +21,10 @@
 //   computeHessian / updateHessian        include/ndt_omp/ndt_omp_impl2.hpp:623-714
 //   updateIntervalMT/trialValueSelectionMT/computeStepLengthMT   :718-755, :759-838, :842-1003
 //   calculateScore                        include/ndt_omp/ndt_omp_impl2.hpp:1007-1040
+//   pclomp_ground (VAR_GROUND)            include/ndt_omp/ndt_ground_impl.hpp: computeTransformation :88-179 (flag_class = 1),
+//                                         computeDerivatives_seg :363-572; everything else is textually ndt_omp_impl2.hpp.
+//                                         It is the one consumer of the eigenVECTORS (leaf normal): the cyclic Jacobi of olin.h
+//                                         converges to the same eigenvector as Eigen's QL up to sign and rounding, and only |n_z| is read.
 // PCL pieces the reference calls but does not vendor (PCL 1.8.1, ros:melodic):
 //   pcl::Registration::align              (copies input to output, resets transforms, calls computeTransformation)
 //   pcl::transformPointCloud (dense)      x' = ((m00*x + m01*y) + m02*z) + m03 in float, no FMA
@@ -65,7 +69,7 @@ using olin::V3;
 namespace {
 
 enum SearchMethod { KDTREE = 0, DIRECT26 = 1, DIRECT7 = 2, DIRECT1 = 3 };  // ndt_omp.h:61
-enum Variant { VAR_OMP = 0, VAR_PCA = 1 };
+enum Variant { VAR_OMP = 0, VAR_PCA = 1, VAR_GROUND = 2 };
 
 struct Leaf {                       // voxel_grid_covariance_omp.h:92-195
   int nr_points = 0;
@@ -218,6 +222,16 @@ void apply_filter(NDT& n) {         // voxel_grid_covariance_omp_impl.hpp:49-370
 
 inline int leaf_weight(const NDT& n, const Leaf& l) {   // int getDimension2d() truncates (voxel_grid_covariance_pca.h:222-226)
   return n.variant == VAR_PCA ? (int)l.dimension_2d : 1;
+}
+
+// pclomp_ground: angle between the leaf's normal (eigenvector of the smallest eigenvalue, first column of evecs_) and the z axis, in
+// degrees with the reference's constant (include/ndt_omp/ndt_ground_impl.hpp:507-511).  evecs_ is assigned before the eigenvalue
+// check (voxel_grid_covariance_omp_impl.hpp:335), so invalidated leaves have one too.
+inline double leaf_angle2xy(const Leaf& l) {
+  double nx = l.evecs[0][0], ny = l.evecs[1][0], nz = l.evecs[2][0];
+  double nrm = std::sqrt((nx * nx + ny * ny) + nz * nz);      // Vector3d::normalize(): divides by norm()
+  nz = nz / nrm;
+  return std::acos(std::fabs(nz)) * 180 / 3.1415926;
 }
 
 // Offsets for the direct searches.  DIRECT7: voxel_grid_covariance_omp_impl.hpp:423-430.
@@ -393,11 +407,18 @@ double compute_derivatives(NDT& n, double g_out[6], double H_out[6][6], const st
     }
     double score_pt = 0, g_pt[6] = {0, 0, 0, 0, 0, 0}, H_pt[6][6];
     std::memset(H_pt, 0, sizeof H_pt);
+    double angle2xy = 0;                             // pclomp_ground: overwritten per cell, so the LAST neighbour decides (ndt_ground_impl.hpp:484,511)
     for (const Leaf* cell : nb) {
       const Pt xo = n.input[idx];
       double x[3] = {xo.x, xo.y, xo.z};
       double x_trans[3] = {(double)xt.x - cell->mean[0], (double)xt.y - cell->mean[1], (double)xt.z - cell->mean[2]};
       point_derivs_f(x, p, J, Hp, compute_hessian);
+      if (n.variant == VAR_GROUND) {
+        // computeDerivatives_seg (ndt_ground_impl.hpp:363-572) calls updateDerivatives TWICE per cell (:519,522): the first call's
+        // score is dropped, but both calls add into the point's gradient and Hessian
+        angle2xy = leaf_angle2xy(*cell);
+        (void)update_derivs(n, g_pt, H_pt, J, Hp, x_trans, cell->icov, compute_hessian);
+      }
       score_pt += update_derivs(n, g_pt, H_pt, J, Hp, x_trans, cell->icov, compute_hessian);
       if (n.variant == VAR_PCA) {
         double w = (double)leaf_weight(n, *cell);
@@ -406,6 +427,8 @@ double compute_derivatives(NDT& n, double g_out[6], double H_out[6][6], const st
         for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) H_pt[i][j] *= w;
       }
     }
+    // flag_class == 1 (the only class align() runs, :130-133): the point counts only when its last neighbour is near-horizontal (:533-538)
+    if (n.variant == VAR_GROUND && !(angle2xy < 10)) continue;
     scores[tn] += score_pt;
     for (int i = 0; i < 6; i++) gs[tn][i] += g_pt[i];
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Hs[tn][i * 6 + j] += H_pt[i][j];
@@ -416,6 +439,10 @@ double compute_derivatives(NDT& n, double g_out[6], double H_out[6][6], const st
     score += scores[t];
     for (int i = 0; i < 6; i++) g_out[i] += gs[t][i];
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) H_out[i][j] += Hs[t][i * 6 + j];
+  }
+  if (n.variant == VAR_GROUND) {                     // :554-561 - only z, roll, pitch are solved for
+    const int off[3] = {0, 1, 5};
+    for (int k : off) { g_out[k] = 0; for (int j = 0; j < 6; j++) { H_out[k][j] = 0; H_out[j][k] = 0; } }
   }
   return score;
 }
@@ -607,7 +634,8 @@ void align(NDT& n, const float guess[16], std::vector<Pt>& output) {
     std::memcpy(p, pn, sizeof p);
     tr.step = step; tr.score = score; std::memcpy(tr.p_after, p, sizeof p);
     n.trace.push_back(tr);
-    if (n.nr_iterations > n.max_iter || (n.nr_iterations && (std::fabs(step) < n.trans_eps))) n.converged = true;
+    // pclomp_ground tests the step length in the first iteration as well (ndt_ground_impl.hpp:173)
+    if (n.nr_iterations > n.max_iter || ((n.nr_iterations || n.variant == VAR_GROUND) && (std::fabs(step) < n.trans_eps))) n.converged = true;
     n.nr_iterations++;
   }
   n.trans_probability = score / N;
@@ -688,6 +716,14 @@ void ondt_get_leaves(void* h, int32_t* keys, int32_t* nr_points, int32_t* raw_po
     if (in_cloud) in_cloud[k] = l.in_centroid_cloud;
     k++;
   }
+}
+
+// pclomp_ground: per occupied cell (ascending key order) the angle of its normal to the z axis in degrees, -1 where the leaf
+// has no eigen-decomposition (fewer than min_points_per_voxel points).
+void ondt_get_leaf_angles(void* h, double* angle2xy) {
+  NDT& n = *(NDT*)h;
+  size_t k = 0;
+  for (auto& kv : n.leaves) { angle2xy[k++] = kv.second.in_centroid_cloud ? leaf_angle2xy(kv.second) : -1.0; }
 }
 
 // Voxel key the lookup path computes for each (already transformed) point, or -1 when outside the box.

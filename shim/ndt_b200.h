@@ -1,6 +1,8 @@
 // Reference-side binding for the NDT path: a pcl::Registration subclass with the class name, namespace and setters of
-// pclomp::NormalDistributionsTransform (/root/reference/include/ndt_omp/ndt_omp.h:69-551) — and, under LVS_SHIM_PCA, of
-// pclpca::NormalDistributionsTransform (include/ndt_pca/ndt_pca.h) — whose computeTransformation forwards to liblvslam_b200.
+// pclomp::NormalDistributionsTransform (/root/reference/include/ndt_omp/ndt_omp.h:69-551) — under LVS_SHIM_PCA, of
+// pclpca::NormalDistributionsTransform (include/ndt_pca/ndt_pca.h); under LVS_SHIM_GROUND, of
+// pclomp_ground::NormalDistributionsTransformGround (include/ndt_omp/ndt_ground.h:69, the object scan_matching_odom_nodelet.cpp:121-126,329
+// configures as ground_s2k) — whose computeTransformation forwards to liblvslam_b200.
 // Header-only; needs PCL 1.8 + Eigen, which are NOT in the build image of this repository, so it is compiled only on the
 // lv_slam side.  It replaces src/ndt_omp/ndt_omp.cpp / src/ndt_pca/ndt_pca.cpp in lv_slam's CMake targets.
 #pragma once
@@ -12,10 +14,18 @@
 #include <vector>
 #include "lvslam_b200.h"
 
-#ifdef LVS_SHIM_PCA
+#if defined(LVS_SHIM_PCA)
 namespace pclpca {
+#define LVS_SHIM_CLASS NormalDistributionsTransform
+#define LVS_SHIM_VARIANT LVS_NDT_PCA
+#elif defined(LVS_SHIM_GROUND)
+namespace pclomp_ground {
+#define LVS_SHIM_CLASS NormalDistributionsTransformGround
+#define LVS_SHIM_VARIANT LVS_NDT_GROUND
 #else
 namespace pclomp {
+#define LVS_SHIM_CLASS NormalDistributionsTransform
+#define LVS_SHIM_VARIANT LVS_NDT_OMP
 #endif
 
 enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };   // ndt_omp.h:61
@@ -34,7 +44,7 @@ struct TargetCells {
 #endif
 
 template <typename PointSource, typename PointTarget>
-class NormalDistributionsTransform : public pcl::Registration<PointSource, PointTarget> {
+class LVS_SHIM_CLASS : public pcl::Registration<PointSource, PointTarget> {
   typedef pcl::Registration<PointSource, PointTarget> Base;
   typedef typename Base::PointCloudSource PointCloudSource;
   typedef typename Base::PointCloudTarget PointCloudTarget;
@@ -42,19 +52,17 @@ class NormalDistributionsTransform : public pcl::Registration<PointSource, Point
   typedef typename PointCloudSource::ConstPtr PointCloudSourceConstPtr;
 
  public:
-  typedef boost::shared_ptr<NormalDistributionsTransform<PointSource, PointTarget> > Ptr;
+  typedef boost::shared_ptr<LVS_SHIM_CLASS<PointSource, PointTarget> > Ptr;
 
-  NormalDistributionsTransform() {
+  LVS_SHIM_CLASS() {
     this->reg_name_ = "NormalDistributionsTransform";
     lvs_ndt_default_params(&prm_);
-#ifdef LVS_SHIM_PCA
-    prm_.variant = LVS_NDT_PCA;
-#endif
+    prm_.variant = LVS_SHIM_VARIANT;
     this->transformation_epsilon_ = prm_.transformation_epsilon;
     this->max_iterations_ = prm_.max_iterations;
     check(lvs_ndt_create(&prm_, 0, nullptr, &h_));
   }
-  virtual ~NormalDistributionsTransform() { lvs_ndt_destroy(h_); }
+  virtual ~LVS_SHIM_CLASS() { lvs_ndt_destroy(h_); }
 
   void setNumThreads(int) {}   // OpenMP team size of the CPU implementation
   inline void setInputTarget(const PointCloudTargetConstPtr& cloud) {
@@ -138,8 +146,10 @@ class NormalDistributionsTransform : public pcl::Registration<PointSource, Point
 //   double score = lvs_fitness_score(registration, fitness_score_max_range);
 template <typename PointT>
 inline double lvs_fitness_score(const typename pcl::Registration<PointT, PointT>::Ptr& reg, double max_range) {
-  if (auto* n = dynamic_cast<NormalDistributionsTransform<PointT, PointT>*>(reg.get())) return n->getFitnessScore(max_range);
+  if (auto* n = dynamic_cast<LVS_SHIM_CLASS<PointT, PointT>*>(reg.get())) return n->getFitnessScore(max_range);
   return reg->getFitnessScore(max_range);     // any other registration (GICP, ICP) keeps PCL's kd-tree path
 }
 
 }  // namespace
+#undef LVS_SHIM_CLASS
+#undef LVS_SHIM_VARIANT

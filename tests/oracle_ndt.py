@@ -14,7 +14,7 @@ _ODIR = os.path.join(_ROOT, "oracle")
 _SO = os.path.join(_ODIR, "libndt_oracle.so")
 
 KDTREE, DIRECT26, DIRECT7, DIRECT1 = 0, 1, 2, 3
-VAR_OMP, VAR_PCA = 0, 1
+VAR_OMP, VAR_PCA, VAR_GROUND = 0, 1, 2
 
 _lib = None
 
@@ -40,6 +40,7 @@ def lib():
         L.ondt_get_gauss.restype = None; L.ondt_get_gauss.argtypes = [vp, vp]
         L.ondt_num_leaves.restype = i32; L.ondt_num_leaves.argtypes = [vp]
         L.ondt_get_leaves.restype = None; L.ondt_get_leaves.argtypes = [vp] * 12
+        L.ondt_get_leaf_angles.restype = None; L.ondt_get_leaf_angles.argtypes = [vp, vp]
         L.ondt_lookup_keys.restype = None; L.ondt_lookup_keys.argtypes = [vp, vp, sz, sz, vp]
         L.ondt_transform.restype = None; L.ondt_transform.argtypes = [vp, sz, sz, vp, vp]
         L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -129,6 +130,12 @@ class OracleNDT:
                    in_cloud=np.zeros(n, np.int32))
         order = ["keys", "nr_points", "raw_points", "mean", "cov", "icov", "evals", "centroid", "weight", "label", "in_cloud"]
         self.L.ondt_get_leaves(self.h, *[out[k].ctypes.data for k in order])
+        return out
+
+    def leaf_angles(self):
+        """pclomp_ground: angle of every occupied cell's normal to the z axis [deg], -1 without an eigen-decomposition."""
+        out = np.zeros(self.L.ondt_num_leaves(self.h))
+        self.L.ondt_get_leaf_angles(self.h, out.ctypes.data)
         return out
 
     def lookup_keys(self, xyz):

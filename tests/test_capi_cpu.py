@@ -422,7 +422,7 @@ def test_save_pose_distributes_the_correction_as_the_reference_writes_it(tmp_pat
 def test_shims_compile_and_link_against_the_abi(tmp_path):
     """The reference-side bindings of shim/  need PCL, Eigen, g2o and boost, none of which is in this image.
     They are compiled here against interface stubs (tests/shim_stubs: the names and signatures the shims touch, nothing more), with
-    the registration classes instantiated for the reference's three point types in both namespaces, and linked against
+    the registration classes instantiated for the reference's three point types in the three namespaces, and linked against
     liblvslam_b200.so with --no-undefined: every ABI call in the shims type-checks against include/lvslam_b200.h and resolves."""
     import shutil
     import subprocess
@@ -433,7 +433,8 @@ def test_shims_compile_and_link_against_the_abi(tmp_path):
     stubs = os.path.join(ROOT, "tests", "shim_stubs")
     inc = ["-I" + stubs, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shim")]
     units = [("graph_slam", [os.path.join(ROOT, "shim", "graph_slam_b200.cpp")]), ("aux", [os.path.join(ROOT, "shim", "aux_b200.cpp")]),
-             ("ndt_omp", [os.path.join(stubs, "instantiate.cpp")]), ("ndt_pca", ["-DLVS_SHIM_PCA", "-Dshim_probe=shim_probe_pca", os.path.join(stubs, "instantiate.cpp")])]
+             ("ndt_omp", [os.path.join(stubs, "instantiate.cpp")]), ("ndt_pca", ["-DLVS_SHIM_PCA", "-Dshim_probe=shim_probe_pca", os.path.join(stubs, "instantiate.cpp")]),
+             ("ndt_ground", ["-DLVS_SHIM_GROUND", "-Dshim_probe=shim_probe_ground", os.path.join(stubs, "instantiate.cpp")])]
     objs = []
     for name, args in units:
         o = str(tmp_path / (name + ".o"))
@@ -451,9 +452,9 @@ def test_shims_compile_and_link_against_the_abi(tmp_path):
     assert used and all(sym + "(" in header for sym in used), used
     # both namespaces carry the three instantiations
     defined = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True).stdout
-    for ns in ("pclomp", "pclpca"):
+    for ns in ("pclomp::NormalDistributionsTransform", "pclpca::NormalDistributionsTransform", "pclomp_ground::NormalDistributionsTransformGround"):
         for pt in ("PointXYZ,", "PointXYZI,", "PointXYZRGBL,"):
-            assert any(ns + "::NormalDistributionsTransform<pcl::" + pt in ln and "computeTransformation" in ln for ln in defined.splitlines()), (ns, pt)
+            assert any(ns + "<pcl::" + pt in ln and "computeTransformation" in ln for ln in defined.splitlines()), (ns, pt)
 
 
 def test_header_is_plain_c_and_a_c_caller_links(tmp_path):

@@ -286,3 +286,96 @@ def test_expf_restatement_matches_the_host_libm():
     ref = np.exp(x[fin].astype(np.float64))
     ok = ref > 1e-37
     assert np.abs(out[fin][ok] / ref[ok] - 1).max() < 1.2e-7       # <= 1 ulp of float
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pclomp_ground::NormalDistributionsTransformGround (include/ndt_omp/ndt_ground_impl.hpp): horizontal-voxel NDT for z / roll / pitch
+
+_OFF7 = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]])
+
+
+def _last_neighbour_angle(o, pts, search):
+    """numpy restatement of "the LAST cell of the point's neighbourhood decides": per point the angle2xy of the last usable leaf the
+    direct search would push (probe order of getNeighborhoodAtPoint7 / 1), 0 for an empty neighbourhood (ndt_ground_impl.hpp:484)."""
+    lv, ang = o.leaves(), o.leaf_angles()
+    mn, mx, dv = o.grid()
+    usable = {int(k): a for k, a, n in zip(lv["keys"], ang, lv["nr_points"]) if n >= 6}
+    cell = np.floor(pts[:, :3].astype(np.float32) / np.float32(o.params["resolution"])).astype(np.int64)
+    out = np.zeros(len(pts))
+    for i, c in enumerate(cell):
+        for off in (_OFF7 if search == O.DIRECT7 else _OFF7[:1]):
+            q = c + off
+            if (q < mn).any() or (q > mx).any():
+                continue
+            key = int((q[0] - mn[0]) + (q[1] - mn[1]) * dv[0] + (q[2] - mn[2]) * dv[0] * dv[1])
+            if key in usable:
+                out[i] = usable[key]
+    return out
+
+
+def test_ground_leaf_normals_against_numpy(small_pair):
+    tgt = small_pair[0]
+    o = O.OracleNDT(variant=O.VAR_GROUND, search=O.DIRECT1, num_threads=1)
+    o.set_target(tgt)
+    lv, ang = o.leaves(), o.leaf_angles()
+    has = lv["in_cloud"] == 1
+    assert (ang[~has] == -1).all() and has.sum() > 100
+    checked = 0
+    for k in np.nonzero(has & (lv["nr_points"] >= 6))[0]:
+        w, v = np.linalg.eigh(lv["cov"][k])
+        if w[1] - w[0] < 1e-6 * w[2]:
+            continue                                        # the normal of a (near-)degenerate pair is not defined
+        ref = np.degrees(np.arccos(min(1.0, abs(v[2, 0]))))
+        assert abs(ref - ang[k]) < 1e-4, (k, ref, ang[k])   # 180/3.1415926 vs 180/pi: 2e-8 relative
+        checked += 1
+    assert checked > 100
+    assert 0.05 < np.mean(ang[has] < 10) < 0.95             # the scene has both ground and wall leaves
+
+
+@pytest.mark.parametrize("search", [O.DIRECT1, O.DIRECT7])
+def test_ground_derivatives_are_the_gated_doubled_masked_omp_sums(small_pair, search):
+    """computeDerivatives_seg with flag_class = 1 (ndt_ground_impl.hpp:363-572) against its definition in terms of the pclomp pass:
+    points whose last neighbour is within 10 degrees of horizontal, score once, gradient and Hessian twice (updateDerivatives is called
+    twice per cell, :519,522), rows / columns x, y, yaw zeroed (:554-561)."""
+    tgt, src, guess, truth = small_pair
+    og = O.OracleNDT(variant=O.VAR_GROUND, search=search, num_threads=1)
+    oo = O.OracleNDT(variant=O.VAR_OMP, search=search, num_threads=1)
+    og.set_target(tgt); oo.set_target(tgt)
+    p = O.se3_log_from_matrix4f(guess)
+    trans = O.transform(src, guess)
+    keep = _last_neighbour_angle(og, trans, search) < 10
+    assert 100 < keep.sum() < len(src) - 100
+    og.set_source(src); oo.set_source(src[keep])
+    sg, gg, Hg = og.eval_derivatives(p, guess)
+    so, go, Ho = oo.eval_derivatives(p, guess)
+    m = np.array([0, 0, 1, 1, 1, 0.0])
+    np.testing.assert_allclose(sg, so, rtol=1e-13)
+    np.testing.assert_allclose(gg, 2 * go * m, rtol=1e-12, atol=1e-12 * np.abs(go).max())
+    np.testing.assert_allclose(Hg, 2 * Ho * np.outer(m, m), rtol=1e-12, atol=1e-12 * np.abs(Ho).max())
+    assert (gg[[0, 1, 5]] == 0).all() and (Hg[[0, 1, 5], :] == 0).all() and (Hg[:, [0, 1, 5]] == 0).all()
+    # the score-only pass (line search trials) gates the same points
+    s2, g2, H2 = og.eval_derivatives(p, guess, False)
+    assert s2 == sg and np.array_equal(g2, gg) and (H2 == 0).all()
+
+
+def test_ground_align_solves_z_roll_pitch_only(small_pair):
+    tgt = small_pair[0]
+    for res, mot, tol_z, tol_r in ((2.0, [0, 0, 0.05, 0, 0, 0.0], 2e-3, 2e-4), (4.0, [0, 0, 0.12, 0.006, -0.004, 0.0], 0.01, 1e-3)):
+        motion = O.se3_exp_matrix4f(np.array(mot))
+        src = O.transform(tgt[::2], np.linalg.inv(motion.astype(np.float64)).astype(np.float32))
+        o = O.OracleNDT(variant=O.VAR_GROUND, resolution=res, trans_eps=0.001, max_iter=64, search=O.DIRECT1, num_threads=os.cpu_count() or 1)
+        o.set_target(tgt); o.set_source(src)
+        r = o.align(np.eye(4, dtype=np.float32))
+        assert r["converged"] and r["iterations"] < 64 and r["n_hess"] == 0 and r["n_eval"] == r["iterations"] + 1
+        tr = r["trace"]
+        assert (tr[:, 6 + 0] == 0).all() and (tr[:, 6 + 1] == 0).all() and (tr[:, 6 + 5] == 0).all()      # unit direction: no x, y, yaw component
+        pf = O.se3_log_from_matrix4f(r["final"])
+        assert abs(pf[2] - mot[2]) < tol_z and abs(pf[3] - mot[3]) < tol_r and abs(pf[4] - mot[4]) < tol_r, pf
+    # the step test has no "not in the first iteration" clause (ndt_ground_impl.hpp:173): a start at the optimum ends after ONE iteration
+    o2 = O.OracleNDT(variant=O.VAR_GROUND, resolution=2.0, trans_eps=0.05, max_iter=64, search=O.DIRECT1, num_threads=1)
+    o2.set_target(tgt); o2.set_source(tgt[::2])
+    r2 = o2.align(np.eye(4, dtype=np.float32))
+    assert r2["converged"] and r2["iterations"] == 1
+    o3 = O.OracleNDT(variant=O.VAR_OMP, resolution=2.0, trans_eps=0.05, max_iter=64, search=O.DIRECT1, num_threads=1)
+    o3.set_target(tgt); o3.set_source(tgt[::2])
+    assert o3.align(np.eye(4, dtype=np.float32))["iterations"] == 2
