@@ -5,7 +5,16 @@
 // configures as ground_s2k) — whose computeTransformation forwards to liblvslam_b200.
 // Header-only; needs PCL 1.8 + Eigen, which are NOT in the build image of this repository, so it is compiled only on the
 // lv_slam side.  It replaces src/ndt_omp/ndt_omp.cpp / src/ndt_pca/ndt_pca.cpp in lv_slam's CMake targets.
-#pragma once
+//
+// The header may be included several times in one translation unit, once per class (scan_matching_odom_nodelet.cpp:24-26 includes
+// ndt_omp.h, ndt_pca.h and ndt_ground.h together):
+//     #include <ndt_b200.h>                                        // pclomp::NormalDistributionsTransform
+//     #define LVS_SHIM_PCA
+//     #include <ndt_b200.h>                                        // pclpca::NormalDistributionsTransform
+//     #undef LVS_SHIM_PCA
+//     #define LVS_SHIM_GROUND
+//     #include <ndt_b200.h>                                        // pclomp_ground::NormalDistributionsTransformGround
+//     #undef LVS_SHIM_GROUND
 #include <pcl/point_types.h>
 #include <pcl/registration/registration.h>
 #include <limits>
@@ -15,18 +24,30 @@
 #include "lvslam_b200.h"
 
 #if defined(LVS_SHIM_PCA)
-namespace pclpca {
+#ifndef LVS_NDT_B200_PCA_DEFINED
+#define LVS_NDT_B200_PCA_DEFINED
+#define LVS_SHIM_NS pclpca
 #define LVS_SHIM_CLASS NormalDistributionsTransform
 #define LVS_SHIM_VARIANT LVS_NDT_PCA
+#endif
 #elif defined(LVS_SHIM_GROUND)
-namespace pclomp_ground {
+#ifndef LVS_NDT_B200_GROUND_DEFINED
+#define LVS_NDT_B200_GROUND_DEFINED
+#define LVS_SHIM_NS pclomp_ground
 #define LVS_SHIM_CLASS NormalDistributionsTransformGround
 #define LVS_SHIM_VARIANT LVS_NDT_GROUND
+#endif
 #else
-namespace pclomp {
+#ifndef LVS_NDT_B200_OMP_DEFINED
+#define LVS_NDT_B200_OMP_DEFINED
+#define LVS_SHIM_NS pclomp
 #define LVS_SHIM_CLASS NormalDistributionsTransform
 #define LVS_SHIM_VARIANT LVS_NDT_OMP
 #endif
+#endif
+
+#ifdef LVS_SHIM_NS
+namespace LVS_SHIM_NS {
 
 enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };   // ndt_omp.h:61
 
@@ -151,5 +172,7 @@ inline double lvs_fitness_score(const typename pcl::Registration<PointT, PointT>
 }
 
 }  // namespace
+#undef LVS_SHIM_NS
 #undef LVS_SHIM_CLASS
 #undef LVS_SHIM_VARIANT
+#endif  // LVS_SHIM_NS

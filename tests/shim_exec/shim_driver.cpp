@@ -1,8 +1,8 @@
 // Executes the reference-side bindings of shim/ on the GPU (tests/test_shim_exec_gpu.py): the calls a lv_slam nodelet makes -
 // setInputTarget / setInputSource / align / getFinalTransformation / hasConverged / getFitnessScore on the registration classes
 // (scan_matching_odom_nodelet.cpp:109-126,197,220-226; loop_detector.hpp:155-184,219-262) and GraphSLAM::optimize on a g2o graph
-// (global_graph_nodelet.cpp:670-764) - against the interface stand-ins of tests/shim_stubs.  Compiled twice: as is (pclomp) and with
-// -DLVS_SHIM_PCA (pclpca).  Input: raw little-endian arrays written by the test; output: one "key v v v ..." line per result.
+// (global_graph_nodelet.cpp:670-764) - against the interface stand-ins of tests/shim_stubs.  Compiled three times: as is (pclomp), with
+// -DLVS_SHIM_PCA (pclpca) and with -DLVS_SHIM_GROUND (pclomp_ground, registration only).  Input: raw little-endian arrays written by the test; output: one "key v v v ..." line per result.
 #include <ndt_b200.h>
 #include <global_graph/graph_slam.hpp>
 #include <global_graph/information_matrix_calculator.hpp>
@@ -17,10 +17,15 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
-#ifdef LVS_SHIM_PCA
+#if defined(LVS_SHIM_PCA)
 namespace ns = pclpca;
+#define NDT_CLASS NormalDistributionsTransform
+#elif defined(LVS_SHIM_GROUND)
+namespace ns = pclomp_ground;
+#define NDT_CLASS NormalDistributionsTransformGround
 #else
 namespace ns = pclomp;
+#define NDT_CLASS NormalDistributionsTransform
 #endif
 pcl::PointCloud<pcl::PointXYZI>::Ptr lvs_prefilter(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr&, bool, double, double, float);   // shim/aux_b200.cpp
 
@@ -43,7 +48,7 @@ static pcl::PointCloud<pcl::PointXYZI>::Ptr cloud_from(const std::vector<float>&
   return c;
 }
 
-#ifndef LVS_SHIM_PCA
+#if !defined(LVS_SHIM_PCA) && !defined(LVS_SHIM_GROUND)
 static Eigen::Isometry3d iso_from7(const double* v) {
   Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
   T.linear() = Eigen::Quaterniond(v[6], v[3], v[4], v[5]).toRotationMatrix();
@@ -60,17 +65,25 @@ int main(int argc, char** argv) {
   const std::vector<float> g = slurp<float>(dir + "/guess.f32");
   Eigen::Matrix4f guess;
   for (int i = 0; i < 16; i++) guess.data()[i] = g[i];                       // column-major
-  boost::shared_ptr<ns::NormalDistributionsTransform<pcl::PointXYZI, pcl::PointXYZI> > ndt(new ns::NormalDistributionsTransform<pcl::PointXYZI, pcl::PointXYZI>());
+  boost::shared_ptr<ns::NDT_CLASS<pcl::PointXYZI, pcl::PointXYZI> > ndt(new ns::NDT_CLASS<pcl::PointXYZI, pcl::PointXYZI>());
+#ifdef LVS_SHIM_GROUND
+  ndt->setResolution(10.0f);                                                   // ground_s2k, scan_matching_odom_nodelet.cpp:121-126
+#else
   ndt->setResolution(1.0f);
+#endif
   ndt->setNumThreads(4);
-#ifdef LVS_SHIM_PCA
+#if defined(LVS_SHIM_PCA) || defined(LVS_SHIM_GROUND)
   ndt->setNeighborhoodSearchMethod(ns::DIRECT1);                               // scan_matching_odom_nodelet.cpp:109-119
 #else
   ndt->setNeighborhoodSearchMethod(ns::DIRECT7);
 #endif
   pcl::Registration<pcl::PointXYZI, pcl::PointXYZI>::Ptr reg = ndt;
   reg->setTransformationEpsilon(0.01);
+#ifdef LVS_SHIM_GROUND
+  reg->setMaximumIterations(64);
+#else
   reg->setMaximumIterations(30);
+#endif
   reg->setInputTarget(tgt);
   reg->setInputSource(src);
   pcl::PointCloud<pcl::PointXYZI> aligned;
@@ -93,6 +106,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < cells.keys.size(); i++) { wsum += cells.weight[i]; usable += cells.nr_points[i] >= 6; }
     std::printf("cells %zu usable %d weight_sum %lld\n", cells.keys.size(), usable, wsum);
   }
+#elif defined(LVS_SHIM_GROUND)
 #else
   // ---------------- the stages either side: InformationMatrixCalculator::calc_fitness_score and the prefilter (shim/aux_b200.cpp)
   {

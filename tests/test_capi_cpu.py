@@ -434,7 +434,8 @@ def test_shims_compile_and_link_against_the_abi(tmp_path):
     inc = ["-I" + stubs, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shim")]
     units = [("graph_slam", [os.path.join(ROOT, "shim", "graph_slam_b200.cpp")]), ("aux", [os.path.join(ROOT, "shim", "aux_b200.cpp")]),
              ("ndt_omp", [os.path.join(stubs, "instantiate.cpp")]), ("ndt_pca", ["-DLVS_SHIM_PCA", "-Dshim_probe=shim_probe_pca", os.path.join(stubs, "instantiate.cpp")]),
-             ("ndt_ground", ["-DLVS_SHIM_GROUND", "-Dshim_probe=shim_probe_ground", os.path.join(stubs, "instantiate.cpp")])]
+             ("ndt_ground", ["-DLVS_SHIM_GROUND", "-Dshim_probe=shim_probe_ground", os.path.join(stubs, "instantiate.cpp")]),
+             ("nodelet_like", [os.path.join(stubs, "nodelet_like.cpp")])]       # the three classes in ONE translation unit
     objs = []
     for name, args in units:
         o = str(tmp_path / (name + ".o"))

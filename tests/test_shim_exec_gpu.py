@@ -25,7 +25,7 @@ def _rot_angle(Ra, Rb):
 def _build(tmp, variant):
     stubs = os.path.join(ROOT, "tests", "shim_stubs")
     exe = str(tmp / ("shim_driver_" + variant))
-    cmd = ["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-O1"] + (["-DLVS_SHIM_PCA"] if variant == "pca" else []) + [
+    cmd = ["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-O1"] + ({"pca": ["-DLVS_SHIM_PCA"], "ground": ["-DLVS_SHIM_GROUND"]}.get(variant, [])) + [
         "-I" + stubs, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shim"),
         os.path.join(ROOT, "tests", "shim_exec", "shim_driver.cpp"), os.path.join(ROOT, "shim", "graph_slam_b200.cpp"), os.path.join(ROOT, "shim", "aux_b200.cpp"),
         "-o", exe, "-L" + os.path.join(ROOT, "lv_slam_b200"), "-llvslam_b200", "-Wl,-rpath," + os.path.join(ROOT, "lv_slam_b200")]
@@ -51,7 +51,7 @@ def _run(exe, d):
     return out
 
 
-@pytest.mark.parametrize("variant", ["omp", "pca"])
+@pytest.mark.parametrize("variant", ["omp", "pca", "ground"])
 def test_shims_run_on_the_gpu_and_match_the_oracle(tmp_path, small_pair, variant):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
@@ -70,8 +70,11 @@ def test_shims_run_on_the_gpu_and_match_the_oracle(tmp_path, small_pair, variant
     out = _run(_build(tmp_path, variant), tmp_path)
 
     # ---- registration vs the CPU restatement with the same settings
-    o = O.OracleNDT(variant=O.VAR_PCA if variant == "pca" else O.VAR_OMP, trans_eps=0.01, max_iter=30,
-                    search=O.DIRECT1 if variant == "pca" else O.DIRECT7, num_threads=8)
+    if variant == "ground":     # ground_s2k as scan_matching_odom_nodelet.cpp:121-126 configures it
+        o = O.OracleNDT(variant=O.VAR_GROUND, resolution=10.0, trans_eps=0.01, max_iter=64, search=O.DIRECT1, num_threads=8)
+    else:
+        o = O.OracleNDT(variant=O.VAR_PCA if variant == "pca" else O.VAR_OMP, trans_eps=0.01, max_iter=30,
+                        search=O.DIRECT1 if variant == "pca" else O.DIRECT7, num_threads=8)
     o.set_target(tgt); o.set_source(src)
     r = o.align(guess, want_cloud=True)
     F = np.array([float(x) for x in out["final"]], dtype=np.float32).reshape(4, 4).T
@@ -87,6 +90,8 @@ def test_shims_run_on_the_gpu_and_match_the_oracle(tmp_path, small_pair, variant
     np.testing.assert_allclose([float(x) for x in out["aligned_last"]], r["cloud"][-1], atol=2e-4)
     assert int(out["second_iterations"][0]) == o.align(r["final"])["iterations"]
 
+    if variant == "ground":
+        return
     if variant == "pca":
         lv = o.leaves()
         c = out["cells"]              # "cells <n> usable <u> weight_sum <w>"
