@@ -14,6 +14,7 @@ Top level = the library's default arithmetic (LVS_ACC_EXACT: the reference's flo
   configs.pca_direct1   pclpca / DIRECT1, what the odometry nodelet runs (scan_matching_odom_nodelet.cpp:109-119), both modes
   configs.pair_latency  BASELINE configs[0]: one hard pair from the first-frame guess (66 iterations), single-object API
   configs.beam128       BASELINE configs[2]: 128-beam scans (~240 k points), 0.5 m voxels; point-sharded across ranks when N > 1
+  configs.ground_s2k    pclomp_ground with the odometry nodelet's ground_s2k settings (parity record; the reference never aligns it)
   configs.pgo           BASELINE configs[3]: 5 000-vertex / 19 599-edge sphere, LM and GN with the direct solver, LM with PCG
   configs.replay        BASELINE configs[4] in small: every rank replays a chunk of the drive through prefilter + odometry (frames/s)
   configs.pgo_50k       BASELINE configs[4] graph: 50 000 vertices / 198 999 edges, LM (one GPU)
@@ -414,6 +415,38 @@ def bench_pair_latency(L, torch):
     return out, (tgt, src, guess, finals["exact"])
 
 
+def bench_ground(L, torch, with_cpu):
+    """pclomp_ground::NormalDistributionsTransformGround configured like ground_s2k (scan_matching_odom_nodelet.cpp:121-126: 10 m voxels,
+    DIRECT1, epsilon 0.01, 64 iterations) on the config-1 pair; the reference never calls its align(), so this is a parity record."""
+    from lv_slam_b200 import synth
+    tgt, src, guess, truth = synth.config1_pair()
+    n = L.NormalDistributionsTransformGround()
+    n.setResolution(10.0); n.setNeighborhoodSearchMethod(L.LVS_DIRECT1); n.setTransformationEpsilon(0.01); n.setMaximumIterations(64)
+    n.setInputTarget(tgt); n.setInputSource(src)
+    for _ in range(3):
+        n.align(guess)
+    torch.cuda.synchronize()
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        n.align(guess)
+    dt = (time.perf_counter() - t0) / reps
+    r = n.result()
+    out = {"workload": "pclomp_ground (LVS_NDT_GROUND), ground_s2k settings, synthetic 64-beam pair, %d / %d points" % (len(tgt), len(src)),
+           "align_ms": dt * 1e3, "iterations": r["iterations"], "evaluations": r["n_eval"], "horizontal_cells": int(n.cell_horizontal().sum())}
+    n.close()
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_ndt as O  # the checker, cpu_baseline leg only
+        o = O.OracleNDT(variant=O.VAR_GROUND, resolution=10.0, trans_eps=0.01, max_iter=64, search=O.DIRECT1, num_threads=os.cpu_count() or 1)
+        o.set_target(tgt); o.set_source(src)
+        t0 = time.perf_counter()
+        ro = o.align(guess)
+        out["cpu_baseline"] = {"kind": "port", "unit": "ms/align", "cores": os.cpu_count() or 1, "align_ms": (time.perf_counter() - t0) * 1e3, "iterations": ro["iterations"],
+                               "max_abs_final_transform_diff_vs_gpu": float(np.abs(ro["final"] - r["final"]).max())}
+    return out
+
+
 def cpu_pair_latency(tgt, src, guess, final_gpu):
     out = {}
     for th in sorted({4, 8, os.cpu_count() or 1}):
@@ -712,6 +745,10 @@ def main_ours(args):
         if not args.no_cpu_baseline:
             pl["cpu_baseline"] = cpu_pair_latency(*pair)
         line["configs"]["pair_latency"] = pl
+        try:
+            line["configs"]["ground_s2k"] = bench_ground(L, torch, not args.no_cpu_baseline)
+        except Exception as e:      # a parity side record must not take the headline down
+            line["configs"]["ground_s2k"] = {"error": repr(e)}
         line["configs"]["pgo"] = bench_pgo(L, not args.no_cpu_baseline)
         line["configs"]["pgo_50k"] = bench_pgo_50k(L)
 

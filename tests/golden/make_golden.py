@@ -26,6 +26,17 @@ json.dump(dict(n_cells=len(lv["keys"]), n_usable=int((lv["nr_points"] >= 6).sum(
                gradient=g.tolist(), hessian=H.tolist(), iterations=r["iterations"], final=r["final"].astype(float).tolist()),
           open(os.path.join(HERE, "ndt_small_pair.json"), "w"), indent=1)
 
+# pclomp_ground (ndt_ground_impl.hpp) on the same pair, configured like ground_s2k (scan_matching_odom_nodelet.cpp:121-126)
+og = O.OracleNDT(variant=O.VAR_GROUND, resolution=10.0, trans_eps=0.01, max_iter=64, search=O.DIRECT1, num_threads=1)
+og.set_target(tgt); og.set_source(src)
+ang = og.leaf_angles()
+sg, gg, Hg = og.eval_derivatives(O.se3_log_from_matrix4f(guess), guess)
+rg = og.align(guess)
+json.dump(dict(n_cells=len(ang), n_with_normal=int((ang >= 0).sum()), n_horizontal=int(((ang >= 0) & (ang < 10)).sum()),
+               horizontal_key_sum=int(og.leaves()["keys"][(ang >= 0) & (ang < 10)].astype(np.int64).sum()), score=sg, gradient=gg.tolist(),
+               hessian=Hg.tolist(), iterations=rg["iterations"], final=rg["final"].astype(float).tolist()),
+          open(os.path.join(HERE, "ndt_ground_small_pair.json"), "w"), indent=1)
+
 # the stages either side of the path on the same pair
 big = float(np.finfo(np.float64).max)
 fit = {}

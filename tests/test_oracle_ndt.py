@@ -379,3 +379,22 @@ def test_ground_align_solves_z_roll_pitch_only(small_pair):
     o3 = O.OracleNDT(variant=O.VAR_OMP, resolution=2.0, trans_eps=0.05, max_iter=64, search=O.DIRECT1, num_threads=1)
     o3.set_target(tgt); o3.set_source(tgt[::2])
     assert o3.align(np.eye(4, dtype=np.float32))["iterations"] == 2
+
+
+def test_golden_regression_of_the_ground_oracle(small_pair):
+    """tests/golden/ndt_ground_small_pair.json (tests/golden/make_golden.py): ground_s2k's configuration on the small pair."""
+    gold = json.load(open(os.path.join(HERE, "golden", "ndt_ground_small_pair.json")))
+    tgt, src, guess, truth = small_pair
+    o = O.OracleNDT(variant=O.VAR_GROUND, resolution=10.0, trans_eps=0.01, max_iter=64, search=O.DIRECT1, num_threads=1)
+    o.set_target(tgt); o.set_source(src)
+    ang = o.leaf_angles()
+    hz = (ang >= 0) & (ang < 10)
+    assert len(ang) == gold["n_cells"] and int((ang >= 0).sum()) == gold["n_with_normal"] and int(hz.sum()) == gold["n_horizontal"]
+    assert int(o.leaves()["keys"][hz].astype(np.int64).sum()) == gold["horizontal_key_sum"]
+    s, g, H = o.eval_derivatives(O.se3_log_from_matrix4f(guess), guess)
+    np.testing.assert_allclose(s, gold["score"], rtol=1e-12)
+    np.testing.assert_allclose(g, gold["gradient"], rtol=1e-10, atol=1e-9 * np.abs(g).max())
+    np.testing.assert_allclose(H, np.array(gold["hessian"]), rtol=1e-10, atol=1e-9 * np.abs(H).max())
+    r = o.align(guess)
+    assert r["iterations"] == gold["iterations"]
+    np.testing.assert_allclose(r["final"], np.array(gold["final"], dtype=np.float32), atol=1e-6)

@@ -53,6 +53,27 @@ def test_ndt_against_the_golden_pair(small_pair):
     assert np.max(np.abs(np.asarray(r["final"], dtype=np.float64)[:3, :3] - fin[:3, :3])) <= 1e-5
 
 
+def test_ground_ndt_against_the_golden_pair(small_pair):
+    import lv_slam_b200 as L
+    gold = _gold("ndt_ground_small_pair.json")
+    tgt, src, guess, truth = small_pair
+    n = L.NormalDistributionsTransformGround()          # ground_s2k, scan_matching_odom_nodelet.cpp:121-126
+    n.setResolution(10.0); n.setNeighborhoodSearchMethod(O.DIRECT1); n.setTransformationEpsilon(0.01); n.setMaximumIterations(64)
+    n.setInputTarget(tgt); n.setInputSource(src)
+    hz = n.cell_horizontal() == 1
+    assert len(hz) == gold["n_cells"] and int(hz.sum()) == gold["n_horizontal"]
+    assert int(n.cells()["keys"][hz].astype(np.int64).sum()) == gold["horizontal_key_sum"]
+    s, g, H = n.eval_derivatives(O.se3_log_from_matrix4f(guess), guess, True)
+    gg, gH = np.array(gold["gradient"]), np.array(gold["hessian"])
+    assert abs(s - gold["score"]) <= 1e-9 * abs(gold["score"])
+    assert np.max(np.abs(np.asarray(g) - gg)) <= 1e-9 * np.max(np.abs(gg)) and np.max(np.abs(np.asarray(H) - gH)) <= 1e-9 * np.max(np.abs(gH))
+    n.align(guess)
+    r = n.result()
+    fin = np.array(gold["final"])
+    assert r["iterations"] == gold["iterations"]
+    assert np.max(np.abs(r["final"][:3, 3] - fin[:3, 3])) <= 1e-4 and np.max(np.abs(np.asarray(r["final"], dtype=np.float64)[:3, :3] - fin[:3, :3])) <= 1e-5
+
+
 def test_fitness_and_prefilter_against_the_golden_pair(small_pair):
     import lv_slam_b200 as L
     gold = _gold("aux_small_pair.json")
