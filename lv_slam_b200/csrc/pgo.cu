@@ -16,9 +16,10 @@
 //   pgo_pcg_kernel        ONE cooperative launch per linear solve: block-Jacobi preconditioner, every PCG iteration with
 //                         grid-wide barriers instead of launches, the LM gain-ratio denominator in the epilogue
 //   pgo_update_kernel     X <- X * fromVectorMQT(dx) with the previous poses kept for LM's pop()
-// The linear solver restates g2o's own LinearSolverPCG (solvers/pcg/linear_solver_pcg.hpp:80-158, solver names *_pcg);
-// the *_var / *_cholmod solver names (direct Cholesky in the reference) run the same PCG to a 1e-24 relative energy
-// tolerance, i.e. to the same solution within ~1e-10 — see DESIGN.md for why no sparse factorisation is done on the device.
+// Linear solvers: the *_pcg solver names restate g2o's own LinearSolverPCG (solvers/pcg/linear_solver_pcg.hpp:80-158); the *_var /
+// *_cholmod names (direct Cholesky in the reference) run the supernodal multifrontal block Cholesky of pgo_chol.cu, analysed once per
+// set_graph on the host (on a second thread, beside the uploads) and factorised on the device at every LM trial.
+#include <future>
 #include <cooperative_groups.h>
 #include <cmath>
 #include <map>
@@ -550,6 +551,20 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
   blocks.erase(std::unique(blocks.begin(), blocks.end()), blocks.end());
   const int noff = (int)blocks.size();
   if ((long long)nfree * 42 + (long long)noff * 36 >= (1ll << 32)) return fail(LVS_ERR_INVALID_ARG, "graph too large (the assembly kernels index its entries with 32 bits)");
+  // cholmod_analyze_p / cs_schol once per structure (linear_solver_cholmod.h:271-338): ordering + symbolic factorisation.  Pure host work on
+  // the block pattern alone, so it runs on a second host thread beside the incidence lists, allocations and uploads below and is collected
+  // just before its result is uploaded (7 of set_graph's 14 ms at 5 000 vertices, 0.13 of 0.3 s at 50 000).
+  const bool want_chol = (h->solver == LVS_PGO_LM_CHOL || h->solver == LVS_PGO_GN_CHOL) && nfree > 0;
+  std::vector<int> off_ij;
+  CholSymbolic sym;
+  std::future<void> analysis;          // declared after what it reads and writes: an early return waits for the thread before those go away
+  if (want_chol) {
+    off_ij.resize((size_t)noff * 2);
+    for (int o = 0; o < noff; o++) { off_ij[2 * o] = blocks[o].second; off_ij[2 * o + 1] = blocks[o].first; }
+    const int* oij = off_ij.data();
+    CholSymbolic* sp = &sym;
+    analysis = std::async(std::launch::async, [nfree, noff, oij, sp]() { chol_analyze(nfree, noff, oij, *sp); });
+  }
   std::vector<int2> edge_ij(ne), edge_h(ne);
   std::vector<unsigned char> edge_tr(ne, 0);
   std::vector<int> edge_off(ne, -1);
@@ -641,12 +656,8 @@ int lvs_pgo_set_graph_typed(lvs_pgo_t* h, int n_vertices, const double* poses7, 
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));
-  if ((h->solver == LVS_PGO_LM_CHOL || h->solver == LVS_PGO_GN_CHOL) && nfree > 0) {
-    // cholmod_analyze_p / cs_schol once per structure (linear_solver_cholmod.h:271-338): ordering + symbolic factorisation
-    std::vector<int> off_ij((size_t)noff * 2);
-    for (int o = 0; o < noff; o++) { off_ij[2 * o] = blocks[o].second; off_ij[2 * o + 1] = blocks[o].first; }
-    CholSymbolic sym;
-    chol_analyze(nfree, noff, off_ij.data(), sym);
+  if (want_chol) {
+    analysis.get();
     if ((rc = chol_upload(sym, noff, h->chol, h->st))) { free_graph(h); return rc; }
     h->use_chol = true;
     h->chol_nnz_l = sym.nnz_l_blocks; h->chol_flops = sym.flops; h->chol_fronts = (int)sym.fronts.size();

@@ -56,8 +56,8 @@ static void minimum_degree(int n, const std::vector<std::vector<int>>& adj, std:
   std::vector<std::vector<int>>& el = pattern;      // an element's member list IS the pivot's column pattern (kept; `dead` marks absorption)
   std::vector<char> gone(n, 0), dead(n, 0);
   std::vector<int> mark(n, -1), deg(n), w(n, 0), wmark(n, -1);
-  // One min-heap of variable indices per degree, with lazy deletion: an entry of bucket d is live while the variable is still
-  // there and its degree is still d.  The pivot is the smallest index of the lowest non-empty degree.
+  // The pivot is the smallest index of the lowest non-empty degree.  Above kBitmapMaxN variables: one min-heap of variable indices per
+  // degree with lazy deletion (an entry of bucket d is live while the variable is still there and its degree is still d).
   const bool use_bitmaps = n <= kBitmapMaxN;
   DegreeBitmaps bm;
   if (use_bitmaps) bm.init(n);
