@@ -9,7 +9,9 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 ZIP=/root/reference/3rdtools/g2o-a48ff8c.zip
 OUT="$HERE/_ref"
 [ -f "$ZIP" ] || { echo "build_ref.sh: $ZIP not found, skipping"; exit 0; }
-if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ]; then exit 0; fi
+SZIP=/root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip
+if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] && [ -f "$OUT/libsophus_ref.so" ] && [ "$OUT/libsophus_ref.so" -nt "$SZIP" ] &&
+   [ "$OUT/libsophus_ref.so" -nt "$HERE/sophus_ref_api.cpp" ] && [ "$OUT/libsophus_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -23,3 +25,18 @@ mkdir -p "$TMP/stub/g2o" "$OUT"
 : > "$TMP/stub/g2o/config.h"      # cs_api.h includes g2o/config.h, which CMake would generate; nothing in it is needed
 /usr/bin/gcc -O2 -fPIC -shared -I"$TMP/stub" -I"$TMP/g2o/EXTERNAL/csparse" -o "$OUT/libcsparse_ref.so" "$TMP"/g2o/EXTERNAL/csparse/*.c -lm
 echo "built $OUT/libcsparse_ref.so"
+
+# The NDT path's Lie-group code: Sophus a621ff2 (so3.cpp, se3.cpp), vendored by the reference as a zip.  It needs Eigen, which this image
+# does not have: the two files are compiled as they are against oracle/ref_stubs/eigen_min.h, a stand-in for the handful of Eigen
+# operations they use (see its header for what that does and does not pin), together with the C entry points of sophus_ref_api.cpp.
+if [ -f "$SZIP" ]; then
+  python3 - "$SZIP" "$TMP" <<'PY'
+import sys, zipfile
+z = zipfile.ZipFile(sys.argv[1])
+for n in ("Sophus/sophus/so3.h", "Sophus/sophus/so3.cpp", "Sophus/sophus/se3.h", "Sophus/sophus/se3.cpp"):
+    z.extract(n, sys.argv[2])
+PY
+  /usr/bin/g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I"$TMP/Sophus/sophus" -o "$OUT/libsophus_ref.so" \
+      "$TMP/Sophus/sophus/so3.cpp" "$TMP/Sophus/sophus/se3.cpp" "$HERE/sophus_ref_api.cpp"
+  echo "built $OUT/libsophus_ref.so"
+fi

@@ -5,7 +5,8 @@
 // PARITY UNPINNED: the reference (BurryChen/lv_slam) ships no test, fixture or golden vector for the
 // NDT path, and neither it nor PCL/Eigen/Sophus can be built in this image, so this
 // restatement is pinned only by its own traceability and by closed-form / finite-difference checks
-// in tests/.
+// in tests/ - with one exception: the Lie-group piece (Sophus SE3 exp / log / product, ose3.h) is held bit for bit to the
+// reference's own Sophus sources, compiled from the vendored zip against an Eigen stand-in (oracle/build_ref.sh, oracle/ref_stubs/).
 //
 // CPU restatement of lv_slam's NDT scan matching, the variant that is actually compiled
 // (src/ndt_omp/ndt_omp.cpp:2 and src/ndt_pca/ndt_pca.cpp:2 include the *_impl2.hpp Lie-algebra files):

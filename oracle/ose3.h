@@ -1,7 +1,11 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see olin.h header).
 //
 // se(3) <-> SE(3) as the reference gets it from Sophus a621ff2 (vendored only as
-// /root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip; needs Eigen, so it cannot be built here).
+// /root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip; it needs Eigen, which this image lacks).
+// PINNED against those sources: oracle/build_ref.sh compiles Sophus' own so3.cpp / se3.cpp against a stand-in for the Eigen operations
+// they use (oracle/ref_stubs/eigen_min.h) into oracle/_ref/libsophus_ref.so, and
+// tests/test_oracle_ndt.py::test_se3_restatement_against_the_reference_sophus_sources holds this file to it bit for bit (random, tiny-angle,
+// near-pi arguments; Sophus' own test_se3.cpp cases pass on the compiled sources).  What that pins is Sophus; Eigen's rounding is not.
 // Restated from  Sophus/sophus/so3.cpp:127-202 (logAndTheta, expAndTheta), so3.h:35 (SMALL_EPS),
 // se3.cpp:60-110 (operator*, inverse), se3.cpp:170-220 (exp, log); the Eigen::Quaterniond
 // pieces Sophus relies on (matrix->quaternion, quaternion->matrix, product, normalize) follow

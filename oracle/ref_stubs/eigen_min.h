@@ -1,0 +1,234 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// A stand-in for the few Eigen 3 operations that Sophus a621ff2's so3.cpp and se3.cpp use, so that those two files — the reference's
+// own Lie-group code, vendored in /root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip — can be compiled in this image, which has no
+// Eigen (oracle/build_ref.sh -> oracle/_ref/libsophus_ref.so).  The compiled library is the checker of the restatement in oracle/ose3.h:
+// it pins Sophus' formulas, series coefficients, thresholds, branches and normalisation points.  It does NOT pin Eigen's own rounding: the
+// quaternion and small-matrix kernels below are written here (Eigen 3.3 Geometry/Quaternion.h semantics, scalar evaluation order) and share
+// those choices with ose3.h, so an agreement to the last bit says "same Sophus", not "same Eigen".
+//
+// Only what so3.cpp / se3.cpp touch is provided: fixed-size double matrices with eager arithmetic, the comma initialiser, fixed-size
+// block / corner / head / tail views, transpose and stream output (for the headers' inline printers), and Quaternion.
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <cstddef>
+#include <ostream>
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+namespace Eigen {
+
+template <typename S, int R, int C>
+class Matrix;
+
+// Writable view of a fixed RB x CB block of a Matrix<S, R, C>.
+template <typename S, int R, int C, int RB, int CB>
+class BlockRef {
+ public:
+  BlockRef(Matrix<S, R, C>& m, int r0, int c0) : m_(m), r0_(r0), c0_(c0) { assert(r0 >= 0 && c0 >= 0 && r0 + RB <= R && c0 + CB <= C); }
+  BlockRef& operator=(const Matrix<S, RB, CB>& v) {
+    for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) m_(r0_ + r, c0_ + c) = v(r, c);
+    return *this;
+  }
+  BlockRef& operator=(const BlockRef& o) { return *this = static_cast<Matrix<S, RB, CB> >(o); }
+  template <int R2, int C2>
+  BlockRef& operator=(const BlockRef<S, R2, C2, RB, CB>& o) { return *this = static_cast<Matrix<S, RB, CB> >(o); }
+  operator Matrix<S, RB, CB>() const {
+    Matrix<S, RB, CB> v;
+    for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) v(r, c) = m_(r0_ + r, c0_ + c);
+    return v;
+  }
+
+ private:
+  Matrix<S, R, C>& m_;
+  int r0_, c0_;
+};
+
+// Writable view of one column: only head(n) / head<N>() are used on it.
+template <typename S, int R, int C>
+class ColRef {
+ public:
+  ColRef(Matrix<S, R, C>& m, int c) : m_(m), c_(c) {}
+  template <int N>
+  BlockRef<S, R, C, N, 1> head() { return BlockRef<S, R, C, N, 1>(m_, 0, c_); }
+  BlockRef<S, R, C, 3, 1> head(int n) { assert(n == 3); (void)n; return BlockRef<S, R, C, 3, 1>(m_, 0, c_); }
+
+ private:
+  Matrix<S, R, C>& m_;
+  int c_;
+};
+
+template <typename S, int R, int C>
+class CommaInit {
+ public:
+  CommaInit(Matrix<S, R, C>& m, S first) : m_(m), k_(0) { put(first); }
+  CommaInit& operator,(S v) { put(v); return *this; }
+  ~CommaInit() { assert(k_ == R * C); }
+
+ private:
+  void put(S v) { assert(k_ < R * C); m_(k_ / C, k_ % C) = v; k_++; }     // row by row, like Eigen
+  Matrix<S, R, C>& m_;
+  int k_;
+};
+
+template <typename S, int R, int C>
+class Matrix {
+ public:
+  Matrix() {}
+  Matrix(S x, S y, S z) { static_assert(R * C == 3, "three-coefficient constructor"); d_[0] = x; d_[1] = y; d_[2] = z; }
+
+  S& operator()(int r, int c) { assert(r >= 0 && r < R && c >= 0 && c < C); return d_[r * C + c]; }
+  const S& operator()(int r, int c) const { assert(r >= 0 && r < R && c >= 0 && c < C); return d_[r * C + c]; }
+  S& operator()(int i) { static_assert(C == 1, "vector access"); return d_[i]; }
+  const S& operator()(int i) const { static_assert(C == 1, "vector access"); return d_[i]; }
+  S& operator[](int i) { static_assert(C == 1, "vector access"); return d_[i]; }
+  const S& operator[](int i) const { static_assert(C == 1, "vector access"); return d_[i]; }
+  const S& x() const { return (*this)(0); }
+  const S& y() const { return (*this)(1); }
+  const S& z() const { return (*this)(2); }
+
+  void setZero() { for (int i = 0; i < R * C; i++) d_[i] = S(0); }
+  void setIdentity() { for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) (*this)(r, c) = r == c ? S(1) : S(0); }
+  static Matrix Zero() { Matrix m; m.setZero(); return m; }
+  static Matrix Zero(int r, int c) { assert(r == R && c == C); (void)r; (void)c; return Zero(); }
+  static Matrix Identity() { Matrix m; m.setIdentity(); return m; }
+
+  CommaInit<S, R, C> operator<<(S first) { return CommaInit<S, R, C>(*this, first); }
+
+  S squaredNorm() const { S s = d_[0] * d_[0]; for (int i = 1; i < R * C; i++) s += d_[i] * d_[i]; return s; }
+  S norm() const { return std::sqrt(squaredNorm()); }
+  Matrix cross(const Matrix& o) const {
+    static_assert(R * C == 3, "cross product");
+    return Matrix(d_[1] * o.d_[2] - d_[2] * o.d_[1], d_[2] * o.d_[0] - d_[0] * o.d_[2], d_[0] * o.d_[1] - d_[1] * o.d_[0]);
+  }
+
+  Matrix<S, C, R> transpose() const { Matrix<S, C, R> t; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) t(c, r) = (*this)(r, c); return t; }
+
+  Matrix& operator+=(const Matrix& o) { for (int i = 0; i < R * C; i++) d_[i] += o.d_[i]; return *this; }
+  Matrix operator-() const { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = -d_[i]; return m; }
+  Matrix operator+(const Matrix& o) const { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = d_[i] + o.d_[i]; return m; }
+  Matrix operator-(const Matrix& o) const { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = d_[i] - o.d_[i]; return m; }
+  Matrix operator*(S s) const { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = d_[i] * s; return m; }
+  template <int C2>
+  Matrix<S, R, C2> operator*(const Matrix<S, C, C2>& o) const {     // coefficient-wise lazy product of small fixed sizes: k ascending
+    Matrix<S, R, C2> m;
+    for (int r = 0; r < R; r++)
+      for (int c = 0; c < C2; c++) {
+        S s = (*this)(r, 0) * o(0, c);
+        for (int k = 1; k < C; k++) s += (*this)(r, k) * o(k, c);
+        m(r, c) = s;
+      }
+    return m;
+  }
+
+  // fixed-size views: a copy from a const object, a writable reference otherwise
+  template <int N> Matrix<S, N, 1> head() const { static_assert(C == 1, "head"); return sub<N, 1>(0, 0); }
+  template <int N> Matrix<S, N, 1> tail() const { static_assert(C == 1, "tail"); return sub<N, 1>(R - N, 0); }
+  template <int N> BlockRef<S, R, C, N, 1> head() { static_assert(C == 1, "head"); return BlockRef<S, R, C, N, 1>(*this, 0, 0); }
+  template <int N> BlockRef<S, R, C, N, 1> tail() { static_assert(C == 1, "tail"); return BlockRef<S, R, C, N, 1>(*this, R - N, 0); }
+  template <int RB, int CB> Matrix<S, RB, CB> topLeftCorner() const { return sub<RB, CB>(0, 0); }
+  template <int RB, int CB> Matrix<S, RB, CB> topRightCorner() const { return sub<RB, CB>(0, C - CB); }
+  template <int RB, int CB> Matrix<S, RB, CB> bottomRightCorner() const { return sub<RB, CB>(R - RB, C - CB); }
+  template <int RB, int CB> BlockRef<S, R, C, RB, CB> topLeftCorner() { return BlockRef<S, R, C, RB, CB>(*this, 0, 0); }
+  template <int RB, int CB> BlockRef<S, R, C, RB, CB> topRightCorner() { return BlockRef<S, R, C, RB, CB>(*this, 0, C - CB); }
+  template <int RB, int CB> BlockRef<S, R, C, RB, CB> bottomRightCorner() { return BlockRef<S, R, C, RB, CB>(*this, R - RB, C - CB); }
+  BlockRef<S, R, C, 3, 3> block(int r0, int c0, int nr, int nc) { assert(nr == 3 && nc == 3); (void)nr; (void)nc; return BlockRef<S, R, C, 3, 3>(*this, r0, c0); }
+  Matrix<S, R, 1> col(int c) const { Matrix<S, R, 1> v; for (int r = 0; r < R; r++) v(r) = (*this)(r, c); return v; }
+  ColRef<S, R, C> col(int c) { return ColRef<S, R, C>(*this, c); }
+
+ private:
+  template <int RB, int CB>
+  Matrix<S, RB, CB> sub(int r0, int c0) const {
+    Matrix<S, RB, CB> v;
+    for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) v(r, c) = (*this)(r0 + r, c0 + c);
+    return v;
+  }
+  S d_[R * C];
+};
+
+template <typename S, int R, int C>
+inline Matrix<S, R, C> operator*(S s, const Matrix<S, R, C>& m) { Matrix<S, R, C> o; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) o(r, c) = s * m(r, c); return o; }
+
+// the inline stream operators of so3.h / se3.h (never called by the checker)
+template <typename S, int R, int C>
+inline std::ostream& operator<<(std::ostream& o, const Matrix<S, R, C>& m) {
+  for (int r = 0; r < R; r++) { for (int c = 0; c < C; c++) o << (c ? " " : "") << m(r, c); if (r + 1 < R) o << "\n"; }
+  return o;
+}
+
+typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<double, 3, 1> Vector3d;
+
+// Eigen::Quaternion<S>, coefficients (x, y, z, w) with the (w, x, y, z) constructor; Geometry/Quaternion.h semantics.
+template <typename S>
+class Quaternion {
+ public:
+  Quaternion() {}
+  Quaternion(S w, S x, S y, S z) : x_(x), y_(y), z_(z), w_(w) {}
+  explicit Quaternion(const Matrix<S, 3, 3>& m) {          // quaternionbase_assign_impl<Other, 3, 3>: not normalised
+    S t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > S(0)) {
+      t = std::sqrt(t + S(1.0));
+      w_ = S(0.5) * t;
+      t = S(0.5) / t;
+      x_ = (m(2, 1) - m(1, 2)) * t;
+      y_ = (m(0, 2) - m(2, 0)) * t;
+      z_ = (m(1, 0) - m(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (m(1, 1) > m(0, 0)) i = 1;
+      if (m(2, 2) > m(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + S(1.0));
+      S v[3];
+      v[i] = S(0.5) * t;
+      t = S(0.5) / t;
+      w_ = (m(k, j) - m(j, k)) * t;
+      v[j] = (m(j, i) + m(i, j)) * t;
+      v[k] = (m(k, i) + m(i, k)) * t;
+      x_ = v[0]; y_ = v[1]; z_ = v[2];
+    }
+  }
+  S w() const { return w_; }
+  S x() const { return x_; }
+  S y() const { return y_; }
+  S z() const { return z_; }
+  Matrix<S, 3, 1> vec() const { return Matrix<S, 3, 1>(x_, y_, z_); }
+  void setIdentity() { x_ = y_ = z_ = S(0); w_ = S(1); }
+  S squaredNorm() const { return w_ * w_ + x_ * x_ + y_ * y_ + z_ * z_; }
+  S norm() const { return std::sqrt(squaredNorm()); }
+  void normalize() { const S n = norm(); w_ /= n; x_ /= n; y_ /= n; z_ /= n; }
+  Quaternion conjugate() const { return Quaternion(w_, -x_, -y_, -z_); }
+  Quaternion operator*(const Quaternion& b) const {
+    const Quaternion& a = *this;
+    return Quaternion(a.w_ * b.w_ - a.x_ * b.x_ - a.y_ * b.y_ - a.z_ * b.z_, a.w_ * b.x_ + a.x_ * b.w_ + a.y_ * b.z_ - a.z_ * b.y_,
+                      a.w_ * b.y_ + a.y_ * b.w_ + a.z_ * b.x_ - a.x_ * b.z_, a.w_ * b.z_ + a.z_ * b.w_ + a.x_ * b.y_ - a.y_ * b.x_);
+  }
+  Quaternion& operator*=(const Quaternion& b) { *this = *this * b; return *this; }
+  // v + w * uv + vec x uv with uv = 2 (vec x v)
+  Matrix<S, 3, 1> _transformVector(const Matrix<S, 3, 1>& v) const {
+    Matrix<S, 3, 1> uv = vec().cross(v);
+    uv += uv;
+    const Matrix<S, 3, 1> c = vec().cross(uv);
+    return Matrix<S, 3, 1>(v(0) + w_ * uv(0) + c(0), v(1) + w_ * uv(1) + c(1), v(2) + w_ * uv(2) + c(2));
+  }
+  Matrix<S, 3, 3> toRotationMatrix() const {
+    const S tx = S(2) * x_, ty = S(2) * y_, tz = S(2) * z_;
+    const S twx = tx * w_, twy = ty * w_, twz = tz * w_;
+    const S txx = tx * x_, txy = ty * x_, txz = tz * x_;
+    const S tyy = ty * y_, tyz = tz * y_, tzz = tz * z_;
+    Matrix<S, 3, 3> r;
+    r(0, 0) = S(1) - (tyy + tzz); r(0, 1) = txy - twz;          r(0, 2) = txz + twy;
+    r(1, 0) = txy + twz;          r(1, 1) = S(1) - (txx + tzz); r(1, 2) = tyz - twx;
+    r(2, 0) = txz - twy;          r(2, 1) = tyz + twx;          r(2, 2) = S(1) - (txx + tyy);
+    return r;
+  }
+
+ private:
+  S x_, y_, z_, w_;
+};
+typedef Quaternion<double> Quaterniond;
+
+}  // namespace Eigen

@@ -254,6 +254,32 @@ def se3_compose_log(delta6, p6):
     return o
 
 
+_sref = False
+
+
+def sophus_ref():
+    """oracle/_ref/libsophus_ref.so: the reference's OWN Sophus sources (so3.cpp, se3.cpp from 3rdtools/Sophus-a621ff2-ubuntu18.04.zip) compiled by
+    oracle/build_ref.sh against the Eigen stand-in of oracle/ref_stubs/.  None where neither the library nor the reference tree is present."""
+    global _sref
+    if _sref is False:
+        so = os.path.join(_ODIR, "_ref", "libsophus_ref.so")
+        if not os.path.exists(so) and os.path.exists("/root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip"):
+            subprocess.call(["sh", os.path.join(_ODIR, "build_ref.sh")])
+        if os.path.exists(so):
+            L = ctypes.CDLL(so)
+            vp = ctypes.c_void_p
+            for name, n in (("sref_se3_exp", 3), ("sref_se3_exp_matrix", 2), ("sref_se3_log_of_Rt", 3), ("sref_compose_log", 3), ("sref_log_exp", 2),
+                            ("sref_inverse", 3), ("sref_transform", 3)):
+                getattr(L, name).restype = None
+                getattr(L, name).argtypes = [vp] * n
+            L.sref_selftest.restype = ctypes.c_double
+            L.sref_selftest.argtypes = []
+            _sref = L
+        else:
+            _sref = None
+    return _sref
+
+
 def svd6_solve(A, b):
     A = np.ascontiguousarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)

@@ -42,6 +42,51 @@ def test_se3_exp_log_round_trip():
     np.testing.assert_allclose(Tab, Ta @ Tb, atol=2e-6)
 
 
+def _sref_call(fn, *arrays_out_last):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays_out_last]
+    fn(*[a.ctypes.data for a in arrs])
+    return arrs
+
+
+def test_se3_restatement_against_the_reference_sophus_sources():
+    """oracle/ose3.h against the reference's own Sophus (so3.cpp / se3.cpp of the vendored Sophus a621ff2, compiled by oracle/build_ref.sh
+    against a stand-in for the Eigen operations they use): the three uses the NDT path makes of Sophus - SE3::exp(p).matrix(),
+    SE3(R, t).log(), (SE3::exp(d) * SE3::exp(p)).log() (ndt_omp_impl2.hpp:119-120,161-166) - on random, tiny-angle (both sides of
+    SMALL_EPS), near-pi and zero arguments.  Sophus' formulas, series coefficients, branches and normalisation points are pinned by this;
+    Eigen's rounding is not (oracle/ref_stubs/eigen_min.h)."""
+    R = O.sophus_ref()
+    if R is None:
+        pytest.skip("no compiled reference Sophus (needs /root/reference or a prebuilt oracle/_ref/libsophus_ref.so)")
+    assert R.sref_selftest() < 1e-10                        # Sophus' own test_se3.cpp cases and bound on the compiled sources
+    rng = np.random.default_rng(11)
+    ps = [np.zeros(6)]
+    for k in range(200):
+        ps.append(rng.normal(0, [5, 5, 2, 0.5, 0.5, 0.5]))
+    for ang in (1e-13, 9e-11, 1.1e-10, 1e-8, 1e-5):         # the Taylor branches switch at theta < 1e-10
+        u = rng.normal(size=3); u /= np.linalg.norm(u)
+        ps.append(np.concatenate([rng.normal(0, 3, 3), ang * u]))
+    for k in range(20):                                     # rotations near pi (|w| of the quaternion near 0)
+        u = rng.normal(size=3); u /= np.linalg.norm(u)
+        ps.append(np.concatenate([rng.normal(0, 3, 3), (np.pi - rng.uniform(0, 1e-6)) * u]))
+    worst = dict(exp=0.0, mat=0.0, log=0.0, comp=0.0)
+    for p in ps:
+        q, t = O.se3_exp(p)
+        _, qr, tr = _sref_call(R.sref_se3_exp, p, np.zeros(4), np.zeros(3))
+        worst["exp"] = max(worst["exp"], np.abs(q - qr).max(), np.abs(t - tr).max() / max(1.0, np.abs(tr).max()))
+        _, Mr = _sref_call(R.sref_se3_exp_matrix, p, np.zeros(16))
+        M = O.se3_exp_matrix4f(p)
+        assert np.array_equal(M, Mr.reshape(4, 4).astype(np.float32))          # the float cast the reference applies (:161-163)
+        # SE3(R, t).log() of the float matrix, as computeTransformation reads its guess
+        Rd, td = M[:3, :3].astype(np.float64), M[:3, 3].astype(np.float64)
+        _, _, lr = _sref_call(R.sref_se3_log_of_Rt, Rd.reshape(9), td, np.zeros(6))
+        lo = O.se3_log_from_matrix4f(M)
+        worst["log"] = max(worst["log"], np.abs(lo - lr).max() / max(1.0, np.abs(lr).max()))
+        d = rng.normal(0, [0.1, 0.1, 0.1, 0.01, 0.01, 0.01])
+        _, _, cr = _sref_call(R.sref_compose_log, d, p, np.zeros(6))
+        worst["comp"] = max(worst["comp"], np.abs(O.se3_compose_log(d, p) - cr).max() / max(1.0, np.abs(cr).max()))
+    assert max(worst.values()) <= 1e-15, worst
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
