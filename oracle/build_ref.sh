@@ -11,7 +11,9 @@ OUT="$HERE/_ref"
 [ -f "$ZIP" ] || { echo "build_ref.sh: $ZIP not found, skipping"; exit 0; }
 SZIP=/root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip
 if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] && [ -f "$OUT/libsophus_ref.so" ] && [ "$OUT/libsophus_ref.so" -nt "$SZIP" ] &&
-   [ "$OUT/libsophus_ref.so" -nt "$HERE/sophus_ref_api.cpp" ] && [ "$OUT/libsophus_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ]; then exit 0; fi
+   [ "$OUT/libsophus_ref.so" -nt "$HERE/sophus_ref_api.cpp" ] && [ "$OUT/libsophus_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ] &&
+   [ -f "$OUT/libndt_ref.so" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/ndt_ref_harness.cpp" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ] &&
+   [ "$OUT/libndt_ref.so" -nt "$HERE/extract_ref_functions.py" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/olin.h" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -39,4 +41,15 @@ PY
   /usr/bin/g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I"$TMP/Sophus/sophus" -o "$OUT/libsophus_ref.so" \
       "$TMP/Sophus/sophus/so3.cpp" "$TMP/Sophus/sophus/se3.cpp" "$HERE/sophus_ref_api.cpp"
   echo "built $OUT/libsophus_ref.so"
+  # The NDT path itself: the member functions of pclomp::NormalDistributionsTransform, taken verbatim from the reference's
+  # include/ndt_omp/ndt_omp_impl2.hpp at build time (into the temporary directory) and compiled inside oracle/ndt_ref_harness.cpp, which
+  # supplies the class declaration, the voxel-grid adapter and pcl::transformPointCloud (see its header for what this pins).
+  IMPL=/root/reference/include/ndt_omp/ndt_omp_impl2.hpp
+  if [ -f "$IMPL" ]; then
+    python3 "$HERE/extract_ref_functions.py" "$IMPL" "$TMP/ref_ndt_bodies.inc" computeTransformation computeDerivatives computePointDerivatives_AngleAxisd \
+        updateDerivatives computeHessian updateHessian updateIntervalMT trialValueSelectionMT computeStepLengthMT calculateScore
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -Wno-unknown-pragmas -DREF_NDT_BODIES="\"$TMP/ref_ndt_bodies.inc\"" -I"$HERE/ref_stubs" \
+        -I"$TMP/Sophus/sophus" -o "$OUT/libndt_ref.so" "$TMP/Sophus/sophus/so3.cpp" "$TMP/Sophus/sophus/se3.cpp" "$HERE/ndt_ref_harness.cpp"
+    echo "built $OUT/libndt_ref.so"
+  fi
 fi

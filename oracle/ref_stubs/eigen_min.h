@@ -13,6 +13,8 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <memory>
+#include <type_traits>
 #include <ostream>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
@@ -39,10 +41,77 @@ class BlockRef {
     for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) v(r, c) = m_(r0_ + r, c0_ + c);
     return v;
   }
+  void setIdentity() { for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) m_(r0_ + r, c0_ + c) = r == c ? S(1) : S(0); }
 
  private:
   Matrix<S, R, C>& m_;
   int r0_, c0_;
+};
+
+// m.block(r0, c0, nr, nc).cast<T>() of a const matrix (run-time sizes): converts to the fixed-size matrix the caller asks for.
+template <typename S, int R, int C, typename T>
+class DynBlockCast {
+ public:
+  DynBlockCast(const Matrix<S, R, C>& m, int r0, int c0, int nr, int nc) : m_(m), r0_(r0), c0_(c0), nr_(nr), nc_(nc) {}
+  template <int RB, int CB>
+  operator Matrix<T, RB, CB>() const {
+    assert(RB == nr_ && CB == nc_);
+    Matrix<T, RB, CB> v;
+    for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) v(r, c) = static_cast<T>(m_(r0_ + r, c0_ + c));
+    return v;
+  }
+
+ private:
+  const Matrix<S, R, C>& m_;
+  int r0_, c0_, nr_, nc_;
+};
+template <typename S, int R, int C>
+class DynBlock {
+ public:
+  DynBlock(const Matrix<S, R, C>& m, int r0, int c0, int nr, int nc) : m_(m), r0_(r0), c0_(c0), nr_(nr), nc_(nc) {}
+  template <typename T>
+  DynBlockCast<S, R, C, T> cast() const { return DynBlockCast<S, R, C, T>(m_, r0_, c0_, nr_, nc_); }
+
+ private:
+  const Matrix<S, R, C>& m_;
+  int r0_, c0_, nr_, nc_;
+};
+
+// The float dot of FOUR products reduces pairwise, (t0 + t2) + (t1 + t3), everything else left to right: the evaluation orders the
+// restatement in oracle/ndt_oracle.cpp assumes for Eigen 3.3 + SSE (its header says what that inference rests on).  Kept identical here
+// on purpose - this file stands in for Eigen's interface, not for its rounding.
+template <typename S, int N>
+struct DotRule {
+  template <typename A, typename B>
+  static S run(const A& a, const B& b) { S s = a(0) * b(0); for (int k = 1; k < N; k++) s += a(k) * b(k); return s; }
+};
+template <typename S>
+struct DotRule<S, 4> {
+  template <typename A, typename B>
+  static S run(const A& a, const B& b) { const S t0 = a(0) * b(0), t1 = a(1) * b(1), t2 = a(2) * b(2), t3 = a(3) * b(3); return (t0 + t2) + (t1 + t3); }
+};
+
+// m.transpose(): printable, convertible to a matrix, and as the LEFT factor of a product every coefficient is an inner product (DotRule)
+template <typename S, int R, int C>
+class Transposed {      // R x C is the shape of the transposed matrix
+ public:
+  explicit Transposed(const Matrix<S, C, R>& src) { for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) t_(r, c) = src(c, r); }
+  operator Matrix<S, R, C>() const { return t_; }
+  const Matrix<S, R, C>& eval() const { return t_; }
+  template <int C2>
+  Matrix<S, R, C2> operator*(const Matrix<S, C, C2>& o) const {
+    Matrix<S, R, C2> m;
+    for (int r = 0; r < R; r++)
+      for (int c = 0; c < C2; c++) {
+        struct Row { const Matrix<S, R, C>& t; int r; S operator()(int k) const { return t(r, k); } } a = {t_, r};
+        struct Col { const Matrix<S, C, C2>& o; int c; S operator()(int k) const { return o(k, c); } } b = {o, c};
+        m(r, c) = DotRule<S, C>::run(a, b);
+      }
+    return m;
+  }
+
+ private:
+  Matrix<S, R, C> t_;
 };
 
 // Writable view of one column: only head(n) / head<N>() are used on it.
@@ -76,14 +145,26 @@ template <typename S, int R, int C>
 class Matrix {
  public:
   Matrix() {}
-  Matrix(S x, S y, S z) { static_assert(R * C == 3, "three-coefficient constructor"); d_[0] = x; d_[1] = y; d_[2] = z; }
+  template <typename A, typename B, typename D>
+  Matrix(A x, B y, D z) { static_assert(R * C == 3, "three-coefficient constructor"); d_[0] = static_cast<S>(x); d_[1] = static_cast<S>(y); d_[2] = static_cast<S>(z); }
+  template <typename A, typename B, typename D, typename E>
+  Matrix(A x, B y, D z, E w) {
+    static_assert(R * C == 4 && (R == 1 || C == 1), "four-coefficient constructor");
+    d_[0] = static_cast<S>(x); d_[1] = static_cast<S>(y); d_[2] = static_cast<S>(z); d_[3] = static_cast<S>(w);
+  }
+  // a row vector initialises a column vector and vice versa (Eigen transposes vectors on assignment)
+  template <int R2, int C2, typename = typename std::enable_if<(R2 == C && C2 == R && R != C && (R == 1 || C == 1))>::type>
+  Matrix(const Matrix<S, R2, C2>& o) { for (int i = 0; i < R * C; i++) d_[i] = o.coeff(i); }
+  S coeff(int i) const { return d_[i]; }
+  int rows() const { return R; }
+  int cols() const { return C; }
 
   S& operator()(int r, int c) { assert(r >= 0 && r < R && c >= 0 && c < C); return d_[r * C + c]; }
   const S& operator()(int r, int c) const { assert(r >= 0 && r < R && c >= 0 && c < C); return d_[r * C + c]; }
-  S& operator()(int i) { static_assert(C == 1, "vector access"); return d_[i]; }
-  const S& operator()(int i) const { static_assert(C == 1, "vector access"); return d_[i]; }
-  S& operator[](int i) { static_assert(C == 1, "vector access"); return d_[i]; }
-  const S& operator[](int i) const { static_assert(C == 1, "vector access"); return d_[i]; }
+  S& operator()(int i) { static_assert(C == 1 || R == 1, "vector access"); return d_[i]; }
+  const S& operator()(int i) const { static_assert(C == 1 || R == 1, "vector access"); return d_[i]; }
+  S& operator[](int i) { static_assert(C == 1 || R == 1, "vector access"); return d_[i]; }
+  const S& operator[](int i) const { static_assert(C == 1 || R == 1, "vector access"); return d_[i]; }
   const S& x() const { return (*this)(0); }
   const S& y() const { return (*this)(1); }
   const S& z() const { return (*this)(2); }
@@ -103,7 +184,20 @@ class Matrix {
     return Matrix(d_[1] * o.d_[2] - d_[2] * o.d_[1], d_[2] * o.d_[0] - d_[0] * o.d_[2], d_[0] * o.d_[1] - d_[1] * o.d_[0]);
   }
 
-  Matrix<S, C, R> transpose() const { Matrix<S, C, R> t; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) t(c, r) = (*this)(r, c); return t; }
+  Transposed<S, C, R> transpose() const { return Transposed<S, C, R>(*this); }
+  template <typename T>
+  Matrix<T, R, C> cast() const { Matrix<T, R, C> m; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) m(r, c) = static_cast<T>((*this)(r, c)); return m; }
+  Matrix& noalias() { return *this; }
+  template <int R2, int C2>
+  S dot(const Matrix<S, R2, C2>& o) const {
+    static_assert((R == 1 || C == 1) && (R2 == 1 || C2 == 1) && R * C == R2 * C2, "dot of two vectors");
+    return DotRule<S, R * C>::run(*this, o);
+  }
+  void normalize() { const S n = norm(); for (int i = 0; i < R * C; i++) d_[i] /= n; }
+  bool operator==(const Matrix& o) const { for (int i = 0; i < R * C; i++) if (!(d_[i] == o.d_[i])) return false; return true; }
+  bool operator!=(const Matrix& o) const { return !(*this == o); }
+  Matrix& operator-=(const Matrix& o) { for (int i = 0; i < R * C; i++) d_[i] -= o.d_[i]; return *this; }
+  Matrix& operator*=(S s) { for (int i = 0; i < R * C; i++) d_[i] *= s; return *this; }
 
   Matrix& operator+=(const Matrix& o) { for (int i = 0; i < R * C; i++) d_[i] += o.d_[i]; return *this; }
   Matrix operator-() const { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = -d_[i]; return m; }
@@ -115,9 +209,14 @@ class Matrix {
     Matrix<S, R, C2> m;
     for (int r = 0; r < R; r++)
       for (int c = 0; c < C2; c++) {
-        S s = (*this)(r, 0) * o(0, c);
-        for (int k = 1; k < C; k++) s += (*this)(r, k) * o(k, c);
-        m(r, c) = s;
+        if constexpr (R == 1) {      // (row vector) x matrix: every coefficient is an inner product
+          struct Col { const Matrix<S, C, C2>& o; int c; S operator()(int k) const { return o(k, c); } } b = {o, c};
+          m(r, c) = DotRule<S, C>::run(*this, b);
+        } else {
+          S s = (*this)(r, 0) * o(0, c);
+          for (int k = 1; k < C; k++) s += (*this)(r, k) * o(k, c);
+          m(r, c) = s;
+        }
       }
     return m;
   }
@@ -134,6 +233,10 @@ class Matrix {
   template <int RB, int CB> BlockRef<S, R, C, RB, CB> topRightCorner() { return BlockRef<S, R, C, RB, CB>(*this, 0, C - CB); }
   template <int RB, int CB> BlockRef<S, R, C, RB, CB> bottomRightCorner() { return BlockRef<S, R, C, RB, CB>(*this, R - RB, C - CB); }
   BlockRef<S, R, C, 3, 3> block(int r0, int c0, int nr, int nc) { assert(nr == 3 && nc == 3); (void)nr; (void)nc; return BlockRef<S, R, C, 3, 3>(*this, r0, c0); }
+  DynBlock<S, R, C> block(int r0, int c0, int nr, int nc) const { return DynBlock<S, R, C>(*this, r0, c0, nr, nc); }
+  BlockRef<S, R, C, 3, 3> topLeftCorner(int nr, int nc) { assert(nr == 3 && nc == 3); (void)nr; (void)nc; return BlockRef<S, R, C, 3, 3>(*this, 0, 0); }
+  template <int RB, int CB> Matrix<S, RB, CB> block(int r0, int c0) const { return sub<RB, CB>(r0, c0); }
+  template <int RB, int CB> BlockRef<S, R, C, RB, CB> block(int r0, int c0) { return BlockRef<S, R, C, RB, CB>(*this, r0, c0); }
   Matrix<S, R, 1> col(int c) const { Matrix<S, R, 1> v; for (int r = 0; r < R; r++) v(r) = (*this)(r, c); return v; }
   ColRef<S, R, C> col(int c) { return ColRef<S, R, C>(*this, c); }
 
@@ -157,6 +260,13 @@ inline std::ostream& operator<<(std::ostream& o, const Matrix<S, R, C>& m) {
   return o;
 }
 
+template <typename S, int R, int C>
+inline std::ostream& operator<<(std::ostream& o, const Transposed<S, R, C>& t) { return o << t.eval(); }
+
+typedef Matrix<float, 4, 4> Matrix4f;
+typedef Matrix<float, 4, 1> Vector4f;
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, 3, 1> Vector3d;
@@ -230,5 +340,47 @@ class Quaternion {
   S x_, y_, z_, w_;
 };
 typedef Quaternion<double> Quaterniond;
+
+template <typename T>
+using aligned_allocator = std::allocator<T>;
+
+// computeTransformation only stores final_transformation_ into one of these (ndt_omp_impl2.hpp:110-111)
+enum { Affine = 2, ColMajor = 0 };
+template <typename S, int Dim, int Mode, int Options>
+class Transform {
+ public:
+  Matrix<S, Dim + 1, Dim + 1>& matrix() { return m_; }
+
+ private:
+  Matrix<S, Dim + 1, Dim + 1> m_;
+};
+
+}  // namespace Eigen
+
+#include "../olin.h"
+
+namespace Eigen {
+
+// JacobiSVD<Matrix<double, 6, 6>>(H, ComputeFullU | ComputeFullV).solve(b): the pseudo-inverse solve with Eigen's rank rule, carried out by the
+// one-sided Jacobi iteration of oracle/olin.h (Eigen's own two-sided sweep is not restated anywhere in this repository).
+enum { ComputeFullU = 0x04, ComputeFullV = 0x10 };
+template <typename M>
+class JacobiSVD;
+template <>
+class JacobiSVD<Matrix<double, 6, 6> > {
+ public:
+  JacobiSVD(const Matrix<double, 6, 6>& A, unsigned int) { for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) a_[r * 6 + c] = A(r, c); }
+  Matrix<double, 6, 1> solve(const Matrix<double, 6, 1>& b) const {
+    double bb[6], x[6];
+    for (int i = 0; i < 6; i++) bb[i] = b(i);
+    olin::svd6_solve(a_, bb, x);
+    Matrix<double, 6, 1> r;
+    for (int i = 0; i < 6; i++) r(i) = x[i];
+    return r;
+  }
+
+ private:
+  double a_[36];
+};
 
 }  // namespace Eigen

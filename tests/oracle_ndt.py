@@ -280,6 +280,86 @@ def sophus_ref():
     return _sref
 
 
+_nref = False
+
+
+def ndt_ref_lib():
+    """oracle/_ref/libndt_ref.so: the reference's OWN member functions of pclomp::NormalDistributionsTransform (taken from ndt_omp_impl2.hpp at
+    build time) compiled in oracle/ndt_ref_harness.cpp.  None where neither the library nor the reference tree is present."""
+    global _nref
+    if _nref is False:
+        so = os.path.join(_ODIR, "_ref", "libndt_ref.so")
+        if not os.path.exists(so) and os.path.exists("/root/reference/include/ndt_omp/ndt_omp_impl2.hpp"):
+            subprocess.call(["sh", os.path.join(_ODIR, "build_ref.sh")])
+        if os.path.exists(so):
+            L = ctypes.CDLL(so)
+            vp, i32, f32, f64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
+            L.nref_create.restype = vp; L.nref_create.argtypes = []
+            L.nref_destroy.restype = None; L.nref_destroy.argtypes = [vp]
+            L.nref_set_params.restype = None; L.nref_set_params.argtypes = [vp, f32, f64, f64, f64, i32, i32]
+            L.nref_set_target_cells.restype = None; L.nref_set_target_cells.argtypes = [vp, i32] + [vp] * 9 + [f32, i32]
+            L.nref_set_source.restype = None; L.nref_set_source.argtypes = [vp, vp, sz, sz]
+            L.nref_eval_derivatives.restype = f64; L.nref_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
+            L.nref_eval_hessian.restype = None; L.nref_eval_hessian.argtypes = [vp, vp, vp, vp]
+            L.nref_calculate_score.restype = f64; L.nref_calculate_score.argtypes = [vp, vp]
+            L.nref_align.restype = i32; L.nref_align.argtypes = [vp, vp, vp, vp, vp, vp]
+            _nref = L
+        else:
+            _nref = None
+    return _nref
+
+
+class ReferenceNDT:
+    """The reference's own computeTransformation / computeDerivatives / ... (oracle/ndt_ref_harness.cpp) on the voxel cells of an OracleNDT."""
+
+    def __init__(self, oracle):
+        self.L = ndt_ref_lib()
+        self.h = self.L.nref_create()
+        p = oracle.params
+        self.L.nref_set_params(self.h, p["resolution"], p["step_size"], p["outlier_ratio"], p["trans_eps"], p["max_iter"], p["search"])
+        lv = oracle.leaves()
+        mn, mx, dv = oracle.grid()
+        self._keep = [np.ascontiguousarray(lv[k]) for k in ("keys", "nr_points", "mean", "icov", "centroid", "in_cloud")] + [mn, mx, dv]
+        self.L.nref_set_target_cells(self.h, len(lv["keys"]), *[a.ctypes.data for a in self._keep], p["resolution"], 6)
+
+    def __del__(self):
+        try:
+            self.L.nref_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_source(self, xyz):
+        a = _f32(xyz)
+        self.n_src = a.shape[0]
+        self.L.nref_set_source(self.h, a.ctypes.data, a.shape[0], a.shape[1])
+
+    def eval_derivatives(self, p6, T=None, compute_hessian=True):
+        p = np.ascontiguousarray(p6, dtype=np.float64)
+        g, H = np.zeros(6), np.zeros((6, 6))
+        M = _colmajor16(T) if T is not None else None
+        s = self.L.nref_eval_derivatives(self.h, p.ctypes.data, M.ctypes.data if M is not None else None, int(compute_hessian), g.ctypes.data, H.ctypes.data)
+        return s, g, H
+
+    def eval_hessian(self, p6, T=None):
+        p = np.ascontiguousarray(p6, dtype=np.float64)
+        H = np.zeros((6, 6))
+        M = _colmajor16(T) if T is not None else None
+        self.L.nref_eval_hessian(self.h, p.ctypes.data, M.ctypes.data if M is not None else None, H.ctypes.data)
+        return H
+
+    def calculate_score(self, T):
+        M = _colmajor16(T)
+        return self.L.nref_calculate_score(self.h, M.ctypes.data)
+
+    def align(self, guess):
+        g = _colmajor16(guess)
+        fin = np.zeros(16, np.float32)
+        it, tp = ctypes.c_int(0), ctypes.c_double(0)
+        cloud = np.zeros((self.n_src, 3), np.float32)
+        conv = self.L.nref_align(self.h, g.ctypes.data, fin.ctypes.data, ctypes.byref(it), ctypes.byref(tp), cloud.ctypes.data)
+        return dict(final=_from_colmajor16(fin), iterations=it.value, converged=bool(conv), trans_probability=tp.value, cloud=cloud)
+
+
 def svd6_solve(A, b):
     A = np.ascontiguousarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)

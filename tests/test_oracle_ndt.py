@@ -87,6 +87,45 @@ def test_se3_restatement_against_the_reference_sophus_sources():
     assert max(worst.values()) <= 1e-15, worst
 
 
+@pytest.mark.parametrize("search", [O.DIRECT7, O.DIRECT1, O.DIRECT26, O.KDTREE])
+def test_restatement_against_the_reference_member_functions(small_pair, search):
+    """The oracle against the reference's OWN code: computeTransformation, computeDerivatives, computePointDerivatives_AngleAxisd,
+    updateDerivatives, computeHessian, updateHessian, computeStepLengthMT, updateIntervalMT, trialValueSelectionMT and calculateScore are
+    taken verbatim from include/ndt_omp/ndt_omp_impl2.hpp at build time and compiled in oracle/ndt_ref_harness.cpp (with the reference's
+    Sophus) against stand-ins for Eigen's interface, the class declaration and the voxel grid; both sides run one thread on the same
+    voxel cells.  Bar: every number identical - derivative passes in all four search modes, the all-double Hessian, calculateScore, whole
+    aligns (iterations, convergence flag, final transformation, probability, aligned cloud), the forced More-Thuente path included."""
+    if O.ndt_ref_lib() is None:
+        pytest.skip("no compiled reference NDT (needs /root/reference or a prebuilt oracle/_ref/libndt_ref.so)")
+    tgt, src, guess, truth = small_pair
+    o = O.OracleNDT(variant=O.VAR_OMP, search=search, num_threads=1, trans_eps=0.01, max_iter=30)
+    o.set_target(tgt); o.set_source(src)
+    r = O.ReferenceNDT(o); r.set_source(src)
+    rng = np.random.default_rng(21)
+    p0 = O.se3_log_from_matrix4f(guess)
+    for k in range(3):
+        p = p0 if k == 0 else p0 + rng.normal(0, [0.05, 0.05, 0.02, 0.004, 0.004, 0.01])
+        T = guess if k == 0 else None
+        for hess in (True, False):
+            so, go, Ho = o.eval_derivatives(p, T, hess)
+            sr, gr, Hr = r.eval_derivatives(p, T, hess)
+            assert abs(so) > 100 and so == sr and np.array_equal(go, gr) and np.array_equal(Ho, Hr), (k, hess)
+        assert np.array_equal(o.eval_hessian(p, T), r.eval_hessian(p, T))
+    assert o.calculate_score(guess) == r.calculate_score(guess)
+    ao, ar = o.align(guess, want_cloud=True), r.align(guess)
+    assert ao["iterations"] == ar["iterations"] > 2 and ao["converged"] == ar["converged"]
+    assert np.array_equal(ao["final"], ar["final"]) and ao["trans_probability"] == ar["trans_probability"] and np.array_equal(ao["cloud"], ar["cloud"])
+    if search == O.DIRECT7:
+        # step_size <= epsilon / 2 is the only way the More-Thuente loop and computeHessian run (the `(step_max - step_min) > 0` quirk)
+        for ss, eps, g0 in ((0.2, 0.5, truth.astype(np.float32)), (0.2, 0.5, guess), (0.1, 0.3, truth.astype(np.float32))):
+            o2 = O.OracleNDT(variant=O.VAR_OMP, search=search, num_threads=1, step_size=ss, trans_eps=eps, max_iter=6)
+            o2.set_target(tgt); o2.set_source(src)
+            r2 = O.ReferenceNDT(o2); r2.set_source(src)
+            a2, b2 = o2.align(g0, want_cloud=True), r2.align(g0)
+            assert a2["n_hess"] > 0 and a2["iterations"] == b2["iterations"] and a2["converged"] == b2["converged"]
+            assert np.array_equal(a2["final"], b2["final"]) and a2["trans_probability"] == b2["trans_probability"] and np.array_equal(a2["cloud"], b2["cloud"])
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
