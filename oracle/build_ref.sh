@@ -13,7 +13,9 @@ SZIP=/root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip
 if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] && [ -f "$OUT/libsophus_ref.so" ] && [ "$OUT/libsophus_ref.so" -nt "$SZIP" ] &&
    [ "$OUT/libsophus_ref.so" -nt "$HERE/sophus_ref_api.cpp" ] && [ "$OUT/libsophus_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ] &&
    [ -f "$OUT/libndt_ref.so" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/ndt_ref_harness.cpp" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ] &&
-   [ "$OUT/libndt_ref.so" -nt "$HERE/extract_ref_functions.py" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/olin.h" ]; then exit 0; fi
+   [ "$OUT/libndt_ref.so" -nt "$HERE/extract_ref_functions.py" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/olin.h" ] &&
+   [ -f "$OUT/libndt_pca_ref.so" ] && [ "$OUT/libndt_pca_ref.so" -nt "$OUT/libndt_ref.so" ] &&
+   [ -f "$OUT/libndt_ground_ref.so" ] && [ "$OUT/libndt_ground_ref.so" -nt "$OUT/libndt_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -44,12 +46,16 @@ PY
   # The NDT path itself: the member functions of pclomp::NormalDistributionsTransform, taken verbatim from the reference's
   # include/ndt_omp/ndt_omp_impl2.hpp at build time (into the temporary directory) and compiled inside oracle/ndt_ref_harness.cpp, which
   # supplies the class declaration, the voxel-grid adapter and pcl::transformPointCloud (see its header for what this pins).
-  IMPL=/root/reference/include/ndt_omp/ndt_omp_impl2.hpp
-  if [ -f "$IMPL" ]; then
-    python3 "$HERE/extract_ref_functions.py" "$IMPL" "$TMP/ref_ndt_bodies.inc" computeTransformation computeDerivatives computePointDerivatives_AngleAxisd \
-        updateDerivatives computeHessian updateHessian updateIntervalMT trialValueSelectionMT computeStepLengthMT calculateScore
-    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -Wno-unknown-pragmas -DREF_NDT_BODIES="\"$TMP/ref_ndt_bodies.inc\"" -I"$HERE/ref_stubs" \
-        -I"$TMP/Sophus/sophus" -o "$OUT/libndt_ref.so" "$TMP/Sophus/sophus/so3.cpp" "$TMP/Sophus/sophus/se3.cpp" "$HERE/ndt_ref_harness.cpp"
-    echo "built $OUT/libndt_ref.so"
-  fi
+  FUNCS="computeTransformation computePointDerivatives_AngleAxisd updateDerivatives computeHessian updateHessian updateIntervalMT trialValueSelectionMT computeStepLengthMT calculateScore"
+  build_ndt() {      # <impl file> <qualified class> <derivative pass> <extra define> <output>
+    [ -f "$1" ] || return 0
+    python3 "$HERE/extract_ref_functions.py" "$1" "$TMP/bodies_$5.inc" "$2" $FUNCS "$3"
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -Wno-unknown-pragmas $4 -DREF_NDT_BODIES="\"$TMP/bodies_$5.inc\"" -I"$HERE/ref_stubs" \
+        -I"$TMP/Sophus/sophus" -o "$OUT/$5" "$TMP/Sophus/sophus/so3.cpp" "$TMP/Sophus/sophus/se3.cpp" "$HERE/ndt_ref_harness.cpp"
+    echo "built $OUT/$5"
+  }
+  INC=/root/reference/include
+  build_ndt "$INC/ndt_omp/ndt_omp_impl2.hpp" pclomp::NormalDistributionsTransform computeDerivatives "" libndt_ref.so
+  build_ndt "$INC/ndt_pca/ndt_pca_impl2.hpp" pclpca::NormalDistributionsTransform computeDerivatives -DREF_PCA libndt_pca_ref.so
+  build_ndt "$INC/ndt_omp/ndt_ground_impl.hpp" pclomp_ground::NormalDistributionsTransformGround computeDerivatives_seg -DREF_GROUND libndt_ground_ref.so
 fi

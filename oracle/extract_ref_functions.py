@@ -1,18 +1,18 @@
 """ORACLE build step — test infrastructure only.
 
-Writes the definitions of named member functions of pclomp::NormalDistributionsTransform, exactly as they stand in the reference's
-include/ndt_omp/ndt_omp_impl2.hpp, to a temporary include file that oracle/ndt_ref_harness.cpp compiles (oracle/build_ref.sh).  Nothing is
+Writes the definitions of named member functions of a registration class (pclomp:: / pclpca::NormalDistributionsTransform,
+pclomp_ground::NormalDistributionsTransformGround), exactly as they stand in the reference's *_impl2.hpp / ndt_ground_impl.hpp, to a temporary include file that oracle/ndt_ref_harness.cpp compiles (oracle/build_ref.sh).  Nothing is
 written into the repository: the output path is a temporary directory of the build.
 
-usage: extract_ref_functions.py <ndt_omp_impl2.hpp> <out.inc> name [name ...]
+usage: extract_ref_functions.py <impl.hpp> <out.inc> <qualified class, e.g. pclomp::NormalDistributionsTransform> name [name ...]
 """
 import re
 import sys
 
 
-def extract(text, name):
+def extract(text, cls, name):
     out = []
-    pat = re.compile(r"pclomp::NormalDistributionsTransform<PointSource, PointTarget>::" + re.escape(name) + r"\s*\(")
+    pat = re.compile(re.escape(cls) + r"<PointSource, PointTarget>::" + re.escape(name) + r"\s*\(")
     for m in pat.finditer(text):
         start = text.rfind("template", 0, m.start())
         brace = text.index("{", m.end())
@@ -33,11 +33,11 @@ def extract(text, name):
 
 
 def main():
-    src, dst, names = sys.argv[1], sys.argv[2], sys.argv[3:]
+    src, dst, cls, names = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4:]
     text = open(src, encoding="utf-8", errors="replace").read()
     with open(dst, "w", encoding="utf-8") as f:
         for n in names:
-            for body in extract(text, n):
+            for body in extract(text, cls, n):
                 f.write("// ---- %s, from %s\n%s\n\n" % (n, src, body))
 
 

@@ -727,6 +727,14 @@ void ondt_get_leaf_angles(void* h, double* angle2xy) {
   for (auto& kv : n.leaves) { angle2xy[k++] = kv.second.in_centroid_cloud ? leaf_angle2xy(kv.second) : -1.0; }
 }
 
+// Eigenvectors of every occupied cell (ascending key order), row-major, columns in the order of the eigenvalues; identity for leaves
+// below min_points_per_voxel (the Leaf constructor's value, voxel_grid_covariance_omp.h:103).
+void ondt_get_leaf_evecs(void* h, double* evecs9) {
+  NDT& n = *(NDT*)h;
+  size_t k = 0;
+  for (auto& kv : n.leaves) { for (int i = 0; i < 9; i++) evecs9[k * 9 + i] = kv.second.evecs[i / 3][i % 3]; k++; }
+}
+
 // Voxel key the lookup path computes for each (already transformed) point, or -1 when outside the box.
 void ondt_lookup_keys(void* h, const float* xyz, size_t npts, size_t stride_floats, int32_t* keys) {
   NDT& n = *(NDT*)h;

@@ -4,7 +4,10 @@
 //   computeTransformation, computeDerivatives, computePointDerivatives_AngleAxisd (float and double), updateDerivatives, computeHessian,
 //   updateHessian, updateIntervalMT, trialValueSelectionMT, computeStepLengthMT, calculateScore
 // exactly as they stand in /root/reference/include/ndt_omp/ndt_omp_impl2.hpp into a temporary file (REF_NDT_BODIES) and compiles them here,
-// together with the reference's own Sophus (so3.cpp / se3.cpp from the vendored zip), into oracle/_ref/libndt_ref.so.  What those definitions
+// together with the reference's own Sophus (so3.cpp / se3.cpp from the vendored zip), into oracle/_ref/libndt_ref.so.  The same source
+// builds two more libraries: -DREF_PCA takes the functions of pclpca::NormalDistributionsTransform from include/ndt_pca/ndt_pca_impl2.hpp
+// (libndt_pca_ref.so), -DREF_GROUND those of pclomp_ground::NormalDistributionsTransformGround from include/ndt_omp/ndt_ground_impl.hpp,
+// computeDerivatives_seg instead of computeDerivatives (libndt_ground_ref.so).  What those definitions
 // need from outside is provided by stand-ins written in this repository, because PCL and Eigen are not in the image:
 //   * oracle/ref_stubs/eigen_min.h       the Eigen operations they use (interface only; evaluation orders as the restatement assumes them)
 //   * the class below                    the member DECLARATIONS of include/ndt_omp/ndt_omp.h:69-551 and of pcl::Registration that the bodies
@@ -51,7 +54,18 @@ void transformPointCloud(const PointCloud<P>& in, PointCloud<P>& out, const Eige
 }
 }  // namespace pcl
 
-namespace pclomp {
+#if defined(REF_PCA)
+#define REF_NS pclpca
+#define REF_CLASS NormalDistributionsTransform
+#elif defined(REF_GROUND)
+#define REF_NS pclomp_ground
+#define REF_CLASS NormalDistributionsTransformGround
+#else
+#define REF_NS pclomp
+#define REF_CLASS NormalDistributionsTransform
+#endif
+
+namespace REF_NS {
 
 enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };     // ndt_omp.h:61
 
@@ -61,8 +75,14 @@ struct RefLeaf {          // what the bodies read of VoxelGridCovariance::Leaf
   Eigen::Vector3d mean_;
   Eigen::Matrix3d icov_;
   float centroid[3];
+  int weight_;            // pclpca: what `int getDimension2d()` returns (voxel_grid_covariance_pca.h:222-226)
+  Eigen::Matrix3d evecs_; // pclomp_ground reads the leaf normal from these (ndt_ground_impl.hpp:507-511)
+  Eigen::Vector3d evals_;
   Eigen::Vector3d getMean() const { return mean_; }
   Eigen::Matrix3d getInverseCov() const { return icov_; }
+  int getDimension2d() const { return weight_; }
+  Eigen::Matrix3d getEvecs() const { return evecs_; }
+  Eigen::Vector3d getEvals() const { return evals_; }
 };
 
 // Stand-in for pclomp::VoxelGridCovariance<PointT>: cells handed in by the caller, searches as voxel_grid_covariance_omp_impl.hpp:373-442
@@ -144,7 +164,7 @@ class VoxelGridAdapter {
 // The declarations of include/ndt_omp/ndt_omp.h (class pclomp::NormalDistributionsTransform, :69-551) and of pcl::Registration that the
 // extracted definitions refer to - same names, types, default arguments and constness.
 template <typename PointSource, typename PointTarget>
-class NormalDistributionsTransform {
+class REF_CLASS {
  public:
   typedef pcl::PointCloud<PointSource> PointCloudSource;
   typedef pcl::PointCloud<PointTarget> PointCloudTarget;
@@ -166,7 +186,7 @@ class NormalDistributionsTransform {
   NeighborSearchMethod search_method = DIRECT7;
   int num_threads_ = 1;
 
-  NormalDistributionsTransform() { final_transformation_.setIdentity(); transformation_.setIdentity(); previous_transformation_.setIdentity(); }
+  REF_CLASS() { final_transformation_.setIdentity(); transformation_.setIdentity(); previous_transformation_.setIdentity(); }
 
   double calculateScore(const PointCloudSource& cloud) const;
   void computeTransformation(PointCloudSource& output, const Eigen::Matrix4f& guess);
@@ -183,20 +203,29 @@ class NormalDistributionsTransform {
   void computeHessian(Eigen::Matrix<double, 6, 6>& hessian, PointCloudSource& trans_cloud, Eigen::Matrix<double, 6, 1>& p);
   void updateHessian(Eigen::Matrix<double, 6, 6>& hessian, const Eigen::Matrix<double, 3, 6>& point_gradient_, const Eigen::Matrix<double, 18, 6>& point_hessian_,
                      const Eigen::Vector3d& x_trans, const Eigen::Matrix3d& c_inv) const;
+#ifdef REF_GROUND      // ndt_ground.h:303-309, :419-428
+  double computeDerivatives_seg(Eigen::Matrix<double, 6, 1>& score_gradient, Eigen::Matrix<double, 6, 6>& hessian, PointCloudSource& trans_cloud,
+                                Eigen::Matrix<double, 6, 1>& p, int flag_class, bool compute_hessian = true);
+  double computeStepLengthMT(const Eigen::Matrix<double, 6, 1>& x, Eigen::Matrix<double, 6, 1>& step_dir, double step_init, double step_max, double step_min,
+                             double& score, Eigen::Matrix<double, 6, 1>& score_gradient, Eigen::Matrix<double, 6, 6>& hessian, PointCloudSource& trans_cloud,
+                             int flag_class);
+#else
   double computeStepLengthMT(const Eigen::Matrix<double, 6, 1>& x, Eigen::Matrix<double, 6, 1>& step_dir, double step_init, double step_max, double step_min,
                              double& score, Eigen::Matrix<double, 6, 1>& score_gradient, Eigen::Matrix<double, 6, 6>& hessian, PointCloudSource& trans_cloud);
+#endif
   bool updateIntervalMT(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t, double g_t);
   double trialValueSelectionMT(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t);
   inline double auxilaryFunction_PsiMT(double a, double f_a, double f_0, double g_0, double mu = 1.e-4) { return (f_a - f_0 - mu * g_0 * a); }    // ndt_omp.h:479-483
   inline double auxilaryFunction_dPsiMT(double g_a, double g_0, double mu = 1.e-4) { return (g_a - mu * g_0); }                                  // ndt_omp.h:492-496
 };
 
-}  // namespace pclomp
+}  // namespace REF_NS
 
 #include REF_NDT_BODIES      // the reference's own definitions of the member functions declared above
 
 // ---------------------------------------------------------------------------------------------------------------------
-typedef pclomp::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> RefNDT;
+typedef REF_NS::REF_CLASS<pcl::PointXYZ, pcl::PointXYZ> RefNDT;
+using REF_NS::RefLeaf;
 struct RefHandle {
   RefNDT ndt;
   pcl::PointCloud<pcl::PointXYZ> source, target;
@@ -227,14 +256,15 @@ void nref_destroy(void* h) { delete (RefHandle*)h; }
 void nref_set_params(void* h, float resolution, double step_size, double outlier_ratio, double trans_eps, int max_iter, int search) {
   RefNDT& n = ((RefHandle*)h)->ndt;
   n.resolution_ = resolution; n.step_size_ = step_size; n.outlier_ratio_ = outlier_ratio; n.transformation_epsilon_ = trans_eps;
-  n.max_iterations_ = max_iter; n.search_method = (pclomp::NeighborSearchMethod)search;
+  n.max_iterations_ = max_iter; n.search_method = (REF_NS::NeighborSearchMethod)search;
   gauss(n);
 }
 
 // The target's cells, as the caller's voxel build produced them (ascending key): raw point count (-1 = invalidated), mean, inverse covariance,
 // float centroid, membership of the centroid cloud; plus the grid geometry.
 void nref_set_target_cells(void* h, int n_cells, const int32_t* keys, const int32_t* nr_points, const double* mean3, const double* icov9, const float* centroid3,
-                           const int32_t* in_cloud, const int32_t* min_b, const int32_t* max_b, const int32_t* div_b, float leaf_size, int min_points) {
+                           const int32_t* in_cloud, const int32_t* min_b, const int32_t* max_b, const int32_t* div_b, float leaf_size, int min_points,
+                           const int32_t* weight, const double* evecs9, const double* evals3) {
   RefHandle& H = *(RefHandle*)h;
   auto& G = H.ndt.target_cells_;
   G.leaves_.clear();
@@ -242,8 +272,10 @@ void nref_set_target_cells(void* h, int n_cells, const int32_t* keys, const int3
   G.divb_mul_[0] = 1; G.divb_mul_[1] = div_b[0]; G.divb_mul_[2] = div_b[0] * div_b[1];
   G.leaf_size_ = leaf_size; G.min_points_per_voxel_ = min_points;
   for (int k = 0; k < n_cells; k++) {
-    pclomp::RefLeaf l;
+    RefLeaf l;
     l.nr_points = nr_points[k]; l.in_cloud = in_cloud[k];
+    l.weight_ = weight ? weight[k] : 1;
+    for (int i = 0; i < 3; i++) { l.evals_[i] = evals3 ? evals3[k * 3 + i] : 0.0; for (int j = 0; j < 3; j++) l.evecs_(i, j) = evecs9 ? evecs9[k * 9 + i * 3 + j] : (i == j ? 1.0 : 0.0); }
     for (int i = 0; i < 3; i++) { l.mean_[i] = mean3[k * 3 + i]; l.centroid[i] = centroid3[k * 3 + i]; }
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) l.icov_(i, j) = icov9[k * 9 + i * 3 + j];
     G.leaves_[(size_t)keys[k]] = l;
@@ -267,7 +299,11 @@ double nref_eval_derivatives(void* h, const double* p6, const float* T16, int co
   pcl::PointCloud<pcl::PointXYZ> trans;
   pcl::transformPointCloud(H.source, trans, T);
   Eigen::Matrix<double, 6, 6> Hm;
+#ifdef REF_GROUND
+  const double s = H.ndt.computeDerivatives_seg(g, Hm, trans, p, 1, compute_hessian != 0);      // flag_class = 1, as computeTransformation calls it (:131-133)
+#else
   const double s = H.ndt.computeDerivatives(g, Hm, trans, p, compute_hessian != 0);
+#endif
   for (int i = 0; i < 6; i++) { g6[i] = g[i]; for (int j = 0; j < 6; j++) H36[i * 6 + j] = Hm(i, j); }
   return s;
 }

@@ -65,6 +65,23 @@ class DynBlockCast {
   const Matrix<S, R, C>& m_;
   int r0_, c0_, nr_, nc_;
 };
+// m.block(r0, c0, nr, nc) of a non-const matrix (run-time sizes): assignable from a fixed-size matrix of that shape, setZero()
+template <typename S, int R, int C>
+class DynBlockRef {
+ public:
+  DynBlockRef(Matrix<S, R, C>& m, int r0, int c0, int nr, int nc) : m_(m), r0_(r0), c0_(c0), nr_(nr), nc_(nc) { assert(r0 >= 0 && c0 >= 0 && r0 + nr <= R && c0 + nc <= C); }
+  template <int RB, int CB>
+  DynBlockRef& operator=(const Matrix<S, RB, CB>& v) {
+    assert(RB == nr_ && CB == nc_);
+    for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) m_(r0_ + r, c0_ + c) = v(r, c);
+    return *this;
+  }
+  void setZero() { for (int r = 0; r < nr_; r++) for (int c = 0; c < nc_; c++) m_(r0_ + r, c0_ + c) = S(0); }
+
+ private:
+  Matrix<S, R, C>& m_;
+  int r0_, c0_, nr_, nc_;
+};
 template <typename S, int R, int C>
 class DynBlock {
  public:
@@ -232,7 +249,7 @@ class Matrix {
   template <int RB, int CB> BlockRef<S, R, C, RB, CB> topLeftCorner() { return BlockRef<S, R, C, RB, CB>(*this, 0, 0); }
   template <int RB, int CB> BlockRef<S, R, C, RB, CB> topRightCorner() { return BlockRef<S, R, C, RB, CB>(*this, 0, C - CB); }
   template <int RB, int CB> BlockRef<S, R, C, RB, CB> bottomRightCorner() { return BlockRef<S, R, C, RB, CB>(*this, R - RB, C - CB); }
-  BlockRef<S, R, C, 3, 3> block(int r0, int c0, int nr, int nc) { assert(nr == 3 && nc == 3); (void)nr; (void)nc; return BlockRef<S, R, C, 3, 3>(*this, r0, c0); }
+  DynBlockRef<S, R, C> block(int r0, int c0, int nr, int nc) { return DynBlockRef<S, R, C>(*this, r0, c0, nr, nc); }
   DynBlock<S, R, C> block(int r0, int c0, int nr, int nc) const { return DynBlock<S, R, C>(*this, r0, c0, nr, nc); }
   BlockRef<S, R, C, 3, 3> topLeftCorner(int nr, int nc) { assert(nr == 3 && nc == 3); (void)nr; (void)nc; return BlockRef<S, R, C, 3, 3>(*this, 0, 0); }
   template <int RB, int CB> Matrix<S, RB, CB> block(int r0, int c0) const { return sub<RB, CB>(r0, c0); }

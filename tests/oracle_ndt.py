@@ -41,6 +41,7 @@ def lib():
         L.ondt_num_leaves.restype = i32; L.ondt_num_leaves.argtypes = [vp]
         L.ondt_get_leaves.restype = None; L.ondt_get_leaves.argtypes = [vp] * 12
         L.ondt_get_leaf_angles.restype = None; L.ondt_get_leaf_angles.argtypes = [vp, vp]
+        L.ondt_get_leaf_evecs.restype = None; L.ondt_get_leaf_evecs.argtypes = [vp, vp]
         L.ondt_lookup_keys.restype = None; L.ondt_lookup_keys.argtypes = [vp, vp, sz, sz, vp]
         L.ondt_transform.restype = None; L.ondt_transform.argtypes = [vp, sz, sz, vp, vp]
         L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -136,6 +137,12 @@ class OracleNDT:
         """pclomp_ground: angle of every occupied cell's normal to the z axis [deg], -1 without an eigen-decomposition."""
         out = np.zeros(self.L.ondt_num_leaves(self.h))
         self.L.ondt_get_leaf_angles(self.h, out.ctypes.data)
+        return out
+
+    def leaf_evecs(self):
+        """Eigenvectors of every occupied cell [n, 3, 3] (columns in eigenvalue order); identity below min_points_per_voxel."""
+        out = np.zeros((self.L.ondt_num_leaves(self.h), 3, 3))
+        self.L.ondt_get_leaf_evecs(self.h, out.ctypes.data)
         return out
 
     def lookup_keys(self, xyz):
@@ -280,15 +287,16 @@ def sophus_ref():
     return _sref
 
 
-_nref = False
+_nref = {}
+_NREF_SO = {VAR_OMP: "libndt_ref.so", VAR_PCA: "libndt_pca_ref.so", VAR_GROUND: "libndt_ground_ref.so"}
 
 
-def ndt_ref_lib():
-    """oracle/_ref/libndt_ref.so: the reference's OWN member functions of pclomp::NormalDistributionsTransform (taken from ndt_omp_impl2.hpp at
-    build time) compiled in oracle/ndt_ref_harness.cpp.  None where neither the library nor the reference tree is present."""
-    global _nref
-    if _nref is False:
-        so = os.path.join(_ODIR, "_ref", "libndt_ref.so")
+def ndt_ref_lib(variant=VAR_OMP):
+    """oracle/_ref/libndt{,_pca,_ground}_ref.so: the reference's OWN member functions of pclomp:: / pclpca::NormalDistributionsTransform /
+    pclomp_ground::NormalDistributionsTransformGround (taken from ndt_omp_impl2.hpp / ndt_pca_impl2.hpp / ndt_ground_impl.hpp at build time)
+    compiled in oracle/ndt_ref_harness.cpp.  None where neither the library nor the reference tree is present."""
+    if variant not in _nref:
+        so = os.path.join(_ODIR, "_ref", _NREF_SO[variant])
         if not os.path.exists(so) and os.path.exists("/root/reference/include/ndt_omp/ndt_omp_impl2.hpp"):
             subprocess.call(["sh", os.path.join(_ODIR, "build_ref.sh")])
         if os.path.exists(so):
@@ -297,30 +305,32 @@ def ndt_ref_lib():
             L.nref_create.restype = vp; L.nref_create.argtypes = []
             L.nref_destroy.restype = None; L.nref_destroy.argtypes = [vp]
             L.nref_set_params.restype = None; L.nref_set_params.argtypes = [vp, f32, f64, f64, f64, i32, i32]
-            L.nref_set_target_cells.restype = None; L.nref_set_target_cells.argtypes = [vp, i32] + [vp] * 9 + [f32, i32]
+            L.nref_set_target_cells.restype = None; L.nref_set_target_cells.argtypes = [vp, i32] + [vp] * 9 + [f32, i32] + [vp] * 3
             L.nref_set_source.restype = None; L.nref_set_source.argtypes = [vp, vp, sz, sz]
             L.nref_eval_derivatives.restype = f64; L.nref_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
             L.nref_eval_hessian.restype = None; L.nref_eval_hessian.argtypes = [vp, vp, vp, vp]
             L.nref_calculate_score.restype = f64; L.nref_calculate_score.argtypes = [vp, vp]
             L.nref_align.restype = i32; L.nref_align.argtypes = [vp, vp, vp, vp, vp, vp]
-            _nref = L
+            _nref[variant] = L
         else:
-            _nref = None
-    return _nref
+            _nref[variant] = None
+    return _nref[variant]
 
 
 class ReferenceNDT:
     """The reference's own computeTransformation / computeDerivatives / ... (oracle/ndt_ref_harness.cpp) on the voxel cells of an OracleNDT."""
 
     def __init__(self, oracle):
-        self.L = ndt_ref_lib()
+        self.L = ndt_ref_lib(oracle.variant)
         self.h = self.L.nref_create()
         p = oracle.params
         self.L.nref_set_params(self.h, p["resolution"], p["step_size"], p["outlier_ratio"], p["trans_eps"], p["max_iter"], p["search"])
         lv = oracle.leaves()
         mn, mx, dv = oracle.grid()
         self._keep = [np.ascontiguousarray(lv[k]) for k in ("keys", "nr_points", "mean", "icov", "centroid", "in_cloud")] + [mn, mx, dv]
-        self.L.nref_set_target_cells(self.h, len(lv["keys"]), *[a.ctypes.data for a in self._keep], p["resolution"], 6)
+        extra = [np.ascontiguousarray(lv["weight"]), np.ascontiguousarray(oracle.leaf_evecs()), np.ascontiguousarray(lv["evals"])]
+        self.L.nref_set_target_cells(self.h, len(lv["keys"]), *[a.ctypes.data for a in self._keep], p["resolution"], 6, *[a.ctypes.data for a in extra])
+        self._keep += extra
 
     def __del__(self):
         try:

@@ -126,6 +126,44 @@ def test_restatement_against_the_reference_member_functions(small_pair, search):
             assert np.array_equal(a2["final"], b2["final"]) and a2["trans_probability"] == b2["trans_probability"] and np.array_equal(a2["cloud"], b2["cloud"])
 
 
+@pytest.mark.parametrize("variant,search,kw", [(O.VAR_PCA, O.DIRECT1, {}), (O.VAR_PCA, O.DIRECT7, {}), (O.VAR_PCA, O.KDTREE, {}),
+                                               (O.VAR_GROUND, O.DIRECT1, dict(resolution=2.0)), (O.VAR_GROUND, O.DIRECT7, dict(resolution=2.0)),
+                                               (O.VAR_GROUND, O.DIRECT26, {}), (O.VAR_GROUND, O.KDTREE, dict(resolution=2.0)),
+                                               (O.VAR_GROUND, O.DIRECT1, dict(resolution=10.0, max_iter=64))])
+def test_pca_and_ground_restatements_against_the_reference_member_functions(small_pair, variant, search, kw):
+    """The same pin for the two other registration classes: pclpca (include/ndt_pca/ndt_pca_impl2.hpp: the per-cell weight on the running
+    sums) and pclomp_ground (include/ndt_omp/ndt_ground_impl.hpp: computeDerivatives_seg with flag_class = 1 - the double updateDerivatives call,
+    the last-neighbour gate on the leaf normal, the zeroed rows and columns - and its computeTransformation without the first-iteration
+    clause).  The per-cell weights and eigenvectors handed to the reference's code are the restatement's."""
+    if O.ndt_ref_lib(variant) is None:
+        pytest.skip("no compiled reference NDT")
+    tgt, src, guess, truth = small_pair
+    prm = dict(trans_eps=0.01, max_iter=30)
+    prm.update(kw)
+    o = O.OracleNDT(variant=variant, search=search, num_threads=1, **prm)
+    o.set_target(tgt); o.set_source(src)
+    r = O.ReferenceNDT(o); r.set_source(src)
+    rng = np.random.default_rng(22)
+    p0 = O.se3_log_from_matrix4f(guess)
+    for k in range(3):
+        p = p0 if k == 0 else p0 + rng.normal(0, [0.05, 0.05, 0.02, 0.004, 0.004, 0.01])
+        T = guess if k == 0 else None
+        for hess in (True, False):
+            so, go, Ho = o.eval_derivatives(p, T, hess)
+            sr, gr, Hr = r.eval_derivatives(p, T, hess)
+            assert abs(so) > 10 and so == sr and np.array_equal(go, gr) and np.array_equal(Ho, Hr), (k, hess)
+    ao, ar = o.align(guess, want_cloud=True), r.align(guess)
+    assert ao["iterations"] == ar["iterations"] >= 1 and ao["converged"] == ar["converged"]
+    assert np.array_equal(ao["final"], ar["final"]) and ao["trans_probability"] == ar["trans_probability"] and np.array_equal(ao["cloud"], ar["cloud"])
+    # forced More-Thuente path (for pclomp_ground: computeStepLengthMT with flag_class, then the unmasked computeHessian)
+    o2 = O.OracleNDT(variant=variant, search=search, num_threads=1, step_size=0.2, trans_eps=0.5, max_iter=4, resolution=prm.get("resolution", 1.0))
+    o2.set_target(tgt); o2.set_source(src)
+    r2 = O.ReferenceNDT(o2); r2.set_source(src)
+    a2, b2 = o2.align(truth.astype(np.float32), want_cloud=True), r2.align(truth.astype(np.float32))
+    assert a2["iterations"] == b2["iterations"] and a2["converged"] == b2["converged"] and np.array_equal(a2["final"], b2["final"])
+    assert a2["trans_probability"] == b2["trans_probability"] and np.array_equal(a2["cloud"], b2["cloud"])
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
