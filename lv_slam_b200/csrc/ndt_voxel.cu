@@ -396,7 +396,9 @@ __global__ void __launch_bounds__(kMomWarps * 32) leaf_moments_kernel(VoxBatch B
   for (int seg = blockIdx.x * kMomWarps + warp; seg < n_seg; seg += warps_total) {
     const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
     const int n_chunks = (s1 - s0 + 31) >> 5;
-    double acc = 0.0;
+    // Leaf::cov_ starts as the IDENTITY (voxel_grid_covariance_omp.h:98-106) and applyFilter adds the point products on top of it (:240,:285):
+    // the xx, yy, zz chains start at 1.0, so every covariance carries + I (n - 1) / n^2 like the reference's
+    double acc = (dcol == 3 || dcol == 6 || dcol == 8) ? 1.0 : 0.0;
     float facc = 0.0f;
     // software pipeline: while chunk c is summed, the points of chunks c+1..c+3 and the index of chunk c+4 are already in
     // registers or in flight (a gather is ~2 dependent L2 round trips, one chunk's chain only ~300 cycles)

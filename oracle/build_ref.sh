@@ -15,7 +15,8 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ -f "$OUT/libndt_ref.so" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/ndt_ref_harness.cpp" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/ref_stubs/eigen_min.h" ] &&
    [ "$OUT/libndt_ref.so" -nt "$HERE/extract_ref_functions.py" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/olin.h" ] &&
    [ -f "$OUT/libndt_pca_ref.so" ] && [ "$OUT/libndt_pca_ref.so" -nt "$OUT/libndt_ref.so" ] &&
-   [ -f "$OUT/libndt_ground_ref.so" ] && [ "$OUT/libndt_ground_ref.so" -nt "$OUT/libndt_ref.so" ]; then exit 0; fi
+   [ -f "$OUT/libndt_ground_ref.so" ] && [ "$OUT/libndt_ground_ref.so" -nt "$OUT/libndt_ref.so" ] &&
+   [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -58,4 +59,14 @@ PY
   build_ndt "$INC/ndt_omp/ndt_omp_impl2.hpp" pclomp::NormalDistributionsTransform computeDerivatives "" libndt_ref.so
   build_ndt "$INC/ndt_pca/ndt_pca_impl2.hpp" pclpca::NormalDistributionsTransform computeDerivatives -DREF_PCA libndt_pca_ref.so
   build_ndt "$INC/ndt_omp/ndt_ground_impl.hpp" pclomp_ground::NormalDistributionsTransformGround computeDerivatives_seg -DREF_GROUND libndt_ground_ref.so
+  # The voxel build and the direct searches: VoxelGridCovariance<PointT>::applyFilter / getNeighborhoodAtPoint{,7,1}, taken the same way from
+  # voxel_grid_covariance_omp_impl.hpp and compiled in oracle/voxel_ref_harness.cpp (class declaration incl. the Leaf constructor's values).
+  VIMPL="$INC/ndt_omp/voxel_grid_covariance_omp_impl.hpp"
+  if [ -f "$VIMPL" ]; then
+    python3 "$HERE/extract_ref_functions.py" "$VIMPL" "$TMP/voxel_bodies.inc" "pclomp::VoxelGridCovariance<PointT>" applyFilter getNeighborhoodAtPoint \
+        getNeighborhoodAtPoint7 getNeighborhoodAtPoint1
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DREF_VOXEL_BODIES="\"$TMP/voxel_bodies.inc\"" -I"$HERE/ref_stubs" -o "$OUT/libvoxel_ref.so" \
+        "$HERE/voxel_ref_harness.cpp"
+    echo "built $OUT/libvoxel_ref.so"
+  fi
 fi

@@ -12,7 +12,8 @@ import sys
 
 def extract(text, cls, name):
     out = []
-    pat = re.compile(re.escape(cls) + r"<PointSource, PointTarget>::" + re.escape(name) + r"\s*\(")
+    prefix = cls if "<" in cls else cls + "<PointSource, PointTarget>"
+    pat = re.compile(re.escape(prefix) + r"::" + re.escape(name) + r"\s*\(")
     for m in pat.finditer(text):
         start = text.rfind("template", 0, m.start())
         brace = text.index("{", m.end())

@@ -75,7 +75,8 @@ enum Variant { VAR_OMP = 0, VAR_PCA = 1, VAR_GROUND = 2 };
 struct Leaf {                       // voxel_grid_covariance_omp.h:92-195
   int nr_points = 0;
   double mean[3] = {0, 0, 0};
-  double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double cov[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};   // the Leaf constructor starts cov_ at the IDENTITY (voxel_grid_covariance_omp.h:98-106) and applyFilter
+                                                           // adds the point products on top of it (:240,:285): every covariance carries + I (n - 1) / n^2
   double icov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double evecs[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   double evals[3] = {0, 0, 0};
@@ -733,6 +734,20 @@ void ondt_get_leaf_evecs(void* h, double* evecs9) {
   NDT& n = *(NDT*)h;
   size_t k = 0;
   for (auto& kv : n.leaves) { for (int i = 0; i < 9; i++) evecs9[k * 9 + i] = kv.second.evecs[i / 3][i % 3]; k++; }
+}
+
+// Keys of the cells a direct search returns for one point, in the order they are pushed.  mode: DIRECT26 / DIRECT7 / DIRECT1.
+int ondt_neighbours(void* h, const float* xyz3, int mode, int32_t* keys_out /* >= 26 */) {
+  NDT& n = *(NDT*)h;
+  Pt p = {xyz3[0], xyz3[1], xyz3[2]};
+  std::vector<const Leaf*> nb;
+  neighbours_direct(n, p, mode, nb);
+  for (size_t i = 0; i < nb.size(); i++) {
+    int32_t key = -1;
+    for (auto& kv : n.leaves) if (&kv.second == nb[i]) { key = (int32_t)kv.first; break; }
+    keys_out[i] = key;
+  }
+  return (int)nb.size();
 }
 
 // Voxel key the lookup path computes for each (already transformed) point, or -1 when outside the box.

@@ -15,6 +15,7 @@
 #include <cstddef>
 #include <memory>
 #include <type_traits>
+#include <vector>
 #include <ostream>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
@@ -150,6 +151,7 @@ class CommaInit {
  public:
   CommaInit(Matrix<S, R, C>& m, S first) : m_(m), k_(0) { put(first); }
   CommaInit& operator,(S v) { put(v); return *this; }
+  Matrix<S, R, C> finished() const { return m_; }
   ~CommaInit() { assert(k_ == R * C); }
 
  private:
@@ -238,6 +240,21 @@ class Matrix {
     return m;
   }
 
+  template <int C2>
+  Matrix<S, R, C2> operator*(const Transposed<S, C, C2>& t) const { return (*this) * t.eval(); }     // column x row^T: outer product (one product per coefficient)
+  template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
+  Matrix& operator/=(T s) { for (int i = 0; i < R * C; i++) d_[i] /= static_cast<S>(s); return *this; }
+  static Matrix Ones() { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = S(1); return m; }
+  const Matrix& array() const { return *this; }                           // coefficient-wise view: the comparisons below
+  struct BoolArray { bool b[R * C]; bool all() const { for (int i = 0; i < R * C; i++) if (!b[i]) return false; return true; } };
+  BoolArray operator<=(const Matrix& o) const { BoolArray r; for (int i = 0; i < R * C; i++) r.b[i] = d_[i] <= o.d_[i]; return r; }
+  BoolArray operator>=(const Matrix& o) const { BoolArray r; for (int i = 0; i < R * C; i++) r.b[i] = d_[i] >= o.d_[i]; return r; }
+  Matrix<S, R, 1> diagonal() const { static_assert(R == C, "diagonal"); Matrix<S, R, 1> v; for (int i = 0; i < R; i++) v(i) = (*this)(i, i); return v; }
+  Matrix<S, R, R> asDiagonal() const { static_assert(C == 1, "asDiagonal"); Matrix<S, R, R> m; m.setZero(); for (int i = 0; i < R; i++) m(i, i) = d_[i]; return m; }
+  S maxCoeff() const { S v = d_[0]; for (int i = 1; i < R * C; i++) if (d_[i] > v) v = d_[i]; return v; }
+  S minCoeff() const { S v = d_[0]; for (int i = 1; i < R * C; i++) if (d_[i] < v) v = d_[i]; return v; }
+  Matrix inverse() const;                                                  // 3 x 3 doubles only (defined after olin.h is included)
+
   // fixed-size views: a copy from a const object, a writable reference otherwise
   template <int N> Matrix<S, N, 1> head() const { static_assert(C == 1, "head"); return sub<N, 1>(0, 0); }
   template <int N> Matrix<S, N, 1> tail() const { static_assert(C == 1, "tail"); return sub<N, 1>(R - N, 0); }
@@ -267,8 +284,10 @@ class Matrix {
   S d_[R * C];
 };
 
-template <typename S, int R, int C>
-inline Matrix<S, R, C> operator*(S s, const Matrix<S, R, C>& m) { Matrix<S, R, C> o; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) o(r, c) = s * m(r, c); return o; }
+template <typename T, typename S, int R, int C, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
+inline Matrix<S, R, C> operator*(T s, const Matrix<S, R, C>& m) { Matrix<S, R, C> o; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) o(r, c) = static_cast<S>(s) * m(r, c); return o; }
+template <typename T, typename S, int R, int C, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
+inline Matrix<S, R, C> operator/(const Matrix<S, R, C>& m, T s) { Matrix<S, R, C> o; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) o(r, c) = m(r, c) / static_cast<S>(s); return o; }
 
 // the inline stream operators of so3.h / se3.h (never called by the checker)
 template <typename S, int R, int C>
@@ -358,6 +377,55 @@ class Quaternion {
 };
 typedef Quaternion<double> Quaterniond;
 
+typedef Matrix<int, 4, 1> Vector4i;
+typedef Matrix<int, 4, 1> Array4i;          // only constructed from a Vector4i and compared coefficient-wise
+
+// Eigen::VectorXf as VoxelGridCovariance::Leaf::centroid uses it
+class VectorXf {
+ public:
+  VectorXf() {}
+  static VectorXf Zero(int n) { VectorXf v; v.d_.assign((size_t)n, 0.0f); return v; }
+  void resize(int n) { d_.resize((size_t)n); }
+  void setZero() { for (size_t i = 0; i < d_.size(); i++) d_[i] = 0.0f; }
+  float& operator[](int i) { return d_[(size_t)i]; }
+  const float& operator[](int i) const { return d_[(size_t)i]; }
+  VectorXf& operator+=(const VectorXf& o) { assert(o.d_.size() == d_.size()); for (size_t i = 0; i < d_.size(); i++) d_[i] += o.d_[i]; return *this; }
+  VectorXf& operator/=(float s) { for (size_t i = 0; i < d_.size(); i++) d_[i] /= s; return *this; }
+  struct Head4 { VectorXf& v; Head4& operator+=(const Matrix<float, 4, 1>& p) { for (int i = 0; i < 4; i++) v.d_[(size_t)i] += p(i); return *this; } };
+  template <int N> Head4 head() { static_assert(N == 4, "head<4>"); assert(d_.size() >= 4); return Head4{*this}; }
+  int size() const { return (int)d_.size(); }
+
+ private:
+  std::vector<float> d_;
+};
+
+// Eigen::MatrixXi as the neighbour-offset tables use it (3 x n)
+class MatrixXi {
+ public:
+  struct Col3 { int v[3]; };
+  MatrixXi() : r_(0), c_(0) {}
+  MatrixXi(int r, int c) : r_(r), c_(c), d_((size_t)r * c) {}
+  static MatrixXi Zero(int r, int c) { MatrixXi m(r, c); m.setZero(); return m; }
+  void setZero() { for (size_t i = 0; i < d_.size(); i++) d_[i] = 0; }
+  int rows() const { return r_; }
+  int cols() const { return c_; }
+  int& operator()(int r, int c) { return d_[(size_t)c * r_ + r]; }
+  int operator()(int r, int c) const { return d_[(size_t)c * r_ + r]; }
+  Col3 col(int c) const { assert(r_ == 3); Col3 o; for (int r = 0; r < 3; r++) o.v[r] = (*this)(r, c); return o; }
+
+ private:
+  int r_, c_;
+  std::vector<int> d_;
+};
+// (Eigen::Vector4i () << relative_coordinates.col (ni), 0).finished ()
+struct CommaInit4i {
+  Matrix<int, 4, 1> m;
+  int k;
+  CommaInit4i& operator,(int v) { assert(k < 4); m(k++) = v; return *this; }
+  Matrix<int, 4, 1> finished() const { assert(k == 4); return m; }
+};
+inline CommaInit4i operator<<(Matrix<int, 4, 1> m, const MatrixXi::Col3& c) { CommaInit4i ci{m, 3}; for (int i = 0; i < 3; i++) ci.m(i) = c.v[i]; return ci; }
+
 template <typename T>
 using aligned_allocator = std::allocator<T>;
 
@@ -377,6 +445,39 @@ class Transform {
 #include "../olin.h"
 
 namespace Eigen {
+
+// Matrix3d::inverse(): Eigen's cofactor inverse of a 3 x 3, as oracle/olin.h restates it
+template <>
+inline Matrix<double, 3, 3> Matrix<double, 3, 3>::inverse() const {
+  olin::M3 a;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a.a[r][c] = (*this)(r, c);
+  const olin::M3 i = olin::m3_inverse(a);
+  Matrix<double, 3, 3> o;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o(r, c) = i.a[r][c];
+  return o;
+}
+
+// SelfAdjointEigenSolver<Matrix3d>: ascending eigenvalues, eigenvectors in columns - by the cyclic Jacobi iteration of oracle/olin.h (Eigen's
+// tridiagonal QL is not restated anywhere in this repository)
+template <typename M>
+class SelfAdjointEigenSolver;
+template <>
+class SelfAdjointEigenSolver<Matrix<double, 3, 3> > {
+ public:
+  void compute(const Matrix<double, 3, 3>& A) {
+    olin::M3 a, v;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a.a[r][c] = A(r, c);
+    double ev[3];
+    olin::sym3_eig(a, ev, v);
+    for (int r = 0; r < 3; r++) { vals_(r) = ev[r]; for (int c = 0; c < 3; c++) vecs_(r, c) = v.a[r][c]; }
+  }
+  const Matrix<double, 3, 1>& eigenvalues() const { return vals_; }
+  const Matrix<double, 3, 3>& eigenvectors() const { return vecs_; }
+
+ private:
+  Matrix<double, 3, 1> vals_;
+  Matrix<double, 3, 3> vecs_;
+};
 
 // JacobiSVD<Matrix<double, 6, 6>>(H, ComputeFullU | ComputeFullV).solve(b): the pseudo-inverse solve with Eigen's rank rule, carried out by the
 // one-sided Jacobi iteration of oracle/olin.h (Eigen's own two-sided sweep is not restated anywhere in this repository).

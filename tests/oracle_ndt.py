@@ -42,6 +42,7 @@ def lib():
         L.ondt_get_leaves.restype = None; L.ondt_get_leaves.argtypes = [vp] * 12
         L.ondt_get_leaf_angles.restype = None; L.ondt_get_leaf_angles.argtypes = [vp, vp]
         L.ondt_get_leaf_evecs.restype = None; L.ondt_get_leaf_evecs.argtypes = [vp, vp]
+        L.ondt_neighbours.restype = i32; L.ondt_neighbours.argtypes = [vp, vp, i32, vp]
         L.ondt_lookup_keys.restype = None; L.ondt_lookup_keys.argtypes = [vp, vp, sz, sz, vp]
         L.ondt_transform.restype = None; L.ondt_transform.argtypes = [vp, sz, sz, vp, vp]
         L.ondt_eval_derivatives.restype = f64; L.ondt_eval_derivatives.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -144,6 +145,13 @@ class OracleNDT:
         out = np.zeros((self.L.ondt_num_leaves(self.h), 3, 3))
         self.L.ondt_get_leaf_evecs(self.h, out.ctypes.data)
         return out
+
+    def neighbours(self, point, mode):
+        """keys of the cells the direct search `mode` returns for one point, in push order"""
+        p = np.ascontiguousarray(point[:3], dtype=np.float32)
+        out = np.zeros(26, np.int32)
+        n = self.L.ondt_neighbours(self.h, p.ctypes.data, int(mode), out.ctypes.data)
+        return out[:n].copy()
 
     def lookup_keys(self, xyz):
         a = _f32(xyz)
@@ -368,6 +376,65 @@ class ReferenceNDT:
         cloud = np.zeros((self.n_src, 3), np.float32)
         conv = self.L.nref_align(self.h, g.ctypes.data, fin.ctypes.data, ctypes.byref(it), ctypes.byref(tp), cloud.ctypes.data)
         return dict(final=_from_colmajor16(fin), iterations=it.value, converged=bool(conv), trans_probability=tp.value, cloud=cloud)
+
+
+_vref = False
+
+
+class ReferenceVoxelGrid:
+    """The reference's own VoxelGridCovariance::applyFilter and getNeighborhoodAtPoint{,7,1} (oracle/voxel_ref_harness.cpp)."""
+
+    @staticmethod
+    def available():
+        global _vref
+        if _vref is False:
+            so = os.path.join(_ODIR, "_ref", "libvoxel_ref.so")
+            if not os.path.exists(so) and os.path.exists("/root/reference/include/ndt_omp/voxel_grid_covariance_omp_impl.hpp"):
+                subprocess.call(["sh", os.path.join(_ODIR, "build_ref.sh")])
+            if os.path.exists(so):
+                L = ctypes.CDLL(so)
+                vp = ctypes.c_void_p
+                L.vref_create.restype = vp; L.vref_create.argtypes = []
+                L.vref_destroy.restype = None; L.vref_destroy.argtypes = [vp]
+                L.vref_build.restype = ctypes.c_int; L.vref_build.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_double]
+                L.vref_get_grid.restype = None; L.vref_get_grid.argtypes = [vp] * 4
+                L.vref_get_leaves.restype = None; L.vref_get_leaves.argtypes = [vp] * 9
+                L.vref_neighbours.restype = ctypes.c_int; L.vref_neighbours.argtypes = [vp, vp, ctypes.c_int, vp]
+                _vref = L
+            else:
+                _vref = None
+        return _vref is not None
+
+    def __init__(self, xyz, leaf=1.0, min_points=6, eig_mult=0.01):
+        assert self.available()
+        self.L = _vref
+        self.h = self.L.vref_create()
+        a = _f32(xyz)
+        self.n = self.L.vref_build(self.h, a.ctypes.data, a.shape[0], a.shape[1], leaf, min_points, eig_mult)
+
+    def __del__(self):
+        try:
+            self.L.vref_destroy(self.h)
+        except Exception:
+            pass
+
+    def grid(self):
+        mn, mx, dv = (np.zeros(3, np.int32) for _ in range(3))
+        self.L.vref_get_grid(self.h, mn.ctypes.data, mx.ctypes.data, dv.ctypes.data)
+        return mn, mx, dv
+
+    def leaves(self):
+        n = self.n
+        out = dict(keys=np.zeros(n, np.int32), nr_points=np.zeros(n, np.int32), mean=np.zeros((n, 3)), cov=np.zeros((n, 3, 3)), icov=np.zeros((n, 3, 3)),
+                   evecs=np.zeros((n, 3, 3)), evals=np.zeros((n, 3)), centroid=np.zeros((n, 3), np.float32))
+        self.L.vref_get_leaves(self.h, *[out[k].ctypes.data for k in ("keys", "nr_points", "mean", "cov", "icov", "evecs", "evals", "centroid")])
+        return out
+
+    def neighbours(self, point, mode):
+        p = np.ascontiguousarray(point[:3], dtype=np.float32)
+        out = np.zeros(26, np.int32)
+        n = self.L.vref_neighbours(self.h, p.ctypes.data, int(mode), out.ctypes.data)
+        return out[:n].copy()
 
 
 def svd6_solve(A, b):

@@ -164,6 +164,41 @@ def test_pca_and_ground_restatements_against_the_reference_member_functions(smal
     assert a2["trans_probability"] == b2["trans_probability"] and np.array_equal(a2["cloud"], b2["cloud"])
 
 
+@pytest.mark.parametrize("leaf", [1.0, 0.5, 2.0, 0.7])
+def test_voxel_build_against_the_reference_member_functions(small_pair, leaf):
+    """VoxelGridCovariance::applyFilter and getNeighborhoodAtPoint{,7,1}, taken verbatim from voxel_grid_covariance_omp_impl.hpp at build
+    time and compiled in oracle/voxel_ref_harness.cpp with the class declaration of voxel_grid_covariance_omp.h - in particular the Leaf
+    constructor that starts cov_ at the identity - against the restatement: grid geometry, keys, counts, float centroids, means,
+    covariances (after the eigenvalue inflation), inverse covariances, eigenvalues and eigenvectors of EVERY cell identical; NaN points
+    and a strided cloud included; the direct searches return the same cells in the same order."""
+    if not O.ReferenceVoxelGrid.available():
+        pytest.skip("no compiled reference voxel grid")
+    tgt = small_pair[0].copy()
+    tgt[::97, 1] = np.nan                                   # skipped by applyFilter (the is_dense = false branch)
+    cloud = np.zeros((len(tgt), 8), np.float32)
+    cloud[:, :3] = tgt
+    r = O.ReferenceVoxelGrid(cloud, leaf)
+    o = O.OracleNDT(search=O.DIRECT7, num_threads=1, resolution=leaf)
+    o.set_target(cloud)
+    assert [a.tolist() for a in r.grid()] == [a.tolist() for a in o.grid()]
+    rl, ol = r.leaves(), o.leaves()
+    for k in ("keys", "nr_points", "centroid", "mean", "cov", "icov", "evals"):
+        assert np.array_equal(rl[k], ol[k]), k
+    assert np.array_equal(rl["evecs"], o.leaf_evecs())
+    n6 = ol["nr_points"] == 6                                # the identity the sums start from: + (n - 1) / n^2 on the diagonal
+    assert n6.any() and (ol["cov"][n6][:, [0, 1, 2], [0, 1, 2]].min(axis=1) > 5 / 36 - 1e-9).all()
+    rng = np.random.default_rng(31)
+    pts = tgt[rng.integers(0, len(tgt), 300)] + rng.normal(0, 0.3, (300, 3)).astype(np.float32)
+    pts = pts[np.isfinite(pts).all(axis=1)]
+    for mode_o, mode_r in ((O.DIRECT26, 1), (O.DIRECT7, 2), (O.DIRECT1, 3)):
+        hits = 0
+        for p in pts:
+            a, b = o.neighbours(p, mode_o), r.neighbours(p, mode_r)
+            assert np.array_equal(a, b), (mode_o, p)
+            hits += len(a)
+        assert hits > 50
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
@@ -190,7 +225,8 @@ def test_small_dense_solvers_against_numpy():
 
 
 def test_single_voxel_hand_case():
-    """Eight points in one 1 m cell: mean, sample covariance with the (n-1)/n factor, eigenvalue inflation, inverse."""
+    """Eight points in one 1 m cell: mean, the one-pass covariance ON TOP OF THE IDENTITY the Leaf constructor starts cov_ with
+    (voxel_grid_covariance_omp.h:98-106; applyFilter :240,:329-330), the (n-1)/n factor, inverse; and a cell where the eigenvalue inflation fires."""
     pts = np.array([[0.2, 0.2, 0.5], [0.8, 0.2, 0.5], [0.2, 0.8, 0.5], [0.8, 0.8, 0.5], [0.5, 0.5, 0.5], [0.4, 0.6, 0.5], [0.6, 0.4, 0.5],
                     [0.5, 0.5, 0.5]], dtype=np.float32)
     o = O.OracleNDT()
@@ -200,11 +236,23 @@ def test_single_voxel_hand_case():
     p = pts.astype(np.float64)
     mean = p.mean(axis=0)
     np.testing.assert_allclose(lv["mean"][0], mean, atol=1e-15)
-    cov = (p - mean).T @ (p - mean) / 8 * (7 / 8)           # one-pass covariance divided by n, times (n-1)/n (:329-330)
+    cov = ((p - mean).T @ (p - mean) + np.eye(3)) / 8 * (7 / 8)      # (I + sum p p^T - 2 s m^T) / n + m m^T, times (n-1)/n
+    np.testing.assert_allclose(lv["cov"][0], cov, atol=1e-12)
     ev = np.linalg.eigvalsh(cov)
-    assert ev[0] < 0.01 * ev[2]                             # planar patch: the smallest eigenvalue gets inflated
-    np.testing.assert_allclose(lv["evals"][0], [0.01 * ev[2], ev[1], ev[2]], rtol=1e-9)
+    assert ev[0] > 0.01 * ev[2]                             # the identity keeps the planar patch away from the inflation: 7/64 on the diagonal
+    np.testing.assert_allclose(lv["evals"][0], ev, rtol=1e-9)
     np.testing.assert_allclose(lv["icov"][0] @ lv["cov"][0], np.eye(3), atol=1e-9)
+    # 160 points of a 10 m cell: the identity's share, 159 / 160^2, is below 1 % of the largest eigenvalue and the smallest one is inflated
+    big = np.tile(pts * 10, (20, 1)).astype(np.float32)
+    o10 = O.OracleNDT(resolution=10.0)
+    o10.set_target(big)
+    l10 = o10.leaves()
+    pb = big.astype(np.float64)
+    covb = ((pb - pb.mean(axis=0)).T @ (pb - pb.mean(axis=0)) + np.eye(3)) / 160 * (159 / 160)
+    evb = np.linalg.eigvalsh(covb)
+    assert l10["nr_points"].tolist() == [160] and evb[0] < 0.01 * evb[2]
+    np.testing.assert_allclose(l10["evals"][0], [0.01 * evb[2], evb[1], evb[2]], rtol=1e-9)
+    np.testing.assert_allclose(l10["icov"][0] @ l10["cov"][0], np.eye(3), atol=1e-9)
     # five points: below min_points_per_voxel, the cell exists but is not usable
     o.set_target(pts[:5])
     lv = o.leaves()
