@@ -12,7 +12,7 @@ Top level = the library's default arithmetic (LVS_ACC_EXACT: the reference's flo
   modes.tolerance       the same workload with lvs_ndt_params::accumulation = LVS_ACC_FAST (north_star's 1e-4 m / 1e-5 rad bar)
   modes.lean_final_evaluation  the top-level mode with the unread Hessian of every align's last pass skipped (bit-identical results)
   configs.pca_direct1   pclpca / DIRECT1, what the odometry nodelet runs (scan_matching_odom_nodelet.cpp:109-119), both modes
-  configs.pair_latency  BASELINE configs[0]: one hard pair from the first-frame guess (66 iterations), single-object API
+  configs.pair_latency  BASELINE configs[0]: the config-1 pair from the reference's first-frame guess, single-object API
   configs.beam128       BASELINE configs[2]: 128-beam scans (~240 k points), 0.5 m voxels; point-sharded across ranks when N > 1
   configs.ground_s2k    pclomp_ground with the odometry nodelet's ground_s2k settings (parity record; the reference never aligns it)
   configs.pgo           BASELINE configs[3]: 5 000-vertex / 19 599-edge sphere, LM and GN with the direct solver, LM with PCG
@@ -206,7 +206,7 @@ def workload_config(args, n_pts, n_keys, variant=None, accumulation=None, resolu
             "registration": "pclomp/DIRECT7" if vp["variant"] == 0 else "pclpca/DIRECT1", "transformation_epsilon": 0.01, "max_iterations": 64,
             "accumulation": accumulation or args.accumulation,
             "guesses": "constant-velocity predictions of a smooth drive: every align stops at the minimum (2 iterations, 3 evaluations) - "
-                       "a best case per align; configs.pair_latency is the 66-iteration case",
+                       "a best case per align; configs.pair_latency is the config-1 pair from the first-frame guess",
             "l2_policy": "inputs larger than L2 (%.0f MB of clouds per step vs 126 MB L2)" % ((args.batch + n_keys) * n_pts * 16 / 1e6)}
 
 

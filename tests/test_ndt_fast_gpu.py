@@ -99,7 +99,9 @@ def test_fast_mode_newton_step_per_iteration(scan_pair, variant, search):
 
 @pytest.mark.parametrize("variant,search", [(O.VAR_OMP, O.DIRECT7), (O.VAR_PCA, O.DIRECT1)])
 def test_fast_mode_align_full_scan(scan_pair, variant, search):
-    """Whole align of the config-1 pair from the reference's first-frame guess.  On this pair the reference's iteration is CHAOTIC: its
+    """Whole align of the config-1 pair from the reference's first-frame guess.  (Written when the voxel covariances still lacked the identity
+    the reference's Leaf starts them from: since that correction the pair converges in 5 iterations in both modes and everything below holds
+    with room to spare.)  On this pair the reference's iteration WAS chaotic: its
     line search is dead code (ndt_omp_impl2.hpp:888), every step is the Newton direction clamped to 0.1, and one iterate has a
     Newton step of 9.9 m at cond(H) = 2e4 - a 1e-9 difference of the first iterate is 4e-2 m after seven iterations
     (tools/fast_trace_check.py prints the table), whatever caused it.  The exact mode reproduces the oracle's trajectory because its
