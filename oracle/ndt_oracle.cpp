@@ -2,11 +2,15 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // build, link or call anything under oracle/.
 //
-// PARITY UNPINNED: the reference (BurryChen/lv_slam) ships no test, fixture or golden vector for the
-// NDT path, and neither it nor PCL/Eigen/Sophus can be built in this image, so this
-// restatement is pinned only by its own traceability and by closed-form / finite-difference checks
-// in tests/ - with one exception: the Lie-group piece (Sophus SE3 exp / log / product, ose3.h) is held bit for bit to the
-// reference's own Sophus sources, compiled from the vendored zip against an Eigen stand-in (oracle/build_ref.sh, oracle/ref_stubs/).
+// PARITY: the reference (BurryChen/lv_slam) ships no test, fixture or golden vector for the NDT path, and PCL / Eigen are not in this
+// image.  Its OWN code is nevertheless the checker of this restatement: oracle/build_ref.sh takes the member functions of
+// the three registration classes and of the voxel grid out of the reference's *_impl2.hpp / ndt_ground_impl.hpp /
+// voxel_grid_covariance_omp_impl.hpp at build time and compiles them, with the reference's vendored Sophus, against interface stand-ins
+// (oracle/ndt_ref_harness.cpp, oracle/voxel_ref_harness.cpp, oracle/ref_stubs/eigen_min.h) into oracle/_ref/*.so; tests/test_oracle_ndt.py
+// holds every function below to them BIT FOR BIT (voxel cells, searches, derivative passes, Hessian, score, whole aligns, line search).
+// Not pinned by that: Eigen's rounding and its two iterative solvers (the stand-in uses olin.h's), PCL's own getMinMax3D /
+// transformPointCloud / getAllNeighborCellIndices / kd-tree (restated on both sides).  The closed-form / finite-difference checks of
+// tests/ remain.
 //
 // CPU restatement of lv_slam's NDT scan matching, the variant that is actually compiled
 // (src/ndt_omp/ndt_omp.cpp:2 and src/ndt_pca/ndt_pca.cpp:2 include the *_impl2.hpp Lie-algebra files):
