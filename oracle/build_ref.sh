@@ -16,7 +16,8 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ "$OUT/libndt_ref.so" -nt "$HERE/extract_ref_functions.py" ] && [ "$OUT/libndt_ref.so" -nt "$HERE/olin.h" ] &&
    [ -f "$OUT/libndt_pca_ref.so" ] && [ "$OUT/libndt_pca_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libndt_ground_ref.so" ] && [ "$OUT/libndt_ground_ref.so" -nt "$OUT/libndt_ref.so" ] &&
-   [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ]; then exit 0; fi
+   [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ] &&
+   [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -68,5 +69,13 @@ PY
     /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DREF_VOXEL_BODIES="\"$TMP/voxel_bodies.inc\"" -I"$HERE/ref_stubs" -o "$OUT/libvoxel_ref.so" \
         "$HERE/voxel_ref_harness.cpp"
     echo "built $OUT/libvoxel_ref.so"
+  fi
+  PIMPL="$INC/ndt_pca/voxel_grid_covariance_pca_impl.hpp"
+  if [ -f "$PIMPL" ]; then
+    python3 "$HERE/extract_ref_functions.py" "$PIMPL" "$TMP/voxel_pca_bodies.inc" "pclpca::VoxelGridCovariance<PointT>" applyFilter getNeighborhoodAtPoint \
+        getNeighborhoodAtPoint7 getNeighborhoodAtPoint1
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DREF_PCA -DREF_VOXEL_BODIES="\"$TMP/voxel_pca_bodies.inc\"" -I"$HERE/ref_stubs" \
+        -o "$OUT/libvoxel_pca_ref.so" "$HERE/voxel_ref_harness.cpp"
+    echo "built $OUT/libvoxel_pca_ref.so"
   fi
 fi

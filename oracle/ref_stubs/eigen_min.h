@@ -252,6 +252,7 @@ class Matrix {
   Matrix<S, R, 1> diagonal() const { static_assert(R == C, "diagonal"); Matrix<S, R, 1> v; for (int i = 0; i < R; i++) v(i) = (*this)(i, i); return v; }
   Matrix<S, R, R> asDiagonal() const { static_assert(C == 1, "asDiagonal"); Matrix<S, R, R> m; m.setZero(); for (int i = 0; i < R; i++) m(i, i) = d_[i]; return m; }
   S maxCoeff() const { S v = d_[0]; for (int i = 1; i < R * C; i++) if (d_[i] > v) v = d_[i]; return v; }
+  template <typename I> S maxCoeff(I* index) const { int k = 0; for (int i = 1; i < R * C; i++) if (d_[i] > d_[k]) k = i; *index = k; return d_[k]; }      // the first maximum wins
   S minCoeff() const { S v = d_[0]; for (int i = 1; i < R * C; i++) if (d_[i] < v) v = d_[i]; return v; }
   Matrix inverse() const;                                                  // 3 x 3 doubles only (defined after olin.h is included)
 

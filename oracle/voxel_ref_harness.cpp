@@ -3,7 +3,9 @@
 // Runs the REFERENCE'S OWN voxel code: oracle/build_ref.sh lets oracle/extract_ref_functions.py write the definitions of
 //   VoxelGridCovariance<PointT>::applyFilter, getNeighborhoodAtPoint (both overloads), getNeighborhoodAtPoint7, getNeighborhoodAtPoint1
 // exactly as they stand in /root/reference/include/ndt_omp/voxel_grid_covariance_omp_impl.hpp into a temporary file (REF_VOXEL_BODIES) and
-// compiles them here into oracle/_ref/libvoxel_ref.so.  Supplied by this repository, because PCL and Eigen are not in the image:
+// compiles them here into oracle/_ref/libvoxel_ref.so; with -DREF_PCA the same functions of pclpca::VoxelGridCovariance from
+// include/ndt_pca/voxel_grid_covariance_pca_impl.hpp (the per-leaf dimension label and weight, :364-397) into libvoxel_pca_ref.so.
+// Supplied by this repository, because PCL and Eigen are not in the image:
 //   * oracle/ref_stubs/eigen_min.h   Eigen's interface (the 3 x 3 eigen-solver and inverse are the Jacobi / cofactor routines of oracle/olin.h)
 //   * the class below                the member declarations of include/ndt_omp/voxel_grid_covariance_omp.h and of pcl::VoxelGrid that the bodies
 //                                    touch - INCLUDING the Leaf constructor's initial values (voxel_grid_covariance_omp.h:98-106: cov_ starts
@@ -74,7 +76,13 @@ inline Eigen::MatrixXi getAllNeighborCellIndices() {
 }
 }  // namespace pcl
 
-namespace pclomp {
+#ifdef REF_PCA
+#define REF_NS pclpca
+#else
+#define REF_NS pclomp
+#endif
+
+namespace REF_NS {
 
 // Declarations of include/ndt_omp/voxel_grid_covariance_omp.h:56-604 (and of the pcl::VoxelGrid members it pulls in with `using`).
 template <typename PointT>
@@ -84,7 +92,12 @@ class VoxelGridCovariance {
   typedef int FieldList;
   struct Leaf {          // voxel_grid_covariance_omp.h:92-195, constructor :98-106
     Leaf() : nr_points(0), mean_(Eigen::Vector3d::Zero()), centroid(), cov_(Eigen::Matrix3d::Identity()), icov_(Eigen::Matrix3d::Zero()),
-             evecs_(Eigen::Matrix3d::Identity()), evals_(Eigen::Vector3d::Zero()) {}
+             evecs_(Eigen::Matrix3d::Identity()), evals_(Eigen::Vector3d::Zero()), dimension_features_(Eigen::Vector3d::Zero()), dimension_label_(0),
+             dimension_2d_(0) {}
+    Eigen::Vector3d dimension_features_;      // pclpca only (voxel_grid_covariance_pca.h:141-143, 252-262)
+    int dimension_label_;
+    double dimension_2d_;
+    int getDimension2d() const { return (dimension_2d_); }      // sic: an int getter over a double member (voxel_grid_covariance_pca.h:222-226)
     int nr_points;
     Eigen::Vector3d mean_;
     Eigen::VectorXf centroid;
@@ -123,11 +136,11 @@ class VoxelGridCovariance {
   int getNeighborhoodAtPoint1(const PointT& reference_point, std::vector<LeafConstPtr>& neighbors) const;
 };
 
-}  // namespace pclomp
+}  // namespace REF_NS
 
 #include REF_VOXEL_BODIES      // the reference's own definitions of the member functions declared above
 
-typedef pclomp::VoxelGridCovariance<pcl::PointXYZ> RefGrid;
+typedef REF_NS::VoxelGridCovariance<pcl::PointXYZ> RefGrid;
 struct VoxHandle {
   RefGrid grid;
   pcl::PointCloud<pcl::PointXYZ> target, centroids;
@@ -158,6 +171,12 @@ void vref_get_grid(void* h, int32_t* min_b, int32_t* max_b, int32_t* div_b) {
 }
 
 // all occupied cells, ascending key; any pointer may be NULL
+void vref_get_pca(void* h, int32_t* label, int32_t* weight) {      // pclpca: dimension label and what getDimension2d() returns, per cell
+  RefGrid& g = ((VoxHandle*)h)->grid;
+  size_t k = 0;
+  for (auto it = g.leaves_.begin(); it != g.leaves_.end(); ++it, ++k) { label[k] = it->second.dimension_label_; weight[k] = it->second.getDimension2d(); }
+}
+
 void vref_get_leaves(void* h, int32_t* keys, int32_t* nr_points, double* mean3, double* cov9, double* icov9, double* evecs9, double* evals3, float* centroid3) {
   RefGrid& g = ((VoxHandle*)h)->grid;
   size_t k = 0;

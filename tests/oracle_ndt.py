@@ -378,17 +378,17 @@ class ReferenceNDT:
         return dict(final=_from_colmajor16(fin), iterations=it.value, converged=bool(conv), trans_probability=tp.value, cloud=cloud)
 
 
-_vref = False
+_vref = {}
 
 
 class ReferenceVoxelGrid:
-    """The reference's own VoxelGridCovariance::applyFilter and getNeighborhoodAtPoint{,7,1} (oracle/voxel_ref_harness.cpp)."""
+    """The reference's own VoxelGridCovariance::applyFilter and getNeighborhoodAtPoint{,7,1} (oracle/voxel_ref_harness.cpp); pca=True: those of
+    pclpca::VoxelGridCovariance (with the per-leaf dimension label and weight)."""
 
     @staticmethod
-    def available():
-        global _vref
-        if _vref is False:
-            so = os.path.join(_ODIR, "_ref", "libvoxel_ref.so")
+    def available(pca=False):
+        if pca not in _vref:
+            so = os.path.join(_ODIR, "_ref", "libvoxel_pca_ref.so" if pca else "libvoxel_ref.so")
             if not os.path.exists(so) and os.path.exists("/root/reference/include/ndt_omp/voxel_grid_covariance_omp_impl.hpp"):
                 subprocess.call(["sh", os.path.join(_ODIR, "build_ref.sh")])
             if os.path.exists(so):
@@ -399,15 +399,16 @@ class ReferenceVoxelGrid:
                 L.vref_build.restype = ctypes.c_int; L.vref_build.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_double]
                 L.vref_get_grid.restype = None; L.vref_get_grid.argtypes = [vp] * 4
                 L.vref_get_leaves.restype = None; L.vref_get_leaves.argtypes = [vp] * 9
+                L.vref_get_pca.restype = None; L.vref_get_pca.argtypes = [vp] * 3
                 L.vref_neighbours.restype = ctypes.c_int; L.vref_neighbours.argtypes = [vp, vp, ctypes.c_int, vp]
-                _vref = L
+                _vref[pca] = L
             else:
-                _vref = None
-        return _vref is not None
+                _vref[pca] = None
+        return _vref[pca] is not None
 
-    def __init__(self, xyz, leaf=1.0, min_points=6, eig_mult=0.01):
-        assert self.available()
-        self.L = _vref
+    def __init__(self, xyz, leaf=1.0, min_points=6, eig_mult=0.01, pca=False):
+        assert self.available(pca)
+        self.L = _vref[pca]
         self.h = self.L.vref_create()
         a = _f32(xyz)
         self.n = self.L.vref_build(self.h, a.ctypes.data, a.shape[0], a.shape[1], leaf, min_points, eig_mult)
@@ -435,6 +436,12 @@ class ReferenceVoxelGrid:
         out = np.zeros(26, np.int32)
         n = self.L.vref_neighbours(self.h, p.ctypes.data, int(mode), out.ctypes.data)
         return out[:n].copy()
+
+    def pca(self):
+        """pclpca: (dimension label, int getDimension2d()) per cell"""
+        label, weight = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self.L.vref_get_pca(self.h, label.ctypes.data, weight.ctypes.data)
+        return label, weight
 
 
 def svd6_solve(A, b):

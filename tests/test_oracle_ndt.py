@@ -199,6 +199,28 @@ def test_voxel_build_against_the_reference_member_functions(small_pair, leaf):
         assert hits > 50
 
 
+@pytest.mark.parametrize("which", ["small", "full"])
+def test_pca_voxel_weights_against_the_reference_member_functions(small_pair, scan_pair, which):
+    """pclpca::VoxelGridCovariance::applyFilter (include/ndt_pca/voxel_grid_covariance_pca_impl.hpp, taken at build time): the dimension label
+    and the integer weight `getDimension2d()` of every usable cell, and the whole grid, identical to the restatement's.  Cells that never
+    reach the label block (fewer than six points) keep the constructor's dimension_2d_ = 0 in the reference and report weight 1 here (and
+    on the device): they are invisible to every search of the path."""
+    if not O.ReferenceVoxelGrid.available(pca=True):
+        pytest.skip("no compiled reference voxel grid")
+    tgt = (small_pair if which == "small" else scan_pair)[0]
+    r = O.ReferenceVoxelGrid(tgt, 1.0, pca=True)
+    o = O.OracleNDT(variant=O.VAR_PCA, search=O.DIRECT1, num_threads=1)
+    o.set_target(tgt)
+    rl, ol = r.leaves(), o.leaves()
+    for k in ("keys", "nr_points", "centroid", "mean", "cov", "icov", "evals"):
+        assert np.array_equal(rl[k], ol[k]), k
+    label, weight = r.pca()
+    usable = ol["nr_points"] >= 6
+    assert usable.sum() > 300 and np.array_equal(label[usable], ol["label"][usable]) and np.array_equal(weight[usable], ol["weight"][usable])
+    assert len(set(label[usable].tolist())) >= 2 and weight[usable].max() > 10
+    assert not weight[~usable].any() and (ol["weight"][~usable] == 1).all()
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
