@@ -17,7 +17,8 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ -f "$OUT/libndt_pca_ref.so" ] && [ "$OUT/libndt_pca_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libndt_ground_ref.so" ] && [ "$OUT/libndt_ground_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ] &&
-   [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ]; then exit 0; fi
+   [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
+   [ -f "$OUT/libinfo_ref.so" ] && [ "$OUT/libinfo_ref.so" -nt "$HERE/info_ref_api.cpp" ] && [ "$OUT/libinfo_ref.so" -nt "$OUT/libvoxel_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -77,5 +78,12 @@ PY
     /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DREF_PCA -DREF_VOXEL_BODIES="\"$TMP/voxel_pca_bodies.inc\"" -I"$HERE/ref_stubs" \
         -o "$OUT/libvoxel_pca_ref.so" "$HERE/voxel_ref_harness.cpp"
     echo "built $OUT/libvoxel_pca_ref.so"
+  fi
+  # The edge information matrix of the pose-graph nodelet: the reference's own src/global_graph/information_matrix_calculator.cpp, whole and as
+  # it lies, against stand-ins for the <ros/ros.h>, <pcl/...> and Eigen headers it includes (oracle/ref_stubs/).
+  ICPP=/root/reference/src/global_graph/information_matrix_calculator.cpp
+  if [ -f "$ICPP" ]; then
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I/root/reference/include -o "$OUT/libinfo_ref.so" "$ICPP" "$HERE/info_ref_api.cpp"
+    echo "built $OUT/libinfo_ref.so"
   fi
 fi

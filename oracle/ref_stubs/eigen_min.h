@@ -427,6 +427,44 @@ struct CommaInit4i {
 };
 inline CommaInit4i operator<<(Matrix<int, 4, 1> m, const MatrixXi::Col3& c) { CommaInit4i ci{m, 3}; for (int i = 0; i < 3; i++) ci.m(i) = c.v[i]; return ci; }
 
+// Eigen::Isometry3d / Isometry3f as information_matrix_calculator.cpp uses them: a 4 x 4 matrix with cast<float>()
+template <typename S>
+class Isometry3 {
+ public:
+  Isometry3() { m_.setIdentity(); }
+  Matrix<S, 4, 4>& matrix() { return m_; }
+  const Matrix<S, 4, 4>& matrix() const { return m_; }
+  template <typename T>
+  Isometry3<T> cast() const { Isometry3<T> o; o.matrix() = m_.template cast<T>(); return o; }
+
+ private:
+  Matrix<S, 4, 4> m_;
+};
+typedef Isometry3<double> Isometry3d;
+typedef Isometry3<float> Isometry3f;
+
+// Eigen::MatrixXd as calc_information_matrix uses it: Identity(6, 6), corner(3, 3).array() /= scalar
+class MatrixXd {
+ public:
+  MatrixXd() : r_(0), c_(0) {}
+  static MatrixXd Identity(int r, int c) { MatrixXd m; m.r_ = r; m.c_ = c; m.d_.assign((size_t)r * c, 0.0); for (int i = 0; i < r && i < c; i++) m(i, i) = 1.0; return m; }
+  int rows() const { return r_; }
+  int cols() const { return c_; }
+  double& operator()(int r, int c) { return d_[(size_t)r * c_ + c]; }
+  double operator()(int r, int c) const { return d_[(size_t)r * c_ + c]; }
+  struct Corner {
+    MatrixXd& m; int r0, c0, nr, nc;
+    Corner& array() { return *this; }
+    template <typename T> Corner& operator/=(T s) { for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) m(r0 + r, c0 + c) /= s; return *this; }      // double / T: usual arithmetic conversions
+  };
+  Corner topLeftCorner(int nr, int nc) { return Corner{*this, 0, 0, nr, nc}; }
+  Corner bottomRightCorner(int nr, int nc) { return Corner{*this, r_ - nr, c_ - nc, nr, nc}; }
+
+ private:
+  int r_, c_;
+  std::vector<double> d_;
+};
+
 template <typename T>
 using aligned_allocator = std::allocator<T>;
 

@@ -444,6 +444,44 @@ class ReferenceVoxelGrid:
         return label, weight
 
 
+_iref = False
+
+
+def info_ref():
+    """oracle/_ref/libinfo_ref.so: the reference's own information_matrix_calculator.cpp compiled against stand-in headers; None if unavailable."""
+    global _iref
+    if _iref is False:
+        so = os.path.join(_ODIR, "_ref", "libinfo_ref.so")
+        if not os.path.exists(so) and os.path.exists("/root/reference/src/global_graph/information_matrix_calculator.cpp"):
+            subprocess.call(["sh", os.path.join(_ODIR, "build_ref.sh")])
+        if os.path.exists(so):
+            L = ctypes.CDLL(so)
+            vp, sz, f64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double
+            L.iref_fitness_score.restype = f64; L.iref_fitness_score.argtypes = [vp, sz, sz, vp, sz, sz, vp, f64]
+            L.iref_information_matrix.restype = None; L.iref_information_matrix.argtypes = [vp, sz, sz, vp, sz, sz, vp, ctypes.c_int, vp, vp, vp]
+            _iref = L
+        else:
+            _iref = None
+    return _iref
+
+
+def ref_fitness_score(cloud1, cloud2, relpose, max_range=np.finfo(np.float64).max):
+    a, b = _f32(cloud1), _f32(cloud2)
+    T = np.ascontiguousarray(relpose, dtype=np.float64)
+    return info_ref().iref_fitness_score(a.ctypes.data, a.shape[0], a.shape[1], b.ctypes.data, b.shape[0], b.shape[1], T.ctypes.data, float(max_range))
+
+
+def ref_information_matrix(cloud1, cloud2, relpose, **params):
+    a, b = _f32(cloud1), _f32(cloud2)
+    T = np.ascontiguousarray(relpose, dtype=np.float64)
+    names = (ctypes.c_char_p * max(len(params), 1))(*[k.encode() for k in params])
+    vals = np.array([float(v) for v in params.values()] or [0.0])
+    out = np.zeros((6, 6))
+    info_ref().iref_information_matrix(a.ctypes.data, a.shape[0], a.shape[1], b.ctypes.data, b.shape[0], b.shape[1], T.ctypes.data, len(params), names,
+                                        vals.ctypes.data, out.ctypes.data)
+    return out
+
+
 def svd6_solve(A, b):
     A = np.ascontiguousarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)

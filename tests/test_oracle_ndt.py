@@ -221,6 +221,35 @@ def test_pca_voxel_weights_against_the_reference_member_functions(small_pair, sc
     assert not weight[~usable].any() and (ol["weight"][~usable] == 1).all()
 
 
+def test_information_matrix_against_the_reference_source(small_pair):
+    """lv_slam::InformationMatrixCalculator - the reference's own src/global_graph/information_matrix_calculator.cpp compiled whole against stand-in
+    ROS / PCL / Eigen headers - against the restatement of its fitness score (oracle) and the host mirror of its weighting
+    (lv_slam_b200/information_matrix.py): constructor defaults, the launch file's threshold, the constant-matrix switch."""
+    if O.info_ref() is None:
+        pytest.skip("no compiled reference information matrix calculator")
+    from lv_slam_b200.information_matrix import InformationMatrixCalculator
+    tgt, src, guess, truth = small_pair
+    tgt, src = tgt[::3], src[::3]                           # the stand-in kd-tree is exhaustive
+    o = O.OracleNDT(num_threads=8)
+    o.set_target(tgt); o.set_source(src)
+    big = float(np.finfo(np.float64).max)
+    for T in (truth, guess.astype(np.float64)):
+        for mr in (big, 0.25, 1e-4):
+            want = O.ref_fitness_score(tgt, src, T, mr)
+            got, cnt = o.fitness_score(np.asarray(T, dtype=np.float64).astype(np.float32), mr)
+            assert got == want or abs(got - want) <= 1e-15 * abs(want), (mr, got, want)
+            assert (cnt == 0) == (want == big)
+    for prm in ({}, dict(fitness_score_thresh=2.0), dict(var_gain_a=10.0, min_stddev_x=0.2, max_stddev_q=0.5), dict(use_const_inf_matrix=1, const_stddev_x=0.3)):
+        want = O.ref_information_matrix(tgt, src, guess.astype(np.float64), **prm)
+        kw = dict(prm)
+        if "use_const_inf_matrix" in kw:
+            kw["use_const_inf_matrix"] = True
+        m = InformationMatrixCalculator(**kw)
+        fs = O.ref_fitness_score(tgt, src, guess.astype(np.float64))
+        got = m.information_from_fitness(fs) if not m.use_const_inf_matrix else m.calc_information_matrix(None, None, None)
+        assert np.array_equal(got, want), (prm, got.diagonal(), want.diagonal())
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
