@@ -18,7 +18,8 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ -f "$OUT/libndt_ground_ref.so" ] && [ "$OUT/libndt_ground_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
-   [ -f "$OUT/libinfo_ref.so" ] && [ "$OUT/libinfo_ref.so" -nt "$HERE/info_ref_api.cpp" ] && [ "$OUT/libinfo_ref.so" -nt "$OUT/libvoxel_ref.so" ]; then exit 0; fi
+   [ -f "$OUT/libinfo_ref.so" ] && [ "$OUT/libinfo_ref.so" -nt "$HERE/info_ref_api.cpp" ] && [ "$OUT/libinfo_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
+   [ -f "$OUT/libdquat_ref.so" ] && [ "$OUT/libdquat_ref.so" -nt "$HERE/dquat_ref_api.cpp" ] && [ "$OUT/libdquat_ref.so" -nt "$OUT/libinfo_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -86,4 +87,16 @@ PY
     /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I/root/reference/include -o "$OUT/libinfo_ref.so" "$ICPP" "$HERE/info_ref_api.cpp"
     echo "built $OUT/libinfo_ref.so"
   fi
+fi
+# g2o's own compute_dq_dR (dquat2mat.cpp + its Maxima-generated cases), as they are in the zip: the table behind EdgeSE3::linearizeOplus
+if [ -f "$ZIP" ]; then
+  python3 - "$ZIP" "$TMP" <<'PY'
+import sys, zipfile
+z = zipfile.ZipFile(sys.argv[1])
+for n in ("g2o/g2o/types/slam3d/dquat2mat.cpp", "g2o/g2o/types/slam3d/dquat2mat.h", "g2o/g2o/types/slam3d/dquat2mat_maxima_generated.cpp"):
+    z.extract(n, sys.argv[2])
+PY
+  /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d" \
+      -o "$OUT/libdquat_ref.so" "$TMP/g2o/g2o/types/slam3d/dquat2mat.cpp" "$HERE/dquat_ref_api.cpp"
+  echo "built $OUT/libdquat_ref.so"
 fi

@@ -710,6 +710,13 @@ int optimize(PGO& g, int max_iters, int algorithm, int solver, double pcg_tol, i
 
 extern "C" {
 
+// tap: compute_dq_dR of a rotation matrix (row-major in, [3][9] row-major out), for the comparison with g2o's own generated code
+void opgo_compute_dq_dR(const double* R9, double* D27) {
+  double D[3][9];
+  compute_dq_dR(D, R9);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 9; c++) D27[r * 9 + c] = D[r][c];
+}
+
 int opgo_load_csparse(const char* path) { return load_csparse(path) ? 1 : 0; }
 int opgo_have_csparse() { return g_cs.ok() ? 1 : 0; }
 

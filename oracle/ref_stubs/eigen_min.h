@@ -22,7 +22,7 @@
 
 namespace Eigen {
 
-template <typename S, int R, int C>
+template <typename S, int R, int C, int Options = 0>      // Options: Eigen::ColMajor (= 0) is the only value that is ever named
 class Matrix;
 
 // Writable view of a fixed RB x CB block of a Matrix<S, R, C>.
@@ -160,7 +160,7 @@ class CommaInit {
   int k_;
 };
 
-template <typename S, int R, int C>
+template <typename S, int R, int C, int Options>
 class Matrix {
  public:
   Matrix() {}

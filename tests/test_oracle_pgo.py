@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 import oracle_pgo as P
 from lv_slam_b200.synth import posegraph as G
@@ -304,3 +305,40 @@ def test_unary_constraint_graph_against_the_golden_pin():
     st = o.optimize(100, P.ALG_LM, P.SOLVER_DENSE)
     np.testing.assert_allclose(st["chi2_after"], gold["chi2_final"], rtol=1e-9)
     np.testing.assert_allclose(o.poses()[0], gold["pose_0"], atol=1e-9)
+
+
+def test_compute_dq_dR_against_g2o_own_generated_code():
+    """g2o's own types/slam3d/dquat2mat.cpp with its Maxima-generated cases (unpacked from the reference's 3rdtools/g2o-a48ff8c.zip and compiled
+    as they are by oracle/build_ref.sh) against the restatement of the table behind EdgeSE3::linearizeOplus: all four branches of the
+    quaternion extraction, identical to the last bit."""
+    import ctypes
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libdquat_ref.so")
+    if not os.path.exists(so):
+        if os.path.exists("/root/reference/3rdtools/g2o-a48ff8c.zip"):
+            import subprocess
+            subprocess.call(["sh", os.path.join(os.path.dirname(so), "..", "build_ref.sh")])
+        if not os.path.exists(so):
+            pytest.skip("no compiled g2o dquat2mat")
+    G = ctypes.CDLL(so)
+    G.gref_compute_dq_dR.restype = None; G.gref_compute_dq_dR.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L = P.lib()
+    rng = np.random.default_rng(41)
+    seen = set()
+    for k in range(400):
+        q = rng.normal(size=4)
+        if k % 4:                                            # push the trace below zero to reach the x / y / z branches
+            q[0] *= 0.05
+            q[1 + k % 3] *= 5
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        tr = np.trace(R)
+        seen.add(0 if tr > 0 else 1 if (R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]) else 2 if R[1, 1] > R[2, 2] else 3)
+        a, b = np.zeros(27), np.zeros(27)
+        Rc = np.ascontiguousarray(R)
+        G.gref_compute_dq_dR(Rc.ctypes.data, a.ctypes.data)
+        L.opgo_compute_dq_dR(Rc.ctypes.data, b.ctypes.data)
+        assert np.array_equal(a, b), (k, np.abs(a - b).max())
+    assert seen == {0, 1, 2, 3}
