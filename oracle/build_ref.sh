@@ -19,7 +19,8 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
    [ -f "$OUT/libinfo_ref.so" ] && [ "$OUT/libinfo_ref.so" -nt "$HERE/info_ref_api.cpp" ] && [ "$OUT/libinfo_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
-   [ -f "$OUT/libdquat_ref.so" ] && [ "$OUT/libdquat_ref.so" -nt "$HERE/dquat_ref_api.cpp" ] && [ "$OUT/libdquat_ref.so" -nt "$OUT/libinfo_ref.so" ]; then exit 0; fi
+   [ -f "$OUT/libdquat_ref.so" ] && [ "$OUT/libdquat_ref.so" -nt "$HERE/dquat_ref_api.cpp" ] && [ "$OUT/libdquat_ref.so" -nt "$OUT/libinfo_ref.so" ] &&
+   [ -f "$OUT/libg2o_ref.so" ] && [ "$OUT/libg2o_ref.so" -nt "$HERE/g2o_ref_harness.cpp" ] && [ "$OUT/libg2o_ref.so" -nt "$OUT/libdquat_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -99,4 +100,19 @@ PY
   /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d" \
       -o "$OUT/libdquat_ref.so" "$TMP/g2o/g2o/types/slam3d/dquat2mat.cpp" "$HERE/dquat_ref_api.cpp"
   echo "built $OUT/libdquat_ref.so"
+  # g2o's own slam3d edge math (error vector, analytic Jacobians, oplus): functions of isometry3d_gradients.h / isometry3d_mappings.cpp taken at
+  # build time and compiled in oracle/g2o_ref_harness.cpp with dquat2mat.cpp
+  python3 - "$ZIP" "$TMP" <<'PY'
+import sys, zipfile
+z = zipfile.ZipFile(sys.argv[1])
+for n in ("g2o/g2o/types/slam3d/isometry3d_gradients.h", "g2o/g2o/types/slam3d/isometry3d_mappings.cpp"):
+    z.extract(n, sys.argv[2])
+PY
+  python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/types/slam3d/isometry3d_gradients.h" "$TMP/g2o_grad.inc" - skew skewT computeEdgeSE3Gradient
+  python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/types/slam3d/isometry3d_mappings.cpp" "$TMP/g2o_map.inc" - normalize toCompactQuaternion \
+      fromCompactQuaternion toVectorMQT fromVectorMQT
+  /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DG2O_GRAD_BODIES="\"$TMP/g2o_grad.inc\"" -DG2O_MAP_BODIES="\"$TMP/g2o_map.inc\"" \
+      -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d" -o "$OUT/libg2o_ref.so" "$TMP/g2o/g2o/types/slam3d/dquat2mat.cpp" \
+      "$HERE/g2o_ref_harness.cpp"
+  echo "built $OUT/libg2o_ref.so"
 fi

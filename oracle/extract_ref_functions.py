@@ -4,13 +4,56 @@ Writes the definitions of named member functions of a registration class (pclomp
 pclomp_ground::NormalDistributionsTransformGround), exactly as they stand in the reference's *_impl2.hpp / ndt_ground_impl.hpp, to a temporary include file that oracle/ndt_ref_harness.cpp compiles (oracle/build_ref.sh).  Nothing is
 written into the repository: the output path is a temporary directory of the build.
 
-usage: extract_ref_functions.py <impl.hpp> <out.inc> <qualified class, e.g. pclomp::NormalDistributionsTransform> name [name ...]
+usage: extract_ref_functions.py <impl.hpp> <out.inc> <qualified class, e.g. pclomp::NormalDistributionsTransform, or - for free functions> name [name ...]
 """
 import re
 import sys
 
 
+def extract_free(text, name):
+    """definitions (not declarations) of a free function `name`, with a preceding template header if there is one"""
+    out = []
+    for m in re.finditer(r"\b" + re.escape(name) + r"\s*\(", text):
+        j = m.end()
+        depth = 1
+        while depth:                       # matching parenthesis of the parameter list
+            c = text[j]
+            depth += (c == "(") - (c == ")")
+            j += 1
+        k = j
+        while text[k] in " \t\r\n":
+            k += 1
+        if text[k] != "{":
+            continue                       # a declaration or a call
+        start = text.rfind("\n", 0, m.start()) + 1
+        head = text[:start].rstrip()
+        t = head.rfind("template")
+        if t >= 0 and not re.search(r"[;{}]", head[t:]):
+            start = t                      # template <...> line(s) directly above
+        elif re.search(r"[;{}]\s*$", head) is None and head.rfind("\n") >= 0:
+            start = head.rfind("\n") + 1   # return type on the line above
+        depth, i = 0, k
+        while True:
+            c = text[i]
+            if c == "{":
+                depth += 1
+            elif c == "}":
+                depth -= 1
+                if depth == 0:
+                    break
+            i += 1
+        line = text[start:m.start()]
+        if re.search(r"\b(return|=)\b|[=.]\s*$", line):
+            continue                       # `x = name(...) {` cannot happen, but a call inside an expression can precede a brace
+        out.append(text[start:i + 1])
+    if not out:
+        raise SystemExit("extract_ref_functions: free function %s not found" % name)
+    return out
+
+
 def extract(text, cls, name):
+    if cls == "-":
+        return extract_free(text, name)
     out = []
     prefix = cls if "<" in cls else cls + "<PointSource, PointTarget>"
     pat = re.compile(re.escape(prefix) + r"::" + re.escape(name) + r"\s*\(")

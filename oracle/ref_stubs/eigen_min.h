@@ -207,6 +207,10 @@ class Matrix {
   template <typename T>
   Matrix<T, R, C> cast() const { Matrix<T, R, C> m; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) m(r, c) = static_cast<T>((*this)(r, c)); return m; }
   Matrix& noalias() { return *this; }
+  Matrix& derived() { return *this; }
+  const Matrix& derived() const { return *this; }
+  void resize(int r, int c) { assert(r == R && c == C); (void)r; (void)c; }
+  S* data() { return d_; }
   template <int R2, int C2>
   S dot(const Matrix<S, R2, C2>& o) const {
     static_assert((R == 1 || C == 1) && (R2 == 1 || C2 == 1) && R * C == R2 * C2, "dot of two vectors");
@@ -343,6 +347,12 @@ class Quaternion {
   S y() const { return y_; }
   S z() const { return z_; }
   Matrix<S, 3, 1> vec() const { return Matrix<S, 3, 1>(x_, y_, z_); }
+  struct Coeffs {            // q.coeffs(): (x, y, z, w); only `*= scalar` and head<3>() are used on it
+    Quaternion& q;
+    template <typename T> Coeffs& operator*=(T s) { q.x_ *= s; q.y_ *= s; q.z_ *= s; q.w_ *= s; return *this; }
+    template <int N> Matrix<S, 3, 1> head() const { static_assert(N == 3, "head<3>"); return Matrix<S, 3, 1>(q.x_, q.y_, q.z_); }
+  };
+  Coeffs coeffs() { return Coeffs{*this}; }
   void setIdentity() { x_ = y_ = z_ = S(0); w_ = S(1); }
   S squaredNorm() const { return w_ * w_ + x_ * x_ + y_ * y_ + z_ * z_; }
   S norm() const { return std::sqrt(squaredNorm()); }
@@ -427,15 +437,40 @@ struct CommaInit4i {
 };
 inline CommaInit4i operator<<(Matrix<int, 4, 1> m, const MatrixXi::Col3& c) { CommaInit4i ci{m, 3}; for (int i = 0; i < 3; i++) ci.m(i) = c.v[i]; return ci; }
 
-// Eigen::Isometry3d / Isometry3f as information_matrix_calculator.cpp uses them: a 4 x 4 matrix with cast<float>()
+// Eigen::Isometry3d / Isometry3f as information_matrix_calculator.cpp and g2o's slam3d code use them.  Product and inverse in the
+// Isometry mode of Eigen::Transform: (R_a R_b, R_a t_b + t_a) and (R^T, -(R^T t)), sums left to right.
 template <typename S>
 class Isometry3 {
  public:
+  typedef Matrix<S, 3, 3> ConstLinearPart;
+  typedef Matrix<S, 3, 1> ConstTranslationPart;
   Isometry3() { m_.setIdentity(); }
   Matrix<S, 4, 4>& matrix() { return m_; }
   const Matrix<S, 4, 4>& matrix() const { return m_; }
   template <typename T>
   Isometry3<T> cast() const { Isometry3<T> o; o.matrix() = m_.template cast<T>(); return o; }
+  Matrix<S, 3, 3> linear() const { return m_.template block<3, 3>(0, 0); }
+  Matrix<S, 3, 1> translation() const { return m_.template block<3, 1>(0, 3); }
+  BlockRef<S, 4, 4, 3, 1> translation() { return BlockRef<S, 4, 4, 3, 1>(m_, 0, 3); }
+  Isometry3& operator=(const Matrix<S, 3, 3>& R) { m_.setIdentity(); m_.template block<3, 3>(0, 0) = R; return *this; }      // rotation, zero translation
+  Isometry3 inverse() const {
+    Isometry3 o;
+    const Matrix<S, 3, 3> R = linear();
+    const Matrix<S, 3, 1> t = translation();
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) o.m_(i, j) = R(j, i);
+      o.m_(i, 3) = -((R(0, i) * t(0) + R(1, i) * t(1)) + R(2, i) * t(2));
+    }
+    return o;
+  }
+  Isometry3 operator*(const Isometry3& b) const {
+    Isometry3 o;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) o.m_(i, j) = (m_(i, 0) * b.m_(0, j) + m_(i, 1) * b.m_(1, j)) + m_(i, 2) * b.m_(2, j);
+      o.m_(i, 3) = ((m_(i, 0) * b.m_(0, 3) + m_(i, 1) * b.m_(1, 3)) + m_(i, 2) * b.m_(2, 3)) + m_(i, 3);
+    }
+    return o;
+  }
 
  private:
   Matrix<S, 4, 4> m_;
@@ -464,6 +499,29 @@ class MatrixXd {
   int r_, c_;
   std::vector<double> d_;
 };
+
+// Eigen::MatrixBase<Derived> in a parameter list: the matrix itself
+template <typename D>
+using MatrixBase = D;
+
+// Eigen::Map<Matrix<double, R, C>> over a buffer in Eigen's default (column-major) storage order
+template <typename M>
+class Map;
+template <typename S, int R, int C>
+class Map<Matrix<S, R, C> > {
+ public:
+  explicit Map(S* p) : p_(p) {}
+  S& operator()(int r, int c) { return p_[c * R + r]; }
+  const S& operator()(int r, int c) const { return p_[c * R + r]; }
+  Map& noalias() { return *this; }
+  Map& operator=(const Matrix<S, R, C>& m) { for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) (*this)(r, c) = m(r, c); return *this; }
+  Matrix<S, R, C> eval() const { Matrix<S, R, C> m; for (int r = 0; r < R; r++) for (int c = 0; c < C; c++) m(r, c) = (*this)(r, c); return m; }
+
+ private:
+  S* p_;
+};
+template <typename S, int R, int K, int C>
+inline Matrix<S, R, C> operator*(const Matrix<S, R, K>& a, const Map<Matrix<S, K, C> >& b) { return a * b.eval(); }
 
 template <typename T>
 using aligned_allocator = std::allocator<T>;

@@ -25,6 +25,7 @@ def lib():
         L = ctypes.CDLL(_SO)
         vp, i32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
         L.opgo_compute_dq_dR.restype = None; L.opgo_compute_dq_dR.argtypes = [vp, vp]
+        L.opgo_oplus_matrix.restype = None; L.opgo_oplus_matrix.argtypes = [vp, vp, vp, vp]
         L.opgo_load_csparse.restype = i32; L.opgo_load_csparse.argtypes = [ctypes.c_char_p]
         L.opgo_have_csparse.restype = i32
         L.opgo_create.restype = vp
