@@ -20,7 +20,9 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
    [ -f "$OUT/libinfo_ref.so" ] && [ "$OUT/libinfo_ref.so" -nt "$HERE/info_ref_api.cpp" ] && [ "$OUT/libinfo_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
    [ -f "$OUT/libdquat_ref.so" ] && [ "$OUT/libdquat_ref.so" -nt "$HERE/dquat_ref_api.cpp" ] && [ "$OUT/libdquat_ref.so" -nt "$OUT/libinfo_ref.so" ] &&
-   [ -f "$OUT/libg2o_ref.so" ] && [ "$OUT/libg2o_ref.so" -nt "$HERE/g2o_ref_harness.cpp" ] && [ "$OUT/libg2o_ref.so" -nt "$OUT/libdquat_ref.so" ]; then exit 0; fi
+   [ -f "$OUT/libg2o_ref.so" ] && [ "$OUT/libg2o_ref.so" -nt "$HERE/g2o_ref_harness.cpp" ] && [ "$OUT/libg2o_ref.so" -nt "$OUT/libdquat_ref.so" ] &&
+   [ -f "$OUT/liblm_ref.so" ] && [ "$OUT/liblm_ref.so" -nt "$HERE/lm_ref_harness.cpp" ] && [ "$OUT/liblm_ref.so" -nt "$HERE/pgo_oracle.cpp" ] &&
+   [ "$OUT/liblm_ref.so" -nt "$OUT/libg2o_ref.so" ]; then exit 0; fi
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 - "$ZIP" "$TMP" <<'PY'
@@ -115,4 +117,15 @@ PY
       -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d" -o "$OUT/libg2o_ref.so" "$TMP/g2o/g2o/types/slam3d/dquat2mat.cpp" \
       "$HERE/g2o_ref_harness.cpp"
   echo "built $OUT/libg2o_ref.so"
+  # g2o's own Levenberg-Marquardt control flow (solve, computeLambdaInit, computeScale) over the restatement's building blocks:
+  # oracle/lm_ref_harness.cpp includes oracle/pgo_oracle.cpp, so the library is a second copy of the oracle whose optimiser is g2o's code
+  python3 - "$ZIP" "$TMP" <<'PY'
+import sys, zipfile
+zipfile.ZipFile(sys.argv[1]).extract("g2o/g2o/core/optimization_algorithm_levenberg.cpp", sys.argv[2])
+PY
+  python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/optimization_algorithm_levenberg.cpp" "$TMP/g2o_lm.inc" "=OptimizationAlgorithmLevenberg" \
+      solve computeLambdaInit computeScale
+  /usr/bin/g++ -O3 -fopenmp -msse4.2 -ffp-contract=off -fPIC -std=c++17 -shared -DG2O_LM_BODIES="\"$TMP/g2o_lm.inc\"" -I"$HERE" -o "$OUT/liblm_ref.so" \
+      "$HERE/lm_ref_harness.cpp" -ldl
+  echo "built $OUT/liblm_ref.so"
 fi

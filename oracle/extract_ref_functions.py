@@ -55,10 +55,11 @@ def extract(text, cls, name):
     if cls == "-":
         return extract_free(text, name)
     out = []
-    prefix = cls if "<" in cls else cls + "<PointSource, PointTarget>"
+    plain = cls.startswith("=")            # "=Class": a member of a non-template class, definition starts on the line of its return type
+    prefix = cls[1:] if plain else (cls if "<" in cls else cls + "<PointSource, PointTarget>")
     pat = re.compile(re.escape(prefix) + r"::" + re.escape(name) + r"\s*\(")
     for m in pat.finditer(text):
-        start = text.rfind("template", 0, m.start())
+        start = text.rfind("\n", 0, m.start()) + 1 if plain else text.rfind("template", 0, m.start())
         brace = text.index("{", m.end())
         depth, i = 0, brace
         while True:

@@ -395,3 +395,75 @@ def test_edge_se3_math_against_g2o_own_code():
         G.gref_oplus(xi.ctypes.data, upd.ctypes.data, Ra.ctypes.data, ta.ctypes.data)
         L.opgo_oplus_matrix(xi.ctypes.data, upd.ctypes.data, Rb.ctypes.data, tb.ctypes.data)
         assert np.array_equal(Ra, Rb) and np.array_equal(ta, tb), k
+
+
+def test_lm_control_flow_against_g2o_own_code():
+    """g2o's own OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale (taken from the reference's g2o zip at build time,
+    oracle/lm_ref_harness.cpp) driving the restatement's building blocks, against the restated loop of oracle/pgo_oracle.cpp: iteration
+    counts, the per-iteration chi2 / lambda / trial counts and the optimised poses identical - on the sphere with Huber kernels (dense and
+    CSparse solves), with unary priors and the floor constraint, with a fixed vertex, and from a start far enough that steps are rejected."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "liblm_ref.so")
+    if not os.path.exists(so):
+        if os.path.exists("/root/reference/3rdtools/g2o-a48ff8c.zip"):
+            import subprocess
+            subprocess.call(["sh", os.path.join(root, "oracle", "build_ref.sh")])
+        if not os.path.exists(so):
+            pytest.skip("no compiled g2o LM")
+    G = ctypes.CDLL(so)
+    vp, i32 = ctypes.c_void_p, ctypes.c_int
+    G.opgo_create.restype = vp
+    G.opgo_destroy.argtypes = [vp]; G.opgo_destroy.restype = None
+    G.opgo_set_graph_typed.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]; G.opgo_set_graph_typed.restype = None
+    G.opgo_set_floor_plane.argtypes = [vp, vp]; G.opgo_set_floor_plane.restype = None
+    G.opgo_get_poses.argtypes = [vp, vp]; G.opgo_get_poses.restype = None
+    G.opgo_load_csparse.restype = i32; G.opgo_load_csparse.argtypes = [ctypes.c_char_p]
+    G.gref_lm_optimize.restype = i32; G.gref_lm_optimize.argtypes = [vp, i32, i32, vp, vp, i32, vp]
+    cs = os.path.join(root, "oracle", "_ref", "libcsparse_ref.so")
+    if os.path.exists(cs):
+        G.opgo_load_csparse(cs.encode())
+
+    def run_g2o(poses, ij, meas, info, hub, fixed, etype, floor, iters, solver):
+        h = G.opgo_create()
+        c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+        p, e, m, inf = c(poses), c(ij, np.int32), c(meas), c(info)
+        hb = c(hub) if hub is not None else None
+        fx = c(fixed, np.uint8) if fixed is not None else None
+        ty = c(etype, np.int32) if etype is not None else None
+        if floor is not None:
+            G.opgo_set_floor_plane(h, c(floor).ctypes.data)
+        G.opgo_set_graph_typed(h, len(p), p.ctypes.data, fx.ctypes.data if fx is not None else None, len(e), e.ctypes.data, m.ctypes.data, inf.ctypes.data,
+                               hb.ctypes.data if hb is not None else None, ty.ctypes.data if ty is not None else None)
+        st, tr, n = np.zeros(5), np.zeros((iters + 1, 3)), ctypes.c_int(0)
+        it = G.gref_lm_optimize(h, iters, solver, st.ctypes.data, tr.ctypes.data, iters + 1, ctypes.byref(n))
+        out = np.zeros((len(p), 7))
+        G.opgo_get_poses(h, out.ctypes.data)
+        G.opgo_destroy(h)
+        return it, st, tr[:n.value], out
+
+    from lv_slam_b200.synth import posegraph as SG
+    g1 = SG.sphere(20, 10, seed=7)
+    rng = np.random.default_rng(9)
+    p_ij, p_meas, p_info, p_hub, p_type = _priors_on(g1, rng, every=5)
+    far = g1["poses7"].copy()
+    far[:, :3] += np.random.default_rng(3).normal(0, 3.0, far[:, :3].shape)      # a start that makes LM reject steps
+    fixed0 = np.zeros(len(g1["poses7"]), np.uint8); fixed0[0] = 1
+    cases = [("sphere, Huber", g1["poses7"], g1["ij"], g1["meas7"], g1["info21"], g1["huber"], None, None, None),
+             ("sphere, fixed vertex", g1["poses7"], g1["ij"], g1["meas7"], g1["info21"], g1["huber"], fixed0, None, None),
+             ("far start", far, g1["ij"], g1["meas7"], g1["info21"], g1["huber"], None, None, None),
+             ("unary priors + floor", g1["poses7"], p_ij, p_meas, p_info, p_hub, None, p_type, FLOOR)]
+    solvers = [P.SOLVER_DENSE] + ([P.SOLVER_CSPARSE] if (P.have_csparse() and os.path.exists(cs)) else [])
+    rejected = 0
+    for ci, (name, poses, ij, meas, info, hub, fixed, etype, floor) in enumerate(cases):
+        for solver in (solvers if ci == 0 or len(solvers) == 1 else solvers[1:]):      # the dense solve is slow: first case only when CSparse is there
+            o = P.OraclePGO()
+            o.set_graph(poses, ij, meas, info, hub, fixed, etype, floor)
+            r = o.optimize(40, P.ALG_LM, solver)
+            it, st, tr, out = run_g2o(poses, ij, meas, info, hub, fixed, etype, floor, 40, solver)
+            assert it == r["iterations"] > 0, (name, it, r["iterations"])
+            assert np.array_equal(tr[:, 0], r["trace"][:, 0]) and np.array_equal(tr[:, 1], r["trace"][:, 1]) and np.array_equal(tr[:, 2], r["trace"][:, 2]), name
+            assert st[1] == r["chi2_after"] and st[2] == r["lam"] and int(st[3]) == r["trials"], name
+            assert np.array_equal(out, o.poses()), name
+            rejected += int((tr[:, 2] > 1).sum())
+    assert rejected > 0                                      # the trial loop (pop, lambda *= ni) was exercised
