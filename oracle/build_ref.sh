@@ -107,13 +107,15 @@ PY
   python3 - "$ZIP" "$TMP" <<'PY'
 import sys, zipfile
 z = zipfile.ZipFile(sys.argv[1])
-for n in ("g2o/g2o/types/slam3d/isometry3d_gradients.h", "g2o/g2o/types/slam3d/isometry3d_mappings.cpp"):
+for n in ("g2o/g2o/types/slam3d/isometry3d_gradients.h", "g2o/g2o/types/slam3d/isometry3d_mappings.cpp", "g2o/g2o/core/robust_kernel_impl.cpp"):
     z.extract(n, sys.argv[2])
 PY
   python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/types/slam3d/isometry3d_gradients.h" "$TMP/g2o_grad.inc" - skew skewT computeEdgeSE3Gradient
   python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/types/slam3d/isometry3d_mappings.cpp" "$TMP/g2o_map.inc" - normalize toCompactQuaternion \
       fromCompactQuaternion toVectorMQT fromVectorMQT
+  python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/robust_kernel_impl.cpp" "$TMP/g2o_huber.inc" "=RobustKernelHuber" robustify
   /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DG2O_GRAD_BODIES="\"$TMP/g2o_grad.inc\"" -DG2O_MAP_BODIES="\"$TMP/g2o_map.inc\"" \
+      -DG2O_HUBER_BODIES="\"$TMP/g2o_huber.inc\"" \
       -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d" -o "$OUT/libg2o_ref.so" "$TMP/g2o/g2o/types/slam3d/dquat2mat.cpp" \
       "$HERE/g2o_ref_harness.cpp"
   echo "built $OUT/libg2o_ref.so"

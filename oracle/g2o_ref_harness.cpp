@@ -5,6 +5,7 @@
 // from the reference's 3rdtools/g2o-a48ff8c.zip; oracle/extract_ref_functions.py writes the definitions of
 //   skew, skewT (both overloads each), computeEdgeSE3Gradient (both overloads)                       [isometry3d_gradients.h]
 //   normalize, toCompactQuaternion, fromCompactQuaternion, toVectorMQT, fromVectorMQT                 [isometry3d_mappings.cpp]
+//   RobustKernelHuber::robustify                                                                      [core/robust_kernel_impl.cpp]
 // exactly as they stand into temporary files (G2O_GRAD_BODIES, G2O_MAP_BODIES) compiled here, with dquat2mat.cpp as it is, into
 // oracle/_ref/libg2o_ref.so.  Written here: the typedefs of g2o/core/eigen_types.h, the one-line extractRotation of isometry3d_mappings.h:46-49,
 // the three call sites (edge_se3.cpp:70-75, :92-103, vertex_se3.h:90-99, restated in the entry points below) and the Eigen interface
@@ -30,6 +31,16 @@ using namespace std;
 #include G2O_MAP_BODIES
 #include G2O_GRAD_BODIES
 }  // namespace internal
+}  // namespace g2o
+
+namespace g2o {
+// RobustKernelHuber (core/robust_kernel_impl.{h,cpp}): the one member the pose graph's Huber kernels use, taken from robust_kernel_impl.cpp
+class RobustKernelHuber {
+ public:
+  double _delta = 1.0;
+  void robustify(double e, Vector3D& rho) const;
+};
+#include G2O_HUBER_BODIES
 }  // namespace g2o
 
 using g2o::Isometry3D;
@@ -70,6 +81,15 @@ void gref_oplus(const double* x7, const double* update6, double* R9, double* t3)
   for (int i = 0; i < 6; i++) v[i] = update6[i];
   const Isometry3D Y = X * g2o::internal::fromVectorMQT(v);
   for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R9[r * 3 + c] = Y.matrix()(r, c); t3[r] = Y.matrix()(r, 3); }
+}
+
+// RobustKernelHuber::robustify (robust_kernel_impl.cpp:65-78): rho, rho', rho'' of the squared error
+void gref_huber(double e, double delta, double* rho3) {
+  g2o::RobustKernelHuber k;
+  k._delta = delta;
+  g2o::Vector3D rho;
+  k.robustify(e, rho);
+  for (int i = 0; i < 3; i++) rho3[i] = rho[i];
 }
 
 }  // extern "C"

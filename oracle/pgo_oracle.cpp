@@ -826,6 +826,7 @@ void opgo_edge_error(const double* z7, const double* xi7, const double* xj7, dou
 void opgo_edge_jacobians(const double* z7, const double* xi7, const double* xj7, double* Ji, double* Jj) {
   edge_gradient(iso_from_qt7(z7), iso_from_qt7(xi7), iso_from_qt7(xj7), Ji, Jj, nullptr);
 }
+void opgo_huber(double e, double delta, double* rho3) { huber(e, delta, rho3); }      // tap: the Huber kernel of the squared error
 void opgo_oplus_matrix(const double* x7, const double* delta6, double* R9, double* t3) {      // the same, as rotation matrix + translation
   Iso r = iso_mul(iso_from_qt7(x7), from_vector_mqt(delta6));
   std::memcpy(R9, r.R, 72); std::memcpy(t3, r.t, 24);

@@ -378,6 +378,12 @@ def test_edge_se3_math_against_g2o_own_code():
             q = -q
         return np.concatenate([rng.normal(0, 10, 3), q[1:], q[:1]])
 
+    G.gref_huber.restype = None; G.gref_huber.argtypes = [ctypes.c_double, ctypes.c_double, vp]
+    L.opgo_huber.restype = None; L.opgo_huber.argtypes = [ctypes.c_double, ctypes.c_double, vp]
+    for e, d in ((0.0, 1.0), (0.5, 1.0), (1.0, 1.0), (1.0000001, 1.0), (37.5, 1.0), (3.0, 2.0), (4.0, 2.0), (1e6, 0.3)):      # RobustKernelHuber::robustify
+        ra, rb = np.zeros(3), np.zeros(3)
+        G.gref_huber(e, d, ra.ctypes.data); L.opgo_huber(e, d, rb.ctypes.data)
+        assert np.array_equal(ra, rb), (e, d)
     for k in range(300):
         z, xi, xj = pose(k % 4), pose((k // 4) % 4), pose((k // 16) % 4)
         a, b = np.zeros(6), np.zeros(6)
