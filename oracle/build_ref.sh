@@ -19,6 +19,7 @@ if [ -f "$OUT/libcsparse_ref.so" ] && [ "$OUT/libcsparse_ref.so" -nt "$ZIP" ] &&
    [ -f "$OUT/libvoxel_ref.so" ] && [ "$OUT/libvoxel_ref.so" -nt "$HERE/voxel_ref_harness.cpp" ] && [ "$OUT/libvoxel_ref.so" -nt "$OUT/libndt_ref.so" ] &&
    [ -f "$OUT/libvoxel_pca_ref.so" ] && [ "$OUT/libvoxel_pca_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
    [ -f "$OUT/libinfo_ref.so" ] && [ "$OUT/libinfo_ref.so" -nt "$HERE/info_ref_api.cpp" ] && [ "$OUT/libinfo_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
+   [ -f "$OUT/libprior_ref.so" ] && [ "$OUT/libprior_ref.so" -nt "$HERE/prior_ref_api.cpp" ] && [ "$OUT/libprior_ref.so" -nt "$OUT/libvoxel_ref.so" ] &&
    [ -f "$OUT/libdquat_ref.so" ] && [ "$OUT/libdquat_ref.so" -nt "$HERE/dquat_ref_api.cpp" ] && [ "$OUT/libdquat_ref.so" -nt "$OUT/libinfo_ref.so" ] &&
    [ -f "$OUT/libg2o_ref.so" ] && [ "$OUT/libg2o_ref.so" -nt "$HERE/g2o_ref_harness.cpp" ] && [ "$OUT/libg2o_ref.so" -nt "$OUT/libdquat_ref.so" ] &&
    [ -f "$OUT/liblm_ref.so" ] && [ "$OUT/liblm_ref.so" -nt "$HERE/lm_ref_harness.cpp" ] && [ "$OUT/liblm_ref.so" -nt "$HERE/pgo_oracle.cpp" ] &&
@@ -89,6 +90,12 @@ PY
   if [ -f "$ICPP" ]; then
     /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I/root/reference/include -o "$OUT/libinfo_ref.so" "$ICPP" "$HERE/info_ref_api.cpp"
     echo "built $OUT/libinfo_ref.so"
+  fi
+  # The reference's own unary edges of the global graph (GPS / IMU priors): include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp as they are, against
+  # stand-ins for the g2o / Eigen headers they include
+  if [ -f /root/reference/include/g2o/edge_se3_priorvec.hpp ]; then
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I/root/reference/include -o "$OUT/libprior_ref.so" "$HERE/prior_ref_api.cpp"
+    echo "built $OUT/libprior_ref.so"
   fi
 fi
 # g2o's own compute_dq_dR (dquat2mat.cpp + its Maxima-generated cases), as they are in the zip: the table behind EdgeSE3::linearizeOplus

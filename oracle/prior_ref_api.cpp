@@ -1,0 +1,44 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// C entry point over the reference's OWN unary edge classes - include/g2o/edge_se3_priorxy.hpp, edge_se3_priorxyz.hpp, edge_se3_priorquat.hpp,
+// edge_se3_priorvec.hpp, included as they are - compiled against stand-ins for the g2o and Eigen headers they include (oracle/ref_stubs/):
+// setMeasurement followed by computeError on one VertexSE3, i.e. what GraphSLAM::add_se3_prior_*_edge sets up (src/global_graph/graph_slam.cpp:194-240).
+#include <g2o/edge_se3_priorxy.hpp>
+#include <g2o/edge_se3_priorxyz.hpp>
+#include <g2o/edge_se3_priorquat.hpp>
+#include <g2o/edge_se3_priorvec.hpp>
+
+static g2o::Isometry3D iso_from_qt7(const double* v) {      // x y z qx qy qz qw, quaternion normalised as VertexSE3::read / fromVectorQT do
+  Eigen::Quaterniond q(v[6], v[3], v[4], v[5]);
+  q.normalize();
+  g2o::Isometry3D t;
+  t = q.toRotationMatrix();
+  t.translation() = Eigen::Vector3d(v[0], v[1], v[2]);
+  return t;
+}
+
+// kind: 1 xy (meas x y), 2 xyz (x y z), 3 quat (qx qy qz qw), 4 vec (direction 3, measurement 3); e6 zero-padded
+extern "C" void pref_prior_error(int kind, const double* meas, const double* x7, double* e6) {
+  g2o::VertexSE3 v;
+  v.setEstimate(iso_from_qt7(x7));
+  for (int i = 0; i < 6; i++) e6[i] = 0.0;
+  if (kind == 1) {
+    g2o::EdgeSE3PriorXY e; e.vertices()[0] = &v;
+    Eigen::Vector2d m; m(0) = meas[0]; m(1) = meas[1];
+    e.setMeasurement(m); e.computeError();
+    for (int i = 0; i < 2; i++) e6[i] = e.error()(i);
+  } else if (kind == 2) {
+    g2o::EdgeSE3PriorXYZ e; e.vertices()[0] = &v;
+    e.setMeasurement(Eigen::Vector3d(meas[0], meas[1], meas[2])); e.computeError();
+    for (int i = 0; i < 3; i++) e6[i] = e.error()(i);
+  } else if (kind == 3) {
+    g2o::EdgeSE3PriorQuat e; e.vertices()[0] = &v;
+    e.setMeasurement(Eigen::Quaterniond(meas[3], meas[0], meas[1], meas[2])); e.computeError();
+    for (int i = 0; i < 3; i++) e6[i] = e.error()(i);
+  } else if (kind == 4) {
+    g2o::EdgeSE3PriorVec e; e.vertices()[0] = &v;
+    Eigen::Matrix<double, 6, 1> m;
+    for (int i = 0; i < 6; i++) m[i] = meas[i];
+    e.setMeasurement(m); e.computeError();
+    for (int i = 0; i < 3; i++) e6[i] = e.error()(i);
+  }
+}

@@ -217,6 +217,7 @@ class Matrix {
     return DotRule<S, R * C>::run(*this, o);
   }
   void normalize() { const S n = norm(); for (int i = 0; i < R * C; i++) d_[i] /= n; }
+  Matrix normalized() const { Matrix m(*this); m.normalize(); return m; }
   bool operator==(const Matrix& o) const { for (int i = 0; i < R * C; i++) if (!(d_[i] == o.d_[i])) return false; return true; }
   bool operator!=(const Matrix& o) const { return !(*this == o); }
   Matrix& operator-=(const Matrix& o) { for (int i = 0; i < R * C; i++) d_[i] -= o.d_[i]; return *this; }
@@ -311,6 +312,7 @@ typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 2, 1> Vector2d;
 
 // Eigen::Quaternion<S>, coefficients (x, y, z, w) with the (w, x, y, z) constructor; Geometry/Quaternion.h semantics.
 template <typename S>
@@ -346,11 +348,20 @@ class Quaternion {
   S x() const { return x_; }
   S y() const { return y_; }
   S z() const { return z_; }
+  S& w() { return w_; }
+  S& x() { return x_; }
+  S& y() { return y_; }
+  S& z() { return z_; }
+  Matrix<S, 4, 1> coeffs() const { return Matrix<S, 4, 1>(x_, y_, z_, w_); }      // Eigen's coefficient order: x, y, z, w
   Matrix<S, 3, 1> vec() const { return Matrix<S, 3, 1>(x_, y_, z_); }
-  struct Coeffs {            // q.coeffs(): (x, y, z, w); only `*= scalar` and head<3>() are used on it
+  struct Coeffs {            // q.coeffs() of a non-const quaternion: (x, y, z, w), writable
     Quaternion& q;
     template <typename T> Coeffs& operator*=(T s) { q.x_ *= s; q.y_ *= s; q.z_ *= s; q.w_ *= s; return *this; }
     template <int N> Matrix<S, 3, 1> head() const { static_assert(N == 3, "head<3>"); return Matrix<S, 3, 1>(q.x_, q.y_, q.z_); }
+    operator Matrix<S, 4, 1>() const { return Matrix<S, 4, 1>(q.x_, q.y_, q.z_, q.w_); }
+    Matrix<S, 4, 1> operator-() const { return Matrix<S, 4, 1>(-q.x_, -q.y_, -q.z_, -q.w_); }
+    Coeffs& operator=(const Matrix<S, 4, 1>& v) { q.x_ = v(0); q.y_ = v(1); q.z_ = v(2); q.w_ = v(3); return *this; }
+    S dot(const Matrix<S, 4, 1>& o) const { return static_cast<Matrix<S, 4, 1> >(*this).dot(o); }
   };
   Coeffs coeffs() { return Coeffs{*this}; }
   void setIdentity() { x_ = y_ = z_ = S(0); w_ = S(1); }

@@ -473,3 +473,46 @@ def test_lm_control_flow_against_g2o_own_code():
             assert np.array_equal(out, o.poses()), name
             rejected += int((tr[:, 2] > 1).sum())
     assert rejected > 0                                      # the trial loop (pop, lambda *= ni) was exercised
+
+
+def test_prior_edges_against_the_reference_own_classes():
+    """The reference's OWN unary edge classes - include/g2o/edge_se3_priorxy.hpp, _priorxyz.hpp, _priorquat.hpp, _priorvec.hpp, included as they
+    are and compiled against stand-ins for the g2o / Eigen headers they include (oracle/prior_ref_api.cpp) - against the restatement:
+    setMeasurement (the quaternion's sign flip, the two normalisations of the vector prior) followed by computeError on random poses,
+    half-turn poses and measurements with negative w."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "libprior_ref.so")
+    if not os.path.exists(so):
+        if os.path.exists("/root/reference/include/g2o/edge_se3_priorvec.hpp"):
+            import subprocess
+            subprocess.call(["sh", os.path.join(root, "oracle", "build_ref.sh")])
+        if not os.path.exists(so):
+            pytest.skip("no compiled reference prior edges")
+    G = ctypes.CDLL(so)
+    G.pref_prior_error.restype = None; G.pref_prior_error.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(47)
+    worst = 0.0
+    for k in range(400):
+        q = rng.normal(size=4)
+        if k % 3 == 0:
+            q[0] *= 0.02
+        q /= np.linalg.norm(q)
+        x7 = np.concatenate([rng.normal(0, 10, 3), q[1:], q[:1]])
+        for kind in (1, 2, 3, 4):
+            meas = np.zeros(8)
+            if kind in (1, 2):
+                meas[:3] = rng.normal(0, 10, 3)
+            elif kind == 3:
+                mq = rng.normal(size=4); mq /= np.linalg.norm(mq)
+                meas[:4] = mq                                # x y z w, either sign of w
+            else:
+                meas[:6] = rng.normal(0, 3, 6)               # direction and measured vector, both normalised by setMeasurement
+            want = np.zeros(6)
+            G.pref_prior_error(kind, meas.ctypes.data, x7.ctypes.data, want.ctypes.data)
+            got = P.prior_error(kind, meas, x7)
+            if kind == 4:                                    # linear().inverse(): the stand-in's 3 x 3 inverse and the restatement's differ in the last bit
+                worst = max(worst, float(np.abs(got - want).max()))
+                assert np.abs(got - want).max() <= 2e-15, (kind, got, want)
+            else:
+                assert np.array_equal(got, want), (kind, got, want)
