@@ -91,10 +91,16 @@ PY
     /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I/root/reference/include -o "$OUT/libinfo_ref.so" "$ICPP" "$HERE/info_ref_api.cpp"
     echo "built $OUT/libinfo_ref.so"
   fi
-  # The reference's own unary edges of the global graph (GPS / IMU priors): include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp as they are, against
+  # The reference's own unary edges of the global graph (GPS / IMU priors, floor plane): include/g2o/edge_se3_prior{xy,xyz,quat,vec}.hpp and
+  # edge_se3_plane.hpp as they are (the latter with g2o's own plane3d.h from the zip), against
   # stand-ins for the g2o / Eigen headers they include
   if [ -f /root/reference/include/g2o/edge_se3_priorvec.hpp ]; then
-    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I/root/reference/include -o "$OUT/libprior_ref.so" "$HERE/prior_ref_api.cpp"
+    python3 - "$ZIP" "$TMP" <<'PY'
+import sys, zipfile
+zipfile.ZipFile(sys.argv[1]).extract("g2o/g2o/types/slam3d_addons/plane3d.h", sys.argv[2])      # g2o's own Plane3D, for edge_se3_plane.hpp
+PY
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d_addons" \
+        -I/root/reference/include -o "$OUT/libprior_ref.so" "$HERE/prior_ref_api.cpp"
     echo "built $OUT/libprior_ref.so"
   fi
 fi

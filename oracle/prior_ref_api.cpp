@@ -1,11 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
 // C entry point over the reference's OWN unary edge classes - include/g2o/edge_se3_priorxy.hpp, edge_se3_priorxyz.hpp, edge_se3_priorquat.hpp,
-// edge_se3_priorvec.hpp, included as they are - compiled against stand-ins for the g2o and Eigen headers they include (oracle/ref_stubs/):
+// edge_se3_priorvec.hpp and edge_se3_plane.hpp, included as they are - compiled against stand-ins for the g2o and Eigen headers they include (oracle/ref_stubs/):
 // setMeasurement followed by computeError on one VertexSE3, i.e. what GraphSLAM::add_se3_prior_*_edge sets up (src/global_graph/graph_slam.cpp:194-240).
 #include <g2o/edge_se3_priorxy.hpp>
 #include <g2o/edge_se3_priorxyz.hpp>
 #include <g2o/edge_se3_priorquat.hpp>
 #include <g2o/edge_se3_priorvec.hpp>
+#include <g2o/edge_se3_plane.hpp>      // with g2o's own types/slam3d_addons/plane3d.h (unpacked from the vendored zip) behind the VertexPlane stand-in
 
 static g2o::Isometry3D iso_from_qt7(const double* v) {      // x y z qx qy qz qw, quaternion normalised as VertexSE3::read / fromVectorQT do
   Eigen::Quaterniond q(v[6], v[3], v[4], v[5]);
@@ -16,7 +17,8 @@ static g2o::Isometry3D iso_from_qt7(const double* v) {      // x y z qx qy qz qw
   return t;
 }
 
-// kind: 1 xy (meas x y), 2 xyz (x y z), 3 quat (qx qy qz qw), 4 vec (direction 3, measurement 3); e6 zero-padded
+// kind: 1 xy (meas x y), 2 xyz (x y z), 3 quat (qx qy qz qw), 4 vec (direction 3, measurement 3), 5 plane (measured plane 4, the fixed
+// VertexPlane's coefficients 4); e6 zero-padded
 extern "C" void pref_prior_error(int kind, const double* meas, const double* x7, double* e6) {
   g2o::VertexSE3 v;
   v.setEstimate(iso_from_qt7(x7));
@@ -33,6 +35,14 @@ extern "C" void pref_prior_error(int kind, const double* meas, const double* x7,
   } else if (kind == 3) {
     g2o::EdgeSE3PriorQuat e; e.vertices()[0] = &v;
     e.setMeasurement(Eigen::Quaterniond(meas[3], meas[0], meas[1], meas[2])); e.computeError();
+    for (int i = 0; i < 3; i++) e6[i] = e.error()(i);
+  } else if (kind == 5) {
+    g2o::VertexPlane vp;
+    Eigen::Vector4d pm, pv;
+    for (int i = 0; i < 4; i++) { pm(i) = meas[i]; pv(i) = meas[4 + i]; }
+    vp.setEstimate(g2o::Plane3D(pv));
+    g2o::EdgeSE3Plane e; e.vertices()[0] = &v; e.vertices()[1] = &vp;
+    e.setMeasurement(g2o::Plane3D(pm)); e.computeError();
     for (int i = 0; i < 3; i++) e6[i] = e.error()(i);
   } else if (kind == 4) {
     g2o::EdgeSE3PriorVec e; e.vertices()[0] = &v;

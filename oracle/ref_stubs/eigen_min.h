@@ -43,6 +43,7 @@ class BlockRef {
     return v;
   }
   void setIdentity() { for (int r = 0; r < RB; r++) for (int c = 0; c < CB; c++) m_(r0_ + r, c0_ + c) = r == c ? S(1) : S(0); }
+  S norm() const { return static_cast<Matrix<S, RB, CB> >(*this).norm(); }
 
  private:
   Matrix<S, R, C>& m_;
@@ -249,6 +250,13 @@ class Matrix {
   Matrix<S, R, C2> operator*(const Transposed<S, C, C2>& t) const { return (*this) * t.eval(); }     // column x row^T: outer product (one product per coefficient)
   template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
   Matrix& operator/=(T s) { for (int i = 0; i < R * C; i++) d_[i] /= static_cast<S>(s); return *this; }
+  static Matrix UnitX() { static_assert(R * C == 3, "unit vector"); return Matrix(S(1), S(0), S(0)); }
+  static Matrix UnitY() { static_assert(R * C == 3, "unit vector"); return Matrix(S(0), S(1), S(0)); }
+  static Matrix UnitZ() { static_assert(R * C == 3, "unit vector"); return Matrix(S(0), S(0), S(1)); }
+  template <int R0, int C0, int RB, int CB>
+  S dot(const BlockRef<S, R0, C0, RB, CB>& b) const { return dot(static_cast<Matrix<S, RB, CB> >(b)); }
+  template <int R0, int C0, int CB>
+  Matrix<S, R, CB> operator*(const BlockRef<S, R0, C0, C, CB>& b) const { return (*this) * static_cast<Matrix<S, C, CB> >(b); }
   static Matrix Ones() { Matrix m; for (int i = 0; i < R * C; i++) m.d_[i] = S(1); return m; }
   const Matrix& array() const { return *this; }                           // coefficient-wise view: the comparisons below
   struct BoolArray { bool b[R * C]; bool all() const { for (int i = 0; i < R * C; i++) if (!b[i]) return false; return true; } };
@@ -399,6 +407,21 @@ class Quaternion {
 };
 typedef Quaternion<double> Quaterniond;
 
+// Eigen::AngleAxisd: only `AngleAxisd(a, axis) * AngleAxisd(b, axis2)` followed by toRotationMatrix() is used (g2o's Plane3D::rotation):
+// the product of two angle-axis rotations is the product of their quaternions (cos(a/2), sin(a/2) axis)
+template <typename S>
+class AngleAxis {
+ public:
+  AngleAxis(S angle, const Matrix<S, 3, 1>& axis) : angle_(angle), axis_(axis) {}
+  Quaternion<S> toQuaternion() const { const S s = std::sin(S(0.5) * angle_), c = std::cos(S(0.5) * angle_); return Quaternion<S>(c, s * axis_(0), s * axis_(1), s * axis_(2)); }
+  Quaternion<S> operator*(const AngleAxis& o) const { return toQuaternion() * o.toQuaternion(); }
+
+ private:
+  S angle_;
+  Matrix<S, 3, 1> axis_;
+};
+typedef AngleAxis<double> AngleAxisd;
+
 typedef Matrix<int, 4, 1> Vector4i;
 typedef Matrix<int, 4, 1> Array4i;          // only constructed from a Vector4i and compared coefficient-wise
 
@@ -461,6 +484,7 @@ class Isometry3 {
   template <typename T>
   Isometry3<T> cast() const { Isometry3<T> o; o.matrix() = m_.template cast<T>(); return o; }
   Matrix<S, 3, 3> linear() const { return m_.template block<3, 3>(0, 0); }
+  Matrix<S, 3, 3> rotation() const { return linear(); }      // Isometry mode: the linear part is the rotation
   Matrix<S, 3, 1> translation() const { return m_.template block<3, 1>(0, 3); }
   BlockRef<S, 4, 4, 3, 1> translation() { return BlockRef<S, 4, 4, 3, 1>(m_, 0, 3); }
   Isometry3& operator=(const Matrix<S, 3, 3>& R) { m_.setIdentity(); m_.template block<3, 3>(0, 0) = R; return *this; }      // rotation, zero translation

@@ -476,8 +476,8 @@ def test_lm_control_flow_against_g2o_own_code():
 
 
 def test_prior_edges_against_the_reference_own_classes():
-    """The reference's OWN unary edge classes - include/g2o/edge_se3_priorxy.hpp, _priorxyz.hpp, _priorquat.hpp, _priorvec.hpp, included as they
-    are and compiled against stand-ins for the g2o / Eigen headers they include (oracle/prior_ref_api.cpp) - against the restatement:
+    """The reference's OWN unary edge classes - include/g2o/edge_se3_priorxy.hpp, _priorxyz.hpp, _priorquat.hpp, _priorvec.hpp and edge_se3_plane.hpp (with
+    g2o's own plane3d.h from the vendored zip), included as they are and compiled against stand-ins for the g2o / Eigen headers they include (oracle/prior_ref_api.cpp) - against the restatement:
     setMeasurement (the quaternion's sign flip, the two normalisations of the vector prior) followed by computeError on random poses,
     half-turn poses and measurements with negative w."""
     import ctypes
@@ -499,9 +499,12 @@ def test_prior_edges_against_the_reference_own_classes():
             q[0] *= 0.02
         q /= np.linalg.norm(q)
         x7 = np.concatenate([rng.normal(0, 10, 3), q[1:], q[:1]])
-        for kind in (1, 2, 3, 4):
+        for kind in (1, 2, 3, 4, 5):
             meas = np.zeros(8)
-            if kind in (1, 2):
+            if kind == 5:                                    # EdgeSE3Plane: measured plane, the (fixed) plane vertex; Plane3D normalises both
+                meas[:4] = np.concatenate([rng.normal(size=3), rng.normal(0, 2, 1)])
+                meas[4:] = np.concatenate([rng.normal(size=3), rng.normal(0, 2, 1)])
+            elif kind in (1, 2):
                 meas[:3] = rng.normal(0, 10, 3)
             elif kind == 3:
                 mq = rng.normal(size=4); mq /= np.linalg.norm(mq)
@@ -511,7 +514,9 @@ def test_prior_edges_against_the_reference_own_classes():
             want = np.zeros(6)
             G.pref_prior_error(kind, meas.ctypes.data, x7.ctypes.data, want.ctypes.data)
             got = P.prior_error(kind, meas, x7)
-            if kind == 4:                                    # linear().inverse(): the stand-in's 3 x 3 inverse and the restatement's differ in the last bit
+            if kind == 5:
+                assert np.abs(got - want).max() <= 1e-15, (kind, got, want)
+            elif kind == 4:                                  # linear().inverse(): the stand-in's 3 x 3 inverse and the restatement's differ in the last bit
                 worst = max(worst, float(np.abs(got - want).max()))
                 assert np.abs(got - want).max() <= 2e-15, (kind, got, want)
             else:
