@@ -97,9 +97,19 @@ PY
   if [ -f /root/reference/include/g2o/edge_se3_priorvec.hpp ]; then
     python3 - "$ZIP" "$TMP" <<'PY'
 import sys, zipfile
-zipfile.ZipFile(sys.argv[1]).extract("g2o/g2o/types/slam3d_addons/plane3d.h", sys.argv[2])      # g2o's own Plane3D, for edge_se3_plane.hpp
+z = zipfile.ZipFile(sys.argv[1])
+for n in ("g2o/g2o/types/slam3d_addons/plane3d.h",          # g2o's own Plane3D, for edge_se3_plane.hpp
+          "g2o/g2o/core/base_unary_edge.hpp", "g2o/g2o/core/base_binary_edge.hpp",      # the numeric linearizeOplus of both edge bases
+          "g2o/g2o/types/slam3d/isometry3d_mappings.cpp"):   # fromVectorMQT behind VertexSE3::oplus
+    z.extract(n, sys.argv[2])
 PY
-    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d_addons" \
+    python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/base_unary_edge.hpp" "$TMP/g2o_unary.inc" "BaseUnaryEdge<D, E, VertexXiType>" "linearizeOplus()"
+    python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/base_binary_edge.hpp" "$TMP/g2o_binary.inc" "BaseBinaryEdge<D, E, VertexXiType, VertexXjType>" \
+        "linearizeOplus()"
+    python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/types/slam3d/isometry3d_mappings.cpp" "$TMP/g2o_map_p.inc" - normalize toCompactQuaternion \
+        fromCompactQuaternion toVectorMQT fromVectorMQT
+    /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DG2O_MAP_BODIES="\"$TMP/g2o_map_p.inc\"" -DG2O_UNARY_BODIES="\"$TMP/g2o_unary.inc\"" \
+        -DG2O_BINARY_BODIES="\"$TMP/g2o_binary.inc\"" -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d_addons" \
         -I/root/reference/include -o "$OUT/libprior_ref.so" "$HERE/prior_ref_api.cpp"
     echo "built $OUT/libprior_ref.so"
   fi

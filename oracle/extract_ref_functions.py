@@ -57,7 +57,8 @@ def extract(text, cls, name):
     out = []
     plain = cls.startswith("=")            # "=Class": a member of a non-template class, definition starts on the line of its return type
     prefix = cls[1:] if plain else (cls if "<" in cls else cls + "<PointSource, PointTarget>")
-    pat = re.compile(re.escape(prefix) + r"::" + re.escape(name) + r"\s*\(")
+    # "name()" selects the overload without parameters
+    pat = re.compile(re.escape(prefix) + r"::" + (re.escape(name[:-2]) + r"\s*\(\s*\)" if name.endswith("()") else re.escape(name) + r"\s*\("))
     for m in pat.finditer(text):
         start = text.rfind("\n", 0, m.start()) + 1 if plain else text.rfind("template", 0, m.start())
         brace = text.index("{", m.end())

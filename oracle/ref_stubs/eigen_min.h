@@ -141,6 +141,7 @@ class ColRef {
   template <int N>
   BlockRef<S, R, C, N, 1> head() { return BlockRef<S, R, C, N, 1>(m_, 0, c_); }
   BlockRef<S, R, C, 3, 1> head(int n) { assert(n == 3); (void)n; return BlockRef<S, R, C, 3, 1>(m_, 0, c_); }
+  ColRef& operator=(const Matrix<S, R, 1>& v) { for (int r = 0; r < R; r++) m_(r, c_) = v(r); return *this; }
 
  private:
   Matrix<S, R, C>& m_;

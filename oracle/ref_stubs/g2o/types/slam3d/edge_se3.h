@@ -17,10 +17,16 @@ class BaseBinaryEdge {
   const InformationType& information() const { return _information; }
   const ErrorVector& error() const { return _error; }
   std::vector<HyperGraphVertex*>& vertices() { return _vertices; }
+  typedef Eigen::Matrix<double, D, V1::Dimension> JacobianXiOplusType;
+  typedef Eigen::Matrix<double, D, V2::Dimension> JacobianXjOplusType;
+  void linearizeOplus();                      // g2o's own definition (core/base_binary_edge.hpp), taken at build time: G2O_BINARY_BODIES
+  const JacobianXiOplusType& jacobianOplusXi() const { return _jacobianOplusXi; }
  protected:
   std::vector<HyperGraphVertex*> _vertices;
   E _measurement;
   ErrorVector _error;
   InformationType _information;
+  JacobianXiOplusType _jacobianOplusXi;
+  JacobianXjOplusType _jacobianOplusXj;
 };
 }  // namespace g2o

@@ -3,17 +3,31 @@
 #pragma once
 #include <istream>
 #include <ostream>
+#include <algorithm>
 #include <vector>
 #include <Eigen/Core>
 namespace g2o {
 typedef Eigen::Isometry3d Isometry3D;
 struct HyperGraphVertex { virtual ~HyperGraphVertex() {} };
+namespace internal { Isometry3D fromVectorMQT(const Eigen::Matrix<double, 6, 1>& v); }      // g2o's own (isometry3d_mappings.cpp), compiled in prior_ref_api.cpp
 class VertexSE3 : public HyperGraphVertex {
  public:
+  static const int Dimension = 6;
   const Isometry3D& estimate() const { return _estimate; }
   void setEstimate(const Isometry3D& e) { _estimate = e; }
+  bool fixed() const { return _fixed; }
+  void setFixed(bool f) { _fixed = f; }
+  void push() { _backup.push_back(_estimate); }
+  void pop() { _estimate = _backup.back(); _backup.pop_back(); }
+  void oplus(const double* update) {      // VertexSE3::oplusImpl (vertex_se3.h:90-99) without the every-1000-calls re-orthogonalisation
+    Eigen::Matrix<double, 6, 1> v;
+    for (int i = 0; i < 6; i++) v[i] = update[i];
+    _estimate = _estimate * internal::fromVectorMQT(v);
+  }
  private:
   Isometry3D _estimate;
+  std::vector<Isometry3D> _backup;
+  bool _fixed = false;
 };
 template <int D, typename E, typename V>
 class BaseUnaryEdge {
@@ -31,10 +45,14 @@ class BaseUnaryEdge {
   const ErrorVector& error() const { return _error; }
   const E& measurement() const { return _measurement; }
   std::vector<HyperGraphVertex*>& vertices() { return _vertices; }
+  typedef Eigen::Matrix<double, D, V::Dimension> JacobianXiOplusType;
+  void linearizeOplus();                      // g2o's own definition (core/base_unary_edge.hpp), taken at build time: G2O_UNARY_BODIES
+  const JacobianXiOplusType& jacobianOplusXi() const { return _jacobianOplusXi; }
  protected:
   std::vector<HyperGraphVertex*> _vertices;
   E _measurement;
   ErrorVector _error;
   InformationType _information;
+  JacobianXiOplusType _jacobianOplusXi;
 };
 }  // namespace g2o

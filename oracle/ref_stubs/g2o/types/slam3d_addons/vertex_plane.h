@@ -6,9 +6,17 @@
 namespace g2o {
 class VertexPlane : public HyperGraphVertex {
  public:
+  static const int Dimension = 3;
   const Plane3D& estimate() const { return _estimate; }
   void setEstimate(const Plane3D& p) { _estimate = p; }
+  bool fixed() const { return _fixed; }
+  void setFixed(bool f) { _fixed = f; }
+  void push() { _backup.push_back(_estimate); }
+  void pop() { _estimate = _backup.back(); _backup.pop_back(); }
+  void oplus(const double* update) { _estimate.oplus(Eigen::Vector3d(update[0], update[1], update[2])); }      // vertex_plane.h oplusImpl
  private:
   Plane3D _estimate;
+  std::vector<Plane3D> _backup;
+  bool _fixed = false;
 };
 }  // namespace g2o

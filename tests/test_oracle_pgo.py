@@ -491,6 +491,7 @@ def test_prior_edges_against_the_reference_own_classes():
             pytest.skip("no compiled reference prior edges")
     G = ctypes.CDLL(so)
     G.pref_prior_error.restype = None; G.pref_prior_error.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    G.pref_prior_jacobian.restype = None; G.pref_prior_jacobian.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     rng = np.random.default_rng(47)
     worst = 0.0
     for k in range(400):
@@ -514,6 +515,15 @@ def test_prior_edges_against_the_reference_own_classes():
             want = np.zeros(6)
             G.pref_prior_error(kind, meas.ctypes.data, x7.ctypes.data, want.ctypes.data)
             got = P.prior_error(kind, meas, x7)
+            # the numeric Jacobian: g2o's own BaseUnaryEdge / BaseBinaryEdge::linearizeOplus (1e-9 central differences through push / oplus /
+            # computeError / pop) around the same classes.  A last-bit difference of an error value is worth 5e8 times as much here.
+            Jw = np.zeros(36)
+            G.pref_prior_jacobian(kind, meas.ctypes.data, x7.ctypes.data, Jw.ctypes.data)
+            Jg = P.prior_jacobian(kind, meas, x7).reshape(36)
+            if kind in (1, 2, 3):
+                assert np.array_equal(Jg, Jw), (kind, np.abs(Jg - Jw).max())
+            else:
+                assert np.abs(Jg - Jw).max() <= 2e-6, (kind, np.abs(Jg - Jw).max())
             if kind == 5:
                 assert np.abs(got - want).max() <= 1e-15, (kind, got, want)
             elif kind == 4:                                  # linear().inverse(): the stand-in's 3 x 3 inverse and the restatement's differ in the last bit
