@@ -100,16 +100,20 @@ import sys, zipfile
 z = zipfile.ZipFile(sys.argv[1])
 for n in ("g2o/g2o/types/slam3d_addons/plane3d.h",          # g2o's own Plane3D, for edge_se3_plane.hpp
           "g2o/g2o/core/base_unary_edge.hpp", "g2o/g2o/core/base_binary_edge.hpp",      # the numeric linearizeOplus of both edge bases
+          "g2o/g2o/core/robust_kernel_impl.cpp",             # the Huber kernel constructQuadraticForm weighs with
           "g2o/g2o/types/slam3d/isometry3d_mappings.cpp"):   # fromVectorMQT behind VertexSE3::oplus
     z.extract(n, sys.argv[2])
 PY
-    python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/base_unary_edge.hpp" "$TMP/g2o_unary.inc" "BaseUnaryEdge<D, E, VertexXiType>" "linearizeOplus()"
+    python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/base_unary_edge.hpp" "$TMP/g2o_unary.inc" "BaseUnaryEdge<D, E, VertexXiType>" "linearizeOplus()" \
+        constructQuadraticForm
     python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/base_binary_edge.hpp" "$TMP/g2o_binary.inc" "BaseBinaryEdge<D, E, VertexXiType, VertexXjType>" \
-        "linearizeOplus()"
+        "linearizeOplus()" constructQuadraticForm
+    python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/robust_kernel_impl.cpp" "$TMP/g2o_huber_p.inc" "=RobustKernelHuber" robustify
     python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/types/slam3d/isometry3d_mappings.cpp" "$TMP/g2o_map_p.inc" - normalize toCompactQuaternion \
         fromCompactQuaternion toVectorMQT fromVectorMQT
     /usr/bin/g++ -O2 -std=gnu++17 -ffp-contract=off -fPIC -shared -DG2O_MAP_BODIES="\"$TMP/g2o_map_p.inc\"" -DG2O_UNARY_BODIES="\"$TMP/g2o_unary.inc\"" \
-        -DG2O_BINARY_BODIES="\"$TMP/g2o_binary.inc\"" -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" -I"$TMP/g2o/g2o/types/slam3d_addons" \
+        -DG2O_BINARY_BODIES="\"$TMP/g2o_binary.inc\"" -DG2O_HUBER_BODIES="\"$TMP/g2o_huber_p.inc\"" -I"$HERE/ref_stubs" -I"$HERE/ref_stubs/g2o_api" \
+        -I"$TMP/g2o/g2o/types/slam3d_addons" \
         -I/root/reference/include -o "$OUT/libprior_ref.so" "$HERE/prior_ref_api.cpp"
     echo "built $OUT/libprior_ref.so"
   fi

@@ -12,7 +12,6 @@
 // pop) and the MQT mappings behind VertexSE3::oplus, taken from the vendored zip at build time
 namespace g2o {
 typedef Eigen::Matrix<double, 3, 3> Matrix3D;
-typedef Eigen::Matrix<double, 3, 1> Vector3D;
 typedef Eigen::Matrix<double, 6, 1> Vector6d;
 namespace internal {
 inline Isometry3D::ConstLinearPart extractRotation(const Isometry3D& A) { return A.matrix().topLeftCorner<3, 3>(); }
@@ -25,6 +24,29 @@ using namespace std;
 }  // namespace internal
 #include G2O_UNARY_BODIES
 #include G2O_BINARY_BODIES
+#include G2O_HUBER_BODIES
+
+// An edge whose Jacobians, error and information are handed in, to run g2o's own constructQuadraticForm on them
+class GivenBinaryEdge : public BaseBinaryEdge<6, Isometry3D, VertexSE3, VertexSE3> {
+ public:
+  void computeError() override {}
+  bool read(std::istream&) override { return false; }
+  bool write(std::ostream&) const override { return false; }
+  void give(const double* Ji, const double* Jj, const double* info36, const double* err6) {
+    for (int r = 0; r < 6; r++) { _error(r) = err6[r]; for (int c = 0; c < 6; c++) { _jacobianOplusXi(r, c) = Ji[r * 6 + c]; _jacobianOplusXj(r, c) = Jj[r * 6 + c]; _information(r, c) = info36[r * 6 + c]; } }
+    _hessian.setZero(); _hessianTransposed.setZero();
+  }
+};
+template <int D>
+class GivenUnaryEdge : public BaseUnaryEdge<D, Eigen::Matrix<double, D, 1>, VertexSE3> {
+ public:
+  void computeError() override {}
+  bool read(std::istream&) override { return false; }
+  bool write(std::ostream&) const override { return false; }
+  void give(const double* J36, const double* info36, const double* err6) {
+    for (int r = 0; r < D; r++) { this->_error(r) = err6[r]; for (int c = 0; c < 6; c++) this->_jacobianOplusXi(r, c) = J36[r * 6 + c]; for (int c = 0; c < D; c++) this->_information(r, c) = info36[r * 6 + c]; }
+  }
+};
 }  // namespace g2o
 
 static g2o::Isometry3D iso_from_qt7(const double* v) {      // x y z qx qy qz qw, quaternion normalised as VertexSE3::read / fromVectorQT do
@@ -103,4 +125,31 @@ extern "C" void pref_prior_jacobian(int kind, const double* meas, const double* 
     g2o::EdgeSE3Plane e; e.vertices()[0] = &v; e.vertices()[1] = &vp;
     e.setMeasurement(g2o::Plane3D(pm)); e.computeError(); e.linearizeOplus(); put(e.jacobianOplusXi(), 3);
   }
+}
+
+// g2o's own BaseBinaryEdge::constructQuadraticForm on given Jacobians (row-major 6 x 6), information, error; huber <= 0: no kernel.
+// Out: the two diagonal blocks, the two right-hand sides and the off-diagonal block (i, j), all row-major, starting from zero.
+extern "C" void pref_quadratic_form_binary(const double* Ji, const double* Jj, const double* info36, const double* err6, double huber, int fixed_i, int fixed_j,
+                                           double* Ai36, double* bi6, double* Aj36, double* bj6, double* Hij36) {
+  g2o::VertexSE3 vi, vj;
+  vi.setFixed(fixed_i != 0); vj.setFixed(fixed_j != 0);
+  vi.A().setZero(); vi.b().setZero(); vj.A().setZero(); vj.b().setZero();
+  g2o::GivenBinaryEdge e;
+  e.vertices()[0] = &vi; e.vertices()[1] = &vj;
+  e.give(Ji, Jj, info36, err6);
+  g2o::RobustKernelHuber k;
+  if (huber > 0) { k._delta = huber; e.setRobustKernel(&k); }
+  e.constructQuadraticForm();
+  for (int r = 0; r < 6; r++) { bi6[r] = vi.b()(r); bj6[r] = vj.b()(r); for (int c = 0; c < 6; c++) { Ai36[r * 6 + c] = vi.A()(r, c); Aj36[r * 6 + c] = vj.A()(r, c); Hij36[r * 6 + c] = e._hessian(r, c); } }
+}
+
+// g2o's own BaseUnaryEdge::constructQuadraticForm for an edge of dimension D (2 or 3) on one VertexSE3
+extern "C" void pref_quadratic_form_unary(int D, const double* J36, const double* info36, const double* err6, double huber, double* A36, double* b6) {
+  g2o::VertexSE3 v;
+  v.A().setZero(); v.b().setZero();
+  g2o::RobustKernelHuber k;
+  k._delta = huber;
+  if (D == 2) { g2o::GivenUnaryEdge<2> e; e.vertices()[0] = &v; e.give(J36, info36, err6); if (huber > 0) e.setRobustKernel(&k); e.constructQuadraticForm(); }
+  else { g2o::GivenUnaryEdge<3> e; e.vertices()[0] = &v; e.give(J36, info36, err6); if (huber > 0) e.setRobustKernel(&k); e.constructQuadraticForm(); }
+  for (int r = 0; r < 6; r++) { b6[r] = v.b()(r); for (int c = 0; c < 6; c++) A36[r * 6 + c] = v.A()(r, c); }
 }

@@ -118,6 +118,10 @@ class Transposed {      // R x C is the shape of the transposed matrix
   operator Matrix<S, R, C>() const { return t_; }
   const Matrix<S, R, C>& eval() const { return t_; }
   template <int C2>
+  Matrix<S, R, C2> operator*(const Transposed<S, C, C2>& o) const { return (*this) * o.eval(); }
+  template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
+  friend Transposed operator*(T s, const Transposed& t) { Transposed o(t); o.t_ = static_cast<S>(s) * t.t_; return o; }
+  template <int C2>
   Matrix<S, R, C2> operator*(const Matrix<S, C, C2>& o) const {
     Matrix<S, R, C2> m;
     for (int r = 0; r < R; r++)

@@ -19,8 +19,18 @@ class BaseBinaryEdge {
   std::vector<HyperGraphVertex*>& vertices() { return _vertices; }
   typedef Eigen::Matrix<double, D, V1::Dimension> JacobianXiOplusType;
   typedef Eigen::Matrix<double, D, V2::Dimension> JacobianXjOplusType;
-  void linearizeOplus();                      // g2o's own definition (core/base_binary_edge.hpp), taken at build time: G2O_BINARY_BODIES
+  void linearizeOplus();                      // g2o's own definitions (core/base_binary_edge.hpp), taken at build time: G2O_BINARY_BODIES
+  void constructQuadraticForm();
   const JacobianXiOplusType& jacobianOplusXi() const { return _jacobianOplusXi; }
+  const JacobianXjOplusType& jacobianOplusXj() const { return _jacobianOplusXj; }
+  RobustKernelHuber* robustKernel() const { return _kernel; }
+  void setRobustKernel(RobustKernelHuber* k) { _kernel = k; }
+  double chi2() const { return _error.dot(information() * _error); }                                             // base_edge.h
+  InformationType robustInformation(const Vector3D& rho) { InformationType result = rho[1] * _information; return result; }      // base_edge.h
+  RobustKernelHuber* _kernel = nullptr;
+  Eigen::Matrix<double, V1::Dimension, V2::Dimension> _hessian;                 // the off-diagonal block the edge owns (mapHessianMemory)
+  Eigen::Matrix<double, V2::Dimension, V1::Dimension> _hessianTransposed;
+  bool _hessianRowMajor = false;
  protected:
   std::vector<HyperGraphVertex*> _vertices;
   E _measurement;

@@ -9,6 +9,13 @@
 namespace g2o {
 typedef Eigen::Isometry3d Isometry3D;
 struct HyperGraphVertex { virtual ~HyperGraphVertex() {} };
+typedef Eigen::Matrix<double, 3, 1> Vector3D;
+// what constructQuadraticForm uses of a robust kernel; robustify is g2o's own RobustKernelHuber::robustify (G2O_HUBER_BODIES)
+class RobustKernelHuber {
+ public:
+  double _delta = 1.0;
+  void robustify(double e, Vector3D& rho) const;
+};
 namespace internal { Isometry3D fromVectorMQT(const Eigen::Matrix<double, 6, 1>& v); }      // g2o's own (isometry3d_mappings.cpp), compiled in prior_ref_api.cpp
 class VertexSE3 : public HyperGraphVertex {
  public:
@@ -17,6 +24,8 @@ class VertexSE3 : public HyperGraphVertex {
   void setEstimate(const Isometry3D& e) { _estimate = e; }
   bool fixed() const { return _fixed; }
   void setFixed(bool f) { _fixed = f; }
+  Eigen::Matrix<double, 6, 6>& A() { return _A; }      // the vertex's diagonal Hessian block and right-hand side (BaseVertex::A(), b())
+  Eigen::Matrix<double, 6, 1>& b() { return _b; }
   void push() { _backup.push_back(_estimate); }
   void pop() { _estimate = _backup.back(); _backup.pop_back(); }
   void oplus(const double* update) {      // VertexSE3::oplusImpl (vertex_se3.h:90-99) without the every-1000-calls re-orthogonalisation
@@ -28,6 +37,8 @@ class VertexSE3 : public HyperGraphVertex {
   Isometry3D _estimate;
   std::vector<Isometry3D> _backup;
   bool _fixed = false;
+  Eigen::Matrix<double, 6, 6> _A;
+  Eigen::Matrix<double, 6, 1> _b;
 };
 template <int D, typename E, typename V>
 class BaseUnaryEdge {
@@ -46,8 +57,14 @@ class BaseUnaryEdge {
   const E& measurement() const { return _measurement; }
   std::vector<HyperGraphVertex*>& vertices() { return _vertices; }
   typedef Eigen::Matrix<double, D, V::Dimension> JacobianXiOplusType;
-  void linearizeOplus();                      // g2o's own definition (core/base_unary_edge.hpp), taken at build time: G2O_UNARY_BODIES
+  void linearizeOplus();                      // g2o's own definitions (core/base_unary_edge.hpp), taken at build time: G2O_UNARY_BODIES
+  void constructQuadraticForm();
   const JacobianXiOplusType& jacobianOplusXi() const { return _jacobianOplusXi; }
+  RobustKernelHuber* robustKernel() const { return _kernel; }
+  void setRobustKernel(RobustKernelHuber* k) { _kernel = k; }
+  double chi2() const { return _error.dot(information() * _error); }                                             // base_edge.h
+  InformationType robustInformation(const Vector3D& rho) { InformationType result = rho[1] * _information; return result; }      // base_edge.h (the rho[2] term is commented out there)
+  RobustKernelHuber* _kernel = nullptr;
  protected:
   std::vector<HyperGraphVertex*> _vertices;
   E _measurement;

@@ -11,6 +11,8 @@ class VertexPlane : public HyperGraphVertex {
   void setEstimate(const Plane3D& p) { _estimate = p; }
   bool fixed() const { return _fixed; }
   void setFixed(bool f) { _fixed = f; }
+  Eigen::Matrix<double, 3, 3>& A() { return _A; }
+  Eigen::Matrix<double, 3, 1>& b() { return _b; }
   void push() { _backup.push_back(_estimate); }
   void pop() { _estimate = _backup.back(); _backup.pop_back(); }
   void oplus(const double* update) { _estimate.oplus(Eigen::Vector3d(update[0], update[1], update[2])); }      // vertex_plane.h oplusImpl
@@ -18,5 +20,7 @@ class VertexPlane : public HyperGraphVertex {
   Plane3D _estimate;
   std::vector<Plane3D> _backup;
   bool _fixed = false;
+  Eigen::Matrix<double, 3, 3> _A;
+  Eigen::Matrix<double, 3, 1> _b;
 };
 }  // namespace g2o

@@ -531,3 +531,82 @@ def test_prior_edges_against_the_reference_own_classes():
                 assert np.abs(got - want).max() <= 2e-15, (kind, got, want)
             else:
                 assert np.array_equal(got, want), (kind, got, want)
+
+
+def test_quadratic_form_against_g2o_own_code():
+    """g2o's own BaseBinaryEdge / BaseUnaryEdge::constructQuadraticForm (core/base_*_edge.hpp of the vendored zip, with its Huber kernel) on the
+    Jacobians, information and error of single edges, against what the restatement's build_system assembles for the same edge: both diagonal
+    blocks, the off-diagonal block, both right-hand sides, with and without kernel (inlier and outlier), fixed vertices, unary priors of
+    dimension 2 and 3.  g2o forms (A^T W) B, the restatement A^T (W B): agreement to rounding (1e-13 of the block's largest entry)."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "libprior_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("no compiled reference edges")
+    G = ctypes.CDLL(so)
+    vp, f64, i32 = ctypes.c_void_p, ctypes.c_double, ctypes.c_int
+    G.pref_quadratic_form_binary.restype = None; G.pref_quadratic_form_binary.argtypes = [vp, vp, vp, vp, f64, i32, i32, vp, vp, vp, vp, vp]
+    G.pref_quadratic_form_unary.restype = None; G.pref_quadratic_form_unary.argtypes = [i32, vp, vp, vp, f64, vp, vp]
+    rng = np.random.default_rng(53)
+
+    def pose():
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        return np.concatenate([rng.normal(0, 5, 3), q[1:], q[:1]])
+
+    def full_info(upper21):
+        M = np.zeros((6, 6)); k = 0
+        for r in range(6):
+            for c in range(r, 6):
+                M[r, c] = M[c, r] = upper21[k]; k += 1
+        return M
+
+    def close(a, b):
+        return np.abs(np.asarray(a) - np.asarray(b)).max() <= 1e-13 * max(1.0, np.abs(b).max())
+
+    seen_outlier = seen_inlier = 0
+    for k in range(120):
+        xi, xj = pose(), pose()
+        z = pose()
+        L = rng.normal(size=(6, 6)); info = L @ L.T + 6 * np.eye(6)
+        info21 = np.array([info[r, c] for r in range(6) for c in range(r, 6)])
+        hub = [0.0, 1.0, 1e6][k % 3]                         # no kernel, outlier (chi2 >> 1), inlier (huge delta)
+        fixed = np.array([k % 5 == 0, k % 7 == 0], np.uint8)
+        if fixed.all():
+            fixed[1] = 0
+        o = P.OraclePGO()
+        o.set_graph(np.stack([xi, xj]), np.array([[0, 1]], np.int32), z[None, :], info21[None, :], np.array([hub]), fixed)
+        lin = o.linearize()
+        err = P.edge_error(z, xi, xj)
+        Ji, Jj = lin["Ji"][0], lin["Jj"][0]
+        Ai, bi, Aj, bj, Hij = np.zeros((6, 6)), np.zeros(6), np.zeros((6, 6)), np.zeros(6), np.zeros((6, 6))
+        G.pref_quadratic_form_binary(np.ascontiguousarray(Ji).ctypes.data, np.ascontiguousarray(Jj).ctypes.data, np.ascontiguousarray(info).ctypes.data, err.ctypes.data,
+                                     float(hub), int(fixed[0]), int(fixed[1]), Ai.ctypes.data, bi.ctypes.data, Aj.ctypes.data, bj.ctypes.data, Hij.ctypes.data)
+        e2 = float(err @ info @ err)
+        if hub > 0:
+            seen_outlier += e2 > hub * hub
+            seen_inlier += e2 <= hub * hub
+        free = [v for v in (0, 1) if not fixed[v]]
+        blocks = {0: (Ai, bi), 1: (Aj, bj)}
+        for slot, v in enumerate(free):
+            assert close(lin["Hd"][slot], blocks[v][0]) and close(lin["b"][slot * 6:slot * 6 + 6], blocks[v][1]), (k, v)
+        if len(free) == 2:
+            assert close(lin["Ho"][0], Hij), k
+    assert seen_outlier > 10 and seen_inlier > 10
+    # unary priors: XY (D = 2) and XYZ (D = 3) on one free vertex, with and without kernel
+    for k in range(60):
+        x = pose()
+        kind = 1 + k % 2
+        D = 2 if kind == 1 else 3
+        meas = np.zeros(8); meas[:D] = x[:D] + rng.normal(0, 3.0, D)
+        Lm = rng.normal(size=(D, D)); infoD = Lm @ Lm.T + D * np.eye(D)
+        info = np.zeros((6, 6)); info[:D, :D] = infoD
+        info21 = np.array([info[r, c] for r in range(6) for c in range(r, 6)])
+        hub = [0.0, 0.5, 1e6][k % 3]
+        o = P.OraclePGO()
+        o.set_graph(x[None, :], np.array([[0, 0]], np.int32), meas[None, :7], info21[None, :], np.array([hub]), None, np.array([kind], np.int32))
+        lin = o.linearize()
+        err = P.prior_error(kind, meas, x)
+        J = P.prior_jacobian(kind, meas, x)
+        A, b = np.zeros((6, 6)), np.zeros(6)
+        G.pref_quadratic_form_unary(D, np.ascontiguousarray(J).ctypes.data, np.ascontiguousarray(info).ctypes.data, err.ctypes.data, float(hub), A.ctypes.data, b.ctypes.data)
+        assert close(lin["Hd"][0], A) and close(lin["b"][:6], b), (k, kind)
