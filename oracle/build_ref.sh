@@ -150,11 +150,14 @@ PY
   # oracle/lm_ref_harness.cpp includes oracle/pgo_oracle.cpp, so the library is a second copy of the oracle whose optimiser is g2o's code
   python3 - "$ZIP" "$TMP" <<'PY'
 import sys, zipfile
-zipfile.ZipFile(sys.argv[1]).extract("g2o/g2o/core/optimization_algorithm_levenberg.cpp", sys.argv[2])
+z = zipfile.ZipFile(sys.argv[1])
+z.extract("g2o/g2o/core/optimization_algorithm_levenberg.cpp", sys.argv[2])
+z.extract("g2o/g2o/core/optimization_algorithm_gauss_newton.cpp", sys.argv[2])
 PY
+  python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/optimization_algorithm_gauss_newton.cpp" "$TMP/g2o_gn.inc" "=OptimizationAlgorithmGaussNewton" solve
   python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/optimization_algorithm_levenberg.cpp" "$TMP/g2o_lm.inc" "=OptimizationAlgorithmLevenberg" \
       solve computeLambdaInit computeScale
-  /usr/bin/g++ -O3 -fopenmp -msse4.2 -ffp-contract=off -fPIC -std=c++17 -shared -DG2O_LM_BODIES="\"$TMP/g2o_lm.inc\"" -I"$HERE" -o "$OUT/liblm_ref.so" \
+  /usr/bin/g++ -O3 -fopenmp -msse4.2 -ffp-contract=off -fPIC -std=c++17 -shared -DG2O_LM_BODIES="\"$TMP/g2o_lm.inc\"" -DG2O_GN_BODIES="\"$TMP/g2o_gn.inc\"" -I"$HERE" -o "$OUT/liblm_ref.so" \
       "$HERE/lm_ref_harness.cpp" -ldl
   echo "built $OUT/liblm_ref.so"
 fi

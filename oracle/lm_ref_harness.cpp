@@ -2,8 +2,9 @@
 //
 // Runs g2o's OWN Levenberg-Marquardt control flow over the restatement's building blocks.  oracle/build_ref.sh unpacks
 // core/optimization_algorithm_levenberg.cpp from the reference's 3rdtools/g2o-a48ff8c.zip and oracle/extract_ref_functions.py writes the
-// definitions of OptimizationAlgorithmLevenberg::solve, ::computeLambdaInit and ::computeScale exactly as they stand into a temporary file
-// (G2O_LM_BODIES), compiled here into oracle/_ref/liblm_ref.so.  Those three functions decide everything about an LM run: the initial damping
+// definitions of OptimizationAlgorithmLevenberg::solve, ::computeLambdaInit and ::computeScale (and OptimizationAlgorithmGaussNewton::solve from
+// core/optimization_algorithm_gauss_newton.cpp) exactly as they stand into temporary files (G2O_LM_BODIES, G2O_GN_BODIES), compiled here into
+// oracle/_ref/liblm_ref.so.  Those three functions decide everything about an LM run: the initial damping
 // (tau * max diagonal), the trial loop with push / pop / discardTop, the gain ratio and its scale, the damping schedule, the termination.
 // What they call is provided here, on top of oracle/pgo_oracle.cpp (included below, so this library is a second, independent copy of the oracle
 // whose optimiser is g2o's code): the members and constructor values of optimization_algorithm_levenberg.{h,cpp:38-52}, a Solver and a
@@ -113,7 +114,17 @@ class OptimizationAlgorithmLevenberg : public OptimizationAlgorithm {
   Property<int> _maxTrials;
 };
 
+// OptimizationAlgorithmGaussNewton (optimization_algorithm_gauss_newton.{h,cpp}): solve() taken the same way
+class OptimizationAlgorithmGaussNewton : public OptimizationAlgorithm {
+ public:
+  explicit OptimizationAlgorithmGaussNewton(Solver& s) : _solver(s) {}
+  SolverResult solve(int iteration, bool online = false);
+  SparseOptimizer* _optimizer = nullptr;
+  Solver& _solver;
+};
+
 #include G2O_LM_BODIES
+#include G2O_GN_BODIES
 
 }  // namespace g2o
 
@@ -153,6 +164,41 @@ int gref_lm_optimize(void* h, int max_iters, int solver_kind, double* stats, dou
   }
   compute_errors(g);
   if (stats) { stats[0] = chi2_before; stats[1] = plain_chi2(g); stats[2] = alg.currentLambda(); stats[3] = total_trials; stats[4] = robust_chi2(g); }
+  if (result == g2o::OptimizationAlgorithm::Fail) return 0;
+  return cjIterations;
+}
+
+// The same outer loop around g2o's own OptimizationAlgorithmGaussNewton::solve; trace3: (chi2 after the iteration, 0, 1)
+int gref_gn_optimize(void* h, int max_iters, int solver_kind, double* stats, double* trace3, int trace_cap, int* n_trace) {
+  PGO& g = *(PGO*)h;
+  *n_trace = 0;
+  if (g.edges.empty()) return -1;
+  build_structure(g);
+  if (g.nfree == 0) return -1;
+  g.pcg_residual = -1.0;
+  compute_errors(g);
+  const double chi2_before = plain_chi2(g);
+  g2o::SparseOptimizer opt;
+  opt.attach(&g);
+  g2o::Solver solver;
+  solver.g = &g; solver.opt = &opt; solver.kind = solver_kind;
+  g2o::OptimizationAlgorithmGaussNewton alg(solver);
+  alg._optimizer = &opt;
+  int cjIterations = 0;
+  bool ok = true;
+  g2o::OptimizationAlgorithm::SolverResult result = g2o::OptimizationAlgorithm::OK;
+  for (int i = 0; i < max_iters && !opt.terminate() && ok; i++) {
+    result = alg.solve(i, false);
+    ok = (result == g2o::OptimizationAlgorithm::OK);
+    if (*n_trace < trace_cap) {
+      compute_errors(g);
+      trace3[*n_trace * 3] = robust_chi2(g); trace3[*n_trace * 3 + 1] = 0; trace3[*n_trace * 3 + 2] = 1;
+      (*n_trace)++;
+    }
+    ++cjIterations;
+  }
+  compute_errors(g);
+  if (stats) { stats[0] = chi2_before; stats[1] = plain_chi2(g); stats[2] = 0; stats[3] = cjIterations; stats[4] = robust_chi2(g); }
   if (result == g2o::OptimizationAlgorithm::Fail) return 0;
   return cjIterations;
 }

@@ -7,10 +7,10 @@
 // reference's own 3rdtools/g2o-a48ff8c.zip at build time and compiled against interface stand-ins (oracle/build_ref.sh, oracle/ref_stubs/,
 // oracle/g2o_ref_harness.cpp, oracle/lm_ref_harness.cpp, oracle/prior_ref_api.cpp, oracle/dquat_ref_api.cpp) as the CHECKERS of this file:
 //   compute_dq_dR, computeEdgeSE3Gradient, the MQT mappings (EdgeSE3 error, both Jacobians, oplus), RobustKernelHuber::robustify   bit for bit
-//   OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale over this file's building blocks                       bit for bit
+//   OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale, OptimizationAlgorithmGaussNewton::solve over this file's blocks  bit for bit
 //   BaseBinaryEdge / BaseUnaryEdge::constructQuadraticForm (1e-13: another association of the products), ::linearizeOplus (numeric)
 //   the reference's own edge_se3_prior{xy,xyz,quat,vec}.hpp and edge_se3_plane.hpp (with g2o's plane3d.h), CSparse
-// (tests/test_oracle_pgo.py).  Not pinned that way: BlockSolver's block bookkeeping, the Gauss-Newton loop, PCG, Eigen's rounding.  The older
+// (tests/test_oracle_pgo.py).  Not pinned that way: BlockSolver's block bookkeeping, PCG, Eigen's rounding.  The older
 // pins remain: (i) g2o's own property test restated in tests/ (analytic vs numeric EdgeSE3 Jacobian, test_slam3d_jacobian.cpp:109-140),
 // (ii) closed-form small graphs, (iii) CSparse cross-checked against a dense Cholesky.
 //

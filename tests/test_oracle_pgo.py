@@ -405,8 +405,8 @@ def test_edge_se3_math_against_g2o_own_code():
 
 def test_lm_control_flow_against_g2o_own_code():
     """g2o's own OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale (taken from the reference's g2o zip at build time,
-    oracle/lm_ref_harness.cpp) driving the restatement's building blocks, against the restated loop of oracle/pgo_oracle.cpp: iteration
-    counts, the per-iteration chi2 / lambda / trial counts and the optimised poses identical - on the sphere with Huber kernels (dense and
+    oracle/lm_ref_harness.cpp) driving the restatement's building blocks, against the restated loops of oracle/pgo_oracle.cpp (Levenberg-Marquardt and, at the end, g2o's
+    OptimizationAlgorithmGaussNewton::solve against the restated Gauss-Newton): iteration counts, the per-iteration chi2 / lambda / trial counts and the optimised poses identical - on the sphere with Huber kernels (dense and
     CSparse solves), with unary priors and the floor constraint, with a fixed vertex, and from a start far enough that steps are rejected."""
     import ctypes
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -473,6 +473,22 @@ def test_lm_control_flow_against_g2o_own_code():
             assert np.array_equal(out, o.poses()), name
             rejected += int((tr[:, 2] > 1).sum())
     assert rejected > 0                                      # the trial loop (pop, lambda *= ni) was exercised
+    # Gauss-Newton: g2o's own OptimizationAlgorithmGaussNewton::solve in the same outer loop (vertex 0 fixed, like GraphSLAM's gn_var solvers need)
+    G.gref_gn_optimize.restype = i32; G.gref_gn_optimize.argtypes = [vp, i32, i32, vp, vp, i32, vp]
+    for solver in solvers[-1:]:
+        o = P.OraclePGO()
+        o.set_graph(g1["poses7"], g1["ij"], g1["meas7"], g1["info21"], g1["huber"], fixed0)
+        r = o.optimize(8, P.ALG_GN, solver)
+        h = G.opgo_create()
+        c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+        p_, e_, m_, i_, hb_, fx_ = c(g1["poses7"]), c(g1["ij"], np.int32), c(g1["meas7"]), c(g1["info21"]), c(g1["huber"]), c(fixed0, np.uint8)
+        G.opgo_set_graph_typed(h, len(p_), p_.ctypes.data, fx_.ctypes.data, len(e_), e_.ctypes.data, m_.ctypes.data, i_.ctypes.data, hb_.ctypes.data, None)
+        st, tr, n = np.zeros(5), np.zeros((9, 3)), ctypes.c_int(0)
+        it = G.gref_gn_optimize(h, 8, solver, st.ctypes.data, tr.ctypes.data, 9, ctypes.byref(n))
+        out = np.zeros((len(p_), 7))
+        G.opgo_get_poses(h, out.ctypes.data)
+        G.opgo_destroy(h)
+        assert it == r["iterations"] == 8 and np.array_equal(tr[:n.value, 0], r["trace"][:, 0]) and np.array_equal(out, o.poses())
 
 
 def test_prior_edges_against_the_reference_own_classes():
