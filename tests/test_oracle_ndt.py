@@ -250,6 +250,71 @@ def test_information_matrix_against_the_reference_source(small_pair):
         assert np.array_equal(got, want), (prm, got.diagonal(), want.diagonal())
 
 
+def test_eigen_stand_in_against_numpy():
+    """oracle/ref_stubs/eigen_min.h - the interface stand-in the reference's own code is compiled against - does what the Eigen operations of the
+    same name do: small-matrix algebra, quaternion <-> matrix, rotation of a vector, angle-axis products, isometry product and inverse."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(HERE)
+    so = os.path.join(root, "oracle", "_ref", "libeigen_min_selftest.so")
+    if not os.path.exists(so):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=gnu++17", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(root, "oracle", "ref_stubs"), "-o", so,
+                               os.path.join(root, "oracle", "ref_stubs", "selftest_api.cpp")])
+    E = ctypes.CDLL(so)
+    vp, f64 = ctypes.c_void_p, ctypes.c_double
+    E.est_matrix3.restype = None; E.est_matrix3.argtypes = [vp] * 5
+    E.est_quaternion.restype = None; E.est_quaternion.argtypes = [vp, vp, vp, f64, f64, vp]
+    E.est_isometry.restype = None; E.est_isometry.argtypes = [vp] * 3
+    rng = np.random.default_rng(61)
+
+    def rot(q):
+        w, x, y, z = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1:] @ b[1:], *(a[0] * b[1:] + b[0] * a[1:] + np.cross(a[1:], b[1:]))])
+
+    for k in range(50):
+        A, B = rng.normal(size=(3, 3)) + 2 * np.eye(3), rng.normal(size=(3, 3))
+        v, w = rng.normal(size=3), rng.normal(size=3)
+        out = np.zeros(44)
+        E.est_matrix3(np.ascontiguousarray(A).ctypes.data, np.ascontiguousarray(B).ctypes.data, v.ctypes.data, w.ctypes.data, out.ctypes.data)
+        np.testing.assert_allclose(out[0:9].reshape(3, 3), A @ B, atol=1e-14)
+        np.testing.assert_allclose(out[9:18].reshape(3, 3), A.T @ B, atol=1e-14)
+        np.testing.assert_allclose(out[18:27].reshape(3, 3), np.linalg.inv(A), atol=1e-12)
+        np.testing.assert_allclose(out[27:30], A @ v, atol=1e-14)
+        np.testing.assert_allclose([out[30], out[34]], [v @ w, np.linalg.norm(v)], atol=1e-14)
+        np.testing.assert_allclose(out[31:34], np.cross(v, w), atol=1e-14)
+        np.testing.assert_allclose(out[35:44].reshape(3, 3), np.outer(v, w), atol=1e-14)
+        q, p = rng.normal(size=4), rng.normal(size=4)
+        q /= np.linalg.norm(q); p /= np.linalg.norm(p)
+        if k % 3 == 0:
+            q[0] = abs(q[0]) * 0.01; q /= np.linalg.norm(q)                  # trace of the rotation below zero: the other branches of the conversion
+        a, b = rng.uniform(-3, 3), rng.uniform(-1.5, 1.5)
+        out = np.zeros(29)
+        E.est_quaternion(q.ctypes.data, p.ctypes.data, v.ctypes.data, a, b, out.ctypes.data)
+        R = rot(q)
+        np.testing.assert_allclose(out[0:9].reshape(3, 3), R, atol=1e-14)
+        back = out[9:13]
+        assert min(np.abs(back - q).max(), np.abs(back + q).max()) < 1e-12     # the matrix determines the quaternion up to sign
+        np.testing.assert_allclose(out[13:16], R @ v, atol=1e-13)
+        np.testing.assert_allclose(out[16:20], qmul(q, p), atol=1e-14)
+        Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        np.testing.assert_allclose(out[20:29].reshape(3, 3), Rz @ Ry, atol=1e-14)
+        Ta, Tb = np.eye(4), np.eye(4)
+        Ta[:3, :3], Ta[:3, 3] = rot(q), rng.normal(0, 5, 3)
+        Tb[:3, :3], Tb[:3, 3] = rot(p), rng.normal(0, 5, 3)
+        out = np.zeros(44)
+        E.est_isometry(np.ascontiguousarray(Ta).ctypes.data, np.ascontiguousarray(Tb).ctypes.data, out.ctypes.data)
+        np.testing.assert_allclose(out[0:16].reshape(4, 4), Ta @ Tb, atol=1e-13)
+        np.testing.assert_allclose(out[16:32].reshape(4, 4), np.linalg.inv(Ta), atol=1e-13)
+        np.testing.assert_allclose(out[32:35], Ta[:3, 3], atol=0)
+        np.testing.assert_allclose(out[35:44].reshape(3, 3), Ta[:3, :3], atol=0)
+
+
 def test_log_of_float_guess_matches_matrix():
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = 1.5                                          # the reference's first-frame guess (scan_matching_odom_nodelet.cpp:199-200)
