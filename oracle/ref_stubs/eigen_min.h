@@ -1,14 +1,18 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
 //
-// A stand-in for the few Eigen 3 operations that Sophus a621ff2's so3.cpp and se3.cpp use, so that those two files — the reference's
-// own Lie-group code, vendored in /root/reference/3rdtools/Sophus-a621ff2-ubuntu18.04.zip — can be compiled in this image, which has no
-// Eigen (oracle/build_ref.sh -> oracle/_ref/libsophus_ref.so).  The compiled library is the checker of the restatement in oracle/ose3.h:
-// it pins Sophus' formulas, series coefficients, thresholds, branches and normalisation points.  It does NOT pin Eigen's own rounding: the
-// quaternion and small-matrix kernels below are written here (Eigen 3.3 Geometry/Quaternion.h semantics, scalar evaluation order) and share
-// those choices with ose3.h, so an agreement to the last bit says "same Sophus", not "same Eigen".
+// A stand-in for the Eigen 3 operations that the reference's own code uses on the paths this repository restates, so that this code can be
+// compiled in an image that has no Eigen (oracle/build_ref.sh -> oracle/_ref/*.so): Sophus a621ff2's so3.cpp / se3.cpp, the member functions of
+// the NDT registration classes and of the voxel grids, information_matrix_calculator.cpp, the prior / plane edges, and g2o's slam3d edge
+// math, Huber kernel, quadratic form and numeric Jacobians.  The compiled libraries are the checkers of the restatements in oracle/: they
+// pin the reference's formulas, constants, thresholds, branches, index conventions and control flow.  They do NOT pin Eigen's own rounding:
+// the kernels below are written here (Eigen 3.3 semantics; evaluation orders as oracle/ndt_oracle.cpp and oracle/pgo_oracle.cpp assume them,
+// see DotRule) and the two iterative solvers (3 x 3 eigen-decomposition, 6 x 6 SVD solve) are those of oracle/olin.h.  So an agreement to
+// the last bit says "same reference code", not "same Eigen".  tests/test_oracle_ndt.py::test_eigen_stand_in_against_numpy holds the semantics
+// of this header against numpy on its own.
 //
-// Only what so3.cpp / se3.cpp touch is provided: fixed-size double matrices with eager arithmetic, the comma initialiser, fixed-size
-// block / corner / head / tail views, transpose and stream output (for the headers' inline printers), and Quaternion.
+// Only what those sources touch is provided: fixed-size matrices with eager arithmetic, the comma initialiser, block / corner / head / tail /
+// column views, transposes, Map, Quaternion, AngleAxis, Isometry3, and the little of VectorXf / MatrixXi / MatrixXd the voxel code and the
+// information matrix use.
 #pragma once
 #include <cassert>
 #include <cmath>
