@@ -156,11 +156,14 @@ import sys, zipfile
 z = zipfile.ZipFile(sys.argv[1])
 z.extract("g2o/g2o/core/optimization_algorithm_levenberg.cpp", sys.argv[2])
 z.extract("g2o/g2o/core/optimization_algorithm_gauss_newton.cpp", sys.argv[2])
+z.extract("g2o/g2o/solvers/pcg/linear_solver_pcg.hpp", sys.argv[2])
 PY
+  python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/solvers/pcg/linear_solver_pcg.hpp" "$TMP/g2o_pcg.inc" "LinearSolverPCG<MatrixType>" solve multDiag mult
   python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/optimization_algorithm_gauss_newton.cpp" "$TMP/g2o_gn.inc" "=OptimizationAlgorithmGaussNewton" solve
   python3 "$HERE/extract_ref_functions.py" "$TMP/g2o/g2o/core/optimization_algorithm_levenberg.cpp" "$TMP/g2o_lm.inc" "=OptimizationAlgorithmLevenberg" \
       solve computeLambdaInit computeScale
-  /usr/bin/g++ -O3 -fopenmp -msse4.2 -ffp-contract=off -fPIC -std=c++17 -shared -DG2O_LM_BODIES="\"$TMP/g2o_lm.inc\"" -DG2O_GN_BODIES="\"$TMP/g2o_gn.inc\"" -I"$HERE" -o "$OUT/liblm_ref.so" \
+  /usr/bin/g++ -O3 -fopenmp -msse4.2 -ffp-contract=off -fPIC -std=gnu++17 -shared -DG2O_LM_BODIES="\"$TMP/g2o_lm.inc\"" -DG2O_GN_BODIES="\"$TMP/g2o_gn.inc\"" \
+      -DG2O_PCG_BODIES="\"$TMP/g2o_pcg.inc\"" -I"$HERE" -I"$HERE/ref_stubs" -o "$OUT/liblm_ref.so" \
       "$HERE/lm_ref_harness.cpp" -ldl
   echo "built $OUT/liblm_ref.so"
 fi

@@ -10,7 +10,8 @@
 //   OptimizationAlgorithmLevenberg::solve / computeLambdaInit / computeScale, OptimizationAlgorithmGaussNewton::solve over this file's blocks  bit for bit
 //   BaseBinaryEdge / BaseUnaryEdge::constructQuadraticForm (1e-13: another association of the products), ::linearizeOplus (numeric)
 //   the reference's own edge_se3_prior{xy,xyz,quat,vec}.hpp and edge_se3_plane.hpp (with g2o's plane3d.h), CSparse
-// (tests/test_oracle_pgo.py).  Not pinned that way: BlockSolver's block bookkeeping, PCG, Eigen's rounding.  The older
+// (tests/test_oracle_pgo.py).  LinearSolverPCG::solve / multDiag / mult: same
+// iteration counts and solutions.  Not pinned that way: BlockSolver's block bookkeeping, Eigen's rounding.  The older
 // pins remain: (i) g2o's own property test restated in tests/ (analytic vs numeric EdgeSE3 Jacobian, test_slam3d_jacobian.cpp:109-140),
 // (ii) closed-form small graphs, (iii) CSparse cross-checked against a dense Cholesky.
 //

@@ -187,6 +187,7 @@ class Matrix {
   S coeff(int i) const { return d_[i]; }
   int rows() const { return R; }
   int cols() const { return C; }
+  enum { RowsAtCompileTime = R, ColsAtCompileTime = C };
 
   S& operator()(int r, int c) { assert(r >= 0 && r < R && c >= 0 && c < C); return d_[r * C + c]; }
   const S& operator()(int r, int c) const { assert(r >= 0 && r < R && c >= 0 && c < C); return d_[r * C + c]; }

@@ -473,6 +473,30 @@ def test_lm_control_flow_against_g2o_own_code():
             assert np.array_equal(out, o.poses()), name
             rejected += int((tr[:, 2] > 1).sum())
     assert rejected > 0                                      # the trial loop (pop, lambda *= ni) was exercised
+    # g2o's own LinearSolverPCG::solve (solvers/pcg/linear_solver_pcg.hpp, block-Jacobi preconditioner, 1e-6 relative tolerance) on the damped
+    # system of the graph's current linearisation, against the restated solve_pcg: same iteration count, same solution
+    G.gref_pcg_solve.restype = i32; G.gref_pcg_solve.argtypes = [vp, ctypes.c_double, vp, vp]
+    for name, poses, ij, meas, info, hub, fixed, etype, floor in cases[:2] + cases[3:]:
+        for lam in (0.0 if fixed is not None else 1e-3, 10.0):
+            o = P.OraclePGO()
+            o.set_graph(poses, ij, meas, info, hub, fixed, etype, floor)
+            o.linearize()
+            ok, x_o, it_o = o.solve(lam, P.SOLVER_PCG)
+            h = G.opgo_create()
+            c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+            p_, e_, m_, i_ = c(poses), c(ij, np.int32), c(meas), c(info)
+            hb_ = c(hub) if hub is not None else None
+            fx_ = c(fixed, np.uint8) if fixed is not None else None
+            ty_ = c(etype, np.int32) if etype is not None else None
+            if floor is not None:
+                G.opgo_set_floor_plane(h, c(floor).ctypes.data)
+            G.opgo_set_graph_typed(h, len(p_), p_.ctypes.data, fx_.ctypes.data if fx_ is not None else None, len(e_), e_.ctypes.data, m_.ctypes.data, i_.ctypes.data,
+                                   hb_.ctypes.data if hb_ is not None else None, ty_.ctypes.data if ty_ is not None else None)
+            x_g, it_g = np.zeros_like(x_o), ctypes.c_int(0)
+            okg = G.gref_pcg_solve(h, lam, x_g.ctypes.data, ctypes.byref(it_g))
+            G.opgo_destroy(h)
+            assert ok and okg and it_g.value == it_o > 3, (name, lam, it_g.value, it_o)
+            assert np.array_equal(x_g, x_o), (name, lam, np.abs(x_g - x_o).max())
     # Gauss-Newton: g2o's own OptimizationAlgorithmGaussNewton::solve in the same outer loop (vertex 0 fixed, like GraphSLAM's gn_var solvers need)
     G.gref_gn_optimize.restype = i32; G.gref_gn_optimize.argtypes = [vp, i32, i32, vp, vp, i32, vp]
     for solver in solvers[-1:]:
